@@ -1,0 +1,73 @@
+"""ctypes binding of libversband_sm100.so — the C-ABI declared in include/versband.h.
+
+The library is the product path: if it is missing or the device is not sm_100 we raise; there
+is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libversband_sm100.so"
+
+c_i32, c_i64, c_f32, c_ptr = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+
+
+class GemmArgs(C.Structure):
+    """Mirror of `struct vb_gemm_args` (include/versband.h)."""
+
+    _fields_ = [
+        ("a", c_ptr), ("a_dims", c_i64 * 4), ("a_strides", c_i64 * 4),
+        ("b", c_ptr), ("b_dims", c_i64 * 3), ("b_strides", c_i64 * 3),
+        ("M", c_i32), ("N", c_i32), ("K", c_i32), ("G1", c_i32), ("G2", c_i32),
+        ("kpt", c_i32), ("dil", c_i32), ("pad", c_i32),
+        ("a_c2_g1", c_i32), ("a_c2_g2", c_i32), ("a_c3_g1", c_i32), ("a_c3_g2", c_i32),
+        ("b_c2_g1", c_i32), ("b_c2_g2", c_i32), ("b_c2_tile", c_i32),
+        ("bn", c_i32),
+        ("tile_group", c_ptr), ("m_tiles_used", c_ptr),
+        ("mode", c_i32), ("alpha", c_f32), ("swiglu", c_i32),
+        ("bias", c_ptr), ("bias_g1", c_i64), ("bias_tile", c_i64),
+        ("act", c_i32), ("act_slope", c_f32),
+        ("row_scale", c_ptr), ("gate", c_ptr), ("gate_rows", c_i32), ("gate_ld", c_i64),
+        ("row_map", c_ptr),
+        ("row_mul", c_i32), ("row_off", c_i32), ("row_off_g1", c_i32), ("rows_out", c_i32),
+        ("residual", c_ptr), ("accumulate", c_i32),
+        ("out_f32", c_ptr), ("out_ld", c_i64), ("out_g1", c_i64), ("out_g2", c_i64),
+        ("out_bf16", c_ptr), ("outb_ld", c_i64), ("outb_g1", c_i64), ("outb_g2", c_i64),
+        ("act_out", c_i32), ("act_out_slope", c_f32), ("out_scale", c_f32),
+        ("rope_cs", c_ptr), ("T", c_i32), ("heads", c_i32), ("head_dim", c_i32), ("Tp", c_i32),
+        ("q_out", c_ptr), ("k_out", c_ptr), ("vt_out", c_ptr),
+    ]
+
+
+class VersbandError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the shared library once; fail loudly if it was not built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise VersbandError(
+                f"{LIB_PATH} not found — run `python -m versband_b200.build` (or "
+                "__graft_entry__.build()); versband_b200 has no fallback path")
+        _lib = C.CDLL(str(LIB_PATH))
+        _lib.vb_last_error.restype = C.c_char_p
+        _lib.vb_launch_count.restype = C.c_longlong
+        _lib.vb_gemm.argtypes = [C.POINTER(GemmArgs), c_ptr]
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().vb_last_error().decode()
+        raise VersbandError(f"{what} failed (status {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().vb_launch_count())

@@ -1,0 +1,57 @@
+// Library-level entry points: version, error string, device check, launch counter.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include "vb_internal.h"
+
+namespace vb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+tensor_map_encode_fn get_tensor_map_encoder() {
+  static tensor_map_encode_fn fn = []() -> tensor_map_encode_fn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<tensor_map_encode_fn>(p);
+  }();
+  return fn;
+}
+
+}  // namespace vb
+
+extern "C" int vb_version(void) { return VB_ABI_VERSION; }
+extern "C" const char* vb_last_error(void) { return vb::g_err; }
+extern "C" long long vb_launch_count(void) { return vb::g_launches.load(); }
+
+extern "C" int vb_check_device(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return vb::set_error(VB_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10)
+    return vb::set_error(VB_ERR_ARCH, "versband_b200 needs an sm_100 (B200) device, found sm_%d%d", major, minor);
+  return VB_OK;
+}
+
+// ABI self-check used by the host binding: sizeof of the public argument structs.
+extern "C" int vb_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(vb_gemm_args);
+    default: return -1;
+  }
+}

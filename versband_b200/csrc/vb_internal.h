@@ -1,0 +1,31 @@
+// Internal helpers shared by the translation units of libversband_sm100.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "../../include/versband.h"
+
+namespace vb {
+
+// printf-style: records the thread-local error string and returns `code`.
+int set_error(int code, const char* fmt, ...);
+// Bumps the process-wide kernel-launch counter (vb_launch_count()).
+void count_launch();
+
+typedef CUresult (*tensor_map_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                         const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                         const cuuint32_t*, CUtensorMapInterleave,
+                                         CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                         CUtensorMapFloatOOBfill);
+// Resolved once through cudaGetDriverEntryPoint (no link-time libcuda dependency).
+tensor_map_encode_fn get_tensor_map_encoder();
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
+  count_launch();
+  return VB_OK;
+}
+
+}  // namespace vb
