@@ -98,9 +98,9 @@ typedef struct vb_gemm_args {
   int32_t act;
   float act_slope; /* v = act(v) */
   const float* row_scale; /* v *= row_scale[m]  (indexed by tile row m, before row mapping) */
-  const float* gate;      /* v *= gate[(m / gate_rows) * gate_ld + n] */
+  const float* gate;      /* v *= gate[(m / gate_rows) * gate_ld + g1 * gate_g1 + n] */
   int32_t gate_rows;
-  int64_t gate_ld;
+  int64_t gate_ld, gate_g1;
   /* output row: orow = row_map ? row_map[m] : m*row_mul + row_off + g1*row_off_g1;
    * rows with orow < 0 or orow >= rows_out are dropped */
   const int32_t* row_map;
@@ -115,8 +115,8 @@ typedef struct vb_gemm_args {
   int32_t act_out;
   float act_out_slope, out_scale;
 
-  /* ---- VB_EPI_QKV_ROPE: N = 3*heads*head_dim, rows m = b*T + t ----------------------- */
-  const float* rope_cs; /* [T][head_dim/2][2] (cos, sin), fp32 */
+  /* ---- VB_EPI_QKV_ROPE: N = 3*heads*head_dim, rows m = b*T + t; v = acc*alpha + bias ---- */
+  const float* rope_cs; /* [T][head_dim/2][2] (cos, sin), fp32; NULL = no rotation (VAE attn) */
   int32_t T, heads, head_dim, Tp;
   void* q_out;  /* bf16 [B, heads, T, head_dim] (rotated) */
   void* k_out;  /* bf16 [B, heads, T, head_dim] (rotated) */
@@ -124,6 +124,87 @@ typedef struct vb_gemm_args {
 } vb_gemm_args;
 
 int vb_gemm(const vb_gemm_args* args, void* stream);
+
+/* sizeof() of the public structs as compiled (ABI self-check for bindings): 0 = vb_gemm_args */
+int vb_sizeof(int which);
+/* number of kernels this library has launched in this process */
+long long vb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Row-wise ops of the DiT step (fp32 in, bf16 GEMM operand and/or fp32 out)
+ * ------------------------------------------------------------------------------------------ */
+/* kind 0: RMSNorm (flag_large_dit_moe.py:52-77); kind 1: LayerNorm (vocal2music_moe.py:274-276,
+ * flag_large_dit_moe.py:156). y = norm(x)[*w][+b]; then adaLN modulate y*(1+scale[bi])+shift[bi]
+ * (flag_large_dit_moe.py:80-81) with bi = row / rows_per_batch, vectors at stride mod_ld. */
+int vb_norm_mod(int kind, const float* x, const float* w, const float* b, const float* shift,
+                const float* scale, int64_t mod_ld, int rows_per_batch, float eps, void* out_bf16,
+                float* out_f32, int rows, int D, void* stream);
+/* P[r,:n] = softmax(S[r,:n]) as bf16, P[r,n:ldp] = 0 (SDPA softmax, flag_large_dit_moe.py:381;
+ * autoencoder1d.py:265) */
+int vb_softmax_rows(const float* S, int64_t lds, void* P_bf16, int64_t ldp, int64_t rows, int n,
+                    void* stream);
+/* attention against a short K/V (L <= 128 keys), fp32 K,V [B,L,*] with row pitch kv_ld; q bf16 with element
+ * strides (batch, token, head). out[b*T+t, h*hd+d] = base + tanh(gate[h]) * ctx (gate/base
+ * optional): text cross-attention flag_large_dit_moe.py:388-402, MoE MHA vocal2music_moe.py:119 */
+int vb_attn_smallkv(const void* q_bf16, int64_t q_sb, int64_t q_st, int64_t q_sh, const float* K,
+                    const float* V, int64_t kv_ld, int B, int T, int H, int hd, int L, float scale,
+                    const float* gate, const float* base, void* out_bf16, float* out_f32,
+                    void* stream);
+/* [cos(t f_i), sin(t f_i)] (flag_large_dit_moe.py:109-127); freqs = host table of f_i */
+int vb_timestep_embed(const int64_t* t, const float* freqs, float* out_f32, void* out_bf16, int B,
+                      int dim, void* stream);
+
+/* out[b,:] = mean_l x[b,l,:] (caption pooling, vocal2music_moe.py:410-412) */
+int vb_mean_tokens(const float* x, int B, int L, int D, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Band-MoE routing (vocal2music_moe.py:117-185)
+ * ------------------------------------------------------------------------------------------ */
+/* out[r,e] = bias[e] + <x[r,:], W[e,:]>, fp32 FMA, E <= 16 (gating networks :132,141-142) */
+int vb_linear_small(const float* x, int64_t ldx, const float* W, const float* bias, float* out,
+                    int rows, int D, int E, void* stream);
+/* Gumbel-softmax router: e0 [N,2], e1/e2 [N,E] are the Exp(1) draws the reference obtains from
+ * torch.empty_like(logits).exponential_() (:82). Emits hard top-1 indices and the combined
+ * weights scale_g[n] = ((1-p)+p) * group_mask_g[n]. */
+int vb_router(const float* cap_feat, const float* Wc, const float* bc, const float* ac_logits,
+              int ac_ld, const float* hl_logits, int hl_ld, const float* e0, const float* e1, const float* e2, float tau,
+              int N, int T, int D, int E, int32_t* idx_c, int32_t* idx_a, float* scale_c,
+              float* scale_a, float* cap_logits_out, void* stream);
+/* counting sort of the 2N (token, group) pairs into 128-row tiles per expert bucket */
+int vb_moe_sort(const int32_t* idx_c, const int32_t* idx_a, const float* scale_c,
+                const float* scale_a, int N, int E, int32_t* row_map, float* row_scale,
+                int32_t* tile_group, int32_t* m_tiles_used, int max_rows, float* lb_out,
+                void* stream);
+int vb_gather_rows(const void* x_bf16, const int32_t* row_map, const int32_t* m_tiles_used,
+                   int n_tokens, int D, void* out_bf16, int max_rows, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Elementwise / layout / GroupNorm / vocoder tail
+ * ------------------------------------------------------------------------------------------ */
+/* out = act(alpha*a + beta*b), rows x D fp32 in, each row written `rep` times (rep=2: nearest x2
+ * upsample, autoencoder1d.py:288) */
+int vb_ew(const float* a, const float* b, float alpha, float beta, int act, float slope,
+          float* out_f32, void* out_bf16, int64_t rows, int D, int rep, void* stream);
+/* [B,C,T] fp32 -> channels-last bf16 [B,T,Cp] (zero padded), times scale */
+int vb_nct_to_ntc(const float* in, float scale, void* out_bf16, int B, int C, int T, int Cp,
+                  void* stream);
+/* e_u == NULL: x[b,c,t] = e_c[b,t,c]; else CFG + Euler (cfm1_audio.py:160):
+ * x[b,c,t] += dt * (e_u + s*(e_c - e_u)) */
+int vb_ntc_to_nct(const float* e_c, const float* e_u, int64_t ld, float s, float dt, float* x, int B,
+                  int C, int T, void* stream);
+int vb_embed_rows(const int64_t* idx, const float* table, int V, int D, void* out_bf16, int64_t rows,
+                  void* stream);
+/* AvgPool1d(2) of one or two branches, summed (vocal2music_moe.py:343,349,392) */
+int vb_pool2_sum(const float* a, const float* b, int B, int Tin, int Tout, int D, void* out_bf16,
+                 float* out_f32, void* stream);
+/* GroupNorm over channels-last [B,T,C] (autoencoder1d.py:165-166) */
+int vb_gn_stats(const float* x, int B, int T, int C, int G, float eps, float* mean, float* rstd,
+                void* stream);
+int vb_gn_apply(const float* x, const float* mean, const float* rstd, const float* w,
+                const float* bias, int B, int T, int C, int G, int act, void* out_bf16, void* stream);
+/* HiFi-GAN conv_post + tanh (vocoder/hifigan/modules/hifigan.py:139-141); w is [k][C] fp32 */
+int vb_conv_post(const void* x_bf16, const float* w, float bias, int B, int T, int C, int k,
+                 float* wav, void* stream);
 
 #ifdef __cplusplus
 }

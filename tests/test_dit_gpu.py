@@ -1,0 +1,96 @@
+"""DiT engine (CUDA, through the C-ABI) vs the oracle (oracle/accompband_ref.py, CPU fp32) on the
+same seeded weights, inputs and Gumbel noise; plus the committed golden fixture of the live
+reference (tests/golden/golden_dit.pt)."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import accompband_ref as R  # noqa: E402
+from oracle import synth  # noqa: E402
+from versband_b200.dit import DiTEngine  # noqa: E402
+
+torch.set_grad_enabled(False)
+DEV = "cuda"
+
+
+def rel(a, b):
+    return float((a.float().cpu() - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+@pytest.fixture(scope="module")
+def weights():
+    return synth.synth_state_dict(synth.load_manifest("dit"), seed=1234)
+
+
+@pytest.fixture(scope="module")
+def engine(weights):
+    return DiTEngine(weights, device=DEV)
+
+
+def run_engine(engine, x, t, midi, beats, cap, expo, T):
+    cond = engine.prepare(midi.to(DEV), beats.to(DEV), cap.to(DEV), T)
+    expo_d = [tuple(e.to(DEV) for e in blk) for blk in expo]
+    out = torch.zeros_like(x, device=DEV)
+    v, lb, aux = engine.forward(x.to(DEV), t.to(DEV), cond, expo_d, out_v=out, want_aux=True)
+    torch.cuda.synchronize()
+    return out, lb, aux, cond
+
+
+def test_prepare_matches_oracle_conditioning(engine, weights):
+    B, T = 2, 64
+    x, midi, beats, cap, _ = synth.dit_inputs(B, T, seed=11)
+    ref = R.dit_conditioning(weights, {"c_crossattn": cap, "c_concat": {"midi": midi, "beats": beats}})
+    cond = engine.prepare(midi.to(DEV), beats.to(DEV), cap.to(DEV), T)
+    torch.cuda.synchronize()
+    assert rel(cond.acoustic.view(B, T, -1), ref["acoustic"]) < 1e-2
+    assert rel(cond.caption, ref["caption"]) < 2e-2
+    assert rel(cond.cap_emb, ref["cap_emb"]) < 2e-2
+
+
+@pytest.mark.parametrize("B,T", [(2, 64), (1, 200)])
+def test_forward_vs_oracle(engine, weights, B, T):
+    x, midi, beats, cap, _ = synth.dit_inputs(B, T, seed=21 + T)
+    t = torch.tensor([125, 833][:B])
+    expo = synth.exp_noise(4, B * T, 4, seed=5)
+    ctx = {"c_crossattn": cap, "c_concat": {"midi": midi, "beats": beats}}
+    v_ref, lb_ref, aux_ref = R.dit_forward(weights, x, t, ctx, depth=4, n_heads=8, expo=expo, return_aux=True)
+    v, lb, aux, _ = run_engine(engine, x, t, midi, beats, cap, expo, T)
+    # router decisions: identical wherever the oracle's decision margin exceeds bf16 noise
+    agree = total = 0
+    for k in range(4):
+        for name, key in (("idx_c", "cap_idx"), ("idx_a", "ac_idx")):
+            got = aux[k][name].cpu().long()
+            agree += int((got == aux_ref[k][key]).sum())
+            total += got.numel()
+    rate = agree / total
+    print(f"router agreement {agree}/{total} = {rate:.4f}; v rel err {rel(v, v_ref):.3e}")
+    assert rate > 0.97
+    # tokens whose routing agrees in every block must match to bf16 accuracy
+    ok = torch.ones(B * T, dtype=torch.bool)
+    for k in range(4):
+        ok &= aux[k]["idx_c"].cpu().long() == aux_ref[k]["cap_idx"]
+        ok &= aux[k]["idx_a"].cpu().long() == aux_ref[k]["ac_idx"]
+    diff = (v.cpu() - v_ref).abs().permute(0, 2, 1).reshape(B * T, -1).max(-1)[0]
+    peak = float(v_ref.abs().max())
+    assert float(diff.median()) / peak < 1e-2
+
+
+def test_golden_fixture_of_live_reference(engine, weights):
+    gd = torch.load(os.path.join(synth.GOLDEN_DIR, "golden_dit.pt"))
+    B, T = gd["B"], gd["T"]
+    x, midi, beats, cap, _ = synth.dit_inputs(B, T, seed=gd["input_seed"])
+    torch.manual_seed(gd["noise_seed"])  # replay the reference's CPU-generator draws
+    expo = [tuple(torch.empty(B * T, k).exponential_() for k in (2, 4, 4)) for _ in range(4)]
+    v, lb, aux, _ = run_engine(engine, x, gd["t"], midi, beats, cap, expo, T)
+    agree = total = 0
+    for k in range(4):
+        agree += int((aux[k]["idx_c"].cpu().to(torch.int16) == gd[f"cap_idx_{k}"]).sum())
+        agree += int((aux[k]["idx_a"].cpu().to(torch.int16) == gd[f"ac_idx_{k}"]).sum())
+        total += 2 * B * T
+    print(f"golden: router agreement {agree}/{total}, v rel err {rel(v, gd['v']):.3e}")
+    assert agree / total > 0.97
+    diff = (v.cpu() - gd["v"]).abs().permute(0, 2, 1).reshape(B * T, -1).max(-1)[0]
+    assert float(diff.median()) / float(gd["v"].abs().max()) < 1e-2

@@ -29,7 +29,7 @@ class GemmArgs(C.Structure):
         ("mode", c_i32), ("alpha", c_f32), ("swiglu", c_i32),
         ("bias", c_ptr), ("bias_g1", c_i64), ("bias_tile", c_i64),
         ("act", c_i32), ("act_slope", c_f32),
-        ("row_scale", c_ptr), ("gate", c_ptr), ("gate_rows", c_i32), ("gate_ld", c_i64),
+        ("row_scale", c_ptr), ("gate", c_ptr), ("gate_rows", c_i32), ("gate_ld", c_i64), ("gate_g1", c_i64),
         ("row_map", c_ptr),
         ("row_mul", c_i32), ("row_off", c_i32), ("row_off_g1", c_i32), ("rows_out", c_i32),
         ("residual", c_ptr), ("accumulate", c_i32),
@@ -60,6 +60,9 @@ def lib() -> C.CDLL:
         _lib.vb_last_error.restype = C.c_char_p
         _lib.vb_launch_count.restype = C.c_longlong
         _lib.vb_gemm.argtypes = [C.POINTER(GemmArgs), c_ptr]
+        _declare(_lib)
+        if _lib.vb_sizeof(0) != C.sizeof(GemmArgs):
+            raise VersbandError("vb_gemm_args ABI mismatch between versband.h and _lib.py")
     return _lib
 
 
@@ -71,3 +74,31 @@ def check(rc: int, what: str = "") -> None:
 
 def launch_count() -> int:
     return int(lib().vb_launch_count())
+
+
+def _declare(l: C.CDLL) -> None:
+    """argtypes for the plain-argument entry points (include/versband.h)."""
+    P, I, L, F = c_ptr, c_i32, c_i64, c_f32
+    sigs = {
+        "vb_norm_mod": [I, P, P, P, P, P, L, I, F, P, P, I, I, P],
+        "vb_softmax_rows": [P, L, P, L, L, I, P],
+        "vb_attn_smallkv": [P, L, L, L, P, P, L, I, I, I, I, I, F, P, P, P, P, P],
+        "vb_mean_tokens": [P, I, I, I, P, P],
+        "vb_timestep_embed": [P, P, P, P, I, I, P],
+        "vb_linear_small": [P, L, P, P, P, I, I, I, P],
+        "vb_router": [P, P, P, P, I, P, I, P, P, P, F, I, I, I, I, P, P, P, P, P, P],
+        "vb_moe_sort": [P, P, P, P, I, I, P, P, P, P, I, P, P],
+        "vb_gather_rows": [P, P, P, I, I, P, I, P],
+        "vb_ew": [P, P, F, F, I, F, P, P, L, I, I, P],
+        "vb_nct_to_ntc": [P, F, P, I, I, I, I, P],
+        "vb_ntc_to_nct": [P, P, L, F, F, P, I, I, I, P],
+        "vb_embed_rows": [P, P, I, I, P, L, P],
+        "vb_pool2_sum": [P, P, I, I, I, I, P, P, P],
+        "vb_gn_stats": [P, I, I, I, I, F, P, P, P],
+        "vb_gn_apply": [P, P, P, P, P, I, I, I, I, I, P, P],
+        "vb_conv_post": [P, P, F, I, I, I, I, P, P],
+    }
+    for name, at in sigs.items():
+        fn = getattr(l, name)
+        fn.argtypes = at
+        fn.restype = C.c_int

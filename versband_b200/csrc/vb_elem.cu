@@ -1,0 +1,312 @@
+// Elementwise / layout / GroupNorm kernels (HBM-bound; coalesced, vectorised where aligned).
+#include "vb_internal.h"
+
+namespace vb {
+
+__device__ __forceinline__ float act_f(float v, int act, float slope) {
+  switch (act) {
+    case VB_ACT_SILU: return v / (1.f + __expf(-v));
+    case VB_ACT_LRELU: return v > 0.f ? v : v * slope;
+    case VB_ACT_GELU_ERF: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+    case VB_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+
+// out = act(alpha*a + beta*b); each input row is written `rep` times (nearest-neighbour x2
+// upsample of autoencoder1d.py:288 when rep == 2). Row length D % 4 == 0.
+__global__ void ew_kernel(const float* __restrict__ a, const float* __restrict__ b, float alpha,
+                          float beta, int act, float slope, float* __restrict__ out_f32,
+                          __nv_bfloat16* __restrict__ out_bf16, long long rows, int D, int rep) {
+  const long long nvec = rows * (D / 4);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (D / 4);
+    const int c = (int)(i - r * (D / 4)) * 4;
+    float4 v = *reinterpret_cast<const float4*>(a + r * D + c);
+    float y[4] = {v.x * alpha, v.y * alpha, v.z * alpha, v.w * alpha};
+    if (b) {
+      float4 w = *reinterpret_cast<const float4*>(b + r * D + c);
+      y[0] += beta * w.x; y[1] += beta * w.y; y[2] += beta * w.z; y[3] += beta * w.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] = act_f(y[j], act, slope);
+    for (int k = 0; k < rep; ++k) {
+      const long long o = (r * rep + k) * D + c;
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(y[0], y[1], y[2], y[3]);
+      if (out_bf16) {
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]);
+        __nv_bfloat162 p1 = __floats2bfloat162_rn(y[2], y[3]);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&p0);
+        u.y = *reinterpret_cast<uint32_t*>(&p1);
+        *reinterpret_cast<uint2*>(out_bf16 + o) = u;
+      }
+    }
+  }
+}
+
+// [B, C, T] fp32 -> [B, T, Cp] bf16 (channels-last, zero padded to Cp), value * scale.
+// 32x32 shared-memory transpose: coalesced on both sides.
+__global__ void nct_to_ntc_kernel(const float* __restrict__ in, float scale,
+                                  __nv_bfloat16* __restrict__ out, int C, int T, int Cp) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, t = t0 + threadIdx.x;
+    tile[j][threadIdx.x] = (c < C && t < T) ? in[((long long)b * C + c) * T + t] * scale : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int t = t0 + j, c = c0 + threadIdx.x;
+    if (t < T && c < Cp) out[((long long)b * T + t) * Cp + c] = __float2bfloat16(tile[threadIdx.x][j]);
+  }
+}
+
+// [B, T, ld] fp32 (first C columns) -> [B, C, T] fp32:  out = alpha*out_prev? no: plain transpose,
+// or the fused CFG + Euler update (cfm1_audio.py:160, torchdyn Euler):
+//   x[b,c,t] += dt * (e_u + s * (e_c - e_u))       when e_u != nullptr
+//   out[b,c,t] = e_c[b,t,c]                          otherwise
+__global__ void ntc_to_nct_kernel(const float* __restrict__ e_c, const float* __restrict__ e_u,
+                                  long long ld, float s, float dt, float* __restrict__ x, int C,
+                                  int T) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int t = t0 + j, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (t < T && c < C) {
+      const long long o = ((long long)b * T + t) * ld + c;
+      v = e_c[o];
+      if (e_u) { const float u = e_u[o]; v = u + s * (v - u); }
+    }
+    tile[j][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, t = t0 + threadIdx.x;
+    if (c < C && t < T) {
+      const long long o = ((long long)b * C + c) * T + t;
+      if (e_u) x[o] = x[o] + dt * tile[threadIdx.x][j];
+      else x[o] = tile[threadIdx.x][j];
+    }
+  }
+}
+
+// out[r, :] = table[idx[r], :] as bf16 (nn.Embedding, vocal2music_moe.py:336-337,388-389)
+__global__ void embed_rows_kernel(const long long* __restrict__ idx, const float* __restrict__ table,
+                                  int V, int D, __nv_bfloat16* __restrict__ out, long long rows) {
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  long long id = idx[r];
+  id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+  const float* src = table + id * D;
+  for (int d = lane * 2; d < D; d += 64) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(src[d], src[d + 1]);
+    *reinterpret_cast<__nv_bfloat162*>(out + r * D + d) = p;
+  }
+}
+
+// out[b, t, :] = 0.5*(a[b,2t]+a[b,2t+1]) + 0.5*(b[b,2t]+b[b,2t+1])  (AvgPool1d(2) of both stem
+// branches + their sum, vocal2music_moe.py:343,349,392); inputs already LeakyReLU'd.
+__global__ void pool2_sum_kernel(const float* __restrict__ a, const float* __restrict__ b2, int Tin,
+                                 int Tout, int D, __nv_bfloat16* __restrict__ out_bf16,
+                                 float* __restrict__ out_f32, int B) {
+  const long long n = (long long)B * Tout * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D);
+    const long long bt = i / D;
+    const int t = (int)(bt % Tout);
+    const int b = (int)(bt / Tout);
+    const long long base = ((long long)b * Tin + 2 * t) * D + d;
+    float v = (a[base] + a[base + D]) * 0.5f;
+    if (b2) v += (b2[base] + b2[base + D]) * 0.5f;
+    if (out_bf16) out_bf16[i] = __float2bfloat16(v);
+    if (out_f32) out_f32[i] = v;
+  }
+}
+
+// GroupNorm statistics over channels-last x[B, T, C]: per (b, group) mean and rstd
+// (autoencoder1d.py:165-166: 32 groups, eps 1e-6). fp64 accumulation.
+__global__ void gn_stats_kernel(const float* __restrict__ x, int T, int C, int G, float eps,
+                                float* __restrict__ mean, float* __restrict__ rstd) {
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int cpg = C / G;
+  const float* base = x + (long long)b * T * C + g * cpg;
+  double s = 0.0, ss = 0.0;
+  const int n = T * cpg;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int t = i / cpg, c = i - t * cpg;
+    const float v = base[(long long)t * C + c];
+    s += v;
+    ss += (double)v * v;
+  }
+  __shared__ double sh[2][32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh[0][warp] = s; sh[1][warp] = ss; }
+  __syncthreads();
+  if (warp == 0) {
+    s = lane < (blockDim.x >> 5) ? sh[0][lane] : 0.0;
+    ss = lane < (blockDim.x >> 5) ? sh[1][lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (lane == 0) {
+      const double m = s / n;
+      const double var = ss / n - m * m;
+      mean[b * G + g] = (float)m;
+      rstd[b * G + g] = (float)(1.0 / sqrt((var > 0 ? var : 0) + (double)eps));
+    }
+  }
+}
+
+// y = act((x - mean) * rstd * w + b) -> bf16 (A operand of the following conv GEMM)
+__global__ void gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                const float* __restrict__ rstd, const float* __restrict__ w,
+                                const float* __restrict__ bias, int T, int C, int G, int act,
+                                __nv_bfloat16* __restrict__ out, long long total_vec) {
+  const int cpg = C / G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i * 4;
+    const int c = (int)(e % C);
+    const int b = (int)(e / ((long long)T * C));
+    float4 v = *reinterpret_cast<const float4*>(x + e);
+    float y[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = (c + j) / cpg;
+      const float m = mean[b * G + g], r = rstd[b * G + g];
+      y[j] = act_f((y[j] - m) * r * w[c + j] + bias[c + j], act, 0.f);
+    }
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]);
+    __nv_bfloat162 p1 = __floats2bfloat162_rn(y[2], y[3]);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&p0);
+    u.y = *reinterpret_cast<uint32_t*>(&p1);
+    *reinterpret_cast<uint2*>(out + e) = u;
+  }
+}
+
+// HiFi-GAN conv_post (modules/hifigan.py:139-141): x is the already leaky-relu'd bf16
+// activation [B, T, C]; wav[b, t] = tanh(bias + sum_{j,c} w[j, c] * x[b, t + j - pad, c]).
+// One warp per 32 output samples: each lane owns one sample; weights in shared memory.
+__global__ void conv_post_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                 float bias, int T, int C, int k, float* __restrict__ wav) {
+  extern __shared__ float sw[];
+  for (int i = threadIdx.x; i < k * C; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const int pad = k / 2;
+  float acc = bias;
+  for (int j = 0; j < k; ++j) {
+    const int tt = t + j - pad;
+    if (tt < 0 || tt >= T) continue;
+    const uint4* row = reinterpret_cast<const uint4*>(x + ((long long)b * T + tt) * C);
+    for (int c8 = 0; c8 < C / 8; ++c8) {
+      const uint4 u = row[c8];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(h[q]);
+        acc = fmaf(f.x, sw[j * C + c8 * 8 + 2 * q], acc);
+        acc = fmaf(f.y, sw[j * C + c8 * 8 + 2 * q + 1], acc);
+      }
+    }
+  }
+  wav[(long long)b * T + t] = tanhf(acc);
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+static inline int grid_for(long long n, int threads) {
+  long long g = (n + threads - 1) / threads;
+  const long long cap = 148LL * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+extern "C" int vb_ew(const float* a, const float* b, float alpha, float beta, int act, float slope,
+                     float* out_f32, void* out_bf16, int64_t rows, int D, int rep, void* stream) {
+  if (!a || rows <= 0 || D <= 0 || D % 4 != 0 || rep < 1 || (!out_f32 && !out_bf16))
+    return set_error(VB_ERR_INVALID, "vb_ew: bad arguments (D %% 4 == 0)");
+  const long long nvec = rows * (D / 4);
+  ew_kernel<<<grid_for(nvec, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      a, b, alpha, beta, act, slope, out_f32, static_cast<__nv_bfloat16*>(out_bf16), rows, D, rep);
+  return check_launch("vb_ew");
+}
+
+extern "C" int vb_nct_to_ntc(const float* in, float scale, void* out_bf16, int B, int C, int T, int Cp,
+                             void* stream) {
+  if (!in || !out_bf16 || Cp < C) return set_error(VB_ERR_INVALID, "vb_nct_to_ntc: bad arguments");
+  dim3 grid((T + 31) / 32, (Cp + 31) / 32, B), block(32, 8);
+  nct_to_ntc_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, scale, static_cast<__nv_bfloat16*>(out_bf16), C, T, Cp);
+  return check_launch("vb_nct_to_ntc");
+}
+
+extern "C" int vb_ntc_to_nct(const float* e_c, const float* e_u, int64_t ld, float s, float dt,
+                             float* x, int B, int C, int T, void* stream) {
+  if (!e_c || !x) return set_error(VB_ERR_INVALID, "vb_ntc_to_nct: bad arguments");
+  dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  ntc_to_nct_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(e_c, e_u, ld, s, dt, x, C, T);
+  return check_launch("vb_ntc_to_nct");
+}
+
+extern "C" int vb_embed_rows(const int64_t* idx, const float* table, int V, int D, void* out_bf16,
+                             int64_t rows, void* stream) {
+  if (!idx || !table || !out_bf16 || D % 2) return set_error(VB_ERR_INVALID, "vb_embed_rows: bad arguments");
+  embed_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(idx), table, V, D, static_cast<__nv_bfloat16*>(out_bf16), rows);
+  return check_launch("vb_embed_rows");
+}
+
+extern "C" int vb_pool2_sum(const float* a, const float* b, int B, int Tin, int Tout, int D,
+                            void* out_bf16, float* out_f32, void* stream) {
+  if (!a || Tout * 2 > Tin) return set_error(VB_ERR_INVALID, "vb_pool2_sum: bad arguments");
+  const long long n = (long long)B * Tout * D;
+  pool2_sum_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      a, b, Tin, Tout, D, static_cast<__nv_bfloat16*>(out_bf16), out_f32, B);
+  return check_launch("vb_pool2_sum");
+}
+
+extern "C" int vb_gn_stats(const float* x, int B, int T, int C, int G, float eps, float* mean,
+                           float* rstd, void* stream) {
+  if (!x || !mean || !rstd || C % G) return set_error(VB_ERR_INVALID, "vb_gn_stats: bad arguments");
+  gn_stats_kernel<<<dim3(G, B), 512, 0, static_cast<cudaStream_t>(stream)>>>(x, T, C, G, eps, mean, rstd);
+  return check_launch("vb_gn_stats");
+}
+
+extern "C" int vb_gn_apply(const float* x, const float* mean, const float* rstd, const float* w,
+                           const float* bias, int B, int T, int C, int G, int act, void* out_bf16,
+                           void* stream) {
+  if (!x || !mean || !rstd || !w || !bias || !out_bf16 || C % 4 || C % G)
+    return set_error(VB_ERR_INVALID, "vb_gn_apply: bad arguments");
+  const long long nvec = (long long)B * T * C / 4;
+  gn_apply_kernel<<<grid_for(nvec, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, mean, rstd, w, bias, T, C, G, act, static_cast<__nv_bfloat16*>(out_bf16), nvec);
+  return check_launch("vb_gn_apply");
+}
+
+extern "C" int vb_conv_post(const void* x_bf16, const float* w, float bias, int B, int T, int C, int k,
+                            float* wav, void* stream) {
+  if (!x_bf16 || !w || !wav || C % 8) return set_error(VB_ERR_INVALID, "vb_conv_post: bad arguments");
+  dim3 grid((T + 127) / 128, B);
+  conv_post_kernel<<<grid, 128, k * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x_bf16), w, bias, T, C, k, wav);
+  return check_launch("vb_conv_post");
+}

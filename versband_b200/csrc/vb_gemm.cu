@@ -33,7 +33,7 @@ struct GemmKParams {
   const float* row_scale;
   const float* gate;
   int gate_rows;
-  long long gate_ld;
+  long long gate_ld, gate_g1;
   const int* row_map;
   int row_mul, row_off, row_off_g1, rows_out;
   const float* residual;
@@ -144,7 +144,7 @@ __device__ __forceinline__ void epilogue_generic(const GemmKParams& p, float (&v
     for (int j = 0; j < 32; ++j) v[j] *= rs;
   }
   if (p.gate) {
-    const float* gp = p.gate + (long long)(m / p.gate_rows) * p.gate_ld + n_base;
+    const float* gp = p.gate + (long long)(m / p.gate_rows) * p.gate_ld + g1 * p.gate_g1 + n_base;
     if (full) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] *= __ldg(gp + j);
@@ -230,15 +230,26 @@ __device__ __forceinline__ void epilogue_qkv(const GemmKParams& p, float (&v)[32
   const int d0 = rem - h * hd;
   const int b = m / T;
   const int t = m - b * T;
-  if (sec < 2) {
-    const float* cs = p.rope_cs + ((long long)t * (hd >> 1) + (d0 >> 1)) * 2;
-    float o[32];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float c = __ldg(cs + 2 * j), s = __ldg(cs + 2 * j + 1);
-      float x0 = v[2 * j], x1 = v[2 * j + 1];
-      o[2 * j] = x0 * c - x1 * s;
-      o[2 * j + 1] = x0 * s + x1 * c;
+  for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + n_base + j);
+  }
+  if (sec < 2) {
+    float o[32];
+    if (p.rope_cs) {
+      const float* cs = p.rope_cs + ((long long)t * (hd >> 1) + (d0 >> 1)) * 2;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float c = __ldg(cs + 2 * j), s = __ldg(cs + 2 * j + 1);
+        float x0 = v[2 * j], x1 = v[2 * j + 1];
+        o[2 * j] = x0 * c - x1 * s;
+        o[2 * j + 1] = x0 * s + x1 * c;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) o[j] = v[j];
     }
     __nv_bfloat16* dst = (sec == 0 ? p.q_out : p.k_out) +
                          (((long long)b * H + h) * T + t) * hd + d0;
@@ -477,7 +488,7 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
     else bn = (a->N >= 64 && tiles(32) > 4 * 148) ? 64 : 32;
   }
   if (a->mode == VB_EPI_QKV_ROPE) {
-    if (!a->rope_cs || !a->q_out || !a->k_out || !a->vt_out || a->head_dim % 32 != 0 ||
+    if (!a->q_out || !a->k_out || !a->vt_out || a->head_dim % 32 != 0 ||
         a->N != 3 * a->heads * a->head_dim || a->T <= 0 || a->M % a->T != 0)
       return set_error(VB_ERR_INVALID, "vb_gemm: bad QKV_ROPE arguments");
     if (bn == 96 && (a->head_dim % 96) != 0) bn = 64;
@@ -505,7 +516,7 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
   p.bias = a->bias; p.bias_g1 = a->bias_g1; p.bias_tile = a->bias_tile;
   p.act = a->act; p.act_slope = a->act_slope;
   p.row_scale = a->row_scale; p.gate = a->gate;
-  p.gate_rows = a->gate_rows > 0 ? a->gate_rows : 1; p.gate_ld = a->gate_ld;
+  p.gate_rows = a->gate_rows > 0 ? a->gate_rows : 1; p.gate_ld = a->gate_ld; p.gate_g1 = a->gate_g1;
   p.row_map = a->row_map;
   p.row_mul = a->row_mul; p.row_off = a->row_off; p.row_off_g1 = a->row_off_g1;
   p.rows_out = a->rows_out;

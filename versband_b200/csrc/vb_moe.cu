@@ -1,0 +1,263 @@
+// Band-MoE routing kernels (vocal2music_moe.py:117-185):
+//   vb_linear_small : fp32 row x [E<=8] gating logits (exact fp32 FMA dot products)
+//   vb_router       : Gumbel-softmax group gate (soft) + hard top-1 per routed group
+//   vb_moe_sort     : counting sort of (token, group) pairs by expert into 128-row tiles
+//   vb_gather_rows  : x_sorted[slot] = x[row_map[slot] % n_tokens]
+#include <math_constants.h>
+#include "vb_internal.h"
+
+namespace vb {
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// out[r, e] = bias[e] + sum_d x[r, d] * W[e, d]      (one warp per row, E <= 16)
+__global__ void linear_small_kernel(const float* __restrict__ x, long long ldx,
+                                    const float* __restrict__ W, const float* __restrict__ bias,
+                                    float* __restrict__ out, int rows, int D, int E) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float acc[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+  const float* xr = x + (long long)row * ldx;
+  for (int d = lane; d < D; d += 32) {
+    const float xv = xr[d];
+#pragma unroll
+    for (int e = 0; e < 16; ++e)
+      if (e < E) acc[e] = fmaf(xv, W[(long long)e * D + d], acc[e]);
+  }
+#pragma unroll
+  for (int e = 0; e < 16; ++e)
+    if (e < E) acc[e] = wsum(acc[e]);
+  if (lane == 0)
+    for (int e = 0; e < E; ++e) out[(long long)row * E + e] = acc[e] + (bias ? bias[e] : 0.f);
+}
+
+// One warp per token n (= b*T + t).
+//  group gate : p = softmax(hl_logits[b] - log(E0[n]))           (tau = 1, always soft)  :132-138
+//  expert gate: y = softmax((logits - log(E)) / tau); idx = argmax (first max); hard weight
+//               w = (1 - y[idx]) + y[idx]  (straight-through value)                       :81-93,150-151
+//  scale_c[n] = w_c * p[0], scale_a[n] = w_a * p[1]                                       :157-165
+template <int E>
+__global__ void router_kernel(const float* __restrict__ cap_feat, const float* __restrict__ Wc,
+                              const float* __restrict__ bc, const float* __restrict__ ac_logits,
+                              const float* __restrict__ hl_logits, int hl_ld, int ac_ld, const float* __restrict__ e0,
+                              const float* __restrict__ e1, const float* __restrict__ e2, float tau,
+                              int N, int T, int D, int* __restrict__ idx_c, int* __restrict__ idx_a,
+                              float* __restrict__ scale_c, float* __restrict__ scale_a,
+                              float* __restrict__ cap_logits_out) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float acc[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) acc[e] = 0.f;
+  const float* xr = cap_feat + (long long)n * D;
+  for (int d = lane; d < D; d += 32) {
+    const float xv = xr[d];
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = fmaf(xv, Wc[(long long)e * D + d], acc[e]);
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) acc[e] = wsum(acc[e]);
+  if (lane != 0) return;
+  const int b = n / T;
+  // group gate
+  const float g0 = hl_logits[b * hl_ld + 0] + (-logf(e0[(long long)n * 2 + 0]));
+  const float g1 = hl_logits[b * hl_ld + 1] + (-logf(e0[(long long)n * 2 + 1]));
+  const float gm = fmaxf(g0, g1);
+  const float x0 = expf(g0 - gm), x1 = expf(g1 - gm);
+  const float mask_c = x0 / (x0 + x1), mask_a = x1 / (x0 + x1);
+  auto hard = [&](const float* logit, const float* expo, int& idx, float& w) {
+    float z[E];
+    float m = -CUDART_INF_F;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      z[e] = (logit[e] + (-logf(expo[e]))) / tau;
+      m = fmaxf(m, z[e]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) { z[e] = expf(z[e] - m); s += z[e]; }
+    int best = 0;
+    float pb = z[0] / s;
+#pragma unroll
+    for (int e = 1; e < E; ++e) {
+      const float p = z[e] / s;
+      if (p > pb) { pb = p; best = e; }
+    }
+    idx = best;
+    w = (1.f - pb) + pb;
+  };
+  float lc[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    lc[e] = acc[e] + bc[e];
+    if (cap_logits_out) cap_logits_out[(long long)n * E + e] = lc[e];
+  }
+  int ic, ia;
+  float wc, wa;
+  hard(lc, e1 + (long long)n * E, ic, wc);
+  hard(ac_logits + (long long)n * ac_ld, e2 + (long long)n * E, ia, wa);
+  idx_c[n] = ic;
+  idx_a[n] = ia;
+  scale_c[n] = wc * mask_c;
+  scale_a[n] = wa * mask_a;
+}
+
+// Single CTA. Entries i in [0, 2N): group g = i / N (0 caption, 1 acoustic), token = i % N,
+// bucket = g*E + idx. Buckets are laid out back to back, each padded to a multiple of 128 rows.
+// Warp w (< 2E) owns bucket w: ordered ballot scan -> deterministic slots.
+// Also reduces the reference's load-balancing loss (vocal2music_moe.py:95-115) for this block.
+__global__ void moe_sort_kernel(const int* __restrict__ idx_c, const int* __restrict__ idx_a,
+                                const float* __restrict__ scale_c, const float* __restrict__ scale_a,
+                                int N, int E, int* __restrict__ row_map, float* __restrict__ row_scale,
+                                int* __restrict__ tile_group, int* __restrict__ m_tiles_used,
+                                int max_rows, float* __restrict__ lb_out) {
+  __shared__ int s_count[16];
+  __shared__ int s_start[17];
+  __shared__ float s_usage[16];
+  __shared__ float s_masksum;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = 2 * E;
+  if (threadIdx.x < 16) { s_count[threadIdx.x] = 0; s_usage[threadIdx.x] = 0.f; }
+  if (threadIdx.x == 0) s_masksum = 0.f;
+  __syncthreads();
+  // pass 1: counts + usage sums
+  if (warp < nb) {
+    const int g = warp / E, e = warp - g * E;
+    const int* idx = g ? idx_a : idx_c;
+    const float* sc = g ? scale_a : scale_c;
+    int cnt = 0;
+    float us = 0.f;
+    for (int n = lane; n < N; n += 32)
+      if (idx[n] == e) { cnt++; us += sc[n]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      us += __shfl_xor_sync(0xffffffffu, us, o);
+    }
+    if (lane == 0) { s_count[warp] = cnt; s_usage[warp] = us; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int k = 0; k < nb; ++k) {
+      s_start[k] = acc;
+      const int padded = (s_count[k] + 127) / 128 * 128;
+      for (int t = acc / 128; t < (acc + padded) / 128; ++t) tile_group[t] = k;
+      acc += padded;
+    }
+    s_start[nb] = acc;
+    *m_tiles_used = acc / 128;
+  }
+  __syncthreads();
+  // pass 2: ordered slot assignment
+  if (warp < nb) {
+    const int g = warp / E, e = warp - g * E;
+    const int* idx = g ? idx_a : idx_c;
+    const float* sc = g ? scale_a : scale_c;
+    int base = s_start[warp];
+    for (int n0 = 0; n0 < N; n0 += 32) {
+      const int n = n0 + lane;
+      const bool mine = (n < N) && (idx[n] == e);
+      const unsigned bal = __ballot_sync(0xffffffffu, mine);
+      if (mine) {
+        const int slot = base + __popc(bal & ((1u << lane) - 1));
+        row_map[slot] = g * N + n;
+        row_scale[slot] = sc[n];
+      }
+      base += __popc(bal);
+    }
+    for (int s = base + lane; s < s_start[warp + 1]; s += 32) { row_map[s] = -1; row_scale[s] = 0.f; }
+  }
+  // rows past the used tiles: mark invalid
+  for (int s = s_start[nb] + threadIdx.x; s < max_rows; s += blockDim.x) { row_map[s] = -1; row_scale[s] = 0.f; }
+  // load-balancing loss: usage_k / (E * (sum mask_c + sum mask_a)); in eval mode the masked hard
+  // probabilities sum, per token and group, to scale_g[n]; sum of masks = sum over tokens of
+  // (mask_c + mask_a) = N (softmax over two groups) up to rounding -> recomputed from usage.
+  if (lb_out && threadIdx.x == 0) {
+    float total = 0.f;  // sum of all expanded-mask entries = E * sum_n (mask_c + mask_a)
+    // hard weights are 1 (+-1ulp), so sum_n mask_g = sum_k usage_{g,k}
+    for (int k = 0; k < nb; ++k) total += s_usage[k];
+    total *= (float)E;
+    float loss = 0.f;
+    for (int k = 0; k < nb; ++k) {
+      const float u = s_usage[k] / (total + 1e-10f);
+      loss += u * logf(u + 1e-10f);
+    }
+    *lb_out = loss / (float)nb;
+  }
+}
+
+// x_sorted[slot, :] = x[row_map[slot] % n_tokens, :] (bf16 rows, 16-byte vectors); slot invalid -> zeros
+__global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ row_map,
+                                   const int* __restrict__ m_tiles_used, int n_tokens, int D,
+                                   __nv_bfloat16* __restrict__ out, int max_rows) {
+  const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (slot >= max_rows || slot >= *m_tiles_used * 128) return;
+  const int r = row_map[slot];
+  uint4* dst = reinterpret_cast<uint4*>(out + (long long)slot * D);
+  if (r < 0) {
+    for (int i = lane; i < D / 8; i += 32) dst[i] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const uint4* src = reinterpret_cast<const uint4*>(x + (long long)(r % n_tokens) * D);
+  for (int i = lane; i < D / 8; i += 32) dst[i] = src[i];
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" int vb_linear_small(const float* x, int64_t ldx, const float* W, const float* bias,
+                               float* out, int rows, int D, int E, void* stream) {
+  if (!x || !W || !out || rows <= 0 || E <= 0 || E > 16)
+    return set_error(VB_ERR_INVALID, "vb_linear_small: bad arguments (E <= 16)");
+  linear_small_kernel<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, W, bias,
+                                                                                     out, rows, D, E);
+  return check_launch("vb_linear_small");
+}
+
+extern "C" int vb_router(const float* cap_feat, const float* Wc, const float* bc,
+                         const float* ac_logits, int ac_ld, const float* hl_logits, int hl_ld,
+                         const float* e0, const float* e1, const float* e2, float tau, int N, int T, int D, int E,
+                         int32_t* idx_c, int32_t* idx_a, float* scale_c, float* scale_a,
+                         float* cap_logits_out, void* stream) {
+  if (!cap_feat || !Wc || !bc || !ac_logits || !hl_logits || !e0 || !e1 || !e2 || !idx_c || !idx_a ||
+      !scale_c || !scale_a || N <= 0 || T <= 0)
+    return set_error(VB_ERR_INVALID, "vb_router: null/invalid argument");
+  if (E != 4) return set_error(VB_ERR_INVALID, "vb_router: num_experts %d not instantiated (4)", E);
+  router_kernel<4><<<(N + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      cap_feat, Wc, bc, ac_logits, hl_logits, hl_ld, ac_ld, e0, e1, e2, tau, N, T, D, idx_c, idx_a, scale_c, scale_a,
+      cap_logits_out);
+  return check_launch("vb_router");
+}
+
+extern "C" int vb_moe_sort(const int32_t* idx_c, const int32_t* idx_a, const float* scale_c,
+                           const float* scale_a, int N, int E, int32_t* row_map, float* row_scale,
+                           int32_t* tile_group, int32_t* m_tiles_used, int max_rows, float* lb_out,
+                           void* stream) {
+  if (!idx_c || !idx_a || !row_map || !row_scale || !tile_group || !m_tiles_used || E <= 0 || E > 8)
+    return set_error(VB_ERR_INVALID, "vb_moe_sort: bad arguments");
+  if (max_rows < ((2 * N + 127) / 128 + 2 * E) * 128)
+    return set_error(VB_ERR_INVALID, "vb_moe_sort: max_rows %d too small for N=%d E=%d", max_rows, N, E);
+  moe_sort_kernel<<<1, 512, 0, static_cast<cudaStream_t>(stream)>>>(
+      idx_c, idx_a, scale_c, scale_a, N, E, row_map, row_scale, tile_group, m_tiles_used, max_rows, lb_out);
+  return check_launch("vb_moe_sort");
+}
+
+extern "C" int vb_gather_rows(const void* x, const int32_t* row_map, const int32_t* m_tiles_used,
+                              int n_tokens, int D, void* out, int max_rows, void* stream) {
+  if (!x || !row_map || !out || D % 8 != 0) return set_error(VB_ERR_INVALID, "vb_gather_rows: bad arguments");
+  gather_rows_kernel<<<(max_rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), row_map, m_tiles_used, n_tokens, D,
+      static_cast<__nv_bfloat16*>(out), max_rows);
+  return check_launch("vb_gather_rows");
+}

@@ -1,0 +1,336 @@
+"""AccompBand DiT on B200: weight packing, step-invariant conditioning cache and the per-ODE-step
+forward, expressed as a sequence of libversband_sm100 kernel launches (versband_b200.ops).
+
+Mirrors `TxtFlagLargeDiT.forward` (reference ldm/modules/diffusionmodules/vocal2music_moe.py:375-434)
+with the restructuring SURVEY.md §0.4/§0.8 shows to be value-equivalent:
+  * routed experts evaluated sparsely (hard top-1 ⇒ non-selected weights are exactly 0, :87-89),
+  * frequency experts restricted to their 192-channel band (:171-178),
+  * everything that depends only on the conditioning computed once per clip (`prepare`).
+All tensors live in HBM as: residual stream fp32 [N, D]; GEMM operands bf16; N = B*T tokens.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+
+BF = torch.bfloat16
+F32 = torch.float32
+
+
+def _bf(t: torch.Tensor) -> torch.Tensor:
+    return t.to(BF).contiguous()
+
+
+def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None) -> torch.Tensor:
+    """Conv1d weight [Cout, Cin, k] -> implicit-GEMM B operand [Cout, k * kpt*64] (tap-major)."""
+    cout, cin, k = w.shape
+    kp = (cin + 63) // 64 * 64 if cin_pad is None else cin_pad
+    out = torch.zeros(cout, k, kp, device=w.device, dtype=BF)
+    out[:, :, :cin] = w.permute(0, 2, 1).to(BF)
+    return out.reshape(cout, k * kp).contiguous()
+
+
+@dataclass
+class DiTCond:
+    """Step-invariant tensors of one batch of clips for one CFG branch."""
+    B: int
+    T: int
+    L: int
+    acoustic: torch.Tensor            # fp32 [N, D]   (midi+beats stem, shared by both CFG branches)
+    ac_logits: torch.Tensor           # fp32 [N, depth*E]
+    caption: torch.Tensor             # fp32 [B, L, D]  (c_embedder output)
+    cap_emb: torch.Tensor             # fp32 [B, D]
+    kv_y: List[torch.Tensor] = field(default_factory=list)    # per block fp32 [B*L, 2D] text cross-attn K|V
+    kv_m: List[torch.Tensor] = field(default_factory=list)    # per block fp32 [B*L, 2D] MoE MHA K|V
+
+
+class DiTEngine:
+    """Holds the packed weights of one TxtFlagLargeImprovedDiTV2 and runs it on the GPU."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], *, in_channels=20, hidden_size=768, depth=4,
+                 num_heads=8, num_experts=4, ori_dim=1024, max_len=1500, norm_eps=1e-5,
+                 temperature=2.0, device="cuda"):
+        self.C, self.D, self.depth, self.H, self.E = in_channels, hidden_size, depth, num_heads, num_experts
+        self.hd = hidden_size // num_heads
+        self.ori_dim, self.max_len, self.eps = ori_dim, max_len, norm_eps
+        self.temperature = temperature
+        self.dev = torch.device(device)
+        assert self.hd % 32 == 0 and hidden_size % (64 * 1) == 0
+        self._ws: Dict[Tuple[int, int], dict] = {}
+        self.pack(sd)
+
+    # ------------------------------------------------------------------ packing
+    def pack(self, sd: Dict[str, torch.Tensor]) -> None:
+        dev, D, E = self.dev, self.D, self.E
+        g = lambda k: sd[k].detach().to(dev, F32).contiguous()  # noqa: E731
+        w: dict = {}
+        # stem
+        w["midi_emb"], w["beats_emb"] = g("midi_embedding.weight"), g("beats_embedding.weight")
+        for name in ("midi_proj", "beats_proj"):
+            w[name + "_w"] = pack_conv_weight(g(name + ".0.weight"))
+            w[name + "_b"] = g(name + ".0.bias")
+        w["final_proj_w"] = _bf(g("final_proj.weight")[:, :, 0])
+        w["final_proj_b"] = g("final_proj.bias")
+        w["proj_in_w"] = pack_conv_weight(g("proj_in.weight"))
+        w["proj_in_b"] = g("proj_in.bias")
+        self.proj_in_k = sd["proj_in.weight"].shape[-1]
+        self.stem_k = sd["midi_proj.0.weight"].shape[-1]
+        # embedders
+        for i in (0, 2):
+            w[f"t_w{i}"], w[f"t_b{i}"] = _bf(g(f"t_embedder.mlp.{i}.weight")), g(f"t_embedder.mlp.{i}.bias")
+            w[f"c_w{i}"], w[f"c_b{i}"] = _bf(g(f"c_embedder.mlp.{i}.weight")), g(f"c_embedder.mlp.{i}.bias")
+        w["c_ln_w"], w["c_ln_b"] = g("c_embedder.mlp.3.weight"), g("c_embedder.mlp.3.bias")
+        w["cap_ln_w"], w["cap_ln_b"] = g("cap_embedder.0.weight"), g("cap_embedder.0.bias")
+        w["cap_w"], w["cap_b"] = _bf(g("cap_embedder.1.weight")), g("cap_embedder.1.bias")
+        half = 128
+        w["t_freqs"] = torch.exp(-math.log(10000.0) * torch.arange(0, half, dtype=F32) / half).to(dev)
+        # adaLN of all blocks + final layer as one [depth*6D + 2D, D] operand
+        ada_w = [g(f"blocks.{k}.adaLN_modulation.1.weight") for k in range(self.depth)]
+        ada_b = [g(f"blocks.{k}.adaLN_modulation.1.bias") for k in range(self.depth)]
+        ada_w.append(g("final_layer.adaLN_modulation.1.weight"))
+        ada_b.append(g("final_layer.adaLN_modulation.1.bias"))
+        w["ada_w"], w["ada_b"] = _bf(torch.cat(ada_w, 0)), torch.cat(ada_b, 0).contiguous()
+        self.mod_ld = w["ada_w"].shape[0]
+        # gating networks stacked over blocks
+        w["hl_w"] = torch.cat([g(f"blocks.{k}.feed_forward.high_level_gating_network.weight") for k in range(self.depth)], 0).contiguous()
+        w["hl_b"] = torch.cat([g(f"blocks.{k}.feed_forward.high_level_gating_network.bias") for k in range(self.depth)], 0).contiguous()
+        w["acg_w"] = torch.cat([g(f"blocks.{k}.feed_forward.acoustic_gating_network.weight") for k in range(self.depth)], 0).contiguous()
+        w["acg_b"] = torch.cat([g(f"blocks.{k}.feed_forward.acoustic_gating_network.bias") for k in range(self.depth)], 0).contiguous()
+        band = D // E
+        blocks = []
+        for k in range(self.depth):
+            p = f"blocks.{k}."
+            a, f = p + "attention.", p + "feed_forward."
+            b: dict = {}
+            b["wqkv"] = _bf(torch.cat([g(a + "wq.weight"), g(a + "wk.weight"), g(a + "wv.weight")], 0))
+            b["wo"] = _bf(g(a + "wo.weight"))
+            b["wkvy"] = _bf(torch.cat([g(a + "wk_y.weight"), g(a + "wv_y.weight")], 0))
+            b["gate"] = g(a + "gate")
+            b["attn_norm"], b["ffn_norm"], b["y_norm"] = g(p + "attention_norm.weight"), g(p + "ffn_norm.weight"), g(p + "attention_y_norm.weight")
+            ipw, ipb = g(f + "cross_attention.in_proj_weight"), g(f + "cross_attention.in_proj_bias")
+            b["mq_w"], b["mq_b"] = _bf(ipw[:D]), ipb[:D].contiguous()
+            b["mkv_w"], b["mkv_b"] = _bf(ipw[D:]), ipb[D:].contiguous()
+            b["mo_w"], b["mo_b"] = _bf(g(f + "cross_attention.out_proj.weight")), g(f + "cross_attention.out_proj.bias")
+            b["capg_w"], b["capg_b"] = g(f + "caption_gating_network.weight"), g(f + "caption_gating_network.bias")
+            w13, w2 = [], []
+            for grp in ("caption_experts", "acoustic_experts"):
+                for e in range(E):
+                    w1, w3 = g(f"{f}{grp}.{e}.w1.weight"), g(f"{f}{grp}.{e}.w3.weight")
+                    w13.append(torch.stack([w1, w3], 1).reshape(2 * w1.shape[0], D))
+                    w2.append(g(f"{f}{grp}.{e}.w2.weight"))
+            b["w13"], b["w2"] = _bf(torch.stack(w13, 0)), _bf(torch.stack(w2, 0))  # [2E,2Fh,D], [2E,D,Fh]
+            f13, f2 = [], []
+            for e in range(E):
+                w1, w3 = g(f"{f}freq_experts.{e}.w1.weight"), g(f"{f}freq_experts.{e}.w3.weight")
+                sl = slice(band * e, band * (e + 1))
+                f13.append(torch.stack([w1[:, sl], w3[:, sl]], 1).reshape(2 * w1.shape[0], band))
+                f2.append(g(f"{f}freq_experts.{e}.w2.weight")[sl, :])
+            b["f13"], b["f2"] = _bf(torch.stack(f13, 0)), _bf(torch.stack(f2, 0))  # [E,2Fh,band], [E,band,Fh]
+            blocks.append(b)
+        self.Fh = blocks[0]["w2"].shape[-1]
+        self.band = band
+        w["blocks"] = blocks
+        fl_w = torch.zeros(32, D, device=dev)
+        fl_w[: self.C] = g("final_layer.linear.weight")
+        fl_b = torch.zeros(32, device=dev)
+        fl_b[: self.C] = g("final_layer.linear.bias")
+        w["final_w"], w["final_b"] = _bf(fl_w), fl_b
+        # RoPE table [max_len, hd/2, (cos, sin)] computed exactly like the reference (vocal2music_moe.py:464-475)
+        freqs = 1.0 / (10000.0 ** (torch.arange(0, self.hd, 2)[: self.hd // 2].float() / self.hd))
+        ang = torch.outer(torch.arange(self.max_len, dtype=F32), freqs).float()
+        cis = torch.polar(torch.ones_like(ang), ang)
+        w["rope"] = torch.stack([cis.real, cis.imag], -1).contiguous().to(dev)
+        self.w = w
+
+    # ------------------------------------------------------------------ workspaces
+    def _workspace(self, B: int, T: int) -> dict:
+        key = (B, T)
+        if key in self._ws:
+            return self._ws[key]
+        dev, D, H, hd, E, Fh = self.dev, self.D, self.H, self.hd, self.E, self.Fh
+        N = B * T
+        Tp = (T + 7) // 8 * 8
+        max_rows = ((2 * N + 127) // 128 + 2 * E) * 128
+        z = lambda *s, dt=F32: torch.zeros(*s, device=dev, dtype=dt)  # noqa: E731
+        ws = dict(
+            Tp=Tp, max_rows=max_rows,
+            x_cl=z(B, T, 32, dt=BF), x=z(N, D), h=z(N, D),
+            temb_sin=z(B, 256, dt=BF), temb_h=z(B, D, dt=BF), temb=z(B, D), ada_in=z(B, D, dt=BF),
+            mod=z(B, self.mod_ld), hl=z(B, 2 * self.depth),
+            xa=z(N, D, dt=BF), q=z(B, H, T, hd, dt=BF), k=z(B, H, T, hd, dt=BF), vt=z(B, H, hd, Tp, dt=BF),
+            S=z(B, H, T, Tp), P=z(B, H, T, Tp, dt=BF), o_self=z(N, D), oa=z(N, D, dt=BF),
+            xm=z(N, D, dt=BF), qm=z(N, D, dt=BF), ctx=z(N, D, dt=BF), cap_feat=z(N, D),
+            idx_c=z(N, dt=torch.int32), idx_a=z(N, dt=torch.int32), scale_c=z(N), scale_a=z(N),
+            cap_logits=z(N, E),
+            row_map=z(max_rows, dt=torch.int32), row_scale=z(max_rows), tile_group=z(max_rows // 128, dt=torch.int32),
+            m_tiles=z(1, dt=torch.int32), lb=z(self.depth),
+            xs=z(max_rows, D, dt=BF), hs=z(max_rows, Fh, dt=BF), y2=z(2 * N, D), y=z(N, D, dt=BF),
+            hf=z(E, N, Fh, dt=BF), xf=z(N, D, dt=BF), v=z(N, 32),
+        )
+        self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ step-invariant part
+    @torch.no_grad()
+    def prepare_acoustic(self, midi: torch.Tensor, beats: torch.Tensor, T: int):
+        """midi/beats int64 [B,1,Tm] -> acoustic fp32 [B*T, D] and the acoustic gate logits
+        (vocal2music_moe.py:388-393,397-401,142)."""
+        w, D, dev = self.w, self.D, self.dev
+        B, _, Tm = midi.shape
+        Tpool = Tm // 2
+        emb = torch.empty(B, Tm, D, device=dev, dtype=BF)
+        conv = [torch.empty(B, Tm, D, device=dev, dtype=F32) for _ in range(2)]
+        for i, (idx, tab, name) in enumerate(((midi, w["midi_emb"], "midi_proj"), (beats, w["beats_emb"], "beats_proj"))):
+            ops.embed_rows(idx.to(dev).contiguous(), tab, emb)
+            ops.gemm(emb, w[name + "_w"], M=Tm, G1=B, kpt=D // 64, dil=1, pad=self.stem_k // 2, a_c2=(1, 0),
+                     bias=w[name + "_b"], act=ops.ACT_LRELU, act_slope=0.01,
+                     out_f32=conv[i], out_ld=D, out_g=(Tm * D, 0))
+        pooled = torch.empty(B, Tpool, D, device=dev, dtype=BF)
+        ops.pool2_sum(conv[0], conv[1], B=B, Tin=Tm, Tout=Tpool, D=D, out_bf16=pooled)
+        ac = torch.empty(B, Tpool, D, device=dev, dtype=F32)
+        ops.gemm(pooled.view(B * Tpool, D), w["final_proj_w"], bias=w["final_proj_b"], out_f32=ac, out_ld=D)
+        if Tpool != T:  # length fix-up, vocal2music_moe.py:397-401
+            assert abs(T - Tpool) <= 2, "latent / conditioning length mismatch"
+            if T > Tpool:
+                ac = torch.cat([ac, ac[:, -1:, :].repeat(1, T - Tpool, 1)], 1).contiguous()
+            else:
+                ac = ac[:, :T].contiguous()
+        ac = ac.view(B * T, D)
+        ac_logits = torch.empty(B * T, self.depth * self.E, device=dev, dtype=F32)
+        ops.linear_small(ac, w["acg_w"], w["acg_b"], ac_logits)
+        return ac, ac_logits
+
+    @torch.no_grad()
+    def prepare(self, midi, beats, caption: torch.Tensor, T: int, acoustic=None) -> DiTCond:
+        """Everything in TxtFlagLargeDiT.forward that does not depend on (x, t)."""
+        w, D, dev = self.w, self.D, self.dev
+        B, L, _ = caption.shape
+        if acoustic is None:
+            acoustic = self.prepare_acoustic(midi, beats, T)
+        ac, ac_logits = acoustic
+        cap16 = torch.empty(B * L, self.ori_dim, device=dev, dtype=BF)
+        ops.ew(caption.to(dev, F32).contiguous().view(B * L, -1), out_bf16=cap16)
+        h1 = torch.empty(B * L, D, device=dev, dtype=BF)
+        ops.gemm(cap16, w["c_w0"], bias=w["c_b0"], act=ops.ACT_GELU, out_bf16=h1, outb_ld=D)
+        h2 = torch.empty(B * L, D, device=dev, dtype=F32)
+        ops.gemm(h1, w["c_w2"], bias=w["c_b2"], out_f32=h2, out_ld=D)
+        cap = torch.empty(B, L, D, device=dev, dtype=F32)
+        cap_bf = torch.empty(B * L, D, device=dev, dtype=BF)
+        ops.norm_mod(h2, kind=1, w=w["c_ln_w"], b=w["c_ln_b"], eps=1e-5, out_f32=cap, out_bf16=cap_bf)
+        pool = torch.empty(B, D, device=dev, dtype=F32)
+        ops.mean_tokens(cap, pool)
+        pool_n = torch.empty(B, D, device=dev, dtype=BF)
+        ops.norm_mod(pool, kind=1, w=w["cap_ln_w"], b=w["cap_ln_b"], eps=1e-5, out_bf16=pool_n)
+        cap_emb = torch.empty(B, D, device=dev, dtype=F32)
+        ops.gemm(pool_n, w["cap_w"], bias=w["cap_b"], out_f32=cap_emb, out_ld=D)
+        cond = DiTCond(B=B, T=T, L=L, acoustic=ac, ac_logits=ac_logits, caption=cap, cap_emb=cap_emb)
+        y16 = torch.empty(B * L, D, device=dev, dtype=BF)
+        for k in range(self.depth):
+            b = w["blocks"][k]
+            ops.norm_mod(cap.view(B * L, D), kind=0, w=b["y_norm"], eps=self.eps, out_bf16=y16)
+            kv = torch.empty(B * L, 2 * D, device=dev, dtype=F32)
+            ops.gemm(y16, b["wkvy"], out_f32=kv, out_ld=2 * D)
+            cond.kv_y.append(kv)
+            kvm = torch.empty(B * L, 2 * D, device=dev, dtype=F32)
+            ops.gemm(cap_bf, b["mkv_w"], bias=b["mkv_b"], out_f32=kvm, out_ld=2 * D)
+            cond.kv_m.append(kvm)
+        return cond
+
+    # ------------------------------------------------------------------ one DiT evaluation
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, t: torch.Tensor, cond: DiTCond,
+                expo: List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]],
+                out_v: Optional[torch.Tensor] = None, want_aux: bool = False):
+        """x fp32 [B, C, T], t int64 [B]; expo[k] = Exp(1) draws ([N,2],[N,E],[N,E]) of block k.
+        Returns v as the channels-last GEMM output [N, 32] (first C columns valid) unless `out_v`
+        ([B, C, T]) is given, plus lb_loss per block (device tensor)."""
+        w, D, H, hd, E, Fh = self.w, self.D, self.H, self.hd, self.E, self.Fh
+        B, C, T = x.shape
+        assert (B, T) == (cond.B, cond.T) and T <= self.max_len
+        N, L = B * T, cond.L
+        ws = self._workspace(B, T)
+        Tp, max_rows = ws["Tp"], ws["max_rows"]
+        scale = 1.0 / math.sqrt(hd)
+        aux = []
+
+        # stem: proj_in conv (k5) + bias, fused "+ acoustic"  (vocal2music_moe.py:395,415)
+        ops.nct_to_ntc(x.contiguous(), ws["x_cl"])
+        ops.gemm(ws["x_cl"][:, :, :C], w["proj_in_w"], M=T, G1=B, kpt=1, dil=1, pad=self.proj_in_k // 2,
+                 a_c2=(1, 0), bias=w["proj_in_b"], residual=cond.acoustic, out_f32=ws["x"], out_ld=D,
+                 out_g=(T * D, 0))
+        # timestep embedding MLP and adaLN input (:406,416)
+        ops.timestep_embed(t.contiguous(), w["t_freqs"], out_bf16=ws["temb_sin"])
+        ops.gemm(ws["temb_sin"], w["t_w0"], bias=w["t_b0"], act=ops.ACT_SILU, out_bf16=ws["temb_h"], outb_ld=D)
+        ops.gemm(ws["temb_h"], w["t_w2"], bias=w["t_b2"], out_f32=ws["temb"], out_ld=D)
+        ops.ew(ws["temb"], cond.cap_emb, act=ops.ACT_SILU, out_bf16=ws["ada_in"])
+        ops.gemm(ws["ada_in"], w["ada_w"], bias=w["ada_b"], out_f32=ws["mod"], out_ld=self.mod_ld)
+        ops.linear_small(ws["temb"], w["hl_w"], w["hl_b"], ws["hl"])
+        mod, mld = ws["mod"], self.mod_ld
+
+        xcur, hbuf = ws["x"], ws["h"]
+        for k in range(self.depth):
+            b = w["blocks"][k]
+            m0 = k * 6 * D
+            sh_msa, sc_msa, g_msa = mod[:, m0:], mod[:, m0 + D:], mod[:, m0 + 2 * D:]
+            sh_mlp, sc_mlp, g_mlp = mod[:, m0 + 3 * D:], mod[:, m0 + 4 * D:], mod[:, m0 + 5 * D:]
+            # ---- attention branch (vocal2music_moe.py:245-250; flag_large_dit_moe.py:323-406)
+            ops.norm_mod(xcur, kind=0, w=b["attn_norm"], shift=sh_msa, scale=sc_msa, mod_ld=mld,
+                         rows_per_batch=T, eps=self.eps, out_bf16=ws["xa"])
+            ops.gemm(ws["xa"], b["wqkv"], mode=ops.EPI_QKV_ROPE, rope_cs=w["rope"], T=T, heads=H, head_dim=hd,
+                     Tp=Tp, q_out=ws["q"], k_out=ws["k"], vt_out=ws["vt"])
+            ops.gemm(ws["q"].view(B * H, T, hd), ws["k"].view(B * H, T, hd), M=T, N=T, K=hd, G1=H, G2=B,
+                     a_c2=(1, H), b_c2=(1, H, 0), alpha=scale, out_f32=ws["S"], out_ld=Tp,
+                     out_g=(T * Tp, H * T * Tp))
+            ops.softmax_rows(ws["S"], Tp, ws["P"], Tp, B * H * T, T)
+            ops.gemm(ws["P"].view(B * H, T, Tp)[:, :, :T], ws["vt"].view(B * H, hd, Tp)[:, :, :T], M=T, N=hd, K=T,
+                     G1=H, G2=B, a_c2=(1, H), b_c2=(1, H, 0), out_f32=ws["o_self"], out_ld=D,
+                     out_g=(hd, T * D))
+            kv = cond.kv_y[k]
+            ops.attn_smallkv(ws["q"], (H * T * hd, hd, T * hd), kv, kv[:, D:], 2 * D, B=B, T=T, H=H, hd=hd, L=L,
+                             scale=scale, gate=b["gate"], base=ws["o_self"], out_bf16=ws["oa"])
+            ops.gemm(ws["oa"], b["wo"], gate=g_msa, gate_rows=T, gate_ld=mld, residual=xcur,
+                     out_f32=hbuf, out_ld=D)
+            # ---- Band-MoE branch (vocal2music_moe.py:251-257, 117-185)
+            ops.norm_mod(hbuf, kind=0, w=b["ffn_norm"], shift=sh_mlp, scale=sc_mlp, mod_ld=mld,
+                         rows_per_batch=T, eps=self.eps, out_bf16=ws["xm"])
+            ops.gemm(ws["xm"], b["mq_w"], bias=b["mq_b"], out_bf16=ws["qm"], outb_ld=D)
+            kvm = cond.kv_m[k]
+            ops.attn_smallkv(ws["qm"], (T * D, D, hd), kvm, kvm[:, D:], 2 * D, B=B, T=T, H=H, hd=hd, L=L,
+                             scale=scale, out_bf16=ws["ctx"])
+            ops.gemm(ws["ctx"], b["mo_w"], bias=b["mo_b"], out_f32=ws["cap_feat"], out_ld=D)
+            e0, e1, e2 = expo[k]
+            ops.router(ws["cap_feat"], b["capg_w"], b["capg_b"], cond.ac_logits[:, k * E:], self.depth * E,
+                       ws["hl"][:, 2 * k:], 2 * self.depth, e0, e1, e2, float(self.temperature), N, T,
+                       ws["idx_c"], ws["idx_a"], ws["scale_c"], ws["scale_a"],
+                       ws["cap_logits"] if want_aux else None)
+            ops.moe_sort(ws["idx_c"], ws["idx_a"], ws["scale_c"], ws["scale_a"], N, E, ws["row_map"],
+                         ws["row_scale"], ws["tile_group"], ws["m_tiles"], max_rows, ws["lb"][k:])
+            ops.gather_rows(ws["xm"], ws["row_map"], ws["m_tiles"], N, ws["xs"], max_rows)
+            ops.gemm(ws["xs"], b["w13"], M=max_rows, b_c2=(0, 0, 1), tile_group=ws["tile_group"],
+                     m_tiles_used=ws["m_tiles"], swiglu=True, out_bf16=ws["hs"], outb_ld=Fh)
+            ops.gemm(ws["hs"], b["w2"], M=max_rows, b_c2=(0, 0, 1), tile_group=ws["tile_group"],
+                     m_tiles_used=ws["m_tiles"], row_map=ws["row_map"], rows_out=2 * N,
+                     row_scale=ws["row_scale"], out_f32=ws["y2"], out_ld=D)
+            ops.ew(ws["y2"][:N], ws["y2"][N:], out_bf16=ws["y"])
+            yb = ws["y"].view(N, E, self.band).permute(1, 0, 2)  # [E, N, band] view: per-band K slice
+            ops.gemm(yb, b["f13"], M=N, G1=E, a_c2=(1, 0), b_c2=(1, 0, 0), swiglu=True,
+                     out_bf16=ws["hf"], outb_ld=Fh, outb_g=(N * Fh, 0))
+            ops.gemm(ws["hf"], b["f2"], M=N, G1=E, a_c2=(1, 0), b_c2=(1, 0, 0),
+                     gate=g_mlp, gate_rows=T, gate_ld=mld, gate_g1=self.band, residual=hbuf,
+                     out_f32=xcur, out_ld=D, out_g=(self.band, 0))
+            if want_aux:
+                aux.append(dict(idx_c=ws["idx_c"].clone(), idx_a=ws["idx_a"].clone(),
+                                cap_logits=ws["cap_logits"].clone(), h=hbuf.clone(), x=xcur.clone()))
+        # ---- final layer (vocal2music_moe.py:268-291,431)
+        f0 = self.depth * 6 * D
+        ops.norm_mod(xcur, kind=1, shift=mod[:, f0:], scale=mod[:, f0 + D:], mod_ld=mld, rows_per_batch=T,
+                     eps=1e-6, out_bf16=ws["xf"])
+        ops.gemm(ws["xf"], w["final_w"], N=C, bias=w["final_b"], out_f32=ws["v"], out_ld=32)
+        if out_v is not None:
+            ops.ntc_to_nct(ws["v"], out_v, ld=32)
+        return (ws["v"], ws["lb"], aux) if want_aux else (ws["v"], ws["lb"])

@@ -48,7 +48,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: Optional[int] = None, N: Option
          bias: Optional[torch.Tensor] = None, bias_g1: int = 0, bias_tile: int = 0,
          act: int = ACT_NONE, act_slope: float = 0.0,
          row_scale: Optional[torch.Tensor] = None,
-         gate: Optional[torch.Tensor] = None, gate_rows: int = 1, gate_ld: int = 0,
+         gate: Optional[torch.Tensor] = None, gate_rows: int = 1, gate_ld: int = 0, gate_g1: int = 0,
          row_map: Optional[torch.Tensor] = None, row_mul: int = 1, row_off: int = 0,
          row_off_g1: int = 0, rows_out: Optional[int] = None,
          residual: Optional[torch.Tensor] = None, accumulate: bool = False,
@@ -88,7 +88,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: Optional[int] = None, N: Option
     args.bias, args.bias_g1, args.bias_tile = _ptr(bias), bias_g1, bias_tile
     args.act, args.act_slope = act, act_slope
     args.row_scale = _ptr(row_scale)
-    args.gate, args.gate_rows, args.gate_ld = _ptr(gate), gate_rows, gate_ld
+    args.gate, args.gate_rows, args.gate_ld, args.gate_g1 = _ptr(gate), gate_rows, gate_ld, gate_g1
     args.row_map = _ptr(row_map)
     args.row_mul, args.row_off, args.row_off_g1 = row_mul, row_off, row_off_g1
     args.rows_out = args.M if rows_out is None else rows_out
@@ -104,3 +104,98 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: Optional[int] = None, N: Option
     args.rope_cs, args.T, args.heads, args.head_dim, args.Tp = _ptr(rope_cs), T, heads, head_dim, Tp
     args.q_out, args.k_out, args.vt_out = _ptr(q_out), _ptr(k_out), _ptr(vt_out)
     _lib.check(_lib.lib().vb_gemm(C.byref(args), _stream()), "vb_gemm")
+
+
+# ------------------------------------------------------------------------------------------
+# plain-argument ops
+# ------------------------------------------------------------------------------------------
+def _call(name: str, *args) -> None:
+    _lib.check(getattr(_lib.lib(), name)(*args, _stream()), name)
+
+
+def norm_mod(x, *, kind: int, w=None, b=None, shift=None, scale=None, mod_ld: int = 0,
+             rows_per_batch: int = 0, eps: float, out_bf16=None, out_f32=None) -> None:
+    """kind 0 RMSNorm / 1 LayerNorm (+ optional affine, + optional adaLN modulate)."""
+    rows, D = x.numel() // x.shape[-1], x.shape[-1]
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    _call("vb_norm_mod", kind, _ptr(x), _ptr(w), _ptr(b), _ptr(shift), _ptr(scale), mod_ld,
+          rows_per_batch or rows, eps, _ptr(out_bf16), _ptr(out_f32), rows, D)
+
+
+def softmax_rows(S, lds: int, P, ldp: int, rows: int, n: int) -> None:
+    _call("vb_softmax_rows", _ptr(S), lds, _ptr(P), ldp, rows, n)
+
+
+def attn_smallkv(q, q_strides, K, V, kv_ld, *, B, T, H, hd, L, scale, gate=None, base=None, out_bf16=None,
+                 out_f32=None) -> None:
+    _call("vb_attn_smallkv", _ptr(q), q_strides[0], q_strides[1], q_strides[2], _ptr(K), _ptr(V), kv_ld, B, T, H,
+          hd, L, scale, _ptr(gate), _ptr(base), _ptr(out_bf16), _ptr(out_f32))
+
+
+def timestep_embed(t, freqs, *, out_f32=None, out_bf16=None, dim: int = 256) -> None:
+    assert t.dtype == torch.int64
+    _call("vb_timestep_embed", _ptr(t), _ptr(freqs), _ptr(out_f32), _ptr(out_bf16), t.numel(), dim)
+
+
+def linear_small(x, W, bias, out) -> None:
+    rows, D = x.numel() // x.shape[-1], x.shape[-1]
+    _call("vb_linear_small", _ptr(x), x.stride(-2) if x.dim() > 1 else D, _ptr(W), _ptr(bias), _ptr(out),
+          rows, D, W.shape[0])
+
+
+def router(cap_feat, Wc, bc, ac_logits, ac_ld, hl_logits, hl_ld, e0, e1, e2, tau, N, T, idx_c, idx_a,
+           scale_c, scale_a, cap_logits_out=None) -> None:
+    _call("vb_router", _ptr(cap_feat), _ptr(Wc), _ptr(bc), _ptr(ac_logits), ac_ld, _ptr(hl_logits), hl_ld, _ptr(e0),
+          _ptr(e1), _ptr(e2), tau, N, T, cap_feat.shape[-1], Wc.shape[0], _ptr(idx_c), _ptr(idx_a),
+          _ptr(scale_c), _ptr(scale_a), _ptr(cap_logits_out))
+
+
+def moe_sort(idx_c, idx_a, scale_c, scale_a, N, E, row_map, row_scale, tile_group, m_tiles_used, max_rows,
+             lb_out=None) -> None:
+    _call("vb_moe_sort", _ptr(idx_c), _ptr(idx_a), _ptr(scale_c), _ptr(scale_a), N, E, _ptr(row_map),
+          _ptr(row_scale), _ptr(tile_group), _ptr(m_tiles_used), max_rows, _ptr(lb_out))
+
+
+def gather_rows(x, row_map, m_tiles_used, n_tokens, out, max_rows) -> None:
+    _call("vb_gather_rows", _ptr(x), _ptr(row_map), _ptr(m_tiles_used), n_tokens, x.shape[-1], _ptr(out),
+          max_rows)
+
+
+def ew(a, b=None, *, alpha=1.0, beta=1.0, act=ACT_NONE, slope=0.0, out_f32=None, out_bf16=None, rep=1):
+    rows, D = a.numel() // a.shape[-1], a.shape[-1]
+    _call("vb_ew", _ptr(a), _ptr(b), alpha, beta, act, slope, _ptr(out_f32), _ptr(out_bf16), rows, D, rep)
+
+
+def nct_to_ntc(x, out_bf16, *, scale=1.0) -> None:
+    B, Cc, T = x.shape
+    _call("vb_nct_to_ntc", _ptr(x), scale, _ptr(out_bf16), B, Cc, T, out_bf16.shape[-1])
+
+
+def ntc_to_nct(e_c, x, *, e_u=None, ld, s=0.0, dt=0.0) -> None:
+    B, Cc, T = x.shape
+    _call("vb_ntc_to_nct", _ptr(e_c), _ptr(e_u), ld, s, dt, _ptr(x), B, Cc, T)
+
+
+def embed_rows(idx, table, out_bf16) -> None:
+    _call("vb_embed_rows", _ptr(idx), _ptr(table), table.shape[0], table.shape[1], _ptr(out_bf16), idx.numel())
+
+
+def pool2_sum(a, b, *, B, Tin, Tout, D, out_bf16=None, out_f32=None) -> None:
+    _call("vb_pool2_sum", _ptr(a), _ptr(b), B, Tin, Tout, D, _ptr(out_bf16), _ptr(out_f32))
+
+
+def gn_stats(x, B, T, Cc, G, eps, mean, rstd) -> None:
+    _call("vb_gn_stats", _ptr(x), B, T, Cc, G, eps, _ptr(mean), _ptr(rstd))
+
+
+def gn_apply(x, mean, rstd, w, b, B, T, Cc, G, act, out_bf16) -> None:
+    _call("vb_gn_apply", _ptr(x), _ptr(mean), _ptr(rstd), _ptr(w), _ptr(b), B, T, Cc, G, act, _ptr(out_bf16))
+
+
+def conv_post(x_bf16, w, bias: float, B, T, Cc, k, wav) -> None:
+    _call("vb_conv_post", _ptr(x_bf16), _ptr(w), bias, B, T, Cc, k, _ptr(wav))
+
+
+def mean_tokens(x, out) -> None:
+    B, L, D = x.shape
+    _call("vb_mean_tokens", _ptr(x), B, L, D, _ptr(out))
