@@ -1,0 +1,142 @@
+"""HiFi-GAN generator on B200: every Conv1d / ConvTranspose1d is an implicit-GEMM vb_gemm launch
+over channels-last bf16 activations; LeakyReLU, bias, residual add, MRF sum and the 1/3 mean are
+fused into the producing GEMM's epilogue.
+
+Mirrors reference vocoder/hifigan/modules/hifigan.py (HifiGanGenerator.forward :126-143,
+ResBlock1.forward :51-58).  Generic over upsample rates / kernel sizes (the reference reads them
+from the checkpoint's config.yaml, vocoder/hifigan/hifigan.py:11-15).  weight_norm is folded at
+pack time (w = g * v / ||v||).
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import torch
+
+from . import ops
+from .dit import BF, F32, pack_conv_weight
+
+LRELU = 0.1
+
+
+def fold_weight_norm(sd: Dict[str, torch.Tensor], pre: str) -> torch.Tensor:
+    if (pre + "weight") in sd:
+        return sd[pre + "weight"].float()
+    v, g = sd[pre + "weight_v"].float(), sd[pre + "weight_g"].float()
+    norm = v.flatten(1).norm(dim=1).view(-1, *([1] * (v.dim() - 1)))
+    return v * (g / norm)
+
+
+class HifiGanEngine:
+    def __init__(self, sd: Dict[str, torch.Tensor], h: dict, device="cuda"):
+        assert str(h["resblock"]) == "1", "only ResBlock1 generators are implemented"
+        self.dev = torch.device(device)
+        self.h = dict(h)
+        self.rates: List[int] = list(h["upsample_rates"])
+        self.up_k: List[int] = list(h["upsample_kernel_sizes"])
+        self.rb_k: List[int] = list(h["resblock_kernel_sizes"])
+        self.rb_d: List[List[int]] = [list(d) for d in h["resblock_dilation_sizes"]]
+        self.C0 = h["upsample_initial_channel"]
+        self.w: Dict[str, torch.Tensor] = {}
+        self._pack({k: v.detach().to(self.dev) for k, v in sd.items()})
+
+    def _pack(self, sd):
+        w = self.w
+        w["pre.w"] = pack_conv_weight(fold_weight_norm(sd, "conv_pre."))
+        w["pre.b"] = sd["conv_pre.bias"].float().contiguous()
+        self.n_mel = sd["conv_pre.weight_v" if "conv_pre.weight_v" in sd else "conv_pre.weight"].shape[1]
+        for i, (u, k) in enumerate(zip(self.rates, self.up_k)):
+            wt = fold_weight_norm(sd, f"ups.{i}.")  # [Cin, Cout, k]
+            cin, cout, _ = wt.shape
+            Q = (k + u - 1) // u
+            kp = (cin + 63) // 64 * 64
+            wp = torch.zeros(u, cout, Q, kp, device=self.dev, dtype=BF)
+            for r in range(u):
+                for q in range(Q):
+                    j = r + u * q
+                    if j < k:  # tap q of phase r reads x[s - q]; stored reversed so time = s-(Q-1)+tap
+                        wp[r, :, Q - 1 - q, :cin] = wt[:, :, j].t().to(BF)
+            w[f"up{i}.w"] = wp.reshape(u, cout, Q * kp).contiguous()
+            w[f"up{i}.b"] = sd[f"ups.{i}.bias"].float().contiguous()
+        nk = len(self.rb_k)
+        for i in range(len(self.rates)):
+            for j in range(nk):
+                pre = f"resblocks.{i * nk + j}."
+                for c in range(len(self.rb_d[j])):
+                    for which in ("convs1", "convs2"):
+                        w[f"rb{i}.{j}.{which}.{c}.w"] = pack_conv_weight(fold_weight_norm(sd, f"{pre}{which}.{c}."))
+                        w[f"rb{i}.{j}.{which}.{c}.b"] = sd[f"{pre}{which}.{c}.bias"].float().contiguous()
+        wpost = fold_weight_norm(sd, "conv_post.")  # [1, C, k]
+        assert wpost.shape[0] == 1
+        w["post.w"] = wpost[0].t().contiguous()  # [k, C]
+        self.post_b = float(sd["conv_post.bias"].float().item())
+        self.post_k = wpost.shape[-1]
+
+    def _conv(self, a, wname, B, T, k, dil, **epi):
+        w = self.w[wname + ".w"]
+        Cout = w.shape[0]
+        kpt = w.shape[1] // k // 64
+        ops.gemm(a, w, M=T, G1=B, kpt=kpt, dil=dil, pad=(k * dil - dil) // 2, a_c2=(1, 0),
+                 bias=self.w[wname + ".b"], out_ld=Cout, out_g=(T * Cout, 0), outb_ld=Cout,
+                 outb_g=(T * Cout, 0), **epi)
+
+    @torch.no_grad()
+    def forward(self, mel: torch.Tensor) -> torch.Tensor:
+        """mel fp32 [B, n_mel, T] -> wav fp32 [B, T * prod(rates)]."""
+        dev = self.dev
+        B, nm, T = mel.shape
+        assert nm == self.n_mel and nm % 8 == 0
+        mel_cl = torch.empty(B, T, nm, device=dev, dtype=BF)
+        ops.nct_to_ntc(mel.to(dev, F32).contiguous(), mel_cl)
+        C = self.C0
+        xb = torch.empty(B, T, C, device=dev, dtype=BF)  # lrelu(conv_pre(mel)), hifigan.py:128-130
+        self._conv(mel_cl, "pre", B, T, 7, 1, out_bf16=xb, act_out=ops.ACT_LRELU, act_out_slope=LRELU)
+        nk = len(self.rb_k)
+        n_stages = len(self.rates)
+        for i, (u, k) in enumerate(zip(self.rates, self.up_k)):
+            # ---- ConvTranspose1d as u polyphase GEMMs in one launch (hifigan.py:131)
+            wup = self.w[f"up{i}.w"]
+            Cout = wup.shape[1]
+            Q = (k + u - 1) // u
+            kp = wup.shape[2] // Q
+            p = (k - u) // 2
+            Tout = (T - 1) * u - 2 * p + k
+            x = torch.empty(B, Tout, Cout, device=dev, dtype=F32)
+            xl = torch.empty(B, Tout, Cout, device=dev, dtype=BF)
+            ops.gemm(xb, wup, M=T + Q - 1, N=Cout, K=Q * kp, G1=u, G2=B, kpt=kp // 64, dil=1, pad=Q - 1,
+                     a_c2=(0, 1), b_c2=(1, 0, 0), bias=self.w[f"up{i}.b"],
+                     row_mul=u, row_off=-p, row_off_g1=1, rows_out=Tout,
+                     out_f32=x, out_ld=Cout, out_g=(0, Tout * Cout),
+                     out_bf16=xl, outb_ld=Cout, outb_g=(0, Tout * Cout), act_out=ops.ACT_LRELU,
+                     act_out_slope=LRELU)
+            T, C = Tout, Cout
+            # ---- MRF: mean of nk ResBlock1 chains that all start from x (hifigan.py:132-138)
+            last_stage = i == n_stages - 1
+            xs = torch.empty(B, T, C, device=dev, dtype=F32)
+            nxt = torch.empty(B, T, C, device=dev, dtype=BF)
+            t1 = torch.empty(B, T, C, device=dev, dtype=BF)
+            rbuf = [torch.empty(B, T, C, device=dev, dtype=F32) for _ in range(2)]
+            rlb = [torch.empty(B, T, C, device=dev, dtype=BF) for _ in range(2)]
+            for j in range(nk):
+                kk, dils = self.rb_k[j], self.rb_d[j]
+                r, rl = x, xl
+                for c, d in enumerate(dils):
+                    self._conv(rl, f"rb{i}.{j}.convs1.{c}", B, T, kk, d, out_bf16=t1,
+                               act_out=ops.ACT_LRELU, act_out_slope=LRELU)
+                    if c < len(dils) - 1:
+                        self._conv(t1, f"rb{i}.{j}.convs2.{c}", B, T, kk, 1, residual=r,
+                                   out_f32=rbuf[c % 2], out_bf16=rlb[c % 2], act_out=ops.ACT_LRELU,
+                                   act_out_slope=LRELU)
+                        r, rl = rbuf[c % 2], rlb[c % 2]
+                    else:
+                        # last pair: xs (+)= r + conv; the last resblock also emits the next stage's
+                        # operand lrelu(xs / nk) (slope 0.1 before ups, 0.01 before conv_post :139)
+                        final = j == nk - 1
+                        self._conv(t1, f"rb{i}.{j}.convs2.{c}", B, T, kk, 1, residual=r,
+                                   out_f32=xs, accumulate=(j > 0),
+                                   out_bf16=nxt if final else None, act_out=ops.ACT_LRELU,
+                                   act_out_slope=(0.01 if last_stage else LRELU), out_scale=1.0 / nk)
+            xb = nxt
+        wav = torch.empty(B, T, device=dev, dtype=F32)
+        ops.conv_post(xb, self.w["post.w"], self.post_b, B, T, C, self.post_k, wav)
+        return wav
