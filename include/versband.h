@@ -130,6 +130,14 @@ int vb_sizeof(int which);
 /* number of kernels this library has launched in this process */
 long long vb_launch_count(void);
 
+/* Optional per-launch timing: when enabled every entry point brackets its kernel with CUDA events
+ * on the launching stream; vb_prof_report() synchronises and returns total ms / launch count per
+ * kernel family (0 gemm, 1 norm, 2 softmax, 3 attn_small, 4 router, 5 moe_sort, 6 elementwise,
+ * 7 layout, 8 groupnorm, 9 conv_post). Not usable during CUDA-graph capture. */
+#define VB_PROF_KINDS 10
+int vb_prof_enable(int on);
+int vb_prof_report(double* ms_by_kind, long long* count_by_kind, int nkinds);
+
 /* ------------------------------------------------------------------------------------------
  * Row-wise ops of the DiT step (fp32 in, bf16 GEMM operand and/or fp32 out)
  * ------------------------------------------------------------------------------------------ */

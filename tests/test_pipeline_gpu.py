@@ -1,0 +1,84 @@
+"""Sampler + full pipeline on the GPU vs the oracle (small clip so the CPU oracle finishes in
+seconds), graph replay vs eager, and size-independent properties at the full 20 s size."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import accompband_ref as R  # noqa: E402
+from oracle import synth  # noqa: E402
+from versband_b200.pipeline import AccompBandPipeline  # noqa: E402
+from versband_b200.sampler import FlowSampler, euler_schedule  # noqa: E402
+
+torch.set_grad_enabled(False)
+
+
+@pytest.fixture(scope="module")
+def sds():
+    return (synth.synth_state_dict(synth.load_manifest("dit"), seed=1234),
+            synth.synth_state_dict(synth.load_manifest("vae"), seed=2345),
+            synth.synth_state_dict(synth.load_manifest("hifigan"), seed=3456, gain=synth.HIFIGAN_GAIN))
+
+
+@pytest.fixture(scope="module")
+def pipe(sds):
+    return AccompBandPipeline(*sds, dit_cfg=synth.DIT_CFG, ddconfig=synth.VAE_DDCONFIG,
+                              embed_dim=synth.VAE_EMBED_DIM, voc_cfg=synth.HIFIGAN_CFG)
+
+
+def test_schedule_is_the_oracles():
+    assert euler_schedule(25) == R.euler_schedule(25)
+
+
+def test_sampler_graph_equals_eager_and_tracks_oracle(pipe, sds):
+    B, T = 1, 32
+    x0, midi, beats, cap_c, cap_u = synth.dit_inputs(B, T, seed=3)
+    dit = pipe.dit
+    ac = dit.prepare_acoustic(midi.cuda(), beats.cuda(), T)
+    cond = dit.prepare(None, None, cap_c.cuda(), T, acoustic=ac)
+    uncond = dit.prepare(None, None, cap_u.cuda(), T, acoustic=ac)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    graph_s = pipe.sampler
+    noise = graph_s.draw_noise(B, T, g)
+    x_graph = graph_s.sample_cfg(x0.cuda(), cond, uncond, 3.0, noise=noise)
+    x_graph2 = graph_s.sample_cfg(x0.cuda(), cond, uncond, 3.0, noise=noise)  # replay
+    eager = FlowSampler(dit, use_graph=False)
+    x_eager = eager.sample_cfg(x0.cuda(), cond, uncond, 3.0, noise=noise)
+    torch.cuda.synchronize()
+    assert torch.equal(x_graph, x_eager) and torch.equal(x_graph, x_graph2)
+    # oracle with the same noise (cond rows first, then uncond rows)
+    N, E = B * T, 4
+    nz = noise.cpu()
+    expo = [[[(nz[s, k, br * N:(br + 1) * N, 0:2], nz[s, k, br * N:(br + 1) * N, 2:2 + E],
+               nz[s, k, br * N:(br + 1) * N, 2 + E:]) for k in range(4)] for br in range(2)] for s in range(24)]
+    ctx_c = {"c_crossattn": cap_c, "c_concat": {"midi": midi, "beats": beats}}
+    ctx_u = {"c_crossattn": cap_u, "c_concat": {"midi": midi, "beats": beats}}
+    x_ref = R.sample_cfg(sds[0], x0, ctx_c, ctx_u, 3.0, depth=4, n_heads=8, expo=expo)
+    err = float((x_graph.cpu() - x_ref).abs().max() / x_ref.abs().max())
+    med = float((x_graph.cpu() - x_ref).abs().median() / x_ref.abs().max())
+    print(f"sampler latent vs oracle: max rel {err:.3e}, median rel {med:.3e}")
+    assert med < 2e-2
+
+
+def test_pipeline_full_size_properties(pipe):
+    """20 s clip (T_mel=1500): shapes, finiteness, determinism, batch-independence of clips."""
+    B, T = 2, 750
+    x0, midi, beats, cap_c, cap_u = synth.dit_inputs(B, T, seed=8)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    noise = pipe.sampler.draw_noise(B, T, g)
+    out = pipe.generate(midi.cuda(), beats.cuda(), cap_c.cuda(), cap_u.cuda(), x0=x0.cuda(), noise=noise)
+    torch.cuda.synchronize()
+    assert out["latent"].shape == (B, 20, T) and out["mel"].shape == (B, 80, 2 * T)
+    assert out["wav"].shape == (B, 2 * T * 320)
+    for k in ("latent", "mel", "wav"):
+        assert torch.isfinite(out[k]).all(), k
+    assert float(out["wav"].abs().max()) <= 1.0
+    out2 = pipe.generate(midi.cuda(), beats.cuda(), cap_c.cuda(), cap_u.cuda(), x0=x0.cuda(), noise=noise)
+    assert torch.equal(out["wav"], out2["wav"])  # bitwise reproducible
+    # clip 0 alone == clip 0 inside the batch (data-parallel sharding changes nothing)
+    N = T
+    n1 = torch.cat([noise[:, :, 0:N], noise[:, :, B * N:B * N + N]], 2).contiguous()
+    o1 = pipe.generate(midi[:1].cuda(), beats[:1].cuda(), cap_c[:1].cuda(), cap_u[:1].cuda(), x0=x0[:1].cuda(), noise=n1)
+    d = float((o1["latent"][0] - out["latent"][0]).abs().max())
+    print("batch-1 vs batch-2 latent max abs diff:", d)
+    assert d < 1e-3

@@ -102,3 +102,19 @@ def _declare(l: C.CDLL) -> None:
         fn = getattr(l, name)
         fn.argtypes = at
         fn.restype = C.c_int
+
+
+PROF_KINDS = ["gemm", "norm", "softmax", "attn_small", "router", "moe_sort", "elementwise", "layout",
+              "groupnorm", "conv_post"]
+
+
+def prof_enable(on: bool) -> None:
+    check(lib().vb_prof_enable(int(on)), "vb_prof_enable")
+
+
+def prof_report() -> dict:
+    n = len(PROF_KINDS)
+    ms = (C.c_double * n)()
+    cnt = (C.c_longlong * n)()
+    check(lib().vb_prof_report(ms, cnt, n), "vb_prof_report")
+    return {k: {"ms": ms[i], "launches": int(cnt[i])} for i, k in enumerate(PROF_KINDS)}

@@ -2,6 +2,8 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
+#include <vector>
 #include "vb_internal.h"
 
 namespace vb {
@@ -30,7 +32,49 @@ tensor_map_encode_fn get_tensor_map_encoder() {
   return fn;
 }
 
+// ---- per-family event profiler ----
+struct ProfEv { cudaEvent_t a, b; int kind; };
+static bool g_prof_on = false;
+static std::vector<ProfEv> g_prof;
+static std::mutex g_prof_mu;
+bool prof_enabled() { return g_prof_on; }
+void prof_start(int kind, cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfEv e; e.kind = kind;
+  cudaEventCreate(&e.a); cudaEventCreate(&e.b);
+  cudaEventRecord(e.a, s);
+  g_prof.push_back(e);
+}
+void prof_stop(int kind, cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (size_t i = g_prof.size(); i-- > 0;)
+    if (g_prof[i].kind == kind) { cudaEventRecord(g_prof[i].b, s); break; }
+}
+
 }  // namespace vb
+
+extern "C" int vb_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(vb::g_prof_mu);
+  for (auto& e : vb::g_prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  vb::g_prof.clear();
+  vb::g_prof_on = on != 0;
+  return VB_OK;
+}
+
+// Synchronises the device and sums event-pair durations per kernel family.
+extern "C" int vb_prof_report(double* ms_by_kind, long long* count_by_kind, int nkinds) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return vb::set_error(VB_ERR_CUDA, "vb_prof_report: %s", cudaGetErrorString(e));
+  for (int i = 0; i < nkinds; ++i) { ms_by_kind[i] = 0; count_by_kind[i] = 0; }
+  std::lock_guard<std::mutex> lk(vb::g_prof_mu);
+  for (auto& ev : vb::g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess && ev.kind < nkinds) {
+      ms_by_kind[ev.kind] += ms; count_by_kind[ev.kind] += 1;
+    }
+  }
+  return VB_OK;
+}
 
 extern "C" int vb_version(void) { return VB_ABI_VERSION; }
 extern "C" const char* vb_last_error(void) { return vb::g_err; }

@@ -242,6 +242,7 @@ static inline int grid_for(long long n, int threads) {
 
 extern "C" int vb_ew(const float* a, const float* b, float alpha, float beta, int act, float slope,
                      float* out_f32, void* out_bf16, int64_t rows, int D, int rep, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_EW, stream);
   if (!a || rows <= 0 || D <= 0 || D % 4 != 0 || rep < 1 || (!out_f32 && !out_bf16))
     return set_error(VB_ERR_INVALID, "vb_ew: bad arguments (D %% 4 == 0)");
   const long long nvec = rows * (D / 4);
@@ -252,6 +253,7 @@ extern "C" int vb_ew(const float* a, const float* b, float alpha, float beta, in
 
 extern "C" int vb_nct_to_ntc(const float* in, float scale, void* out_bf16, int B, int C, int T, int Cp,
                              void* stream) {
+  vb::ProfScope prof_scope(vb::PK_LAYOUT, stream);
   if (!in || !out_bf16 || Cp < C) return set_error(VB_ERR_INVALID, "vb_nct_to_ntc: bad arguments");
   dim3 grid((T + 31) / 32, (Cp + 31) / 32, B), block(32, 8);
   nct_to_ntc_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -261,6 +263,7 @@ extern "C" int vb_nct_to_ntc(const float* in, float scale, void* out_bf16, int B
 
 extern "C" int vb_ntc_to_nct(const float* e_c, const float* e_u, int64_t ld, float s, float dt,
                              float* x, int B, int C, int T, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_LAYOUT, stream);
   if (!e_c || !x) return set_error(VB_ERR_INVALID, "vb_ntc_to_nct: bad arguments");
   dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
   ntc_to_nct_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(e_c, e_u, ld, s, dt, x, C, T);
@@ -269,6 +272,7 @@ extern "C" int vb_ntc_to_nct(const float* e_c, const float* e_u, int64_t ld, flo
 
 extern "C" int vb_embed_rows(const int64_t* idx, const float* table, int V, int D, void* out_bf16,
                              int64_t rows, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_LAYOUT, stream);
   if (!idx || !table || !out_bf16 || D % 2) return set_error(VB_ERR_INVALID, "vb_embed_rows: bad arguments");
   embed_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const long long*>(idx), table, V, D, static_cast<__nv_bfloat16*>(out_bf16), rows);
@@ -277,6 +281,7 @@ extern "C" int vb_embed_rows(const int64_t* idx, const float* table, int V, int 
 
 extern "C" int vb_pool2_sum(const float* a, const float* b, int B, int Tin, int Tout, int D,
                             void* out_bf16, float* out_f32, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_EW, stream);
   if (!a || Tout * 2 > Tin) return set_error(VB_ERR_INVALID, "vb_pool2_sum: bad arguments");
   const long long n = (long long)B * Tout * D;
   pool2_sum_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -286,6 +291,7 @@ extern "C" int vb_pool2_sum(const float* a, const float* b, int B, int Tin, int 
 
 extern "C" int vb_gn_stats(const float* x, int B, int T, int C, int G, float eps, float* mean,
                            float* rstd, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_GN, stream);
   if (!x || !mean || !rstd || C % G) return set_error(VB_ERR_INVALID, "vb_gn_stats: bad arguments");
   gn_stats_kernel<<<dim3(G, B), 512, 0, static_cast<cudaStream_t>(stream)>>>(x, T, C, G, eps, mean, rstd);
   return check_launch("vb_gn_stats");
@@ -294,6 +300,7 @@ extern "C" int vb_gn_stats(const float* x, int B, int T, int C, int G, float eps
 extern "C" int vb_gn_apply(const float* x, const float* mean, const float* rstd, const float* w,
                            const float* bias, int B, int T, int C, int G, int act, void* out_bf16,
                            void* stream) {
+  vb::ProfScope prof_scope(vb::PK_GN, stream);
   if (!x || !mean || !rstd || !w || !bias || !out_bf16 || C % 4 || C % G)
     return set_error(VB_ERR_INVALID, "vb_gn_apply: bad arguments");
   const long long nvec = (long long)B * T * C / 4;
@@ -304,6 +311,7 @@ extern "C" int vb_gn_apply(const float* x, const float* mean, const float* rstd,
 
 extern "C" int vb_conv_post(const void* x_bf16, const float* w, float bias, int B, int T, int C, int k,
                             float* wav, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_CONV_POST, stream);
   if (!x_bf16 || !w || !wav || C % 8) return set_error(VB_ERR_INVALID, "vb_conv_post: bad arguments");
   dim3 grid((T + 127) / 128, B);
   conv_post_kernel<<<grid, 128, k * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(

@@ -462,6 +462,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKPar
 }  // namespace vb
 
 extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
+  vb::ProfScope prof_scope(vb::PK_GEMM, stream_);
   using namespace vb;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!a || !a->a || !a->b) return set_error(VB_ERR_INVALID, "vb_gemm: null operand");

@@ -21,6 +21,20 @@ typedef CUresult (*tensor_map_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuui
 // Resolved once through cudaGetDriverEntryPoint (no link-time libcuda dependency).
 tensor_map_encode_fn get_tensor_map_encoder();
 
+// Optional per-launch CUDA-event timing by kernel family (vb_prof_enable / vb_prof_report).
+enum ProfKind { PK_GEMM = 0, PK_NORM, PK_SOFTMAX, PK_ATTN_SMALL, PK_ROUTER, PK_MOE_SORT, PK_EW, PK_LAYOUT,
+                PK_GN, PK_CONV_POST, PK_COUNT };
+bool prof_enabled();
+void prof_start(int kind, cudaStream_t s);
+void prof_stop(int kind, cudaStream_t s);
+struct ProfScope {
+  int kind; cudaStream_t s; bool on;
+  ProfScope(int k, void* stream) : kind(k), s(static_cast<cudaStream_t>(stream)), on(prof_enabled()) {
+    if (on) prof_start(kind, s);
+  }
+  ~ProfScope() { if (on) prof_stop(kind, s); }
+};
+
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));

@@ -218,6 +218,7 @@ using namespace vb;
 
 extern "C" int vb_linear_small(const float* x, int64_t ldx, const float* W, const float* bias,
                                float* out, int rows, int D, int E, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_ROUTER, stream);
   if (!x || !W || !out || rows <= 0 || E <= 0 || E > 16)
     return set_error(VB_ERR_INVALID, "vb_linear_small: bad arguments (E <= 16)");
   linear_small_kernel<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, W, bias,
@@ -230,6 +231,7 @@ extern "C" int vb_router(const float* cap_feat, const float* Wc, const float* bc
                          const float* e0, const float* e1, const float* e2, float tau, int N, int T, int D, int E,
                          int32_t* idx_c, int32_t* idx_a, float* scale_c, float* scale_a,
                          float* cap_logits_out, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_ROUTER, stream);
   if (!cap_feat || !Wc || !bc || !ac_logits || !hl_logits || !e0 || !e1 || !e2 || !idx_c || !idx_a ||
       !scale_c || !scale_a || N <= 0 || T <= 0)
     return set_error(VB_ERR_INVALID, "vb_router: null/invalid argument");
@@ -244,6 +246,7 @@ extern "C" int vb_moe_sort(const int32_t* idx_c, const int32_t* idx_a, const flo
                            const float* scale_a, int N, int E, int32_t* row_map, float* row_scale,
                            int32_t* tile_group, int32_t* m_tiles_used, int max_rows, float* lb_out,
                            void* stream) {
+  vb::ProfScope prof_scope(vb::PK_MOE_SORT, stream);
   if (!idx_c || !idx_a || !row_map || !row_scale || !tile_group || !m_tiles_used || E <= 0 || E > 8)
     return set_error(VB_ERR_INVALID, "vb_moe_sort: bad arguments");
   if (max_rows < ((2 * N + 127) / 128 + 2 * E) * 128)
@@ -255,6 +258,7 @@ extern "C" int vb_moe_sort(const int32_t* idx_c, const int32_t* idx_a, const flo
 
 extern "C" int vb_gather_rows(const void* x, const int32_t* row_map, const int32_t* m_tiles_used,
                               int n_tokens, int D, void* out, int max_rows, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_MOE_SORT, stream);
   if (!x || !row_map || !out || D % 8 != 0) return set_error(VB_ERR_INVALID, "vb_gather_rows: bad arguments");
   gather_rows_kernel<<<(max_rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), row_map, m_tiles_used, n_tokens, D,

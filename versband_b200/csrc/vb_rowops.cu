@@ -222,6 +222,7 @@ extern "C" int vb_norm_mod(int kind, const float* x, const float* w, const float
                            const float* shift, const float* scale, int64_t mod_ld,
                            int rows_per_batch, float eps, void* out_bf16, float* out_f32, int rows,
                            int D, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_NORM, stream);
   if (!x || rows <= 0 || D <= 0 || D % 4 != 0 || (!out_bf16 && !out_f32))
     return set_error(VB_ERR_INVALID, "vb_norm_mod: bad arguments (D must be a multiple of 4)");
   if (rows_per_batch <= 0) rows_per_batch = rows;
@@ -239,6 +240,7 @@ extern "C" int vb_norm_mod(int kind, const float* x, const float* w, const float
 
 extern "C" int vb_softmax_rows(const float* S, int64_t lds, void* P, int64_t ldp, int64_t rows,
                                int n, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_SOFTMAX, stream);
   if (!S || !P || rows <= 0 || n <= 0 || ldp < n)
     return set_error(VB_ERR_INVALID, "vb_softmax_rows: bad arguments");
   const int wpb = 8;
@@ -252,6 +254,7 @@ extern "C" int vb_attn_smallkv(const void* q, int64_t q_sb, int64_t q_st, int64_
                                const float* K, const float* V, int64_t kv_ld, int B, int T, int H,
                                int hd, int L, float scale, const float* gate, const float* base, void* out_bf16,
                                float* out_f32, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_ATTN_SMALL, stream);
   if (!q || !K || !V || L <= 0 || L > 128 || (!out_bf16 && !out_f32))
     return set_error(VB_ERR_INVALID, "vb_attn_smallkv: bad arguments (L must be <= 128)");
   if (hd != 96 && hd != 64 && hd != 128)
@@ -261,8 +264,12 @@ extern "C" int vb_attn_smallkv(const void* q, int64_t q_sb, int64_t q_st, int64_
   dim3 grid((T + tpb - 1) / tpb, H, B);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   auto go = [&](auto kern) -> int {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "attn_smallkv smem attr: %s", cudaGetErrorString(e));
+    static size_t attr_smem = 0;  // one per instantiation of this generic lambda
+    if (smem > attr_smem) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "attn_smallkv smem attr: %s", cudaGetErrorString(e));
+      attr_smem = smem;
+    }
     kern<<<grid, threads, smem, s>>>(static_cast<const __nv_bfloat16*>(q), q_sb, q_st, q_sh, K, V, kv_ld, L,
                                      H, T, scale, gate, base, static_cast<__nv_bfloat16*>(out_bf16),
                                      out_f32, tpb);
@@ -275,6 +282,7 @@ extern "C" int vb_attn_smallkv(const void* q, int64_t q_sb, int64_t q_st, int64_
 
 extern "C" int vb_timestep_embed(const int64_t* t, const float* freqs, float* out_f32,
                                  void* out_bf16, int B, int dim, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_EW, stream);
   if (!t || !freqs || B <= 0 || dim <= 0 || dim % 2) return set_error(VB_ERR_INVALID, "vb_timestep_embed: bad arguments");
   const int n = B * dim / 2;
   timestep_embed_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -295,6 +303,7 @@ __global__ void mean_tokens_kernel(const float* __restrict__ x, int L, int D, fl
 }  // namespace vb
 
 extern "C" int vb_mean_tokens(const float* x, int B, int L, int D, float* out, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_EW, stream);
   if (!x || !out || B <= 0 || L <= 0) return set_error(VB_ERR_INVALID, "vb_mean_tokens: bad arguments");
   mean_tokens_kernel<<<dim3((D + 127) / 128, B), 128, 0, static_cast<cudaStream_t>(stream)>>>(x, L, D, out);
   return check_launch("vb_mean_tokens");

@@ -48,6 +48,28 @@ class DiTCond:
     kv_y: List[torch.Tensor] = field(default_factory=list)    # per block fp32 [B*L, 2D] text cross-attn K|V
     kv_m: List[torch.Tensor] = field(default_factory=list)    # per block fp32 [B*L, 2D] MoE MHA K|V
 
+    def tensors(self) -> List[torch.Tensor]:
+        return [self.acoustic, self.ac_logits, self.caption, self.cap_emb, *self.kv_y, *self.kv_m]
+
+    @staticmethod
+    def cat(conds: "List[DiTCond]") -> "DiTCond":
+        """Stack conditioning branches along the batch axis (cond first, then uncond)."""
+        c0 = conds[0]
+        D = c0.acoustic.shape[-1]
+        out = DiTCond(B=sum(c.B for c in conds), T=c0.T, L=c0.L,
+                      acoustic=torch.cat([c.acoustic for c in conds], 0),
+                      ac_logits=torch.cat([c.ac_logits for c in conds], 0),
+                      caption=torch.cat([c.caption for c in conds], 0),
+                      cap_emb=torch.cat([c.cap_emb for c in conds], 0))
+        for k in range(len(c0.kv_y)):
+            out.kv_y.append(torch.cat([c.kv_y[k] for c in conds], 0))
+            out.kv_m.append(torch.cat([c.kv_m[k] for c in conds], 0))
+        return out
+
+    def copy_from(self, other: "DiTCond") -> None:
+        for dst, src in zip(self.tensors(), other.tensors()):
+            dst.copy_(src)
+
 
 class DiTEngine:
     """Holds the packed weights of one TxtFlagLargeImprovedDiTV2 and runs it on the GPU."""
@@ -250,8 +272,9 @@ class DiTEngine:
         Returns v as the channels-last GEMM output [N, 32] (first C columns valid) unless `out_v`
         ([B, C, T]) is given, plus lb_loss per block (device tensor)."""
         w, D, H, hd, E, Fh = self.w, self.D, self.H, self.hd, self.E, self.Fh
-        B, C, T = x.shape
-        assert (B, T) == (cond.B, cond.T) and T <= self.max_len
+        Bx, C, T = x.shape
+        B = cond.B
+        assert B % Bx == 0 and T == cond.T and T <= self.max_len
         N, L = B * T, cond.L
         ws = self._workspace(B, T)
         Tp, max_rows = ws["Tp"], ws["max_rows"]
@@ -259,7 +282,8 @@ class DiTEngine:
         aux = []
 
         # stem: proj_in conv (k5) + bias, fused "+ acoustic"  (vocal2music_moe.py:395,415)
-        ops.nct_to_ntc(x.contiguous(), ws["x_cl"])
+        for r in range(B // Bx):  # CFG batching: the same latent feeds every conditioning branch
+            ops.nct_to_ntc(x.contiguous(), ws["x_cl"][r * Bx:(r + 1) * Bx])
         ops.gemm(ws["x_cl"][:, :, :C], w["proj_in_w"], M=T, G1=B, kpt=1, dil=1, pad=self.proj_in_k // 2,
                  a_c2=(1, 0), bias=w["proj_in_b"], residual=cond.acoustic, out_f32=ws["x"], out_ld=D,
                  out_g=(T * D, 0))
