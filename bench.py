@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""Benchmark of the AccompBand inference hot path (BASELINE.json metric: 24 kHz audio-seconds per
+wall-second, plus DiT latent-frame evaluations per second).
+
+  python bench.py --gpus N --steps K --warmup W                 # this repo (CUDA, C-ABI kernels)
+  python bench.py --impl reference --gpus N --steps K --warmup W # the reference algorithm on host cores
+
+One "step" = one batch of synthetic 20 s clips through conditioning -> 24-step CFG flow sampler
+(48 DiT evaluations) -> VAE decode -> HiFi-GAN. Workload at N GPUs: `--clips` clips per GPU
+(default 1 = BASELINE configs[1], "25-step sampler, batch 1, 20 s clip, 1xB200"), weak scaling,
+no data-path collective (clips are independent). Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CLIP_SECONDS = 20.0
+T_MEL = 1500
+T_LAT = 750
+N_EVALS = 48  # 24 Euler steps x (cond, uncond)
+# Algorithmic FLOPs per 20 s clip: 48 x 51.0 + 22 (sampler) + 160.3 (VAE) + 848.5 (HiFi-GAN)
+FLOP_SAMPLER = 48 * 51.0e9 + 22e9
+FLOP_VAE = 160.3e9
+FLOP_VOC = 848.5e9
+FLOP_CLIP = FLOP_SAMPLER + FLOP_VAE + FLOP_VOC
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def synth_weights():
+    from oracle import synth
+    return (synth.synth_state_dict(synth.load_manifest("dit"), seed=1234),
+            synth.synth_state_dict(synth.load_manifest("vae"), seed=2345),
+            synth.synth_state_dict(synth.load_manifest("hifigan"), seed=3456, gain=synth.HIFIGAN_GAIN))
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference algorithm on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_reference_step(sds, euler_steps: int = 2, seed: int = 0):
+    """Bounded sample of one clip on the CPU: `euler_steps` of the 24 Euler steps (2 DiT evals each,
+    dense experts as in the reference) + full VAE decode + full HiFi-GAN; the sampler time is
+    extrapolated to 24 steps. Returns (seconds per clip, breakdown)."""
+    from oracle import accompband_ref as R, synth
+    torch.set_grad_enabled(False)
+    x, midi, beats, cap_c, cap_u = synth.dit_inputs(1, T_LAT, seed=seed)
+    ctx_c = {"c_crossattn": cap_c, "c_concat": {"midi": midi, "beats": beats}}
+    ctx_u = {"c_crossattn": cap_u, "c_concat": {"midi": midi, "beats": beats}}
+    sched = R.euler_schedule(25)[:euler_steps]
+    t0 = time.perf_counter()
+    for t_long, dt in sched:
+        t = torch.full((1,), t_long, dtype=torch.long)
+        e_c, _ = R.dit_forward(sds[0], x, t, ctx_c, depth=4, n_heads=8)
+        e_u, _ = R.dit_forward(sds[0], x, t, ctx_u, depth=4, n_heads=8)
+        x = x + dt * (e_u + 3.0 * (e_c - e_u))
+    t1 = time.perf_counter()
+    mel = R.vae_decode(sds[1], x, synth.VAE_DDCONFIG)
+    t2 = time.perf_counter()
+    wav = R.hifigan_forward(sds[2], mel, synth.HIFIGAN_CFG)
+    t3 = time.perf_counter()
+    assert wav.shape[-1] == T_MEL * 320
+    sampler = (t1 - t0) * (24.0 / euler_steps)
+    return sampler + (t2 - t1) + (t3 - t2), {"sampler_s": sampler, "vae_s": t2 - t1, "vocoder_s": t3 - t2}
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sds = synth_weights()
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_reference_step(sds, euler_steps=1)
+    times = []
+    brk = {}
+    for i in range(args.steps):
+        s, brk = cpu_reference_step(sds, euler_steps=2, seed=i)
+        times.append(s)
+    sec = sum(times) / len(times)
+    value = CLIP_SECONDS / sec
+    sample = ("1 clip: 2 of 24 Euler steps (4 dense DiT evals, x12 extrapolated) + full VAE decode + full HiFi-GAN, "
+              "fp32 torch CPU oracle port")
+    line = {
+        "impl": "reference", "metric": "audio_sec_per_wall_sec", "value": value,
+        "unit": "x real-time (24 kHz audio-s / wall-s)", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"AccompBand 25-point (24-step) CFG flow sampler + VAE decode + HiFi-GAN, 1 clip of 20 s, host CPU",
+                   "clips_per_gpu": 1, "guidance": 3.0},
+        "dit_latent_frame_evals_per_s": T_LAT * N_EVALS / brk["sampler_s"],
+        "cpu_baseline": {"value": value, "unit": "x real-time", "cores": cores, "kind": "port", "sample": sample,
+                         "breakdown_s": brk},
+        "e2e": {"value": value, "unit": "x real-time (24 kHz audio-s / wall-s)", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_ours(args):
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — versband_b200 has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from oracle import synth
+    from versband_b200 import _lib
+    from versband_b200.pipeline import AccompBandPipeline
+
+    sds = synth_weights()
+    pipe = AccompBandPipeline(*sds, dit_cfg=synth.DIT_CFG, ddconfig=synth.VAE_DDCONFIG,
+                              embed_dim=synth.VAE_EMBED_DIM, voc_cfg=synth.HIFIGAN_CFG, device=dev)
+    B = args.clips
+    # per-clip seeding (not per rank): clip c of the job is the same whatever the GPU count
+    x0, midi, beats, cap_c, cap_u = [], [], [], [], []
+    for c in range(B):
+        gid = rank * B + c
+        a = synth.dit_inputs(1, T_LAT, seed=1000 + gid)
+        for lst, t in zip((x0, midi, beats, cap_c, cap_u), a):
+            lst.append(t)
+    host = [torch.cat(l, 0).pin_memory() for l in (midi, beats, cap_c, cap_u, x0)]
+    devt = [t.to(dev) for t in host]
+    gen = torch.Generator(device=dev).manual_seed(4242 + rank)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_device(events=None):
+        return pipe.generate(devt[0], devt[1], devt[2], devt[3], x0=devt[4], generator=gen, events=events)
+
+    wav_host = torch.empty(B, T_MEL * 320, dtype=torch.float32, pin_memory=True)
+
+    def step_host():
+        return pipe.generate_host(host[0], host[1], host[2], host[3], x0=host[4], generator=gen, out_wav=wav_host)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+        step_host()
+    # ---- timed region A: inputs resident in HBM (value) ----
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    tot_ms, samp_ms, vae_ms, voc_ms = 0.0, 0.0, 0.0, 0.0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        ev = {}
+        step_device(ev)
+        torch.cuda.synchronize()
+        tot_ms += ev["start"].elapsed_time(ev["end"])
+        samp_ms += ev["sampler_start"].elapsed_time(ev["sampler_end"])
+        vae_ms += ev["sampler_end"].elapsed_time(ev["vae_end"])
+        voc_ms += ev["vae_end"].elapsed_time(ev["end"])
+    barrier()
+    # ---- timed region B: host buffers in/out through the public call (e2e) ----
+    e2e_ms = 0.0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step_host()
+        b.record()
+        torch.cuda.synchronize()
+        e2e_ms += a.elapsed_time(b)
+    barrier()
+    clk = clocks.stop()
+    t = torch.tensor([tot_ms, samp_ms, vae_ms, voc_ms, e2e_ms], device=dev, dtype=torch.float64) / args.steps
+    if use_dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
+    ms_step, ms_samp, ms_vae, ms_voc, ms_e2e = [float(v) for v in t]
+
+    # ---- instrumented eager pass (rank 0): per-family kernel time by CUDA events, launch count ----
+    roof, launches, fam = None, None, None
+    if rank == 0:
+        import json as _json
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = _json.load(f)
+        except Exception:
+            pass
+        peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+        peak_src = "measured sustained (MEASURED_PEAKS.json)" if peaks else "fallback 1.4 PF sustained"
+        from versband_b200.sampler import FlowSampler
+        saved = pipe.sampler
+        pipe.sampler = FlowSampler(pipe.dit, use_graph=False)
+        step_device()
+        n0 = _lib.launch_count()
+        _lib.prof_enable(True)
+        step_device()
+        fam = _lib.prof_report()
+        _lib.prof_enable(False)
+        launches = _lib.launch_count() - n0
+        pipe.sampler = saved
+        gemm_ms = fam["gemm"]["ms"]
+        n_gemm = fam["gemm"]["launches"]
+        achieved = FLOP_CLIP * B / (gemm_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "vb_gemm_kernel<BN> (tcgen05/TMA implicit-GEMM, all launches of one step)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "peak_source": peak_src, "traffic": None,
+                "launches_per_step": n_gemm, "avg_launch_us": gemm_ms * 1e3 / max(n_gemm, 1),
+                "algorithmic_flop_per_step": FLOP_CLIP * B,
+                "kernel_time_share_of_step": gemm_ms / sum(v["ms"] for v in fam.values())}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sec, brk = cpu_reference_step(sds, euler_steps=2)
+        cpu = {"value": CLIP_SECONDS / sec, "unit": "x real-time", "cores": cores, "kind": "port",
+               "sample": "1 clip: 2 of 24 Euler steps (x12 extrapolated) + full VAE decode + full HiFi-GAN, fp32 oracle port",
+               "breakdown_s": brk}
+
+    if rank == 0:
+        clips = B * world
+        audio = clips * CLIP_SECONDS
+        line = {
+            "metric": "audio_sec_per_wall_sec", "value": audio / (ms_step * 1e-3),
+            "unit": "x real-time (24 kHz audio-s / wall-s)", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "AccompBand 25-point (24-step) CFG flow sampler + VAE decode + HiFi-GAN, 20 s clips",
+                       "clips_per_gpu": B, "global_clips": clips, "guidance": 3.0, "t_lat": T_LAT,
+                       "parallelism": f"dp{world}", "precision": "bf16 operands, fp32 accumulate/residual",
+                       "l2": "256 MiB buffer written between timed steps (L2 flush)"},
+            "dit_latent_frame_evals_per_s": clips * T_LAT * N_EVALS / (ms_samp * 1e-3),
+            "stage_ms": {"sampler": ms_samp, "vae_decode": ms_vae, "vocoder": ms_voc},
+            "e2e": {"value": audio / (ms_e2e * 1e-3), "unit": "x real-time (24 kHz audio-s / wall-s)",
+                    "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in host)),
+                    "d2h_bytes_per_step": int(wav_host.numel() * 4)},
+            "gpu_launches": int(launches) * args.steps * 2 if launches else None,
+            "gpu_launches_per_step": int(launches) if launches else None,
+            "kernel_family_ms": {k: round(v["ms"], 3) for k, v in fam.items()} if fam else None,
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
+        }
+        print(json.dumps(line))
+    if use_dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=1, help="clips per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -3,9 +3,9 @@ guidance — reference ldm/models/diffusion/cfm1_audio_sampler.py:87-116 and cfm
 (`Wrapper_cfg`), torchdyn's Euler restated as in SURVEY.md §8c.
 
 B200 specifics: the conditional and unconditional DiT evaluations of a step run as ONE batch of
-2B clips (weights stream from HBM once), the CFG mix + Euler update is one kernel, the Gumbel
-noise of all 48 evaluations is drawn up front with torch's generator in the reference's order,
-and the whole 24-step loop is replayed from a CUDA graph.
+2B clips (weights stream from HBM once), the CFG mix + Euler update is one kernel, and the whole
+24-step loop — including the router's Exp(1) draws, taken from torch's Philox generator with the
+reference's shapes and order — is replayed from a CUDA graph.
 """
 from __future__ import annotations
 
@@ -32,91 +32,100 @@ def euler_schedule(n_points: int = 25) -> List[Tuple[int, float]]:
     return out
 
 
-def draw_router_noise(depth: int, n_tokens: int, E: int, device, generator=None):
-    """One DiT evaluation's Exp(1) draws, shapes/order of vocal2music_moe.py:134,150,151."""
-    out = []
-    for _ in range(depth):
-        out.append(tuple(torch.empty(n_tokens, k, device=device, dtype=F32).exponential_(generator=generator)
-                         for k in (2, E, E)))
-    return out
-
-
 class FlowSampler:
     def __init__(self, dit: DiTEngine, n_points: int = 25, use_graph: bool = True):
         self.dit = dit
         self.sched = euler_schedule(n_points)
         self.use_graph = use_graph
-        self._graphs: Dict[Tuple[int, int, int], dict] = {}
+        self._state: Dict[tuple, dict] = {}
+
+    # ---------------------------------------------------------------- noise
+    def _draw_step(self, st: dict, s: int, generator) -> None:
+        """Exp(1) draws of Euler step s into the static buffers, in the reference's consumption
+        order: cond evaluation then uncond evaluation; per evaluation block 0..depth-1; per block
+        [N,2] (group gate), [N,E] (caption gate), [N,E] (acoustic gate) — vocal2music_moe.py:134,150,151.
+        Each draw is its own `exponential_` call on a contiguous [N,k] view, which consumes the
+        Philox stream exactly like the reference's `torch.empty_like(logits).exponential_()`."""
+        N = st["N"]
+        for br in range(2):
+            rows = slice(br * N, (br + 1) * N)
+            for k in range(self.dit.depth):
+                st["e0"][s, k, rows].exponential_(generator=generator)
+                st["e1"][s, k, rows].exponential_(generator=generator)
+                st["e2"][s, k, rows].exponential_(generator=generator)
 
     def draw_noise(self, B: int, T: int, generator=None) -> torch.Tensor:
-        """[steps, 2 (cond, uncond), depth] draws packed as one tensor [steps, depth, 2*N, 2+2E]
-        (cond rows first) in the reference's consumption order: per step cond forward then
-        uncond forward, per forward block 0..depth-1, per block ([N,2],[N,E],[N,E])."""
+        """All draws of one sampling run as a tensor [steps, depth, 2N, 2+2E] (cond rows first)."""
         d, E, N = self.dit.depth, self.dit.E, B * T
-        buf = torch.empty(len(self.sched), d, 2 * N, 2 + 2 * E, device=self.dit.dev, dtype=F32)
+        st = dict(N=N, e0=torch.empty(len(self.sched), d, 2 * N, 2, device=self.dit.dev, dtype=F32),
+                  e1=torch.empty(len(self.sched), d, 2 * N, E, device=self.dit.dev, dtype=F32),
+                  e2=torch.empty(len(self.sched), d, 2 * N, E, device=self.dit.dev, dtype=F32))
         for s in range(len(self.sched)):
-            for br in range(2):
-                for k, (e0, e1, e2) in enumerate(draw_router_noise(d, N, E, self.dit.dev, generator)):
-                    rows = slice(br * N, (br + 1) * N)
-                    buf[s, k, rows, 0:2] = e0
-                    buf[s, k, rows, 2:2 + E] = e1
-                    buf[s, k, rows, 2 + E:] = e2
-        return buf
+            self._draw_step(st, s, generator)
+        return torch.cat([st["e0"], st["e1"], st["e2"]], -1)
 
-    def _run(self, x: torch.Tensor, cond2: DiTCond, noise: torch.Tensor, scale: float, t_all: torch.Tensor):
-        d, E = self.dit.depth, self.dit.E
-        N2 = cond2.B * cond2.T
-        N = N2 // 2
+    # ---------------------------------------------------------------- loop body
+    def _run(self, st: dict, scale: float, rng: bool, generator) -> None:
+        d = self.dit.depth
+        x, cond2, N = st["x"], st["cond2"], st["N"]
         for s, (_, dt) in enumerate(self.sched):
-            # noise rows are stored [2N, 2+2E]; the kernels want dense [2N,2],[2N,E],[2N,E]
-            expo = [(self._e0[s, k], self._e1[s, k], self._e2[s, k]) for k in range(d)]
-            v, _ = self.dit.forward(x, t_all[s], cond2, expo)
+            if rng:
+                self._draw_step(st, s, generator)
+            expo = [(st["e0"][s, k], st["e1"][s, k], st["e2"][s, k]) for k in range(d)]
+            v, _ = self.dit.forward(x, st["t_all"][s], cond2, expo)
             ops.ntc_to_nct(v[:N], x, e_u=v[N:], ld=v.shape[-1], s=scale, dt=dt)
 
     @torch.no_grad()
     def sample_cfg(self, x0: torch.Tensor, cond: DiTCond, uncond: DiTCond, scale: float,
                    noise: Optional[torch.Tensor] = None, generator=None) -> torch.Tensor:
-        """x0 fp32 [B, C, T] -> x1 [B, C, T]. `noise` from draw_noise(); drawn here if None."""
-        dev = self.dit.dev
+        """x0 fp32 [B, C, T] -> x1 [B, C, T].  With `noise` (from draw_noise) the run is a pure
+        function of its arguments; otherwise the draws come from `generator` (default CUDA
+        generator if None) inside the replayed graph."""
+        dev, d, E = self.dit.dev, self.dit.depth, self.dit.E
         B, C, T = x0.shape
-        if noise is None:
-            noise = self.draw_noise(B, T, generator)
-        E = self.dit.E
+        N = B * T
+        rng = noise is None
         key = (B, T, cond.L)
-        st = self._graphs.get(key)
+        st = self._state.get(key)
         if st is None:
-            st = dict(x=torch.empty(B, C, T, device=dev, dtype=F32),
-                      cond2=DiTCond.cat([cond, uncond]),
-                      e0=torch.empty(*noise.shape[:3], 2, device=dev, dtype=F32),
-                      e1=torch.empty(*noise.shape[:3], E, device=dev, dtype=F32),
-                      e2=torch.empty(*noise.shape[:3], E, device=dev, dtype=F32),
+            S = len(self.sched)
+            st = dict(N=N, x=torch.empty(B, C, T, device=dev, dtype=F32), cond2=DiTCond.cat([cond, uncond]),
+                      e0=torch.empty(S, d, 2 * N, 2, device=dev, dtype=F32),
+                      e1=torch.empty(S, d, 2 * N, E, device=dev, dtype=F32),
+                      e2=torch.empty(S, d, 2 * N, E, device=dev, dtype=F32),
                       t_all=torch.tensor([[t] * (2 * B) for t, _ in self.sched], device=dev, dtype=torch.int64),
-                      scale=None, graph=None)
-            self._graphs[key] = st
+                      graphs={})
+            self._state[key] = st
         else:
             st["cond2"].copy_from(DiTCond.cat([cond, uncond]))
         st["x"].copy_(x0)
-        st["e0"].copy_(noise[..., 0:2])
-        st["e1"].copy_(noise[..., 2:2 + E])
-        st["e2"].copy_(noise[..., 2 + E:])
-        self._e0, self._e1, self._e2 = st["e0"], st["e1"], st["e2"]
+        if not rng:
+            st["e0"].copy_(noise[..., 0:2])
+            st["e1"].copy_(noise[..., 2:2 + E])
+            st["e2"].copy_(noise[..., 2 + E:])
         if not self.use_graph:
-            self._run(st["x"], st["cond2"], noise, scale, st["t_all"])
-        else:
-            if st["graph"] is None or st["scale"] != scale:
-                # warm-up outside capture (sets kernel attributes, sizes workspaces), then capture
-                self.dit._workspace(2 * B, T)
-                xsave = st["x"].clone()
-                side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
-                    v, _ = self.dit.forward(st["x"], st["t_all"][0], st["cond2"],
-                                            [(st["e0"][0, k], st["e1"][0, k], st["e2"][0, k]) for k in range(self.dit.depth)])
-                torch.cuda.current_stream().wait_stream(side)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._run(st["x"], st["cond2"], noise, scale, st["t_all"])
-                st["graph"], st["scale"] = g, scale
-                st["x"].copy_(xsave)
-            st["graph"].replay()
+            self._run(st, scale, rng, generator)
+            return st["x"].clone()
+        gkey = (rng, float(scale), id(generator) if rng else 0)
+        g = st["graphs"].get(gkey)
+        if g is None:
+            # warm-up one evaluation outside capture (kernel attributes, workspaces), then capture
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for name in ("e0", "e1", "e2"):  # any positive value works for the warm-up
+                    st[name][0].fill_(1.0)
+                self.dit.forward(st["x"], st["t_all"][0], st["cond2"],
+                                 [(st["e0"][0, k], st["e1"][0, k], st["e2"][0, k]) for k in range(d)])
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            if not rng:
+                st["e0"].copy_(noise[..., 0:2]); st["e1"].copy_(noise[..., 2:2 + E]); st["e2"].copy_(noise[..., 2 + E:])
+            g = torch.cuda.CUDAGraph()
+            if rng and generator is not None:
+                g.register_generator_state(generator)
+            with torch.cuda.graph(g):
+                self._run(st, scale, rng, generator)
+            st["graphs"][gkey] = g
+        g.replay()
         return st["x"].clone()
