@@ -76,13 +76,33 @@ def cpu_reference_step(sds, euler_steps: int = 2, seed: int = 0):
     return sampler + (t2 - t1) + (t3 - t2), {"sampler_s": sampler, "vae_s": t2 - t1, "vocoder_s": t3 - t2}
 
 
+def pick_cpu_threads(sds) -> int:
+    """Thread count for the CPU arm: the fastest of {8,16,32,64,all usable cores} on a short DiT
+    evaluation (T_lat=96). os.cpu_count() threads is often far from the best on a shared host."""
+    from oracle import accompband_ref as R, synth
+    torch.set_grad_enabled(False)
+    usable = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    x, midi, beats, cap_c, _ = synth.dit_inputs(1, 96, seed=0)
+    ctx = {"c_crossattn": cap_c, "c_concat": {"midi": midi, "beats": beats}}
+    best, best_t = 1, float("inf")
+    for n in sorted({min(c, usable) for c in (8, 16, 32, 64, usable)}):
+        torch.set_num_threads(n)
+        R.dit_forward(sds[0], x, torch.tensor([1]), ctx, depth=4, n_heads=8)
+        t0 = time.perf_counter()
+        R.dit_forward(sds[0], x, torch.tensor([1]), ctx, depth=4, n_heads=8)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = n, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     sds = synth_weights()
+    cores = pick_cpu_threads(sds)
     for _ in range(max(args.warmup, 0) and 1):
         cpu_reference_step(sds, euler_steps=1)
     times = []
@@ -185,8 +205,27 @@ def run_ours(args):
 
     wav_host = torch.empty(B, T_MEL * 320, dtype=torch.float32, pin_memory=True)
 
+    if use_dist and rank == 0:
+        # single-controller e2e: rank 0 owns the host buffers of ALL clips of the job
+        allc = [[], [], [], [], []]
+        for gid in range(B * world):
+            for lst, t in zip(allc, synth.dit_inputs(1, T_LAT, seed=1000 + gid)):
+                lst.append(t)
+        host_all = [torch.cat(allc[i], 0).pin_memory() for i in (1, 2, 3, 4, 0)]
+        wav_all = torch.empty(B * world, T_MEL * 320, dtype=torch.float32, pin_memory=True)
+
     def step_host():
-        return pipe.generate_host(host[0], host[1], host[2], host[3], x0=host[4], generator=gen, out_wav=wav_host)
+        if not use_dist:
+            return pipe.generate_host(host[0], host[1], host[2], host[3], x0=host[4], generator=gen, out_wav=wav_host)
+        # N > 1: H2D on rank 0 -> NCCL scatter of the clips -> generate -> NCCL gather -> D2H on rank 0
+        from versband_b200.dist import run_data_parallel
+        ins = [t.to(dev, non_blocking=True) for t in host_all] if rank == 0 else None
+        wav = run_data_parallel(
+            lambda loc: pipe.generate(loc[0], loc[1], loc[2], loc[3], x0=loc[4], generator=gen)["wav"],
+            ins, B * world, device=dev)
+        if rank == 0:
+            wav_all.copy_(wav, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
 
     def barrier():
         torch.cuda.synchronize()
@@ -265,8 +304,7 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
+        cores = pick_cpu_threads(sds)
         sec, brk = cpu_reference_step(sds, euler_steps=2)
         cpu = {"value": CLIP_SECONDS / sec, "unit": "x real-time", "cores": cores, "kind": "port",
                "sample": "1 clip: 2 of 24 Euler steps (x12 extrapolated) + full VAE decode + full HiFi-GAN, fp32 oracle port",
@@ -288,8 +326,10 @@ def run_ours(args):
             "stage_ms": {"sampler": ms_samp, "vae_decode": ms_vae, "vocoder": ms_voc},
             "e2e": {"value": audio / (ms_e2e * 1e-3), "unit": "x real-time (24 kHz audio-s / wall-s)",
                     "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in host)),
-                    "d2h_bytes_per_step": int(wav_host.numel() * 4)},
+                    "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in (host_all if use_dist else host))),
+                    "d2h_bytes_per_step": int((wav_all if use_dist else wav_host).numel() * 4),
+                    "path": ("pinned host -> H2D -> NCCL scatter -> generate -> NCCL gather -> D2H (rank 0)" if use_dist
+                             else "pinned host -> H2D -> generate -> D2H")},
             "gpu_launches": int(launches) * args.steps * 2 if launches else None,
             "gpu_launches_per_step": int(launches) if launches else None,
             "kernel_family_ms": {k: round(v["ms"], 3) for k, v in fam.items()} if fam else None,

@@ -1,0 +1,52 @@
+"""world_size-2 gloo test of the data-parallel clip sharding (scatter inputs / gather outputs)."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from versband_b200.dist import run_data_parallel, shard_bounds
+
+
+def test_shard_bounds_cover_everything():
+    for n in (1, 2, 7, 8, 32):
+        for w in (1, 2, 4, 8):
+            spans = [shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def _worker(rank, world, port, n_clips, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    midi = torch.randint(0, 130, (n_clips, 1, 16), generator=g) if rank == 0 else None
+    cap = torch.randn(n_clips, 4, 8, generator=g) if rank == 0 else None
+
+    def fake_pipeline(local):  # per-clip function: result must not depend on the sharding
+        m, c = local
+        return m.float().sum((1, 2))[:, None] + c.sum((1, 2))[:, None] * torch.ones(1, 5)
+
+    out = run_data_parallel(fake_pipeline, [midi, cap] if rank == 0 else None, n_clips)
+    if rank == 0:
+        q.put(out)
+    dist.destroy_process_group()
+
+
+def test_scatter_compute_gather_world2():
+    ctx = mp.get_context("spawn")
+    for n_clips in (5, 2):
+        q = ctx.SimpleQueue()
+        procs = [ctx.Process(target=_worker, args=(r, 2, 29611 + n_clips, n_clips, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        out = q.get()
+        for p in procs:
+            p.join(60)
+            assert p.exitcode == 0
+        g = torch.Generator().manual_seed(0)
+        midi = torch.randint(0, 130, (n_clips, 1, 16), generator=g)
+        cap = torch.randn(n_clips, 4, 8, generator=g)
+        ref = midi.float().sum((1, 2))[:, None] + cap.sum((1, 2))[:, None] * torch.ones(1, 5)
+        assert torch.allclose(out, ref)

@@ -4,3 +4,24 @@ Hand-written CUDA kernels behind a C-ABI library (include/versband.h), driven by
 modules that mirror the reference's nn.Module surfaces. No fallback path exists.
 """
 __version__ = "0.1.0"
+
+
+def install_compat() -> str:
+    """Put the shadow `ldm` / `vocoder` packages first on sys.path so that the reference's YAML
+    `target:` strings instantiate the B200 modules. Returns the inserted path."""
+    import os
+    import sys
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "compat")
+    if path in sys.path:
+        sys.path.remove(path)
+    sys.path.insert(0, path)
+    return path
+
+
+def instantiate_from_config(config: dict):
+    """`{"target": "pkg.mod.Class", "params": {...}}` -> object (reference ldm/util.py:110-125)."""
+    import importlib
+
+    module, cls = config["target"].rsplit(".", 1)
+    return getattr(importlib.import_module(module), cls)(**dict(config.get("params", {}) or {}))

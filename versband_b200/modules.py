@@ -1,0 +1,536 @@
+"""Drop-in `nn.Module` surfaces of the AccompBand hot path.
+
+Same class names, constructor signatures, `forward` signatures and `state_dict` keys/shapes as
+the reference classes that `configs/vocal2music.yaml` instantiates by dotted name:
+
+  ldm.modules.diffusionmodules.vocal2music_moe.TxtFlagLargeImprovedDiTV2   (vocal2music_moe.py:477-520)
+  ldm.models.autoencoder1d.AutoencoderKL                                    (autoencoder1d.py:14-58)
+  vocoder.hifigan.hifigan.HifiGAN                                           (vocoder/hifigan/hifigan.py:6-42)
+
+The parameter trees below exist only to own the weights under the reference's names (so a
+reference checkpoint loads with `load_state_dict`); all arithmetic runs in libversband_sm100
+through the engines (dit.py / vae.py / vocoder.py). There is no PyTorch-op fallback: calling
+`forward` without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import glob
+import os
+import re
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .sampler import FlowSampler
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: versband_b200 runs on sm_100 GPUs only (no CPU fallback); "
+                           "move the module and its inputs to a CUDA device")
+
+
+def _param_version(mod: nn.Module):
+    return tuple((p.data_ptr(), p._version) for p in mod.parameters())
+
+
+# ==========================================================================================
+# DiT
+# ==========================================================================================
+def _ffn_hidden(dim: int, hidden_dim: int, multiple_of: int = 256) -> int:
+    """FeedForward hidden size rule (flag_large_dit_moe.py:462-468)."""
+    h = int(2 * hidden_dim / 3)
+    return multiple_of * ((h + multiple_of - 1) // multiple_of)
+
+
+class _SwiGLUParams(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.w1 = nn.Linear(dim, hidden, bias=False)
+        self.w2 = nn.Linear(hidden, dim, bias=False)
+        self.w3 = nn.Linear(dim, hidden, bias=False)
+
+
+class _MoEParams(nn.Module):
+    """Parameter names of `MoE` (vocal2music_moe.py:36-79)."""
+
+    def __init__(self, dim, num_experts):
+        super().__init__()
+        hidden = _ffn_hidden(dim, dim)
+        ids = [str(i) for i in range(num_experts)]
+        self.high_level_gating_network = nn.Linear(dim, 2)
+        self.caption_experts = nn.ModuleDict({i: _SwiGLUParams(dim, hidden) for i in ids})
+        self.acoustic_experts = nn.ModuleDict({i: _SwiGLUParams(dim, hidden) for i in ids})
+        self.caption_gating_network = nn.Linear(dim, num_experts)
+        self.acoustic_gating_network = nn.Linear(dim, num_experts)
+        self.freq_experts = nn.ModuleDict({i: _SwiGLUParams(dim, hidden) for i in ids})
+        self.cross_attention = nn.MultiheadAttention(embed_dim=dim, num_heads=8, batch_first=True)
+        self.temperature = 2.0
+        self.num_experts = num_experts
+
+
+class _AttentionParams(nn.Module):
+    def __init__(self, dim, n_heads, y_dim):
+        super().__init__()
+        for name, cin in (("wq", dim), ("wk", dim), ("wv", dim), ("wk_y", y_dim), ("wv_y", y_dim), ("wo", dim)):
+            setattr(self, name, nn.Linear(cin, dim, bias=False))
+        self.gate = nn.Parameter(torch.zeros(n_heads))
+
+
+class _NormWeight(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim))
+
+
+class _BlockParams(nn.Module):
+    def __init__(self, dim, n_heads, y_dim, num_experts):
+        super().__init__()
+        self.attention = _AttentionParams(dim, n_heads, y_dim)
+        self.feed_forward = _MoEParams(dim, num_experts)
+        self.attention_norm = _NormWeight(dim)
+        self.ffn_norm = _NormWeight(dim)
+        self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(dim, 6 * dim, bias=True))
+        self.attention_y_norm = _NormWeight(y_dim)
+
+
+class _MLP(nn.Module):
+    def __init__(self, *layers):
+        super().__init__()
+        self.mlp = nn.Sequential(*layers)
+
+
+class _FinalLayerParams(nn.Module):
+    def __init__(self, dim, out_channels):
+        super().__init__()
+        self.norm_final = nn.LayerNorm(dim, elementwise_affine=False, eps=1e-6)
+        self.linear = nn.Linear(dim, out_channels, bias=True)
+        self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(dim, 2 * dim, bias=True))
+
+
+class TxtFlagLargeImprovedDiTV2(nn.Module):
+    """AccompBand DiT with Band-MoE. forward(x, t, context) -> (v, lb_loss) exactly like the
+    reference (vocal2music_moe.py:375-434); inference only."""
+
+    def __init__(self, in_channels, context_dim, hidden_size=1152, depth=28, num_heads=16, max_len=1000,
+                 num_experts=4, ori_dim=1024):
+        super().__init__()
+        D = hidden_size
+        self.in_channels = self.out_channels = in_channels
+        self.num_heads, self.hidden_size, self.num_experts = num_heads, D, num_experts
+        self.depth, self.max_len, self.context_dim = depth, max_len, context_dim
+        # the reference accepts `ori_dim` but does not forward it (vocal2music_moe.py:489-491):
+        # c_embedder is always sized by the base-class default 1024.
+        self.ori_dim = 1024
+        k = 5
+        self.t_embedder = _MLP(nn.Linear(256, D), nn.SiLU(), nn.Linear(D, D))
+        self.proj_in = nn.Conv1d(in_channels, D, k, padding=k // 2)
+        self.code_proj = nn.Sequential(nn.Conv1d(in_channels, D, k, padding=k // 2), nn.LeakyReLU(), nn.AvgPool1d(2))  # unused (:330-334)
+        self.midi_embedding = nn.Embedding(130, D)
+        self.beats_embedding = nn.Embedding(3, D)
+        self.midi_proj = nn.Sequential(nn.Conv1d(D, D, k, padding=k // 2), nn.LeakyReLU(), nn.AvgPool1d(2))
+        self.beats_proj = nn.Sequential(nn.Conv1d(D, D, k, padding=k // 2), nn.LeakyReLU(), nn.AvgPool1d(2))
+        self.blocks = nn.ModuleList([_BlockParams(D, num_heads, context_dim, num_experts) for _ in range(depth)])
+        self.final_proj = nn.Conv1d(D, D, 1)
+        self.final_layer = _FinalLayerParams(D, in_channels)
+        self.cap_embedder = nn.Sequential(nn.LayerNorm(context_dim), nn.Linear(context_dim, D, bias=True))
+        self.c_embedder = _MLP(nn.Linear(self.ori_dim, D), nn.GELU(), nn.Linear(D, D), nn.LayerNorm(D))
+        self.loss_w = 1
+        self.initialize_weights()
+        self._engine = None
+        self._engine_key = None
+        self._cond_cache: List[tuple] = []
+
+    def initialize_weights(self):
+        """Same initial state as the reference (vocal2music_moe.py:496-518): xavier linears,
+        zeroed adaLN / output layers ⇒ the freshly constructed network is the zero map."""
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+        nn.init.normal_(self.t_embedder.mlp[0].weight, std=0.02)
+        nn.init.normal_(self.t_embedder.mlp[2].weight, std=0.02)
+        for blk in self.blocks:
+            nn.init.constant_(blk.adaLN_modulation[-1].weight, 0)
+            nn.init.constant_(blk.adaLN_modulation[-1].bias, 0)
+        for p in (self.final_layer.adaLN_modulation[-1].weight, self.final_layer.adaLN_modulation[-1].bias,
+                  self.final_layer.linear.weight, self.final_layer.linear.bias):
+            nn.init.constant_(p, 0)
+
+    # ---- engine management -------------------------------------------------------------
+    def engine(self):
+        from .dit import DiTEngine
+        key = _param_version(self)
+        if self._engine is None or key != self._engine_key:
+            dev = next(self.parameters()).device
+            _require_cuda(next(self.parameters()), "TxtFlagLargeImprovedDiTV2")
+            self._engine = DiTEngine({k: v for k, v in self.state_dict().items()}, in_channels=self.in_channels,
+                                     hidden_size=self.hidden_size, depth=self.depth, num_heads=self.num_heads,
+                                     num_experts=self.num_experts, ori_dim=self.ori_dim, max_len=self.max_len,
+                                     temperature=float(self.blocks[0].feed_forward.temperature), device=dev)
+            self._engine_key = key
+            self._cond_cache.clear()
+        return self._engine
+
+    def _cond(self, eng, midi, beats, caption, T):
+        """Step-invariant conditioning, memoised on the identity of the context tensors: the
+        reference's sampler calls forward 48x with the same two context dicts (cfm1_audio.py:158-159)."""
+        key = (midi.data_ptr(), midi._version, beats.data_ptr(), beats._version, caption.data_ptr(),
+               caption._version, tuple(caption.shape), T)
+        for k, c in self._cond_cache:
+            if k == key:
+                return c
+        c = eng.prepare(midi, beats, caption, T)
+        self._cond_cache.append((key, c))
+        del self._cond_cache[:-4]
+        return c
+
+    @torch.no_grad()
+    def forward(self, x, t, context):
+        if self.training:
+            raise NotImplementedError("versband_b200 implements the inference path (eval mode) only; "
+                                      "the soft-router training step is SURVEY.md §8f rank 2")
+        _require_cuda(x, "TxtFlagLargeImprovedDiTV2.forward")
+        eng = self.engine()
+        midi, beats = context["c_concat"]["midi"], context["c_concat"]["beats"]
+        caption = context["c_crossattn"]
+        B, _, T = x.shape
+        cond = self._cond(eng, midi, beats, caption.float(), T)
+        # Gumbel noise: same generator, shapes and order as MoE.forward (vocal2music_moe.py:134,150,151)
+        N, E = B * T, self.num_experts
+        expo = [tuple(torch.empty(N, k, device=x.device, dtype=torch.float32).exponential_() for k in (2, E, E))
+                for _ in range(self.depth)]
+        v = torch.empty(B, self.out_channels, T, device=x.device, dtype=torch.float32)
+        _, lb = eng.forward(x.float(), t.long(), cond, expo, out_v=v)
+        loss = lb.sum() / self.depth
+        if self.loss_w > 0.01:  # vocal2music_moe.py:427-429 (decays in eval too)
+            self.loss_w *= 0.9999
+        return v.to(x.dtype), loss * self.loss_w
+
+
+# ==========================================================================================
+# VAE
+# ==========================================================================================
+class DiagonalGaussianDistribution:
+    """Posterior of AutoencoderKL.encode (ldm/modules/distributions/distributions.py:4-43)."""
+
+    def __init__(self, parameters: torch.Tensor):
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+
+    def sample(self):
+        return self.mean + self.std * torch.randn(self.mean.shape, device=self.parameters.device)
+
+    def mode(self):
+        return self.mean
+
+    def kl(self):
+        return 0.5 * torch.sum(torch.pow(self.mean, 2) + self.var - 1.0 - self.logvar, dim=[1, 2])
+
+
+def _gn(c):
+    return nn.GroupNorm(num_groups=32, num_channels=c, eps=1e-6, affine=True)
+
+
+class _ResParams(nn.Module):
+    def __init__(self, cin, cout, k):
+        super().__init__()
+        self.norm1 = _gn(cin)
+        self.conv1 = nn.Conv1d(cin, cout, k, padding=k // 2)
+        self.norm2 = _gn(cout)
+        self.conv2 = nn.Conv1d(cout, cout, k, padding=k // 2)
+        if cin != cout:
+            self.nin_shortcut = nn.Conv1d(cin, cout, 1)
+
+
+class _AttnParams(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.norm = _gn(c)
+        for n in ("q", "k", "v", "proj_out"):
+            setattr(self, n, nn.Conv1d(c, c, 1))
+
+
+class _Resample(nn.Module):
+    def __init__(self, c, stride):
+        super().__init__()
+        self.conv = nn.Conv1d(c, c, 3, stride=stride, padding=1 if stride == 1 else 0)
+
+
+def _mid(c, k):
+    m = nn.Module()
+    m.block_1, m.attn_1, m.block_2 = _ResParams(c, c, k), _AttnParams(c), _ResParams(c, c, k)
+    return m
+
+
+class _Encoder1DParams(nn.Module):
+    """Parameter tree of Encoder1D (autoencoder1d.py:315-382)."""
+
+    def __init__(self, *, ch, ch_mult, num_res_blocks, attn_layers, down_layers, in_channels, z_channels,
+                 double_z=True, kernel_size=3, **_):
+        super().__init__()
+        k = kernel_size
+        self.conv_in = nn.Conv1d(in_channels, ch, k, padding=k // 2)
+        in_mult = (1,) + tuple(ch_mult)
+        self.down = nn.ModuleList()
+        cin = ch
+        for lvl in range(len(ch_mult)):
+            level = nn.Module()
+            level.block, level.attn = nn.ModuleList(), nn.ModuleList()
+            cin, cout = ch * in_mult[lvl], ch * ch_mult[lvl]
+            for _ in range(num_res_blocks):
+                level.block.append(_ResParams(cin, cout, k))
+                cin = cout
+                if lvl in attn_layers:
+                    level.attn.append(_AttnParams(cin))
+            if lvl in down_layers:
+                level.downsample = _Resample(cin, 2)
+            self.down.append(level)
+        self.mid = _mid(cin, k)
+        self.norm_out = _gn(cin)
+        self.conv_out = nn.Conv1d(cin, 2 * z_channels if double_z else z_channels, k, padding=k // 2)
+
+
+class _Decoder1DParams(nn.Module):
+    """Parameter tree of Decoder1D (autoencoder1d.py:411-478): conv_in/out use `kernel_size`,
+    the ResNet blocks use the default k=3 (kernel_size is not forwarded to them, :440-460)."""
+
+    def __init__(self, *, ch, out_ch, ch_mult, num_res_blocks, attn_layers, down_layers, z_channels,
+                 kernel_size=3, **_):
+        super().__init__()
+        k = kernel_size
+        n = len(ch_mult)
+        up_levels = [i + 1 for i in down_layers]
+        cin = ch * ch_mult[n - 1]
+        self.conv_in = nn.Conv1d(z_channels, cin, k, padding=k // 2)
+        self.mid = _mid(cin, 3)
+        ups = []
+        for lvl in reversed(range(n)):
+            level = nn.Module()
+            level.block, level.attn = nn.ModuleList(), nn.ModuleList()
+            cout = ch * ch_mult[lvl]
+            for _ in range(num_res_blocks + 1):
+                level.block.append(_ResParams(cin, cout, 3))
+                cin = cout
+                if lvl in attn_layers:
+                    level.attn.append(_AttnParams(cin))
+            if lvl in up_levels:
+                level.upsample = _Resample(cin, 1)
+            ups.insert(0, level)
+        self.up = nn.ModuleList(ups)
+        self.norm_out = _gn(cin)
+        self.conv_out = nn.Conv1d(cin, out_ch, k, padding=k // 2)
+
+
+class AutoencoderKL(nn.Module):
+    """1-D KL autoencoder: encode(x) -> DiagonalGaussianDistribution, decode(z) -> mel."""
+
+    def __init__(self, embed_dim, ddconfig, lossconfig=None, ckpt_path=None, ignore_keys=[], image_key="image",
+                 monitor=None):
+        super().__init__()
+        dd = dict(ddconfig)
+        assert dd["double_z"]
+        self.image_key = image_key
+        # plain python containers (the YAML loader may hand us OmegaConf lists)
+        self.ddconfig = {k: (list(v) if hasattr(v, "__iter__") and not isinstance(v, str) else v) for k, v in dd.items()}
+        self.encoder = _Encoder1DParams(**self.ddconfig)
+        self.decoder = _Decoder1DParams(**self.ddconfig)
+        self.loss = nn.Identity()  # configs/vocal2music.yaml:68-69 (training losses are out of scope)
+        self.quant_conv = nn.Conv1d(2 * dd["z_channels"], 2 * embed_dim, 1)
+        self.post_quant_conv = nn.Conv1d(embed_dim, dd["z_channels"], 1)
+        self.embed_dim = embed_dim
+        if monitor is not None:
+            self.monitor = monitor
+        self._engine = None
+        self._engine_key = None
+        if ckpt_path is not None:
+            self.init_from_ckpt(ckpt_path, ignore_keys=ignore_keys)
+
+    def init_from_ckpt(self, path, ignore_keys=list()):
+        sd = torch.load(path, map_location="cpu")["state_dict"]
+        for k in list(sd.keys()):
+            if any(k.startswith(ik) for ik in ignore_keys):
+                del sd[k]
+        self.load_state_dict(sd, strict=False)
+
+    def engine(self):
+        from .vae import VAEEngine
+        key = _param_version(self)
+        if self._engine is None or key != self._engine_key:
+            p = next(self.parameters())
+            _require_cuda(p, "AutoencoderKL")
+            self._engine = VAEEngine(dict(self.state_dict()), self.ddconfig, self.embed_dim, device=p.device)
+            self._engine_key = key
+        return self._engine
+
+    @torch.no_grad()
+    def encode(self, x):
+        _require_cuda(x, "AutoencoderKL.encode")
+        return DiagonalGaussianDistribution(self.engine().encode_moments(x.float()))
+
+    @torch.no_grad()
+    def decode(self, z):
+        _require_cuda(z, "AutoencoderKL.decode")
+        return self.engine().decode(z.float())
+
+    def forward(self, input, sample_posterior=True):
+        posterior = self.encode(input)
+        z = posterior.sample() if sample_posterior else posterior.mode()
+        return self.decode(z), posterior
+
+
+# ==========================================================================================
+# HiFi-GAN
+# ==========================================================================================
+def _wn_conv(cin, cout, k, transposed=False, **kw):
+    conv = (nn.ConvTranspose1d if transposed else nn.Conv1d)(cin, cout, k, **kw)
+    return torch.nn.utils.weight_norm(conv)  # old-style: weight_g / weight_v keys, as in the reference
+
+
+class _ResBlock1Params(nn.Module):
+    def __init__(self, ch, k, dilations):
+        super().__init__()
+        self.convs1 = nn.ModuleList([_wn_conv(ch, ch, k, dilation=d, padding=(k * d - d) // 2) for d in dilations])
+        self.convs2 = nn.ModuleList([_wn_conv(ch, ch, k, padding=(k - 1) // 2) for _ in dilations])
+
+
+class HifiGanGenerator(nn.Module):
+    """Parameter tree + GPU forward of HifiGanGenerator (vocoder/hifigan/modules/hifigan.py:101-143)."""
+
+    def __init__(self, h, c_out=1):
+        super().__init__()
+        import warnings
+        self.h = dict(h)
+        assert str(h["resblock"]) == "1", "only ResBlock1 generators are implemented"
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            c0 = h["upsample_initial_channel"]
+            self.conv_pre = _wn_conv(80, c0, 7, padding=3)
+            self.ups = nn.ModuleList()
+            self.resblocks = nn.ModuleList()
+            for i, (u, k) in enumerate(zip(h["upsample_rates"], h["upsample_kernel_sizes"])):
+                c = c0 // (2 ** (i + 1))
+                self.ups.append(_wn_conv(2 * c, c, k, transposed=True, stride=u, padding=(k - u) // 2))
+                for kk, dd in zip(h["resblock_kernel_sizes"], h["resblock_dilation_sizes"]):
+                    self.resblocks.append(_ResBlock1Params(c, kk, dd))
+            self.conv_post = _wn_conv(c, c_out, 7, padding=3)
+        self._engine = None
+        self._engine_key = None
+
+    def engine(self):
+        from .vocoder import HifiGanEngine
+        key = _param_version(self)
+        if self._engine is None or key != self._engine_key:
+            p = next(self.parameters())
+            _require_cuda(p, "HifiGanGenerator")
+            self._engine = HifiGanEngine(dict(self.state_dict()), self.h, device=p.device)
+            self._engine_key = key
+        return self._engine
+
+    @torch.no_grad()
+    def forward(self, x, f0=None):
+        """mel [B, 80, T] -> wav [B, 1, T*hop]"""
+        _require_cuda(x, "HifiGanGenerator.forward")
+        return self.engine().forward(x.float()).unsqueeze(1)
+
+
+def _load_yaml_with_bases(path: str) -> dict:
+    """Minimal `set_hparams`: YAML with recursive `base_config` inheritance (utils/commons/hparams.py:25-133)."""
+    import yaml
+    with open(path) as f:
+        cfg = yaml.safe_load(f) or {}
+    out: dict = {}
+    bases = cfg.get("base_config", [])
+    for b in ([bases] if isinstance(bases, str) else bases):
+        bp = b if os.path.isabs(b) or os.path.exists(b) else os.path.join(os.path.dirname(path), b)
+        out.update(_load_yaml_with_bases(bp))
+    out.update({k: v for k, v in cfg.items() if k != "base_config"})
+    return out
+
+
+def _load_generator_ckpt(model: nn.Module, base_dir: str, key: str = "model_gen") -> None:
+    """Newest `model_ckpt_steps_*.ckpt` under base_dir, sub-dict `key` (utils/commons/ckpt_utils.py:7-67)."""
+    paths = sorted(glob.glob(os.path.join(base_dir, "model_ckpt_steps_*.ckpt")),
+                   key=lambda p: int(re.findall(r"steps_(\d+)\.ckpt", p)[0]))
+    if not paths:
+        raise FileNotFoundError(f"no model_ckpt_steps_*.ckpt under {base_dir}")
+    sd = torch.load(paths[-1], map_location="cpu")["state_dict"]
+    if key in sd:
+        sd = sd[key]
+    else:
+        sd = {k[len(key) + 1:]: v for k, v in sd.items() if k.startswith(key + ".")}
+    model.load_state_dict(sd, strict=True)
+
+
+class HifiGAN(nn.Module):
+    """Vocoder wrapper with the reference's call surface: `__call__(mel[T,80]) -> np.float32[T*hop]`,
+    `spec2wav`, `vocode` (vocoder/hifigan/hifigan.py:6-42)."""
+
+    def __init__(self, vocoder_ckpt, device=None, config: Optional[dict] = None, state_dict: Optional[dict] = None):
+        super().__init__()
+        if config is None:
+            config = _load_yaml_with_bases(os.path.join(vocoder_ckpt, "config.yaml"))
+        self.config = config
+        self.device = torch.device(device) if device is not None else torch.device("cuda")
+        self.model = HifiGanGenerator(config)
+        if state_dict is not None:
+            self.model.load_state_dict(state_dict, strict=True)
+        elif vocoder_ckpt is not None:
+            _load_generator_ckpt(self.model, vocoder_ckpt, "model_gen")
+        self.model.to(self.device)
+        self.model.eval()
+
+    def spec2wav(self, mel, **kwargs):
+        with torch.no_grad():
+            c = torch.as_tensor(np.asarray(mel) if not isinstance(mel, torch.Tensor) else mel, dtype=torch.float32)
+            c = c.unsqueeze(0).to(self.device).transpose(2, 1)  # [1, T, C] -> [1, C, T]
+            y = self.model(c).view(-1)
+        return y.cpu().numpy()
+
+    def __call__(self, mel):
+        return self.spec2wav(mel)
+
+    def vocode(self, mel):
+        assert len(mel.shape) == 2
+        with torch.no_grad():
+            c = torch.as_tensor(np.asarray(mel) if not isinstance(mel, torch.Tensor) else mel, dtype=torch.float32)
+            c = c.unsqueeze(0).to(self.device)
+            if c.shape[1] != 80:
+                c = c.transpose(2, 1)
+            y = self.model(c).view(-1)
+        return y.cpu().numpy()
+
+
+# ==========================================================================================
+# Sampler glue with the reference's call surface (cfm1_audio_sampler.py:87-116)
+# ==========================================================================================
+class CFMSampler:
+    """`sample_cfg(cond, unconditional_guidance_scale, unconditional_conditioning, batch_size, shape)`
+    over a TxtFlagLargeImprovedDiTV2: the fused B200 sampler (CFG-batched, CUDA-graph)."""
+
+    def __init__(self, dit: TxtFlagLargeImprovedDiTV2, num_timesteps: int = 1000, **_):
+        self.dit = dit
+        self._sampler = None
+
+    @torch.no_grad()
+    def sample_cfg(self, cond, unconditional_guidance_scale, unconditional_conditioning, batch_size=16,
+                   timesteps=None, shape=None, x_latent=None, **kwargs):
+        eng = self.dit.engine()
+        if self._sampler is None or self._sampler.dit is not eng:
+            self._sampler = FlowSampler(eng, n_points=25 if timesteps is None else timesteps)
+        dev = eng.dev
+        C, T = shape
+        # reference order of RNG consumption: x0 first (cfm1_audio_sampler.py:113), then the router noise
+        x0 = torch.randn((batch_size, C, T), device=dev) if x_latent is None else x_latent
+        ac = cond["acoustic"]
+        acoustic = eng.prepare_acoustic(ac["midi"], ac["beats"], T)
+        c = eng.prepare(None, None, cond["caption"].float(), T, acoustic=acoustic)
+        u = eng.prepare(None, None, unconditional_conditioning["caption"].float(), T, acoustic=acoustic)
+        x = self._sampler.sample_cfg(x0.float(), c, u, float(unconditional_guidance_scale))
+        return x, [x0, x]
