@@ -118,6 +118,7 @@ typedef struct vb_gemm_args {
   /* ---- VB_EPI_QKV_ROPE: N = 3*heads*head_dim, rows m = b*T + t; v = acc*alpha + bias ---- */
   const float* rope_cs; /* [T][head_dim/2][2] (cos, sin), fp32; NULL = no rotation (VAE attn) */
   int32_t T, heads, head_dim, Tp;
+  int32_t qkv_sec0; /* first section present: 0 = q|k|v (N = 3*H*hd), 1 = k|v only (N = 2*H*hd) */
   void* q_out;  /* bf16 [B, heads, T, head_dim] (rotated) */
   void* k_out;  /* bf16 [B, heads, T, head_dim] (rotated) */
   void* vt_out; /* bf16 [B, heads, head_dim, Tp]  (V transposed: PV GEMM's K-major B) */
@@ -125,7 +126,35 @@ typedef struct vb_gemm_args {
 
 int vb_gemm(const vb_gemm_args* args, void* stream);
 
-/* sizeof() of the public structs as compiled (ABI self-check for bindings): 0 = vb_gemm_args */
+/* ------------------------------------------------------------------------------------------
+ * vb_attn_fused — flash-style attention on tcgen05 (S and O_j in TMEM, P through shared memory).
+ * Replaces Attention.forward's two SDPA calls and the gated add (flag_large_dit_moe.py:381-402)
+ * in one launch, and nn.MultiheadAttention's attention core (vocal2music_moe.py:119):
+ *   out[b*T+t, h*hd:(h+1)*hd] = softmax(q k_self^T * scale) v_self
+ *                              + tanh(gate[h]) * softmax(q k_text^T * scale) v_text
+ * Either segment may be absent (k_self == NULL or k_text == NULL). All operands bf16:
+ *   q        element strides (q_st token, q_sh head, q_sb batch), head_dim contiguous
+ *   k_self   [B, H, T, hd]      vt_self  [B, H, hd, Tp]   (V transposed, Tp % 8 == 0)
+ *   k_text   [B, H, L, hd]      vt_text  [B, H, hd, Lp]   (L <= 128, Lp % 8 == 0)
+ * gate: fp32 [H] (raw, tanh applied inside) or NULL (= 1). head_dim in {64, 96, 128}.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct vb_attn_args {
+  const void* q;
+  int64_t q_st, q_sh, q_sb;
+  const void* k_self;
+  const void* vt_self;
+  const void* k_text;
+  const void* vt_text;
+  const float* gate;
+  void* out_bf16; /* [B*T, H*hd] */
+  float* out_f32; /* optional, same layout */
+  int32_t B, T, H, hd, Tp, L, Lp;
+  float scale;
+} vb_attn_args;
+
+int vb_attn_fused(const vb_attn_args* args, void* stream);
+
+/* sizeof() of the public structs as compiled (ABI self-check for bindings): 0 = vb_gemm_args, 1 = vb_attn_args */
 int vb_sizeof(int which);
 /* number of kernels this library has launched in this process */
 long long vb_launch_count(void);

@@ -36,8 +36,20 @@ class GemmArgs(C.Structure):
         ("out_f32", c_ptr), ("out_ld", c_i64), ("out_g1", c_i64), ("out_g2", c_i64),
         ("out_bf16", c_ptr), ("outb_ld", c_i64), ("outb_g1", c_i64), ("outb_g2", c_i64),
         ("act_out", c_i32), ("act_out_slope", c_f32), ("out_scale", c_f32),
-        ("rope_cs", c_ptr), ("T", c_i32), ("heads", c_i32), ("head_dim", c_i32), ("Tp", c_i32),
+        ("rope_cs", c_ptr), ("T", c_i32), ("heads", c_i32), ("head_dim", c_i32), ("Tp", c_i32), ("qkv_sec0", c_i32),
         ("q_out", c_ptr), ("k_out", c_ptr), ("vt_out", c_ptr),
+    ]
+
+
+class AttnArgs(C.Structure):
+    """Mirror of `struct vb_attn_args`."""
+
+    _fields_ = [
+        ("q", c_ptr), ("q_st", c_i64), ("q_sh", c_i64), ("q_sb", c_i64),
+        ("k_self", c_ptr), ("vt_self", c_ptr), ("k_text", c_ptr), ("vt_text", c_ptr),
+        ("gate", c_ptr), ("out_bf16", c_ptr), ("out_f32", c_ptr),
+        ("B", c_i32), ("T", c_i32), ("H", c_i32), ("hd", c_i32), ("Tp", c_i32), ("L", c_i32), ("Lp", c_i32),
+        ("scale", c_f32),
     ]
 
 
@@ -61,6 +73,9 @@ def lib() -> C.CDLL:
         _lib.vb_launch_count.restype = C.c_longlong
         _lib.vb_gemm.argtypes = [C.POINTER(GemmArgs), c_ptr]
         _declare(_lib)
+        _lib.vb_attn_fused.argtypes = [C.POINTER(AttnArgs), c_ptr]
+        if _lib.vb_sizeof(1) != C.sizeof(AttnArgs):
+            raise VersbandError("vb_attn_args ABI mismatch between versband.h and _lib.py")
         if _lib.vb_sizeof(0) != C.sizeof(GemmArgs):
             raise VersbandError("vb_gemm_args ABI mismatch between versband.h and _lib.py")
     return _lib

@@ -96,6 +96,7 @@ extern "C" int vb_check_device(void) {
 extern "C" int vb_sizeof(int which) {
   switch (which) {
     case 0: return (int)sizeof(vb_gemm_args);
+    case 1: return (int)sizeof(vb_attn_args);
     default: return -1;
   }
 }

@@ -1,0 +1,360 @@
+// vb_attn_fused — flash-style attention on tcgen05/TMEM/TMA for sm_100a.
+//
+// One CTA = 128 query rows of one (batch, head). Key tiles of 128 keys stream through a
+// 2-stage TMA ring; per tile:
+//   MMA1  S = Q K^T        (UMMA 128x128x16, fp32 S in TMEM, double-buffered)
+//   softmax warps: TMEM -> registers, online max/sum, P (bf16) -> swizzled smem
+//   MMA2  O_j = P V        (UMMA 128xHDx16, B operand = V^T tile), TMEM -> registers,
+//                           acc = acc * alpha + O_j   (running output kept in registers)
+// Two KV segments with independent softmax (flag_large_dit_moe.py:381-402):
+//   segment 0: self-attention over T keys            out  = O0 / l0
+//   segment 1: one tile of L <= 128 "text" keys      out += tanh(gate[h]) * O1 / l1
+// With segment 0 disabled the kernel is the MoE cross-attention of vocal2music_moe.py:119.
+//
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer,
+// warps 2..5 softmax/epilogue (thread = query row = TMEM lane).
+#include <math_constants.h>
+#include "vb_internal.h"
+#include "vb_ptx.cuh"
+
+namespace vb {
+
+struct AttnKParams {
+  int T, L, H, n_self;
+  int has_text;
+  float scale;
+  const float* gate;
+  __nv_bfloat16* out_bf16;
+  float* out_f32;
+};
+
+template <int HD>
+struct AttnCfg {
+  static constexpr int kQBytes = 2 * 16384;            // Q tile: 2 k-blocks of [128 x 64] bf16
+  static constexpr int kKBytes = 2 * 16384;            // K tile per stage
+  static constexpr int kVBytes = 2 * HD * 128;         // V^T tile per stage: 2 k-blocks of [HD x 64]
+  static constexpr int kPBytes = 2 * 16384;            // P tile
+  static constexpr int kSmem = kQBytes + 2 * kKBytes + 2 * kVBytes + kPBytes + 1024 + 256;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(192, 1)
+attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKs,
+                  const __grid_constant__ CUtensorMap tmVs, const __grid_constant__ CUtensorMap tmKt,
+                  const __grid_constant__ CUtensorMap tmVt, const AttnKParams p) {
+  using Cfg = AttnCfg<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::kQBytes;          // [2 stages][2 kb][16384]
+  uint8_t* sV = sK + 2 * Cfg::kKBytes;      // [2 stages][2 kb][HD*128]
+  uint8_t* sP = sV + 2 * Cfg::kVBytes;      // [2 kb][16384]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kPBytes);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;    // [2]
+  uint64_t* p_full = bars + 7;
+  uint64_t* o_full = bars + 8;
+  uint64_t* o_empty = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n_self = p.n_self;
+  const int n_tiles = n_self + (p.has_text ? 1 : 0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+    }
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_O = tmem_base + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, HD > 64 ? Cfg::kQBytes : 16384);
+      tma_load_4d(sQ, &tmQ, q_full, 0, q0, h, b);
+      if (HD > 64) tma_load_4d(sQ + 16384, &tmQ, q_full, 64, q0, h, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        const bool text = j >= n_self;
+        const CUtensorMap* mk = text ? &tmKt : &tmKs;
+        const CUtensorMap* mv = text ? &tmVt : &tmVs;
+        const int key0 = text ? 0 : j * 128;
+        mbar_expect_tx(&kv_full[st], (HD > 64 ? Cfg::kKBytes : 16384) + Cfg::kVBytes);
+        uint8_t* k_dst = sK + st * Cfg::kKBytes;
+        uint8_t* v_dst = sV + st * Cfg::kVBytes;
+        tma_load_4d(k_dst, mk, &kv_full[st], 0, key0, h, b);
+        if (HD > 64) tma_load_4d(k_dst + 16384, mk, &kv_full[st], 64, key0, h, b);
+        tma_load_4d(v_dst, mv, &kv_full[st], key0, 0, h, b);
+        tma_load_4d(v_dst + HD * 128, mv, &kv_full[st], key0 + 64, 0, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, HD);
+      mbar_wait(q_full, 0);
+      auto mma1 = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const int kb = k >> 2, off = (k & 3) * 2;
+          const uint64_t da = make_kmajor_sw128_desc(smem_u32(sQ + kb * 16384)) + off;
+          const uint64_t db = make_kmajor_sw128_desc(smem_u32(sK + st * Cfg::kKBytes + kb * 16384)) + off;
+          umma_bf16(tmem_base + st * 128, da, db, idesc_s, k > 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[st]);
+      };
+      mma1(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        if (j + 1 < n_tiles) mma1(j + 1);  // overlaps the softmax of tile j
+        mbar_wait(p_full, j & 1);
+        if (j > 0) mbar_wait(o_empty, (j - 1) & 1);
+        tc_fence_after();
+        const int keys = (j >= n_self) ? p.L : min(128, p.T - j * 128);
+        const int ksteps = (keys + 15) >> 4;
+        for (int k = 0; k < ksteps; ++k) {
+          const int kb = k >> 2, off = (k & 3) * 2;
+          const uint64_t da = make_kmajor_sw128_desc(smem_u32(sP + kb * 16384)) + off;
+          const uint64_t db = make_kmajor_sw128_desc(smem_u32(sV + st * Cfg::kVBytes + kb * HD * 128)) + off;
+          umma_bf16(tmem_O, da, db, idesc_o, k > 0 ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[st]);
+      }
+    }
+  } else {
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
+    float acc[HD];
+#pragma unroll
+    for (int i = 0; i < HD; ++i) acc[i] = 0.f;
+    float m = -CUDART_INF_F, l = 0.f;
+    const float scale = p.scale;
+    const float g = p.gate ? tanhf(p.gate[h]) : 1.f;
+    const int rsw = row & 7;
+    uint8_t* prow = sP + (row >> 3) * 1024 + rsw * 128;
+    for (int j = 0; j < n_tiles; ++j) {
+      const bool text = j >= n_self;
+      if (text) {
+        if (n_self > 0) {
+          const float inv = 1.f / l;
+#pragma unroll
+          for (int i = 0; i < HD; ++i) acc[i] *= inv;
+        }
+        m = -CUDART_INF_F;
+        l = 0.f;
+      }
+      const int valid = text ? p.L : min(128, p.T - j * 128);
+      const uint32_t tS = tmem_base + (j & 1) * 128 + lane_sel;
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      // pass A: row maximum over the valid keys of this tile
+      float tmax = -CUDART_INF_F;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        if (c * 32 >= valid) break;
+        uint32_t raw[32];
+        tmem_ld32(tS + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i < valid) tmax = fmaxf(tmax, __uint_as_float(raw[i]));
+      }
+      const float m_new = fmaxf(m, tmax * scale);
+      const float alpha = (m == -CUDART_INF_F) ? 0.f : __expf(m - m_new);
+      // pass B: p = exp(s*scale - m_new) -> bf16 -> swizzled smem (A operand of MMA2)
+      float rowsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t packed[16];
+        if (c * 32 < valid) {
+          uint32_t raw[32];
+          tmem_ld32(tS + c * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float p0 = (c * 32 + 2 * i < valid) ? __expf(__uint_as_float(raw[2 * i]) * scale - m_new) : 0.f;
+            float p1 = (c * 32 + 2 * i + 1 < valid) ? __expf(__uint_as_float(raw[2 * i + 1]) * scale - m_new) : 0.f;
+            rowsum += p0 + p1;
+            __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
+            packed[i] = *reinterpret_cast<uint32_t*>(&t);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) packed[i] = 0u;
+        }
+        uint8_t* pk = prow + (c >> 1) * 16384;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ch = (c & 1) * 4 + i;
+          *reinterpret_cast<uint4*>(pk + ((ch ^ rsw) << 4)) =
+              make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+        }
+      }
+      l = l * alpha + rowsum;
+      m = m_new;
+      tc_fence_before();
+      fence_proxy_async();  // make the generic-proxy smem writes visible to the tensor core
+      mbar_arrive(p_full);
+      // O_j
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+      const float f_old = text ? 1.f : alpha;
+      const float f_new = text ? g / l : 1.f;
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_O + lane_sel + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[c * 32 + i] = acc[c * 32 + i] * f_old + __uint_as_float(raw[i]) * f_new;
+      }
+      tc_fence_before();
+      mbar_arrive(o_empty);
+    }
+    if (!p.has_text && n_self > 0) {
+      const float inv = 1.f / l;
+#pragma unroll
+      for (int i = 0; i < HD; ++i) acc[i] *= inv;
+    }
+    const int t = q0 + row;
+    if (t < p.T) {
+      const long long o = ((long long)b * p.T + t) * ((long long)p.H * HD) + (long long)h * HD;
+      if (p.out_bf16) {
+        uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + o);
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i) {
+          __nv_bfloat162 a0 = __floats2bfloat162_rn(acc[8 * i], acc[8 * i + 1]);
+          __nv_bfloat162 a1 = __floats2bfloat162_rn(acc[8 * i + 2], acc[8 * i + 3]);
+          __nv_bfloat162 a2 = __floats2bfloat162_rn(acc[8 * i + 4], acc[8 * i + 5]);
+          __nv_bfloat162 a3 = __floats2bfloat162_rn(acc[8 * i + 6], acc[8 * i + 7]);
+          dst[i] = make_uint4(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1),
+                              *reinterpret_cast<uint32_t*>(&a2), *reinterpret_cast<uint32_t*>(&a3));
+        }
+      }
+      if (p.out_f32) {
+        float4* dst = reinterpret_cast<float4*>(p.out_f32 + o);
+#pragma unroll
+        for (int i = 0; i < HD / 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+static int encode4(CUtensorMap* map, const void* base, const int64_t* dims, const int64_t* strides_el,
+                   uint32_t box0, uint32_t box1) {
+  cuuint64_t gdim[4], gstr[3];
+  cuuint32_t box[4] = {box0, box1, 1, 1}, es[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 4; ++i) gdim[i] = (cuuint64_t)dims[i];
+  for (int i = 1; i < 4; ++i) {
+    gstr[i - 1] = (cuuint64_t)strides_el[i] * 2;
+    if (gstr[i - 1] % 16 != 0 || gstr[i - 1] == 0)
+      return set_error(VB_ERR_INVALID, "vb_attn_fused: stride %lld of dim %d not a positive multiple of 8 elements",
+                       (long long)strides_el[i], i);
+  }
+  if (reinterpret_cast<uintptr_t>(base) & 15) return set_error(VB_ERR_INVALID, "vb_attn_fused: unaligned operand");
+  auto fn = get_tensor_map_encoder();
+  if (!fn) return set_error(VB_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(VB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return VB_OK;
+}
+
+template <int HD>
+static int launch_attn(const vb_attn_args* a, cudaStream_t stream) {
+  using Cfg = AttnCfg<HD>;
+  CUtensorMap tmQ, tmKs, tmVs, tmKt, tmVt;
+  int rc;
+  {
+    int64_t d[4] = {HD, a->T, a->H, a->B};
+    int64_t s[4] = {1, a->q_st, a->q_sh, a->q_sb};
+    if ((rc = encode4(&tmQ, a->q, d, s, 64, 128))) return rc;
+  }
+  const bool self = a->k_self != nullptr;
+  const bool text = a->k_text != nullptr;
+  if (self) {
+    int64_t d[4] = {HD, a->T, a->H, a->B};
+    int64_t s[4] = {1, HD, (int64_t)a->T * HD, (int64_t)a->H * a->T * HD};
+    if ((rc = encode4(&tmKs, a->k_self, d, s, 64, 128))) return rc;
+    int64_t dv[4] = {a->T, HD, a->H, a->B};
+    int64_t sv[4] = {1, a->Tp, (int64_t)HD * a->Tp, (int64_t)a->H * HD * a->Tp};
+    if ((rc = encode4(&tmVs, a->vt_self, dv, sv, 64, HD))) return rc;
+  }
+  if (text) {
+    int64_t d[4] = {HD, a->L, a->H, a->B};
+    int64_t s[4] = {1, HD, (int64_t)a->L * HD, (int64_t)a->H * a->L * HD};
+    if ((rc = encode4(&tmKt, a->k_text, d, s, 64, 128))) return rc;
+    int64_t dv[4] = {a->L, HD, a->H, a->B};
+    int64_t sv[4] = {1, a->Lp, (int64_t)HD * a->Lp, (int64_t)a->H * HD * a->Lp};
+    if ((rc = encode4(&tmVt, a->vt_text, dv, sv, 64, HD))) return rc;
+  }
+  if (!self) { tmKs = tmKt; tmVs = tmVt; }
+  if (!text) { tmKt = tmKs; tmVt = tmVs; }
+  AttnKParams p{};
+  p.T = a->T; p.L = a->L; p.H = a->H;
+  p.n_self = self ? (a->T + 127) / 128 : 0;
+  p.has_text = text ? 1 : 0;
+  p.scale = a->scale; p.gate = a->gate;
+  p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16);
+  p.out_f32 = a->out_f32;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fused_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "attn_fused smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  dim3 grid((a->T + 127) / 128, a->H, a->B);
+  attn_fused_kernel<HD><<<grid, 192, Cfg::kSmem, stream>>>(tmQ, tmKs, tmVs, tmKt, tmVt, p);
+  return check_launch("vb_attn_fused");
+}
+
+}  // namespace vb
+
+extern "C" int vb_attn_fused(const vb_attn_args* a, void* stream) {
+  using namespace vb;
+  ProfScope prof_scope(PK_ATTN_SMALL, stream);
+  if (!a || !a->q || (!a->k_self && !a->k_text) || (!a->out_bf16 && !a->out_f32))
+    return set_error(VB_ERR_INVALID, "vb_attn_fused: null argument");
+  if (a->k_self && (!a->vt_self || a->Tp < a->T || a->Tp % 8))
+    return set_error(VB_ERR_INVALID, "vb_attn_fused: bad self K/V^T");
+  if (a->k_text && (!a->vt_text || a->L <= 0 || a->L > 128 || a->Lp < a->L || a->Lp % 8))
+    return set_error(VB_ERR_INVALID, "vb_attn_fused: text segment needs 0 < L <= 128 and Lp %% 8 == 0");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (a->hd) {
+    case 96: return launch_attn<96>(a, s);
+    case 64: return launch_attn<64>(a, s);
+    case 128: return launch_attn<128>(a, s);
+    default: return set_error(VB_ERR_INVALID, "vb_attn_fused: head_dim %d not instantiated (64/96/128)", a->hd);
+  }
+}

@@ -47,7 +47,7 @@ struct GemmKParams {
   int vec_f32, vec_bf16;  // alignment allows 16-byte accesses
   // qkv-rope
   const float* rope_cs;
-  int T, heads, head_dim, Tp;
+  int T, heads, head_dim, Tp, qkv_sec0;
   __nv_bfloat16* q_out;
   __nv_bfloat16* k_out;
   __nv_bfloat16* vt_out;
@@ -224,8 +224,9 @@ __device__ __forceinline__ void epilogue_qkv(const GemmKParams& p, float (&v)[32
                                              int n_base) {
   const int hd = p.head_dim, H = p.heads, T = p.T;
   const int D = H * hd;
-  const int sec = n_base / D;
-  const int rem = n_base - sec * D;
+  const int sec0 = n_base / D;
+  const int rem = n_base - sec0 * D;
+  const int sec = sec0 + p.qkv_sec0;
   const int h = rem / hd;
   const int d0 = rem - h * hd;
   const int b = m / T;
@@ -489,8 +490,8 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
     else bn = (a->N >= 64 && tiles(32) > 4 * 148) ? 64 : 32;
   }
   if (a->mode == VB_EPI_QKV_ROPE) {
-    if (!a->q_out || !a->k_out || !a->vt_out || a->head_dim % 32 != 0 ||
-        a->N != 3 * a->heads * a->head_dim || a->T <= 0 || a->M % a->T != 0)
+    if (!a->k_out || !a->vt_out || a->head_dim % 32 != 0 ||
+        a->N != (3 - a->qkv_sec0) * a->heads * a->head_dim || a->qkv_sec0 < 0 || a->qkv_sec0 > 1 || (a->qkv_sec0 == 0 && !a->q_out) || a->T <= 0 || a->M % a->T != 0)
       return set_error(VB_ERR_INVALID, "vb_gemm: bad QKV_ROPE arguments");
     if (bn == 96 && (a->head_dim % 96) != 0) bn = 64;
   }
@@ -526,7 +527,7 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
   p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16);
   p.outb_ld = a->outb_ld; p.outb_g1 = a->outb_g1; p.outb_g2 = a->outb_g2;
   p.act_out = a->act_out; p.act_out_slope = a->act_out_slope; p.out_scale = a->out_scale;
-  p.rope_cs = a->rope_cs; p.T = a->T; p.heads = a->heads; p.head_dim = a->head_dim; p.Tp = a->Tp;
+  p.rope_cs = a->rope_cs; p.T = a->T; p.heads = a->heads; p.head_dim = a->head_dim; p.Tp = a->Tp; p.qkv_sec0 = a->qkv_sec0;
   p.q_out = static_cast<__nv_bfloat16*>(a->q_out);
   p.k_out = static_cast<__nv_bfloat16*>(a->k_out);
   p.vt_out = static_cast<__nv_bfloat16*>(a->vt_out);

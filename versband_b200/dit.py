@@ -45,11 +45,14 @@ class DiTCond:
     ac_logits: torch.Tensor           # fp32 [N, depth*E]
     caption: torch.Tensor             # fp32 [B, L, D]  (c_embedder output)
     cap_emb: torch.Tensor             # fp32 [B, D]
-    kv_y: List[torch.Tensor] = field(default_factory=list)    # per block fp32 [B*L, 2D] text cross-attn K|V
-    kv_m: List[torch.Tensor] = field(default_factory=list)    # per block fp32 [B*L, 2D] MoE MHA K|V
+    # per block, bf16: text cross-attention K [B,H,L,hd] and V^T [B,H,hd,Lp]; same for the MoE MHA
+    k_y: List[torch.Tensor] = field(default_factory=list)
+    vt_y: List[torch.Tensor] = field(default_factory=list)
+    k_m: List[torch.Tensor] = field(default_factory=list)
+    vt_m: List[torch.Tensor] = field(default_factory=list)
 
     def tensors(self) -> List[torch.Tensor]:
-        return [self.acoustic, self.ac_logits, self.caption, self.cap_emb, *self.kv_y, *self.kv_m]
+        return [self.acoustic, self.ac_logits, self.caption, self.cap_emb, *self.k_y, *self.vt_y, *self.k_m, *self.vt_m]
 
     @staticmethod
     def cat(conds: "List[DiTCond]") -> "DiTCond":
@@ -61,9 +64,9 @@ class DiTCond:
                       ac_logits=torch.cat([c.ac_logits for c in conds], 0),
                       caption=torch.cat([c.caption for c in conds], 0),
                       cap_emb=torch.cat([c.cap_emb for c in conds], 0))
-        for k in range(len(c0.kv_y)):
-            out.kv_y.append(torch.cat([c.kv_y[k] for c in conds], 0))
-            out.kv_m.append(torch.cat([c.kv_m[k] for c in conds], 0))
+        for name in ("k_y", "vt_y", "k_m", "vt_m"):
+            for k in range(len(c0.k_y)):
+                getattr(out, name).append(torch.cat([getattr(c, name)[k] for c in conds], 0))
         return out
 
     def copy_from(self, other: "DiTCond") -> None:
@@ -185,7 +188,7 @@ class DiTEngine:
             temb_sin=z(B, 256, dt=BF), temb_h=z(B, D, dt=BF), temb=z(B, D), ada_in=z(B, D, dt=BF),
             mod=z(B, self.mod_ld), hl=z(B, 2 * self.depth),
             xa=z(N, D, dt=BF), q=z(B, H, T, hd, dt=BF), k=z(B, H, T, hd, dt=BF), vt=z(B, H, hd, Tp, dt=BF),
-            S=z(B, H, T, Tp), P=z(B, H, T, Tp, dt=BF), o_self=z(N, D), oa=z(N, D, dt=BF),
+            oa=z(N, D, dt=BF),
             xm=z(N, D, dt=BF), qm=z(N, D, dt=BF), ctx=z(N, D, dt=BF), cap_feat=z(N, D),
             idx_c=z(N, dt=torch.int32), idx_a=z(N, dt=torch.int32), scale_c=z(N), scale_a=z(N),
             cap_logits=z(N, E),
@@ -252,15 +255,20 @@ class DiTEngine:
         ops.gemm(pool_n, w["cap_w"], bias=w["cap_b"], out_f32=cap_emb, out_ld=D)
         cond = DiTCond(B=B, T=T, L=L, acoustic=ac, ac_logits=ac_logits, caption=cap, cap_emb=cap_emb)
         y16 = torch.empty(B * L, D, device=dev, dtype=BF)
+        H, hd = self.H, self.hd
+        Lp = (L + 7) // 8 * 8
         for k in range(self.depth):
             b = w["blocks"][k]
+            # K / V^T of the two short-KV attentions, written head-major by the k|v GEMM epilogue
             ops.norm_mod(cap.view(B * L, D), kind=0, w=b["y_norm"], eps=self.eps, out_bf16=y16)
-            kv = torch.empty(B * L, 2 * D, device=dev, dtype=F32)
-            ops.gemm(y16, b["wkvy"], out_f32=kv, out_ld=2 * D)
-            cond.kv_y.append(kv)
-            kvm = torch.empty(B * L, 2 * D, device=dev, dtype=F32)
-            ops.gemm(cap_bf, b["mkv_w"], bias=b["mkv_b"], out_f32=kvm, out_ld=2 * D)
-            cond.kv_m.append(kvm)
+            for src, wt, bias, kl, vl in ((y16, b["wkvy"], None, cond.k_y, cond.vt_y),
+                                          (cap_bf, b["mkv_w"], b["mkv_b"], cond.k_m, cond.vt_m)):
+                kk = torch.empty(B, H, L, hd, device=dev, dtype=BF)
+                vt = torch.zeros(B, H, hd, Lp, device=dev, dtype=BF)
+                ops.gemm(src, wt, mode=ops.EPI_QKV_ROPE, qkv_sec0=1, bias=bias, T=L, heads=H, head_dim=hd, Tp=Lp,
+                         k_out=kk, vt_out=vt)
+                kl.append(kk)
+                vl.append(vt)
         return cond
 
     # ------------------------------------------------------------------ one DiT evaluation
@@ -307,25 +315,18 @@ class DiTEngine:
                          rows_per_batch=T, eps=self.eps, out_bf16=ws["xa"])
             ops.gemm(ws["xa"], b["wqkv"], mode=ops.EPI_QKV_ROPE, rope_cs=w["rope"], T=T, heads=H, head_dim=hd,
                      Tp=Tp, q_out=ws["q"], k_out=ws["k"], vt_out=ws["vt"])
-            ops.gemm(ws["q"].view(B * H, T, hd), ws["k"].view(B * H, T, hd), M=T, N=T, K=hd, G1=H, G2=B,
-                     a_c2=(1, H), b_c2=(1, H, 0), alpha=scale, out_f32=ws["S"], out_ld=Tp,
-                     out_g=(T * Tp, H * T * Tp))
-            ops.softmax_rows(ws["S"], Tp, ws["P"], Tp, B * H * T, T)
-            ops.gemm(ws["P"].view(B * H, T, Tp)[:, :, :T], ws["vt"].view(B * H, hd, Tp)[:, :, :T], M=T, N=hd, K=T,
-                     G1=H, G2=B, a_c2=(1, H), b_c2=(1, H, 0), out_f32=ws["o_self"], out_ld=D,
-                     out_g=(hd, T * D))
-            kv = cond.kv_y[k]
-            ops.attn_smallkv(ws["q"], (H * T * hd, hd, T * hd), kv, kv[:, D:], 2 * D, B=B, T=T, H=H, hd=hd, L=L,
-                             scale=scale, gate=b["gate"], base=ws["o_self"], out_bf16=ws["oa"])
+            # self-attention + gated text cross-attention in one tcgen05 flash-attention launch
+            ops.attn_fused(ws["q"], (hd, T * hd, H * T * hd), B=B, T=T, H=H, hd=hd, scale=scale,
+                           k_self=ws["k"], vt_self=ws["vt"], Tp=Tp, k_text=cond.k_y[k], vt_text=cond.vt_y[k],
+                           L=L, Lp=cond.vt_y[k].shape[-1], gate=b["gate"], out_bf16=ws["oa"])
             ops.gemm(ws["oa"], b["wo"], gate=g_msa, gate_rows=T, gate_ld=mld, residual=xcur,
                      out_f32=hbuf, out_ld=D)
             # ---- Band-MoE branch (vocal2music_moe.py:251-257, 117-185)
             ops.norm_mod(hbuf, kind=0, w=b["ffn_norm"], shift=sh_mlp, scale=sc_mlp, mod_ld=mld,
                          rows_per_batch=T, eps=self.eps, out_bf16=ws["xm"])
             ops.gemm(ws["xm"], b["mq_w"], bias=b["mq_b"], out_bf16=ws["qm"], outb_ld=D)
-            kvm = cond.kv_m[k]
-            ops.attn_smallkv(ws["qm"], (T * D, D, hd), kvm, kvm[:, D:], 2 * D, B=B, T=T, H=H, hd=hd, L=L,
-                             scale=scale, out_bf16=ws["ctx"])
+            ops.attn_fused(ws["qm"], (D, hd, T * D), B=B, T=T, H=H, hd=hd, scale=scale, k_text=cond.k_m[k],
+                           vt_text=cond.vt_m[k], L=L, Lp=cond.vt_m[k].shape[-1], out_bf16=ws["ctx"])
             ops.gemm(ws["ctx"], b["mo_w"], bias=b["mo_b"], out_f32=ws["cap_feat"], out_ld=D)
             e0, e1, e2 = expo[k]
             ops.router(ws["cap_feat"], b["capg_w"], b["capg_b"], cond.ac_logits[:, k * E:], self.depth * E,

@@ -8,7 +8,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import GemmArgs
+from ._lib import AttnArgs, GemmArgs
 
 ACT_NONE, ACT_SILU, ACT_LRELU, ACT_GELU, ACT_TANH = 0, 1, 2, 3, 4
 EPI_GENERIC, EPI_QKV_ROPE = 0, 1
@@ -56,7 +56,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: Optional[int] = None, N: Option
          out_bf16: Optional[torch.Tensor] = None, outb_ld: int = 0, outb_g=(0, 0),
          act_out: int = ACT_NONE, act_out_slope: float = 0.0, out_scale: float = 1.0,
          rope_cs: Optional[torch.Tensor] = None, T: int = 0, heads: int = 0, head_dim: int = 0,
-         Tp: int = 0, q_out=None, k_out=None, vt_out=None) -> None:
+         Tp: int = 0, q_out=None, k_out=None, vt_out=None, qkv_sec0: int = 0) -> None:
     """D = epilogue(A @ B^T) on the tcgen05 GEMM (see include/versband.h: vb_gemm).
 
     `a` is a bf16 view of up to 4 dims [c3, c2, rows, k]; `b` a bf16 view [group, n, k].
@@ -103,6 +103,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: Optional[int] = None, N: Option
     _check_f32(rope_cs, "rope_cs")
     args.rope_cs, args.T, args.heads, args.head_dim, args.Tp = _ptr(rope_cs), T, heads, head_dim, Tp
     args.q_out, args.k_out, args.vt_out = _ptr(q_out), _ptr(k_out), _ptr(vt_out)
+    args.qkv_sec0 = qkv_sec0
     _lib.check(_lib.lib().vb_gemm(C.byref(args), _stream()), "vb_gemm")
 
 
@@ -199,3 +200,15 @@ def conv_post(x_bf16, w, bias: float, B, T, Cc, k, wav) -> None:
 def mean_tokens(x, out) -> None:
     B, L, D = x.shape
     _call("vb_mean_tokens", _ptr(x), B, L, D, _ptr(out))
+
+
+def attn_fused(q, q_strides, *, B, T, H, hd, scale, k_self=None, vt_self=None, Tp=0, k_text=None, vt_text=None,
+               L=0, Lp=0, gate=None, out_bf16=None, out_f32=None) -> None:
+    """Fused tcgen05 attention (self segment and/or one short "text" segment), see vb_attn_fused."""
+    a = AttnArgs()
+    a.q = _ptr(q)
+    a.q_st, a.q_sh, a.q_sb = q_strides
+    a.k_self, a.vt_self, a.k_text, a.vt_text = _ptr(k_self), _ptr(vt_self), _ptr(k_text), _ptr(vt_text)
+    a.gate, a.out_bf16, a.out_f32 = _ptr(gate), _ptr(out_bf16), _ptr(out_f32)
+    a.B, a.T, a.H, a.hd, a.Tp, a.L, a.Lp, a.scale = B, T, H, hd, Tp, L, Lp, scale
+    _lib.check(_lib.lib().vb_attn_fused(C.byref(a), _stream()), "vb_attn_fused")
