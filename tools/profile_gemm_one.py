@@ -1,0 +1,28 @@
+"""A few vb_gemm launches of chosen shapes, for `ncu --set full` captures."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from versband_b200 import ops  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else "voc32"
+if which.startswith("voc"):
+    C = int(which[3:])
+    T = {32: 480000, 64: 240000, 128: 60000, 256: 12000}[C]
+    k = 3
+    x = torch.randn(1, T, C, device="cuda").bfloat16()
+    w = torch.randn(C, k * 64 * ((C + 63) // 64), device="cuda").bfloat16()
+    out = torch.empty(1, T, C, device="cuda", dtype=torch.bfloat16)
+    fn = lambda: ops.gemm(x, w, M=T, G1=1, kpt=(C + 63) // 64, dil=1, pad=1, a_c2=(1, 0), out_bf16=out, outb_ld=C,
+                          outb_g=(T * C, 0))
+else:
+    M, N, K = 1500, 768, 768
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    b = torch.randn(N, K, device="cuda").bfloat16()
+    o = torch.empty(M, N, device="cuda")
+    fn = lambda: ops.gemm(a, b, out_f32=o, out_ld=N)
+for _ in range(5):
+    fn()
+torch.cuda.synchronize()

@@ -18,6 +18,7 @@ struct GemmKParams {
   int M, N, K;
   int G1;
   int num_kb, kpt, dil, pad;
+  int m_tiles, n_tiles, num_tiles;
   int a_c2_g1, a_c2_g2, a_c3_g1, a_c3_g2;
   int b_c2_g1, b_c2_g2, b_c2_tile;
   const int* tile_group;
@@ -44,7 +45,7 @@ struct GemmKParams {
   long long outb_ld, outb_g1, outb_g2;
   int act_out;
   float act_out_slope, out_scale;
-  int vec_f32, vec_bf16;  // alignment allows 16-byte accesses
+  int vec_f32, vec_bf16, vec_aux;  // alignment allows 16-byte accesses (outputs / bias+gate)
   // qkv-rope
   const float* rope_cs;
   int T, heads, head_dim, Tp, qkv_sec0;
@@ -53,18 +54,32 @@ struct GemmKParams {
   __nv_bfloat16* vt_out;
 };
 
-__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+// Activations are applied by whole-chunk loops selected ONCE per chunk (one uniform branch, then a
+// straight-line 32-wide loop): keeps the executed instruction stream short — the epilogue runs per
+// tile on four warps and was instruction-fetch bound when the switch sat inside the unrolled loop.
+template <int ACT>
+__device__ __forceinline__ float act_one(float v, float slope) {
+  if (ACT == VB_ACT_SILU) return v / (1.f + __expf(-v));
+  if (ACT == VB_ACT_LRELU) return v > 0.f ? v : v * slope;
+  if (ACT == VB_ACT_GELU_ERF) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+  if (ACT == VB_ACT_TANH) return tanhf(v);
+  return v;
+}
+template <int ACT, int N>
+__device__ __forceinline__ void act_loop(float (&v)[N], float slope, float pre) {
+#pragma unroll
+  for (int j = 0; j < N; ++j) v[j] = act_one<ACT>(v[j] * pre, slope);
+}
+template <int N>
+__device__ __forceinline__ void apply_act_all(float (&v)[N], int act, float slope, float pre = 1.f) {
   switch (act) {
-    case VB_ACT_SILU:
-      return v / (1.f + __expf(-v));
-    case VB_ACT_LRELU:
-      return v > 0.f ? v : v * slope;
-    case VB_ACT_GELU_ERF:
-      return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
-    case VB_ACT_TANH:
-      return tanhf(v);
+    case VB_ACT_SILU: act_loop<VB_ACT_SILU>(v, slope, pre); break;
+    case VB_ACT_LRELU: act_loop<VB_ACT_LRELU>(v, slope, pre); break;
+    case VB_ACT_GELU_ERF: act_loop<VB_ACT_GELU_ERF>(v, slope, pre); break;
+    case VB_ACT_TANH: act_loop<VB_ACT_TANH>(v, slope, pre); break;
     default:
-      return v;
+      if (pre != 1.f) act_loop<VB_ACT_NONE>(v, slope, pre);
+      break;
   }
 }
 
@@ -73,29 +88,45 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// v[j] (op)= src[j] for the 32 columns of this chunk; vector path when the chunk is full & aligned
+template <bool MUL>
+__device__ __forceinline__ void combine32(float (&v)[32], const float* __restrict__ src, bool vec,
+                                          int n_left) {
+  if (vec) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 r = __ldg(reinterpret_cast<const float4*>(src) + j);
+      if (MUL) { v[4 * j] *= r.x; v[4 * j + 1] *= r.y; v[4 * j + 2] *= r.z; v[4 * j + 3] *= r.w; }
+      else { v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w; }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < n_left) { if (MUL) v[j] *= src[j]; else v[j] += src[j]; }
+  }
+}
+
 // ------------------------------------------------------------------ generic epilogue
 // One thread owns one output row (TMEM lane) and 32 consecutive columns of it.
 __device__ __forceinline__ void epilogue_generic(const GemmKParams& p, float (&v)[32], int m,
                                                  int n_base, int g1, int g2, int tg,
                                                  long long orow) {
   const int N = p.N;
+  if (p.alpha != 1.f) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+    for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+  }
 
   if (p.swiglu) {
     // columns (2i, 2i+1) = (w1 x, w3 x)  ->  silu(w1 x) * (w3 x), 16 outputs
     const int n_out0 = n_base >> 1;
     const int n_out_total = N >> 1;
+    const float rs = p.row_scale ? p.row_scale[m] : 1.f;
     float o[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      float a = v[2 * j], b = v[2 * j + 1];
-      o[j] = (a / (1.f + __expf(-a))) * b;
-    }
-    if (p.row_scale) {
-      float rs = p.row_scale[m];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) o[j] *= rs;
+      const float a = v[2 * j], b = v[2 * j + 1];
+      o[j] = (a / (1.f + __expf(-a))) * b * rs;
     }
     if (p.out_bf16) {
       __nv_bfloat16* dst = p.out_bf16 + g1 * p.outb_g1 + g2 * p.outb_g2 + orow * p.outb_ld + n_out0;
@@ -123,62 +154,23 @@ __device__ __forceinline__ void epilogue_generic(const GemmKParams& p, float (&v
   }
 
   const bool full = (n_base + 32 <= N);
-  if (p.bias) {
-    const float* bp = p.bias + g1 * p.bias_g1 + tg * p.bias_tile + n_base;
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] += __ldg(bp + j);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n_base + j < N) v[j] += __ldg(bp + j);
-    }
-  }
-  if (p.act != VB_ACT_NONE) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act, p.act_slope);
-  }
+  const int n_left = N - n_base;
+  if (p.bias) combine32<false>(v, p.bias + g1 * p.bias_g1 + tg * p.bias_tile + n_base, full && p.vec_aux, n_left);
+  if (p.act != VB_ACT_NONE) apply_act_all(v, p.act, p.act_slope);
   if (p.row_scale) {
-    float rs = p.row_scale[m];
+    const float rs = p.row_scale[m];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= rs;
   }
-  if (p.gate) {
-    const float* gp = p.gate + (long long)(m / p.gate_rows) * p.gate_ld + g1 * p.gate_g1 + n_base;
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] *= __ldg(gp + j);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n_base + j < N) v[j] *= __ldg(gp + j);
-    }
-  }
+  if (p.gate)
+    combine32<true>(v, p.gate + (long long)(m / p.gate_rows) * p.gate_ld + g1 * p.gate_g1 + n_base,
+                    full && p.vec_aux, n_left);
   const long long off32 = g1 * p.out_g1 + g2 * p.out_g2 + orow * p.out_ld + n_base;
-  if (p.residual) {
-    const float* rp = p.residual + off32;
-    if (full && p.vec_f32) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 r = reinterpret_cast<const float4*>(rp)[j];
-        v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n_base + j < N) v[j] += rp[j];
-    }
-  }
+  if (p.residual) combine32<false>(v, p.residual + off32, full && p.vec_f32, n_left);
   if (p.out_f32) {
     float* dst = p.out_f32 + off32;
+    if (p.accumulate) combine32<false>(v, dst, full && p.vec_f32, n_left);
     if (full && p.vec_f32) {
-      if (p.accumulate) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 r = reinterpret_cast<const float4*>(dst)[j];
-          v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
-        }
-      }
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         reinterpret_cast<float4*>(dst)[j] =
@@ -186,32 +178,27 @@ __device__ __forceinline__ void epilogue_generic(const GemmKParams& p, float (&v
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (n_base + j < N) {
-          if (p.accumulate) v[j] += dst[j];
-          dst[j] = v[j];
-        }
+        if (j < n_left) dst[j] = v[j];
     }
   }
   if (p.out_bf16) {
     __nv_bfloat16* dst =
         p.out_bf16 + g1 * p.outb_g1 + g2 * p.outb_g2 + orow * p.outb_ld + n_base;
-    float o[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) o[j] = apply_act(v[j] * p.out_scale, p.act_out, p.act_out_slope);
+    apply_act_all(v, p.act_out, p.act_out_slope, p.out_scale);
     if (full && p.vec_bf16) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 w;
-        w.x = pack_bf16(o[8 * j], o[8 * j + 1]);
-        w.y = pack_bf16(o[8 * j + 2], o[8 * j + 3]);
-        w.z = pack_bf16(o[8 * j + 4], o[8 * j + 5]);
-        w.w = pack_bf16(o[8 * j + 6], o[8 * j + 7]);
+        w.x = pack_bf16(v[8 * j], v[8 * j + 1]);
+        w.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+        w.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+        w.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
         reinterpret_cast<uint4*>(dst)[j] = w;
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (n_base + j < N) dst[j] = __float2bfloat16(o[j]);
+        if (j < n_left) dst[j] = __float2bfloat16(v[j]);
     }
   }
 }
@@ -272,24 +259,44 @@ __device__ __forceinline__ void epilogue_qkv(const GemmKParams& p, float (&v)[32
 }
 
 // ------------------------------------------------------------------ kernel
+// Persistent: one CTA per SM walks the tile list (m fastest). The smem ring is as deep as
+// shared memory allows (6-10 stages) so a latency-bound small GEMM has all of its k-blocks in
+// flight, and two TMEM accumulators let the epilogue of tile i overlap the mainloop of tile i+1.
 template <int BN>
 struct GemmCfg {
-  static constexpr int kStages = (BN <= 32) ? 4 : 4;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
-  static constexpr int kTmemCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
-  static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + 1024 /*align*/ + 256;
+  static constexpr int kStages = (200 * 1024) / (kABytes + kBBytes) > 12 ? 12 : (200 * 1024) / (kABytes + kBBytes);
+  static constexpr int kAccStride = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  static constexpr int kTmemCols = 2 * kAccStride;
+  static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + 1024 /*align*/ + 512;
 };
 
+struct TileCoord {
+  int m_tile, n_tile, g1, g2, tg;
+  bool skip;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int t, int m_used) {
+  TileCoord c;
+  const int per_g = p.m_tiles * p.n_tiles;
+  const int g = t / per_g;
+  const int r = t - g * per_g;
+  c.n_tile = r / p.m_tiles;
+  c.m_tile = r - c.n_tile * p.m_tiles;
+  c.g1 = g % p.G1;
+  c.g2 = g / p.G1;
+  c.skip = c.m_tile >= m_used;
+  c.tg = (p.tile_group && !c.skip) ? p.tile_group[c.m_tile] : 0;
+  return c;
+}
+
 template <int BN>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 1)
 vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmKParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
-
-  const int m_tile = blockIdx.y;
-  if (p.m_tiles_used != nullptr && m_tile >= *p.m_tiles_used) return;  // uniform per CTA
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -298,17 +305,12 @@ vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem_b = smem + kStages * Cfg::kABytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + kStages * Cfg::kBBytes);
   uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full_bar = empty_bar + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + kStages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = m_tile * BM;
-  const int g = blockIdx.z;
-  const int g1 = g % p.G1;
-  const int g2 = g / p.G1;
-  const int tg = p.tile_group ? p.tile_group[m_tile] : 0;
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -317,7 +319,10 @@ vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 128);
+    }
     fence_barrier_init();
   }
   if (warp_idx == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -327,24 +332,30 @@ vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_kb = p.num_kb;
+  const int m_used = p.m_tiles_used ? *p.m_tiles_used : p.m_tiles;
 
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const int a_c2 = g1 * p.a_c2_g1 + g2 * p.a_c2_g2;
-      const int a_c3 = g1 * p.a_c3_g1 + g2 * p.a_c3_g2;
-      const int b_c2 = g1 * p.b_c2_g1 + g2 * p.b_c2_g2 + tg * p.b_c2_tile;
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
-        const int tap = kb / p.kpt;
-        const int c0 = (kb - tap * p.kpt) * BK;
-        const int c1 = m0 + tap * p.dil - p.pad;
-        tma_load_4d(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], c0, c1, a_c2, a_c3);
-        tma_load_3d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n0, b_c2);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t, m_used);
+        if (tc.skip) continue;
+        const int m0 = tc.m_tile * BM, n0 = tc.n_tile * BN;
+        const int a_c2 = tc.g1 * p.a_c2_g1 + tc.g2 * p.a_c2_g2;
+        const int a_c3 = tc.g1 * p.a_c3_g1 + tc.g2 * p.a_c3_g2;
+        const int b_c2 = tc.g1 * p.b_c2_g1 + tc.g2 * p.b_c2_g2 + tc.tg * p.b_c2_tile;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
+          const int tap = kb / p.kpt;
+          const int c0 = (kb - tap * p.kpt) * BK;
+          const int c1 = m0 + tap * p.dil - p.pad;
+          tma_load_4d(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], c0, c1, a_c2, a_c3);
+          tma_load_3d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n0, b_c2);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp_idx == 1) {
@@ -353,49 +364,70 @@ vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+      int local = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t, m_used);
+        if (tc.skip) continue;
+        const int acc = local & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((local >> 1) & 1) ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
-        const uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + stage * Cfg::kABytes));
-        const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
+        const uint32_t tmem_d = tmem_base + acc * Cfg::kAccStride;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
-          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
+            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs retire
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+        ++local;
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
     // ===================== epilogue warps (2..5) =====================
     const int q = warp_idx & 3;  // TMEM lane quadrant this warp may access
     const int r = q * 32 + lane;
-    const int m = m0 + r;
-    const bool row_ok = m < p.M;
-    long long orow = 0;
-    bool store_ok = row_ok;
-    if (row_ok && p.mode == VB_EPI_GENERIC) {
-      if (p.row_map) orow = p.row_map[m];
-      else orow = (long long)m * p.row_mul + p.row_off + (long long)g1 * p.row_off_g1;
-      store_ok = (orow >= 0 && orow < p.rows_out);
-    }
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t raw[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, raw);
-      tmem_ld_wait();
-      const int n_base = n0 + c;
-      if (store_ok && n_base < p.N) {
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        if (p.mode == VB_EPI_QKV_ROPE) epilogue_qkv(p, v, m, n_base);
-        else epilogue_generic(p, v, m, n_base, g1, g2, tg, orow);
+    int local = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(p, t, m_used);
+      if (tc.skip) continue;
+      const int acc = local & 1;
+      const int m0 = tc.m_tile * BM, n0 = tc.n_tile * BN;
+      const int m = m0 + r;
+      const bool row_ok = m < p.M;
+      long long orow = 0;
+      bool store_ok = row_ok;
+      if (row_ok && p.mode == VB_EPI_GENERIC) {
+        if (p.row_map) orow = p.row_map[m];
+        else orow = (long long)m * p.row_mul + p.row_off + (long long)tc.g1 * p.row_off_g1;
+        store_ok = (orow >= 0 && orow < p.rows_out);
       }
+      mbar_wait(&tmem_full_bar[acc], (local >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_d + c, raw);
+        tmem_ld_wait();
+        const int n_base = n0 + c;
+        if (store_ok && n_base < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          if (p.mode == VB_EPI_QKV_ROPE) epilogue_qkv(p, v, m, n_base);
+          else epilogue_generic(p, v, m, n_base, tc.g1, tc.g2, tc.tg, orow);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);  // 128 arrivals release the accumulator to the MMA warp
+      ++local;
     }
   }
 
@@ -482,12 +514,16 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
   const int m_tiles = (a->M + BM - 1) / BM;
   const int G = a->G1 * a->G2;
   if (bn == 0) {
+    // one CTA per SM: prefer the tile width whose tile count best fills 148 SMs; small problems
+    // are latency-bound (more, narrower tiles = more SMs pulling from L2 in parallel), large ones
+    // want wide tiles (less operand re-fetch).
     auto tiles = [&](int t) { return (long long)m_tiles * ((a->N + t - 1) / t) * G; };
     if (a->N <= 32) bn = 32;
     else if (a->N % 96 == 0 && a->N % 128 != 0 && a->N <= 192) bn = 96;
-    else if (tiles(128) >= 2 * 148 && a->N >= 128) bn = 128;
-    else if (tiles(64) >= 148 && a->N >= 64) bn = 64;
-    else bn = (a->N >= 64 && tiles(32) > 4 * 148) ? 64 : 32;
+    else if (a->N >= 256 && tiles(256) >= 2 * 148) bn = 256;
+    else if (a->N >= 128 && (tiles(128) >= 120 || (a->K >= 2048 && tiles(128) >= 48))) bn = 128;
+    else if (a->N >= 64 && tiles(64) >= 100) bn = 64;
+    else bn = a->N >= 64 && tiles(32) > 296 ? 64 : 32;
   }
   if (a->mode == VB_EPI_QKV_ROPE) {
     if (!a->k_out || !a->vt_out || a->head_dim % 32 != 0 ||
@@ -542,16 +578,31 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
                 (!a->out_f32 || al(a->out_f32, 16)) && (!a->residual || al(a->residual, 16));
     p.vec_bf16 = (a->outb_ld % 8 == 0) && (a->outb_g1 % 8 == 0) && (a->outb_g2 % 8 == 0) &&
                  (!a->out_bf16 || al(a->out_bf16, 16));
-    if ((a->residual || a->accumulate) && !a->out_f32)
-      return set_error(VB_ERR_INVALID, "vb_gemm: residual/accumulate need out_f32 addressing");
+    p.vec_aux = (!a->bias || (al(a->bias, 16) && a->bias_g1 % 4 == 0 && a->bias_tile % 4 == 0)) &&
+                (!a->gate || (al(a->gate, 16) && a->gate_ld % 4 == 0 && a->gate_g1 % 4 == 0));
+    if (a->accumulate && !a->out_f32)
+      return set_error(VB_ERR_INVALID, "vb_gemm: accumulate needs out_f32");
+    if (a->residual && a->out_ld <= 0)
+      return set_error(VB_ERR_INVALID, "vb_gemm: residual needs out_ld (it shares the fp32 output addressing)");
   }
 
-  dim3 grid((a->N + bn - 1) / bn, m_tiles, G);
+  p.m_tiles = m_tiles;
+  p.n_tiles = (a->N + bn - 1) / bn;
+  p.num_tiles = p.m_tiles * p.n_tiles * G;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  dim3 grid(p.num_tiles < num_sms ? p.num_tiles : num_sms, 1, 1);
   switch (bn) {
     case 32: return launch<32>(tmA, tmB, p, grid, stream);
     case 64: return launch<64>(tmA, tmB, p, grid, stream);
     case 96: return launch<96>(tmA, tmB, p, grid, stream);
     case 128: return launch<128>(tmA, tmB, p, grid, stream);
+    case 256: return launch<256>(tmA, tmB, p, grid, stream);
     default: return set_error(VB_ERR_INVALID, "vb_gemm: unsupported N tile %d", bn);
   }
 }

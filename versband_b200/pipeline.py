@@ -30,6 +30,8 @@ class AccompBandPipeline:
         self.voc = HifiGanEngine(voc_sd, voc_cfg, device=device)
         self.sampler = FlowSampler(self.dit, n_points=n_points, use_graph=use_graph)
         self.scale_factor = float(scale_factor)
+        self.use_graph = use_graph
+        self._post = {}
         self.hop = 1
         for u in voc_cfg["upsample_rates"]:
             self.hop *= u
@@ -54,11 +56,33 @@ class AccompBandPipeline:
         mark("sampler_start")
         z = self.sampler.sample_cfg(x0, cond, uncond, guidance, noise=noise, generator=generator)
         mark("sampler_end")
-        mel = self.vae.decode(z, scale=1.0 / self.scale_factor)  # ddpm_audio.py:386
-        mark("vae_end")
-        wav = self.voc.forward(mel)
+        if not self.use_graph:
+            mel = self.vae.decode(z, scale=1.0 / self.scale_factor)  # ddpm_audio.py:386
+            mark("vae_end")
+            wav = self.voc.forward(mel)
+            mark("end")
+            return {"latent": z, "mel": mel, "wav": wav}
+        # VAE decode + vocoder replayed from one CUDA graph per (B, T)
+        st = self._post.get((B, T))
+        if st is None:
+            st = {"z": z.clone()}
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):  # warm-up: kernel attributes, allocator pools
+                self.voc.forward(self.vae.decode(st["z"], scale=1.0 / self.scale_factor))
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st["mel"] = self.vae.decode(st["z"], scale=1.0 / self.scale_factor)
+                st["wav"] = self.voc.forward(st["mel"])
+            st["graph"] = g
+            self._post[(B, T)] = st
+        st["z"].copy_(z)
+        st["graph"].replay()
+        mark("vae_end")  # (decode and vocoder are one graph: the split is not observable)
         mark("end")
-        return {"latent": z, "mel": mel, "wav": wav}
+        return {"latent": z, "mel": st["mel"].clone(), "wav": st["wav"].clone()}
 
     @torch.no_grad()
     def generate_host(self, midi, beats, caption, caption_uncond, *, guidance=3.0, x0=None, noise=None,
