@@ -163,6 +163,10 @@ long long vb_launch_count(void);
  * on the launching stream; vb_prof_report() synchronises and returns total ms / launch count per
  * kernel family (0 gemm, 1 norm, 2 softmax, 3 attn_small, 4 router, 5 moe_sort, 6 elementwise,
  * 7 layout, 8 groupnorm, 9 conv_post). Not usable during CUDA-graph capture. */
+/* debug: writes %globaltimer (ns) to *slot when the stream reaches this point */
+int vb_timestamp(uint64_t* slot, void* stream);
+/* programmatic dependent launch between this library's kernels (default on) */
+int vb_set_pdl(int on);
 #define VB_PROF_KINDS 10
 int vb_prof_enable(int on);
 int vb_prof_report(double* ms_by_kind, long long* count_by_kind, int nkinds);
@@ -203,10 +207,22 @@ int vb_linear_small(const float* x, int64_t ldx, const float* W, const float* bi
 /* Gumbel-softmax router: e0 [N,2], e1/e2 [N,E] are the Exp(1) draws the reference obtains from
  * torch.empty_like(logits).exponential_() (:82). Emits hard top-1 indices and the combined
  * weights scale_g[n] = ((1-p)+p) * group_mask_g[n]. */
-int vb_router(const float* cap_feat, const float* Wc, const float* bc, const float* ac_logits,
+int vb_router(const float* cap_feat, const void* cap_feat_bf16, const float* Wc, const float* bc, const float* ac_logits,
               int ac_ld, const float* hl_logits, int hl_ld, const float* e0, const float* e1, const float* e2, float tau,
               int N, int T, int D, int E, int32_t* idx_c, int32_t* idx_a, float* scale_c,
-              float* scale_a, float* cap_logits_out, void* stream);
+              float* scale_a, float* cap_logits_out, int32_t* bucket_count, float* usage,
+              int32_t* slot_c, int32_t* slot_a, void* stream);
+/* Features may be fp32 (cap_feat) or bf16 (cap_feat_bf16). With bucket_count != NULL the router also
+ * claims an (unordered) slot per (token, group) in its expert bucket with atomics; vb_moe_finalize
+ * turns the counts into 128-row-padded bucket starts / tile table / lb loss (and re-zeroes them),
+ * vb_moe_scatter writes row_map/row_scale and gathers the activation rows into bucket order. */
+int vb_moe_finalize(int32_t* bucket_count, float* usage, int E, int32_t* bucket_start, int32_t* row_map,
+                    float* row_scale, int32_t* tile_group, int32_t* m_tiles_used, int max_rows,
+                    float* lb_out, void* stream);
+int vb_moe_scatter(const int32_t* idx_c, const int32_t* idx_a, const int32_t* slot_c, const int32_t* slot_a,
+                   const float* scale_c, const float* scale_a, const int32_t* bucket_start, int N, int E,
+                   int D, const void* x_bf16, void* xs_bf16, int32_t* row_map, float* row_scale,
+                   void* stream);
 /* counting sort of the 2N (token, group) pairs into 128-row tiles per expert bucket */
 int vb_moe_sort(const int32_t* idx_c, const int32_t* idx_a, const float* scale_c,
                 const float* scale_a, int N, int E, int32_t* row_map, float* row_scale,

@@ -101,10 +101,13 @@ def _declare(l: C.CDLL) -> None:
         "vb_mean_tokens": [P, I, I, I, P, P],
         "vb_timestep_embed": [P, P, P, P, I, I, P],
         "vb_linear_small": [P, L, P, P, P, I, I, I, P],
-        "vb_router": [P, P, P, P, I, P, I, P, P, P, F, I, I, I, I, P, P, P, P, P, P],
+        "vb_router": [P, P, P, P, P, I, P, I, P, P, P, F, I, I, I, I, P, P, P, P, P, P, P, P, P, P],
+        "vb_moe_finalize": [P, P, I, P, P, P, P, P, I, P, P],
+        "vb_moe_scatter": [P, P, P, P, P, P, P, I, I, I, P, P, P, P, P],
         "vb_moe_sort": [P, P, P, P, I, I, P, P, P, P, I, P, P],
         "vb_gather_rows": [P, P, P, I, I, P, I, P],
         "vb_ew": [P, P, F, F, I, F, P, P, L, I, I, P],
+        "vb_timestamp": [P, P],
         "vb_nct_to_ntc": [P, F, P, I, I, I, I, P],
         "vb_ntc_to_nct": [P, P, L, F, F, P, I, I, I, P],
         "vb_embed_rows": [P, P, I, I, P, L, P],

@@ -32,6 +32,9 @@ tensor_map_encode_fn get_tensor_map_encoder() {
   return fn;
 }
 
+static bool g_pdl = true;
+bool pdl_enabled() { return g_pdl; }
+
 // ---- per-family event profiler ----
 struct ProfEv { cudaEvent_t a, b; int kind; };
 static bool g_prof_on = false;
@@ -52,6 +55,11 @@ void prof_stop(int kind, cudaStream_t s) {
 }
 
 }  // namespace vb
+
+extern "C" int vb_set_pdl(int on) {
+  vb::g_pdl = on != 0;
+  return VB_OK;
+}
 
 extern "C" int vb_prof_enable(int on) {
   std::lock_guard<std::mutex> lk(vb::g_prof_mu);

@@ -85,6 +85,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_O = tmem_base + 256;
+  pdl_sync();  // prologue above overlaps the previous kernel
 
   if (warp == 0) {
     if (lane == 0) {
@@ -335,7 +336,7 @@ static int launch_attn(const vb_attn_args* a, cudaStream_t stream) {
     attr = true;
   }
   dim3 grid((a->T + 127) / 128, a->H, a->B);
-  attn_fused_kernel<HD><<<grid, 192, Cfg::kSmem, stream>>>(tmQ, tmKs, tmVs, tmKt, tmVt, p);
+  launch_k(attn_fused_kernel<HD>, dim3(grid), dim3(192), Cfg::kSmem, stream, tmQ, tmKs, tmVs, tmKt, tmVt, p);
   return check_launch("vb_attn_fused");
 }
 

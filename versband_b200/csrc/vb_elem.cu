@@ -18,6 +18,7 @@ __device__ __forceinline__ float act_f(float v, int act, float slope) {
 __global__ void ew_kernel(const float* __restrict__ a, const float* __restrict__ b, float alpha,
                           float beta, int act, float slope, float* __restrict__ out_f32,
                           __nv_bfloat16* __restrict__ out_bf16, long long rows, int D, int rep) {
+  pdl_sync();
   const long long nvec = rows * (D / 4);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
@@ -50,6 +51,7 @@ __global__ void ew_kernel(const float* __restrict__ a, const float* __restrict__
 // 32x32 shared-memory transpose: coalesced on both sides.
 __global__ void nct_to_ntc_kernel(const float* __restrict__ in, float scale,
                                   __nv_bfloat16* __restrict__ out, int C, int T, int Cp) {
+  pdl_sync();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -71,6 +73,7 @@ __global__ void nct_to_ntc_kernel(const float* __restrict__ in, float scale,
 __global__ void ntc_to_nct_kernel(const float* __restrict__ e_c, const float* __restrict__ e_u,
                                   long long ld, float s, float dt, float* __restrict__ x, int C,
                                   int T) {
+  pdl_sync();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -98,6 +101,7 @@ __global__ void ntc_to_nct_kernel(const float* __restrict__ e_c, const float* __
 // out[r, :] = table[idx[r], :] as bf16 (nn.Embedding, vocal2music_moe.py:336-337,388-389)
 __global__ void embed_rows_kernel(const long long* __restrict__ idx, const float* __restrict__ table,
                                   int V, int D, __nv_bfloat16* __restrict__ out, long long rows) {
+  pdl_sync();
   const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
@@ -115,6 +119,7 @@ __global__ void embed_rows_kernel(const long long* __restrict__ idx, const float
 __global__ void pool2_sum_kernel(const float* __restrict__ a, const float* __restrict__ b2, int Tin,
                                  int Tout, int D, __nv_bfloat16* __restrict__ out_bf16,
                                  float* __restrict__ out_f32, int B) {
+  pdl_sync();
   const long long n = (long long)B * Tout * D;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -134,6 +139,7 @@ __global__ void pool2_sum_kernel(const float* __restrict__ a, const float* __res
 // (autoencoder1d.py:165-166: 32 groups, eps 1e-6). fp64 accumulation.
 __global__ void gn_stats_kernel(const float* __restrict__ x, int T, int C, int G, float eps,
                                 float* __restrict__ mean, float* __restrict__ rstd) {
+  pdl_sync();
   const int g = blockIdx.x, b = blockIdx.y;
   const int cpg = C / G;
   const float* base = x + (long long)b * T * C + g * cpg;
@@ -176,6 +182,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, const float* __rest
                                 const float* __restrict__ rstd, const float* __restrict__ w,
                                 const float* __restrict__ bias, int T, int C, int G, int act,
                                 __nv_bfloat16* __restrict__ out, long long total_vec) {
+  pdl_sync();
   const int cpg = C / G;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
        i += (long long)gridDim.x * blockDim.x) {
@@ -204,6 +211,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, const float* __rest
 // One warp per 32 output samples: each lane owns one sample; weights in shared memory.
 __global__ void conv_post_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                  float bias, int T, int C, int k, float* __restrict__ wav) {
+  pdl_sync();
   extern __shared__ float sw[];
   for (int i = threadIdx.x; i < k * C; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
@@ -246,7 +254,7 @@ extern "C" int vb_ew(const float* a, const float* b, float alpha, float beta, in
   if (!a || rows <= 0 || D <= 0 || D % 4 != 0 || rep < 1 || (!out_f32 && !out_bf16))
     return set_error(VB_ERR_INVALID, "vb_ew: bad arguments (D %% 4 == 0)");
   const long long nvec = rows * (D / 4);
-  ew_kernel<<<grid_for(nvec, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(ew_kernel, dim3(grid_for(nvec, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       a, b, alpha, beta, act, slope, out_f32, static_cast<__nv_bfloat16*>(out_bf16), rows, D, rep);
   return check_launch("vb_ew");
 }
@@ -256,7 +264,7 @@ extern "C" int vb_nct_to_ntc(const float* in, float scale, void* out_bf16, int B
   vb::ProfScope prof_scope(vb::PK_LAYOUT, stream);
   if (!in || !out_bf16 || Cp < C) return set_error(VB_ERR_INVALID, "vb_nct_to_ntc: bad arguments");
   dim3 grid((T + 31) / 32, (Cp + 31) / 32, B), block(32, 8);
-  nct_to_ntc_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(nct_to_ntc_kernel, dim3(grid), dim3(block), 0, static_cast<cudaStream_t>(stream), 
       in, scale, static_cast<__nv_bfloat16*>(out_bf16), C, T, Cp);
   return check_launch("vb_nct_to_ntc");
 }
@@ -266,7 +274,7 @@ extern "C" int vb_ntc_to_nct(const float* e_c, const float* e_u, int64_t ld, flo
   vb::ProfScope prof_scope(vb::PK_LAYOUT, stream);
   if (!e_c || !x) return set_error(VB_ERR_INVALID, "vb_ntc_to_nct: bad arguments");
   dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
-  ntc_to_nct_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(e_c, e_u, ld, s, dt, x, C, T);
+  launch_k(ntc_to_nct_kernel, dim3(grid), dim3(block), 0, static_cast<cudaStream_t>(stream), e_c, e_u, ld, s, dt, x, C, T);
   return check_launch("vb_ntc_to_nct");
 }
 
@@ -274,7 +282,7 @@ extern "C" int vb_embed_rows(const int64_t* idx, const float* table, int V, int 
                              int64_t rows, void* stream) {
   vb::ProfScope prof_scope(vb::PK_LAYOUT, stream);
   if (!idx || !table || !out_bf16 || D % 2) return set_error(VB_ERR_INVALID, "vb_embed_rows: bad arguments");
-  embed_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(embed_rows_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const long long*>(idx), table, V, D, static_cast<__nv_bfloat16*>(out_bf16), rows);
   return check_launch("vb_embed_rows");
 }
@@ -284,7 +292,7 @@ extern "C" int vb_pool2_sum(const float* a, const float* b, int B, int Tin, int 
   vb::ProfScope prof_scope(vb::PK_EW, stream);
   if (!a || Tout * 2 > Tin) return set_error(VB_ERR_INVALID, "vb_pool2_sum: bad arguments");
   const long long n = (long long)B * Tout * D;
-  pool2_sum_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(pool2_sum_kernel, dim3(grid_for(n, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       a, b, Tin, Tout, D, static_cast<__nv_bfloat16*>(out_bf16), out_f32, B);
   return check_launch("vb_pool2_sum");
 }
@@ -293,7 +301,7 @@ extern "C" int vb_gn_stats(const float* x, int B, int T, int C, int G, float eps
                            float* rstd, void* stream) {
   vb::ProfScope prof_scope(vb::PK_GN, stream);
   if (!x || !mean || !rstd || C % G) return set_error(VB_ERR_INVALID, "vb_gn_stats: bad arguments");
-  gn_stats_kernel<<<dim3(G, B), 512, 0, static_cast<cudaStream_t>(stream)>>>(x, T, C, G, eps, mean, rstd);
+  launch_k(gn_stats_kernel, dim3(dim3(G, B)), dim3(512), 0, static_cast<cudaStream_t>(stream), x, T, C, G, eps, mean, rstd);
   return check_launch("vb_gn_stats");
 }
 
@@ -304,7 +312,7 @@ extern "C" int vb_gn_apply(const float* x, const float* mean, const float* rstd,
   if (!x || !mean || !rstd || !w || !bias || !out_bf16 || C % 4 || C % G)
     return set_error(VB_ERR_INVALID, "vb_gn_apply: bad arguments");
   const long long nvec = (long long)B * T * C / 4;
-  gn_apply_kernel<<<grid_for(nvec, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(gn_apply_kernel, dim3(grid_for(nvec, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       x, mean, rstd, w, bias, T, C, G, act, static_cast<__nv_bfloat16*>(out_bf16), nvec);
   return check_launch("vb_gn_apply");
 }
@@ -314,7 +322,21 @@ extern "C" int vb_conv_post(const void* x_bf16, const float* w, float bias, int 
   vb::ProfScope prof_scope(vb::PK_CONV_POST, stream);
   if (!x_bf16 || !w || !wav || C % 8) return set_error(VB_ERR_INVALID, "vb_conv_post: bad arguments");
   dim3 grid((T + 127) / 128, B);
-  conv_post_kernel<<<grid, 128, k * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+  launch_k(conv_post_kernel, dim3(grid), dim3(128), k * C * sizeof(float), static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x_bf16), w, bias, T, C, k, wav);
   return check_launch("vb_conv_post");
+}
+
+// Debug aid: write the GPU global timer to *slot (in-graph timeline of an op sequence).
+namespace vb {
+__global__ void timestamp_kernel(unsigned long long* slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *slot = t;
+}
+}  // namespace vb
+
+extern "C" int vb_timestamp(uint64_t* slot, void* stream) {
+  vb::timestamp_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<unsigned long long*>(slot));
+  return vb::check_launch("vb_timestamp");
 }

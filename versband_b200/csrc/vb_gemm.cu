@@ -330,6 +330,7 @@ vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();  // prologue above overlaps the previous kernel; global memory is touched only below
 
   const int num_kb = p.num_kb;
   const int m_used = p.m_tiles_used ? *p.m_tiles_used : p.m_tiles;
@@ -484,7 +485,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKPar
                        cudaGetErrorString(e));
     attr_set = true;
   }
-  vb_gemm_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  launch_k(vb_gemm_kernel<BN>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, tmA, tmB, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return set_error(VB_ERR_CUDA, "vb_gemm launch failed: %s", cudaGetErrorString(e));

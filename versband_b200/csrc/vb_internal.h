@@ -35,6 +35,33 @@ struct ProfScope {
   ~ProfScope() { if (on) prof_stop(kind, s); }
 };
 
+// Programmatic dependent launch (PDL): every kernel of this library starts with pdl_sync() and is
+// launched with programmaticStreamSerializationAllowed, so the launch latency and prologue of
+// kernel N+1 overlap the execution of kernel N. griddepcontrol.wait blocks until the preceding
+// grid has fully completed (memory visible), which keeps stream-order semantics intact.
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));

@@ -14,28 +14,22 @@ __device__ __forceinline__ float wsum(float v) {
   return v;
 }
 
-// out[r, e] = bias[e] + sum_d x[r, d] * W[e, d]      (one warp per row, E <= 16)
+// out[r, e] = bias[e] + sum_d x[r, d] * W[e, d]      (one warp per (row, output) pair)
 __global__ void linear_small_kernel(const float* __restrict__ x, long long ldx,
                                     const float* __restrict__ W, const float* __restrict__ bias,
                                     float* __restrict__ out, int rows, int D, int E) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  pdl_sync();
+  const int pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  float acc[16];
-#pragma unroll
-  for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+  if (pair >= rows * E) return;
+  const int row = pair / E, e = pair - row * E;
   const float* xr = x + (long long)row * ldx;
-  for (int d = lane; d < D; d += 32) {
-    const float xv = xr[d];
-#pragma unroll
-    for (int e = 0; e < 16; ++e)
-      if (e < E) acc[e] = fmaf(xv, W[(long long)e * D + d], acc[e]);
-  }
-#pragma unroll
-  for (int e = 0; e < 16; ++e)
-    if (e < E) acc[e] = wsum(acc[e]);
-  if (lane == 0)
-    for (int e = 0; e < E; ++e) out[(long long)row * E + e] = acc[e] + (bias ? bias[e] : 0.f);
+  const float* wr = W + (long long)e * D;
+  float acc = 0.f;
+#pragma unroll 4
+  for (int d = lane; d < D; d += 32) acc = fmaf(__ldg(xr + d), __ldg(wr + d), acc);
+  acc = wsum(acc);
+  if (lane == 0) out[(long long)row * E + e] = acc + (bias ? bias[e] : 0.f);
 }
 
 // One warp per token n (= b*T + t).
@@ -44,24 +38,39 @@ __global__ void linear_small_kernel(const float* __restrict__ x, long long ldx,
 //               w = (1 - y[idx]) + y[idx]  (straight-through value)                       :81-93,150-151
 //  scale_c[n] = w_c * p[0], scale_a[n] = w_a * p[1]                                       :157-165
 template <int E>
-__global__ void router_kernel(const float* __restrict__ cap_feat, const float* __restrict__ Wc,
+__global__ void router_kernel(const float* __restrict__ cap_feat, const __nv_bfloat16* __restrict__ cap_feat_bf,
+                              const float* __restrict__ Wc,
                               const float* __restrict__ bc, const float* __restrict__ ac_logits,
                               const float* __restrict__ hl_logits, int hl_ld, int ac_ld, const float* __restrict__ e0,
                               const float* __restrict__ e1, const float* __restrict__ e2, float tau,
                               int N, int T, int D, int* __restrict__ idx_c, int* __restrict__ idx_a,
                               float* __restrict__ scale_c, float* __restrict__ scale_a,
-                              float* __restrict__ cap_logits_out) {
+                              float* __restrict__ cap_logits_out, int* __restrict__ bucket_count,
+                              float* __restrict__ usage, int* __restrict__ slot_c,
+                              int* __restrict__ slot_a) {
+  pdl_sync();
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
   float acc[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) acc[e] = 0.f;
-  const float* xr = cap_feat + (long long)n * D;
-  for (int d = lane; d < D; d += 32) {
-    const float xv = xr[d];
+  if (cap_feat_bf) {
+    const __nv_bfloat16* xr = cap_feat_bf + (long long)n * D;
+#pragma unroll 4
+    for (int d = lane; d < D; d += 32) {
+      const float xv = __bfloat162float(xr[d]);
 #pragma unroll
-    for (int e = 0; e < E; ++e) acc[e] = fmaf(xv, Wc[(long long)e * D + d], acc[e]);
+      for (int e = 0; e < E; ++e) acc[e] = fmaf(xv, __ldg(Wc + (long long)e * D + d), acc[e]);
+    }
+  } else {
+    const float* xr = cap_feat + (long long)n * D;
+#pragma unroll 4
+    for (int d = lane; d < D; d += 32) {
+      const float xv = xr[d];
+#pragma unroll
+      for (int e = 0; e < E; ++e) acc[e] = fmaf(xv, __ldg(Wc + (long long)e * D + d), acc[e]);
+    }
   }
 #pragma unroll
   for (int e = 0; e < E; ++e) acc[e] = wsum(acc[e]);
@@ -108,6 +117,73 @@ __global__ void router_kernel(const float* __restrict__ cap_feat, const float* _
   idx_a[n] = ia;
   scale_c[n] = wc * mask_c;
   scale_a[n] = wa * mask_a;
+  if (bucket_count) {  // unordered slot claim inside the (group, expert) bucket
+    slot_c[n] = atomicAdd(&bucket_count[ic], 1);
+    slot_a[n] = atomicAdd(&bucket_count[E + ia], 1);
+    atomicAdd(&usage[ic], wc * mask_c);
+    atomicAdd(&usage[E + ia], wa * mask_a);
+  }
+}
+
+// One small CTA: padded bucket starts, tile table, tile count, load-balancing loss; marks padding
+// rows invalid; re-zeroes the counters for the next evaluation.
+__global__ void moe_finalize_kernel(int* __restrict__ bucket_count, float* __restrict__ usage, int nb, int E,
+                                    int* __restrict__ bucket_start, int* __restrict__ row_map,
+                                    float* __restrict__ row_scale, int* __restrict__ tile_group,
+                                    int* __restrict__ m_tiles_used, int max_rows, float* __restrict__ lb_out) {
+  pdl_sync();
+  __shared__ int s_start[17], s_cnt[16];
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    float tot = 0.f;
+    for (int k = 0; k < nb; ++k) {
+      const int c = bucket_count[k];
+      s_cnt[k] = c;
+      s_start[k] = acc;
+      bucket_start[k] = acc;
+      const int padded = (c + 127) / 128 * 128;
+      for (int t = acc / 128; t < (acc + padded) / 128; ++t) tile_group[t] = k;
+      acc += padded;
+      tot += usage[k];
+    }
+    s_start[nb] = acc;
+    *m_tiles_used = acc / 128;
+    if (lb_out) {
+      float loss = 0.f;
+      const float total = tot * (float)E;
+      for (int k = 0; k < nb; ++k) {
+        const float u = usage[k] / (total + 1e-10f);
+        loss += u * logf(u + 1e-10f);
+      }
+      *lb_out = loss / (float)nb;
+    }
+  }
+  __syncthreads();
+  for (int k = 0; k < nb; ++k)
+    for (int s = s_start[k] + s_cnt[k] + threadIdx.x; s < s_start[k + 1]; s += blockDim.x) { row_map[s] = -1; row_scale[s] = 0.f; }
+  for (int s = s_start[nb] + threadIdx.x; s < max_rows; s += blockDim.x) { row_map[s] = -1; row_scale[s] = 0.f; }
+  __syncthreads();
+  if (threadIdx.x < nb) { bucket_count[threadIdx.x] = 0; usage[threadIdx.x] = 0.f; }
+}
+
+// One warp per (token, group) entry: place it in its bucket slot and copy its activation row.
+__global__ void moe_scatter_kernel(const int* __restrict__ idx_c, const int* __restrict__ idx_a,
+                                   const int* __restrict__ slot_c, const int* __restrict__ slot_a,
+                                   const float* __restrict__ scale_c, const float* __restrict__ scale_a,
+                                   const int* __restrict__ bucket_start, int N, int E, int D,
+                                   const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ xs,
+                                   int* __restrict__ row_map, float* __restrict__ row_scale) {
+  pdl_sync();
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= 2 * N) return;
+  const int g = i / N, n = i - g * N;
+  const int bucket = g * E + (g ? idx_a[n] : idx_c[n]);
+  const int slot = bucket_start[bucket] + (g ? slot_a[n] : slot_c[n]);
+  if (lane == 0) { row_map[slot] = i; row_scale[slot] = g ? scale_a[n] : scale_c[n]; }
+  const uint4* src = reinterpret_cast<const uint4*>(x + (long long)n * D);
+  uint4* dst = reinterpret_cast<uint4*>(xs + (long long)slot * D);
+  for (int k = lane; k < D / 8; k += 32) dst[k] = src[k];
 }
 
 // Single CTA. Entries i in [0, 2N): group g = i / N (0 caption, 1 acoustic), token = i % N,
@@ -119,6 +195,7 @@ __global__ void moe_sort_kernel(const int* __restrict__ idx_c, const int* __rest
                                 int N, int E, int* __restrict__ row_map, float* __restrict__ row_scale,
                                 int* __restrict__ tile_group, int* __restrict__ m_tiles_used,
                                 int max_rows, float* __restrict__ lb_out) {
+  pdl_sync();
   __shared__ int s_count[16];
   __shared__ int s_start[17];
   __shared__ float s_usage[16];
@@ -199,6 +276,7 @@ __global__ void moe_sort_kernel(const int* __restrict__ idx_c, const int* __rest
 __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ row_map,
                                    const int* __restrict__ m_tiles_used, int n_tokens, int D,
                                    __nv_bfloat16* __restrict__ out, int max_rows) {
+  pdl_sync();
   const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (slot >= max_rows || slot >= *m_tiles_used * 128) return;
@@ -221,24 +299,25 @@ extern "C" int vb_linear_small(const float* x, int64_t ldx, const float* W, cons
   vb::ProfScope prof_scope(vb::PK_ROUTER, stream);
   if (!x || !W || !out || rows <= 0 || E <= 0 || E > 16)
     return set_error(VB_ERR_INVALID, "vb_linear_small: bad arguments (E <= 16)");
-  linear_small_kernel<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, W, bias,
+  launch_k(linear_small_kernel, dim3((rows * E + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream), x, ldx, W, bias,
                                                                                      out, rows, D, E);
   return check_launch("vb_linear_small");
 }
 
-extern "C" int vb_router(const float* cap_feat, const float* Wc, const float* bc,
+extern "C" int vb_router(const float* cap_feat, const void* cap_feat_bf16, const float* Wc, const float* bc,
                          const float* ac_logits, int ac_ld, const float* hl_logits, int hl_ld,
                          const float* e0, const float* e1, const float* e2, float tau, int N, int T, int D, int E,
                          int32_t* idx_c, int32_t* idx_a, float* scale_c, float* scale_a,
-                         float* cap_logits_out, void* stream) {
+                         float* cap_logits_out, int32_t* bucket_count, float* usage, int32_t* slot_c,
+                         int32_t* slot_a, void* stream) {
   vb::ProfScope prof_scope(vb::PK_ROUTER, stream);
-  if (!cap_feat || !Wc || !bc || !ac_logits || !hl_logits || !e0 || !e1 || !e2 || !idx_c || !idx_a ||
+  if ((!cap_feat && !cap_feat_bf16) || !Wc || !bc || !ac_logits || !hl_logits || !e0 || !e1 || !e2 || !idx_c || !idx_a ||
       !scale_c || !scale_a || N <= 0 || T <= 0)
     return set_error(VB_ERR_INVALID, "vb_router: null/invalid argument");
   if (E != 4) return set_error(VB_ERR_INVALID, "vb_router: num_experts %d not instantiated (4)", E);
-  router_kernel<4><<<(N + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      cap_feat, Wc, bc, ac_logits, hl_logits, hl_ld, ac_ld, e0, e1, e2, tau, N, T, D, idx_c, idx_a, scale_c, scale_a,
-      cap_logits_out);
+  launch_k(router_kernel<4>, dim3((N + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      cap_feat, static_cast<const __nv_bfloat16*>(cap_feat_bf16), Wc, bc, ac_logits, hl_logits, hl_ld, ac_ld, e0, e1, e2, tau, N, T, D, idx_c, idx_a, scale_c, scale_a,
+      cap_logits_out, bucket_count, usage, slot_c, slot_a);
   return check_launch("vb_router");
 }
 
@@ -251,7 +330,7 @@ extern "C" int vb_moe_sort(const int32_t* idx_c, const int32_t* idx_a, const flo
     return set_error(VB_ERR_INVALID, "vb_moe_sort: bad arguments");
   if (max_rows < ((2 * N + 127) / 128 + 2 * E) * 128)
     return set_error(VB_ERR_INVALID, "vb_moe_sort: max_rows %d too small for N=%d E=%d", max_rows, N, E);
-  moe_sort_kernel<<<1, 512, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(moe_sort_kernel, dim3(1), dim3(512), 0, static_cast<cudaStream_t>(stream), 
       idx_c, idx_a, scale_c, scale_a, N, E, row_map, row_scale, tile_group, m_tiles_used, max_rows, lb_out);
   return check_launch("vb_moe_sort");
 }
@@ -260,8 +339,33 @@ extern "C" int vb_gather_rows(const void* x, const int32_t* row_map, const int32
                               int n_tokens, int D, void* out, int max_rows, void* stream) {
   vb::ProfScope prof_scope(vb::PK_MOE_SORT, stream);
   if (!x || !row_map || !out || D % 8 != 0) return set_error(VB_ERR_INVALID, "vb_gather_rows: bad arguments");
-  gather_rows_kernel<<<(max_rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(gather_rows_kernel, dim3((max_rows + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), row_map, m_tiles_used, n_tokens, D,
       static_cast<__nv_bfloat16*>(out), max_rows);
   return check_launch("vb_gather_rows");
+}
+
+extern "C" int vb_moe_finalize(int32_t* bucket_count, float* usage, int E, int32_t* bucket_start,
+                               int32_t* row_map, float* row_scale, int32_t* tile_group,
+                               int32_t* m_tiles_used, int max_rows, float* lb_out, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_MOE_SORT, stream);
+  if (!bucket_count || !usage || !bucket_start || !row_map || !row_scale || !tile_group || !m_tiles_used ||
+      E <= 0 || E > 8)
+    return set_error(VB_ERR_INVALID, "vb_moe_finalize: bad arguments");
+  launch_k(moe_finalize_kernel, dim3(1), dim3(256), 0, static_cast<cudaStream_t>(stream), bucket_count, usage,
+           2 * E, E, bucket_start, row_map, row_scale, tile_group, m_tiles_used, max_rows, lb_out);
+  return check_launch("vb_moe_finalize");
+}
+
+extern "C" int vb_moe_scatter(const int32_t* idx_c, const int32_t* idx_a, const int32_t* slot_c,
+                              const int32_t* slot_a, const float* scale_c, const float* scale_a,
+                              const int32_t* bucket_start, int N, int E, int D, const void* x_bf16,
+                              void* xs_bf16, int32_t* row_map, float* row_scale, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_MOE_SORT, stream);
+  if (!idx_c || !idx_a || !slot_c || !slot_a || !bucket_start || !x_bf16 || !xs_bf16 || D % 8)
+    return set_error(VB_ERR_INVALID, "vb_moe_scatter: bad arguments");
+  launch_k(moe_scatter_kernel, dim3((2 * N + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream), idx_c,
+           idx_a, slot_c, slot_a, scale_c, scale_a, bucket_start, N, E, D,
+           static_cast<const __nv_bfloat16*>(x_bf16), static_cast<__nv_bfloat16*>(xs_bf16), row_map, row_scale);
+  return check_launch("vb_moe_scatter");
 }

@@ -27,6 +27,7 @@ __global__ void norm_mod_kernel(const float* __restrict__ x, const float* __rest
                                 const float* __restrict__ scale, long long mod_ld,
                                 int rows_per_batch, float eps, __nv_bfloat16* __restrict__ out_bf16,
                                 float* __restrict__ out_f32, int rows, int D) {
+  pdl_sync();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -85,6 +86,7 @@ __global__ void norm_mod_kernel(const float* __restrict__ x, const float* __rest
 __global__ void softmax_rows_kernel(const float* __restrict__ S, long long lds,
                                     __nv_bfloat16* __restrict__ P, long long ldp, long long rows,
                                     int n) {
+  pdl_sync();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -114,6 +116,7 @@ __global__ void attn_smallkv_kernel(const __nv_bfloat16* __restrict__ q, long lo
                                     const float* __restrict__ gate, const float* __restrict__ base,
                                     __nv_bfloat16* __restrict__ out_bf16,
                                     float* __restrict__ out_f32, int tokens_per_block) {
+  pdl_sync();
   extern __shared__ float sm[];
   constexpr int HP = HD + 1;
   float* sK = sm;
@@ -201,6 +204,7 @@ __global__ void attn_smallkv_kernel(const __nv_bfloat16* __restrict__ q, long lo
 __global__ void timestep_embed_kernel(const long long* __restrict__ t, const float* __restrict__ freqs,
                                       float* __restrict__ out_f32,
                                       __nv_bfloat16* __restrict__ out_bf16, int B, int dim) {
+  pdl_sync();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * half) return;
@@ -230,10 +234,10 @@ extern "C" int vb_norm_mod(int kind, const float* x, const float* w, const float
   dim3 grid((rows + wpb - 1) / wpb), block(wpb * 32);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (kind == 0)
-    norm_mod_kernel<0><<<grid, block, 0, s>>>(x, w, b, shift, scale, mod_ld, rows_per_batch, eps,
+    launch_k(norm_mod_kernel<0>, dim3(grid), dim3(block), 0, s, x, w, b, shift, scale, mod_ld, rows_per_batch, eps,
                                               static_cast<__nv_bfloat16*>(out_bf16), out_f32, rows, D);
   else
-    norm_mod_kernel<1><<<grid, block, 0, s>>>(x, w, b, shift, scale, mod_ld, rows_per_batch, eps,
+    launch_k(norm_mod_kernel<1>, dim3(grid), dim3(block), 0, s, x, w, b, shift, scale, mod_ld, rows_per_batch, eps,
                                               static_cast<__nv_bfloat16*>(out_bf16), out_f32, rows, D);
   return check_launch("vb_norm_mod");
 }
@@ -245,7 +249,7 @@ extern "C" int vb_softmax_rows(const float* S, int64_t lds, void* P, int64_t ldp
     return set_error(VB_ERR_INVALID, "vb_softmax_rows: bad arguments");
   const int wpb = 8;
   dim3 grid((unsigned)((rows + wpb - 1) / wpb)), block(wpb * 32);
-  softmax_rows_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(softmax_rows_kernel, dim3(grid), dim3(block), 0, static_cast<cudaStream_t>(stream), 
       S, lds, static_cast<__nv_bfloat16*>(P), ldp, rows, n);
   return check_launch("vb_softmax_rows");
 }
@@ -270,7 +274,7 @@ extern "C" int vb_attn_smallkv(const void* q, int64_t q_sb, int64_t q_st, int64_
       if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "attn_smallkv smem attr: %s", cudaGetErrorString(e));
       attr_smem = smem;
     }
-    kern<<<grid, threads, smem, s>>>(static_cast<const __nv_bfloat16*>(q), q_sb, q_st, q_sh, K, V, kv_ld, L,
+    launch_k(kern, dim3(grid), dim3(threads), smem, s, static_cast<const __nv_bfloat16*>(q), q_sb, q_st, q_sh, K, V, kv_ld, L,
                                      H, T, scale, gate, base, static_cast<__nv_bfloat16*>(out_bf16),
                                      out_f32, tpb);
     return check_launch("vb_attn_smallkv");
@@ -285,7 +289,7 @@ extern "C" int vb_timestep_embed(const int64_t* t, const float* freqs, float* ou
   vb::ProfScope prof_scope(vb::PK_EW, stream);
   if (!t || !freqs || B <= 0 || dim <= 0 || dim % 2) return set_error(VB_ERR_INVALID, "vb_timestep_embed: bad arguments");
   const int n = B * dim / 2;
-  timestep_embed_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(timestep_embed_kernel, dim3((n + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const long long*>(t), freqs, out_f32, static_cast<__nv_bfloat16*>(out_bf16), B, dim);
   return check_launch("vb_timestep_embed");
 }
@@ -293,6 +297,7 @@ extern "C" int vb_timestep_embed(const int64_t* t, const float* freqs, float* ou
 // mean over the token axis: out[b, d] = (1/L) sum_l x[b, l, d]   (vocal2music_moe.py:410-412)
 namespace vb {
 __global__ void mean_tokens_kernel(const float* __restrict__ x, int L, int D, float* __restrict__ out) {
+  pdl_sync();
   const int b = blockIdx.y;
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= D) return;
@@ -305,6 +310,6 @@ __global__ void mean_tokens_kernel(const float* __restrict__ x, int L, int D, fl
 extern "C" int vb_mean_tokens(const float* x, int B, int L, int D, float* out, void* stream) {
   vb::ProfScope prof_scope(vb::PK_EW, stream);
   if (!x || !out || B <= 0 || L <= 0) return set_error(VB_ERR_INVALID, "vb_mean_tokens: bad arguments");
-  mean_tokens_kernel<<<dim3((D + 127) / 128, B), 128, 0, static_cast<cudaStream_t>(stream)>>>(x, L, D, out);
+  launch_k(mean_tokens_kernel, dim3(dim3((D + 127) / 128, B)), dim3(128), 0, static_cast<cudaStream_t>(stream), x, L, D, out);
   return check_launch("vb_mean_tokens");
 }

@@ -140,8 +140,12 @@ class DiTEngine:
             ipw, ipb = g(f + "cross_attention.in_proj_weight"), g(f + "cross_attention.in_proj_bias")
             b["mq_w"], b["mq_b"] = _bf(ipw[:D]), ipb[:D].contiguous()
             b["mkv_w"], b["mkv_b"] = _bf(ipw[D:]), ipb[D:].contiguous()
-            b["mo_w"], b["mo_b"] = _bf(g(f + "cross_attention.out_proj.weight")), g(f + "cross_attention.out_proj.bias")
-            b["capg_w"], b["capg_b"] = g(f + "caption_gating_network.weight"), g(f + "caption_gating_network.bias")
+            # caption gate folded through the MHA out-projection (its only consumer, vocal2music_moe.py:122,141):
+            # logits = Wg (Wo ctx + bo) + bg = (Wg Wo) ctx + (Wg bo + bg), all in fp32
+            wo_m, bo_m = g(f + "cross_attention.out_proj.weight"), g(f + "cross_attention.out_proj.bias")
+            wg, bg = g(f + "caption_gating_network.weight"), g(f + "caption_gating_network.bias")
+            b["capg_w"] = (wg.double() @ wo_m.double()).float().contiguous()
+            b["capg_b"] = (wg.double() @ bo_m.double() + bg.double()).float().contiguous()
             w13, w2 = [], []
             for grp in ("caption_experts", "acoustic_experts"):
                 for e in range(E):
@@ -189,9 +193,10 @@ class DiTEngine:
             mod=z(B, self.mod_ld), hl=z(B, 2 * self.depth),
             xa=z(N, D, dt=BF), q=z(B, H, T, hd, dt=BF), k=z(B, H, T, hd, dt=BF), vt=z(B, H, hd, Tp, dt=BF),
             oa=z(N, D, dt=BF),
-            xm=z(N, D, dt=BF), qm=z(N, D, dt=BF), ctx=z(N, D, dt=BF), cap_feat=z(N, D),
+            xm=z(N, D, dt=BF), qm=z(N, D, dt=BF), ctx=z(N, D, dt=BF),
             idx_c=z(N, dt=torch.int32), idx_a=z(N, dt=torch.int32), scale_c=z(N), scale_a=z(N),
-            cap_logits=z(N, E),
+            cap_logits=z(N, E), bucket_count=z(2 * E, dt=torch.int32), usage=z(2 * E), bucket_start=z(2 * E, dt=torch.int32),
+            slot_c=z(N, dt=torch.int32), slot_a=z(N, dt=torch.int32),
             row_map=z(max_rows, dt=torch.int32), row_scale=z(max_rows), tile_group=z(max_rows // 128, dt=torch.int32),
             m_tiles=z(1, dt=torch.int32), lb=z(self.depth),
             xs=z(max_rows, D, dt=BF), hs=z(max_rows, Fh, dt=BF), y2=z(2 * N, D), y=z(N, D, dt=BF),
@@ -292,16 +297,24 @@ class DiTEngine:
         # stem: proj_in conv (k5) + bias, fused "+ acoustic"  (vocal2music_moe.py:395,415)
         for r in range(B // Bx):  # CFG batching: the same latent feeds every conditioning branch
             ops.nct_to_ntc(x.contiguous(), ws["x_cl"][r * Bx:(r + 1) * Bx])
+            ops.mark("nct_to_ntc")
         ops.gemm(ws["x_cl"][:, :, :C], w["proj_in_w"], M=T, G1=B, kpt=1, dil=1, pad=self.proj_in_k // 2,
                  a_c2=(1, 0), bias=w["proj_in_b"], residual=cond.acoustic, out_f32=ws["x"], out_ld=D,
                  out_g=(T * D, 0))
+        ops.mark("gemm:proj_in_w")
         # timestep embedding MLP and adaLN input (:406,416)
         ops.timestep_embed(t.contiguous(), w["t_freqs"], out_bf16=ws["temb_sin"])
+        ops.mark("timestep_embed")
         ops.gemm(ws["temb_sin"], w["t_w0"], bias=w["t_b0"], act=ops.ACT_SILU, out_bf16=ws["temb_h"], outb_ld=D)
+        ops.mark("gemm:t_w0")
         ops.gemm(ws["temb_h"], w["t_w2"], bias=w["t_b2"], out_f32=ws["temb"], out_ld=D)
+        ops.mark("gemm:t_w2")
         ops.ew(ws["temb"], cond.cap_emb, act=ops.ACT_SILU, out_bf16=ws["ada_in"])
+        ops.mark("ew")
         ops.gemm(ws["ada_in"], w["ada_w"], bias=w["ada_b"], out_f32=ws["mod"], out_ld=self.mod_ld)
+        ops.mark("gemm:ada_w")
         ops.linear_small(ws["temb"], w["hl_w"], w["hl_b"], ws["hl"])
+        ops.mark("linear_small")
         mod, mld = ws["mod"], self.mod_ld
 
         xcur, hbuf = ws["x"], ws["h"]
@@ -313,41 +326,57 @@ class DiTEngine:
             # ---- attention branch (vocal2music_moe.py:245-250; flag_large_dit_moe.py:323-406)
             ops.norm_mod(xcur, kind=0, w=b["attn_norm"], shift=sh_msa, scale=sc_msa, mod_ld=mld,
                          rows_per_batch=T, eps=self.eps, out_bf16=ws["xa"])
+            ops.mark("norm_mod")
             ops.gemm(ws["xa"], b["wqkv"], mode=ops.EPI_QKV_ROPE, rope_cs=w["rope"], T=T, heads=H, head_dim=hd,
                      Tp=Tp, q_out=ws["q"], k_out=ws["k"], vt_out=ws["vt"])
+            ops.mark("gemm:wqkv")
             # self-attention + gated text cross-attention in one tcgen05 flash-attention launch
             ops.attn_fused(ws["q"], (hd, T * hd, H * T * hd), B=B, T=T, H=H, hd=hd, scale=scale,
                            k_self=ws["k"], vt_self=ws["vt"], Tp=Tp, k_text=cond.k_y[k], vt_text=cond.vt_y[k],
                            L=L, Lp=cond.vt_y[k].shape[-1], gate=b["gate"], out_bf16=ws["oa"])
+            ops.mark("attn_fused")
             ops.gemm(ws["oa"], b["wo"], gate=g_msa, gate_rows=T, gate_ld=mld, residual=xcur,
                      out_f32=hbuf, out_ld=D)
+            ops.mark("gemm:wo")
             # ---- Band-MoE branch (vocal2music_moe.py:251-257, 117-185)
             ops.norm_mod(hbuf, kind=0, w=b["ffn_norm"], shift=sh_mlp, scale=sc_mlp, mod_ld=mld,
                          rows_per_batch=T, eps=self.eps, out_bf16=ws["xm"])
+            ops.mark("norm_mod")
             ops.gemm(ws["xm"], b["mq_w"], bias=b["mq_b"], out_bf16=ws["qm"], outb_ld=D)
+            ops.mark("gemm:mq_w")
             ops.attn_fused(ws["qm"], (D, hd, T * D), B=B, T=T, H=H, hd=hd, scale=scale, k_text=cond.k_m[k],
                            vt_text=cond.vt_m[k], L=L, Lp=cond.vt_m[k].shape[-1], out_bf16=ws["ctx"])
-            ops.gemm(ws["ctx"], b["mo_w"], bias=b["mo_b"], out_f32=ws["cap_feat"], out_ld=D)
+            ops.mark("attn_fused")
             e0, e1, e2 = expo[k]
-            ops.router(ws["cap_feat"], b["capg_w"], b["capg_b"], cond.ac_logits[:, k * E:], self.depth * E,
+            ops.router(ws["ctx"], b["capg_w"], b["capg_b"], cond.ac_logits[:, k * E:], self.depth * E,
                        ws["hl"][:, 2 * k:], 2 * self.depth, e0, e1, e2, float(self.temperature), N, T,
                        ws["idx_c"], ws["idx_a"], ws["scale_c"], ws["scale_a"],
-                       ws["cap_logits"] if want_aux else None)
-            ops.moe_sort(ws["idx_c"], ws["idx_a"], ws["scale_c"], ws["scale_a"], N, E, ws["row_map"],
-                         ws["row_scale"], ws["tile_group"], ws["m_tiles"], max_rows, ws["lb"][k:])
-            ops.gather_rows(ws["xm"], ws["row_map"], ws["m_tiles"], N, ws["xs"], max_rows)
+                       ws["cap_logits"] if want_aux else None, ws["bucket_count"], ws["usage"],
+                       ws["slot_c"], ws["slot_a"])
+            ops.mark("router")
+            ops.moe_finalize(ws["bucket_count"], ws["usage"], E, ws["bucket_start"], ws["row_map"], ws["row_scale"],
+                             ws["tile_group"], ws["m_tiles"], max_rows, ws["lb"][k:])
+            ops.mark("moe_finalize")
+            ops.moe_scatter(ws["idx_c"], ws["idx_a"], ws["slot_c"], ws["slot_a"], ws["scale_c"], ws["scale_a"],
+                            ws["bucket_start"], N, E, ws["xm"], ws["xs"], ws["row_map"], ws["row_scale"])
+            ops.mark("moe_scatter")
             ops.gemm(ws["xs"], b["w13"], M=max_rows, b_c2=(0, 0, 1), tile_group=ws["tile_group"],
                      m_tiles_used=ws["m_tiles"], swiglu=True, out_bf16=ws["hs"], outb_ld=Fh)
+            ops.mark("gemm:w13")
             ops.gemm(ws["hs"], b["w2"], M=max_rows, b_c2=(0, 0, 1), tile_group=ws["tile_group"],
                      m_tiles_used=ws["m_tiles"], row_map=ws["row_map"], rows_out=2 * N,
                      row_scale=ws["row_scale"], out_f32=ws["y2"], out_ld=D)
+            ops.mark("gemm:w2")
             ops.ew(ws["y2"][:N], ws["y2"][N:], out_bf16=ws["y"])
+            ops.mark("ew")
             yb = ws["y"].view(N, E, self.band).permute(1, 0, 2)  # [E, N, band] view: per-band K slice
             ops.gemm(yb, b["f13"], M=N, G1=E, a_c2=(1, 0), b_c2=(1, 0, 0), swiglu=True,
                      out_bf16=ws["hf"], outb_ld=Fh, outb_g=(N * Fh, 0))
+            ops.mark("gemm:f13")
             ops.gemm(ws["hf"], b["f2"], M=N, G1=E, a_c2=(1, 0), b_c2=(1, 0, 0),
                      gate=g_mlp, gate_rows=T, gate_ld=mld, gate_g1=self.band, residual=hbuf,
                      out_f32=xcur, out_ld=D, out_g=(self.band, 0))
+            ops.mark("gemm:f2")
             if want_aux:
                 aux.append(dict(idx_c=ws["idx_c"].clone(), idx_a=ws["idx_a"].clone(),
                                 cap_logits=ws["cap_logits"].clone(), h=hbuf.clone(), x=xcur.clone()))
@@ -355,7 +384,10 @@ class DiTEngine:
         f0 = self.depth * 6 * D
         ops.norm_mod(xcur, kind=1, shift=mod[:, f0:], scale=mod[:, f0 + D:], mod_ld=mld, rows_per_batch=T,
                      eps=1e-6, out_bf16=ws["xf"])
+        ops.mark("norm_mod")
         ops.gemm(ws["xf"], w["final_w"], N=C, bias=w["final_b"], out_f32=ws["v"], out_ld=32)
+        ops.mark("gemm:final_w")
         if out_v is not None:
             ops.ntc_to_nct(ws["v"], out_v, ld=32)
+            ops.mark("ntc_to_nct")
         return (ws["v"], ws["lb"], aux) if want_aux else (ws["v"], ws["lb"])

@@ -145,10 +145,24 @@ def linear_small(x, W, bias, out) -> None:
 
 
 def router(cap_feat, Wc, bc, ac_logits, ac_ld, hl_logits, hl_ld, e0, e1, e2, tau, N, T, idx_c, idx_a,
-           scale_c, scale_a, cap_logits_out=None) -> None:
-    _call("vb_router", _ptr(cap_feat), _ptr(Wc), _ptr(bc), _ptr(ac_logits), ac_ld, _ptr(hl_logits), hl_ld, _ptr(e0),
-          _ptr(e1), _ptr(e2), tau, N, T, cap_feat.shape[-1], Wc.shape[0], _ptr(idx_c), _ptr(idx_a),
-          _ptr(scale_c), _ptr(scale_a), _ptr(cap_logits_out))
+           scale_c, scale_a, cap_logits_out=None, bucket_count=None, usage=None, slot_c=None, slot_a=None) -> None:
+    f32 = cap_feat if cap_feat.dtype == torch.float32 else None
+    b16 = cap_feat if cap_feat.dtype == torch.bfloat16 else None
+    _call("vb_router", _ptr(f32), _ptr(b16), _ptr(Wc), _ptr(bc), _ptr(ac_logits), ac_ld, _ptr(hl_logits), hl_ld,
+          _ptr(e0), _ptr(e1), _ptr(e2), tau, N, T, cap_feat.shape[-1], Wc.shape[0], _ptr(idx_c), _ptr(idx_a),
+          _ptr(scale_c), _ptr(scale_a), _ptr(cap_logits_out), _ptr(bucket_count), _ptr(usage), _ptr(slot_c),
+          _ptr(slot_a))
+
+
+def moe_finalize(bucket_count, usage, E, bucket_start, row_map, row_scale, tile_group, m_tiles_used, max_rows,
+                 lb_out=None) -> None:
+    _call("vb_moe_finalize", _ptr(bucket_count), _ptr(usage), E, _ptr(bucket_start), _ptr(row_map), _ptr(row_scale),
+          _ptr(tile_group), _ptr(m_tiles_used), max_rows, _ptr(lb_out))
+
+
+def moe_scatter(idx_c, idx_a, slot_c, slot_a, scale_c, scale_a, bucket_start, N, E, x, xs, row_map, row_scale) -> None:
+    _call("vb_moe_scatter", _ptr(idx_c), _ptr(idx_a), _ptr(slot_c), _ptr(slot_a), _ptr(scale_c), _ptr(scale_a),
+          _ptr(bucket_start), N, E, x.shape[-1], _ptr(x), _ptr(xs), _ptr(row_map), _ptr(row_scale))
 
 
 def moe_sort(idx_c, idx_a, scale_c, scale_a, N, E, row_map, row_scale, tile_group, m_tiles_used, max_rows,
@@ -212,3 +226,17 @@ def attn_fused(q, q_strides, *, B, T, H, hd, scale, k_self=None, vt_self=None, T
     a.gate, a.out_bf16, a.out_f32 = _ptr(gate), _ptr(out_bf16), _ptr(out_f32)
     a.B, a.T, a.H, a.hd, a.Tp, a.L, a.Lp, a.scale = B, T, H, hd, Tp, L, Lp, scale
     _lib.check(_lib.lib().vb_attn_fused(C.byref(a), _stream()), "vb_attn_fused")
+
+
+# ---- debug timeline: ops.TIMELINE = (int64 cuda tensor, [names]) enables a timestamp after each op
+TIMELINE = None
+
+
+def mark(name: str) -> None:
+    if TIMELINE is None:
+        return
+    buf, names = TIMELINE
+    i = len(names)
+    if i < buf.numel():
+        names.append(name)
+        _lib.check(_lib.lib().vb_timestamp(C.c_void_p(buf.data_ptr() + 8 * i), _stream()), "vb_timestamp")
