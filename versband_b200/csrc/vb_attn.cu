@@ -11,13 +11,15 @@
 //   segment 1: one tile of L <= 128 "text" keys      out += tanh(gate[h]) * O1 / l1
 // With segment 0 disabled the kernel is the MoE cross-attention of vocal2music_moe.py:119.
 //
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer,
-// warps 2..5 softmax/epilogue (thread = query row = TMEM lane).
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer,
+// warps 2..9 softmax/epilogue (two threads per query row, each owning half of the columns).
 #include <math_constants.h>
 #include "vb_internal.h"
 #include "vb_ptx.cuh"
 
 namespace vb {
+
+static long long* g_attn_trace = nullptr;
 
 struct AttnKParams {
   int T, L, H, n_self;
@@ -26,6 +28,7 @@ struct AttnKParams {
   const float* gate;
   __nv_bfloat16* out_bf16;
   float* out_f32;
+  long long* trace;  // debug: per-tile clock64 stamps of CTA (0,0,0)
 };
 
 template <int HD>
@@ -34,11 +37,11 @@ struct AttnCfg {
   static constexpr int kKBytes = 2 * 16384;            // K tile per stage
   static constexpr int kVBytes = 2 * HD * 128;         // V^T tile per stage: 2 k-blocks of [HD x 64]
   static constexpr int kPBytes = 2 * 16384;            // P tile
-  static constexpr int kSmem = kQBytes + 2 * kKBytes + 2 * kVBytes + kPBytes + 1024 + 256;
+  static constexpr int kSmem = kQBytes + 2 * kKBytes + 2 * kVBytes + kPBytes + 1024 + 256 + 1024;  // + row exchange
 };
 
 template <int HD>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKs,
                   const __grid_constant__ CUtensorMap tmVs, const __grid_constant__ CUtensorMap tmKt,
                   const __grid_constant__ CUtensorMap tmVt, const AttnKParams p) {
@@ -74,9 +77,9 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mbar_init(&kv_empty[i], 1);
       mbar_init(&s_full[i], 1);
     }
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 256);
     mbar_init(o_full, 1);
-    mbar_init(o_empty, 128);
+    mbar_init(o_empty, 256);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -146,108 +149,141 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
     }
   } else {
+    // Two threads per query row: half 0 (warps 2..5) owns score columns 0..63 and output dims
+    // 0..HD/2-1, half 1 (warps 6..9) the rest. S is read from TMEM once (it is the TMEM read port,
+    // 64 B/clk/SM, that bounds this loop), the row maximum is exchanged through shared memory.
+    constexpr int HH = HD / 2;
+    const int half = (warp - 2) >> 2;
     const int qd = warp & 3;
     const int row = qd * 32 + lane;
     const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
-    float acc[HD];
+    float acc[HH];
 #pragma unroll
-    for (int i = 0; i < HD; ++i) acc[i] = 0.f;
-    float m = -CUDART_INF_F, l = 0.f;
-    const float scale = p.scale;
+    for (int i = 0; i < HH; ++i) acc[i] = 0.f;
+    constexpr float kLog2e = 1.4426950408889634f;
+    float m2 = -CUDART_INF_F, l = 0.f;  // running max (log2 domain) and this half's partial sum
+    const float c1 = p.scale * kLog2e;
     const float g = p.gate ? tanhf(p.gate[h]) : 1.f;
     const int rsw = row & 7;
-    uint8_t* prow = sP + (row >> 3) * 1024 + rsw * 128;
+    uint8_t* prow = sP + half * 16384 + (row >> 3) * 1024 + rsw * 128;
+    float* xch = reinterpret_cast<float*>(tmem_slot + 4);  // [2 halves][128 rows] exchange buffer
     for (int j = 0; j < n_tiles; ++j) {
       const bool text = j >= n_self;
       if (text) {
-        if (n_self > 0) {
-          const float inv = 1.f / l;
+        if (n_self > 0) {  // close the self segment: acc /= (l_half0 + l_half1)
+          xch[half * 128 + row] = l;
+          named_bar_sync(1 + qd, 64);
+          const float inv = 1.f / (l + xch[(half ^ 1) * 128 + row]);
+          named_bar_sync(1 + qd, 64);
 #pragma unroll
-          for (int i = 0; i < HD; ++i) acc[i] *= inv;
+          for (int i = 0; i < HH; ++i) acc[i] *= inv;
         }
-        m = -CUDART_INF_F;
+        m2 = -CUDART_INF_F;
         l = 0.f;
       }
-      const int valid = text ? p.L : min(128, p.T - j * 128);
-      const uint32_t tS = tmem_base + (j & 1) * 128 + lane_sel;
+      const int valid = (text ? p.L : min(128, p.T - j * 128)) - half * 64;  // valid columns of my half
+      const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && row == 0 && half == 0;
+      if (tr) p.trace[j * 8 + 0] = clock64();
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      // pass A: row maximum over the valid keys of this tile
-      float tmax = -CUDART_INF_F;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        if (c * 32 >= valid) break;
-        uint32_t raw[32];
-        tmem_ld32(tS + c * 32, raw);
+      if (tr) p.trace[j * 8 + 1] = clock64();
+      float sv[64];
+      {
+        const uint32_t tS = tmem_base + (j & 1) * 128 + half * 64 + lane_sel;
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tS, r0);
+        tmem_ld32(tS + 32, r1);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < valid) tmax = fmaxf(tmax, __uint_as_float(raw[i]));
+        for (int i = 0; i < 32; ++i) { sv[i] = __uint_as_float(r0[i]); sv[32 + i] = __uint_as_float(r1[i]); }
       }
-      const float m_new = fmaxf(m, tmax * scale);
-      const float alpha = (m == -CUDART_INF_F) ? 0.f : __expf(m - m_new);
-      // pass B: p = exp(s*scale - m_new) -> bf16 -> swizzled smem (A operand of MMA2)
-      float rowsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t packed[16];
-        if (c * 32 < valid) {
-          uint32_t raw[32];
-          tmem_ld32(tS + c * 32, raw);
-          tmem_ld_wait();
+      if (valid < 64) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float p0 = (c * 32 + 2 * i < valid) ? __expf(__uint_as_float(raw[2 * i]) * scale - m_new) : 0.f;
-            float p1 = (c * 32 + 2 * i + 1 < valid) ? __expf(__uint_as_float(raw[2 * i + 1]) * scale - m_new) : 0.f;
-            rowsum += p0 + p1;
-            __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
-            packed[i] = *reinterpret_cast<uint32_t*>(&t);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) packed[i] = 0u;
-        }
-        uint8_t* pk = prow + (c >> 1) * 16384;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int ch = (c & 1) * 4 + i;
-          *reinterpret_cast<uint4*>(pk + ((ch ^ rsw) << 4)) =
-              make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
-        }
+        for (int i = 0; i < 64; ++i) if (i >= valid) sv[i] = -CUDART_INF_F;
       }
-      l = l * alpha + rowsum;
-      m = m_new;
+      float tmax = -CUDART_INF_F;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) tmax = fmaxf(tmax, sv[i]);
+      xch[half * 128 + row] = tmax;
+      named_bar_sync(1 + qd, 64);
+      tmax = fmaxf(tmax, xch[(half ^ 1) * 128 + row]);
+      if (tr) p.trace[j * 8 + 2] = clock64();
+      const float m_new = fmaxf(m2, tmax * c1);
+      const float alpha = (m2 == -CUDART_INF_F) ? 0.f : ex2_ftz(m2 - m_new);
+      // p = 2^(s*c1 - m_new)  (ftz: masked columns are -inf -> exactly 0)
+#pragma unroll
+      for (int i = 0; i < 64; ++i) sv[i] = ex2_ftz(fmaf(sv[i], c1, -m_new));
+      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) { rs0 += sv[i]; rs1 += sv[i + 1]; rs2 += sv[i + 2]; rs3 += sv[i + 3]; }
+      l = l * alpha + ((rs0 + rs1) + (rs2 + rs3));
+      m2 = m_new;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        uint4 w;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(sv[8 * ch], sv[8 * ch + 1]);
+        __nv_bfloat162 t1 = __floats2bfloat162_rn(sv[8 * ch + 2], sv[8 * ch + 3]);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(sv[8 * ch + 4], sv[8 * ch + 5]);
+        __nv_bfloat162 t3 = __floats2bfloat162_rn(sv[8 * ch + 6], sv[8 * ch + 7]);
+        w.x = *reinterpret_cast<uint32_t*>(&t0); w.y = *reinterpret_cast<uint32_t*>(&t1);
+        w.z = *reinterpret_cast<uint32_t*>(&t2); w.w = *reinterpret_cast<uint32_t*>(&t3);
+        *reinterpret_cast<uint4*>(prow + ((ch ^ rsw) << 4)) = w;
+      }
       tc_fence_before();
       fence_proxy_async();  // make the generic-proxy smem writes visible to the tensor core
       mbar_arrive(p_full);
-      // O_j
+      if (tr) p.trace[j * 8 + 3] = clock64();
+      // O_j (my HD/2 output columns)
       mbar_wait(o_full, j & 1);
       tc_fence_after();
-      const float f_old = text ? 1.f : alpha;
-      const float f_new = text ? g / l : 1.f;
+      if (tr) p.trace[j * 8 + 4] = clock64();
+      float f_old = alpha, f_new = 1.f;
+      if (text) {  // single text tile: l is final after the exchange
+        xch[half * 128 + row] = l;
+        named_bar_sync(1 + qd, 64);
+        f_old = 1.f;
+        f_new = g / (l + xch[(half ^ 1) * 128 + row]);
+      }
+      {
+        const uint32_t tO = tmem_O + half * HH + lane_sel;
+        if (HH == 48) {
+          uint32_t r0[32], r1[16];
+          tmem_ld32(tO, r0);
+          tmem_ld16(tO + 32, r1);
+          tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < HD / 32; ++c) {
-        uint32_t raw[32];
-        tmem_ld32(tmem_O + lane_sel + c * 32, raw);
-        tmem_ld_wait();
+          for (int i = 0; i < 32; ++i) acc[i] = acc[i] * f_old + __uint_as_float(r0[i]) * f_new;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[c * 32 + i] = acc[c * 32 + i] * f_old + __uint_as_float(raw[i]) * f_new;
+          for (int i = 0; i < 16; ++i) acc[32 + i] = acc[32 + i] * f_old + __uint_as_float(r1[i]) * f_new;
+        } else {
+#pragma unroll
+          for (int c = 0; c < HH / 32; ++c) {
+            uint32_t r0[32];
+            tmem_ld32(tO + c * 32, r0);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[c * 32 + i] = acc[c * 32 + i] * f_old + __uint_as_float(r0[i]) * f_new;
+          }
+        }
       }
       tc_fence_before();
       mbar_arrive(o_empty);
+      if (tr) p.trace[j * 8 + 5] = clock64();
     }
     if (!p.has_text && n_self > 0) {
-      const float inv = 1.f / l;
+      xch[half * 128 + row] = l;
+      named_bar_sync(1 + qd, 64);
+      const float inv = 1.f / (l + xch[(half ^ 1) * 128 + row]);
 #pragma unroll
-      for (int i = 0; i < HD; ++i) acc[i] *= inv;
+      for (int i = 0; i < HH; ++i) acc[i] *= inv;
     }
     const int t = q0 + row;
     if (t < p.T) {
-      const long long o = ((long long)b * p.T + t) * ((long long)p.H * HD) + (long long)h * HD;
+      const long long o = ((long long)b * p.T + t) * ((long long)p.H * HD) + (long long)h * HD + half * HH;
       if (p.out_bf16) {
         uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + o);
 #pragma unroll
-        for (int i = 0; i < HD / 8; ++i) {
+        for (int i = 0; i < HH / 8; ++i) {
           __nv_bfloat162 a0 = __floats2bfloat162_rn(acc[8 * i], acc[8 * i + 1]);
           __nv_bfloat162 a1 = __floats2bfloat162_rn(acc[8 * i + 2], acc[8 * i + 3]);
           __nv_bfloat162 a2 = __floats2bfloat162_rn(acc[8 * i + 4], acc[8 * i + 5]);
@@ -259,7 +295,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       if (p.out_f32) {
         float4* dst = reinterpret_cast<float4*>(p.out_f32 + o);
 #pragma unroll
-        for (int i = 0; i < HD / 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+        for (int i = 0; i < HH / 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
       }
     }
   }
@@ -329,6 +365,7 @@ static int launch_attn(const vb_attn_args* a, cudaStream_t stream) {
   p.scale = a->scale; p.gate = a->gate;
   p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16);
   p.out_f32 = a->out_f32;
+  p.trace = g_attn_trace;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_fused_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
@@ -336,11 +373,16 @@ static int launch_attn(const vb_attn_args* a, cudaStream_t stream) {
     attr = true;
   }
   dim3 grid((a->T + 127) / 128, a->H, a->B);
-  launch_k(attn_fused_kernel<HD>, dim3(grid), dim3(192), Cfg::kSmem, stream, tmQ, tmKs, tmVs, tmKt, tmVt, p);
+  launch_k(attn_fused_kernel<HD>, dim3(grid), dim3(320), Cfg::kSmem, stream, tmQ, tmKs, tmVs, tmKt, tmVt, p);
   return check_launch("vb_attn_fused");
 }
 
 }  // namespace vb
+
+extern "C" int vb_attn_set_trace(void* buf) {
+  vb::g_attn_trace = static_cast<long long*>(buf);
+  return VB_OK;
+}
 
 extern "C" int vb_attn_fused(const vb_attn_args* a, void* stream) {
   using namespace vb;
