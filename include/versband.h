@@ -83,7 +83,9 @@ typedef struct vb_gemm_args {
   int32_t kpt, dil, pad;
   int32_t a_c2_g1, a_c2_g2, a_c3_g1, a_c3_g2;
   int32_t b_c2_g1, b_c2_g2, b_c2_tile;
-  int32_t bn; /* N-tile override (32/64/96/128), 0 = auto */
+  int32_t bn; /* N-tile override (32/64/96/128/256), 0 = auto */
+  int32_t operand_f32; /* 1: A and B are fp32 tensors multiplied as TF32 (kind::tf32); K multiple of 32,
+                          strides in fp32 elements; the accuracy mode of DESIGN.md section 2 */
 
   /* MoE grouped mode (optional): per-M-tile group id and device-side tile count */
   const int32_t* tile_group;
@@ -111,6 +113,7 @@ typedef struct vb_gemm_args {
   int64_t out_ld, out_g1, out_g2; /* elements */
   /* optional bf16 store of act_out(v * out_scale): the next GEMM's A operand */
   void* out_bf16;
+  int32_t outb_f32; /* 1: this slot stores fp32 (the next GEMM runs in operand_f32 mode) */
   int64_t outb_ld, outb_g1, outb_g2;
   int32_t act_out;
   float act_out_slope, out_scale;

@@ -234,3 +234,44 @@ def test_transposed_conv_polyphase_addressing():
              out_f32=out, out_ld=Cout)
     ref = F.conv_transpose1d(x.float().transpose(1, 2), w.float(), stride=u, padding=p)[0].t()
     close(out, ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# fp32 operands multiplied as TF32 (kind::tf32): the accuracy mode
+# ---------------------------------------------------------------------------------------------
+def tf32_round(x):
+    xi = x.contiguous().view(torch.int32)
+    return ((xi + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("M,N,K", [(750, 768, 768), (1500, 2304, 768), (300, 20, 96), (257, 192, 512)])
+def test_tf32_plain(M, N, K):
+    torch.manual_seed(0)
+    a = torch.randn(M, K, device="cuda")
+    b = torch.randn(N, K, device="cuda")
+    ld = (N + 3) // 4 * 4
+    out = torch.zeros(M, ld, device="cuda")
+    ops.gemm(a, b, out_f32=out, out_ld=ld)
+    ref = a @ b.t()
+    err = float((out[:, :N] - ref).abs().max() / ref.abs().max())
+    assert err < 1.5e-3, err              # tf32 has a 10-bit mantissa
+    # with operands already on the tf32 grid the product is exact up to fp32 summation order
+    at, bt = tf32_round(a), tf32_round(b)
+    ops.gemm(at, bt, out_f32=out, out_ld=ld)
+    close(out[:, :N], at @ bt.t(), 2e-5)
+
+
+def test_tf32_conv_and_fp32_operand_output():
+    torch.manual_seed(1)
+    B, T, Cin, Cout, k = 2, 300, 20, 64, 5
+    x = tf32_round(torch.randn(B, T, Cin, device="cuda"))
+    w = tf32_round(torch.randn(Cout, Cin, k, device="cuda") * 0.2)
+    kpt = (Cin + 31) // 32
+    wp = torch.zeros(Cout, k, kpt * 32, device="cuda")
+    wp[:, :, :Cin] = w.permute(0, 2, 1)
+    wp = wp.reshape(Cout, k * kpt * 32)
+    nxt = torch.zeros(B, T, Cout, device="cuda")  # fp32 "operand output" slot
+    ops.gemm(x, wp, M=T, G1=B, kpt=kpt, dil=1, pad=k // 2, a_c2=(1, 0), out_bf16=nxt, outb_ld=Cout,
+             outb_g=(T * Cout, 0), act_out=ops.ACT_LRELU, act_out_slope=0.1)
+    ref = F.leaky_relu(F.conv1d(x.transpose(1, 2), w, padding=k // 2), 0.1).transpose(1, 2)
+    close(nxt, ref, 2e-5)

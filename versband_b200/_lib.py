@@ -24,7 +24,7 @@ class GemmArgs(C.Structure):
         ("kpt", c_i32), ("dil", c_i32), ("pad", c_i32),
         ("a_c2_g1", c_i32), ("a_c2_g2", c_i32), ("a_c3_g1", c_i32), ("a_c3_g2", c_i32),
         ("b_c2_g1", c_i32), ("b_c2_g2", c_i32), ("b_c2_tile", c_i32),
-        ("bn", c_i32),
+        ("bn", c_i32), ("operand_f32", c_i32),
         ("tile_group", c_ptr), ("m_tiles_used", c_ptr),
         ("mode", c_i32), ("alpha", c_f32), ("swiglu", c_i32),
         ("bias", c_ptr), ("bias_g1", c_i64), ("bias_tile", c_i64),
@@ -34,7 +34,7 @@ class GemmArgs(C.Structure):
         ("row_mul", c_i32), ("row_off", c_i32), ("row_off_g1", c_i32), ("rows_out", c_i32),
         ("residual", c_ptr), ("accumulate", c_i32),
         ("out_f32", c_ptr), ("out_ld", c_i64), ("out_g1", c_i64), ("out_g2", c_i64),
-        ("out_bf16", c_ptr), ("outb_ld", c_i64), ("outb_g1", c_i64), ("outb_g2", c_i64),
+        ("out_bf16", c_ptr), ("outb_f32", c_i32), ("outb_ld", c_i64), ("outb_g1", c_i64), ("outb_g2", c_i64),
         ("act_out", c_i32), ("act_out_slope", c_f32), ("out_scale", c_f32),
         ("rope_cs", c_ptr), ("T", c_i32), ("heads", c_i32), ("head_dim", c_i32), ("Tp", c_i32), ("qkv_sec0", c_i32),
         ("q_out", c_ptr), ("k_out", c_ptr), ("vt_out", c_ptr),

@@ -11,7 +11,7 @@
 namespace vb {
 
 constexpr int BM = 128;
-constexpr int BK = 64;  // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int BK = 64;  // bf16 elements per k-block = one 128-byte swizzle row (32 for fp32/tf32 operands)
 constexpr int kThreads = 192;
 
 struct GemmKParams {
@@ -42,6 +42,7 @@ struct GemmKParams {
   float* out_f32;
   long long out_ld, out_g1, out_g2;
   __nv_bfloat16* out_bf16;
+  int outb_f32;  // the operand-output slot stores fp32 (tf32 operand mode) instead of bf16
   long long outb_ld, outb_g1, outb_g2;
   int act_out;
   float act_out_slope, out_scale;
@@ -128,7 +129,12 @@ __device__ __forceinline__ void epilogue_generic(const GemmKParams& p, float (&v
       const float a = v[2 * j], b = v[2 * j + 1];
       o[j] = (a / (1.f + __expf(-a))) * b * rs;
     }
-    if (p.out_bf16) {
+    if (p.out_bf16 && p.outb_f32) {
+      float* dstf = reinterpret_cast<float*>(p.out_bf16) + g1 * p.outb_g1 + g2 * p.outb_g2 + orow * p.outb_ld + n_out0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (n_out0 + j < n_out_total) dstf[j] = o[j];
+    } else if (p.out_bf16) {
       __nv_bfloat16* dst = p.out_bf16 + g1 * p.outb_g1 + g2 * p.outb_g2 + orow * p.outb_ld + n_out0;
       if (p.vec_bf16 && n_out0 + 16 <= n_out_total) {
         uint4 w0, w1;
@@ -182,9 +188,22 @@ __device__ __forceinline__ void epilogue_generic(const GemmKParams& p, float (&v
     }
   }
   if (p.out_bf16) {
-    __nv_bfloat16* dst =
-        p.out_bf16 + g1 * p.outb_g1 + g2 * p.outb_g2 + orow * p.outb_ld + n_base;
+    const long long offb = g1 * p.outb_g1 + g2 * p.outb_g2 + orow * p.outb_ld + n_base;
     apply_act_all(v, p.act_out, p.act_out_slope, p.out_scale);
+    if (p.outb_f32) {
+      float* dstf = reinterpret_cast<float*>(p.out_bf16) + offb;
+      if (full && p.vec_bf16) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          reinterpret_cast<float4*>(dstf)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < n_left) dstf[j] = v[j];
+      }
+      return;
+    }
+    __nv_bfloat16* dst = p.out_bf16 + offb;
     if (full && p.vec_bf16) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -291,7 +310,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int t, in
   return c;
 }
 
-template <int BN>
+template <int BN, bool TF32>
 __global__ void __launch_bounds__(kThreads, 1)
 vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmKParams p) {
@@ -351,10 +370,11 @@ vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
           const int tap = kb / p.kpt;
-          const int c0 = (kb - tap * p.kpt) * BK;
+          constexpr int kBkElems = TF32 ? 32 : 64;
+          const int c0 = (kb - tap * p.kpt) * kBkElems;
           const int c1 = m0 + tap * p.dil - p.pad;
           tma_load_4d(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], c0, c1, a_c2, a_c3);
-          tma_load_3d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * BK, n0, b_c2);
+          tma_load_3d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBkElems, n0, b_c2);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -362,7 +382,7 @@ vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp_idx == 1) {
     // ===================== MMA issuer (single thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = TF32 ? make_idesc_tf32(BM, BN) : make_idesc_bf16(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -379,9 +399,11 @@ vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + stage * Cfg::kABytes));
           const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
-            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            // advance 32 bytes (16 bf16 or 8 tf32 = one MMA K-step) inside the 128-byte swizzle
+            // row: +2 in 16-byte units
+            if (TF32) umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -442,7 +464,8 @@ vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // ------------------------------------------------------------------ host side
 static int encode_map(CUtensorMap* map, const void* base, int rank, const int64_t* dims,
-                      const int64_t* strides, const uint32_t* box) {
+                      const int64_t* strides, const uint32_t* box, bool tf32) {
+  const int esz = tf32 ? 4 : 2;
   cuuint64_t gdim[5];
   cuuint64_t gstr[4];
   cuuint32_t bx[5];
@@ -452,9 +475,9 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const int64_
     bx[i] = box[i];
     estr[i] = 1;
     if (i > 0) {
-      gstr[i - 1] = static_cast<cuuint64_t>(strides[i]) * 2;  // bytes
+      gstr[i - 1] = static_cast<cuuint64_t>(strides[i]) * esz;  // bytes
       if (gstr[i - 1] % 16 != 0 || gstr[i - 1] == 0)
-        return set_error(VB_ERR_INVALID, "vb_gemm: tensor stride %lld of dim %d is not a positive multiple of 8 elements",
+        return set_error(VB_ERR_INVALID, "vb_gemm: tensor stride %lld of dim %d is not a positive multiple of 16 bytes",
                          (long long)strides[i], i);
     }
     if (dims[i] <= 0) return set_error(VB_ERR_INVALID, "vb_gemm: non-positive tensor dim");
@@ -463,7 +486,7 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const int64_
     return set_error(VB_ERR_INVALID, "vb_gemm: operand base pointer not 16-byte aligned");
   auto fn = get_tensor_map_encoder();
   if (!fn) return set_error(VB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr,
+  CUresult r = fn(map, tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr,
                   bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -471,13 +494,13 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const int64_
   return VB_OK;
 }
 
-template <int BN>
+template <int BN, bool TF32>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p,
                   dim3 grid, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(vb_gemm_kernel<BN>,
+    cudaError_t e = cudaFuncSetAttribute(vb_gemm_kernel<BN, TF32>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess)
@@ -485,7 +508,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKPar
                        cudaGetErrorString(e));
     attr_set = true;
   }
-  launch_k(vb_gemm_kernel<BN>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, tmA, tmB, p);
+  launch_k(vb_gemm_kernel<BN, TF32>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, tmA, tmB, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return set_error(VB_ERR_CUDA, "vb_gemm launch failed: %s", cudaGetErrorString(e));
@@ -500,11 +523,13 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
   using namespace vb;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!a || !a->a || !a->b) return set_error(VB_ERR_INVALID, "vb_gemm: null operand");
-  if (a->M <= 0 || a->N <= 0 || a->K <= 0 || a->K % BK != 0)
-    return set_error(VB_ERR_INVALID, "vb_gemm: bad problem size M=%d N=%d K=%d (K must be a multiple of 64)",
-                     a->M, a->N, a->K);
+  const bool tf32 = a->operand_f32 != 0;
+  const int bk = tf32 ? 32 : 64;  // elements per 128-byte k-block
+  if (a->M <= 0 || a->N <= 0 || a->K <= 0 || a->K % bk != 0)
+    return set_error(VB_ERR_INVALID, "vb_gemm: bad problem size M=%d N=%d K=%d (K must be a multiple of %d)",
+                     a->M, a->N, a->K, bk);
   if (a->G1 <= 0 || a->G2 <= 0) return set_error(VB_ERR_INVALID, "vb_gemm: bad group grid");
-  const int num_kb = a->K / BK;
+  const int num_kb = a->K / bk;
   const int kpt = a->kpt > 0 ? a->kpt : num_kb;
   if (num_kb % kpt != 0) return set_error(VB_ERR_INVALID, "vb_gemm: K/64 not a multiple of kpt");
   if (a->a_strides[0] != 1 || a->b_strides[0] != 1)
@@ -537,11 +562,11 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
 
   CUtensorMap tmA, tmB;
   {
-    uint32_t box[4] = {BK, BM, 1, 1};
-    int rc = encode_map(&tmA, a->a, 4, a->a_dims, a->a_strides, box);
+    uint32_t box[4] = {static_cast<uint32_t>(bk), BM, 1, 1};
+    int rc = encode_map(&tmA, a->a, 4, a->a_dims, a->a_strides, box, tf32);
     if (rc) return rc;
-    uint32_t boxb[3] = {BK, static_cast<uint32_t>(bn), 1};
-    rc = encode_map(&tmB, a->b, 3, a->b_dims, a->b_strides, boxb);
+    uint32_t boxb[3] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(bn), 1};
+    rc = encode_map(&tmB, a->b, 3, a->b_dims, a->b_strides, boxb, tf32);
     if (rc) return rc;
   }
 
@@ -562,6 +587,7 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
   p.residual = a->residual; p.accumulate = a->accumulate;
   p.out_f32 = a->out_f32; p.out_ld = a->out_ld; p.out_g1 = a->out_g1; p.out_g2 = a->out_g2;
   p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16);
+  p.outb_f32 = a->outb_f32;
   p.outb_ld = a->outb_ld; p.outb_g1 = a->outb_g1; p.outb_g2 = a->outb_g2;
   p.act_out = a->act_out; p.act_out_slope = a->act_out_slope; p.out_scale = a->out_scale;
   p.rope_cs = a->rope_cs; p.T = a->T; p.heads = a->heads; p.head_dim = a->head_dim; p.Tp = a->Tp; p.qkv_sec0 = a->qkv_sec0;
@@ -577,7 +603,7 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
     };
     p.vec_f32 = (a->out_ld % 4 == 0) && (a->out_g1 % 4 == 0) && (a->out_g2 % 4 == 0) &&
                 (!a->out_f32 || al(a->out_f32, 16)) && (!a->residual || al(a->residual, 16));
-    p.vec_bf16 = (a->outb_ld % 8 == 0) && (a->outb_g1 % 8 == 0) && (a->outb_g2 % 8 == 0) &&
+    p.vec_bf16 = (a->outb_ld % (a->outb_f32 ? 4 : 8) == 0) && (a->outb_g1 % 8 == 0) && (a->outb_g2 % 8 == 0) &&
                  (!a->out_bf16 || al(a->out_bf16, 16));
     p.vec_aux = (!a->bias || (al(a->bias, 16) && a->bias_g1 % 4 == 0 && a->bias_tile % 4 == 0)) &&
                 (!a->gate || (al(a->gate, 16) && a->gate_ld % 4 == 0 && a->gate_g1 % 4 == 0));
@@ -599,11 +625,11 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
   }
   dim3 grid(p.num_tiles < num_sms ? p.num_tiles : num_sms, 1, 1);
   switch (bn) {
-    case 32: return launch<32>(tmA, tmB, p, grid, stream);
-    case 64: return launch<64>(tmA, tmB, p, grid, stream);
-    case 96: return launch<96>(tmA, tmB, p, grid, stream);
-    case 128: return launch<128>(tmA, tmB, p, grid, stream);
-    case 256: return launch<256>(tmA, tmB, p, grid, stream);
+    case 32: return tf32 ? launch<32, true>(tmA, tmB, p, grid, stream) : launch<32, false>(tmA, tmB, p, grid, stream);
+    case 64: return tf32 ? launch<64, true>(tmA, tmB, p, grid, stream) : launch<64, false>(tmA, tmB, p, grid, stream);
+    case 96: return tf32 ? launch<96, true>(tmA, tmB, p, grid, stream) : launch<96, false>(tmA, tmB, p, grid, stream);
+    case 128: return tf32 ? launch<128, true>(tmA, tmB, p, grid, stream) : launch<128, false>(tmA, tmB, p, grid, stream);
+    case 256: return tf32 ? launch<256, true>(tmA, tmB, p, grid, stream) : launch<256, false>(tmA, tmB, p, grid, stream);
     default: return set_error(VB_ERR_INVALID, "vb_gemm: unsupported N tile %d", bn);
   }
 }

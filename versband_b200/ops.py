@@ -30,7 +30,7 @@ def _rev_desc(t: torch.Tensor, rank: int):
     ext = 1
     for i in range(rank):
         if i > 0 and (dims[i] == 1 or strides[i] == 0):
-            strides[i] = max(8, (ext + 7) // 8 * 8)
+            strides[i] = max(8, (ext + 7) // 8 * 8)  # any 16-byte multiple: the coordinate is always 0
         ext = max(ext, dims[i] * max(strides[i], 1))
     return dims, strides
 
@@ -61,8 +61,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: Optional[int] = None, N: Option
 
     `a` is a bf16 view of up to 4 dims [c3, c2, rows, k]; `b` a bf16 view [group, n, k].
     """
-    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_cuda and b.is_cuda
+    assert a.dtype == b.dtype and a.dtype in (torch.bfloat16, torch.float32) and a.is_cuda and b.is_cuda
     args = GemmArgs()
+    args.operand_f32 = int(a.dtype == torch.float32)
+    kq = 32 if args.operand_f32 else 64
     ad, as_ = _rev_desc(a, 4)
     bd, bs = _rev_desc(b, 3)
     args.a = _ptr(a)
@@ -74,7 +76,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: Optional[int] = None, N: Option
     args.M = a.shape[-2] if M is None else M
     args.N = b.shape[-2] if N is None else N
     kk = b.shape[-1] if K is None else K
-    args.K = (kk + 63) // 64 * 64
+    args.K = (kk + kq - 1) // kq * kq
     args.G1, args.G2 = G1, G2
     args.kpt, args.dil, args.pad = kpt, dil, pad
     args.a_c2_g1, args.a_c2_g2 = a_c2
@@ -96,7 +98,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: Optional[int] = None, N: Option
     args.out_f32, args.out_ld = _ptr(out_f32), out_ld
     args.out_g1, args.out_g2 = out_g
     if out_bf16 is not None:
-        assert out_bf16.dtype == torch.bfloat16
+        assert out_bf16.dtype in (torch.bfloat16, torch.float32)
+        args.outb_f32 = int(out_bf16.dtype == torch.float32)
     args.out_bf16, args.outb_ld = _ptr(out_bf16), outb_ld
     args.outb_g1, args.outb_g2 = outb_g
     args.act_out, args.act_out_slope, args.out_scale = act_out, act_out_slope, out_scale
