@@ -224,7 +224,7 @@ int vb_moe_finalize(int32_t* bucket_count, float* usage, int E, int32_t* bucket_
                     float* lb_out, void* stream);
 int vb_moe_scatter(const int32_t* idx_c, const int32_t* idx_a, const int32_t* slot_c, const int32_t* slot_a,
                    const float* scale_c, const float* scale_a, const int32_t* bucket_start, int N, int E,
-                   int D, const void* x_bf16, void* xs_bf16, int32_t* row_map, float* row_scale,
+                   int row_bytes, const void* x, void* xs, int32_t* row_map, float* row_scale,
                    void* stream);
 /* counting sort of the 2N (token, group) pairs into 128-row tiles per expert bucket */
 int vb_moe_sort(const int32_t* idx_c, const int32_t* idx_a, const float* scale_c,
@@ -242,14 +242,14 @@ int vb_gather_rows(const void* x_bf16, const int32_t* row_map, const int32_t* m_
 int vb_ew(const float* a, const float* b, float alpha, float beta, int act, float slope,
           float* out_f32, void* out_bf16, int64_t rows, int D, int rep, void* stream);
 /* [B,C,T] fp32 -> channels-last bf16 [B,T,Cp] (zero padded), times scale */
-int vb_nct_to_ntc(const float* in, float scale, void* out_bf16, int B, int C, int T, int Cp,
+int vb_nct_to_ntc(const float* in, float scale, void* out, int B, int C, int T, int Cp, int out_is_f32,
                   void* stream);
 /* e_u == NULL: x[b,c,t] = e_c[b,t,c]; else CFG + Euler (cfm1_audio.py:160):
  * x[b,c,t] += dt * (e_u + s*(e_c - e_u)) */
 int vb_ntc_to_nct(const float* e_c, const float* e_u, int64_t ld, float s, float dt, float* x, int B,
                   int C, int T, void* stream);
-int vb_embed_rows(const int64_t* idx, const float* table, int V, int D, void* out_bf16, int64_t rows,
-                  void* stream);
+int vb_embed_rows(const int64_t* idx, const float* table, int V, int D, void* out, int64_t rows,
+                  int out_is_f32, void* stream);
 /* AvgPool1d(2) of one or two branches, summed (vocal2music_moe.py:343,349,392) */
 int vb_pool2_sum(const float* a, const float* b, int B, int Tin, int Tout, int D, void* out_bf16,
                  float* out_f32, void* stream);

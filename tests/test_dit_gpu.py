@@ -94,3 +94,32 @@ def test_golden_fixture_of_live_reference(engine, weights):
     assert agree / total > 0.97
     diff = (v.cpu() - gd["v"]).abs().permute(0, 2, 1).reshape(B * T, -1).max(-1)[0]
     assert float(diff.median()) / float(gd["v"].abs().max()) < 1e-2
+
+
+# ---------------------------------------------------------------------------------------------
+# accuracy mode: fp32 operands multiplied as TF32 in the linear layers
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def engine_tf32(weights):
+    return DiTEngine(weights, device=DEV, precision="tf32")
+
+
+@pytest.mark.parametrize("B,T", [(2, 64), (1, 200)])
+def test_forward_tf32_vs_oracle(engine_tf32, weights, B, T):
+    x, midi, beats, cap, _ = synth.dit_inputs(B, T, seed=21 + T)
+    t = torch.tensor([125, 833][:B])
+    expo = synth.exp_noise(4, B * T, 4, seed=5)
+    ctx = {"c_crossattn": cap, "c_concat": {"midi": midi, "beats": beats}}
+    v_ref, lb_ref, aux_ref = R.dit_forward(weights, x, t, ctx, depth=4, n_heads=8, expo=expo, return_aux=True)
+    v, lb, aux, _ = run_engine(engine_tf32, x, t, midi, beats, cap, expo, T)
+    agree = total = 0
+    for k in range(4):
+        agree += int((aux[k]["idx_c"].cpu().long() == aux_ref[k]["cap_idx"]).sum())
+        agree += int((aux[k]["idx_a"].cpu().long() == aux_ref[k]["ac_idx"]).sum())
+        total += 2 * B * T
+    d = (v.cpu() - v_ref).abs()
+    peak = float(v_ref.abs().max())
+    l2 = float((v.cpu() - v_ref).norm() / v_ref.norm())
+    print(f"tf32: router agreement {agree}/{total}; v max {float(d.max()) / peak:.2e} median {float(d.median()) / peak:.2e} rel-L2 {l2:.2e}")
+    assert agree >= total - 2
+    assert float(d.median()) / peak < 1e-3 and l2 < 3e-3

@@ -108,9 +108,9 @@ def _declare(l: C.CDLL) -> None:
         "vb_gather_rows": [P, P, P, I, I, P, I, P],
         "vb_ew": [P, P, F, F, I, F, P, P, L, I, I, P],
         "vb_timestamp": [P, P],
-        "vb_nct_to_ntc": [P, F, P, I, I, I, I, P],
+        "vb_nct_to_ntc": [P, F, P, I, I, I, I, I, P],
         "vb_ntc_to_nct": [P, P, L, F, F, P, I, I, I, P],
-        "vb_embed_rows": [P, P, I, I, P, L, P],
+        "vb_embed_rows": [P, P, I, I, P, L, I, P],
         "vb_pool2_sum": [P, P, I, I, I, I, P, P, P],
         "vb_gn_stats": [P, I, I, I, I, F, P, P, P],
         "vb_gn_apply": [P, P, P, P, P, I, I, I, I, I, P, P],

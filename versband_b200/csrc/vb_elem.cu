@@ -50,7 +50,7 @@ __global__ void ew_kernel(const float* __restrict__ a, const float* __restrict__
 // [B, C, T] fp32 -> [B, T, Cp] bf16 (channels-last, zero padded to Cp), value * scale.
 // 32x32 shared-memory transpose: coalesced on both sides.
 __global__ void nct_to_ntc_kernel(const float* __restrict__ in, float scale,
-                                  __nv_bfloat16* __restrict__ out, int C, int T, int Cp) {
+                                  __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32, int C, int T, int Cp) {
   pdl_sync();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
@@ -62,7 +62,10 @@ __global__ void nct_to_ntc_kernel(const float* __restrict__ in, float scale,
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int t = t0 + j, c = c0 + threadIdx.x;
-    if (t < T && c < Cp) out[((long long)b * T + t) * Cp + c] = __float2bfloat16(tile[threadIdx.x][j]);
+    if (t < T && c < Cp) {
+      if (out_f32) out_f32[((long long)b * T + t) * Cp + c] = tile[threadIdx.x][j];
+      else out[((long long)b * T + t) * Cp + c] = __float2bfloat16(tile[threadIdx.x][j]);
+    }
   }
 }
 
@@ -100,7 +103,8 @@ __global__ void ntc_to_nct_kernel(const float* __restrict__ e_c, const float* __
 
 // out[r, :] = table[idx[r], :] as bf16 (nn.Embedding, vocal2music_moe.py:336-337,388-389)
 __global__ void embed_rows_kernel(const long long* __restrict__ idx, const float* __restrict__ table,
-                                  int V, int D, __nv_bfloat16* __restrict__ out, long long rows) {
+                                  int V, int D, __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32,
+                                  long long rows) {
   pdl_sync();
   const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -109,8 +113,12 @@ __global__ void embed_rows_kernel(const long long* __restrict__ idx, const float
   id = id < 0 ? 0 : (id >= V ? V - 1 : id);
   const float* src = table + id * D;
   for (int d = lane * 2; d < D; d += 64) {
-    __nv_bfloat162 p = __floats2bfloat162_rn(src[d], src[d + 1]);
-    *reinterpret_cast<__nv_bfloat162*>(out + r * D + d) = p;
+    if (out_f32) {
+      *reinterpret_cast<float2*>(out_f32 + r * D + d) = make_float2(src[d], src[d + 1]);
+    } else {
+      __nv_bfloat162 p = __floats2bfloat162_rn(src[d], src[d + 1]);
+      *reinterpret_cast<__nv_bfloat162*>(out + r * D + d) = p;
+    }
   }
 }
 
@@ -260,12 +268,13 @@ extern "C" int vb_ew(const float* a, const float* b, float alpha, float beta, in
 }
 
 extern "C" int vb_nct_to_ntc(const float* in, float scale, void* out_bf16, int B, int C, int T, int Cp,
-                             void* stream) {
+                             int out_is_f32, void* stream) {
   vb::ProfScope prof_scope(vb::PK_LAYOUT, stream);
   if (!in || !out_bf16 || Cp < C) return set_error(VB_ERR_INVALID, "vb_nct_to_ntc: bad arguments");
   dim3 grid((T + 31) / 32, (Cp + 31) / 32, B), block(32, 8);
   launch_k(nct_to_ntc_kernel, dim3(grid), dim3(block), 0, static_cast<cudaStream_t>(stream), 
-      in, scale, static_cast<__nv_bfloat16*>(out_bf16), C, T, Cp);
+      in, scale, out_is_f32 ? nullptr : static_cast<__nv_bfloat16*>(out_bf16),
+      out_is_f32 ? static_cast<float*>(out_bf16) : nullptr, C, T, Cp);
   return check_launch("vb_nct_to_ntc");
 }
 
@@ -279,11 +288,12 @@ extern "C" int vb_ntc_to_nct(const float* e_c, const float* e_u, int64_t ld, flo
 }
 
 extern "C" int vb_embed_rows(const int64_t* idx, const float* table, int V, int D, void* out_bf16,
-                             int64_t rows, void* stream) {
+                             int64_t rows, int out_is_f32, void* stream) {
   vb::ProfScope prof_scope(vb::PK_LAYOUT, stream);
   if (!idx || !table || !out_bf16 || D % 2) return set_error(VB_ERR_INVALID, "vb_embed_rows: bad arguments");
   launch_k(embed_rows_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
-      reinterpret_cast<const long long*>(idx), table, V, D, static_cast<__nv_bfloat16*>(out_bf16), rows);
+      reinterpret_cast<const long long*>(idx), table, V, D, out_is_f32 ? nullptr : static_cast<__nv_bfloat16*>(out_bf16),
+      out_is_f32 ? static_cast<float*>(out_bf16) : nullptr, rows);
   return check_launch("vb_embed_rows");
 }
 

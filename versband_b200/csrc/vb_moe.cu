@@ -170,8 +170,8 @@ __global__ void moe_finalize_kernel(int* __restrict__ bucket_count, float* __res
 __global__ void moe_scatter_kernel(const int* __restrict__ idx_c, const int* __restrict__ idx_a,
                                    const int* __restrict__ slot_c, const int* __restrict__ slot_a,
                                    const float* __restrict__ scale_c, const float* __restrict__ scale_a,
-                                   const int* __restrict__ bucket_start, int N, int E, int D,
-                                   const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ xs,
+                                   const int* __restrict__ bucket_start, int N, int E, int row_bytes,
+                                   const uint8_t* __restrict__ x, uint8_t* __restrict__ xs,
                                    int* __restrict__ row_map, float* __restrict__ row_scale) {
   pdl_sync();
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -181,9 +181,9 @@ __global__ void moe_scatter_kernel(const int* __restrict__ idx_c, const int* __r
   const int bucket = g * E + (g ? idx_a[n] : idx_c[n]);
   const int slot = bucket_start[bucket] + (g ? slot_a[n] : slot_c[n]);
   if (lane == 0) { row_map[slot] = i; row_scale[slot] = g ? scale_a[n] : scale_c[n]; }
-  const uint4* src = reinterpret_cast<const uint4*>(x + (long long)n * D);
-  uint4* dst = reinterpret_cast<uint4*>(xs + (long long)slot * D);
-  for (int k = lane; k < D / 8; k += 32) dst[k] = src[k];
+  const uint4* src = reinterpret_cast<const uint4*>(x + (long long)n * row_bytes);
+  uint4* dst = reinterpret_cast<uint4*>(xs + (long long)slot * row_bytes);
+  for (int k = lane; k < row_bytes / 16; k += 32) dst[k] = src[k];
 }
 
 // Single CTA. Entries i in [0, 2N): group g = i / N (0 caption, 1 acoustic), token = i % N,
@@ -359,13 +359,13 @@ extern "C" int vb_moe_finalize(int32_t* bucket_count, float* usage, int E, int32
 
 extern "C" int vb_moe_scatter(const int32_t* idx_c, const int32_t* idx_a, const int32_t* slot_c,
                               const int32_t* slot_a, const float* scale_c, const float* scale_a,
-                              const int32_t* bucket_start, int N, int E, int D, const void* x_bf16,
-                              void* xs_bf16, int32_t* row_map, float* row_scale, void* stream) {
+                              const int32_t* bucket_start, int N, int E, int row_bytes, const void* x,
+                              void* xs, int32_t* row_map, float* row_scale, void* stream) {
   vb::ProfScope prof_scope(vb::PK_MOE_SORT, stream);
-  if (!idx_c || !idx_a || !slot_c || !slot_a || !bucket_start || !x_bf16 || !xs_bf16 || D % 8)
+  if (!idx_c || !idx_a || !slot_c || !slot_a || !bucket_start || !x || !xs || row_bytes % 16)
     return set_error(VB_ERR_INVALID, "vb_moe_scatter: bad arguments");
   launch_k(moe_scatter_kernel, dim3((2 * N + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream), idx_c,
-           idx_a, slot_c, slot_a, scale_c, scale_a, bucket_start, N, E, D,
-           static_cast<const __nv_bfloat16*>(x_bf16), static_cast<__nv_bfloat16*>(xs_bf16), row_map, row_scale);
+           idx_a, slot_c, slot_a, scale_c, scale_a, bucket_start, N, E, row_bytes,
+           static_cast<const uint8_t*>(x), static_cast<uint8_t*>(xs), row_map, row_scale);
   return check_launch("vb_moe_scatter");
 }

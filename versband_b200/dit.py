@@ -26,12 +26,22 @@ def _bf(t: torch.Tensor) -> torch.Tensor:
     return t.to(BF).contiguous()
 
 
-def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None) -> torch.Tensor:
-    """Conv1d weight [Cout, Cin, k] -> implicit-GEMM B operand [Cout, k * kpt*64] (tap-major)."""
+def tf32_round(t: torch.Tensor) -> torch.Tensor:
+    """Round fp32 to the TF32 grid (10-bit mantissa, round-to-nearest) so that the tensor core's
+    operand truncation is exact."""
+    ti = t.contiguous().view(torch.int32)
+    return ((ti + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None, dtype=BF) -> torch.Tensor:
+    """Conv1d weight [Cout, Cin, k] -> implicit-GEMM B operand [Cout, k * kpt*kq] (tap-major);
+    kq = 64 (bf16) or 32 (fp32/tf32) elements = one 128-byte k-block."""
     cout, cin, k = w.shape
-    kp = (cin + 63) // 64 * 64 if cin_pad is None else cin_pad
-    out = torch.zeros(cout, k, kp, device=w.device, dtype=BF)
-    out[:, :, :cin] = w.permute(0, 2, 1).to(BF)
+    kq = 64 if dtype == BF else 32
+    kp = (cin + kq - 1) // kq * kq if cin_pad is None else cin_pad
+    out = torch.zeros(cout, k, kp, device=w.device, dtype=dtype)
+    src = w.permute(0, 2, 1)
+    out[:, :, :cin] = src.to(BF) if dtype == BF else tf32_round(src.float())
     return out.reshape(cout, k * kp).contiguous()
 
 
@@ -79,7 +89,13 @@ class DiTEngine:
 
     def __init__(self, sd: Dict[str, torch.Tensor], *, in_channels=20, hidden_size=768, depth=4,
                  num_heads=8, num_experts=4, ori_dim=1024, max_len=1500, norm_eps=1e-5,
-                 temperature=2.0, device="cuda"):
+                 temperature=2.0, device="cuda", precision: str = "bf16"):
+        """precision: "bf16" — bf16 GEMM operands (fast); "tf32" — fp32 activations/weights
+        multiplied as TF32 (UMMA kind::tf32) for the linear layers, bf16 attention core."""
+        assert precision in ("bf16", "tf32")
+        self.precision = precision
+        self.adt = BF if precision == "bf16" else F32      # dtype of GEMM operands
+        self.kq = 64 if precision == "bf16" else 32        # elements per 128-byte k-block
         self.C, self.D, self.depth, self.H, self.E = in_channels, hidden_size, depth, num_heads, num_experts
         self.hd = hidden_size // num_heads
         self.ori_dim, self.max_len, self.eps = ori_dim, max_len, norm_eps
@@ -93,15 +109,18 @@ class DiTEngine:
     def pack(self, sd: Dict[str, torch.Tensor]) -> None:
         dev, D, E = self.dev, self.D, self.E
         g = lambda k: sd[k].detach().to(dev, F32).contiguous()  # noqa: E731
+        adt = self.adt
+        _bf = (lambda t: t.to(BF).contiguous()) if adt == BF else (lambda t: tf32_round(t.float()))  # noqa: E731
+        pack_conv = lambda w_: pack_conv_weight(w_, dtype=adt)  # noqa: E731
         w: dict = {}
         # stem
         w["midi_emb"], w["beats_emb"] = g("midi_embedding.weight"), g("beats_embedding.weight")
         for name in ("midi_proj", "beats_proj"):
-            w[name + "_w"] = pack_conv_weight(g(name + ".0.weight"))
+            w[name + "_w"] = pack_conv(g(name + ".0.weight"))
             w[name + "_b"] = g(name + ".0.bias")
         w["final_proj_w"] = _bf(g("final_proj.weight")[:, :, 0])
         w["final_proj_b"] = g("final_proj.bias")
-        w["proj_in_w"] = pack_conv_weight(g("proj_in.weight"))
+        w["proj_in_w"] = pack_conv(g("proj_in.weight"))
         w["proj_in_b"] = g("proj_in.bias")
         self.proj_in_k = sd["proj_in.weight"].shape[-1]
         self.stem_k = sd["midi_proj.0.weight"].shape[-1]
@@ -186,21 +205,22 @@ class DiTEngine:
         Tp = (T + 7) // 8 * 8
         max_rows = ((2 * N + 127) // 128 + 2 * E) * 128
         z = lambda *s, dt=F32: torch.zeros(*s, device=dev, dtype=dt)  # noqa: E731
+        AD = self.adt
         ws = dict(
             Tp=Tp, max_rows=max_rows,
-            x_cl=z(B, T, 32, dt=BF), x=z(N, D), h=z(N, D),
-            temb_sin=z(B, 256, dt=BF), temb_h=z(B, D, dt=BF), temb=z(B, D), ada_in=z(B, D, dt=BF),
+            x_cl=z(B, T, 32, dt=AD), x=z(N, D), h=z(N, D),
+            temb_sin=z(B, 256, dt=AD), temb_h=z(B, D, dt=AD), temb=z(B, D), ada_in=z(B, D, dt=AD),
             mod=z(B, self.mod_ld), hl=z(B, 2 * self.depth),
-            xa=z(N, D, dt=BF), q=z(B, H, T, hd, dt=BF), k=z(B, H, T, hd, dt=BF), vt=z(B, H, hd, Tp, dt=BF),
-            oa=z(N, D, dt=BF),
-            xm=z(N, D, dt=BF), qm=z(N, D, dt=BF), ctx=z(N, D, dt=BF),
+            xa=z(N, D, dt=AD), q=z(B, H, T, hd, dt=BF), k=z(B, H, T, hd, dt=BF), vt=z(B, H, hd, Tp, dt=BF),
+            oa=z(N, D, dt=AD),
+            xm=z(N, D, dt=AD), qm=z(N, D, dt=BF), ctx=z(N, D, dt=BF),
             idx_c=z(N, dt=torch.int32), idx_a=z(N, dt=torch.int32), scale_c=z(N), scale_a=z(N),
             cap_logits=z(N, E), bucket_count=z(2 * E, dt=torch.int32), usage=z(2 * E), bucket_start=z(2 * E, dt=torch.int32),
             slot_c=z(N, dt=torch.int32), slot_a=z(N, dt=torch.int32),
             row_map=z(max_rows, dt=torch.int32), row_scale=z(max_rows), tile_group=z(max_rows // 128, dt=torch.int32),
             m_tiles=z(1, dt=torch.int32), lb=z(self.depth),
-            xs=z(max_rows, D, dt=BF), hs=z(max_rows, Fh, dt=BF), y2=z(2 * N, D), y=z(N, D, dt=BF),
-            hf=z(E, N, Fh, dt=BF), xf=z(N, D, dt=BF), v=z(N, 32),
+            xs=z(max_rows, D, dt=AD), hs=z(max_rows, Fh, dt=AD), y2=z(2 * N, D), y=z(N, D, dt=AD),
+            hf=z(E, N, Fh, dt=AD), xf=z(N, D, dt=AD), v=z(N, 32),
         )
         self._ws[key] = ws
         return ws
@@ -213,14 +233,14 @@ class DiTEngine:
         w, D, dev = self.w, self.D, self.dev
         B, _, Tm = midi.shape
         Tpool = Tm // 2
-        emb = torch.empty(B, Tm, D, device=dev, dtype=BF)
+        emb = torch.empty(B, Tm, D, device=dev, dtype=self.adt)
         conv = [torch.empty(B, Tm, D, device=dev, dtype=F32) for _ in range(2)]
         for i, (idx, tab, name) in enumerate(((midi, w["midi_emb"], "midi_proj"), (beats, w["beats_emb"], "beats_proj"))):
             ops.embed_rows(idx.to(dev).contiguous(), tab, emb)
-            ops.gemm(emb, w[name + "_w"], M=Tm, G1=B, kpt=D // 64, dil=1, pad=self.stem_k // 2, a_c2=(1, 0),
+            ops.gemm(emb, w[name + "_w"], M=Tm, G1=B, kpt=D // self.kq, dil=1, pad=self.stem_k // 2, a_c2=(1, 0),
                      bias=w[name + "_b"], act=ops.ACT_LRELU, act_slope=0.01,
                      out_f32=conv[i], out_ld=D, out_g=(Tm * D, 0))
-        pooled = torch.empty(B, Tpool, D, device=dev, dtype=BF)
+        pooled = torch.empty(B, Tpool, D, device=dev, dtype=self.adt)
         ops.pool2_sum(conv[0], conv[1], B=B, Tin=Tm, Tout=Tpool, D=D, out_bf16=pooled)
         ac = torch.empty(B, Tpool, D, device=dev, dtype=F32)
         ops.gemm(pooled.view(B * Tpool, D), w["final_proj_w"], bias=w["final_proj_b"], out_f32=ac, out_ld=D)
@@ -243,23 +263,27 @@ class DiTEngine:
         if acoustic is None:
             acoustic = self.prepare_acoustic(midi, beats, T)
         ac, ac_logits = acoustic
-        cap16 = torch.empty(B * L, self.ori_dim, device=dev, dtype=BF)
+        cap16 = torch.empty(B * L, self.ori_dim, device=dev, dtype=self.adt)
         ops.ew(caption.to(dev, F32).contiguous().view(B * L, -1), out_bf16=cap16)
-        h1 = torch.empty(B * L, D, device=dev, dtype=BF)
+        h1 = torch.empty(B * L, D, device=dev, dtype=self.adt)
         ops.gemm(cap16, w["c_w0"], bias=w["c_b0"], act=ops.ACT_GELU, out_bf16=h1, outb_ld=D)
         h2 = torch.empty(B * L, D, device=dev, dtype=F32)
         ops.gemm(h1, w["c_w2"], bias=w["c_b2"], out_f32=h2, out_ld=D)
         cap = torch.empty(B, L, D, device=dev, dtype=F32)
-        cap_bf = torch.empty(B * L, D, device=dev, dtype=BF)
-        ops.norm_mod(h2, kind=1, w=w["c_ln_w"], b=w["c_ln_b"], eps=1e-5, out_f32=cap, out_bf16=cap_bf)
+        if self.adt == BF:
+            cap_bf = torch.empty(B * L, D, device=dev, dtype=BF)
+            ops.norm_mod(h2, kind=1, w=w["c_ln_w"], b=w["c_ln_b"], eps=1e-5, out_f32=cap, out_bf16=cap_bf)
+        else:  # fp32 operands: the fp32 caption is the GEMM operand itself
+            ops.norm_mod(h2, kind=1, w=w["c_ln_w"], b=w["c_ln_b"], eps=1e-5, out_f32=cap)
+            cap_bf = cap.view(B * L, D)
         pool = torch.empty(B, D, device=dev, dtype=F32)
         ops.mean_tokens(cap, pool)
-        pool_n = torch.empty(B, D, device=dev, dtype=BF)
+        pool_n = torch.empty(B, D, device=dev, dtype=self.adt)
         ops.norm_mod(pool, kind=1, w=w["cap_ln_w"], b=w["cap_ln_b"], eps=1e-5, out_bf16=pool_n)
         cap_emb = torch.empty(B, D, device=dev, dtype=F32)
         ops.gemm(pool_n, w["cap_w"], bias=w["cap_b"], out_f32=cap_emb, out_ld=D)
         cond = DiTCond(B=B, T=T, L=L, acoustic=ac, ac_logits=ac_logits, caption=cap, cap_emb=cap_emb)
-        y16 = torch.empty(B * L, D, device=dev, dtype=BF)
+        y16 = torch.empty(B * L, D, device=dev, dtype=self.adt)
         H, hd = self.H, self.hd
         Lp = (L + 7) // 8 * 8
         for k in range(self.depth):

@@ -112,7 +112,10 @@ class _FinalLayerParams(nn.Module):
 
 class TxtFlagLargeImprovedDiTV2(nn.Module):
     """AccompBand DiT with Band-MoE. forward(x, t, context) -> (v, lb_loss) exactly like the
-    reference (vocal2music_moe.py:375-434); inference only."""
+    reference (vocal2music_moe.py:375-434); inference only.
+    `precision` ("bf16" | "tf32") selects the GEMM operand format of the engine."""
+
+    precision = "bf16"
 
     def __init__(self, in_channels, context_dim, hidden_size=1152, depth=28, num_heads=16, max_len=1000,
                  num_experts=4, ori_dim=1024):
@@ -163,14 +166,15 @@ class TxtFlagLargeImprovedDiTV2(nn.Module):
     # ---- engine management -------------------------------------------------------------
     def engine(self):
         from .dit import DiTEngine
-        key = _param_version(self)
+        key = (_param_version(self), self.precision)
         if self._engine is None or key != self._engine_key:
             dev = next(self.parameters()).device
             _require_cuda(next(self.parameters()), "TxtFlagLargeImprovedDiTV2")
             self._engine = DiTEngine({k: v for k, v in self.state_dict().items()}, in_channels=self.in_channels,
                                      hidden_size=self.hidden_size, depth=self.depth, num_heads=self.num_heads,
                                      num_experts=self.num_experts, ori_dim=self.ori_dim, max_len=self.max_len,
-                                     temperature=float(self.blocks[0].feed_forward.temperature), device=dev)
+                                     temperature=float(self.blocks[0].feed_forward.temperature), device=dev,
+                                     precision=self.precision)
             self._engine_key = key
             self._cond_cache.clear()
         return self._engine

@@ -35,6 +35,14 @@ def _rev_desc(t: torch.Tensor, rank: int):
     return dims, strides
 
 
+def _route(out_bf16, out_f32):
+    """An fp32 tensor passed in the operand-output slot is routed to the fp32 output pointer."""
+    if out_bf16 is not None and out_bf16.dtype == torch.float32:
+        assert out_f32 is None
+        return None, out_bf16
+    return out_bf16, out_f32
+
+
 def _check_f32(t: Optional[torch.Tensor], name: str):
     if t is not None:
         assert t.dtype == torch.float32 and t.is_cuda, name
@@ -122,6 +130,7 @@ def norm_mod(x, *, kind: int, w=None, b=None, shift=None, scale=None, mod_ld: in
     """kind 0 RMSNorm / 1 LayerNorm (+ optional affine, + optional adaLN modulate)."""
     rows, D = x.numel() // x.shape[-1], x.shape[-1]
     assert x.dtype == torch.float32 and x.is_contiguous()
+    out_bf16, out_f32 = _route(out_bf16, out_f32)
     _call("vb_norm_mod", kind, _ptr(x), _ptr(w), _ptr(b), _ptr(shift), _ptr(scale), mod_ld,
           rows_per_batch or rows, eps, _ptr(out_bf16), _ptr(out_f32), rows, D)
 
@@ -138,6 +147,7 @@ def attn_smallkv(q, q_strides, K, V, kv_ld, *, B, T, H, hd, L, scale, gate=None,
 
 def timestep_embed(t, freqs, *, out_f32=None, out_bf16=None, dim: int = 256) -> None:
     assert t.dtype == torch.int64
+    out_bf16, out_f32 = _route(out_bf16, out_f32)
     _call("vb_timestep_embed", _ptr(t), _ptr(freqs), _ptr(out_f32), _ptr(out_bf16), t.numel(), dim)
 
 
@@ -165,7 +175,7 @@ def moe_finalize(bucket_count, usage, E, bucket_start, row_map, row_scale, tile_
 
 def moe_scatter(idx_c, idx_a, slot_c, slot_a, scale_c, scale_a, bucket_start, N, E, x, xs, row_map, row_scale) -> None:
     _call("vb_moe_scatter", _ptr(idx_c), _ptr(idx_a), _ptr(slot_c), _ptr(slot_a), _ptr(scale_c), _ptr(scale_a),
-          _ptr(bucket_start), N, E, x.shape[-1], _ptr(x), _ptr(xs), _ptr(row_map), _ptr(row_scale))
+          _ptr(bucket_start), N, E, x.shape[-1] * x.element_size(), _ptr(x), _ptr(xs), _ptr(row_map), _ptr(row_scale))
 
 
 def moe_sort(idx_c, idx_a, scale_c, scale_a, N, E, row_map, row_scale, tile_group, m_tiles_used, max_rows,
@@ -181,12 +191,14 @@ def gather_rows(x, row_map, m_tiles_used, n_tokens, out, max_rows) -> None:
 
 def ew(a, b=None, *, alpha=1.0, beta=1.0, act=ACT_NONE, slope=0.0, out_f32=None, out_bf16=None, rep=1):
     rows, D = a.numel() // a.shape[-1], a.shape[-1]
+    out_bf16, out_f32 = _route(out_bf16, out_f32)
     _call("vb_ew", _ptr(a), _ptr(b), alpha, beta, act, slope, _ptr(out_f32), _ptr(out_bf16), rows, D, rep)
 
 
 def nct_to_ntc(x, out_bf16, *, scale=1.0) -> None:
     B, Cc, T = x.shape
-    _call("vb_nct_to_ntc", _ptr(x), scale, _ptr(out_bf16), B, Cc, T, out_bf16.shape[-1])
+    _call("vb_nct_to_ntc", _ptr(x), scale, _ptr(out_bf16), B, Cc, T, out_bf16.shape[-1],
+          int(out_bf16.dtype == torch.float32))
 
 
 def ntc_to_nct(e_c, x, *, e_u=None, ld, s=0.0, dt=0.0) -> None:
@@ -195,10 +207,12 @@ def ntc_to_nct(e_c, x, *, e_u=None, ld, s=0.0, dt=0.0) -> None:
 
 
 def embed_rows(idx, table, out_bf16) -> None:
-    _call("vb_embed_rows", _ptr(idx), _ptr(table), table.shape[0], table.shape[1], _ptr(out_bf16), idx.numel())
+    _call("vb_embed_rows", _ptr(idx), _ptr(table), table.shape[0], table.shape[1], _ptr(out_bf16), idx.numel(),
+          int(out_bf16.dtype == torch.float32))
 
 
 def pool2_sum(a, b, *, B, Tin, Tout, D, out_bf16=None, out_f32=None) -> None:
+    out_bf16, out_f32 = _route(out_bf16, out_f32)
     _call("vb_pool2_sum", _ptr(a), _ptr(b), B, Tin, Tout, D, _ptr(out_bf16), _ptr(out_f32))
 
 
@@ -222,6 +236,7 @@ def mean_tokens(x, out) -> None:
 def attn_fused(q, q_strides, *, B, T, H, hd, scale, k_self=None, vt_self=None, Tp=0, k_text=None, vt_text=None,
                L=0, Lp=0, gate=None, out_bf16=None, out_f32=None) -> None:
     """Fused tcgen05 attention (self segment and/or one short "text" segment), see vb_attn_fused."""
+    out_bf16, out_f32 = _route(out_bf16, out_f32)
     a = AttnArgs()
     a.q = _ptr(q)
     a.q_st, a.q_sh, a.q_sb = q_strides

@@ -19,13 +19,14 @@ class AccompBandPipeline:
     def __init__(self, dit_sd: Dict[str, torch.Tensor], vae_sd: Dict[str, torch.Tensor],
                  voc_sd: Dict[str, torch.Tensor], *, dit_cfg: dict, ddconfig: dict, embed_dim: int,
                  voc_cfg: dict, scale_factor: float = 1.0, device="cuda", use_graph: bool = True,
-                 n_points: int = 25):
+                 n_points: int = 25, precision: str = "bf16"):
         from . import _lib
         _lib.check(_lib.lib().vb_check_device(), "vb_check_device")
         self.dev = torch.device(device)
         kw = {k: dit_cfg[k] for k in ("in_channels", "hidden_size", "depth", "num_experts", "max_len") if k in dit_cfg}
         # NB: the reference does not forward `ori_dim` (vocal2music_moe.py:489-491): c_embedder is sized by the default 1024
-        self.dit = DiTEngine(dit_sd, num_heads=dit_cfg["num_heads"], device=device, **kw)
+        self.dit = DiTEngine(dit_sd, num_heads=dit_cfg["num_heads"], device=device, precision=precision, **kw)
+        self.precision = precision
         self.vae = VAEEngine(vae_sd, ddconfig, embed_dim, device=device, with_encoder=False)
         self.voc = HifiGanEngine(voc_sd, voc_cfg, device=device)
         self.sampler = FlowSampler(self.dit, n_points=n_points, use_graph=use_graph)
