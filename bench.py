@@ -186,7 +186,8 @@ def run_ours(args):
 
     sds = synth_weights()
     pipe = AccompBandPipeline(*sds, dit_cfg=synth.DIT_CFG, ddconfig=synth.VAE_DDCONFIG,
-                              embed_dim=synth.VAE_EMBED_DIM, voc_cfg=synth.HIFIGAN_CFG, device=dev)
+                              embed_dim=synth.VAE_EMBED_DIM, voc_cfg=synth.HIFIGAN_CFG, device=dev,
+                              precision=args.precision)
     B = args.clips
     # per-clip seeding (not per rank): clip c of the job is the same whatever the GPU count
     x0, midi, beats, cap_c, cap_u = [], [], [], [], []
@@ -284,6 +285,7 @@ def run_ours(args):
         from versband_b200.sampler import FlowSampler
         saved = pipe.sampler
         pipe.sampler = FlowSampler(pipe.dit, use_graph=False)
+        pipe.use_graph = False
         step_device()
         n0 = _lib.launch_count()
         _lib.prof_enable(True)
@@ -292,6 +294,7 @@ def run_ours(args):
         _lib.prof_enable(False)
         launches = _lib.launch_count() - n0
         pipe.sampler = saved
+        pipe.use_graph = True
         gemm_ms = fam["gemm"]["ms"]
         n_gemm = fam["gemm"]["launches"]
         achieved = FLOP_CLIP * B / (gemm_ms * 1e-3) / 1e12
@@ -317,10 +320,12 @@ def run_ours(args):
             "metric": "audio_sec_per_wall_sec", "value": audio / (ms_step * 1e-3),
             "unit": "x real-time (24 kHz audio-s / wall-s)", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": "AccompBand 25-point (24-step) CFG flow sampler + VAE decode + HiFi-GAN, 20 s clips",
                        "clips_per_gpu": B, "global_clips": clips, "guidance": 3.0, "t_lat": T_LAT,
-                       "parallelism": f"dp{world}", "precision": "bf16 operands, fp32 accumulate/residual",
+                       "parallelism": f"dp{world}",
+                       "precision": ("bf16 operands, fp32 accumulate/residual" if args.precision == "bf16" else
+                                     "DiT linears: fp32 operands as TF32 (kind::tf32), bf16 attention core; VAE/vocoder bf16 operands"),
                        "l2": "256 MiB buffer written between timed steps (L2 flush)"},
             "dit_latent_frame_evals_per_s": clips * T_LAT * N_EVALS / (ms_samp * 1e-3),
             "stage_ms": {"sampler": ms_samp, "vae_decode": ms_vae, "vocoder": ms_voc},
@@ -348,6 +353,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=1, help="clips per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="tf32", choices=["bf16", "tf32"],
+                    help="GEMM operand format of the DiT: bf16 (default) or fp32-as-TF32 (accuracy mode)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

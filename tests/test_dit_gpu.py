@@ -27,7 +27,7 @@ def weights():
 
 @pytest.fixture(scope="module")
 def engine(weights):
-    return DiTEngine(weights, device=DEV)
+    return DiTEngine(weights, device=DEV, precision="bf16")
 
 
 def run_engine(engine, x, t, midi, beats, cap, expo, T):

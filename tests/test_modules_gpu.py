@@ -35,7 +35,8 @@ def test_dit_module_forward_like_diffusion_wrapper():
                                   depth=4, n_heads=8, expo=expo)
     assert v.shape == (B, 20, T) and lb.dim() == 0
     diff = (v.cpu() - v_ref).abs().permute(0, 2, 1).reshape(B * T, -1).max(-1)[0]
-    assert float(diff.median()) / float(v_ref.abs().max()) < 1e-2
+    assert float(diff.median()) / float(v_ref.abs().max()) < 1e-3   # default precision = tf32
+    assert float((v.cpu() - v_ref).norm() / v_ref.norm()) < 2e-3
     assert abs(float(lb) - float(lb_ref)) < 5e-3
     # second call re-uses the memoised step-invariant conditioning and decays loss_w like the reference
     w0 = net.loss_w

@@ -89,9 +89,10 @@ class DiTEngine:
 
     def __init__(self, sd: Dict[str, torch.Tensor], *, in_channels=20, hidden_size=768, depth=4,
                  num_heads=8, num_experts=4, ori_dim=1024, max_len=1500, norm_eps=1e-5,
-                 temperature=2.0, device="cuda", precision: str = "bf16"):
-        """precision: "bf16" — bf16 GEMM operands (fast); "tf32" — fp32 activations/weights
-        multiplied as TF32 (UMMA kind::tf32) for the linear layers, bf16 attention core."""
+                 temperature=2.0, device="cuda", precision: str = "tf32"):
+        """precision: "tf32" (default) — fp32 activations/weights multiplied as TF32 (UMMA
+        kind::tf32) in every linear layer, bf16 attention core: DiT output within 1e-3 (rel. L2) of
+        the fp32 reference; "bf16" — bf16 GEMM operands, ~12 % faster, ~1e-2 of peak."""
         assert precision in ("bf16", "tf32")
         self.precision = precision
         self.adt = BF if precision == "bf16" else F32      # dtype of GEMM operands

@@ -115,7 +115,7 @@ class TxtFlagLargeImprovedDiTV2(nn.Module):
     reference (vocal2music_moe.py:375-434); inference only.
     `precision` ("bf16" | "tf32") selects the GEMM operand format of the engine."""
 
-    precision = "bf16"
+    precision = "tf32"
 
     def __init__(self, in_channels, context_dim, hidden_size=1152, depth=28, num_heads=16, max_len=1000,
                  num_experts=4, ori_dim=1024):

@@ -19,7 +19,7 @@ class AccompBandPipeline:
     def __init__(self, dit_sd: Dict[str, torch.Tensor], vae_sd: Dict[str, torch.Tensor],
                  voc_sd: Dict[str, torch.Tensor], *, dit_cfg: dict, ddconfig: dict, embed_dim: int,
                  voc_cfg: dict, scale_factor: float = 1.0, device="cuda", use_graph: bool = True,
-                 n_points: int = 25, precision: str = "bf16"):
+                 n_points: int = 25, precision: str = "tf32"):
         from . import _lib
         _lib.check(_lib.lib().vb_check_device(), "vb_check_device")
         self.dev = torch.device(device)
