@@ -17,10 +17,18 @@ if which.startswith("voc"):
     out = torch.empty(1, T, C, device="cuda", dtype=torch.bfloat16)
     fn = lambda: ops.gemm(x, w, M=T, G1=1, kpt=(C + 63) // 64, dil=1, pad=1, a_c2=(1, 0), out_bf16=out, outb_ld=C,
                           outb_g=(T * C, 0))
+elif which == "vae":
+    T, C, k = 750, 1536, 3
+    x = torch.randn(1, T, C, device="cuda").bfloat16()
+    w = torch.randn(C, k * C, device="cuda").bfloat16()
+    out = torch.empty(1, T, C, device="cuda")
+    fn = lambda: ops.gemm(x, w, M=T, G1=1, kpt=C // 64, dil=1, pad=1, a_c2=(1, 0), out_f32=out, out_ld=C,
+                          out_g=(T * C, 0))
 else:
-    M, N, K = 1500, 768, 768
-    a = torch.randn(M, K, device="cuda").bfloat16()
-    b = torch.randn(N, K, device="cuda").bfloat16()
+    M, N, K = 1500, 2304 if "qkv" in which else 768, 768
+    dt = torch.float32 if "tf32" in which else torch.bfloat16
+    a = torch.randn(M, K, device="cuda").to(dt)
+    b = torch.randn(N, K, device="cuda").to(dt)
     o = torch.empty(M, N, device="cuda")
     fn = lambda: ops.gemm(a, b, out_f32=o, out_ld=N)
 for _ in range(5):
