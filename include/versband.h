@@ -226,6 +226,12 @@ int vb_moe_scatter(const int32_t* idx_c, const int32_t* idx_a, const int32_t* sl
                    const float* scale_c, const float* scale_a, const int32_t* bucket_start, int N, int E,
                    int row_bytes, const void* x, void* xs, int32_t* row_map, float* row_scale,
                    void* stream);
+/* All router noise of one sampling run in one launch, bit-identical to the reference's sequence of
+ * torch `exponential_()` calls (PyTorch Philox4x32-10 stream: seed, offset advancing by 4 per call).
+ * Layout: e0 [steps, depth, 2N, 2], e1/e2 [steps, depth, 2N, E], rows [0,N) = cond, [N,2N) = uncond;
+ * call order (step, branch, block, {group, caption, acoustic}). */
+int vb_router_noise(uint64_t seed, uint64_t offset, int N, int E, int depth, int steps, float* e0,
+                    float* e1, float* e2, void* stream);
 /* counting sort of the 2N (token, group) pairs into 128-row tiles per expert bucket */
 int vb_moe_sort(const int32_t* idx_c, const int32_t* idx_a, const float* scale_c,
                 const float* scale_a, int N, int E, int32_t* row_map, float* row_scale,

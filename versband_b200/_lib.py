@@ -108,6 +108,7 @@ def _declare(l: C.CDLL) -> None:
         "vb_gather_rows": [P, P, P, I, I, P, I, P],
         "vb_ew": [P, P, F, F, I, F, P, P, L, I, I, P],
         "vb_timestamp": [P, P],
+        "vb_router_noise": [C.c_uint64, C.c_uint64, I, I, I, I, P, P, P, P],
         "vb_nct_to_ntc": [P, F, P, I, I, I, I, I, P],
         "vb_ntc_to_nct": [P, P, L, F, F, P, I, I, I, P],
         "vb_embed_rows": [P, P, I, I, P, L, I, P],

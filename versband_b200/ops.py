@@ -258,3 +258,7 @@ def mark(name: str) -> None:
     if i < buf.numel():
         names.append(name)
         _lib.check(_lib.lib().vb_timestamp(C.c_void_p(buf.data_ptr() + 8 * i), _stream()), "vb_timestamp")
+
+
+def router_noise(seed: int, offset: int, N: int, E: int, depth: int, steps: int, e0, e1, e2) -> None:
+    _call("vb_router_noise", seed, offset, N, E, depth, steps, _ptr(e0), _ptr(e1), _ptr(e2))
