@@ -55,7 +55,7 @@ __global__ void router_noise_kernel(unsigned long long seed, unsigned long long 
       const int li = li0 + stride * ii;
       if (li < n) {
         const float u = (float)ctr[ii] * 2.3283064365386963e-10f + 1.1641532182693481e-10f;
-        const float lg = (u >= 1.0f - 5.9604644775390625e-08f) ? -5.9604644775390625e-08f : logf(u);
+        const float lg = (u >= 1.0f - 5.9604644775390625e-08f) ? -5.9604644775390625e-08f : __logf(u);  // torch (at::log in device code) resolves to the fast intrinsic
         dst[li] = -1.0f * lg;
       }
     }
