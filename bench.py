@@ -298,12 +298,39 @@ def run_ours(args):
         gemm_ms = fam["gemm"]["ms"]
         n_gemm = fam["gemm"]["launches"]
         achieved = FLOP_CLIP * B / (gemm_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "vb_gemm_kernel<BN> (tcgen05/TMA implicit-GEMM, all launches of one step)",
+        traffic = None
+        try:  # dram bytes of the same kernel family over one step, from the committed ncu capture
+            with open(os.path.join(ROOT, "profiles", "r1_traffic_eager_step.json")) as f:
+                tj = _json.load(f)["vb_gemm_kernel"]
+            traffic = tj["dram_bytes"] / tj["launches"]
+        except Exception:
+            pass
+        roof = {"bound": "tensor", "kernel": "vb_gemm_kernel<BN,TF32> (tcgen05/TMA implicit-GEMM, all launches of one step)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "peak_source": peak_src, "traffic": None,
+                "peak_source": peak_src, "traffic": traffic,
+                "traffic_note": "mean dram read+write bytes per launch (ncu, L2 flushed before every launch), profiles/r1_traffic_eager_step.json",
                 "launches_per_step": n_gemm, "avg_launch_us": gemm_ms * 1e3 / max(n_gemm, 1),
                 "algorithmic_flop_per_step": FLOP_CLIP * B,
                 "kernel_time_share_of_step": gemm_ms / sum(v["ms"] for v in fam.values())}
+
+    fast = None
+    if rank == 0 and world == 1 and args.precision == "tf32" and not args.no_fast_mode:
+        pipe_bf = AccompBandPipeline(*sds, dit_cfg=synth.DIT_CFG, ddconfig=synth.VAE_DDCONFIG,
+                                     embed_dim=synth.VAE_EMBED_DIM, voc_cfg=synth.HIFIGAN_CFG, device=dev,
+                                     precision="bf16")
+        for _ in range(3):
+            pipe_bf.generate(devt[0], devt[1], devt[2], devt[3], x0=devt[4], generator=gen)
+        ms = 0.0
+        for _ in range(args.steps):
+            flush.fill_(1)
+            ev = {}
+            pipe_bf.generate(devt[0], devt[1], devt[2], devt[3], x0=devt[4], generator=gen, events=ev)
+            torch.cuda.synchronize()
+            ms += ev["start"].elapsed_time(ev["end"])
+        ms /= args.steps
+        fast = {"precision": "bf16 operands everywhere (DiT forward ~1e-2 of peak vs the fp32 reference)",
+                "value": B * CLIP_SECONDS / (ms * 1e-3), "ms_per_step": ms}
+        del pipe_bf
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -338,7 +365,7 @@ def run_ours(args):
             "gpu_launches": int(launches) * args.steps * 2 if launches else None,
             "gpu_launches_per_step": int(launches) if launches else None,
             "kernel_family_ms": {k: round(v["ms"], 3) for k, v in fam.items()} if fam else None,
-            "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clk, "bf16_fast_mode": fast,
         }
         print(json.dumps(line))
     if use_dist:
@@ -353,6 +380,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=1, help="clips per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fast-mode", action="store_true", help="skip the extra bf16-mode measurement")
     ap.add_argument("--precision", default="tf32", choices=["bf16", "tf32"],
                     help="GEMM operand format of the DiT: bf16 (default) or fp32-as-TF32 (accuracy mode)")
     args = ap.parse_args()
