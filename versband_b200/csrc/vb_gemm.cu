@@ -462,6 +462,183 @@ vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------------------ 2-CTA kernel
+// CTA pairs (cluster of 2 along M) run tcgen05.mma.cta_group::2: UMMA M = 256 (128 rows per CTA),
+// N = BN. Each CTA loads its own A tile and only HALF of the B tile; the tensor core reads both
+// halves across the pair. Per output element the operand bytes an SM has to pull from L2 drop
+// from (1/128 + 1/BN) to (1/128 + 1/(2 BN)) ... with BN = 256: half of the 128x128 kernel.
+// Protocol (leader = cluster rank 0): both CTAs' TMA credit the LEADER's full barrier, the leader
+// issues the MMAs and its commits arrive (multicast) on both CTAs' empty / accumulator-full
+// barriers, both epilogues release the accumulator on the leader's tmem_empty barrier.
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int kABytes = BM * 128;
+  static constexpr int kBBytes = (BN / 2) * 128;
+  static constexpr int kStages = (200 * 1024) / (kABytes + kBBytes) > 12 ? 12 : (200 * 1024) / (kABytes + kBBytes);
+  static constexpr int kAccStride = BN <= 128 ? 128 : 256;
+  static constexpr int kTmemCols = 2 * kAccStride;
+  static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + 1024 + 512;
+};
+
+template <int BN, bool TF32>
+__global__ void __launch_bounds__(kThreads, 1)
+vb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const GemmKParams p) {
+  using Cfg = Gemm2Cfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kBkElems = TF32 ? 32 : 64;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + kStages * Cfg::kBBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 2);   // leader's arrive.expect_tx + the peer producer's arrive
+      mbar_init(&empty_bar[s], 1);  // one multicast commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 256);  // 128 epilogue threads of each CTA
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 1) tmem_alloc2<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs initialised, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
+
+  const int num_kb = p.num_kb;
+  const int m_pairs = (p.m_tiles + 1) >> 1;
+  const int per_g = m_pairs * p.n_tiles;
+  const int num_pairs = per_g * (p.num_tiles / (p.m_tiles * p.n_tiles));  // x groups
+  const int n_clusters = gridDim.x >> 1;
+  const int first = blockIdx.x >> 1;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = first; t < num_pairs; t += n_clusters) {
+        const int g = t / per_g, r = t - g * per_g;
+        const int n_tile = r / m_pairs, m_tile = 2 * (r - n_tile * m_pairs) + (int)rank;
+        const int g1 = g % p.G1, g2 = g / p.G1;
+        const int m0 = m_tile * BM, n0 = n_tile * BN + (int)rank * (BN / 2);
+        const int a_c2 = g1 * p.a_c2_g1 + g2 * p.a_c2_g2;
+        const int a_c3 = g1 * p.a_c3_g1 + g2 * p.a_c3_g2;
+        const int b_c2 = g1 * p.b_c2_g1 + g2 * p.b_c2_g2;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t lead_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::kABytes + Cfg::kBBytes));
+          else mbar_arrive_cluster(lead_full);
+          const int tap = kb / p.kpt;
+          const int c0 = (kb - tap * p.kpt) * kBkElems;
+          const int c1 = m0 + tap * p.dil - p.pad;
+          tma_load_4d_2sm(smem_a + stage * Cfg::kABytes, &tmA, lead_full, c0, c1, a_c2, a_c3);
+          tma_load_3d_2sm(smem_b + stage * Cfg::kBBytes, &tmB, lead_full, kb * kBkElems, n0, b_c2);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer (leader CTA, single thread) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = TF32 ? make_idesc_tf32(2 * BM, BN) : make_idesc_bf16(2 * BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int t = first; t < num_pairs; t += n_clusters) {
+        const int acc = local & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((local >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * Cfg::kAccStride;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (TF32) umma2_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else umma2_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit2_mc(&empty_bar[stage], 3);  // frees the slot in both CTAs
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit2_mc(&tmem_full_bar[acc], 3);
+        ++local;
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs) =====================
+    const int q = warp_idx & 3;
+    const int r_in = q * 32 + lane;
+    int local = 0;
+    for (int t = first; t < num_pairs; t += n_clusters) {
+      const int g = t / per_g, rr = t - g * per_g;
+      const int n_tile = rr / m_pairs, m_tile = 2 * (rr - n_tile * m_pairs) + (int)rank;
+      const int g1 = g % p.G1, g2 = g / p.G1;
+      const int acc = local & 1;
+      const int m0 = m_tile * BM, n0 = n_tile * BN;
+      const int m = m0 + r_in;
+      const bool row_ok = m < p.M;
+      long long orow = 0;
+      bool store_ok = row_ok;
+      if (row_ok && p.mode == VB_EPI_GENERIC) {
+        if (p.row_map) orow = p.row_map[m];
+        else orow = (long long)m * p.row_mul + p.row_off + (long long)g1 * p.row_off_g1;
+        store_ok = (orow >= 0 && orow < p.rows_out);
+      }
+      mbar_wait(&tmem_full_bar[acc], (local >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_d + c, raw);
+        tmem_ld_wait();
+        const int n_base = n0 + c;
+        if (store_ok && n_base < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          if (p.mode == VB_EPI_QKV_ROPE) epilogue_qkv(p, v, m, n_base);
+          else epilogue_generic(p, v, m, n_base, g1, g2, 0, orow);
+        }
+      }
+      tc_fence_before();
+      if (leader) mbar_arrive(&tmem_empty_bar[acc]);
+      else mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));
+      ++local;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer may still signal my barriers / read my smem until here
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc2<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 static int encode_map(CUtensorMap* map, const void* base, int rank, const int64_t* dims,
                       const int64_t* strides, const uint32_t* box, bool tf32) {
@@ -516,7 +693,33 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKPar
   return VB_OK;
 }
 
+template <int BN, bool TF32>
+static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, int grid,
+                   cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(vb_gemm2_kernel<BN, TF32>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess)
+      return set_error(VB_ERR_CUDA, "cudaFuncSetAttribute(gemm2 smem=%d): %s", Cfg::kSmemBytes,
+                       cudaGetErrorString(e));
+    attr_set = true;
+  }
+  cudaError_t e = launch_k_cluster(vb_gemm2_kernel<BN, TF32>, 2, dim3(grid), dim3(kThreads), Cfg::kSmemBytes,
+                                   stream, tmA, tmB, p);
+  if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "vb_gemm (2-CTA) launch failed: %s", cudaGetErrorString(e));
+  return check_launch("vb_gemm2");
+}
+
+static int g_gemm2_mode = 0;  // 0 = off, 1 = heuristic, 2 = whenever legal
+
 }  // namespace vb
+
+extern "C" int vb_set_gemm2(int mode) {
+  vb::g_gemm2_mode = mode;
+  return VB_OK;
+}
 
 extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
   vb::ProfScope prof_scope(vb::PK_GEMM, stream_);
@@ -560,12 +763,21 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
   if (a->swiglu && (a->N % 2 != 0))
     return set_error(VB_ERR_INVALID, "vb_gemm: swiglu needs an even N");
 
+  // 2-CTA path (cta_group::2): non-grouped problems only (a pair shares its B tile)
+  bool use2 = false;
+  if (g_gemm2_mode > 0 && !a->tile_group && a->bn == 0 && a->N >= 128 && m_tiles >= 2) {
+    const int bn2 = a->N >= 256 ? 256 : 128;
+    const long long pairs = (long long)((m_tiles + 1) / 2) * ((a->N + bn2 - 1) / bn2) * G;
+    if (g_gemm2_mode == 2 || pairs >= 48) { use2 = true; bn = bn2; }
+    if (a->mode == VB_EPI_QKV_ROPE && (a->head_dim % 32) != 0) use2 = false;
+  }
+
   CUtensorMap tmA, tmB;
   {
     uint32_t box[4] = {static_cast<uint32_t>(bk), BM, 1, 1};
     int rc = encode_map(&tmA, a->a, 4, a->a_dims, a->a_strides, box, tf32);
     if (rc) return rc;
-    uint32_t boxb[3] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(bn), 1};
+    uint32_t boxb[3] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(use2 ? bn / 2 : bn), 1};
     rc = encode_map(&tmB, a->b, 3, a->b_dims, a->b_strides, boxb, tf32);
     if (rc) return rc;
   }
@@ -622,6 +834,13 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
+  }
+  if (use2) {
+    const long long pairs = (long long)((m_tiles + 1) / 2) * p.n_tiles * G;
+    int clusters = (int)(pairs < num_sms / 2 ? pairs : num_sms / 2);
+    const int g2 = clusters * 2;
+    if (bn == 256) return tf32 ? launch2<256, true>(tmA, tmB, p, g2, stream) : launch2<256, false>(tmA, tmB, p, g2, stream);
+    return tf32 ? launch2<128, true>(tmA, tmB, p, g2, stream) : launch2<128, false>(tmA, tmB, p, g2, stream);
   }
   dim3 grid(p.num_tiles < num_sms ? p.num_tiles : num_sms, 1, 1);
   switch (bn) {
