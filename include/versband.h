@@ -224,6 +224,12 @@ int vb_router(const float* cap_feat, const void* cap_feat_bf16, const float* Wc,
 int vb_moe_finalize(int32_t* bucket_count, float* usage, int E, int32_t* bucket_start, int32_t* row_map,
                     float* row_scale, int32_t* tile_group, int32_t* m_tiles_used, int max_rows,
                     float* lb_out, void* stream);
+/* finalize + scatter in one launch; also zeroes next_count/next_usage (the next block's counters) */
+int vb_moe_dispatch(const int32_t* idx_c, const int32_t* idx_a, const int32_t* slot_c, const int32_t* slot_a,
+                    const float* scale_c, const float* scale_a, const int32_t* bucket_count, const float* usage,
+                    int32_t* next_count, float* next_usage, int N, int E, int row_bytes, const void* x, void* xs,
+                    int32_t* row_map, float* row_scale, int32_t* tile_group, int32_t* m_tiles_used,
+                    int max_rows, float* lb_out, void* stream);
 int vb_moe_scatter(const int32_t* idx_c, const int32_t* idx_a, const int32_t* slot_c, const int32_t* slot_a,
                    const float* scale_c, const float* scale_a, const int32_t* bucket_start, int N, int E,
                    int row_bytes, const void* x, void* xs, int32_t* row_map, float* row_scale,

@@ -103,6 +103,7 @@ def _declare(l: C.CDLL) -> None:
         "vb_linear_small": [P, L, P, P, P, I, I, I, P],
         "vb_router": [P, P, P, P, P, I, P, I, P, P, P, F, I, I, I, I, P, P, P, P, P, P, P, P, P, P],
         "vb_moe_finalize": [P, P, I, P, P, P, P, P, I, P, P],
+        "vb_moe_dispatch": [P, P, P, P, P, P, P, P, P, P, I, I, I, P, P, P, P, P, P, I, P, P],
         "vb_moe_scatter": [P, P, P, P, P, P, P, I, I, I, P, P, P, P, P],
         "vb_moe_sort": [P, P, P, P, I, I, P, P, P, P, I, P, P],
         "vb_gather_rows": [P, P, P, I, I, P, I, P],

@@ -5,6 +5,7 @@
 // warps 2..5 = epilogue (TMEM lane quadrant = warp_idx % 4). One 128 x BN output tile per
 // CTA; several CTAs are co-resident per SM (smem permitting) so one CTA's epilogue overlaps
 // another's mainloop.
+#include <math.h>
 #include "vb_internal.h"
 #include "vb_ptx.cuh"
 
@@ -289,6 +290,7 @@ struct GemmCfg {
   static constexpr int kAccStride = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   static constexpr int kTmemCols = 2 * kAccStride;
   static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + 1024 /*align*/ + 512;
+  static_assert(BN % 32 == 0 && BN <= 256, "N tile");
 };
 
 struct TileCoord {
@@ -547,13 +549,13 @@ vb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t lead_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::kABytes + Cfg::kBBytes));
-          else mbar_arrive_cluster(lead_full);
           const int tap = kb / p.kpt;
           const int c0 = (kb - tap * p.kpt) * kBkElems;
           const int c1 = m0 + tap * p.dil - p.pad;
           tma_load_4d_2sm(smem_a + stage * Cfg::kABytes, &tmA, lead_full, c0, c1, a_c2, a_c3);
           tma_load_3d_2sm(smem_b + stage * Cfg::kBBytes, &tmB, lead_full, kb * kBkElems, n0, b_c2);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::kABytes + Cfg::kBBytes));
+          else mbar_arrive_cluster(lead_full);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -712,7 +714,7 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKPa
   return check_launch("vb_gemm2");
 }
 
-static int g_gemm2_mode = 0;  // 0 = off, 1 = heuristic, 2 = whenever legal
+static int g_gemm2_mode = 1;  // 0 = off, 1 = cost model, 2 = whenever legal
 
 }  // namespace vb
 
@@ -742,35 +744,53 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
   int bn = a->bn;
   const int m_tiles = (a->M + BM - 1) / BM;
   const int G = a->G1 * a->G2;
-  if (bn == 0) {
-    // one CTA per SM: prefer the tile width whose tile count best fills 148 SMs; small problems
-    // are latency-bound (more, narrower tiles = more SMs pulling from L2 in parallel), large ones
-    // want wide tiles (less operand re-fetch).
-    auto tiles = [&](int t) { return (long long)m_tiles * ((a->N + t - 1) / t) * G; };
-    if (a->N <= 32) bn = 32;
-    else if (a->N % 96 == 0 && a->N % 128 != 0 && a->N <= 192) bn = 96;
-    else if (a->N >= 256 && tiles(256) >= 2 * 148) bn = 256;
-    else if (a->N >= 128 && (tiles(128) >= 120 || (a->K >= 2048 && tiles(128) >= 48))) bn = 128;
-    else if (a->N >= 64 && tiles(64) >= 100) bn = 64;
-    else bn = a->N >= 64 && tiles(32) > 296 ? 64 : 32;
+  // ---- tile selection -------------------------------------------------------------------
+  // Cost model fitted to device timings on B200 (tools/bench_bn.py): operand ingest is bounded per
+  // SM (~64 B/clk) and chip-wide (L2 throughput, ~half of 148 x 64 B/clk), every tile pays an
+  // epilogue proportional to its width plus a fixed pipeline fill. Units: 128-byte rows.
+  bool use2 = false;
+  {
+    const bool user_bn = bn != 0;
+    const int cands[6] = {32, 64, 96, 128, 192, 256};
+    double best = 1e30;
+    int best_bn = 32;
+    const int n_cap = (a->N + 31) / 32 * 32;
+    for (int i = 0; i < 6; ++i) {
+      const int c = cands[i];
+      if (user_bn && c != bn) continue;
+      if (c > n_cap && c != 32) continue;
+      const double tiles = (double)m_tiles * ((a->N + c - 1) / c) * G;
+      const double waves = ceil(tiles / 148.0);
+      const double u = (double)num_kb * (128 + c);
+      const double cost = fmax(waves * u, tiles * u / 74.0) + waves * (40.0 * c + 1500.0);
+      if (cost < best) { best = cost; best_bn = c; }
+    }
+    // 2-CTA pairs (cta_group::2): each CTA loads only half of the B tile. Non-grouped problems only.
+    if (g_gemm2_mode > 0 && !user_bn && !a->tile_group && m_tiles >= 2 && a->N >= 128) {
+      const int c2s[3] = {128, 192, 256};
+      for (int i = 0; i < 3; ++i) {
+        const int c = c2s[i];
+        if (c > n_cap) continue;
+        const double ctas = 2.0 * ((m_tiles + 1) / 2) * ((a->N + c - 1) / c) * G;
+        const double waves = ceil(ctas / 148.0);
+        const double u = (double)num_kb * (128 + c / 2);
+        const double cost = fmax(waves * u, ctas * u / 74.0) + waves * (40.0 * c + 2100.0);
+        if (cost < best || g_gemm2_mode == 2) {
+          if (g_gemm2_mode == 2 && use2 && cost >= best) continue;
+          best = cost; best_bn = c; use2 = true;
+        }
+      }
+    }
+    bn = best_bn;
   }
   if (a->mode == VB_EPI_QKV_ROPE) {
     if (!a->k_out || !a->vt_out || a->head_dim % 32 != 0 ||
         a->N != (3 - a->qkv_sec0) * a->heads * a->head_dim || a->qkv_sec0 < 0 || a->qkv_sec0 > 1 || (a->qkv_sec0 == 0 && !a->q_out) || a->T <= 0 || a->M % a->T != 0)
       return set_error(VB_ERR_INVALID, "vb_gemm: bad QKV_ROPE arguments");
-    if (bn == 96 && (a->head_dim % 96) != 0) bn = 64;
+    if ((bn == 96 || bn == 192) && (a->head_dim % 32) != 0) { bn = 64; use2 = false; }
   }
   if (a->swiglu && (a->N % 2 != 0))
     return set_error(VB_ERR_INVALID, "vb_gemm: swiglu needs an even N");
-
-  // 2-CTA path (cta_group::2): non-grouped problems only (a pair shares its B tile)
-  bool use2 = false;
-  if (g_gemm2_mode > 0 && !a->tile_group && a->bn == 0 && a->N >= 128 && m_tiles >= 2) {
-    const int bn2 = a->N >= 256 ? 256 : 128;
-    const long long pairs = (long long)((m_tiles + 1) / 2) * ((a->N + bn2 - 1) / bn2) * G;
-    if (g_gemm2_mode == 2 || pairs >= 48) { use2 = true; bn = bn2; }
-    if (a->mode == VB_EPI_QKV_ROPE && (a->head_dim % 32) != 0) use2 = false;
-  }
 
   CUtensorMap tmA, tmB;
   {
@@ -840,6 +860,7 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
     int clusters = (int)(pairs < num_sms / 2 ? pairs : num_sms / 2);
     const int g2 = clusters * 2;
     if (bn == 256) return tf32 ? launch2<256, true>(tmA, tmB, p, g2, stream) : launch2<256, false>(tmA, tmB, p, g2, stream);
+    if (bn == 192) return tf32 ? launch2<192, true>(tmA, tmB, p, g2, stream) : launch2<192, false>(tmA, tmB, p, g2, stream);
     return tf32 ? launch2<128, true>(tmA, tmB, p, g2, stream) : launch2<128, false>(tmA, tmB, p, g2, stream);
   }
   dim3 grid(p.num_tiles < num_sms ? p.num_tiles : num_sms, 1, 1);
@@ -848,6 +869,7 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
     case 64: return tf32 ? launch<64, true>(tmA, tmB, p, grid, stream) : launch<64, false>(tmA, tmB, p, grid, stream);
     case 96: return tf32 ? launch<96, true>(tmA, tmB, p, grid, stream) : launch<96, false>(tmA, tmB, p, grid, stream);
     case 128: return tf32 ? launch<128, true>(tmA, tmB, p, grid, stream) : launch<128, false>(tmA, tmB, p, grid, stream);
+    case 192: return tf32 ? launch<192, true>(tmA, tmB, p, grid, stream) : launch<192, false>(tmA, tmB, p, grid, stream);
     case 256: return tf32 ? launch<256, true>(tmA, tmB, p, grid, stream) : launch<256, false>(tmA, tmB, p, grid, stream);
     default: return set_error(VB_ERR_INVALID, "vb_gemm: unsupported N tile %d", bn);
   }

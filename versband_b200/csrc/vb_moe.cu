@@ -290,6 +290,69 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ x, const in
   for (int i = lane; i < D / 8; i += 32) dst[i] = src[i];
 }
 
+// Dispatch in one launch. Every CTA rebuilds the (<= 16) padded bucket starts from the router's
+// counters; one warp per (token, group) entry places the entry in its bucket slot and copies its
+// activation row; CTA 0 additionally writes the tile table, tile count, load-balancing loss,
+// marks padding rows invalid and zeroes the NEXT block's counters (this block's counters were
+// zeroed by the previous block's dispatch, so no separate memset/finalize launch is needed).
+__global__ void moe_dispatch_kernel(const int* __restrict__ idx_c, const int* __restrict__ idx_a,
+                                    const int* __restrict__ slot_c, const int* __restrict__ slot_a,
+                                    const float* __restrict__ scale_c, const float* __restrict__ scale_a,
+                                    const int* __restrict__ bucket_count, const float* __restrict__ usage,
+                                    int* __restrict__ next_count, float* __restrict__ next_usage, int N, int E,
+                                    int row_bytes, const uint8_t* __restrict__ x, uint8_t* __restrict__ xs,
+                                    int* __restrict__ row_map, float* __restrict__ row_scale,
+                                    int* __restrict__ tile_group, int* __restrict__ m_tiles_used, int max_rows,
+                                    float* __restrict__ lb_out) {
+  pdl_sync();
+  __shared__ int s_start[17], s_cnt[16];
+  const int nb = 2 * E;
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int k = 0; k < nb; ++k) {
+      const int c = bucket_count[k];
+      s_cnt[k] = c;
+      s_start[k] = acc;
+      acc += (c + 127) / 128 * 128;
+    }
+    s_start[nb] = acc;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int k = 0; k < nb; ++k) {
+        for (int t = s_start[k] / 128; t < s_start[k + 1] / 128; ++t) tile_group[t] = k;
+        tot += usage[k];
+      }
+      *m_tiles_used = s_start[nb] / 128;
+      if (lb_out) {
+        float loss = 0.f;
+        const float total = tot * (float)E;
+        for (int k = 0; k < nb; ++k) {
+          const float u = usage[k] / (total + 1e-10f);
+          loss += u * logf(u + 1e-10f);
+        }
+        *lb_out = loss / (float)nb;
+      }
+    }
+    for (int k = 0; k < nb; ++k)
+      for (int sl = s_start[k] + s_cnt[k] + threadIdx.x; sl < s_start[k + 1]; sl += blockDim.x) { row_map[sl] = -1; row_scale[sl] = 0.f; }
+    for (int sl = s_start[nb] + threadIdx.x; sl < max_rows; sl += blockDim.x) { row_map[sl] = -1; row_scale[sl] = 0.f; }
+    if (threadIdx.x < nb && next_count) { next_count[threadIdx.x] = 0; next_usage[threadIdx.x] = 0.f; }
+  }
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= 2 * N) return;
+  const int g = i / N, n = i - g * N;
+  const int bucket = g * E + (g ? idx_a[n] : idx_c[n]);
+  const int slot = s_start[bucket] + (g ? slot_a[n] : slot_c[n]);
+  if (lane == 0) { row_map[slot] = i; row_scale[slot] = g ? scale_a[n] : scale_c[n]; }
+  const uint4* src = reinterpret_cast<const uint4*>(x + (long long)n * row_bytes);
+  uint4* dst = reinterpret_cast<uint4*>(xs + (long long)slot * row_bytes);
+  for (int k = lane; k < row_bytes / 16; k += 32) dst[k] = src[k];
+}
+
 }  // namespace vb
 
 using namespace vb;
@@ -368,4 +431,23 @@ extern "C" int vb_moe_scatter(const int32_t* idx_c, const int32_t* idx_a, const 
            idx_a, slot_c, slot_a, scale_c, scale_a, bucket_start, N, E, row_bytes,
            static_cast<const uint8_t*>(x), static_cast<uint8_t*>(xs), row_map, row_scale);
   return check_launch("vb_moe_scatter");
+}
+
+extern "C" int vb_moe_dispatch(const int32_t* idx_c, const int32_t* idx_a, const int32_t* slot_c,
+                               const int32_t* slot_a, const float* scale_c, const float* scale_a,
+                               const int32_t* bucket_count, const float* usage, int32_t* next_count,
+                               float* next_usage, int N, int E, int row_bytes, const void* x, void* xs,
+                               int32_t* row_map, float* row_scale, int32_t* tile_group,
+                               int32_t* m_tiles_used, int max_rows, float* lb_out, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_MOE_SORT, stream);
+  if (!idx_c || !idx_a || !slot_c || !slot_a || !bucket_count || !usage || !x || !xs || !row_map || !row_scale ||
+      !tile_group || !m_tiles_used || row_bytes % 16 || E <= 0 || E > 8)
+    return set_error(VB_ERR_INVALID, "vb_moe_dispatch: bad arguments");
+  if (max_rows < ((2 * N + 127) / 128 + 2 * E) * 128)
+    return set_error(VB_ERR_INVALID, "vb_moe_dispatch: max_rows %d too small for N=%d E=%d", max_rows, N, E);
+  launch_k(moe_dispatch_kernel, dim3((2 * N + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream), idx_c, idx_a,
+           slot_c, slot_a, scale_c, scale_a, bucket_count, usage, next_count, next_usage, N, E, row_bytes,
+           static_cast<const uint8_t*>(x), static_cast<uint8_t*>(xs), row_map, row_scale, tile_group, m_tiles_used,
+           max_rows, lb_out);
+  return check_launch("vb_moe_dispatch");
 }

@@ -179,7 +179,7 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_smem_addr, uint32
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_slot) {

@@ -216,7 +216,7 @@ class DiTEngine:
             oa=z(N, D, dt=AD),
             xm=z(N, D, dt=AD), qm=z(N, D, dt=BF), ctx=z(N, D, dt=BF),
             idx_c=z(N, dt=torch.int32), idx_a=z(N, dt=torch.int32), scale_c=z(N), scale_a=z(N),
-            cap_logits=z(N, E), bucket_count=z(2 * E, dt=torch.int32), usage=z(2 * E), bucket_start=z(2 * E, dt=torch.int32),
+            cap_logits=z(N, E), bucket_count=z(self.depth, 2 * E, dt=torch.int32), usage=z(self.depth, 2 * E), bucket_start=z(2 * E, dt=torch.int32),
             slot_c=z(N, dt=torch.int32), slot_a=z(N, dt=torch.int32),
             row_map=z(max_rows, dt=torch.int32), row_scale=z(max_rows), tile_group=z(max_rows // 128, dt=torch.int32),
             m_tiles=z(1, dt=torch.int32), lb=z(self.depth),
@@ -301,11 +301,30 @@ class DiTEngine:
                 vl.append(vt)
         return cond
 
+    # ------------------------------------------------------------------ time conditioning
+    @torch.no_grad()
+    def time_conditioning(self, t: torch.Tensor, cap_emb: torch.Tensor, mod_out: torch.Tensor, hl_out: torch.Tensor):
+        """t int64 [R], cap_emb fp32 [R, D] -> mod_out [R, mod_ld] (adaLN vectors of every block + final
+        layer) and hl_out [R, 2*depth] (group-gate logits). Rows are independent (R = batch, or
+        steps x batch when the sampler precomputes the whole schedule)."""
+        w, D, dev = self.w, self.D, self.dev
+        R = t.numel()
+        sin = torch.empty(R, 256, device=dev, dtype=self.adt)
+        h = torch.empty(R, D, device=dev, dtype=self.adt)
+        temb = torch.empty(R, D, device=dev, dtype=F32)
+        ada = torch.empty(R, D, device=dev, dtype=self.adt)
+        ops.timestep_embed(t, w["t_freqs"], out_bf16=sin)
+        ops.gemm(sin, w["t_w0"], bias=w["t_b0"], act=ops.ACT_SILU, out_bf16=h, outb_ld=D)
+        ops.gemm(h, w["t_w2"], bias=w["t_b2"], out_f32=temb, out_ld=D)
+        ops.ew(temb, cap_emb, act=ops.ACT_SILU, out_bf16=ada)
+        ops.gemm(ada, w["ada_w"], bias=w["ada_b"], out_f32=mod_out, out_ld=self.mod_ld)
+        ops.linear_small(temb, w["hl_w"], w["hl_b"], hl_out)
+
     # ------------------------------------------------------------------ one DiT evaluation
     @torch.no_grad()
     def forward(self, x: torch.Tensor, t: torch.Tensor, cond: DiTCond,
                 expo: List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]],
-                out_v: Optional[torch.Tensor] = None, want_aux: bool = False):
+                out_v: Optional[torch.Tensor] = None, want_aux: bool = False, pre=None):
         """x fp32 [B, C, T], t int64 [B]; expo[k] = Exp(1) draws ([N,2],[N,E],[N,E]) of block k.
         Returns v as the channels-last GEMM output [N, 32] (first C columns valid) unless `out_v`
         ([B, C, T]) is given, plus lb_loss per block (device tensor)."""
@@ -327,20 +346,14 @@ class DiTEngine:
                  a_c2=(1, 0), bias=w["proj_in_b"], residual=cond.acoustic, out_f32=ws["x"], out_ld=D,
                  out_g=(T * D, 0))
         ops.mark("gemm:proj_in_w")
-        # timestep embedding MLP and adaLN input (:406,416)
-        ops.timestep_embed(t.contiguous(), w["t_freqs"], out_bf16=ws["temb_sin"])
-        ops.mark("timestep_embed")
-        ops.gemm(ws["temb_sin"], w["t_w0"], bias=w["t_b0"], act=ops.ACT_SILU, out_bf16=ws["temb_h"], outb_ld=D)
-        ops.mark("gemm:t_w0")
-        ops.gemm(ws["temb_h"], w["t_w2"], bias=w["t_b2"], out_f32=ws["temb"], out_ld=D)
-        ops.mark("gemm:t_w2")
-        ops.ew(ws["temb"], cond.cap_emb, act=ops.ACT_SILU, out_bf16=ws["ada_in"])
-        ops.mark("ew")
-        ops.gemm(ws["ada_in"], w["ada_w"], bias=w["ada_b"], out_f32=ws["mod"], out_ld=self.mod_ld)
-        ops.mark("gemm:ada_w")
-        ops.linear_small(ws["temb"], w["hl_w"], w["hl_b"], ws["hl"])
-        ops.mark("linear_small")
-        mod, mld = ws["mod"], self.mod_ld
+        # timestep embedding MLP, adaLN input and all modulation vectors (:406,416,242,290): depend only on
+        # (t, caption) — the sampler precomputes them for all 24 steps at once (`time_conditioning`)
+        if pre is None:
+            self.time_conditioning(t.contiguous(), cond.cap_emb, ws["mod"], ws["hl"])
+            mod_t, hl_t = ws["mod"], ws["hl"]
+        else:
+            mod_t, hl_t = pre
+        mod, mld = mod_t, self.mod_ld
 
         xcur, hbuf = ws["x"], ws["h"]
         for k in range(self.depth):
@@ -374,17 +387,23 @@ class DiTEngine:
             ops.mark("attn_fused")
             e0, e1, e2 = expo[k]
             ops.router(ws["ctx"], b["capg_w"], b["capg_b"], cond.ac_logits[:, k * E:], self.depth * E,
-                       ws["hl"][:, 2 * k:], 2 * self.depth, e0, e1, e2, float(self.temperature), N, T,
+                       hl_t[:, 2 * k:], 2 * self.depth, e0, e1, e2, float(self.temperature), N, T,
                        ws["idx_c"], ws["idx_a"], ws["scale_c"], ws["scale_a"],
-                       ws["cap_logits"] if want_aux else None, ws["bucket_count"], ws["usage"],
+                       ws["cap_logits"] if want_aux else None, ws["bucket_count"][k], ws["usage"][k],
                        ws["slot_c"], ws["slot_a"])
             ops.mark("router")
-            ops.moe_finalize(ws["bucket_count"], ws["usage"], E, ws["bucket_start"], ws["row_map"], ws["row_scale"],
-                             ws["tile_group"], ws["m_tiles"], max_rows, ws["lb"][k:])
-            ops.mark("moe_finalize")
-            ops.moe_scatter(ws["idx_c"], ws["idx_a"], ws["slot_c"], ws["slot_a"], ws["scale_c"], ws["scale_a"],
-                            ws["bucket_start"], N, E, ws["xm"], ws["xs"], ws["row_map"], ws["row_scale"])
-            ops.mark("moe_scatter")
+            if self.depth > 1:
+                kn = (k + 1) % self.depth  # the dispatch of block k zeroes the counters of block k+1
+                ops.moe_dispatch(ws["idx_c"], ws["idx_a"], ws["slot_c"], ws["slot_a"], ws["scale_c"], ws["scale_a"],
+                                 ws["bucket_count"][k], ws["usage"][k], ws["bucket_count"][kn], ws["usage"][kn], N, E,
+                                 ws["xm"], ws["xs"], ws["row_map"], ws["row_scale"], ws["tile_group"], ws["m_tiles"],
+                                 max_rows, ws["lb"][k:])
+            else:  # single block: counters must be re-zeroed by a separate launch
+                ops.moe_finalize(ws["bucket_count"][0], ws["usage"][0], E, ws["bucket_start"], ws["row_map"],
+                                 ws["row_scale"], ws["tile_group"], ws["m_tiles"], max_rows, ws["lb"][k:])
+                ops.moe_scatter(ws["idx_c"], ws["idx_a"], ws["slot_c"], ws["slot_a"], ws["scale_c"], ws["scale_a"],
+                                ws["bucket_start"], N, E, ws["xm"], ws["xs"], ws["row_map"], ws["row_scale"])
+            ops.mark("moe_dispatch")
             ops.gemm(ws["xs"], b["w13"], M=max_rows, b_c2=(0, 0, 1), tile_group=ws["tile_group"],
                      m_tiles_used=ws["m_tiles"], swiglu=True, out_bf16=ws["hs"], outb_ld=Fh)
             ops.mark("gemm:w13")

@@ -173,6 +173,13 @@ def moe_finalize(bucket_count, usage, E, bucket_start, row_map, row_scale, tile_
           _ptr(tile_group), _ptr(m_tiles_used), max_rows, _ptr(lb_out))
 
 
+def moe_dispatch(idx_c, idx_a, slot_c, slot_a, scale_c, scale_a, bucket_count, usage, next_count, next_usage, N, E,
+                 x, xs, row_map, row_scale, tile_group, m_tiles_used, max_rows, lb_out=None) -> None:
+    _call("vb_moe_dispatch", _ptr(idx_c), _ptr(idx_a), _ptr(slot_c), _ptr(slot_a), _ptr(scale_c), _ptr(scale_a),
+          _ptr(bucket_count), _ptr(usage), _ptr(next_count), _ptr(next_usage), N, E, x.shape[-1] * x.element_size(),
+          _ptr(x), _ptr(xs), _ptr(row_map), _ptr(row_scale), _ptr(tile_group), _ptr(m_tiles_used), max_rows, _ptr(lb_out))
+
+
 def moe_scatter(idx_c, idx_a, slot_c, slot_a, scale_c, scale_a, bucket_start, N, E, x, xs, row_map, row_scale) -> None:
     _call("vb_moe_scatter", _ptr(idx_c), _ptr(idx_a), _ptr(slot_c), _ptr(slot_a), _ptr(scale_c), _ptr(scale_a),
           _ptr(bucket_start), N, E, x.shape[-1] * x.element_size(), _ptr(x), _ptr(xs), _ptr(row_map), _ptr(row_scale))

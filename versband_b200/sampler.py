@@ -103,11 +103,15 @@ class FlowSampler:
     def _run(self, st: dict, scale: float, rng: bool, generator) -> None:
         d = self.dit.depth
         x, cond2, N = st["x"], st["cond2"], st["N"]
+        # adaLN / gate vectors of all steps in one batch of S*2B rows (they only depend on t and caption)
+        S, B2 = st["t_all"].shape
+        self.dit.time_conditioning(st["t_all"].reshape(-1), cond2.cap_emb.repeat(S, 1), st["mod_all"].view(S * B2, -1),
+                                   st["hl_all"].view(S * B2, -1))
         for s, (_, dt) in enumerate(self.sched):
             if rng:
                 self._draw_step(st, s, generator)
             expo = [(st["e0"][s, k], st["e1"][s, k], st["e2"][s, k]) for k in range(d)]
-            v, _ = self.dit.forward(x, st["t_all"][s], cond2, expo)
+            v, _ = self.dit.forward(x, st["t_all"][s], cond2, expo, pre=(st["mod_all"][s], st["hl_all"][s]))
             ops.ntc_to_nct(v[:N], x, e_u=v[N:], ld=v.shape[-1], s=scale, dt=dt)
 
     @torch.no_grad()
@@ -129,6 +133,8 @@ class FlowSampler:
                       e1=torch.empty(S, d, 2 * N, E, device=dev, dtype=F32),
                       e2=torch.empty(S, d, 2 * N, E, device=dev, dtype=F32),
                       t_all=torch.tensor([[t] * (2 * B) for t, _ in self.sched], device=dev, dtype=torch.int64),
+                      mod_all=torch.empty(S, 2 * B, self.dit.mod_ld, device=dev, dtype=F32),
+                      hl_all=torch.empty(S, 2 * B, 2 * d, device=dev, dtype=F32),
                       graphs={})
             self._state[key] = st
         else:
