@@ -295,8 +295,14 @@ def run_ours(args):
         launches = _lib.launch_count() - n0
         pipe.sampler = saved
         pipe.use_graph = True
-        gemm_ms = fam["gemm"]["ms"]
+        gemm_ms_eager = fam["gemm"]["ms"]
         n_gemm = fam["gemm"]["launches"]
+        share = gemm_ms_eager / sum(v["ms"] for v in fam.values())
+        # Per-launch CUDA-event pairs exist only in the instrumented EAGER pass, where the GPU idles between
+        # launches (Python-bound) and the kernels run cold. The timed region replays CUDA graphs, so the GEMM
+        # time inside it is taken as (device-timed step) x (GEMM share of kernel time from the event pairs);
+        # the raw event-timed figure is reported next to it.
+        gemm_ms = ms_step * share
         achieved = FLOP_CLIP * B / (gemm_ms * 1e-3) / 1e12
         traffic = None
         try:  # dram bytes of the same kernel family over one step, from the committed ncu capture
@@ -305,13 +311,15 @@ def run_ours(args):
             traffic = tj["dram_bytes"] / tj["launches"]
         except Exception:
             pass
-        roof = {"bound": "tensor", "kernel": "vb_gemm_kernel<BN,TF32> (tcgen05/TMA implicit-GEMM, all launches of one step)",
+        roof = {"bound": "tensor", "kernel": "vb_gemm_kernel / vb_gemm2_kernel <BN,TF32> (tcgen05/TMA implicit-GEMM, all launches of one step)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "peak_source": peak_src, "traffic": traffic,
                 "traffic_note": "mean dram read+write bytes per launch (ncu, L2 flushed before every launch), profiles/r1_traffic_eager_step.json",
                 "launches_per_step": n_gemm, "avg_launch_us": gemm_ms * 1e3 / max(n_gemm, 1),
                 "algorithmic_flop_per_step": FLOP_CLIP * B,
-                "kernel_time_share_of_step": gemm_ms / sum(v["ms"] for v in fam.values())}
+                "kernel_time_share_of_step": share,
+                "method": "GEMM time in the timed (graph-replay) region = ms_per_step x share; share from per-launch CUDA-event pairs in an eager pass",
+                "eager_event_timed": {"gemm_ms": gemm_ms_eager, "achieved": FLOP_CLIP * B / (gemm_ms_eager * 1e-3) / 1e12}}
 
     fast = None
     if rank == 0 and world == 1 and args.precision == "tf32" and not args.no_fast_mode:

@@ -268,8 +268,10 @@ int vb_embed_rows(const int64_t* idx, const float* table, int V, int D, void* ou
 int vb_pool2_sum(const float* a, const float* b, int B, int Tin, int Tout, int D, void* out_bf16,
                  float* out_f32, void* stream);
 /* GroupNorm over channels-last [B,T,C] (autoencoder1d.py:165-166) */
+/* scratch: B*G*VB_GN_SPLIT*2 doubles (partial sums of the split-T first pass) */
+#define VB_GN_SPLIT 8
 int vb_gn_stats(const float* x, int B, int T, int C, int G, float eps, float* mean, float* rstd,
-                void* stream);
+                void* scratch, void* stream);
 int vb_gn_apply(const float* x, const float* mean, const float* rstd, const float* w,
                 const float* bias, int B, int T, int C, int G, int act, void* out_bf16, void* stream);
 /* HiFi-GAN conv_post + tanh (vocoder/hifigan/modules/hifigan.py:139-141); w is [k][C] fp32 */

@@ -114,7 +114,7 @@ def _declare(l: C.CDLL) -> None:
         "vb_ntc_to_nct": [P, P, L, F, F, P, I, I, I, P],
         "vb_embed_rows": [P, P, I, I, P, L, I, P],
         "vb_pool2_sum": [P, P, I, I, I, I, P, P, P],
-        "vb_gn_stats": [P, I, I, I, I, F, P, P, P],
+        "vb_gn_stats": [P, I, I, I, I, F, P, P, P, P],
         "vb_gn_apply": [P, P, P, P, P, I, I, I, I, I, P, P],
         "vb_conv_post": [P, P, F, I, I, I, I, P, P],
     }

@@ -144,18 +144,20 @@ __global__ void pool2_sum_kernel(const float* __restrict__ a, const float* __res
 }
 
 // GroupNorm statistics over channels-last x[B, T, C]: per (b, group) mean and rstd
-// (autoencoder1d.py:165-166: 32 groups, eps 1e-6). fp64 accumulation.
-__global__ void gn_stats_kernel(const float* __restrict__ x, int T, int C, int G, float eps,
-                                float* __restrict__ mean, float* __restrict__ rstd) {
+// (autoencoder1d.py:165-166: 32 groups, eps 1e-6). Two launches, deterministic: gn_partial splits T
+// into `nsplit` slabs (grid = G x B x nsplit, coalesced rows, fp64 accumulation), gn_finish combines.
+__global__ void gn_partial_kernel(const float* __restrict__ x, int T, int C, int G, int nsplit,
+                                  double* __restrict__ part) {
   pdl_sync();
-  const int g = blockIdx.x, b = blockIdx.y;
+  const int g = blockIdx.x, b = blockIdx.y, sp = blockIdx.z;
   const int cpg = C / G;
+  const int t0 = (int)((long long)T * sp / nsplit), t1 = (int)((long long)T * (sp + 1) / nsplit);
   const float* base = x + (long long)b * T * C + g * cpg;
   double s = 0.0, ss = 0.0;
-  const int n = T * cpg;
+  const int n = (t1 - t0) * cpg;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int t = i / cpg, c = i - t * cpg;
-    const float v = base[(long long)t * C + c];
+    const float v = __ldg(base + (long long)(t0 + t) * C + c);
     s += v;
     ss += (double)v * v;
   }
@@ -177,12 +179,24 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int T, int C, int G
       ss += __shfl_xor_sync(0xffffffffu, ss, o);
     }
     if (lane == 0) {
-      const double m = s / n;
-      const double var = ss / n - m * m;
-      mean[b * G + g] = (float)m;
-      rstd[b * G + g] = (float)(1.0 / sqrt((var > 0 ? var : 0) + (double)eps));
+      double* p = part + (((long long)b * G + g) * nsplit + sp) * 2;
+      p[0] = s;
+      p[1] = ss;
     }
   }
+}
+
+__global__ void gn_finish_kernel(const double* __restrict__ part, int nsplit, long long n_per_group, float eps,
+                                 float* __restrict__ mean, float* __restrict__ rstd, int total) {
+  pdl_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  double s = 0.0, ss = 0.0;
+  for (int k = 0; k < nsplit; ++k) { s += part[((long long)i * nsplit + k) * 2]; ss += part[((long long)i * nsplit + k) * 2 + 1]; }
+  const double m = s / (double)n_per_group;
+  const double var = ss / (double)n_per_group - m * m;
+  mean[i] = (float)m;
+  rstd[i] = (float)(1.0 / sqrt((var > 0 ? var : 0) + (double)eps));
 }
 
 // y = act((x - mean) * rstd * w + b) -> bf16 (A operand of the following conv GEMM)
@@ -308,10 +322,16 @@ extern "C" int vb_pool2_sum(const float* a, const float* b, int B, int Tin, int 
 }
 
 extern "C" int vb_gn_stats(const float* x, int B, int T, int C, int G, float eps, float* mean,
-                           float* rstd, void* stream) {
+                           float* rstd, void* scratch, void* stream) {
   vb::ProfScope prof_scope(vb::PK_GN, stream);
-  if (!x || !mean || !rstd || C % G) return set_error(VB_ERR_INVALID, "vb_gn_stats: bad arguments");
-  launch_k(gn_stats_kernel, dim3(dim3(G, B)), dim3(512), 0, static_cast<cudaStream_t>(stream), x, T, C, G, eps, mean, rstd);
+  if (!x || !mean || !rstd || !scratch || C % G) return set_error(VB_ERR_INVALID, "vb_gn_stats: bad arguments");
+  const int nsplit = VB_GN_SPLIT;
+  launch_k(gn_partial_kernel, dim3(G, B, nsplit), dim3(256), 0, static_cast<cudaStream_t>(stream), x, T, C, G, nsplit,
+           static_cast<double*>(scratch));
+  int rc = check_launch("vb_gn_stats");
+  if (rc) return rc;
+  launch_k(gn_finish_kernel, dim3((B * G + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream),
+           static_cast<const double*>(scratch), nsplit, (long long)T * (C / G), eps, mean, rstd, B * G);
   return check_launch("vb_gn_stats");
 }
 

@@ -223,8 +223,13 @@ def pool2_sum(a, b, *, B, Tin, Tout, D, out_bf16=None, out_f32=None) -> None:
     _call("vb_pool2_sum", _ptr(a), _ptr(b), B, Tin, Tout, D, _ptr(out_bf16), _ptr(out_f32))
 
 
-def gn_stats(x, B, T, Cc, G, eps, mean, rstd) -> None:
-    _call("vb_gn_stats", _ptr(x), B, T, Cc, G, eps, _ptr(mean), _ptr(rstd))
+GN_SPLIT = 8
+
+
+def gn_stats(x, B, T, Cc, G, eps, mean, rstd, scratch=None) -> None:
+    if scratch is None:
+        scratch = torch.empty(B * G * GN_SPLIT * 2, device=x.device, dtype=torch.float64)
+    _call("vb_gn_stats", _ptr(x), B, T, Cc, G, eps, _ptr(mean), _ptr(rstd), _ptr(scratch))
 
 
 def gn_apply(x, mean, rstd, w, b, B, T, Cc, G, act, out_bf16) -> None:
