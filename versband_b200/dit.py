@@ -301,6 +301,14 @@ class DiTEngine:
                 vl.append(vt)
         return cond
 
+    @torch.no_grad()
+    def prepare_pair(self, midi, beats, caption: torch.Tensor, caption_uncond: torch.Tensor, T: int) -> DiTCond:
+        """Conditioning of the (cond, uncond) CFG pair as ONE batch of 2B clips (cond rows first): the
+        acoustic stem is computed once and shared, the caption path runs once on the stacked captions."""
+        ac, ac_logits = self.prepare_acoustic(midi, beats, T)
+        return self.prepare(None, None, torch.cat([caption, caption_uncond], 0), T,
+                            acoustic=(torch.cat([ac, ac], 0), torch.cat([ac_logits, ac_logits], 0)))
+
     # ------------------------------------------------------------------ time conditioning
     @torch.no_grad()
     def time_conditioning(self, t: torch.Tensor, cap_emb: torch.Tensor, mod_out: torch.Tensor, hl_out: torch.Tensor):

@@ -33,6 +33,7 @@ class AccompBandPipeline:
         self.scale_factor = float(scale_factor)
         self.use_graph = use_graph
         self._post = {}
+        self._prep = {}
         self.hop = 1
         for u in voc_cfg["upsample_rates"]:
             self.hop *= u
@@ -49,13 +50,11 @@ class AccompBandPipeline:
         T = (Tm + 1) // 2  # scripts/test_final.py:389 — latent length = ceil(T_mel / 2)
         mark = (lambda k: events.__setitem__(k, _ev())) if events is not None else (lambda k: None)
         mark("start")
-        ac = self.dit.prepare_acoustic(midi, beats, T)
-        cond = self.dit.prepare(midi, beats, caption, T, acoustic=ac)
-        uncond = self.dit.prepare(midi, beats, caption_uncond, T, acoustic=ac)
+        cond2 = self._prepare(midi, beats, caption, caption_uncond, T)
         if x0 is None:
             x0 = torch.randn(B, self.dit.C, T, device=dev, dtype=F32, generator=generator)
         mark("sampler_start")
-        z = self.sampler.sample_cfg(x0, cond, uncond, guidance, noise=noise, generator=generator)
+        z = self.sampler.sample_cfg(x0, cond2, None, guidance, noise=noise, generator=generator)
         mark("sampler_end")
         if not self.use_graph:
             mel = self.vae.decode(z, scale=1.0 / self.scale_factor)  # ddpm_audio.py:386
@@ -84,6 +83,30 @@ class AccompBandPipeline:
         mark("vae_end")  # (decode and vocoder are one graph: the split is not observable)
         mark("end")
         return {"latent": z, "mel": st["mel"].clone(), "wav": st["wav"].clone()}
+
+    def _prepare(self, midi, beats, caption, caption_uncond, T):
+        """Step-invariant conditioning of the CFG pair; replayed from a CUDA graph per input shape."""
+        if not self.use_graph:
+            return self.dit.prepare_pair(midi, beats, caption, caption_uncond, T)
+        key = (tuple(midi.shape), tuple(caption.shape), T)
+        st = self._prep.get(key)
+        if st is None:
+            st = {"in": [t.clone() for t in (midi, beats, caption.float(), caption_uncond.float())]}
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.dit.prepare_pair(*st["in"], T)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st["cond2"] = self.dit.prepare_pair(*st["in"], T)
+            st["graph"] = g
+            self._prep[key] = st
+        for dst, src in zip(st["in"], (midi, beats, caption, caption_uncond)):
+            dst.copy_(src)
+        st["graph"].replay()
+        return st["cond2"]
 
     @torch.no_grad()
     def generate_host(self, midi, beats, caption, caption_uncond, *, guidance=3.0, x0=None, noise=None,

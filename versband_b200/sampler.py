@@ -115,20 +115,26 @@ class FlowSampler:
             ops.ntc_to_nct(v[:N], x, e_u=v[N:], ld=v.shape[-1], s=scale, dt=dt)
 
     @torch.no_grad()
-    def sample_cfg(self, x0: torch.Tensor, cond: DiTCond, uncond: DiTCond, scale: float,
+    def sample_cfg(self, x0: torch.Tensor, cond: DiTCond, uncond: Optional[DiTCond], scale: float,
                    noise: Optional[torch.Tensor] = None, generator=None) -> torch.Tensor:
         """x0 fp32 [B, C, T] -> x1 [B, C, T].  With `noise` (from draw_noise) the run is a pure
         function of its arguments; otherwise the draws come from `generator` (default CUDA
-        generator if None) inside the replayed graph."""
+        generator if None).  `uncond=None` means `cond` already is the stacked (cond, uncond) pair of
+        2B clips (DiTEngine.prepare_pair); a pair object that stays the same between calls is used in
+        place (no copies), which is how the pipeline feeds the sampler graph from its prepare graph."""
         dev, d, E = self.dit.dev, self.dit.depth, self.dit.E
         B, C, T = x0.shape
         N = B * T
         rng = noise is None
         key = (B, T, cond.L)
+        pair = cond if uncond is None else None
+        if pair is not None:
+            assert pair.B == 2 * B
         st = self._state.get(key)
         if st is None:
             S = len(self.sched)
-            st = dict(N=N, x=torch.empty(B, C, T, device=dev, dtype=F32), cond2=DiTCond.cat([cond, uncond]),
+            st = dict(N=N, x=torch.empty(B, C, T, device=dev, dtype=F32),
+                      cond2=pair if pair is not None else DiTCond.cat([cond, uncond]),
                       e0=torch.empty(S, d, 2 * N, 2, device=dev, dtype=F32),
                       e1=torch.empty(S, d, 2 * N, E, device=dev, dtype=F32),
                       e2=torch.empty(S, d, 2 * N, E, device=dev, dtype=F32),
@@ -137,8 +143,10 @@ class FlowSampler:
                       hl_all=torch.empty(S, 2 * B, 2 * d, device=dev, dtype=F32),
                       graphs={})
             self._state[key] = st
-        else:
+        elif pair is None:
             st["cond2"].copy_from(DiTCond.cat([cond, uncond]))
+        elif pair is not st["cond2"]:
+            st["cond2"].copy_from(pair)
         st["x"].copy_(x0)
         if rng and self.native_noise_ok():
             # all 576 Exp(1) draws in one launch, bit-identical to torch's stream; the graph below then
