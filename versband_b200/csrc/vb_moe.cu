@@ -74,45 +74,60 @@ __global__ void router_kernel(const float* __restrict__ cap_feat, const __nv_bfl
   }
 #pragma unroll
   for (int e = 0; e < E; ++e) acc[e] = wsum(acc[e]);
-  if (lane != 0) return;
+  // The three Gumbel-softmaxes of this token run in parallel on lanes 0..E-1 (caption gate),
+  // E..2E-1 (acoustic gate) and 2E, 2E+1 (group gate); every lane of a gate gathers the gate's
+  // values with shuffles and reduces them in index order, i.e. the same arithmetic as a serial loop.
   const int b = n / T;
-  // group gate
-  const float g0 = hl_logits[b * hl_ld + 0] + (-logf(e0[(long long)n * 2 + 0]));
-  const float g1 = hl_logits[b * hl_ld + 1] + (-logf(e0[(long long)n * 2 + 1]));
-  const float gm = fmaxf(g0, g1);
-  const float x0 = expf(g0 - gm), x1 = expf(g1 - gm);
-  const float mask_c = x0 / (x0 + x1), mask_a = x1 / (x0 + x1);
-  auto hard = [&](const float* logit, const float* expo, int& idx, float& w) {
-    float z[E];
-    float m = -CUDART_INF_F;
+  const int gate = lane < E ? 0 : (lane < 2 * E ? 1 : 2);
+  const int base = gate == 0 ? 0 : (gate == 1 ? E : 2 * E);
+  const int width = gate == 2 ? 2 : E;
+  const int j = lane - base;
+  const bool active = lane < 2 * E + 2;
+  float logit = 0.f, ex = 1.f, tau_g = tau;
+  if (gate == 0) {
+    float lcv = acc[0];
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-      z[e] = (logit[e] + (-logf(expo[e]))) / tau;
-      m = fmaxf(m, z[e]);
-    }
-    float s = 0.f;
-#pragma unroll
-    for (int e = 0; e < E; ++e) { z[e] = expf(z[e] - m); s += z[e]; }
-    int best = 0;
-    float pb = z[0] / s;
-#pragma unroll
-    for (int e = 1; e < E; ++e) {
-      const float p = z[e] / s;
-      if (p > pb) { pb = p; best = e; }
-    }
-    idx = best;
-    w = (1.f - pb) + pb;
-  };
-  float lc[E];
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    lc[e] = acc[e] + bc[e];
-    if (cap_logits_out) cap_logits_out[(long long)n * E + e] = lc[e];
+    for (int e = 1; e < E; ++e) lcv = (j == e) ? acc[e] : lcv;
+    logit = lcv + bc[j < E ? j : 0];
+    if (cap_logits_out && lane < E) cap_logits_out[(long long)n * E + j] = logit;
+    ex = e1[(long long)n * E + (j < E ? j : 0)];
+  } else if (gate == 1) {
+    logit = ac_logits[(long long)n * ac_ld + j];
+    ex = e2[(long long)n * E + j];
+  } else if (active) {
+    logit = hl_logits[b * hl_ld + j];
+    ex = e0[(long long)n * 2 + j];
+    tau_g = 1.0f;
   }
-  int ic, ia;
-  float wc, wa;
-  hard(lc, e1 + (long long)n * E, ic, wc);
-  hard(ac_logits + (long long)n * ac_ld, e2 + (long long)n * E, ia, wa);
+  const float z = (logit + (-logf(ex))) / tau_g;
+  float zz[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) zz[e] = __shfl_sync(0xffffffffu, z, base + (e < width ? e : 0));
+  float m = zz[0];
+#pragma unroll
+  for (int e = 1; e < E; ++e) if (e < width) m = fmaxf(m, zz[e]);
+  float ssum = 0.f;
+#pragma unroll
+  for (int e = 0; e < E; ++e) if (e < width) { zz[e] = expf(zz[e] - m); ssum += zz[e]; }
+  // (lanes of one gate now hold identical zz[], m, ssum)
+  int best = 0;
+  float pb = zz[0] / ssum;
+#pragma unroll
+  for (int e = 1; e < E; ++e) {
+    if (e < width) {
+      const float pe = zz[e] / ssum;
+      if (pe > pb) { pb = pe; best = e; }
+    }
+  }
+  const float w_hard = (1.f - pb) + pb;
+  // group masks: soft probabilities of the group gate (lane 2E holds p[0] in zz[0]/ssum, etc.)
+  const float mask_c = __shfl_sync(0xffffffffu, zz[0] / ssum, 2 * E);
+  const float mask_a = __shfl_sync(0xffffffffu, zz[1] / ssum, 2 * E);
+  const int ia = __shfl_sync(0xffffffffu, best, E);
+  const float wa = __shfl_sync(0xffffffffu, w_hard, E);
+  if (lane != 0) return;
+  const int ic = best;
+  const float wc = w_hard;
   idx_c[n] = ic;
   idx_a[n] = ia;
   scale_c[n] = wc * mask_c;
