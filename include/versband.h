@@ -166,6 +166,8 @@ long long vb_launch_count(void);
  * on the launching stream; vb_prof_report() synchronises and returns total ms / launch count per
  * kernel family (0 gemm, 1 norm, 2 softmax, 3 attn_small, 4 router, 5 moe_sort, 6 elementwise,
  * 7 layout, 8 groupnorm, 9 conv_post). Not usable during CUDA-graph capture. */
+/* haloed small-C conv path inside vb_gemm (C_in <= 64, N <= 64, bf16): 0 off, 1 on */
+int vb_set_conv_halo(int mode);
 /* 2-CTA (tcgen05 cta_group::2, cluster of 2) GEMM path: 0 off, 1 heuristic, 2 whenever legal */
 int vb_set_gemm2(int mode);
 /* debug: writes %globaltimer (ns) to *slot when the stream reaches this point */

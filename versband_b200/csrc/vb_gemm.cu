@@ -47,6 +47,7 @@ struct GemmKParams {
   long long outb_ld, outb_g1, outb_g2;
   int act_out;
   float act_out_slope, out_scale;
+  int dbg_shift;  // experiment: A tile loaded `dbg_shift` rows early, UMMA descriptor shifted back
   int vec_f32, vec_bf16, vec_aux;  // alignment allows 16-byte accesses (outputs / bias+gate)
   // qkv-rope
   const float* rope_cs;
@@ -374,7 +375,7 @@ vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int tap = kb / p.kpt;
           constexpr int kBkElems = TF32 ? 32 : 64;
           const int c0 = (kb - tap * p.kpt) * kBkElems;
-          const int c1 = m0 + tap * p.dil - p.pad;
+          const int c1 = m0 + tap * p.dil - p.pad - (p.dbg_shift & 0xffff);
           tma_load_4d(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], c0, c1, a_c2, a_c3);
           tma_load_3d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBkElems, n0, b_c2);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -398,7 +399,9 @@ vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + stage * Cfg::kABytes));
+          const int dsh = p.dbg_shift & 0xffff;
+          const uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + stage * Cfg::kABytes) + dsh * 128) |
+                              ((p.dbg_shift >> 16) ? 0ull : (static_cast<uint64_t>(dsh & 7) << 49));  // base_offset
           const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -641,6 +644,140 @@ vb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------ haloed small-C conv kernel
+// Conv1d with C_in <= 64 (one 128-byte k-block per tap) and N <= 64 output channels — the two last
+// HiFi-GAN stages. The per-tap implicit-GEMM kernel above re-fetches the same activation rows once
+// per tap (k = 3..11); here each tile's rows are fetched ONCE as a tall tile of 128 + (taps-1)*dil
+// rows, tap j is the same shared-memory tile seen through a UMMA descriptor shifted by j*dil rows
+// (start address + rows*128 B, base_offset = rows % 8), and all tap weights stay resident in shared
+// memory for the lifetime of the persistent CTA. Operand traffic per output row drops ~taps-fold.
+struct HaloParams {
+  int taps, row_shift, rows, rows8, n_ksteps, stages, base_off;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+vb_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmKParams p, const HaloParams hp) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  constexpr int kWTap = BN * 128;             // bytes of one tap's [BN x 64] weight block
+  const int a_slot = hp.rows8 * 128;          // bytes of one haloed activation tile
+  uint8_t* smem_w = smem;
+  uint8_t* smem_a = smem + ((hp.taps * kWTap + 1023) & ~1023);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_a + hp.stages * a_slot);
+  uint64_t* a_empty = a_full + 8;
+  uint64_t* w_full = a_empty + 8;
+  uint64_t* tmem_full_bar = w_full + 1;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  constexpr int kAcc = BN <= 32 ? 32 : 64;
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < hp.stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    mbar_init(w_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 128); }
+    fence_barrier_init();
+  }
+  if (warp_idx == 1) tmem_alloc<2 * kAcc>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
+
+  if (warp_idx == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(w_full, hp.taps * kWTap);
+      for (int j = 0; j < hp.taps; ++j) tma_load_3d(smem_w + j * kWTap, &tmB, w_full, j * 64, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int g = t / p.m_tiles, m_tile = t - g * p.m_tiles;
+        mbar_wait(&a_empty[stage], phase ^ 1);
+        mbar_expect_tx(&a_full[stage], hp.rows * 128);
+        tma_load_4d(smem_a + stage * a_slot, &tmA, &a_full[stage], 0, m_tile * BM - p.pad, g * p.a_c2_g1, 0);
+        if (++stage == hp.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp_idx == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      mbar_wait(w_full, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int acc = local & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((local >> 1) & 1) ^ 1);
+        mbar_wait(&a_full[stage], phase);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * kAcc;
+        const uint32_t a_base = smem_u32(smem_a + stage * a_slot);
+        for (int j = 0; j < hp.taps; ++j) {
+          const int rs = j * hp.row_shift;
+          uint64_t da = make_kmajor_sw128_desc(a_base + rs * 128);
+          if (hp.base_off) da |= static_cast<uint64_t>(rs & 7) << 49;
+          const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_w + j * kWTap));
+          for (int k = 0; k < hp.n_ksteps; ++k)
+            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (j > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&a_empty[stage]);
+        umma_commit(&tmem_full_bar[acc]);
+        if (++stage == hp.stages) { stage = 0; phase ^= 1; }
+        ++local;
+      }
+    }
+  } else {
+    const int q = warp_idx & 3;
+    const int r = q * 32 + lane;
+    int local = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      const int g = t / p.m_tiles, m_tile = t - g * p.m_tiles;
+      const int g1 = g % p.G1, g2 = g / p.G1;
+      const int acc = local & 1;
+      const int m = m_tile * BM + r;
+      const bool row_ok = m < p.M;
+      long long orow = 0;
+      bool store_ok = row_ok;
+      if (row_ok) {
+        if (p.row_map) orow = p.row_map[m];
+        else orow = (long long)m * p.row_mul + p.row_off + (long long)g1 * p.row_off_g1;
+        store_ok = (orow >= 0 && orow < p.rows_out);
+      }
+      mbar_wait(&tmem_full_bar[acc], (local >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * kAcc + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_d + c, raw);
+        tmem_ld_wait();
+        if (store_ok && c < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          epilogue_generic(p, v, m, c, g1, g2, 0, orow);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+      ++local;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc<2 * kAcc>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 static int encode_map(CUtensorMap* map, const void* base, int rank, const int64_t* dims,
                       const int64_t* strides, const uint32_t* box, bool tf32) {
@@ -714,9 +851,21 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKPa
   return check_launch("vb_gemm2");
 }
 
+static int g_dbg_shift = 0;
+static int g_conv_halo = 0;  // 0 off, 1 on (base_offset descriptors), 2 on (plain shifted start address)
 static int g_gemm2_mode = 1;  // 0 = off, 1 = cost model, 2 = whenever legal
 
 }  // namespace vb
+
+extern "C" int vb_set_conv_halo(int mode) {
+  vb::g_conv_halo = mode;
+  return VB_OK;
+}
+
+extern "C" int vb_set_debug_shift(int rows) {
+  vb::g_dbg_shift = rows;
+  return VB_OK;
+}
 
 extern "C" int vb_set_gemm2(int mode) {
   vb::g_gemm2_mode = mode;
@@ -804,6 +953,7 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
 
   GemmKParams p{};
   p.M = a->M; p.N = a->N; p.K = a->K; p.G1 = a->G1;
+  p.dbg_shift = g_dbg_shift;
   p.num_kb = num_kb; p.kpt = kpt; p.dil = a->dil; p.pad = a->pad;
   p.a_c2_g1 = a->a_c2_g1; p.a_c2_g2 = a->a_c2_g2; p.a_c3_g1 = a->a_c3_g1; p.a_c3_g2 = a->a_c3_g2;
   p.b_c2_g1 = a->b_c2_g1; p.b_c2_g2 = a->b_c2_g2; p.b_c2_tile = a->b_c2_tile;
@@ -854,6 +1004,49 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
+  }
+  // haloed small-C conv path (see vb_conv_halo_kernel)
+  if (g_conv_halo > 0 && !tf32 && !use2 && !a->tile_group && a->mode == VB_EPI_GENERIC && kpt == 1 && num_kb >= 2 &&
+      num_kb <= 16 && a->N <= 64 && a->a_dims[0] <= 64 && a->dil >= 1 && !a->swiglu && a->G2 == 1 &&
+      a->a_c2_g2 == 0 && a->a_c3_g1 == 0 && a->a_c3_g2 == 0 && a->b_c2_g1 == 0 && a->b_c2_g2 == 0 && m_tiles >= 64) {
+    HaloParams hp{};
+    hp.taps = num_kb;
+    hp.row_shift = a->dil;
+    hp.rows = BM + (num_kb - 1) * a->dil;
+    hp.rows8 = (hp.rows + 7) / 8 * 8;
+    hp.n_ksteps = (int)((a->a_dims[0] + 15) / 16);
+    hp.base_off = g_conv_halo == 1;
+    const int hbn = a->N <= 32 ? 32 : 64;
+    const int w_bytes = ((hp.taps * hbn * 128 + 1023) / 1024) * 1024;
+    if (hp.rows <= 256) {
+      int stages = (200 * 1024 - w_bytes) / (hp.rows8 * 128);
+      if (stages > 6) stages = 6;
+      if (stages >= 2) {
+        hp.stages = stages;
+        CUtensorMap tmA2, tmB2;
+        uint32_t boxa[4] = {64, static_cast<uint32_t>(hp.rows), 1, 1};
+        int rc = encode_map(&tmA2, a->a, 4, a->a_dims, a->a_strides, boxa, false);
+        if (rc) return rc;
+        uint32_t boxb2[3] = {64, static_cast<uint32_t>(hbn), 1};
+        rc = encode_map(&tmB2, a->b, 3, a->b_dims, a->b_strides, boxb2, false);
+        if (rc) return rc;
+        GemmKParams ph = p;
+        ph.n_tiles = 1;
+        ph.num_tiles = m_tiles * G;
+        const int smem_bytes = w_bytes + stages * hp.rows8 * 128 + 1024 + 512;
+        const int grid_h = ph.num_tiles < num_sms ? ph.num_tiles : num_sms;
+        cudaError_t e;
+        if (hbn == 32) {
+          e = cudaFuncSetAttribute(vb_conv_halo_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+          if (e == cudaSuccess) e = launch_k(vb_conv_halo_kernel<32>, dim3(grid_h), dim3(kThreads), smem_bytes, stream, tmA2, tmB2, ph, hp);
+        } else {
+          e = cudaFuncSetAttribute(vb_conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+          if (e == cudaSuccess) e = launch_k(vb_conv_halo_kernel<64>, dim3(grid_h), dim3(kThreads), smem_bytes, stream, tmA2, tmB2, ph, hp);
+        }
+        if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "vb_gemm (conv halo) launch failed: %s", cudaGetErrorString(e));
+        return check_launch("vb_conv_halo");
+      }
+    }
   }
   if (use2) {
     const long long pairs = (long long)((m_tiles + 1) / 2) * p.n_tiles * G;
