@@ -649,13 +649,14 @@ vb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // HiFi-GAN stages. The per-tap implicit-GEMM kernel above re-fetches the same activation rows once
 // per tap (k = 3..11); here each tile's rows are fetched ONCE as a tall tile of 128 + (taps-1)*dil
 // rows, tap j is the same shared-memory tile seen through a UMMA descriptor shifted by j*dil rows
-// (start address + rows*128 B, base_offset = rows % 8), and all tap weights stay resident in shared
+// (start address + rows*128 B; base_offset stays 0 because the 128B swizzle is a pure function of the
+// shared-memory address — verified by tools/exp_rowshift.py), and all tap weights stay resident in shared
 // memory for the lifetime of the persistent CTA. Operand traffic per output row drops ~taps-fold.
 struct HaloParams {
   int taps, row_shift, rows, rows8, n_ksteps, stages, base_off;
 };
 
-template <int BN>
+template <int BN, int KSTEPS>
 __global__ void __launch_bounds__(kThreads, 1)
 vb_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmKParams p, const HaloParams hp) {
@@ -709,6 +710,7 @@ vb_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
       mbar_wait(w_full, 0);
+      const uint64_t w_desc0 = make_kmajor_sw128_desc(smem_u32(smem_w));
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -718,14 +720,21 @@ vb_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(&a_full[stage], phase);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kAcc;
-        const uint32_t a_base = smem_u32(smem_a + stage * a_slot);
-        for (int j = 0; j < hp.taps; ++j) {
-          const int rs = j * hp.row_shift;
-          uint64_t da = make_kmajor_sw128_desc(a_base + rs * 128);
-          if (hp.base_off) da |= static_cast<uint64_t>(rs & 7) << 49;
-          const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_w + j * kWTap));
-          for (int k = 0; k < hp.n_ksteps; ++k)
-            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (j > 0 || k > 0) ? 1u : 0u);
+        // The single issuing thread is the bottleneck for these skinny (128 x BN x 16) MMAs: keep the
+        // per-MMA instruction count minimal — descriptors advance by plain adds (16-byte units).
+        uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + stage * a_slot));
+        uint64_t db = w_desc0;
+        const uint64_t da_step = static_cast<uint64_t>(hp.row_shift * 8);  // row_shift rows * 128 B / 16
+        constexpr uint64_t db_step = kWTap / 16;
+        umma_bf16(tmem_d, da, db, idesc, 0u);
+#pragma unroll
+        for (int k = 1; k < KSTEPS; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, 1u);
+#pragma unroll 1
+        for (int j = 1; j < hp.taps; ++j) {
+          da += da_step;
+          db += db_step;
+#pragma unroll
+          for (int k = 0; k < KSTEPS; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, 1u);
         }
         umma_commit(&a_empty[stage]);
         umma_commit(&tmem_full_bar[acc]);
@@ -852,7 +861,7 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKPa
 }
 
 static int g_dbg_shift = 0;
-static int g_conv_halo = 0;  // 0 off, 1 on (base_offset descriptors), 2 on (plain shifted start address)
+static int g_conv_halo = 1;  // 0 off, 1 on
 static int g_gemm2_mode = 1;  // 0 = off, 1 = cost model, 2 = whenever legal
 
 }  // namespace vb
@@ -1015,7 +1024,7 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
     hp.rows = BM + (num_kb - 1) * a->dil;
     hp.rows8 = (hp.rows + 7) / 8 * 8;
     hp.n_ksteps = (int)((a->a_dims[0] + 15) / 16);
-    hp.base_off = g_conv_halo == 1;
+    hp.base_off = g_conv_halo == 3;  // (experiment: base_offset must stay 0 — the 128B swizzle is a pure function of the smem address)
     const int hbn = a->N <= 32 ? 32 : 64;
     const int w_bytes = ((hp.taps * hbn * 128 + 1023) / 1024) * 1024;
     if (hp.rows <= 256) {
@@ -1036,13 +1045,14 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
         const int smem_bytes = w_bytes + stages * hp.rows8 * 128 + 1024 + 512;
         const int grid_h = ph.num_tiles < num_sms ? ph.num_tiles : num_sms;
         cudaError_t e;
-        if (hbn == 32) {
-          e = cudaFuncSetAttribute(vb_conv_halo_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-          if (e == cudaSuccess) e = launch_k(vb_conv_halo_kernel<32>, dim3(grid_h), dim3(kThreads), smem_bytes, stream, tmA2, tmB2, ph, hp);
-        } else {
-          e = cudaFuncSetAttribute(vb_conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-          if (e == cudaSuccess) e = launch_k(vb_conv_halo_kernel<64>, dim3(grid_h), dim3(kThreads), smem_bytes, stream, tmA2, tmB2, ph, hp);
-        }
+        auto go = [&](auto kern) {
+          cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+          if (err == cudaSuccess) err = launch_k(kern, dim3(grid_h), dim3(kThreads), smem_bytes, stream, tmA2, tmB2, ph, hp);
+          return err;
+        };
+        const bool k2 = hp.n_ksteps <= 2;
+        if (hbn == 32) e = k2 ? go(vb_conv_halo_kernel<32, 2>) : go(vb_conv_halo_kernel<32, 4>);
+        else e = k2 ? go(vb_conv_halo_kernel<64, 2>) : go(vb_conv_halo_kernel<64, 4>);
         if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "vb_gemm (conv halo) launch failed: %s", cudaGetErrorString(e));
         return check_launch("vb_conv_halo");
       }
