@@ -170,6 +170,14 @@ long long vb_launch_count(void);
 int vb_set_conv_halo(int mode);
 /* 2-CTA (tcgen05 cta_group::2, cluster of 2) GEMM path: 0 off, 1 heuristic, 2 whenever legal */
 int vb_set_gemm2(int mode);
+/* tuning hook: force tile width `bn` (and the 2-CTA path if cta2) for every vb_gemm with this
+ * (N, K, grouped) signature; N <= 0 clears the table. Used by tools/tune_insitu.py only. */
+int vb_set_gemm_override(int N, int K, int grouped, int bn, int cta2);
+/* debug: the next `max_calls` vb_gemm launches (1-CTA kernel) each write a record of 256 CTAs x 8
+ * uint64 %globaltimer stamps (entry, prologue done, first operands landed, first tile's MMAs
+ * issued, its accumulator ready, its epilogue done, kernel exit) into consecutive 16 KB records of
+ * this device buffer; NULL disables. See tools/trace_gemm.py */
+int vb_set_gemm_trace(void* device_buf, int max_calls);
 /* debug: writes %globaltimer (ns) to *slot when the stream reaches this point */
 int vb_timestamp(uint64_t* slot, void* stream);
 /* programmatic dependent launch between this library's kernels (default on) */

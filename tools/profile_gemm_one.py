@@ -24,6 +24,13 @@ elif which == "vae":
     out = torch.empty(1, T, C, device="cuda")
     fn = lambda: ops.gemm(x, w, M=T, G1=1, kpt=C // 64, dil=1, pad=1, a_c2=(1, 0), out_f32=out, out_ld=C,
                           out_g=(T * C, 0))
+elif which == "mq":  # the DiT mq projection in tf32 mode: bias, fp32 operand-slot output
+    M, N, K = 1500, 768, 768
+    a = torch.randn(M, K, device="cuda")
+    b = torch.randn(N, K, device="cuda")
+    bias = torch.randn(N, device="cuda")
+    o = torch.empty(M, N, device="cuda")
+    fn = lambda: ops.gemm(a, b, bias=bias, out_bf16=o, outb_ld=N)
 else:
     M, N, K = 1500, 2304 if "qkv" in which else 768, 768
     dt = torch.float32 if "tf32" in which else torch.bfloat16

@@ -1,0 +1,918 @@
+// Device code of vb_gemm: tcgen05 / TMEM / TMA GEMM kernels for sm_100a with implicit-conv A
+// addressing and fused epilogues, templated on the epilogue class (vb_gemm_params.h). Included by the
+// vb_gemm_ec*.cu instantiation units only. See include/versband.h for the contract.
+//
+// CTA = 320 threads: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2..9 = epilogue (TMEM lane quadrant = warp_idx % 4). Persistent: one CTA per SM walks the
+// tile list; two TMEM accumulators let the epilogue of tile i overlap the mainloop of tile i+1.
+#pragma once
+#include <math.h>
+#include "vb_gemm_params.h"
+#include "vb_ptx.cuh"
+
+namespace vb {
+
+
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define VB_TRACE(slot) do { if (p.trace) p.trace[blockIdx.x * 8 + (slot)] = gtime_ns(); } while (0)
+
+// Activations are applied by whole-chunk loops selected ONCE per chunk (one uniform branch, then a
+// straight-line 32-wide loop): keeps the executed instruction stream short — the epilogue runs per
+// tile on four warps and was instruction-fetch bound when the switch sat inside the unrolled loop.
+template <int ACT>
+__device__ __forceinline__ float act_one(float v, float slope) {
+  if (ACT == VB_ACT_SILU) return v / (1.f + __expf(-v));
+  if (ACT == VB_ACT_LRELU) return v > 0.f ? v : v * slope;
+  if (ACT == VB_ACT_GELU_ERF) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+  if (ACT == VB_ACT_TANH) return tanhf(v);
+  return v;
+}
+template <int ACT, int N>
+__device__ __forceinline__ void act_loop(float (&v)[N], float slope, float pre) {
+#pragma unroll
+  for (int j = 0; j < N; ++j) v[j] = act_one<ACT>(v[j] * pre, slope);
+}
+template <int N>
+__device__ __forceinline__ void apply_act_all(float (&v)[N], int act, float slope, float pre = 1.f) {
+  switch (act) {
+    case VB_ACT_SILU: act_loop<VB_ACT_SILU>(v, slope, pre); break;
+    case VB_ACT_LRELU: act_loop<VB_ACT_LRELU>(v, slope, pre); break;
+    case VB_ACT_GELU_ERF: act_loop<VB_ACT_GELU_ERF>(v, slope, pre); break;
+    case VB_ACT_TANH: act_loop<VB_ACT_TANH>(v, slope, pre); break;
+    default:
+      if (pre != 1.f) act_loop<VB_ACT_NONE>(v, slope, pre);
+      break;
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// ------------------------------------------------------------------ coalesced epilogue
+// tcgen05.ld hands each thread one accumulator ROW (32 consecutive columns). Storing straight from
+// that layout makes every warp-level 16-byte access touch 32 different cache lines (32 L1
+// wavefronts per instruction): tools/trace_gemm.py measured ~2 us per 32-column chunk, more than the
+// whole mainloop of the DiT linears. Each epilogue warp therefore transposes its 32x32 chunk
+// through a private, XOR-swizzled 4 KB smem block: afterwards 8 lanes cover 128 contiguous bytes
+// of one row, one warp instruction touches 4 rows x 128 B, and every load of the fused operands
+// (bias, gate, residual, rope table) and every store is coalesced.
+//   lane -> (lr = lane >> 3, cq = lane & 7); item i in 0..7 = row 4i + lr of the warp's 32 rows,
+//   columns 4cq .. 4cq+3 of the chunk; v[4i + k] is component k of item i.
+
+struct EpiRows {
+  int orow[8];  // generic: output row, QKV: b*H*T + t; -1 = row not stored
+  int aux[8];   // generic: gate batch index (m / gate_rows), QKV: t
+  float rs[8];  // row_scale
+};
+
+template <int EC>
+__device__ __forceinline__ void epi_prepare_rows(const GemmKParams& p, EpiRows& rows, int m_base, int g1, int lane) {
+  const int lr = lane >> 3;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m_base + 4 * i + lr;
+    const bool ok = m < p.M;
+    int o = -1, a = 0;
+    float rs = 1.f;
+    if (ok) {
+      if (EC == EC_QKV) {
+        const int b = m / p.T;
+        a = m - b * p.T;
+        o = b * p.heads * p.T + a;
+      } else {
+        o = p.row_map ? p.row_map[m] : m * p.row_mul + p.row_off + g1 * p.row_off_g1;
+        if (o < 0 || o >= p.rows_out) o = -1;
+        if (EC != EC_SWIGLU && p.gate) a = m / p.gate_rows;
+        if (p.row_scale) rs = p.row_scale[m];
+      }
+    }
+    rows.orow[i] = o;
+    rows.aux[i] = a;
+    rows.rs[i] = rs;
+  }
+}
+
+// thread `lane` owns accumulator row `lane` of the warp: write it, read back the item layout
+__device__ __forceinline__ void epi_transpose(const uint32_t (&raw)[32], float* stg, int lane, float (&v)[32]) {
+  __syncwarp();  // previous chunk's reads are done
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+        make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+  __syncwarp();
+  const int lr = lane >> 3, cq = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = 4 * i + lr;
+    const float4 x = *reinterpret_cast<const float4*>(stg + row * 32 + ((cq ^ (row & 7)) << 2));
+    v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+  }
+}
+
+__device__ __forceinline__ float4 ld4(const float* __restrict__ src, bool vec, int n_left) {
+  if (vec) return __ldg(reinterpret_cast<const float4*>(src));
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n_left > 0) r.x = src[0];
+  if (n_left > 1) r.y = src[1];
+  if (n_left > 2) r.z = src[2];
+  if (n_left > 3) r.w = src[3];
+  return r;
+}
+__device__ __forceinline__ void st4(float* __restrict__ dst, const float* v, bool vec, int n_left) {
+  if (vec) { *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]); return; }
+  if (n_left > 0) dst[0] = v[0];
+  if (n_left > 1) dst[1] = v[1];
+  if (n_left > 2) dst[2] = v[2];
+  if (n_left > 3) dst[3] = v[3];
+}
+
+// Global operands of one chunk's epilogue, requested ahead of use (together with the chunk's TMEM
+// load): all loads are unconditional (rows that are not stored read a clamped valid row) so that
+// they are in flight together — the epilogue is bound by round trips to L2, not by bytes.
+struct EpiOperands {
+  float4 res[8];      // generic: residual (or the accumulate target) per item; QKV: rope (cos,sin) x2 per item
+  float4 bias;        // per column quad
+  float4 g_lo, g_hi;  // gate rows of the (at most two) batches this lane's rows fall in
+};
+
+template <int EC>
+__device__ __forceinline__ void epi_load_operands(const GemmKParams& p, const EpiRows& rows, EpiOperands& op,
+                                                  int n_base, int g1, int g2, int tg, int lane) {
+  const int cq = lane & 7;
+  const int n = n_base + 4 * cq;
+  if (EC == EC_QKV) {
+    const int hd = p.head_dim;
+    const int D = p.heads * hd;
+    const int sec = n_base / D + p.qkv_sec0;
+    if (sec == 2) return;
+    op.bias = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.rope_cs) {
+      const int d = (n_base % hd) + 4 * cq;  // dim inside the head (chunks never straddle heads)
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        op.res[i] = __ldg(reinterpret_cast<const float4*>(p.rope_cs + ((long long)rows.aux[i] * (hd >> 1) + (d >> 1)) * 2));
+    }
+    return;
+  }
+  if (EC == EC_SWIGLU || (EC == EC_FULL && p.swiglu)) return;
+  const int n_left = p.N - n;
+  const bool full = n_left >= 4;
+  if (p.bias) op.bias = ld4(p.bias + g1 * p.bias_g1 + tg * p.bias_tile + n, full && p.vec_aux, n_left);
+  if (p.gate) {
+    const float* gsrc = p.gate + g1 * p.gate_g1 + n;
+    op.g_lo = ld4(gsrc + (long long)rows.aux[0] * p.gate_ld, full && p.vec_aux, n_left);
+    op.g_hi = ld4(gsrc + (long long)rows.aux[7] * p.gate_ld, full && p.vec_aux, n_left);
+  }
+  const float* rsrc = p.residual ? p.residual : ((p.accumulate && p.out_f32) ? p.out_f32 : nullptr);
+  if (rsrc) {
+    rsrc += g1 * p.out_g1 + g2 * p.out_g2 + n;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int o = rows.orow[i] < 0 ? 0 : rows.orow[i];
+      op.res[i] = ld4(rsrc + (long long)o * p.out_ld, full && p.vec_f32, n_left);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ generic epilogue (one 32-column chunk)
+template <int EC>
+__device__ __forceinline__ void epilogue_generic(const GemmKParams& p, float (&v)[32], const EpiRows& rows,
+                                                 const EpiOperands& op, int n_base, int g1, int g2, int tg, int lane) {
+  const int N = p.N;
+  const int cq = lane & 7;
+  const int n = n_base + 4 * cq;  // first of this lane's 4 columns
+  const int n_left = N - n;       // columns of the quad that exist
+  if (EC == EC_FULL && p.alpha != 1.f) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+  }
+
+  if (EC == EC_SWIGLU || (EC == EC_FULL && p.swiglu)) {
+    // columns (2i, 2i+1) = (w1 x, w3 x)  ->  silu(w1 x) * (w3 x): two outputs per quad
+    const int no = n >> 1;
+    const int no_left = (N >> 1) - no;
+    const long long gofs = g1 * p.outb_g1 + g2 * p.outb_g2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float a0 = v[4 * i], b0 = v[4 * i + 1], a1 = v[4 * i + 2], b1 = v[4 * i + 3];
+      const float o0 = (a0 / (1.f + __expf(-a0))) * b0 * rows.rs[i];
+      const float o1 = (a1 / (1.f + __expf(-a1))) * b1 * rows.rs[i];
+      if (rows.orow[i] < 0 || no_left <= 0) continue;
+      const bool two = no_left > 1;
+      if (p.out_bf16 && p.outb_f32) {
+        float* dst = reinterpret_cast<float*>(p.out_bf16) + gofs + (long long)rows.orow[i] * p.outb_ld + no;
+        if (two && p.vec_bf16) *reinterpret_cast<float2*>(dst) = make_float2(o0, o1);
+        else { dst[0] = o0; if (two) dst[1] = o1; }
+      } else if (p.out_bf16) {
+        __nv_bfloat16* dst = p.out_bf16 + gofs + (long long)rows.orow[i] * p.outb_ld + no;
+        if (two && p.vec_bf16) *reinterpret_cast<uint32_t*>(dst) = pack_bf16(o0, o1);
+        else { dst[0] = __float2bfloat16(o0); if (two) dst[1] = __float2bfloat16(o1); }
+      }
+      if (EC == EC_FULL && p.out_f32) {
+        float* dst = p.out_f32 + g1 * p.out_g1 + g2 * p.out_g2 + (long long)rows.orow[i] * p.out_ld + no;
+        dst[0] = o0;
+        if (two) dst[1] = o1;
+      }
+    }
+    return;
+  }
+  if (EC == EC_SWIGLU) return;
+
+  const bool full = n_left >= 4;
+  if (p.bias) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[4 * i] += op.bias.x; v[4 * i + 1] += op.bias.y; v[4 * i + 2] += op.bias.z; v[4 * i + 3] += op.bias.w; }
+  }
+  if (EC == EC_FULL) {
+    if (p.act != VB_ACT_NONE) apply_act_all(v, p.act, p.act_slope);
+  } else if (p.act == VB_ACT_LRELU) {
+    act_loop<VB_ACT_LRELU>(v, p.act_slope, 1.f);
+  }
+  if (p.row_scale) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[4 * i] *= rows.rs[i]; v[4 * i + 1] *= rows.rs[i]; v[4 * i + 2] *= rows.rs[i]; v[4 * i + 3] *= rows.rs[i]; }
+  }
+  if (p.gate) {
+    if (rows.aux[7] - rows.aux[0] <= 1) {  // the lane's 8 rows fall in at most two batches
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 g4 = rows.aux[i] == rows.aux[0] ? op.g_lo : op.g_hi;
+        v[4 * i] *= g4.x; v[4 * i + 1] *= g4.y; v[4 * i + 2] *= g4.z; v[4 * i + 3] *= g4.w;
+      }
+    } else {
+      const float* gsrc = p.gate + g1 * p.gate_g1 + n;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 g4 = ld4(gsrc + (long long)rows.aux[i] * p.gate_ld, full && p.vec_aux, n_left);
+        v[4 * i] *= g4.x; v[4 * i + 1] *= g4.y; v[4 * i + 2] *= g4.z; v[4 * i + 3] *= g4.w;
+      }
+    }
+  }
+  const long long gofs32 = g1 * p.out_g1 + g2 * p.out_g2 + n;
+  if (p.residual || (p.accumulate && p.out_f32)) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[4 * i] += op.res[i].x; v[4 * i + 1] += op.res[i].y; v[4 * i + 2] += op.res[i].z; v[4 * i + 3] += op.res[i].w; }
+    if (p.residual && p.accumulate && p.out_f32) {  // both: the accumulate target is read here
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int o = rows.orow[i] < 0 ? 0 : rows.orow[i];
+        const float4 r4 = ld4(p.out_f32 + gofs32 + (long long)o * p.out_ld, full && p.vec_f32, n_left);
+        v[4 * i] += r4.x; v[4 * i + 1] += r4.y; v[4 * i + 2] += r4.z; v[4 * i + 3] += r4.w;
+      }
+    }
+  }
+  if (p.out_f32) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (rows.orow[i] >= 0) st4(p.out_f32 + gofs32 + (long long)rows.orow[i] * p.out_ld, &v[4 * i], full && p.vec_f32, n_left);
+  }
+  if (p.out_bf16) {
+    const long long gofsb = g1 * p.outb_g1 + g2 * p.outb_g2 + n;
+    if (EC == EC_FULL) {
+      apply_act_all(v, p.act_out, p.act_out_slope, p.out_scale);
+    } else if (p.act_out == VB_ACT_LRELU) {
+      act_loop<VB_ACT_LRELU>(v, p.act_out_slope, p.out_scale);
+    } else if (p.out_scale != 1.f) {
+      act_loop<VB_ACT_NONE>(v, 0.f, p.out_scale);
+    }
+    if (p.outb_f32) {
+      float* base = reinterpret_cast<float*>(p.out_bf16) + gofsb;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (rows.orow[i] >= 0) st4(base + (long long)rows.orow[i] * p.outb_ld, &v[4 * i], full && p.vec_bf16, n_left);
+      return;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (rows.orow[i] < 0) continue;
+      __nv_bfloat16* dst = p.out_bf16 + gofsb + (long long)rows.orow[i] * p.outb_ld;
+      if (full && p.vec_bf16) {
+        *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(v[4 * i], v[4 * i + 1]), pack_bf16(v[4 * i + 2], v[4 * i + 3]));
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < n_left) dst[k] = __float2bfloat16(v[4 * i + k]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ QKV + RoPE epilogue
+// Row m = b*T + t, column n in [0, 3*H*hd): section = n / (H*hd) (q,k,v), head, dim.
+// Rotary: pairs (2i, 2i+1) rotated by angle(t, i) — flag_large_dit_moe.py:263-269.
+// A 32-column chunk never straddles a head or section because head_dim % 32 == 0.
+// q / k go through the transposed (coalesced) layout; V^T[b][h][d][t] is written straight from the
+// TMEM layout (lanes = consecutive t -> coalesced 2-byte stores).
+__device__ __forceinline__ void epilogue_qkv(const GemmKParams& p, const uint32_t (&raw)[32], float* stg,
+                                             const EpiRows& rows, const EpiOperands& op, int m_base, int n_base,
+                                             int lane) {
+  const int hd = p.head_dim, H = p.heads, T = p.T;
+  const int D = H * hd;
+  const int sec0 = n_base / D;
+  const int rem = n_base - sec0 * D;
+  const int sec = sec0 + p.qkv_sec0;
+  const int h = rem / hd;
+  const int d0 = rem - h * hd;
+  if (sec == 2) {
+    const int m = m_base + lane;
+    if (m >= p.M) return;
+    const int b = m / T;
+    const int t = m - b * T;
+    __nv_bfloat16* dst = p.vt_out + (((long long)b * H + h) * hd + d0) * p.Tp + t;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = __uint_as_float(raw[j]) * p.alpha;
+      if (p.bias) x += __ldg(p.bias + n_base + j);
+      dst[(long long)j * p.Tp] = __float2bfloat16(x);
+    }
+    return;
+  }
+  float v[32];
+  epi_transpose(raw, stg, lane, v);
+  const int cq = lane & 7;
+  __nv_bfloat16* out = (sec == 0 ? p.q_out : p.k_out) + d0 + 4 * cq;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float x0 = v[4 * i] * p.alpha + op.bias.x, x1 = v[4 * i + 1] * p.alpha + op.bias.y;
+    float x2 = v[4 * i + 2] * p.alpha + op.bias.z, x3 = v[4 * i + 3] * p.alpha + op.bias.w;
+    if (p.rope_cs) {
+      const float4 cs = op.res[i];
+      const float y0 = x0 * cs.x - x1 * cs.y, y1 = x0 * cs.y + x1 * cs.x;
+      const float y2 = x2 * cs.z - x3 * cs.w, y3 = x2 * cs.w + x3 * cs.z;
+      x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+    }
+    if (rows.orow[i] >= 0)
+      *reinterpret_cast<uint2*>(out + ((long long)rows.orow[i] + (long long)h * T) * hd) =
+          make_uint2(pack_bf16(x0, x1), pack_bf16(x2, x3));
+  }
+}
+
+// One 32-column chunk of one warp's 32 rows: TMEM registers -> fused epilogue -> global.
+template <int EC>
+__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint32_t (&raw)[32], float* stg,
+                                               const EpiRows& rows, const EpiOperands& op, int m_base, int n_base,
+                                               int g1, int g2, int tg, int lane) {
+  if (EC == EC_QKV) {
+    epilogue_qkv(p, raw, stg, rows, op, m_base, n_base, lane);
+  } else {
+    float v[32];
+    epi_transpose(raw, stg, lane, v);
+    epilogue_generic<EC>(p, v, rows, op, n_base, g1, g2, tg, lane);
+  }
+}
+
+// The chunk loop shared by the three kernels. Eight epilogue warps: two per TMEM lane quadrant, the
+// pair splitting the tile's 32-column chunks even/odd (`c_first` = 0 or 32) — a single warp per
+// scheduler runs the ~400-instruction chunk body latency-bound, so warps, not bytes, set the pace.
+// A chunk's global operands are requested together with its TMEM load, before either is consumed.
+#define VB_EPILOGUE_TILE(BN_, N0, G1_, G2_, TG_, WAIT_STMT)                                              \
+  {                                                                                                      \
+    EpiRows rows;                                                                                        \
+    epi_prepare_rows<EC>(p, rows, m_base, (G1_), lane);                                                  \
+    WAIT_STMT;                                                                                           \
+    tc_fence_after();                                                                                    \
+    _Pragma("unroll 1") for (int c = c_first; c < (BN_); c += kEpiColStep) {                             \
+      const int n_base = (N0) + c;                                                                       \
+      if (n_base >= p.N) break;                                                                          \
+      uint32_t raw[32];                                                                                  \
+      tmem_ld32(tmem_d + c, raw);                                                                        \
+      EpiOperands op;                                                                                    \
+      epi_load_operands<EC>(p, rows, op, n_base, (G1_), (G2_), (TG_), lane);                             \
+      tmem_ld_wait();                                                                                    \
+      epilogue_chunk<EC>(p, raw, stg, rows, op, m_base, n_base, (G1_), (G2_), (TG_), lane);              \
+    }                                                                                                    \
+  }
+
+// ------------------------------------------------------------------ kernel
+// Persistent: one CTA per SM walks the tile list (m fastest). The smem ring is as deep as
+// shared memory allows (6-10 stages) so a latency-bound small GEMM has all of its k-blocks in
+// flight, and two TMEM accumulators let the epilogue of tile i overlap the mainloop of tile i+1.
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStages = kPipeBytes / (kABytes + kBBytes) > 12 ? 12 : kPipeBytes / (kABytes + kBBytes);
+  static constexpr int kAccStride = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  static constexpr int kTmemCols = 2 * kAccStride;
+  static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + 1024 /*align*/ + 1024 /*barriers*/ + kEpiStageBytes;
+  static_assert(BN % 32 == 0 && BN <= 256, "N tile");
+};
+
+struct TileCoord {
+  int m_tile, n_tile, g1, g2, tg;
+  bool skip;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int t, int m_used) {
+  TileCoord c;
+  const int per_g = p.m_tiles * p.n_tiles;
+  const int g = t / per_g;
+  const int r = t - g * per_g;
+  c.n_tile = r / p.m_tiles;
+  c.m_tile = r - c.n_tile * p.m_tiles;
+  c.g1 = g % p.G1;
+  c.g2 = g / p.G1;
+  c.skip = c.m_tile >= m_used;
+  c.tg = (p.tile_group && !c.skip) ? p.tile_group[c.m_tile] : 0;
+  return c;
+}
+
+template <int BN, bool TF32, int EC>
+__global__ void __launch_bounds__(kThreads, 1)
+vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const GemmKParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + kStages * Cfg::kBBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* epi_stage = reinterpret_cast<float*>(smem + kStages * (Cfg::kABytes + Cfg::kBBytes) + 1024);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp_idx == 0 && lane == 0) {
+    VB_TRACE(0);
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], kEpiWarps * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();  // prologue above overlaps the previous kernel; global memory is touched only below
+  if (threadIdx.x == 0) VB_TRACE(1);
+
+  const int num_kb = p.num_kb;
+  const int m_used = p.m_tiles_used ? *p.m_tiles_used : p.m_tiles;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t, m_used);
+        if (tc.skip) continue;
+        const int m0 = tc.m_tile * BM, n0 = tc.n_tile * BN;
+        const int a_c2 = tc.g1 * p.a_c2_g1 + tc.g2 * p.a_c2_g2;
+        const int a_c3 = tc.g1 * p.a_c3_g1 + tc.g2 * p.a_c3_g2;
+        const int b_c2 = tc.g1 * p.b_c2_g1 + tc.g2 * p.b_c2_g2 + tc.tg * p.b_c2_tile;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
+          const int tap = kb / p.kpt;
+          constexpr int kBkElems = TF32 ? 32 : 64;
+          const int c0 = (kb - tap * p.kpt) * kBkElems;
+          const int c1 = m0 + tap * p.dil - p.pad - (p.dbg_shift & 0xffff);
+          tma_load_4d(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], c0, c1, a_c2, a_c3);
+          tma_load_3d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBkElems, n0, b_c2);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = TF32 ? make_idesc_tf32(BM, BN) : make_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t, m_used);
+        if (tc.skip) continue;
+        const int acc = local & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((local >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * Cfg::kAccStride;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (kb == 0 && local == 0) VB_TRACE(2);
+          const int dsh = p.dbg_shift & 0xffff;
+          const uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + stage * Cfg::kABytes) + dsh * 128) |
+                              ((p.dbg_shift >> 16) ? 0ull : (static_cast<uint64_t>(dsh & 7) << 49));  // base_offset
+          const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // advance 32 bytes (16 bf16 or 8 tf32 = one MMA K-step) inside the 128-byte swizzle
+            // row: +2 in 16-byte units
+            if (TF32) umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+        if (local == 0) VB_TRACE(3);
+        ++local;
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int q = warp_idx & 3;  // TMEM lane quadrant this warp may access
+    const int c_first = ((warp_idx - 2) >> 2) * 32;
+    float* stg = epi_stage + (warp_idx - 2) * 1024;
+    int local = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(p, t, m_used);
+      if (tc.skip) continue;
+      const int acc = local & 1;
+      const int m_base = tc.m_tile * BM + q * 32, n0 = tc.n_tile * BN;
+      const uint32_t tmem_d = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+      VB_EPILOGUE_TILE(BN, n0, tc.g1, tc.g2, tc.tg,
+                       mbar_wait(&tmem_full_bar[acc], (local >> 1) & 1); if (local == 0 && threadIdx.x == 64) VB_TRACE(4))
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);  // all epilogue threads release the accumulator to the MMA warp
+      if (local == 0 && threadIdx.x == 64) VB_TRACE(5);
+      ++local;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) VB_TRACE(6);
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------ 2-CTA kernel
+// CTA pairs (cluster of 2 along M) run tcgen05.mma.cta_group::2: UMMA M = 256 (128 rows per CTA),
+// N = BN. Each CTA loads its own A tile and only HALF of the B tile; the tensor core reads both
+// halves across the pair. Per output element the operand bytes an SM has to pull from L2 drop
+// from (1/128 + 1/BN) to (1/128 + 1/(2 BN)) ... with BN = 256: half of the 128x128 kernel.
+// Protocol (leader = cluster rank 0): both CTAs' TMA credit the LEADER's full barrier, the leader
+// issues the MMAs and its commits arrive (multicast) on both CTAs' empty / accumulator-full
+// barriers, both epilogues release the accumulator on the leader's tmem_empty barrier.
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int kABytes = BM * 128;
+  static constexpr int kBBytes = (BN / 2) * 128;
+  static constexpr int kStages = kPipeBytes / (kABytes + kBBytes) > 12 ? 12 : kPipeBytes / (kABytes + kBBytes);
+  static constexpr int kAccStride = BN <= 128 ? 128 : 256;
+  static constexpr int kTmemCols = 2 * kAccStride;
+  static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + 1024 + 1024 + kEpiStageBytes;
+};
+
+template <int BN, bool TF32, int EC>
+__global__ void __launch_bounds__(kThreads, 1)
+vb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const GemmKParams p) {
+  using Cfg = Gemm2Cfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kBkElems = TF32 ? 32 : 64;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + kStages * Cfg::kBBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* epi_stage = reinterpret_cast<float*>(smem + kStages * (Cfg::kABytes + Cfg::kBBytes) + 1024);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 2);   // leader's arrive.expect_tx + the peer producer's arrive
+      mbar_init(&empty_bar[s], 1);  // one multicast commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 2 * kEpiWarps * 32);  // the epilogue threads of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 1) tmem_alloc2<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs initialised, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
+
+  const int num_kb = p.num_kb;
+  const int m_pairs = (p.m_tiles + 1) >> 1;
+  const int per_g = m_pairs * p.n_tiles;
+  const int num_pairs = per_g * (p.num_tiles / (p.m_tiles * p.n_tiles));  // x groups
+  const int n_clusters = gridDim.x >> 1;
+  const int first = blockIdx.x >> 1;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = first; t < num_pairs; t += n_clusters) {
+        const int g = t / per_g, r = t - g * per_g;
+        const int n_tile = r / m_pairs, m_tile = 2 * (r - n_tile * m_pairs) + (int)rank;
+        const int g1 = g % p.G1, g2 = g / p.G1;
+        const int m0 = m_tile * BM, n0 = n_tile * BN + (int)rank * (BN / 2);
+        const int a_c2 = g1 * p.a_c2_g1 + g2 * p.a_c2_g2;
+        const int a_c3 = g1 * p.a_c3_g1 + g2 * p.a_c3_g2;
+        const int b_c2 = g1 * p.b_c2_g1 + g2 * p.b_c2_g2;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t lead_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          const int tap = kb / p.kpt;
+          const int c0 = (kb - tap * p.kpt) * kBkElems;
+          const int c1 = m0 + tap * p.dil - p.pad;
+          tma_load_4d_2sm(smem_a + stage * Cfg::kABytes, &tmA, lead_full, c0, c1, a_c2, a_c3);
+          tma_load_3d_2sm(smem_b + stage * Cfg::kBBytes, &tmB, lead_full, kb * kBkElems, n0, b_c2);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::kABytes + Cfg::kBBytes));
+          else mbar_arrive_cluster(lead_full);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer (leader CTA, single thread) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = TF32 ? make_idesc_tf32(2 * BM, BN) : make_idesc_bf16(2 * BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int t = first; t < num_pairs; t += n_clusters) {
+        const int acc = local & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((local >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * Cfg::kAccStride;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (TF32) umma2_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else umma2_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit2_mc(&empty_bar[stage], 3);  // frees the slot in both CTAs
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit2_mc(&tmem_full_bar[acc], 3);
+        ++local;
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs) =====================
+    const int q = warp_idx & 3;
+    const int c_first = ((warp_idx - 2) >> 2) * 32;
+    float* stg = epi_stage + (warp_idx - 2) * 1024;
+    int local = 0;
+    for (int t = first; t < num_pairs; t += n_clusters) {
+      const int g = t / per_g, rr = t - g * per_g;
+      const int n_tile = rr / m_pairs, m_tile = 2 * (rr - n_tile * m_pairs) + (int)rank;
+      const int g1 = g % p.G1, g2 = g / p.G1;
+      const int acc = local & 1;
+      const int m_base = m_tile * BM + q * 32, n0 = n_tile * BN;
+      const uint32_t tmem_d = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+      VB_EPILOGUE_TILE(BN, n0, g1, g2, 0, mbar_wait(&tmem_full_bar[acc], (local >> 1) & 1))
+      tc_fence_before();
+      if (leader) mbar_arrive(&tmem_empty_bar[acc]);
+      else mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));
+      ++local;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer may still signal my barriers / read my smem until here
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc2<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------ haloed small-C conv kernel
+// Conv1d with C_in <= 64 (one 128-byte k-block per tap) and N <= 64 output channels — the two last
+// HiFi-GAN stages. The per-tap implicit-GEMM kernel above re-fetches the same activation rows once
+// per tap (k = 3..11); here each tile's rows are fetched ONCE as a tall tile of 128 + (taps-1)*dil
+// rows, tap j is the same shared-memory tile seen through a UMMA descriptor shifted by j*dil rows
+// (start address + rows*128 B; base_offset stays 0 because the 128B swizzle is a pure function of the
+// shared-memory address — verified by tools/exp_rowshift.py), and all tap weights stay resident in shared
+// memory for the lifetime of the persistent CTA. Operand traffic per output row drops ~taps-fold.
+
+template <int BN, int KSTEPS, int EC>
+__global__ void __launch_bounds__(kThreads, 1)
+vb_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmKParams p, const HaloParams hp) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  constexpr int kWTap = BN * 128;             // bytes of one tap's [BN x 64] weight block
+  const int a_slot = hp.rows8 * 128;          // bytes of one haloed activation tile
+  uint8_t* smem_w = smem;
+  uint8_t* smem_a = smem + ((hp.taps * kWTap + 1023) & ~1023);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_a + hp.stages * a_slot);
+  uint64_t* a_empty = a_full + 8;
+  uint64_t* w_full = a_empty + 8;
+  uint64_t* tmem_full_bar = w_full + 1;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* epi_stage = reinterpret_cast<float*>(smem_a + hp.stages * a_slot + 1024);
+  constexpr int kAcc = BN <= 32 ? 32 : 64;
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < hp.stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    mbar_init(w_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], kEpiWarps * 32); }
+    fence_barrier_init();
+  }
+  if (warp_idx == 1) tmem_alloc<2 * kAcc>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
+
+  if (warp_idx == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(w_full, hp.taps * kWTap);
+      for (int j = 0; j < hp.taps; ++j) tma_load_3d(smem_w + j * kWTap, &tmB, w_full, j * 64, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int g = t / p.m_tiles, m_tile = t - g * p.m_tiles;
+        mbar_wait(&a_empty[stage], phase ^ 1);
+        mbar_expect_tx(&a_full[stage], hp.rows * 128);
+        tma_load_4d(smem_a + stage * a_slot, &tmA, &a_full[stage], 0, m_tile * BM - p.pad, g * p.a_c2_g1, 0);
+        if (++stage == hp.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp_idx == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      mbar_wait(w_full, 0);
+      const uint64_t w_desc0 = make_kmajor_sw128_desc(smem_u32(smem_w));
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int acc = local & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((local >> 1) & 1) ^ 1);
+        mbar_wait(&a_full[stage], phase);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * kAcc;
+        // The single issuing thread is the bottleneck for these skinny (128 x BN x 16) MMAs: keep the
+        // per-MMA instruction count minimal — descriptors advance by plain adds (16-byte units).
+        uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + stage * a_slot));
+        uint64_t db = w_desc0;
+        const uint64_t da_step = static_cast<uint64_t>(hp.row_shift * 8);  // row_shift rows * 128 B / 16
+        constexpr uint64_t db_step = kWTap / 16;
+        umma_bf16(tmem_d, da, db, idesc, 0u);
+#pragma unroll
+        for (int k = 1; k < KSTEPS; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, 1u);
+#pragma unroll 1
+        for (int j = 1; j < hp.taps; ++j) {
+          da += da_step;
+          db += db_step;
+#pragma unroll
+          for (int k = 0; k < KSTEPS; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, 1u);
+        }
+        umma_commit(&a_empty[stage]);
+        umma_commit(&tmem_full_bar[acc]);
+        if (++stage == hp.stages) { stage = 0; phase ^= 1; }
+        ++local;
+      }
+    }
+  } else {
+    const int q = warp_idx & 3;
+    const int c_first = ((warp_idx - 2) >> 2) * 32;
+    float* stg = epi_stage + (warp_idx - 2) * 1024;
+    int local = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      const int g = t / p.m_tiles, m_tile = t - g * p.m_tiles;
+      const int g1 = g % p.G1, g2 = g / p.G1;
+      const int acc = local & 1;
+      const int m_base = m_tile * BM + q * 32;
+      const uint32_t tmem_d = tmem_base + acc * kAcc + (static_cast<uint32_t>(q * 32) << 16);
+      VB_EPILOGUE_TILE(BN, 0, g1, g2, 0, mbar_wait(&tmem_full_bar[acc], (local >> 1) & 1))
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+      ++local;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc<2 * kAcc>(tmem_base);
+  }
+}
+
+template <int BN, bool TF32, int EC>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p,
+                  dim3 grid, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(vb_gemm_kernel<BN, TF32, EC>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess)
+      return set_error(VB_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes,
+                       cudaGetErrorString(e));
+    attr_set = true;
+  }
+  launch_k(vb_gemm_kernel<BN, TF32, EC>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, tmA, tmB, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return set_error(VB_ERR_CUDA, "vb_gemm launch failed: %s", cudaGetErrorString(e));
+  count_launch();
+  return VB_OK;
+}
+
+template <int BN, bool TF32, int EC>
+static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, int grid,
+                   cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(vb_gemm2_kernel<BN, TF32, EC>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess)
+      return set_error(VB_ERR_CUDA, "cudaFuncSetAttribute(gemm2 smem=%d): %s", Cfg::kSmemBytes,
+                       cudaGetErrorString(e));
+    attr_set = true;
+  }
+  cudaError_t e = launch_k_cluster(vb_gemm2_kernel<BN, TF32, EC>, 2, dim3(grid), dim3(kThreads), Cfg::kSmemBytes,
+                                   stream, tmA, tmB, p);
+  if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "vb_gemm (2-CTA) launch failed: %s", cudaGetErrorString(e));
+  return check_launch("vb_gemm2");
+}
+
+
+template <int EC>
+int launch_gemm_class(int bn, bool tf32, bool use2, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p,
+                      int grid_, cudaStream_t stream) {
+  if (use2) {
+    if (bn == 256) return tf32 ? launch2<256, true, EC>(tmA, tmB, p, grid_, stream) : launch2<256, false, EC>(tmA, tmB, p, grid_, stream);
+    if (bn == 192) return tf32 ? launch2<192, true, EC>(tmA, tmB, p, grid_, stream) : launch2<192, false, EC>(tmA, tmB, p, grid_, stream);
+    return tf32 ? launch2<128, true, EC>(tmA, tmB, p, grid_, stream) : launch2<128, false, EC>(tmA, tmB, p, grid_, stream);
+  }
+  dim3 grid(grid_, 1, 1);
+  switch (bn) {
+    case 32: return tf32 ? launch<32, true, EC>(tmA, tmB, p, grid, stream) : launch<32, false, EC>(tmA, tmB, p, grid, stream);
+    case 64: return tf32 ? launch<64, true, EC>(tmA, tmB, p, grid, stream) : launch<64, false, EC>(tmA, tmB, p, grid, stream);
+    case 96: return tf32 ? launch<96, true, EC>(tmA, tmB, p, grid, stream) : launch<96, false, EC>(tmA, tmB, p, grid, stream);
+    case 128: return tf32 ? launch<128, true, EC>(tmA, tmB, p, grid, stream) : launch<128, false, EC>(tmA, tmB, p, grid, stream);
+    case 192: return tf32 ? launch<192, true, EC>(tmA, tmB, p, grid, stream) : launch<192, false, EC>(tmA, tmB, p, grid, stream);
+    case 256: return tf32 ? launch<256, true, EC>(tmA, tmB, p, grid, stream) : launch<256, false, EC>(tmA, tmB, p, grid, stream);
+    default: return set_error(VB_ERR_INVALID, "vb_gemm: unsupported N tile %d", bn);
+  }
+}
+
+template <int EC>
+int launch_halo_class(int hbn, bool k2, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p,
+                      const HaloParams& hp, int grid, int smem_bytes, cudaStream_t stream) {
+  cudaError_t e;
+  auto go = [&](auto kern) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (err == cudaSuccess) err = launch_k(kern, dim3(grid), dim3(kThreads), smem_bytes, stream, tmA, tmB, p, hp);
+    return err;
+  };
+  if (hbn == 32) e = k2 ? go(vb_conv_halo_kernel<32, 2, EC>) : go(vb_conv_halo_kernel<32, 4, EC>);
+  else e = k2 ? go(vb_conv_halo_kernel<64, 2, EC>) : go(vb_conv_halo_kernel<64, 4, EC>);
+  if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "vb_gemm (conv halo) launch failed: %s", cudaGetErrorString(e));
+  return check_launch("vb_conv_halo");
+}
+
+}  // namespace vb

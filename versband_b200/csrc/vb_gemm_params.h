@@ -1,0 +1,84 @@
+// Kernel-side parameter blocks of vb_gemm and the per-epilogue-class launch entry points. The GEMM
+// kernels are instantiated once per EPILOGUE CLASS (vb_gemm_ec*.cu) so that each instance carries only
+// the epilogue code it executes: the all-in-one epilogue was ~9000 SASS instructions (144 KB) and ran
+// instruction-fetch bound (ncu: stall_no_inst on top, 22 % instruction-cache misses).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include "vb_internal.h"
+
+namespace vb {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // bf16 elements per k-block = one 128-byte swizzle row (32 for fp32/tf32 operands)
+constexpr int kEpiWarps = 8;                      // two per TMEM lane quadrant
+constexpr int kThreads = 64 + 32 * kEpiWarps;     // + TMA producer warp + MMA warp
+constexpr int kEpiColStep = 32 * (kEpiWarps / 4); // columns between two chunks of the same warp
+constexpr int kEpiStageBytes = kEpiWarps * 4096;  // per epilogue warp: one 32 x 32 fp32 transpose block
+constexpr int kPipeBytes = 192 * 1024;            // operand ring; + barriers + transpose blocks <= 227 KB
+
+// epilogue classes (compile-time specialisations of the fused epilogue)
+enum EpiClass {
+  EC_FULL = 0,    // everything: alpha, every activation, accumulate, ... (small MLPs, odd layers)
+  EC_LINEAR = 1,  // bias, {none, leaky-relu} activations, row_scale/row_map, gate, residual, accumulate, fp32 and/or operand-slot output
+  EC_SWIGLU = 2,  // silu(w1 x) * (w3 x) pairs -> operand-slot output (expert FFN first layers)
+  EC_QKV = 3,     // bias + rotary + head-major q/k and transposed v stores
+};
+
+struct GemmKParams {
+  int M, N, K;
+  int G1;
+  int num_kb, kpt, dil, pad;
+  int m_tiles, n_tiles, num_tiles;
+  int a_c2_g1, a_c2_g2, a_c3_g1, a_c3_g2;
+  int b_c2_g1, b_c2_g2, b_c2_tile;
+  const int* tile_group;
+  const int* m_tiles_used;
+  // epilogue
+  int mode;
+  float alpha;
+  int swiglu;
+  const float* bias;
+  long long bias_g1, bias_tile;
+  int act;
+  float act_slope;
+  const float* row_scale;
+  const float* gate;
+  int gate_rows;
+  long long gate_ld, gate_g1;
+  const int* row_map;
+  int row_mul, row_off, row_off_g1, rows_out;
+  const float* residual;
+  int accumulate;
+  float* out_f32;
+  long long out_ld, out_g1, out_g2;
+  __nv_bfloat16* out_bf16;
+  int outb_f32;  // the operand-output slot stores fp32 (tf32 operand mode) instead of bf16
+  long long outb_ld, outb_g1, outb_g2;
+  int act_out;
+  float act_out_slope, out_scale;
+  int dbg_shift;  // experiment: A tile loaded `dbg_shift` rows early, UMMA descriptor shifted back
+  int vec_f32, vec_bf16, vec_aux;  // alignment allows 16-byte accesses (outputs / bias+gate)
+  // qkv-rope
+  const float* rope_cs;
+  int T, heads, head_dim, Tp, qkv_sec0;
+  __nv_bfloat16* q_out;
+  __nv_bfloat16* k_out;
+  __nv_bfloat16* vt_out;
+  unsigned long long* trace;  // debug (vb_set_gemm_trace): 8 x u64 per CTA, see tools/trace_gemm.py
+};
+
+
+struct HaloParams {
+  int taps, row_shift, rows, rows8, n_ksteps, stages, base_off;
+};
+
+template <int EC>
+int launch_gemm_class(int bn, bool tf32, bool use2, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p,
+                      int grid, cudaStream_t stream);
+template <int EC>
+int launch_halo_class(int hbn, bool k2, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p,
+                      const HaloParams& hp, int grid, int smem_bytes, cudaStream_t stream);
+
+}  // namespace vb
