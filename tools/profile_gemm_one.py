@@ -31,6 +31,20 @@ elif which == "mq":  # the DiT mq projection in tf32 mode: bias, fp32 operand-sl
     bias = torch.randn(N, device="cuda")
     o = torch.empty(M, N, device="cuda")
     fn = lambda: ops.gemm(a, b, bias=bias, out_bf16=o, outb_ld=N)
+elif which == "wo":  # the DiT attention output projection in tf32 mode: gate, residual, fp32 out; 1-CTA bn96
+    M, N, K = 1500, 768, 768
+    a = torch.randn(M, K, device="cuda")
+    b = torch.randn(N, K, device="cuda")
+    gate = torch.randn(2, N, device="cuda")
+    res = torch.randn(M, N, device="cuda")
+    o = torch.empty(M, N, device="cuda")
+    fn = lambda: ops.gemm(a, b, gate=gate, gate_rows=750, gate_ld=N, residual=res, out_f32=o, out_ld=N, bn=96)
+elif which == "w13":  # swiglu, fp32 operand-slot output, bn128
+    M, N, K = 3072, 1024, 768
+    a = torch.randn(M, K, device="cuda")
+    b = torch.randn(N, K, device="cuda")
+    o = torch.empty(M, N // 2, device="cuda")
+    fn = lambda: ops.gemm(a, b, swiglu=True, out_bf16=o, outb_ld=N // 2, bn=128)
 else:
     M, N, K = 1500, 2304 if "qkv" in which else 768, 768
     dt = torch.float32 if "tf32" in which else torch.bfloat16

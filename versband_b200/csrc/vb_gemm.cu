@@ -220,6 +220,9 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
                  (!a->out_bf16 || al(a->out_bf16, 16));
     p.vec_aux = (!a->bias || (al(a->bias, 16) && a->bias_g1 % 4 == 0 && a->bias_tile % 4 == 0)) &&
                 (!a->gate || (al(a->gate, 16) && a->gate_ld % 4 == 0 && a->gate_g1 % 4 == 0));
+    const long long lim = 1ll << 31;
+    p.fast_ok = p.vec_f32 && p.vec_bf16 && p.vec_aux && (long long)a->rows_out * a->out_ld < lim &&
+                (long long)a->rows_out * a->outb_ld < lim && a->out_ld >= 0 && a->outb_ld >= 0;
     if (a->accumulate && !a->out_f32)
       return set_error(VB_ERR_INVALID, "vb_gemm: accumulate needs out_f32");
     if (a->residual && a->out_ld <= 0)

@@ -56,138 +56,292 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 // ------------------------------------------------------------------ coalesced epilogue
 // tcgen05.ld hands each thread one accumulator ROW (32 consecutive columns). Storing straight from
-// that layout makes every warp-level 16-byte access touch 32 different cache lines (32 L1
-// wavefronts per instruction): tools/trace_gemm.py measured ~2 us per 32-column chunk, more than the
-// whole mainloop of the DiT linears. Each epilogue warp therefore transposes its 32x32 chunk
-// through a private, XOR-swizzled 4 KB smem block: afterwards 8 lanes cover 128 contiguous bytes
-// of one row, one warp instruction touches 4 rows x 128 B, and every load of the fused operands
-// (bias, gate, residual, rope table) and every store is coalesced.
+// that layout makes every warp-level 16-byte access touch 32 different cache lines. Each epilogue
+// warp therefore transposes its 32x32 chunk through a private, XOR-swizzled 4 KB smem block:
+// afterwards 8 lanes cover 128 contiguous bytes of one row, one warp instruction touches 4 rows x
+// 128 B, and every load of the fused operands (bias, gate, residual, rope table) and every store is
+// coalesced.
 //   lane -> (lr = lane >> 3, cq = lane & 7); item i in 0..7 = row 4i + lr of the warp's 32 rows,
 //   columns 4cq .. 4cq+3 of the chunk; v[4i + k] is component k of item i.
-
+// The epilogue is instruction-issue bound (a few warps running a long dependent chain), so the
+// fast path keeps per-chunk work minimal: row offsets are computed once per tile as 32-bit element
+// offsets, alignment / raggedness is decided once per chunk (edge chunks fall back to the row-wise
+// code), and invalid rows are handled by predicated stores.
 struct EpiRows {
-  int orow[8];  // generic: output row, QKV: b*H*T + t; -1 = row not stored
-  int aux[8];   // generic: gate batch index (m / gate_rows), QKV: t
-  float rs[8];  // row_scale
+  unsigned off[8];   // generic: orow * out_ld;  QKV: (b*H*T + t) * hd         (0 for rows not stored)
+  unsigned offb[8];  // generic: orow * outb_ld; QKV: t * hd (row of the rope table)
+  float rs[8];       // row_scale
+  unsigned valid;    // bit i: item row i is stored
+  unsigned hi;       // bit i: item row i belongs to gate batch b_lo + 1
+  int b_lo;          // gate batch of the lane's first row
+  bool multi;        // the lane's rows span more than two gate batches -> row-wise path
 };
 
 template <int EC>
 __device__ __forceinline__ void epi_prepare_rows(const GemmKParams& p, EpiRows& rows, int m_base, int g1, int lane) {
-  const int lr = lane >> 3;
+  const int m0 = m_base + (lane >> 3);
+  rows.valid = 0; rows.hi = 0; rows.multi = false; rows.b_lo = 0;
+  if (EC == EC_QKV) {
+    const int mc = m0 < p.M ? m0 : p.M - 1;
+    int b = mc / p.T, t = mc - b * p.T;
+    t += m0 - mc;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      while (t >= p.T) { t -= p.T; ++b; }
+      const bool ok = m0 + 4 * i < p.M;
+      rows.off[i] = ok ? static_cast<unsigned>((b * p.heads * p.T + t) * p.head_dim) : 0u;
+      rows.offb[i] = ok ? static_cast<unsigned>(t * p.head_dim) : 0u;
+      rows.rs[i] = 1.f;
+      if (ok) rows.valid |= 1u << i;
+      t += 4;
+    }
+    return;
+  }
+  int b = 0, r = 0;
+  if (EC != EC_SWIGLU && p.gate) {
+    const int mc = m0 < p.M ? m0 : p.M - 1;
+    b = mc / p.gate_rows;
+    r = mc - b * p.gate_rows + (m0 - mc);
+    rows.b_lo = b;
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int m = m_base + 4 * i + lr;
-    const bool ok = m < p.M;
-    int o = -1, a = 0;
+    const int m = m0 + 4 * i;
+    int o = -1;
     float rs = 1.f;
-    if (ok) {
-      if (EC == EC_QKV) {
-        const int b = m / p.T;
-        a = m - b * p.T;
-        o = b * p.heads * p.T + a;
-      } else {
-        o = p.row_map ? p.row_map[m] : m * p.row_mul + p.row_off + g1 * p.row_off_g1;
-        if (o < 0 || o >= p.rows_out) o = -1;
-        if (EC != EC_SWIGLU && p.gate) a = m / p.gate_rows;
-        if (p.row_scale) rs = p.row_scale[m];
+    if (m < p.M) {
+      o = p.row_map ? p.row_map[m] : m * p.row_mul + p.row_off + g1 * p.row_off_g1;
+      if (o >= p.rows_out) o = -1;
+      if (p.row_scale) rs = p.row_scale[m];
+      if (EC != EC_SWIGLU && p.gate) {
+        while (r >= p.gate_rows) { r -= p.gate_rows; ++b; }
+        if (b - rows.b_lo == 1) rows.hi |= 1u << i;
+        if (b - rows.b_lo > 1) rows.multi = true;
+        r += 4;
       }
     }
-    rows.orow[i] = o;
-    rows.aux[i] = a;
+    if (o >= 0) rows.valid |= 1u << i;
+    rows.off[i] = o >= 0 ? static_cast<unsigned>(o) * static_cast<unsigned>(p.out_ld) : 0u;
+    rows.offb[i] = o >= 0 ? static_cast<unsigned>(o) * static_cast<unsigned>(p.outb_ld) : 0u;
     rows.rs[i] = rs;
   }
 }
 
 // thread `lane` owns accumulator row `lane` of the warp: write it, read back the item layout
-__device__ __forceinline__ void epi_transpose(const uint32_t (&raw)[32], float* stg, int lane, float (&v)[32]) {
+__device__ __forceinline__ void epi_transpose(const uint32_t (&raw)[32], uint32_t stg, int lane, float (&v)[32]) {
   __syncwarp();  // previous chunk's reads are done
 #pragma unroll
   for (int j = 0; j < 8; ++j)
-    *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-        make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 128 + ((j ^ (lane & 7)) << 4)),
+                 "r"(raw[4 * j]), "r"(raw[4 * j + 1]), "r"(raw[4 * j + 2]), "r"(raw[4 * j + 3])
+                 : "memory");
   __syncwarp();
   const int lr = lane >> 3, cq = lane & 7;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int row = 4 * i + lr;
-    const float4 x = *reinterpret_cast<const float4*>(stg + row * 32 + ((cq ^ (row & 7)) << 2));
-    v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v[4 * i]), "=f"(v[4 * i + 1]), "=f"(v[4 * i + 2]), "=f"(v[4 * i + 3])
+                 : "r"(stg + row * 128 + ((cq ^ (row & 7)) << 4))
+                 : "memory");
   }
 }
 
-__device__ __forceinline__ float4 ld4(const float* __restrict__ src, bool vec, int n_left) {
-  if (vec) return __ldg(reinterpret_cast<const float4*>(src));
-  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (n_left > 0) r.x = src[0];
-  if (n_left > 1) r.y = src[1];
-  if (n_left > 2) r.z = src[2];
-  if (n_left > 3) r.w = src[3];
-  return r;
+__device__ __forceinline__ float silu_mul(float a, float b) { return __fdividef(a, 1.f + __expf(-a)) * b; }
+
+// v[j] (op)= src[j] for the 32 columns of this chunk; vector path when the chunk is full & aligned
+template <bool MUL>
+__device__ __forceinline__ void combine32(float (&v)[32], const float* __restrict__ src, bool vec,
+                                          int n_left) {
+  if (vec) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 r = __ldg(reinterpret_cast<const float4*>(src) + j);
+      if (MUL) { v[4 * j] *= r.x; v[4 * j + 1] *= r.y; v[4 * j + 2] *= r.z; v[4 * j + 3] *= r.w; }
+      else { v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w; }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < n_left) { if (MUL) v[j] *= src[j]; else v[j] += src[j]; }
+  }
 }
-__device__ __forceinline__ void st4(float* __restrict__ dst, const float* v, bool vec, int n_left) {
-  if (vec) { *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]); return; }
-  if (n_left > 0) dst[0] = v[0];
-  if (n_left > 1) dst[1] = v[1];
-  if (n_left > 2) dst[2] = v[2];
-  if (n_left > 3) dst[3] = v[3];
+
+// ------------------------------------------------------------------ row-wise (edge) epilogue
+// One thread owns one output row (TMEM lane) and 32 consecutive columns of it: handles ragged N,
+// unaligned pointers and every fusion; only used for chunks the coalesced path below rejects.
+__device__ __forceinline__ void epilogue_rowwise(const GemmKParams& p, float (&v)[32], int m,
+                                                 int n_base, int g1, int g2, int tg,
+                                                 long long orow) {
+  const int N = p.N;
+  if (p.alpha != 1.f) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+  }
+
+  if (p.swiglu) {
+    // columns (2i, 2i+1) = (w1 x, w3 x)  ->  silu(w1 x) * (w3 x), 16 outputs
+    const int n_out0 = n_base >> 1;
+    const int n_out_total = N >> 1;
+    const float rs = p.row_scale ? p.row_scale[m] : 1.f;
+    float o[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float a = v[2 * j], b = v[2 * j + 1];
+      o[j] = (a / (1.f + __expf(-a))) * b * rs;
+    }
+    if (p.out_bf16 && p.outb_f32) {
+      float* dstf = reinterpret_cast<float*>(p.out_bf16) + g1 * p.outb_g1 + g2 * p.outb_g2 + orow * p.outb_ld + n_out0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (n_out0 + j < n_out_total) dstf[j] = o[j];
+    } else if (p.out_bf16) {
+      __nv_bfloat16* dst = p.out_bf16 + g1 * p.outb_g1 + g2 * p.outb_g2 + orow * p.outb_ld + n_out0;
+      if (p.vec_bf16 && n_out0 + 16 <= n_out_total) {
+        uint4 w0, w1;
+        w0.x = pack_bf16(o[0], o[1]);   w0.y = pack_bf16(o[2], o[3]);
+        w0.z = pack_bf16(o[4], o[5]);   w0.w = pack_bf16(o[6], o[7]);
+        w1.x = pack_bf16(o[8], o[9]);   w1.y = pack_bf16(o[10], o[11]);
+        w1.z = pack_bf16(o[12], o[13]); w1.w = pack_bf16(o[14], o[15]);
+        reinterpret_cast<uint4*>(dst)[0] = w0;
+        reinterpret_cast<uint4*>(dst)[1] = w1;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (n_out0 + j < n_out_total) dst[j] = __float2bfloat16(o[j]);
+      }
+    }
+    if (p.out_f32) {
+      float* dst = p.out_f32 + g1 * p.out_g1 + g2 * p.out_g2 + orow * p.out_ld + n_out0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (n_out0 + j < n_out_total) dst[j] = o[j];
+    }
+    return;
+  }
+
+  const bool full = (n_base + 32 <= N);
+  const int n_left = N - n_base;
+  if (p.bias) combine32<false>(v, p.bias + g1 * p.bias_g1 + tg * p.bias_tile + n_base, full && p.vec_aux, n_left);
+  if (p.act != VB_ACT_NONE) apply_act_all(v, p.act, p.act_slope);
+  if (p.row_scale) {
+    const float rs = p.row_scale[m];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= rs;
+  }
+  if (p.gate)
+    combine32<true>(v, p.gate + (long long)(m / p.gate_rows) * p.gate_ld + g1 * p.gate_g1 + n_base,
+                    full && p.vec_aux, n_left);
+  const long long off32 = g1 * p.out_g1 + g2 * p.out_g2 + orow * p.out_ld + n_base;
+  if (p.residual) combine32<false>(v, p.residual + off32, full && p.vec_f32, n_left);
+  if (p.out_f32) {
+    float* dst = p.out_f32 + off32;
+    if (p.accumulate) combine32<false>(v, dst, full && p.vec_f32, n_left);
+    if (full && p.vec_f32) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        reinterpret_cast<float4*>(dst)[j] =
+            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < n_left) dst[j] = v[j];
+    }
+  }
+  if (p.out_bf16) {
+    const long long offb = g1 * p.outb_g1 + g2 * p.outb_g2 + orow * p.outb_ld + n_base;
+    apply_act_all(v, p.act_out, p.act_out_slope, p.out_scale);
+    if (p.outb_f32) {
+      float* dstf = reinterpret_cast<float*>(p.out_bf16) + offb;
+      if (full && p.vec_bf16) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          reinterpret_cast<float4*>(dstf)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < n_left) dstf[j] = v[j];
+      }
+      return;
+    }
+    __nv_bfloat16* dst = p.out_bf16 + offb;
+    if (full && p.vec_bf16) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 w;
+        w.x = pack_bf16(v[8 * j], v[8 * j + 1]);
+        w.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+        w.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+        w.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+        reinterpret_cast<uint4*>(dst)[j] = w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < n_left) dst[j] = __float2bfloat16(v[j]);
+    }
+  }
+}
+
+struct Raw32 { uint32_t r[32]; };
+// Out of line on purpose: keeps the (rarely executed) edge code out of the hot instruction stream.
+static __device__ __noinline__ void epilogue_rowwise_chunk(const GemmKParams& p, Raw32 raw, int m, int n_base, int g1,
+                                                    int g2, int tg) {
+  if (m >= p.M) return;
+  const long long orow = p.row_map ? (long long)p.row_map[m]
+                                   : (long long)m * p.row_mul + p.row_off + (long long)g1 * p.row_off_g1;
+  if (orow < 0 || orow >= p.rows_out) return;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw.r[j]);
+  epilogue_rowwise(p, v, m, n_base, g1, g2, tg, orow);
 }
 
 // Global operands of one chunk's epilogue, requested ahead of use (together with the chunk's TMEM
-// load): all loads are unconditional (rows that are not stored read a clamped valid row) so that
-// they are in flight together — the epilogue is bound by round trips to L2, not by bytes.
+// load): all loads are unconditional (rows that are not stored read row 0) so that they are in
+// flight together.
 struct EpiOperands {
   float4 res[8];      // generic: residual (or the accumulate target) per item; QKV: rope (cos,sin) x2 per item
   float4 bias;        // per column quad
-  float4 g_lo, g_hi;  // gate rows of the (at most two) batches this lane's rows fall in
+  float4 g_lo, g_hi;  // gate rows of the two batches this lane's rows fall in
 };
 
 template <int EC>
 __device__ __forceinline__ void epi_load_operands(const GemmKParams& p, const EpiRows& rows, EpiOperands& op,
                                                   int n_base, int g1, int g2, int tg, int lane) {
-  const int cq = lane & 7;
-  const int n = n_base + 4 * cq;
+  const int n = n_base + 4 * (lane & 7);
   if (EC == EC_QKV) {
     const int hd = p.head_dim;
-    const int D = p.heads * hd;
-    const int sec = n_base / D + p.qkv_sec0;
-    if (sec == 2) return;
+    if (n_base / (p.heads * hd) + p.qkv_sec0 == 2) return;
     op.bias = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.rope_cs) {
-      const int d = (n_base % hd) + 4 * cq;  // dim inside the head (chunks never straddle heads)
+      const float* cs = p.rope_cs + (n_base % hd) + 4 * (lane & 7);  // 2 floats per pair: column d <-> floats d, d+1
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        op.res[i] = __ldg(reinterpret_cast<const float4*>(p.rope_cs + ((long long)rows.aux[i] * (hd >> 1) + (d >> 1)) * 2));
+      for (int i = 0; i < 8; ++i) op.res[i] = __ldg(reinterpret_cast<const float4*>(cs + rows.offb[i]));
     }
     return;
   }
   if (EC == EC_SWIGLU || (EC == EC_FULL && p.swiglu)) return;
-  const int n_left = p.N - n;
-  const bool full = n_left >= 4;
-  if (p.bias) op.bias = ld4(p.bias + g1 * p.bias_g1 + tg * p.bias_tile + n, full && p.vec_aux, n_left);
+  if (p.bias) op.bias = __ldg(reinterpret_cast<const float4*>(p.bias + g1 * p.bias_g1 + tg * p.bias_tile + n));
   if (p.gate) {
-    const float* gsrc = p.gate + g1 * p.gate_g1 + n;
-    op.g_lo = ld4(gsrc + (long long)rows.aux[0] * p.gate_ld, full && p.vec_aux, n_left);
-    op.g_hi = ld4(gsrc + (long long)rows.aux[7] * p.gate_ld, full && p.vec_aux, n_left);
+    const float* gsrc = p.gate + g1 * p.gate_g1 + n + (long long)rows.b_lo * p.gate_ld;
+    op.g_lo = __ldg(reinterpret_cast<const float4*>(gsrc));
+    op.g_hi = __ldg(reinterpret_cast<const float4*>(gsrc + (rows.hi ? p.gate_ld : 0)));
   }
   const float* rsrc = p.residual ? p.residual : ((p.accumulate && p.out_f32) ? p.out_f32 : nullptr);
   if (rsrc) {
     rsrc += g1 * p.out_g1 + g2 * p.out_g2 + n;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int o = rows.orow[i] < 0 ? 0 : rows.orow[i];
-      op.res[i] = ld4(rsrc + (long long)o * p.out_ld, full && p.vec_f32, n_left);
-    }
+    for (int i = 0; i < 8; ++i) op.res[i] = __ldg(reinterpret_cast<const float4*>(rsrc + rows.off[i]));
   }
 }
 
-// ------------------------------------------------------------------ generic epilogue (one 32-column chunk)
+// ------------------------------------------------------------------ generic epilogue, coalesced fast path
+// (full 32-column chunk, every pointer / stride 16-byte friendly: GemmKParams::fast_ok)
 template <int EC>
 __device__ __forceinline__ void epilogue_generic(const GemmKParams& p, float (&v)[32], const EpiRows& rows,
                                                  const EpiOperands& op, int n_base, int g1, int g2, int tg, int lane) {
-  const int N = p.N;
-  const int cq = lane & 7;
-  const int n = n_base + 4 * cq;  // first of this lane's 4 columns
-  const int n_left = N - n;       // columns of the quad that exist
+  const int n = n_base + 4 * (lane & 7);  // first of this lane's 4 columns
   if (EC == EC_FULL && p.alpha != 1.f) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
@@ -196,35 +350,33 @@ __device__ __forceinline__ void epilogue_generic(const GemmKParams& p, float (&v
   if (EC == EC_SWIGLU || (EC == EC_FULL && p.swiglu)) {
     // columns (2i, 2i+1) = (w1 x, w3 x)  ->  silu(w1 x) * (w3 x): two outputs per quad
     const int no = n >> 1;
-    const int no_left = (N >> 1) - no;
-    const long long gofs = g1 * p.outb_g1 + g2 * p.outb_g2;
+    float o[16];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float a0 = v[4 * i], b0 = v[4 * i + 1], a1 = v[4 * i + 2], b1 = v[4 * i + 3];
-      const float o0 = (a0 / (1.f + __expf(-a0))) * b0 * rows.rs[i];
-      const float o1 = (a1 / (1.f + __expf(-a1))) * b1 * rows.rs[i];
-      if (rows.orow[i] < 0 || no_left <= 0) continue;
-      const bool two = no_left > 1;
-      if (p.out_bf16 && p.outb_f32) {
-        float* dst = reinterpret_cast<float*>(p.out_bf16) + gofs + (long long)rows.orow[i] * p.outb_ld + no;
-        if (two && p.vec_bf16) *reinterpret_cast<float2*>(dst) = make_float2(o0, o1);
-        else { dst[0] = o0; if (two) dst[1] = o1; }
-      } else if (p.out_bf16) {
-        __nv_bfloat16* dst = p.out_bf16 + gofs + (long long)rows.orow[i] * p.outb_ld + no;
-        if (two && p.vec_bf16) *reinterpret_cast<uint32_t*>(dst) = pack_bf16(o0, o1);
-        else { dst[0] = __float2bfloat16(o0); if (two) dst[1] = __float2bfloat16(o1); }
-      }
-      if (EC == EC_FULL && p.out_f32) {
-        float* dst = p.out_f32 + g1 * p.out_g1 + g2 * p.out_g2 + (long long)rows.orow[i] * p.out_ld + no;
-        dst[0] = o0;
-        if (two) dst[1] = o1;
-      }
+      o[2 * i] = silu_mul(v[4 * i], v[4 * i + 1]) * rows.rs[i];
+      o[2 * i + 1] = silu_mul(v[4 * i + 2], v[4 * i + 3]) * rows.rs[i];
+    }
+    if (p.out_bf16 && p.outb_f32) {
+      float* dst = reinterpret_cast<float*>(p.out_bf16) + g1 * p.outb_g1 + g2 * p.outb_g2 + no;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (rows.valid >> i & 1) *reinterpret_cast<float2*>(dst + rows.offb[i]) = make_float2(o[2 * i], o[2 * i + 1]);
+    } else if (p.out_bf16) {
+      __nv_bfloat16* dst = p.out_bf16 + g1 * p.outb_g1 + g2 * p.outb_g2 + no;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (rows.valid >> i & 1) *reinterpret_cast<uint32_t*>(dst + rows.offb[i]) = pack_bf16(o[2 * i], o[2 * i + 1]);
+    }
+    if (EC == EC_FULL && p.out_f32) {
+      float* dst = p.out_f32 + g1 * p.out_g1 + g2 * p.out_g2 + no;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (rows.valid >> i & 1) *reinterpret_cast<float2*>(dst + rows.off[i]) = make_float2(o[2 * i], o[2 * i + 1]);
     }
     return;
   }
   if (EC == EC_SWIGLU) return;
 
-  const bool full = n_left >= 4;
   if (p.bias) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { v[4 * i] += op.bias.x; v[4 * i + 1] += op.bias.y; v[4 * i + 2] += op.bias.z; v[4 * i + 3] += op.bias.w; }
@@ -239,19 +391,10 @@ __device__ __forceinline__ void epilogue_generic(const GemmKParams& p, float (&v
     for (int i = 0; i < 8; ++i) { v[4 * i] *= rows.rs[i]; v[4 * i + 1] *= rows.rs[i]; v[4 * i + 2] *= rows.rs[i]; v[4 * i + 3] *= rows.rs[i]; }
   }
   if (p.gate) {
-    if (rows.aux[7] - rows.aux[0] <= 1) {  // the lane's 8 rows fall in at most two batches
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 g4 = rows.aux[i] == rows.aux[0] ? op.g_lo : op.g_hi;
-        v[4 * i] *= g4.x; v[4 * i + 1] *= g4.y; v[4 * i + 2] *= g4.z; v[4 * i + 3] *= g4.w;
-      }
-    } else {
-      const float* gsrc = p.gate + g1 * p.gate_g1 + n;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 g4 = ld4(gsrc + (long long)rows.aux[i] * p.gate_ld, full && p.vec_aux, n_left);
-        v[4 * i] *= g4.x; v[4 * i + 1] *= g4.y; v[4 * i + 2] *= g4.z; v[4 * i + 3] *= g4.w;
-      }
+    for (int i = 0; i < 8; ++i) {
+      const float4 g4 = (rows.hi >> i & 1) ? op.g_hi : op.g_lo;
+      v[4 * i] *= g4.x; v[4 * i + 1] *= g4.y; v[4 * i + 2] *= g4.z; v[4 * i + 3] *= g4.w;
     }
   }
   const long long gofs32 = g1 * p.out_g1 + g2 * p.out_g2 + n;
@@ -261,16 +404,17 @@ __device__ __forceinline__ void epilogue_generic(const GemmKParams& p, float (&v
     if (p.residual && p.accumulate && p.out_f32) {  // both: the accumulate target is read here
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int o = rows.orow[i] < 0 ? 0 : rows.orow[i];
-        const float4 r4 = ld4(p.out_f32 + gofs32 + (long long)o * p.out_ld, full && p.vec_f32, n_left);
+        const float4 r4 = *reinterpret_cast<const float4*>(p.out_f32 + gofs32 + rows.off[i]);
         v[4 * i] += r4.x; v[4 * i + 1] += r4.y; v[4 * i + 2] += r4.z; v[4 * i + 3] += r4.w;
       }
     }
   }
   if (p.out_f32) {
+    float* dst = p.out_f32 + gofs32;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      if (rows.orow[i] >= 0) st4(p.out_f32 + gofs32 + (long long)rows.orow[i] * p.out_ld, &v[4 * i], full && p.vec_f32, n_left);
+      if (rows.valid >> i & 1)
+        *reinterpret_cast<float4*>(dst + rows.off[i]) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
   }
   if (p.out_bf16) {
     const long long gofsb = g1 * p.outb_g1 + g2 * p.outb_g2 + n;
@@ -282,23 +426,18 @@ __device__ __forceinline__ void epilogue_generic(const GemmKParams& p, float (&v
       act_loop<VB_ACT_NONE>(v, 0.f, p.out_scale);
     }
     if (p.outb_f32) {
-      float* base = reinterpret_cast<float*>(p.out_bf16) + gofsb;
+      float* dst = reinterpret_cast<float*>(p.out_bf16) + gofsb;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        if (rows.orow[i] >= 0) st4(base + (long long)rows.orow[i] * p.outb_ld, &v[4 * i], full && p.vec_bf16, n_left);
-      return;
-    }
+        if (rows.valid >> i & 1)
+          *reinterpret_cast<float4*>(dst + rows.offb[i]) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+      __nv_bfloat16* dst = p.out_bf16 + gofsb;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (rows.orow[i] < 0) continue;
-      __nv_bfloat16* dst = p.out_bf16 + gofsb + (long long)rows.orow[i] * p.outb_ld;
-      if (full && p.vec_bf16) {
-        *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(v[4 * i], v[4 * i + 1]), pack_bf16(v[4 * i + 2], v[4 * i + 3]));
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k < n_left) dst[k] = __float2bfloat16(v[4 * i + k]);
-      }
+      for (int i = 0; i < 8; ++i)
+        if (rows.valid >> i & 1)
+          *reinterpret_cast<uint2*>(dst + rows.offb[i]) =
+              make_uint2(pack_bf16(v[4 * i], v[4 * i + 1]), pack_bf16(v[4 * i + 2], v[4 * i + 3]));
     }
   }
 }
@@ -309,7 +448,7 @@ __device__ __forceinline__ void epilogue_generic(const GemmKParams& p, float (&v
 // A 32-column chunk never straddles a head or section because head_dim % 32 == 0.
 // q / k go through the transposed (coalesced) layout; V^T[b][h][d][t] is written straight from the
 // TMEM layout (lanes = consecutive t -> coalesced 2-byte stores).
-__device__ __forceinline__ void epilogue_qkv(const GemmKParams& p, const uint32_t (&raw)[32], float* stg,
+__device__ __forceinline__ void epilogue_qkv(const GemmKParams& p, const uint32_t (&raw)[32], uint32_t stg,
                                              const EpiRows& rows, const EpiOperands& op, int m_base, int n_base,
                                              int lane) {
   const int hd = p.head_dim, H = p.heads, T = p.T;
@@ -335,8 +474,7 @@ __device__ __forceinline__ void epilogue_qkv(const GemmKParams& p, const uint32_
   }
   float v[32];
   epi_transpose(raw, stg, lane, v);
-  const int cq = lane & 7;
-  __nv_bfloat16* out = (sec == 0 ? p.q_out : p.k_out) + d0 + 4 * cq;
+  __nv_bfloat16* out = (sec == 0 ? p.q_out : p.k_out) + (long long)h * T * hd + d0 + 4 * (lane & 7);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     float x0 = v[4 * i] * p.alpha + op.bias.x, x1 = v[4 * i + 1] * p.alpha + op.bias.y;
@@ -347,34 +485,20 @@ __device__ __forceinline__ void epilogue_qkv(const GemmKParams& p, const uint32_
       const float y2 = x2 * cs.z - x3 * cs.w, y3 = x2 * cs.w + x3 * cs.z;
       x0 = y0; x1 = y1; x2 = y2; x3 = y3;
     }
-    if (rows.orow[i] >= 0)
-      *reinterpret_cast<uint2*>(out + ((long long)rows.orow[i] + (long long)h * T) * hd) =
-          make_uint2(pack_bf16(x0, x1), pack_bf16(x2, x3));
-  }
-}
-
-// One 32-column chunk of one warp's 32 rows: TMEM registers -> fused epilogue -> global.
-template <int EC>
-__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint32_t (&raw)[32], float* stg,
-                                               const EpiRows& rows, const EpiOperands& op, int m_base, int n_base,
-                                               int g1, int g2, int tg, int lane) {
-  if (EC == EC_QKV) {
-    epilogue_qkv(p, raw, stg, rows, op, m_base, n_base, lane);
-  } else {
-    float v[32];
-    epi_transpose(raw, stg, lane, v);
-    epilogue_generic<EC>(p, v, rows, op, n_base, g1, g2, tg, lane);
+    if (rows.valid >> i & 1)
+      *reinterpret_cast<uint2*>(out + rows.off[i]) = make_uint2(pack_bf16(x0, x1), pack_bf16(x2, x3));
   }
 }
 
 // The chunk loop shared by the three kernels. Eight epilogue warps: two per TMEM lane quadrant, the
 // pair splitting the tile's 32-column chunks even/odd (`c_first` = 0 or 32) — a single warp per
-// scheduler runs the ~400-instruction chunk body latency-bound, so warps, not bytes, set the pace.
+// scheduler runs the chunk body latency-bound, so warps, not bytes, set the pace.
 // A chunk's global operands are requested together with its TMEM load, before either is consumed.
 #define VB_EPILOGUE_TILE(BN_, N0, G1_, G2_, TG_, WAIT_STMT)                                              \
   {                                                                                                      \
     EpiRows rows;                                                                                        \
     epi_prepare_rows<EC>(p, rows, m_base, (G1_), lane);                                                  \
+    const bool tile_fast = EC == EC_QKV || (p.fast_ok && !__any_sync(0xffffffffu, rows.multi));          \
     WAIT_STMT;                                                                                           \
     tc_fence_after();                                                                                    \
     _Pragma("unroll 1") for (int c = c_first; c < (BN_); c += kEpiColStep) {                             \
@@ -382,10 +506,23 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
       if (n_base >= p.N) break;                                                                          \
       uint32_t raw[32];                                                                                  \
       tmem_ld32(tmem_d + c, raw);                                                                        \
-      EpiOperands op;                                                                                    \
-      epi_load_operands<EC>(p, rows, op, n_base, (G1_), (G2_), (TG_), lane);                             \
-      tmem_ld_wait();                                                                                    \
-      epilogue_chunk<EC>(p, raw, stg, rows, op, m_base, n_base, (G1_), (G2_), (TG_), lane);              \
+      if (tile_fast && (EC == EC_QKV || n_base + 32 <= p.N)) {                                           \
+        EpiOperands op;                                                                                  \
+        epi_load_operands<EC>(p, rows, op, n_base, (G1_), (G2_), (TG_), lane);                           \
+        tmem_ld_wait();                                                                                  \
+        if (EC == EC_QKV) {                                                                              \
+          epilogue_qkv(p, raw, stg, rows, op, m_base, n_base, lane);                                     \
+        } else {                                                                                         \
+          float v[32];                                                                                   \
+          epi_transpose(raw, stg, lane, v);                                                              \
+          epilogue_generic<EC>(p, v, rows, op, n_base, (G1_), (G2_), (TG_), lane);                       \
+        }                                                                                                \
+      } else {                                                                                           \
+        tmem_ld_wait();                                                                                  \
+        Raw32 rr;                                                                                        \
+        _Pragma("unroll") for (int j = 0; j < 32; ++j) rr.r[j] = raw[j];                                 \
+        epilogue_rowwise_chunk(p, rr, m_base + lane, n_base, (G1_), (G2_), (TG_));                       \
+      }                                                                                                  \
     }                                                                                                    \
   }
 
@@ -426,7 +563,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int t, in
 template <int BN, bool TF32, int EC>
 __global__ void __launch_bounds__(kThreads, 1)
 vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const GemmKParams p) {
+               const __grid_constant__ GemmKParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
 
@@ -536,7 +673,7 @@ vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue warps (2..5) =====================
     const int q = warp_idx & 3;  // TMEM lane quadrant this warp may access
     const int c_first = ((warp_idx - 2) >> 2) * 32;
-    float* stg = epi_stage + (warp_idx - 2) * 1024;
+    const uint32_t stg = smem_u32(epi_stage) + (warp_idx - 2) * 4096;
     int local = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(p, t, m_used);
@@ -583,7 +720,7 @@ struct Gemm2Cfg {
 template <int BN, bool TF32, int EC>
 __global__ void __launch_bounds__(kThreads, 1)
 vb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const GemmKParams p) {
+                const __grid_constant__ GemmKParams p) {
   using Cfg = Gemm2Cfg<BN>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kBkElems = TF32 ? 32 : 64;
@@ -692,7 +829,7 @@ vb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===================== epilogue warps (both CTAs) =====================
     const int q = warp_idx & 3;
     const int c_first = ((warp_idx - 2) >> 2) * 32;
-    float* stg = epi_stage + (warp_idx - 2) * 1024;
+    const uint32_t stg = smem_u32(epi_stage) + (warp_idx - 2) * 4096;
     int local = 0;
     for (int t = first; t < num_pairs; t += n_clusters) {
       const int g = t / per_g, rr = t - g * per_g;
@@ -729,7 +866,7 @@ vb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 template <int BN, int KSTEPS, int EC>
 __global__ void __launch_bounds__(kThreads, 1)
 vb_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmKParams p, const HaloParams hp) {
+                    const __grid_constant__ GemmKParams p, const HaloParams hp) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -816,7 +953,7 @@ vb_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     const int q = warp_idx & 3;
     const int c_first = ((warp_idx - 2) >> 2) * 32;
-    float* stg = epi_stage + (warp_idx - 2) * 1024;
+    const uint32_t stg = smem_u32(epi_stage) + (warp_idx - 2) * 4096;
     int local = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       const int g = t / p.m_tiles, m_tile = t - g * p.m_tiles;

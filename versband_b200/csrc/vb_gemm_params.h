@@ -60,6 +60,7 @@ struct GemmKParams {
   float act_out_slope, out_scale;
   int dbg_shift;  // experiment: A tile loaded `dbg_shift` rows early, UMMA descriptor shifted back
   int vec_f32, vec_bf16, vec_aux;  // alignment allows 16-byte accesses (outputs / bias+gate)
+  int fast_ok;  // all of the above and every row offset fits 32 bits: coalesced epilogue path allowed
   // qkv-rope
   const float* rope_cs;
   int T, heads, head_dim, Tp, qkv_sec0;
