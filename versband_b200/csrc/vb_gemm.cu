@@ -109,9 +109,11 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
   const int m_tiles = (a->M + BM - 1) / BM;
   const int G = a->G1 * a->G2;
   // ---- tile selection -------------------------------------------------------------------
-  // Cost model fitted to device timings on B200 (tools/bench_bn.py): operand ingest is bounded per
-  // SM (~64 B/clk) and chip-wide (L2 throughput, ~half of 148 x 64 B/clk), every tile pays an
-  // epilogue proportional to its width plus a fixed pipeline fill. Units: 128-byte rows.
+  // Cost model fitted to in-sequence device timings on B200 (tools/tune_insitu.py: every candidate
+  // forced in turn inside one graph-replayed DiT evaluation): operand ingest is bounded per SM
+  // (~64 B/clk) and chip-wide (L2 throughput, ~90 x 64 B/clk), every tile pays an epilogue
+  // proportional to its width in 64-column rounds (two epilogue warps per TMEM quadrant) plus a
+  // fixed pipeline fill. Units: 128-byte rows.
   bool use2 = false;
   {
     const bool user_bn = bn != 0;
@@ -126,7 +128,7 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
       const double tiles = (double)m_tiles * ((a->N + c - 1) / c) * G;
       const double waves = ceil(tiles / 148.0);
       const double u = (double)num_kb * (128 + c);
-      const double cost = fmax(waves * u, tiles * u / 74.0) + waves * (40.0 * c + 1500.0);
+      const double cost = fmax(waves * u, tiles * u / 90.0) + waves * (40.0 * ((c + 63) / 64 * 64) + 1500.0);
       if (cost < best) { best = cost; best_bn = c; }
     }
     // 2-CTA pairs (cta_group::2): each CTA loads only half of the B tile. Non-grouped problems only.
@@ -138,7 +140,7 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
         const double ctas = 2.0 * ((m_tiles + 1) / 2) * ((a->N + c - 1) / c) * G;
         const double waves = ceil(ctas / 148.0);
         const double u = (double)num_kb * (128 + c / 2);
-        const double cost = fmax(waves * u, ctas * u / 74.0) + waves * (40.0 * c + 2100.0);
+        const double cost = fmax(waves * u, ctas * u / 90.0) + waves * (40.0 * ((c + 63) / 64 * 64) + 2100.0);
         if (cost < best || g_gemm2_mode == 2) {
           if (g_gemm2_mode == 2 && use2 && cost >= best) continue;
           best = cost; best_bn = c; use2 = true;

@@ -592,7 +592,7 @@ vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], kEpiWarps * 32);
+      mbar_init(&tmem_empty_bar[i], BN == 32 ? kEpiWarps * 16 : kEpiWarps * 32);
     }
     fence_barrier_init();
   }
@@ -672,13 +672,17 @@ vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ===================== epilogue warps (2..5) =====================
     const int q = warp_idx & 3;  // TMEM lane quadrant this warp may access
-    const int c_first = ((warp_idx - 2) >> 2) * 32;
+    // BN >= 64: the two warps of a quadrant split a tile's chunks even/odd. BN == 32 (one chunk):
+    // they alternate TILES instead — warp set s owns TMEM accumulator s.
+    const int wset = (warp_idx - 2) >> 2;
+    const int c_first = BN == 32 ? 0 : wset * 32;
     const uint32_t stg = smem_u32(epi_stage) + (warp_idx - 2) * 4096;
     int local = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(p, t, m_used);
       if (tc.skip) continue;
       const int acc = local & 1;
+      if (BN == 32 && acc != wset) { ++local; continue; }
       const int m_base = tc.m_tile * BM + q * 32, n0 = tc.n_tile * BN;
       const uint32_t tmem_d = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
       VB_EPILOGUE_TILE(BN, n0, tc.g1, tc.g2, tc.tg,
@@ -890,7 +894,7 @@ vb_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < hp.stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     mbar_init(w_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], kEpiWarps * 32); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], BN == 32 ? kEpiWarps * 16 : kEpiWarps * 32); }
     fence_barrier_init();
   }
   if (warp_idx == 1) tmem_alloc<2 * kAcc>(tmem_slot);
@@ -952,13 +956,15 @@ vb_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     const int q = warp_idx & 3;
-    const int c_first = ((warp_idx - 2) >> 2) * 32;
+    const int wset = (warp_idx - 2) >> 2;  // BN == 32: warp set s owns accumulator s (see vb_gemm_kernel)
+    const int c_first = BN == 32 ? 0 : wset * 32;
     const uint32_t stg = smem_u32(epi_stage) + (warp_idx - 2) * 4096;
     int local = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       const int g = t / p.m_tiles, m_tile = t - g * p.m_tiles;
       const int g1 = g % p.G1, g2 = g / p.G1;
       const int acc = local & 1;
+      if (BN == 32 && acc != wset) { ++local; continue; }
       const int m_base = m_tile * BM + q * 32;
       const uint32_t tmem_d = tmem_base + acc * kAcc + (static_cast<uint32_t>(q * 32) << 16);
       VB_EPILOGUE_TILE(BN, 0, g1, g2, 0, mbar_wait(&tmem_full_bar[acc], (local >> 1) & 1))

@@ -49,13 +49,38 @@ __global__ void router_kernel(const float* __restrict__ cap_feat, const __nv_bfl
                               float* __restrict__ usage, int* __restrict__ slot_c,
                               int* __restrict__ slot_a) {
   pdl_sync();
-  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  __shared__ int s_cnt[2 * E], s_base[2 * E];
+  __shared__ float s_use[2 * E];
+  if (threadIdx.x < 2 * E) { s_cnt[threadIdx.x] = 0; s_use[threadIdx.x] = 0.f; }
+  __syncthreads();
+  const int n_raw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const bool tok_ok = n_raw < N;
+  const int n = tok_ok ? n_raw : N - 1;  // surplus warps recompute the last token and store nothing
   const int lane = threadIdx.x & 31;
-  if (n >= N) return;
   float acc[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) acc[e] = 0.f;
-  if (cap_feat_bf) {
+  if ((D & 127) == 0) {  // 16-byte loads: lane owns 4 consecutive features per 128-feature slab
+    for (int d = lane * 4; d < D; d += 128) {
+      float4 xv;
+      if (cap_feat_bf) {
+        const uint2 u = *reinterpret_cast<const uint2*>(cap_feat_bf + (long long)n * D + d);
+        const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+        const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+        xv = make_float4(__low2float(p0), __high2float(p0), __low2float(p1), __high2float(p1));
+      } else {
+        xv = *reinterpret_cast<const float4*>(cap_feat + (long long)n * D + d);
+      }
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(Wc + (long long)e * D + d));
+        acc[e] = fmaf(xv.x, wv.x, acc[e]);
+        acc[e] = fmaf(xv.y, wv.y, acc[e]);
+        acc[e] = fmaf(xv.z, wv.z, acc[e]);
+        acc[e] = fmaf(xv.w, wv.w, acc[e]);
+      }
+    }
+  } else if (cap_feat_bf) {
     const __nv_bfloat16* xr = cap_feat_bf + (long long)n * D;
 #pragma unroll 4
     for (int d = lane; d < D; d += 32) {
@@ -89,7 +114,7 @@ __global__ void router_kernel(const float* __restrict__ cap_feat, const __nv_bfl
 #pragma unroll
     for (int e = 1; e < E; ++e) lcv = (j == e) ? acc[e] : lcv;
     logit = lcv + bc[j < E ? j : 0];
-    if (cap_logits_out && lane < E) cap_logits_out[(long long)n * E + j] = logit;
+    if (cap_logits_out && lane < E && tok_ok) cap_logits_out[(long long)n * E + j] = logit;
     ex = e1[(long long)n * E + (j < E ? j : 0)];
   } else if (gate == 1) {
     logit = ac_logits[(long long)n * ac_ld + j];
@@ -125,18 +150,35 @@ __global__ void router_kernel(const float* __restrict__ cap_feat, const __nv_bfl
   const float mask_a = __shfl_sync(0xffffffffu, zz[1] / ssum, 2 * E);
   const int ia = __shfl_sync(0xffffffffu, best, E);
   const float wa = __shfl_sync(0xffffffffu, w_hard, E);
-  if (lane != 0) return;
   const int ic = best;
   const float wc = w_hard;
-  idx_c[n] = ic;
-  idx_a[n] = ia;
-  scale_c[n] = wc * mask_c;
-  scale_a[n] = wa * mask_a;
-  if (bucket_count) {  // unordered slot claim inside the (group, expert) bucket
-    slot_c[n] = atomicAdd(&bucket_count[ic], 1);
-    slot_a[n] = atomicAdd(&bucket_count[E + ia], 1);
-    atomicAdd(&usage[ic], wc * mask_c);
-    atomicAdd(&usage[E + ia], wa * mask_a);
+  const bool writer = lane == 0 && tok_ok;
+  if (writer) {
+    idx_c[n] = ic;
+    idx_a[n] = ia;
+    scale_c[n] = wc * mask_c;
+    scale_a[n] = wa * mask_a;
+  }
+  if (bucket_count) {
+    // unordered slot claim inside the (group, expert) bucket: ranks inside the CTA from shared-memory
+    // atomics, ONE global atomic per bucket and CTA (16 addresses chip-wide would serialise otherwise)
+    int rc = 0, ra = 0;
+    if (writer) {
+      rc = atomicAdd(&s_cnt[ic], 1);
+      ra = atomicAdd(&s_cnt[E + ia], 1);
+      atomicAdd(&s_use[ic], wc * mask_c);
+      atomicAdd(&s_use[E + ia], wa * mask_a);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * E && s_cnt[threadIdx.x] > 0) {
+      s_base[threadIdx.x] = atomicAdd(&bucket_count[threadIdx.x], s_cnt[threadIdx.x]);
+      atomicAdd(&usage[threadIdx.x], s_use[threadIdx.x]);
+    }
+    __syncthreads();
+    if (writer) {
+      slot_c[n] = s_base[ic] + rc;
+      slot_a[n] = s_base[E + ia] + ra;
+    }
   }
 }
 
@@ -393,7 +435,7 @@ extern "C" int vb_router(const float* cap_feat, const void* cap_feat_bf16, const
       !scale_c || !scale_a || N <= 0 || T <= 0)
     return set_error(VB_ERR_INVALID, "vb_router: null/invalid argument");
   if (E != 4) return set_error(VB_ERR_INVALID, "vb_router: num_experts %d not instantiated (4)", E);
-  launch_k(router_kernel<4>, dim3((N + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+  launch_k(router_kernel<4>, dim3((N + 15) / 16), dim3(512), 0, static_cast<cudaStream_t>(stream), 
       cap_feat, static_cast<const __nv_bfloat16*>(cap_feat_bf16), Wc, bc, ac_logits, hl_logits, hl_ld, ac_ld, e0, e1, e2, tau, N, T, D, idx_c, idx_a, scale_c, scale_a,
       cap_logits_out, bucket_count, usage, slot_c, slot_a);
   return check_launch("vb_router");

@@ -437,7 +437,8 @@ class DiTEngine:
         ops.norm_mod(xcur, kind=1, shift=mod[:, f0:], scale=mod[:, f0 + D:], mod_ld=mld, rows_per_batch=T,
                      eps=1e-6, out_bf16=ws["xf"])
         ops.mark("norm_mod")
-        ops.gemm(ws["xf"], w["final_w"], N=C, bias=w["final_b"], out_f32=ws["v"], out_ld=32)
+        # all 32 (zero-padded) output columns are computed so the chunk takes the coalesced epilogue path
+        ops.gemm(ws["xf"], w["final_w"], bias=w["final_b"], out_f32=ws["v"], out_ld=32)
         ops.mark("gemm:final_w")
         if out_v is not None:
             ops.ntc_to_nct(ws["v"], out_v, ld=32)
