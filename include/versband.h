@@ -42,7 +42,8 @@ enum {
 /* vb_gemm epilogue modes */
 enum {
   VB_EPI_GENERIC = 0,
-  VB_EPI_QKV_ROPE = 1 /* fused q/k rotary + V transpose (flag_large_dit_moe.py:340-352) */
+  VB_EPI_QKV_ROPE = 1, /* fused q/k rotary + V transpose (flag_large_dit_moe.py:340-352) */
+  VB_EPI_ROUTE = 2     /* short-KV attention folded into a gate: see the route_* fields */
 };
 
 int vb_version(void);
@@ -125,6 +126,16 @@ typedef struct vb_gemm_args {
   void* q_out;  /* bf16 [B, heads, T, head_dim] (rotated) */
   void* k_out;  /* bf16 [B, heads, T, head_dim] (rotated) */
   void* vt_out; /* bf16 [B, heads, head_dim, Tp]  (V transposed: PV GEMM's K-major B) */
+  /* ---- VB_EPI_ROUTE: the caption cross-attention that feeds the Band-MoE caption gate
+   * (vocal2music_moe.py:117-131: MultiheadAttention -> gating Linear) collapsed into this GEMM.
+   * B holds, per batch g1 and head h, the 96 rows (scale * K_h W_q,h) (keys beyond the text length are
+   * zero rows whose bias is -1e30), so that acc[m, h*96 + j] + bias is the attention score of token m
+   * and key j; the epilogue takes the softmax over the 96 columns of a head and contracts it with
+   * route_vg[g1][h][j][0..3] = V_h[j,:] . (W_gate W_o)[e, head h] — i.e. it emits, per token and head,
+   * the head's contribution to the 4 gate logits: out_f32[(g1*M + m) * out_ld + h*4 + e].
+   * Requires N % 96 == 0 (N = heads * 96), batches in G1 (M rows each), bias with bias_g1 = N. */
+  const float* route_vg;
+  int64_t route_vg_g1; /* elements between batches of route_vg (heads * 96 * 4) */
 } vb_gemm_args;
 
 int vb_gemm(const vb_gemm_args* args, void* stream);
@@ -226,11 +237,18 @@ int vb_router(const float* cap_feat, const void* cap_feat_bf16, const float* Wc,
               int ac_ld, const float* hl_logits, int hl_ld, const float* e0, const float* e1, const float* e2, float tau,
               int N, int T, int D, int E, int32_t* idx_c, int32_t* idx_a, float* scale_c,
               float* scale_a, float* cap_logits_out, int32_t* bucket_count, float* usage,
-              int32_t* slot_c, int32_t* slot_a, void* stream);
-/* Features may be fp32 (cap_feat) or bf16 (cap_feat_bf16). With bucket_count != NULL the router also
+              int32_t* slot_c, int32_t* slot_a, const float* cap_partial, int n_heads, void* stream);
+/* Features may be fp32 (cap_feat) or bf16 (cap_feat_bf16); or, with cap_partial != NULL, the caption
+ * gate logits are bc + the sum over heads (in head order) of cap_partial[n][h][E] written by a
+ * VB_EPI_ROUTE GEMM and cap_feat / Wc are not read. With bucket_count != NULL the router also
  * claims an (unordered) slot per (token, group) in its expert bucket with atomics; vb_moe_finalize
  * turns the counts into 128-row-padded bucket starts / tile table / lb loss (and re-zeroes them),
  * vb_moe_scatter writes row_map/row_scale and gathers the activation rows into bucket order. */
+/* Step-invariant operands of a VB_EPI_ROUTE GEMM from the MoE cross-attention's fp32 k|v projection
+ * kv [B*L, 2*H*hd] (L <= 96): bias_s [B, H, 96] = <k_h[j], bq_h> (-1e30 for j >= L) and
+ * vg [B, H, 96, 4] = <v_h[j], capg_w[e, head h]> (capg_w [4, H*hd] = W_gate W_out_proj). */
+int vb_route_prepare(const float* kv, int B, int L, int H, int hd, const float* bq, const float* capg_w,
+                     float* bias_s, float* vg, void* stream);
 int vb_moe_finalize(int32_t* bucket_count, float* usage, int E, int32_t* bucket_start, int32_t* row_map,
                     float* row_scale, int32_t* tile_group, int32_t* m_tiles_used, int max_rows,
                     float* lb_out, void* stream);

@@ -37,7 +37,7 @@ for _ in range(5):
     g.replay()
 torch.cuda.synchronize()
 rec = buf.cpu()
-names = ["proj_in", "t_w0", "t_w2", "ada"] + [f"b{k}.{n}" for k in range(4) for n in ("wqkv", "wo", "mq", "w13", "w2", "f13", "f2")] + ["final"]
+names = ["proj_in", "t_w0", "t_w2", "ada"] + [f"b{k}.{n}" for k in range(4) for n in ("wqkv", "wo", "route", "w13", "w2", "f13", "f2")] + ["final"]
 print("times in us; entry->pro = prologue, ->data = first operands, ->mma = first tile mainloop issue, "
       "->acc = accumulator ready, ->epi = first tile epilogue, ->exit; span = first entry to last exit over CTAs")
 prev_end = None

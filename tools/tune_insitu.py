@@ -50,7 +50,7 @@ def measure():
 D, H3, Fh = eng.D, 3 * eng.D, None
 sigs = {}
 for k, blk in enumerate(eng.w["blocks"][:1]):
-    for name in ("wqkv", "wo", "mq_w", "w13", "w2", "f13", "f2"):
+    for name in ("wqkv", "wo", "w13", "w2", "f13", "f2"):
         wt = blk[name]
         N, K = int(wt.shape[-2]), int(wt.shape[-1])
         grouped = 1 if name in ("w13", "w2") else 0

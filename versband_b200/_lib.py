@@ -38,6 +38,7 @@ class GemmArgs(C.Structure):
         ("act_out", c_i32), ("act_out_slope", c_f32), ("out_scale", c_f32),
         ("rope_cs", c_ptr), ("T", c_i32), ("heads", c_i32), ("head_dim", c_i32), ("Tp", c_i32), ("qkv_sec0", c_i32),
         ("q_out", c_ptr), ("k_out", c_ptr), ("vt_out", c_ptr),
+        ("route_vg", c_ptr), ("route_vg_g1", c_i64),
     ]
 
 
@@ -101,7 +102,8 @@ def _declare(l: C.CDLL) -> None:
         "vb_mean_tokens": [P, I, I, I, P, P],
         "vb_timestep_embed": [P, P, P, P, I, I, P],
         "vb_linear_small": [P, L, P, P, P, I, I, I, P],
-        "vb_router": [P, P, P, P, P, I, P, I, P, P, P, F, I, I, I, I, P, P, P, P, P, P, P, P, P, P],
+        "vb_router": [P, P, P, P, P, I, P, I, P, P, P, F, I, I, I, I, P, P, P, P, P, P, P, P, P, P, I, P],
+        "vb_route_prepare": [P, I, I, I, I, P, P, P, P, P],
         "vb_moe_finalize": [P, P, I, P, P, P, P, P, I, P, P],
         "vb_moe_dispatch": [P, P, P, P, P, P, P, P, P, P, I, I, I, P, P, P, P, P, P, I, P, P],
         "vb_moe_scatter": [P, P, P, P, P, P, P, I, I, I, P, P, P, P, P],

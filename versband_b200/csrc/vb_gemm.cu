@@ -160,6 +160,14 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
       fprintf(stderr, "vb_gemm M=%d N=%d K=%d G=%d grouped=%d tf32=%d kpt=%d -> bn=%d cta2=%d\n", a->M, a->N, a->K, G,
               a->tile_group ? 1 : 0, (int)tf32, kpt, bn, (int)use2);
   }
+  if (a->mode == VB_EPI_ROUTE) {
+    if (!a->route_vg || !a->bias || !a->out_f32 || a->N % 96 != 0 || a->bias_g1 % 4 != 0 || a->out_ld % 4 != 0 ||
+        a->tile_group || a->G2 != 1 || (reinterpret_cast<uintptr_t>(a->bias) & 15) ||
+        (reinterpret_cast<uintptr_t>(a->route_vg) & 15) || (reinterpret_cast<uintptr_t>(a->out_f32) & 15))
+      return set_error(VB_ERR_INVALID, "vb_gemm: bad ROUTE arguments (N = heads*96, bias/route_vg/out_f32 16-byte aligned)");
+    bn = 96;
+    use2 = false;
+  }
   if (a->mode == VB_EPI_QKV_ROPE) {
     if (!a->k_out || !a->vt_out || a->head_dim % 32 != 0 ||
         a->N != (3 - a->qkv_sec0) * a->heads * a->head_dim || a->qkv_sec0 < 0 || a->qkv_sec0 > 1 || (a->qkv_sec0 == 0 && !a->q_out) || a->T <= 0 || a->M % a->T != 0)
@@ -209,6 +217,7 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
   p.q_out = static_cast<__nv_bfloat16*>(a->q_out);
   p.k_out = static_cast<__nv_bfloat16*>(a->k_out);
   p.vt_out = static_cast<__nv_bfloat16*>(a->vt_out);
+  p.route_vg = a->route_vg; p.route_vg_g1 = a->route_vg_g1;
   if (a->mode == VB_EPI_GENERIC) {
     if (!a->out_f32 && !a->out_bf16)
       return set_error(VB_ERR_INVALID, "vb_gemm: no output pointer");
@@ -236,7 +245,8 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
   {
     const bool lrelu_only = (a->act == VB_ACT_NONE || a->act == VB_ACT_LRELU) &&
                             (a->act_out == VB_ACT_NONE || a->act_out == VB_ACT_LRELU);
-    if (a->mode == VB_EPI_QKV_ROPE) ec = EC_QKV;
+    if (a->mode == VB_EPI_ROUTE) ec = EC_ROUTE;
+    else if (a->mode == VB_EPI_QKV_ROPE) ec = EC_QKV;
     else if (a->swiglu && a->alpha == 1.f && !a->out_f32) ec = EC_SWIGLU;
     else if (!a->swiglu && a->alpha == 1.f && lrelu_only) ec = EC_LINEAR;
   }
@@ -294,6 +304,7 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
     grid = clusters * 2;
   }
   switch (ec) {
+    case EC_ROUTE: return launch_gemm_class<EC_ROUTE>(bn, tf32, use2, tmA, tmB, p, grid, stream);
     case EC_QKV: return launch_gemm_class<EC_QKV>(bn, tf32, use2, tmA, tmB, p, grid, stream);
     case EC_SWIGLU: return launch_gemm_class<EC_SWIGLU>(bn, tf32, use2, tmA, tmB, p, grid, stream);
     case EC_LINEAR: return launch_gemm_class<EC_LINEAR>(bn, tf32, use2, tmA, tmB, p, grid, stream);

@@ -490,6 +490,50 @@ __device__ __forceinline__ void epilogue_qkv(const GemmKParams& p, const uint32_
   }
 }
 
+// ------------------------------------------------------------------ ROUTE epilogue (BN = 96 = one head)
+// Thread = accumulator row (token). Online softmax over the head's 96 score columns (3 TMEM chunks),
+// contracted on the fly with route_vg[batch][head][j][0..3]; one float4 per (token, head).
+__device__ __forceinline__ void epilogue_route_tile(const GemmKParams& p, uint32_t tmem_d, int m, int n_tile, int g1) {
+  const float4* bias4 = reinterpret_cast<const float4*>(p.bias + g1 * p.bias_g1 + n_tile * 96);
+  const float4* vg = reinterpret_cast<const float4*>(p.route_vg + g1 * p.route_vg_g1) + n_tile * 96;
+  float mx = -1e30f, sum = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int c = 0; c < 96; c += 32) {
+    uint32_t raw[32];
+    tmem_ld32(tmem_d + c, raw);
+    tmem_ld_wait();
+    float v[32];
+    float cmax = -1e30f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b4 = __ldg(bias4 + (c >> 2) + j);
+      v[4 * j] = __uint_as_float(raw[4 * j]) + b4.x;
+      v[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) + b4.y;
+      v[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) + b4.z;
+      v[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) + b4.w;
+      cmax = fmaxf(cmax, fmaxf(fmaxf(v[4 * j], v[4 * j + 1]), fmaxf(v[4 * j + 2], v[4 * j + 3])));
+    }
+    const float m_new = fmaxf(mx, cmax);
+    const float resc = __expf(mx - m_new);
+    sum *= resc; acc.x *= resc; acc.y *= resc; acc.z *= resc; acc.w *= resc;
+    mx = m_new;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float pj = __expf(v[j] - mx);
+      const float4 g = __ldg(vg + c + j);
+      sum += pj;
+      acc.x = fmaf(pj, g.x, acc.x); acc.y = fmaf(pj, g.y, acc.y);
+      acc.z = fmaf(pj, g.z, acc.z); acc.w = fmaf(pj, g.w, acc.w);
+    }
+  }
+  if (m < p.M) {
+    const float inv = 1.f / sum;
+    *reinterpret_cast<float4*>(p.out_f32 + ((long long)g1 * p.M + m) * p.out_ld + n_tile * 4) =
+        make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+  }
+}
+
 // The chunk loop shared by the three kernels. Eight epilogue warps: two per TMEM lane quadrant, the
 // pair splitting the tile's 32-column chunks even/odd (`c_first` = 0 or 32) — a single warp per
 // scheduler runs the chunk body latency-bound, so warps, not bytes, set the pace.
@@ -685,6 +729,11 @@ vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (BN == 32 && acc != wset) { ++local; continue; }
       const int m_base = tc.m_tile * BM + q * 32, n0 = tc.n_tile * BN;
       const uint32_t tmem_d = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+      if (EC == EC_ROUTE) {
+        mbar_wait(&tmem_full_bar[acc], (local >> 1) & 1);
+        tc_fence_after();
+        if (wset == 0) epilogue_route_tile(p, tmem_d, m_base + lane, tc.n_tile, tc.g1);
+      } else
       VB_EPILOGUE_TILE(BN, n0, tc.g1, tc.g2, tc.tg,
                        mbar_wait(&tmem_full_bar[acc], (local >> 1) & 1); if (local == 0 && threadIdx.x == 64) VB_TRACE(4))
       tc_fence_before();
@@ -1026,6 +1075,11 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKPa
 template <int EC>
 int launch_gemm_class(int bn, bool tf32, bool use2, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p,
                       int grid_, cudaStream_t stream) {
+  if constexpr (EC == EC_ROUTE) {
+    if (use2 || bn != 96) return set_error(VB_ERR_INVALID, "vb_gemm: the ROUTE epilogue runs on 128x96 tiles only");
+    return tf32 ? launch<96, true, EC>(tmA, tmB, p, dim3(grid_, 1, 1), stream)
+                : launch<96, false, EC>(tmA, tmB, p, dim3(grid_, 1, 1), stream);
+  } else {
   if (use2) {
     if (bn == 256) return tf32 ? launch2<256, true, EC>(tmA, tmB, p, grid_, stream) : launch2<256, false, EC>(tmA, tmB, p, grid_, stream);
     if (bn == 192) return tf32 ? launch2<192, true, EC>(tmA, tmB, p, grid_, stream) : launch2<192, false, EC>(tmA, tmB, p, grid_, stream);
@@ -1040,6 +1094,7 @@ int launch_gemm_class(int bn, bool tf32, bool use2, const CUtensorMap& tmA, cons
     case 192: return tf32 ? launch<192, true, EC>(tmA, tmB, p, grid, stream) : launch<192, false, EC>(tmA, tmB, p, grid, stream);
     case 256: return tf32 ? launch<256, true, EC>(tmA, tmB, p, grid, stream) : launch<256, false, EC>(tmA, tmB, p, grid, stream);
     default: return set_error(VB_ERR_INVALID, "vb_gemm: unsupported N tile %d", bn);
+  }
   }
 }
 

@@ -24,6 +24,7 @@ enum EpiClass {
   EC_LINEAR = 1,  // bias, {none, leaky-relu} activations, row_scale/row_map, gate, residual, accumulate, fp32 and/or operand-slot output
   EC_SWIGLU = 2,  // silu(w1 x) * (w3 x) pairs -> operand-slot output (expert FFN first layers)
   EC_QKV = 3,     // bias + rotary + head-major q/k and transposed v stores
+  EC_ROUTE = 4,   // per-head softmax over 96 score columns contracted with V.(gate) -> gate-logit partials
 };
 
 struct GemmKParams {
@@ -67,6 +68,9 @@ struct GemmKParams {
   __nv_bfloat16* q_out;
   __nv_bfloat16* k_out;
   __nv_bfloat16* vt_out;
+  // route
+  const float* route_vg;
+  long long route_vg_g1;
   unsigned long long* trace;  // debug (vb_set_gemm_trace): 8 x u64 per CTA, see tools/trace_gemm.py
 };
 

@@ -47,7 +47,7 @@ __global__ void router_kernel(const float* __restrict__ cap_feat, const __nv_bfl
                               float* __restrict__ scale_c, float* __restrict__ scale_a,
                               float* __restrict__ cap_logits_out, int* __restrict__ bucket_count,
                               float* __restrict__ usage, int* __restrict__ slot_c,
-                              int* __restrict__ slot_a) {
+                              int* __restrict__ slot_a, const float* __restrict__ cap_partial, int n_heads) {
   pdl_sync();
   __shared__ int s_cnt[2 * E], s_base[2 * E];
   __shared__ float s_use[2 * E];
@@ -60,7 +60,15 @@ __global__ void router_kernel(const float* __restrict__ cap_feat, const __nv_bfl
   float acc[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) acc[e] = 0.f;
-  if ((D & 127) == 0) {  // 16-byte loads: lane owns 4 consecutive features per 128-feature slab
+  if (cap_partial) {
+    // per-head contributions from the VB_EPI_ROUTE GEMM, summed in head order (deterministic)
+    static_assert(E == 4, "cap_partial layout is [N, heads, 4]");
+    const float4* pp = reinterpret_cast<const float4*>(cap_partial) + (long long)n * n_heads;
+    for (int h = 0; h < n_heads; ++h) {
+      const float4 v = __ldg(pp + h);
+      acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+    }
+  } else if ((D & 127) == 0) {  // 16-byte loads: lane owns 4 consecutive features per 128-feature slab
     for (int d = lane * 4; d < D; d += 128) {
       float4 xv;
       if (cap_feat_bf) {
@@ -97,8 +105,10 @@ __global__ void router_kernel(const float* __restrict__ cap_feat, const __nv_bfl
       for (int e = 0; e < E; ++e) acc[e] = fmaf(xv, __ldg(Wc + (long long)e * D + d), acc[e]);
     }
   }
+  if (!cap_partial) {
 #pragma unroll
-  for (int e = 0; e < E; ++e) acc[e] = wsum(acc[e]);
+    for (int e = 0; e < E; ++e) acc[e] = wsum(acc[e]);
+  }
   // The three Gumbel-softmaxes of this token run in parallel on lanes 0..E-1 (caption gate),
   // E..2E-1 (acoustic gate) and 2E, 2E+1 (group gate); every lane of a gate gathers the gate's
   // values with shuffles and reduces them in index order, i.e. the same arithmetic as a serial loop.
@@ -410,6 +420,37 @@ __global__ void moe_dispatch_kernel(const int* __restrict__ idx_c, const int* __
   for (int k = lane; k < row_bytes / 16; k += 32) dst[k] = src[k];
 }
 
+
+// Step-invariant operands of the VB_EPI_ROUTE GEMM (include/versband.h): one CTA per (batch, head),
+// thread j = key. kv = [B*L, 2*H*hd] fp32 rows (k | v) of the MoE cross-attention's in-projection.
+//   bias_s[b][h][j] = <k_h[j], bq_h>            (bq already carries 1/sqrt(hd)); -1e30 for j >= L
+//   vg[b][h][j][e]  = <v_h[j], capg_w[e][h*hd : (h+1)*hd]>;                        0 for j >= L
+__global__ void route_prepare_kernel(const float* __restrict__ kv, int L, int H, int hd,
+                                     const float* __restrict__ bq, const float* __restrict__ capg_w,
+                                     float* __restrict__ bias_s, float* __restrict__ vg) {
+  pdl_sync();
+  const int h = blockIdx.x, b = blockIdx.y, j = threadIdx.x;  // blockDim.x == 96
+  const int D = H * hd;
+  float s = -1e30f;
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (j < L) {
+    const float* kr = kv + ((long long)b * L + j) * 2 * D + h * hd;
+    const float* vr = kr + D;
+    s = 0.f;
+    for (int d = 0; d < hd; ++d) {
+      s = fmaf(kr[d], bq[h * hd + d], s);
+      const float v = vr[d];
+      g.x = fmaf(v, capg_w[0 * D + h * hd + d], g.x);
+      g.y = fmaf(v, capg_w[1 * D + h * hd + d], g.y);
+      g.z = fmaf(v, capg_w[2 * D + h * hd + d], g.z);
+      g.w = fmaf(v, capg_w[3 * D + h * hd + d], g.w);
+    }
+  }
+  const long long o = ((long long)b * H + h) * 96 + j;
+  bias_s[o] = s;
+  reinterpret_cast<float4*>(vg)[o] = g;
+}
+
 }  // namespace vb
 
 using namespace vb;
@@ -429,16 +470,26 @@ extern "C" int vb_router(const float* cap_feat, const void* cap_feat_bf16, const
                          const float* e0, const float* e1, const float* e2, float tau, int N, int T, int D, int E,
                          int32_t* idx_c, int32_t* idx_a, float* scale_c, float* scale_a,
                          float* cap_logits_out, int32_t* bucket_count, float* usage, int32_t* slot_c,
-                         int32_t* slot_a, void* stream) {
+                         int32_t* slot_a, const float* cap_partial, int n_heads, void* stream) {
   vb::ProfScope prof_scope(vb::PK_ROUTER, stream);
-  if ((!cap_feat && !cap_feat_bf16) || !Wc || !bc || !ac_logits || !hl_logits || !e0 || !e1 || !e2 || !idx_c || !idx_a ||
+  if ((!cap_feat && !cap_feat_bf16 && !cap_partial) || (!Wc && !cap_partial) || !bc || !ac_logits || !hl_logits || !e0 || !e1 || !e2 || !idx_c || !idx_a ||
       !scale_c || !scale_a || N <= 0 || T <= 0)
     return set_error(VB_ERR_INVALID, "vb_router: null/invalid argument");
   if (E != 4) return set_error(VB_ERR_INVALID, "vb_router: num_experts %d not instantiated (4)", E);
   launch_k(router_kernel<4>, dim3((N + 15) / 16), dim3(512), 0, static_cast<cudaStream_t>(stream), 
       cap_feat, static_cast<const __nv_bfloat16*>(cap_feat_bf16), Wc, bc, ac_logits, hl_logits, hl_ld, ac_ld, e0, e1, e2, tau, N, T, D, idx_c, idx_a, scale_c, scale_a,
-      cap_logits_out, bucket_count, usage, slot_c, slot_a);
+      cap_logits_out, bucket_count, usage, slot_c, slot_a, cap_partial, n_heads);
   return check_launch("vb_router");
+}
+
+extern "C" int vb_route_prepare(const float* kv, int B, int L, int H, int hd, const float* bq, const float* capg_w,
+                                float* bias_s, float* vg, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_ROUTER, stream);
+  if (!kv || !bq || !capg_w || !bias_s || !vg || B <= 0 || L <= 0 || L > 96 || H <= 0 || hd <= 0)
+    return set_error(VB_ERR_INVALID, "vb_route_prepare: bad arguments (1 <= L <= 96)");
+  launch_k(route_prepare_kernel, dim3(H, B), dim3(96), 0, static_cast<cudaStream_t>(stream), kv, L, H, hd, bq, capg_w,
+           bias_s, vg);
+  return check_launch("vb_route_prepare");
 }
 
 extern "C" int vb_moe_sort(const int32_t* idx_c, const int32_t* idx_a, const float* scale_c,

@@ -58,11 +58,17 @@ class DiTCond:
     # per block, bf16: text cross-attention K [B,H,L,hd] and V^T [B,H,hd,Lp]; same for the MoE MHA
     k_y: List[torch.Tensor] = field(default_factory=list)
     vt_y: List[torch.Tensor] = field(default_factory=list)
-    k_m: List[torch.Tensor] = field(default_factory=list)
-    vt_m: List[torch.Tensor] = field(default_factory=list)
+    # per block, the MoE caption cross-attention folded into its gate (include/versband.h: VB_EPI_ROUTE):
+    # wk_m [B, H*96, D] operand dtype (scale * K_h W_q,h), bs_m fp32 [B, H, 96], vg_m fp32 [B, H, 96, E]
+    wk_m: List[torch.Tensor] = field(default_factory=list)
+    bs_m: List[torch.Tensor] = field(default_factory=list)
+    vg_m: List[torch.Tensor] = field(default_factory=list)
+
+    _LISTS = ("k_y", "vt_y", "wk_m", "bs_m", "vg_m")
 
     def tensors(self) -> List[torch.Tensor]:
-        return [self.acoustic, self.ac_logits, self.caption, self.cap_emb, *self.k_y, *self.vt_y, *self.k_m, *self.vt_m]
+        return [self.acoustic, self.ac_logits, self.caption, self.cap_emb,
+                *[t for name in self._LISTS for t in getattr(self, name)]]
 
     @staticmethod
     def cat(conds: "List[DiTCond]") -> "DiTCond":
@@ -74,7 +80,7 @@ class DiTCond:
                       ac_logits=torch.cat([c.ac_logits for c in conds], 0),
                       caption=torch.cat([c.caption for c in conds], 0),
                       cap_emb=torch.cat([c.cap_emb for c in conds], 0))
-        for name in ("k_y", "vt_y", "k_m", "vt_m"):
+        for name in DiTCond._LISTS:
             for k in range(len(c0.k_y)):
                 getattr(out, name).append(torch.cat([getattr(c, name)[k] for c in conds], 0))
         return out
@@ -99,6 +105,7 @@ class DiTEngine:
         self.kq = 64 if precision == "bf16" else 32        # elements per 128-byte k-block
         self.C, self.D, self.depth, self.H, self.E = in_channels, hidden_size, depth, num_heads, num_experts
         self.hd = hidden_size // num_heads
+        self.LK = 96  # key slots per head of the folded caption cross-attention (VB_EPI_ROUTE tile width)
         self.ori_dim, self.max_len, self.eps = ori_dim, max_len, norm_eps
         self.temperature = temperature
         self.dev = torch.device(device)
@@ -158,7 +165,6 @@ class DiTEngine:
             b["gate"] = g(a + "gate")
             b["attn_norm"], b["ffn_norm"], b["y_norm"] = g(p + "attention_norm.weight"), g(p + "ffn_norm.weight"), g(p + "attention_y_norm.weight")
             ipw, ipb = g(f + "cross_attention.in_proj_weight"), g(f + "cross_attention.in_proj_bias")
-            b["mq_w"], b["mq_b"] = _bf(ipw[:D]), ipb[:D].contiguous()
             b["mkv_w"], b["mkv_b"] = _bf(ipw[D:]), ipb[D:].contiguous()
             # caption gate folded through the MHA out-projection (its only consumer, vocal2music_moe.py:122,141):
             # logits = Wg (Wo ctx + bo) + bg = (Wg Wo) ctx + (Wg bo + bg), all in fp32
@@ -166,6 +172,14 @@ class DiTEngine:
             wg, bg = g(f + "caption_gating_network.weight"), g(f + "caption_gating_network.bias")
             b["capg_w"] = (wg.double() @ wo_m.double()).float().contiguous()
             b["capg_b"] = (wg.double() @ bo_m.double() + bg.double()).float().contiguous()
+            # ... and the attention itself folded into one GEMM per step: scores = xm . (scale K_h W_q,h)^T.
+            # mq_wT[h] = (scale W_q,h)^T  [D_in, hd (padded to the k-block)]: B operand of the per-clip WK GEMM
+            sc = 1.0 / math.sqrt(self.hd)
+            kpad = (self.hd + self.kq - 1) // self.kq * self.kq
+            wqT = torch.zeros(self.H, D, kpad, device=dev)
+            wqT[:, :, : self.hd] = (ipw[:D] * sc).view(self.H, self.hd, D).permute(0, 2, 1)
+            b["mq_wT"] = _bf(wqT)
+            b["mq_bs"] = (ipb[:D] * sc).contiguous()
             w13, w2 = [], []
             for grp in ("caption_experts", "acoustic_experts"):
                 for e in range(E):
@@ -214,7 +228,7 @@ class DiTEngine:
             mod=z(B, self.mod_ld), hl=z(B, 2 * self.depth),
             xa=z(N, D, dt=AD), q=z(B, H, T, hd, dt=BF), k=z(B, H, T, hd, dt=BF), vt=z(B, H, hd, Tp, dt=BF),
             oa=z(N, D, dt=AD),
-            xm=z(N, D, dt=AD), qm=z(N, D, dt=BF), ctx=z(N, D, dt=BF),
+            xm=z(N, D, dt=AD), cap_part=z(N, self.H, E),
             idx_c=z(N, dt=torch.int32), idx_a=z(N, dt=torch.int32), scale_c=z(N), scale_a=z(N),
             cap_logits=z(N, E), bucket_count=z(self.depth, 2 * E, dt=torch.int32), usage=z(self.depth, 2 * E), bucket_start=z(2 * E, dt=torch.int32),
             slot_c=z(N, dt=torch.int32), slot_a=z(N, dt=torch.int32),
@@ -291,14 +305,28 @@ class DiTEngine:
             b = w["blocks"][k]
             # K / V^T of the two short-KV attentions, written head-major by the k|v GEMM epilogue
             ops.norm_mod(cap.view(B * L, D), kind=0, w=b["y_norm"], eps=self.eps, out_bf16=y16)
-            for src, wt, bias, kl, vl in ((y16, b["wkvy"], None, cond.k_y, cond.vt_y),
-                                          (cap_bf, b["mkv_w"], b["mkv_b"], cond.k_m, cond.vt_m)):
-                kk = torch.empty(B, H, L, hd, device=dev, dtype=BF)
-                vt = torch.zeros(B, H, hd, Lp, device=dev, dtype=BF)
-                ops.gemm(src, wt, mode=ops.EPI_QKV_ROPE, qkv_sec0=1, bias=bias, T=L, heads=H, head_dim=hd, Tp=Lp,
-                         k_out=kk, vt_out=vt)
-                kl.append(kk)
-                vl.append(vt)
+            kk = torch.empty(B, H, L, hd, device=dev, dtype=BF)
+            vt = torch.zeros(B, H, hd, Lp, device=dev, dtype=BF)
+            ops.gemm(y16, b["wkvy"], mode=ops.EPI_QKV_ROPE, qkv_sec0=1, T=L, heads=H, head_dim=hd, Tp=Lp,
+                     k_out=kk, vt_out=vt)
+            cond.k_y.append(kk)
+            cond.vt_y.append(vt)
+            # MoE caption cross-attention (vocal2music_moe.py:117-131), folded: fp32 k|v projection, then
+            # WK[b,h] = K_h (scale W_q,h) as one batched GEMM, score bias and V.(W_gate W_o) by vb_route_prepare
+            kvf = torch.empty(B * L, 2 * D, device=dev, dtype=F32)
+            kvo = kvf if self.adt == F32 else torch.empty(B * L, 2 * D, device=dev, dtype=BF)
+            ops.gemm(cap_bf, b["mkv_w"], bias=b["mkv_b"], out_f32=kvf, out_ld=2 * D,
+                     out_bf16=None if self.adt == F32 else kvo, outb_ld=2 * D)
+            wk = torch.zeros(B, H * self.LK, D, device=dev, dtype=self.adt)
+            ops.gemm(kvo[:, :D].view(B, L, H, hd).permute(0, 2, 1, 3), b["mq_wT"], M=L, N=D, G1=H, G2=B,
+                     a_c2=(1, 0), a_c3=(0, 1), b_c2=(1, 0, 0), out_bf16=wk, outb_ld=D,
+                     outb_g=(self.LK * D, H * self.LK * D))
+            bs = torch.empty(B, H, self.LK, device=dev, dtype=F32)
+            vg = torch.empty(B, H, self.LK, self.E, device=dev, dtype=F32)
+            ops.route_prepare(kvf, B, L, H, hd, b["mq_bs"], b["capg_w"], bs, vg)
+            cond.wk_m.append(wk)
+            cond.bs_m.append(bs)
+            cond.vg_m.append(vg)
         return cond
 
     @torch.no_grad()
@@ -388,17 +416,17 @@ class DiTEngine:
             ops.norm_mod(hbuf, kind=0, w=b["ffn_norm"], shift=sh_mlp, scale=sc_mlp, mod_ld=mld,
                          rows_per_batch=T, eps=self.eps, out_bf16=ws["xm"])
             ops.mark("norm_mod")
-            ops.gemm(ws["xm"], b["mq_w"], bias=b["mq_b"], out_bf16=ws["qm"], outb_ld=D)
-            ops.mark("gemm:mq_w")
-            ops.attn_fused(ws["qm"], (D, hd, T * D), B=B, T=T, H=H, hd=hd, scale=scale, k_text=cond.k_m[k],
-                           vt_text=cond.vt_m[k], L=L, Lp=cond.vt_m[k].shape[-1], out_bf16=ws["ctx"])
-            ops.mark("attn_fused")
+            # caption gate: per-head softmax(xm . WK^T + bias) . VG inside one GEMM epilogue
+            ops.gemm(ws["xm"].view(B, T, D), cond.wk_m[k], M=T, G1=B, a_c2=(1, 0), b_c2=(1, 0, 0), mode=ops.EPI_ROUTE,
+                     bias=cond.bs_m[k], bias_g1=H * self.LK, route_vg=cond.vg_m[k], route_vg_g1=H * self.LK * E,
+                     out_f32=ws["cap_part"], out_ld=H * E)
+            ops.mark("gemm:route")
             e0, e1, e2 = expo[k]
-            ops.router(ws["ctx"], b["capg_w"], b["capg_b"], cond.ac_logits[:, k * E:], self.depth * E,
+            ops.router(None, None, b["capg_b"], cond.ac_logits[:, k * E:], self.depth * E,
                        hl_t[:, 2 * k:], 2 * self.depth, e0, e1, e2, float(self.temperature), N, T,
                        ws["idx_c"], ws["idx_a"], ws["scale_c"], ws["scale_a"],
                        ws["cap_logits"] if want_aux else None, ws["bucket_count"][k], ws["usage"][k],
-                       ws["slot_c"], ws["slot_a"])
+                       ws["slot_c"], ws["slot_a"], cap_partial=ws["cap_part"])
             ops.mark("router")
             if self.depth > 1:
                 kn = (k + 1) % self.depth  # the dispatch of block k zeroes the counters of block k+1

@@ -11,7 +11,7 @@ from . import _lib
 from ._lib import AttnArgs, GemmArgs
 
 ACT_NONE, ACT_SILU, ACT_LRELU, ACT_GELU, ACT_TANH = 0, 1, 2, 3, 4
-EPI_GENERIC, EPI_QKV_ROPE = 0, 1
+EPI_GENERIC, EPI_QKV_ROPE, EPI_ROUTE = 0, 1, 2
 
 
 def _stream() -> C.c_void_p:
@@ -64,7 +64,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: Optional[int] = None, N: Option
          out_bf16: Optional[torch.Tensor] = None, outb_ld: int = 0, outb_g=(0, 0),
          act_out: int = ACT_NONE, act_out_slope: float = 0.0, out_scale: float = 1.0,
          rope_cs: Optional[torch.Tensor] = None, T: int = 0, heads: int = 0, head_dim: int = 0,
-         Tp: int = 0, q_out=None, k_out=None, vt_out=None, qkv_sec0: int = 0) -> None:
+         Tp: int = 0, q_out=None, k_out=None, vt_out=None, qkv_sec0: int = 0,
+         route_vg: Optional[torch.Tensor] = None, route_vg_g1: int = 0) -> None:
     """D = epilogue(A @ B^T) on the tcgen05 GEMM (see include/versband.h: vb_gemm).
 
     `a` is a bf16 view of up to 4 dims [c3, c2, rows, k]; `b` a bf16 view [group, n, k].
@@ -115,6 +116,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: Optional[int] = None, N: Option
     args.rope_cs, args.T, args.heads, args.head_dim, args.Tp = _ptr(rope_cs), T, heads, head_dim, Tp
     args.q_out, args.k_out, args.vt_out = _ptr(q_out), _ptr(k_out), _ptr(vt_out)
     args.qkv_sec0 = qkv_sec0
+    _check_f32(route_vg, "route_vg")
+    args.route_vg, args.route_vg_g1 = _ptr(route_vg), route_vg_g1
     _lib.check(_lib.lib().vb_gemm(C.byref(args), _stream()), "vb_gemm")
 
 
@@ -158,13 +161,22 @@ def linear_small(x, W, bias, out) -> None:
 
 
 def router(cap_feat, Wc, bc, ac_logits, ac_ld, hl_logits, hl_ld, e0, e1, e2, tau, N, T, idx_c, idx_a,
-           scale_c, scale_a, cap_logits_out=None, bucket_count=None, usage=None, slot_c=None, slot_a=None) -> None:
-    f32 = cap_feat if cap_feat.dtype == torch.float32 else None
-    b16 = cap_feat if cap_feat.dtype == torch.bfloat16 else None
+           scale_c, scale_a, cap_logits_out=None, bucket_count=None, usage=None, slot_c=None, slot_a=None,
+           cap_partial=None) -> None:
+    """cap_feat: fp32/bf16 caption-attention features [N, D] (gate = Wc . feat + bc), or None with
+    cap_partial [N, heads, E] = per-head gate contributions from a VB_EPI_ROUTE GEMM."""
+    f32 = cap_feat if cap_feat is not None and cap_feat.dtype == torch.float32 else None
+    b16 = cap_feat if cap_feat is not None and cap_feat.dtype == torch.bfloat16 else None
+    D = cap_feat.shape[-1] if cap_feat is not None else 0
+    _check_f32(cap_partial, "cap_partial")
     _call("vb_router", _ptr(f32), _ptr(b16), _ptr(Wc), _ptr(bc), _ptr(ac_logits), ac_ld, _ptr(hl_logits), hl_ld,
-          _ptr(e0), _ptr(e1), _ptr(e2), tau, N, T, cap_feat.shape[-1], Wc.shape[0], _ptr(idx_c), _ptr(idx_a),
+          _ptr(e0), _ptr(e1), _ptr(e2), tau, N, T, D, bc.shape[0], _ptr(idx_c), _ptr(idx_a),
           _ptr(scale_c), _ptr(scale_a), _ptr(cap_logits_out), _ptr(bucket_count), _ptr(usage), _ptr(slot_c),
-          _ptr(slot_a))
+          _ptr(slot_a), _ptr(cap_partial), cap_partial.shape[1] if cap_partial is not None else 0)
+
+
+def route_prepare(kv, B, L, H, hd, bq, capg_w, bias_s, vg) -> None:
+    _call("vb_route_prepare", _ptr(kv), B, L, H, hd, _ptr(bq), _ptr(capg_w), _ptr(bias_s), _ptr(vg))
 
 
 def moe_finalize(bucket_count, usage, E, bucket_start, row_map, row_scale, tile_group, m_tiles_used, max_rows,
