@@ -193,7 +193,8 @@ class DiTEngine:
                 sl = slice(band * e, band * (e + 1))
                 f13.append(torch.stack([w1[:, sl], w3[:, sl]], 1).reshape(2 * w1.shape[0], band))
                 f2.append(g(f"{f}freq_experts.{e}.w2.weight")[sl, :])
-            b["f13"], b["f2"] = _bf(torch.stack(f13, 0)), _bf(torch.stack(f2, 0))  # [E,2Fh,band], [E,band,Fh]
+            f13w = torch.stack(f13, 0)
+            b["f13"], b["f2"] = _bf(torch.cat([f13w, f13w], -1)), _bf(torch.stack(f2, 0))  # [E,2Fh,2*band], [E,band,Fh]
             blocks.append(b)
         self.Fh = blocks[0]["w2"].shape[-1]
         self.band = band
@@ -234,7 +235,7 @@ class DiTEngine:
             slot_c=z(N, dt=torch.int32), slot_a=z(N, dt=torch.int32),
             row_map=z(max_rows, dt=torch.int32), row_scale=z(max_rows), tile_group=z(max_rows // 128, dt=torch.int32),
             m_tiles=z(1, dt=torch.int32), lb=z(self.depth),
-            xs=z(max_rows, D, dt=AD), hs=z(max_rows, Fh, dt=AD), y2=z(2 * N, D), y=z(N, D, dt=AD),
+            xs=z(max_rows, D, dt=AD), hs=z(max_rows, Fh, dt=AD), y2=z(2 * N, D, dt=AD),
             hf=z(E, N, Fh, dt=AD), xf=z(N, D, dt=AD), v=z(N, 32),
         )
         self._ws[key] = ws
@@ -445,13 +446,14 @@ class DiTEngine:
             ops.mark("gemm:w13")
             ops.gemm(ws["hs"], b["w2"], M=max_rows, b_c2=(0, 0, 1), tile_group=ws["tile_group"],
                      m_tiles_used=ws["m_tiles"], row_map=ws["row_map"], rows_out=2 * N,
-                     row_scale=ws["row_scale"], out_f32=ws["y2"], out_ld=D)
+                     row_scale=ws["row_scale"], out_bf16=ws["y2"], outb_ld=D)
             ops.mark("gemm:w2")
-            ops.ew(ws["y2"][:N], ws["y2"][N:], out_bf16=ws["y"])
-            ops.mark("ew")
-            yb = ws["y"].view(N, E, self.band).permute(1, 0, 2)  # [E, N, band] view: per-band K slice
-            ops.gemm(yb, b["f13"], M=N, G1=E, a_c2=(1, 0), b_c2=(1, 0, 0), swiglu=True,
-                     out_bf16=ws["hf"], outb_ld=Fh, outb_g=(N * Fh, 0))
+            # y = y_caption + y_acoustic (vocal2music_moe.py:166) is never materialised: the frequency experts'
+            # first GEMM reads both halves of y2 through the conv addressing (2 "taps" N rows apart, the band's
+            # weights repeated along K), so the sum happens in the fp32 accumulator.
+            yb = ws["y2"].view(2 * N, E, self.band).permute(1, 0, 2)  # [E, 2N, band] view: per-band K slice
+            ops.gemm(yb, b["f13"], M=N, G1=E, kpt=self.band // self.kq, dil=N, pad=0, a_c2=(1, 0), b_c2=(1, 0, 0),
+                     swiglu=True, out_bf16=ws["hf"], outb_ld=Fh, outb_g=(N * Fh, 0))
             ops.mark("gemm:f13")
             ops.gemm(ws["hf"], b["f2"], M=N, G1=E, a_c2=(1, 0), b_c2=(1, 0, 0),
                      gate=g_mlp, gate_rows=T, gate_ld=mld, gate_g1=self.band, residual=hbuf,
