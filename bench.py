@@ -134,31 +134,69 @@ def run_reference(args):
 # this repo's arm
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons DURING the timed region. Primary source: NVML polled in-process every
+    ~5 ms (the timed region of a fast run is shorter than one `nvidia-smi -lms` period); the recipe's
+    `nvidia-smi --query-gpu=... -lms` loop runs beside it (started before the warm-up) and is the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+            0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.nv, self.h, self.samples, self.mask, self.max_mhz = None, None, [], 0, None
+        self._stop = threading.Event()
+        self._in_region = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                pr = torch.cuda.get_device_properties(index)
+                bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            if self._in_region.is_set():
+                try:
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                except Exception:
+                    pass
+            time.sleep(0.005)
 
     def start(self):
+        """call before the warm-up steps"""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
+        if self.nv:
+            threading.Thread(target=self._poll, daemon=True).start()
+
+    def region(self, on: bool):
+        (self._in_region.set if on else self._in_region.clear)()
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
+        self._stop.set()
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        smi = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
         mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
         reasons = set()
         for r in self.rows:
@@ -166,8 +204,16 @@ class ClockSampler:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.samples:
+            sm = sorted(self.samples)
+            reasons |= {n for b, n in self.BITS.items() if self.mask & b}
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz or (max(mx) if mx else None),
+                    "reasons": sorted(reasons), "samples": len(sm), "source": "NVML, 5 ms poll inside the timed region",
+                    "nvidia_smi_samples_warmup_and_timed": len(smi)}
+        if not smi:
+            return {"sm_mhz": None, "sm_max_mhz": max(mx) if mx else None, "reasons": ["no clock samples"], "samples": 0}
+        return {"sm_mhz": smi[len(smi) // 2], "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(smi), "source": "nvidia-smi -lms 100 over warm-up + timed region"}
 
 
 def run_ours(args):
@@ -234,13 +280,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     for _ in range(max(args.warmup, 3)):
         step_device()
         step_host()
     # ---- timed region A: inputs resident in HBM (value) ----
-    clocks = ClockSampler(local_rank)
     barrier()
-    clocks.start()
+    clocks.region(True)
     tot_ms, samp_ms, vae_ms, voc_ms = 0.0, 0.0, 0.0, 0.0
     for _ in range(args.steps):
         flush.fill_(1)
@@ -264,6 +311,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         e2e_ms += a.elapsed_time(b)
     barrier()
+    clocks.region(False)
     clk = clocks.stop()
     t = torch.tensor([tot_ms, samp_ms, vae_ms, voc_ms, e2e_ms], device=dev, dtype=torch.float64) / args.steps
     if use_dist:
@@ -383,7 +431,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=1, help="clips per GPU per step")

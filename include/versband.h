@@ -287,9 +287,11 @@ int vb_ew(const float* a, const float* b, float alpha, float beta, int act, floa
 int vb_nct_to_ntc(const float* in, float scale, void* out, int B, int C, int T, int Cp, int out_is_f32,
                   void* stream);
 /* e_u == NULL: x[b,c,t] = e_c[b,t,c]; else CFG + Euler (cfm1_audio.py:160):
- * x[b,c,t] += dt * (e_u + s*(e_c - e_u)) */
+ * x[b,c,t] += dt * (e_u + s*(e_c - e_u)).
+ * x_cl != NULL (C <= 32): the new x is also written channels-last to x_cl[r][b][t][0..C) for r < x_cl_rep
+ * ([rep][B][T][32], bf16 or fp32): the next DiT evaluation's stem operand for each CFG branch. */
 int vb_ntc_to_nct(const float* e_c, const float* e_u, int64_t ld, float s, float dt, float* x, int B,
-                  int C, int T, void* stream);
+                  int C, int T, void* x_cl, int x_cl_is_f32, int x_cl_rep, void* stream);
 int vb_embed_rows(const int64_t* idx, const float* table, int V, int D, void* out, int64_t rows,
                   int out_is_f32, void* stream);
 /* AvgPool1d(2) of one or two branches, summed (vocal2music_moe.py:343,349,392) */

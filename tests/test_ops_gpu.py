@@ -158,9 +158,13 @@ def test_layout_embed_pool_ew():
     assert (cl[:, :, 20:] == 0).all()
     e_c, e_u = torch.randn(2 * 75, 32, device=d), torch.randn(2 * 75, 32, device=d)
     x0 = x.clone()
-    ops.ntc_to_nct(e_c, x, e_u=e_u, ld=32, s=3.0, dt=0.04)
+    xcl = torch.zeros(4, 75, 32, device=d)  # two channels-last replicas of the updated latent
+    ops.ntc_to_nct(e_c, x, e_u=e_u, ld=32, s=3.0, dt=0.04, x_cl=xcl)
     mix = (e_u + 3.0 * (e_c - e_u))[:, :20].view(2, 75, 20).transpose(1, 2)
     close(x, x0 + 0.04 * mix, 1e-6)
+    for r in range(2):
+        assert torch.equal(xcl[2 * r:2 * r + 2, :, :20], x.transpose(1, 2))
+    assert (xcl[:, :, 20:] == 0).all()
     idx = torch.randint(0, 130, (3, 50), device=d)
     tab = torch.randn(130, 64, device=d)
     out = torch.empty(3, 50, 64, device=d, dtype=BF)

@@ -113,7 +113,7 @@ def _declare(l: C.CDLL) -> None:
         "vb_timestamp": [P, P],
         "vb_router_noise": [C.c_uint64, C.c_uint64, I, I, I, I, P, P, P, P],
         "vb_nct_to_ntc": [P, F, P, I, I, I, I, I, P],
-        "vb_ntc_to_nct": [P, P, L, F, F, P, I, I, I, P],
+        "vb_ntc_to_nct": [P, P, L, F, F, P, I, I, I, P, I, I, P],
         "vb_embed_rows": [P, P, I, I, P, L, I, P],
         "vb_pool2_sum": [P, P, I, I, I, I, P, P, P],
         "vb_gn_stats": [P, I, I, I, I, F, P, P, P, P],

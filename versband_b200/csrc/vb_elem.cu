@@ -75,9 +75,10 @@ __global__ void nct_to_ntc_kernel(const float* __restrict__ in, float scale,
 //   out[b,c,t] = e_c[b,t,c]                          otherwise
 __global__ void ntc_to_nct_kernel(const float* __restrict__ e_c, const float* __restrict__ e_u,
                                   long long ld, float s, float dt, float* __restrict__ x, int C,
-                                  int T) {
+                                  int T, void* __restrict__ x_cl, int x_cl_f32, int rep, long long rep_stride) {
   pdl_sync();
   __shared__ float tile[32][33];
+  __shared__ float tile2[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -95,8 +96,24 @@ __global__ void ntc_to_nct_kernel(const float* __restrict__ e_c, const float* __
     const int c = c0 + j, t = t0 + threadIdx.x;
     if (c < C && t < T) {
       const long long o = ((long long)b * C + c) * T + t;
-      if (e_u) x[o] = x[o] + dt * tile[threadIdx.x][j];
-      else x[o] = tile[threadIdx.x][j];
+      float nv = tile[threadIdx.x][j];
+      if (e_u) nv = x[o] + dt * nv;
+      x[o] = nv;
+      tile2[threadIdx.x][j] = nv;
+    }
+  }
+  if (!x_cl) return;
+  // also refresh the channels-last operand copies of the latent ([rep][B][T][32], the DiT stem's A
+  // operand for every CFG branch) so the next evaluation needs no layout launch
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int t = t0 + j, c = c0 + threadIdx.x;
+    if (t < T && c < C) {
+      const long long o = ((long long)b * T + t) * 32 + c;
+      for (int r = 0; r < rep; ++r) {
+        if (x_cl_f32) static_cast<float*>(x_cl)[r * rep_stride + o] = tile2[j][threadIdx.x];
+        else static_cast<__nv_bfloat16*>(x_cl)[r * rep_stride + o] = __float2bfloat16(tile2[j][threadIdx.x]);
+      }
     }
   }
 }
@@ -293,11 +310,12 @@ extern "C" int vb_nct_to_ntc(const float* in, float scale, void* out_bf16, int B
 }
 
 extern "C" int vb_ntc_to_nct(const float* e_c, const float* e_u, int64_t ld, float s, float dt,
-                             float* x, int B, int C, int T, void* stream) {
+                             float* x, int B, int C, int T, void* x_cl, int x_cl_is_f32, int x_cl_rep, void* stream) {
   vb::ProfScope prof_scope(vb::PK_LAYOUT, stream);
-  if (!e_c || !x) return set_error(VB_ERR_INVALID, "vb_ntc_to_nct: bad arguments");
+  if (!e_c || !x || (x_cl && C > 32)) return set_error(VB_ERR_INVALID, "vb_ntc_to_nct: bad arguments");
   dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
-  launch_k(ntc_to_nct_kernel, dim3(grid), dim3(block), 0, static_cast<cudaStream_t>(stream), e_c, e_u, ld, s, dt, x, C, T);
+  launch_k(ntc_to_nct_kernel, dim3(grid), dim3(block), 0, static_cast<cudaStream_t>(stream), e_c, e_u, ld, s, dt, x, C, T,
+           x_cl, x_cl_is_f32, x_cl_rep, (long long)B * T * 32);
   return check_launch("vb_ntc_to_nct");
 }
 

@@ -361,7 +361,7 @@ class DiTEngine:
     @torch.no_grad()
     def forward(self, x: torch.Tensor, t: torch.Tensor, cond: DiTCond,
                 expo: List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]],
-                out_v: Optional[torch.Tensor] = None, want_aux: bool = False, pre=None):
+                out_v: Optional[torch.Tensor] = None, want_aux: bool = False, pre=None, x_cl_ready: bool = False):
         """x fp32 [B, C, T], t int64 [B]; expo[k] = Exp(1) draws ([N,2],[N,E],[N,E]) of block k.
         Returns v as the channels-last GEMM output [N, 32] (first C columns valid) unless `out_v`
         ([B, C, T]) is given, plus lb_loss per block (device tensor)."""
@@ -376,7 +376,8 @@ class DiTEngine:
         aux = []
 
         # stem: proj_in conv (k5) + bias, fused "+ acoustic"  (vocal2music_moe.py:395,415)
-        for r in range(B // Bx):  # CFG batching: the same latent feeds every conditioning branch
+        # (x_cl_ready: the sampler's Euler-update launch already refreshed the channels-last copies)
+        for r in range(0 if x_cl_ready else B // Bx):  # CFG batching: the same latent feeds every conditioning branch
             ops.nct_to_ntc(x.contiguous(), ws["x_cl"][r * Bx:(r + 1) * Bx])
             ops.mark("nct_to_ntc")
         ops.gemm(ws["x_cl"][:, :, :C], w["proj_in_w"], M=T, G1=B, kpt=1, dil=1, pad=self.proj_in_k // 2,

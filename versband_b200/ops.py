@@ -220,9 +220,15 @@ def nct_to_ntc(x, out_bf16, *, scale=1.0) -> None:
           int(out_bf16.dtype == torch.float32))
 
 
-def ntc_to_nct(e_c, x, *, e_u=None, ld, s=0.0, dt=0.0) -> None:
+def ntc_to_nct(e_c, x, *, e_u=None, ld, s=0.0, dt=0.0, x_cl=None) -> None:
+    """x_cl: optional [rep*B, T, 32] channels-last operand copies of x to refresh in the same launch."""
     B, Cc, T = x.shape
-    _call("vb_ntc_to_nct", _ptr(e_c), _ptr(e_u), ld, s, dt, _ptr(x), B, Cc, T)
+    rep = 0
+    if x_cl is not None:
+        assert x_cl.is_contiguous() and x_cl.shape[-1] == 32 and x_cl.shape[0] % B == 0 and x_cl.shape[1] == T
+        rep = x_cl.shape[0] // B
+    _call("vb_ntc_to_nct", _ptr(e_c), _ptr(e_u), ld, s, dt, _ptr(x), B, Cc, T, _ptr(x_cl),
+          int(x_cl is not None and x_cl.dtype == torch.float32), rep)
 
 
 def embed_rows(idx, table, out_bf16) -> None:

@@ -111,8 +111,11 @@ class FlowSampler:
             if rng:
                 self._draw_step(st, s, generator)
             expo = [(st["e0"][s, k], st["e1"][s, k], st["e2"][s, k]) for k in range(d)]
-            v, _ = self.dit.forward(x, st["t_all"][s], cond2, expo, pre=(st["mod_all"][s], st["hl_all"][s]))
-            ops.ntc_to_nct(v[:N], x, e_u=v[N:], ld=v.shape[-1], s=scale, dt=dt)
+            v, _ = self.dit.forward(x, st["t_all"][s], cond2, expo, pre=(st["mod_all"][s], st["hl_all"][s]),
+                                    x_cl_ready=s > 0)
+            # CFG + Euler update; the same launch rewrites the DiT's channels-last copies of x for the next step
+            ops.ntc_to_nct(v[:N], x, e_u=v[N:], ld=v.shape[-1], s=scale, dt=dt,
+                           x_cl=self.dit._workspace(cond2.B, cond2.T)["x_cl"])
 
     @torch.no_grad()
     def sample_cfg(self, x0: torch.Tensor, cond: DiTCond, uncond: Optional[DiTCond], scale: float,
