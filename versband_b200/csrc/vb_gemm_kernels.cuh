@@ -97,6 +97,21 @@ __device__ __forceinline__ void epi_prepare_rows(const GemmKParams& p, EpiRows& 
     }
     return;
   }
+  if (!p.row_map && !p.row_scale && (EC == EC_SWIGLU || !p.gate)) {
+    // affine rows (every conv, most linears): a handful of instructions per row instead of the general path
+    const int o0 = m0 * p.row_mul + p.row_off + g1 * p.row_off_g1, ostep = 4 * p.row_mul;
+    const unsigned ld = static_cast<unsigned>(p.out_ld), ldb = static_cast<unsigned>(p.outb_ld);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int o = o0 + i * ostep;
+      const bool ok = (m0 + 4 * i < p.M) && (static_cast<unsigned>(o) < static_cast<unsigned>(p.rows_out));
+      if (ok) rows.valid |= 1u << i;
+      rows.off[i] = ok ? static_cast<unsigned>(o) * ld : 0u;
+      rows.offb[i] = ok ? static_cast<unsigned>(o) * ldb : 0u;
+      rows.rs[i] = 1.f;
+    }
+    return;
+  }
   int b = 0, r = 0;
   if (EC != EC_SWIGLU && p.gate) {
     const int mc = m0 < p.M ? m0 : p.M - 1;
