@@ -97,20 +97,34 @@ __device__ __forceinline__ void epi_prepare_rows(const GemmKParams& p, EpiRows& 
     }
     return;
   }
-  if (!p.row_map && !p.row_scale && (EC == EC_SWIGLU || !p.gate)) {
+  if (!p.row_map && !p.row_scale) {
     // affine rows (every conv, most linears): a handful of instructions per row instead of the general path
-    const int o0 = m0 * p.row_mul + p.row_off + g1 * p.row_off_g1, ostep = 4 * p.row_mul;
-    const unsigned ld = static_cast<unsigned>(p.out_ld), ldb = static_cast<unsigned>(p.outb_ld);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int o = o0 + i * ostep;
-      const bool ok = (m0 + 4 * i < p.M) && (static_cast<unsigned>(o) < static_cast<unsigned>(p.rows_out));
-      if (ok) rows.valid |= 1u << i;
-      rows.off[i] = ok ? static_cast<unsigned>(o) * ld : 0u;
-      rows.offb[i] = ok ? static_cast<unsigned>(o) * ldb : 0u;
-      rows.rs[i] = 1.f;
+    const bool gated = EC != EC_SWIGLU && p.gate != nullptr;
+    int r0 = 0;
+    bool simple = true;
+    if (gated) {  // gate batch of the first row; all 8 rows (span 29) must fall in at most two batches
+      const int mc = m0 < p.M ? m0 : p.M - 1;
+      const int b0 = mc / p.gate_rows;
+      r0 = mc - b0 * p.gate_rows + (m0 - mc);
+      rows.b_lo = b0;
+      simple = r0 + 28 < 2 * p.gate_rows;
     }
-    return;
+    if (simple) {
+      const int o0 = m0 * p.row_mul + p.row_off + g1 * p.row_off_g1, ostep = 4 * p.row_mul;
+      const unsigned ld = static_cast<unsigned>(p.out_ld), ldb = static_cast<unsigned>(p.outb_ld);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int o = o0 + i * ostep;
+        const bool ok = (m0 + 4 * i < p.M) && (static_cast<unsigned>(o) < static_cast<unsigned>(p.rows_out));
+        if (ok) rows.valid |= 1u << i;
+        if (gated && ok && r0 + 4 * i >= p.gate_rows) rows.hi |= 1u << i;
+        rows.off[i] = ok ? static_cast<unsigned>(o) * ld : 0u;
+        rows.offb[i] = ok ? static_cast<unsigned>(o) * ldb : 0u;
+        rows.rs[i] = 1.f;
+      }
+      return;
+    }
+    rows.b_lo = 0;
   }
   int b = 0, r = 0;
   if (EC != EC_SWIGLU && p.gate) {

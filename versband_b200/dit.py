@@ -276,6 +276,9 @@ class DiTEngine:
         """Everything in TxtFlagLargeDiT.forward that does not depend on (x, t)."""
         w, D, dev = self.w, self.D, self.dev
         B, L, _ = caption.shape
+        if L > self.LK:
+            raise ValueError(f"caption length {L} > {self.LK}: the folded caption gate (VB_EPI_ROUTE) holds {self.LK} key "
+                             "slots per head (the reference pads captions to 80 tokens, encoders/modules.py:88-89)")
         if acoustic is None:
             acoustic = self.prepare_acoustic(midi, beats, T)
         ac, ac_logits = acoustic
