@@ -150,7 +150,7 @@ int vb_gemm(const vb_gemm_args* args, void* stream);
  *   q        element strides (q_st token, q_sh head, q_sb batch), head_dim contiguous
  *   k_self   [B, H, T, hd]      vt_self  [B, H, hd, Tp]   (V transposed, Tp % 8 == 0)
  *   k_text   [B, H, L, hd]      vt_text  [B, H, hd, Lp]   (L <= 128, Lp % 8 == 0)
- * gate: fp32 [H] (raw, tanh applied inside) or NULL (= 1). head_dim in {64, 96, 128}.
+ * gate: fp32 [H] (raw, tanh applied inside) or NULL (= 1). head_dim in {64, 96}.
  * ------------------------------------------------------------------------------------------ */
 typedef struct vb_attn_args {
   const void* q;

@@ -6,6 +6,8 @@
 //   softmax warps: TMEM -> registers, online max/sum, P (bf16) -> swizzled smem
 //   MMA2  O_j = P V        (UMMA 128xHDx16, B operand = V^T tile), TMEM -> registers,
 //                           acc = acc * alpha + O_j   (running output kept in registers)
+// P and O are double-buffered: the softmax warps start on tile j+1 right after publishing P_j and
+// fold O_j into their accumulators one tile later, so they never wait for MMA2.
 // Two KV segments with independent softmax (flag_large_dit_moe.py:381-402):
 //   segment 0: self-attention over T keys            out  = O0 / l0
 //   segment 1: one tile of L <= 128 "text" keys      out += tanh(gate[h]) * O1 / l1
@@ -36,8 +38,8 @@ struct AttnCfg {
   static constexpr int kQBytes = 2 * 16384;            // Q tile: 2 k-blocks of [128 x 64] bf16
   static constexpr int kKBytes = 2 * 16384;            // K tile per stage
   static constexpr int kVBytes = 2 * HD * 128;         // V^T tile per stage: 2 k-blocks of [HD x 64]
-  static constexpr int kPBytes = 2 * 16384;            // P tile
-  static constexpr int kSmem = kQBytes + 2 * kKBytes + 2 * kVBytes + kPBytes + 1024 + 256 + 1024;  // + row exchange
+  static constexpr int kPBytes = 2 * 16384;            // P tile (two buffers)
+  static constexpr int kSmem = kQBytes + 2 * kKBytes + 2 * kVBytes + 2 * kPBytes + 1024 + 256 + 3 * 1024;  // + row exchange buffers
 };
 
 template <int HD>
@@ -52,16 +54,18 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::kQBytes;          // [2 stages][2 kb][16384]
   uint8_t* sV = sK + 2 * Cfg::kKBytes;      // [2 stages][2 kb][HD*128]
-  uint8_t* sP = sV + 2 * Cfg::kVBytes;      // [2 kb][16384]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kPBytes);
+  uint8_t* sP = sV + 2 * Cfg::kVBytes;      // [2 buffers][2 kb][16384]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::kPBytes);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* k_full = bars + 1;    // [2]  K and V^T tiles ride separate rings: a K slot is free as soon as
+  uint64_t* k_empty = bars + 3;   // [2]  its S = Q K^T retires (a whole tile before the V slot), so K_{j+1} is
+  uint64_t* v_full = bars + 13;   // [2]  already in flight while tile j-1's P V is still running
+  uint64_t* v_empty = bars + 15;  // [2]
   uint64_t* s_full = bars + 5;    // [2]
-  uint64_t* p_full = bars + 7;
-  uint64_t* o_full = bars + 8;
-  uint64_t* o_empty = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* p_full = bars + 7;    // [2]
+  uint64_t* o_full = bars + 9;    // [2]
+  uint64_t* o_empty = bars + 11;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128;
@@ -73,13 +77,15 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     tma_prefetch_desc(&tmQ);
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 256);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_empty[i], 256);
     }
-    mbar_init(p_full, 256);
-    mbar_init(o_full, 1);
-    mbar_init(o_empty, 256);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -87,7 +93,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_O = tmem_base + 256;
+  const uint32_t tmem_O = tmem_base + 256;  // two O buffers of 128 columns
   pdl_sync();  // prologue above overlaps the previous kernel
 
   if (warp == 0) {
@@ -97,18 +103,20 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       if (HD > 64) tma_load_4d(sQ + 16384, &tmQ, q_full, 64, q0, h, b);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
         const bool text = j >= n_self;
         const CUtensorMap* mk = text ? &tmKt : &tmKs;
         const CUtensorMap* mv = text ? &tmVt : &tmVs;
         const int key0 = text ? 0 : j * 128;
-        mbar_expect_tx(&kv_full[st], (HD > 64 ? Cfg::kKBytes : 16384) + Cfg::kVBytes);
         uint8_t* k_dst = sK + st * Cfg::kKBytes;
         uint8_t* v_dst = sV + st * Cfg::kVBytes;
-        tma_load_4d(k_dst, mk, &kv_full[st], 0, key0, h, b);
-        if (HD > 64) tma_load_4d(k_dst + 16384, mk, &kv_full[st], 64, key0, h, b);
-        tma_load_4d(v_dst, mv, &kv_full[st], key0, 0, h, b);
-        tma_load_4d(v_dst + HD * 128, mv, &kv_full[st], key0 + 64, 0, h, b);
+        mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&k_full[st], HD > 64 ? Cfg::kKBytes : 16384);
+        tma_load_4d(k_dst, mk, &k_full[st], 0, key0, h, b);
+        if (HD > 64) tma_load_4d(k_dst + 16384, mk, &k_full[st], 64, key0, h, b);
+        mbar_wait(&v_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&v_full[st], Cfg::kVBytes);
+        tma_load_4d(v_dst, mv, &v_full[st], key0, 0, h, b);
+        tma_load_4d(v_dst + HD * 128, mv, &v_full[st], key0 + 64, 0, h, b);
       }
     }
   } else if (warp == 1) {
@@ -118,7 +126,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mbar_wait(q_full, 0);
       auto mma1 = [&](int j) {
         const int st = j & 1;
-        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        mbar_wait(&k_full[st], (j >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) {
@@ -128,24 +136,26 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           umma_bf16(tmem_base + st * 128, da, db, idesc_s, k > 0 ? 1u : 0u);
         }
         umma_commit(&s_full[st]);
+        umma_commit(&k_empty[st]);
       };
       mma1(0);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j & 1;
         if (j + 1 < n_tiles) mma1(j + 1);  // overlaps the softmax of tile j
-        mbar_wait(p_full, j & 1);
-        if (j > 0) mbar_wait(o_empty, (j - 1) & 1);
+        mbar_wait(&p_full[st], (j >> 1) & 1);
+        if (j >= 2) mbar_wait(&o_empty[st], ((j - 2) >> 1) & 1);  // O_{j-2} has been folded into the registers
+        mbar_wait(&v_full[st], (j >> 1) & 1);
         tc_fence_after();
         const int keys = (j >= n_self) ? p.L : min(128, p.T - j * 128);
         const int ksteps = (keys + 15) >> 4;
         for (int k = 0; k < ksteps; ++k) {
           const int kb = k >> 2, off = (k & 3) * 2;
-          const uint64_t da = make_kmajor_sw128_desc(smem_u32(sP + kb * 16384)) + off;
+          const uint64_t da = make_kmajor_sw128_desc(smem_u32(sP + st * Cfg::kPBytes + kb * 16384)) + off;
           const uint64_t db = make_kmajor_sw128_desc(smem_u32(sV + st * Cfg::kVBytes + kb * HD * 128)) + off;
-          umma_bf16(tmem_O, da, db, idesc_o, k > 0 ? 1u : 0u);
+          umma_bf16(tmem_O + st * 128, da, db, idesc_o, k > 0 ? 1u : 0u);
         }
-        umma_commit(o_full);
-        umma_commit(&kv_empty[st]);
+        umma_commit(&o_full[st]);
+        umma_commit(&v_empty[st]);
       }
     }
   } else {
@@ -166,11 +176,48 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const float g = p.gate ? tanhf(p.gate[h]) : 1.f;
     const int rsw = row & 7;
     uint8_t* prow = sP + half * 16384 + (row >> 3) * 1024 + rsw * 128;
-    float* xch = reinterpret_cast<float*>(tmem_slot + 4);  // [2 halves][128 rows] exchange buffer
+    // row exchange between the two threads of a query row: [2 halves][128 rows] floats per buffer; the
+    // per-tile maxima alternate between buffers 0/1 (a thread may be a tile ahead of its partner's read),
+    // buffer 2 carries the segment sums (those exchanges are bracketed by their own barriers)
+    float* xch_base = reinterpret_cast<float*>(tmem_slot + 4);
+    float* xch = xch_base + 2 * 256;
+    // acc += O_k of a tile whose P was published one iteration earlier (f_old/f_new are that tile's factors)
+    int pend = -1;
+    float pend_old = 0.f, pend_new = 0.f;
+    auto fold = [&]() {
+      if (pend < 0) return;
+      const int pb = pend & 1;
+      mbar_wait(&o_full[pb], (pend >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tO = tmem_O + pb * 128 + half * HH + lane_sel;
+      if (HH == 48) {
+        uint32_t r0[32], r1[16];
+        tmem_ld32(tO, r0);
+        tmem_ld16(tO + 32, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = acc[i] * pend_old + __uint_as_float(r0[i]) * pend_new;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[32 + i] = acc[32 + i] * pend_old + __uint_as_float(r1[i]) * pend_new;
+      } else {
+#pragma unroll
+        for (int c = 0; c < HH / 32; ++c) {
+          uint32_t r0[32];
+          tmem_ld32(tO + c * 32, r0);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[c * 32 + i] = acc[c * 32 + i] * pend_old + __uint_as_float(r0[i]) * pend_new;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&o_empty[pb]);
+      pend = -1;
+    };
     for (int j = 0; j < n_tiles; ++j) {
       const bool text = j >= n_self;
       if (text) {
         if (n_self > 0) {  // close the self segment: acc /= (l_half0 + l_half1)
+          fold();          // (the last self tile's O first)
           xch[half * 128 + row] = l;
           named_bar_sync(1 + qd, 64);
           const float inv = 1.f / (l + xch[(half ^ 1) * 128 + row]);
@@ -204,9 +251,10 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       float tmax = -CUDART_INF_F;
 #pragma unroll
       for (int i = 0; i < 64; ++i) tmax = fmaxf(tmax, sv[i]);
-      xch[half * 128 + row] = tmax;
+      float* xm = xch_base + (j & 1) * 256;
+      xm[half * 128 + row] = tmax;
       named_bar_sync(1 + qd, 64);
-      tmax = fmaxf(tmax, xch[(half ^ 1) * 128 + row]);
+      tmax = fmaxf(tmax, xm[(half ^ 1) * 128 + row]);
       if (tr) p.trace[j * 8 + 2] = clock64();
       const float m_new = fmaxf(m2, tmax * c1);
       const float alpha = (m2 == -CUDART_INF_F) ? 0.f : ex2_ftz(m2 - m_new);
@@ -218,6 +266,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       for (int i = 0; i < 64; i += 4) { rs0 += sv[i]; rs1 += sv[i + 1]; rs2 += sv[i + 2]; rs3 += sv[i + 3]; }
       l = l * alpha + ((rs0 + rs1) + (rs2 + rs3));
       m2 = m_new;
+      uint8_t* prow_j = prow + (j & 1) * Cfg::kPBytes;
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {
         uint4 w;
@@ -227,49 +276,29 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         __nv_bfloat162 t3 = __floats2bfloat162_rn(sv[8 * ch + 6], sv[8 * ch + 7]);
         w.x = *reinterpret_cast<uint32_t*>(&t0); w.y = *reinterpret_cast<uint32_t*>(&t1);
         w.z = *reinterpret_cast<uint32_t*>(&t2); w.w = *reinterpret_cast<uint32_t*>(&t3);
-        *reinterpret_cast<uint4*>(prow + ((ch ^ rsw) << 4)) = w;
+        *reinterpret_cast<uint4*>(prow_j + ((ch ^ rsw) << 4)) = w;
       }
       tc_fence_before();
       fence_proxy_async();  // make the generic-proxy smem writes visible to the tensor core
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[j & 1]);
       if (tr) p.trace[j * 8 + 3] = clock64();
-      // O_j (my HD/2 output columns)
-      mbar_wait(o_full, j & 1);
-      tc_fence_after();
-      if (tr) p.trace[j * 8 + 4] = clock64();
       float f_old = alpha, f_new = 1.f;
       if (text) {  // single text tile: l is final after the exchange
+        named_bar_sync(1 + qd, 64);  // (both halves are done reading the max exchange)
         xch[half * 128 + row] = l;
         named_bar_sync(1 + qd, 64);
         f_old = 1.f;
         f_new = g / (l + xch[(half ^ 1) * 128 + row]);
       }
-      {
-        const uint32_t tO = tmem_O + half * HH + lane_sel;
-        if (HH == 48) {
-          uint32_t r0[32], r1[16];
-          tmem_ld32(tO, r0);
-          tmem_ld16(tO + 32, r1);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) acc[i] = acc[i] * f_old + __uint_as_float(r0[i]) * f_new;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) acc[32 + i] = acc[32 + i] * f_old + __uint_as_float(r1[i]) * f_new;
-        } else {
-#pragma unroll
-          for (int c = 0; c < HH / 32; ++c) {
-            uint32_t r0[32];
-            tmem_ld32(tO + c * 32, r0);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) acc[c * 32 + i] = acc[c * 32 + i] * f_old + __uint_as_float(r0[i]) * f_new;
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(o_empty);
-      if (tr) p.trace[j * 8 + 5] = clock64();
+      // O_{j-1} is complete by now (MMA2 of tile j-1 ran under this tile's softmax): fold it in, then
+      // queue this tile
+      fold();
+      if (tr) p.trace[j * 8 + 4] = clock64();
+      pend = j;
+      pend_old = f_old;
+      pend_new = f_new;
     }
+    fold();
     if (!p.has_text && n_self > 0) {
       xch[half * 128 + row] = l;
       named_bar_sync(1 + qd, 64);
@@ -397,7 +426,7 @@ extern "C" int vb_attn_fused(const vb_attn_args* a, void* stream) {
   switch (a->hd) {
     case 96: return launch_attn<96>(a, s);
     case 64: return launch_attn<64>(a, s);
-    case 128: return launch_attn<128>(a, s);
-    default: return set_error(VB_ERR_INVALID, "vb_attn_fused: head_dim %d not instantiated (64/96/128)", a->hd);
+    default:  // (128 would need 228 KB of shared memory with the double-buffered P tile)
+      return set_error(VB_ERR_INVALID, "vb_attn_fused: head_dim %d not instantiated (64/96)", a->hd);
   }
 }
