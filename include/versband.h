@@ -84,7 +84,7 @@ typedef struct vb_gemm_args {
   int32_t kpt, dil, pad;
   int32_t a_c2_g1, a_c2_g2, a_c3_g1, a_c3_g2;
   int32_t b_c2_g1, b_c2_g2, b_c2_tile;
-  int32_t bn; /* N-tile override (32/64/96/128/256), 0 = auto */
+  int32_t bn; /* N-tile override (32/64/96/128/192/256; forces the 1-CTA kernel), 0 = auto (cost model, may pick the 2-CTA kernel) */
   int32_t operand_f32; /* 1: A and B are fp32 tensors multiplied as TF32 (kind::tf32); K multiple of 32,
                           strides in fp32 elements; the accuracy mode of DESIGN.md section 2 */
 
