@@ -21,3 +21,15 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _library_present():
+    """The in-tree .so is git-ignored: a fresh checkout has none until `__graft_entry__.build()` ran. Building it
+    here (only when it is missing altogether) is test infrastructure — the product path itself still refuses to
+    run without the library (versband_b200._lib.lib)."""
+    from versband_b200 import build
+
+    if not build.LIB.exists():
+        build.build()
+    yield
