@@ -31,9 +31,11 @@ T_LAT = 750
 N_EVALS = 48  # 24 Euler steps x (cond, uncond)
 # Algorithmic FLOPs per 20 s clip: 48 x 51.0 + 22 (sampler) + 160.3 (VAE) + 848.5 (HiFi-GAN)
 FLOP_SAMPLER = 48 * 51.0e9 + 22e9
+FLOP_ATTN = 48 * 4 * 2 * (0.864e9 + 0.092e9)  # self + text attention core (GMAC per block) -> 0.367 TFLOP
 FLOP_VAE = 160.3e9
 FLOP_VOC = 848.5e9
 FLOP_CLIP = FLOP_SAMPLER + FLOP_VAE + FLOP_VOC
+BYTES_VOC_16 = 3.18e9  # HiFi-GAN per-layer compulsory bytes at 16-bit storage
 
 
 def dist_env():
@@ -50,10 +52,11 @@ def synth_weights():
 # ------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port of the reference algorithm on the host cores
 # ------------------------------------------------------------------------------------------
-def cpu_reference_step(sds, euler_steps: int = 2, seed: int = 0):
-    """Bounded sample of one clip on the CPU: `euler_steps` of the 24 Euler steps (2 DiT evals each,
-    dense experts as in the reference) + full VAE decode + full HiFi-GAN; the sampler time is
-    extrapolated to 24 steps. Returns (seconds per clip, breakdown)."""
+def cpu_reference_step(sds, euler_steps: int = 24, seed: int = 0):
+    """One clip on the CPU through the oracle port of the reference algorithm: `euler_steps` Euler steps
+    (default: all 24; 2 DiT evaluations each, dense experts as in the reference) + full VAE decode + full
+    HiFi-GAN. With fewer than 24 steps the sampler time is scaled up and the result is marked as such by the
+    caller. Returns (seconds per clip, breakdown)."""
     from oracle import accompband_ref as R, synth
     torch.set_grad_enabled(False)
     x, midi, beats, cap_c, cap_u = synth.dit_inputs(1, T_LAT, seed=seed)
@@ -73,7 +76,8 @@ def cpu_reference_step(sds, euler_steps: int = 2, seed: int = 0):
     t3 = time.perf_counter()
     assert wav.shape[-1] == T_MEL * 320
     sampler = (t1 - t0) * (24.0 / euler_steps)
-    return sampler + (t2 - t1) + (t3 - t2), {"sampler_s": sampler, "vae_s": t2 - t1, "vocoder_s": t3 - t2}
+    return sampler + (t2 - t1) + (t3 - t2), {"sampler_s": sampler, "vae_s": t2 - t1, "vocoder_s": t3 - t2,
+                                             "euler_steps_run": euler_steps}
 
 
 def pick_cpu_threads(sds) -> int:
@@ -98,34 +102,38 @@ def pick_cpu_threads(sds) -> int:
 
 
 def run_reference(args):
+    """Reference arm: every step is ONE COMPLETE clip (24 Euler steps x 2 dense DiT evaluations + VAE decode +
+    HiFi-GAN) through the oracle port on the host cores — nothing extrapolated. The number of steps actually
+    run is bounded by a wall-clock budget so the arm ends within a few minutes; `steps` reports what ran."""
     rank, _, world = dist_env()
     if rank != 0:
         return
     sds = synth_weights()
     cores = pick_cpu_threads(sds)
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_reference_step(sds, euler_steps=1)
-    times = []
-    brk = {}
-    t_budget = 150.0  # seconds of bounded CPU samples: the arm must end within a few minutes whatever K is
+    if args.warmup > 0:
+        cpu_reference_step(sds, euler_steps=1)  # warm-up: thread pools, allocator
+    times, brks = [], []
+    t_budget = 120.0
     t_run = time.time()
-    for i in range(args.steps):
-        s, brk = cpu_reference_step(sds, euler_steps=2, seed=i)
+    for i in range(max(args.steps, 1)):
+        s, brk = cpu_reference_step(sds, euler_steps=24, seed=i)
         times.append(s)
-        if time.time() - t_run > t_budget:
+        brks.append(brk)
+        if time.time() - t_run + s > t_budget:  # the next clip would overrun the budget
             break
     sec = sum(times) / len(times)
+    brk = {k: sum(b[k] for b in brks) / len(brks) for k in ("sampler_s", "vae_s", "vocoder_s")}
     value = CLIP_SECONDS / sec
-    sample = ("1 clip: 2 of 24 Euler steps (4 dense DiT evals, x12 extrapolated) + full VAE decode + full HiFi-GAN, "
-              "fp32 torch CPU oracle port")
+    sample = (f"{len(times)} complete clip(s): 24 Euler steps (48 dense DiT evaluations) + VAE decode + HiFi-GAN each, "
+              "fp32 torch CPU oracle port of the reference algorithm, nothing extrapolated")
     line = {
         "impl": "reference", "metric": "audio_sec_per_wall_sec", "value": value,
         "unit": "x real-time (24 kHz audio-s / wall-s)", "n_gpus": args.gpus, "steps": len(times),
         "steps_requested": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": 1 if args.warmup > 0 else 0, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"AccompBand 25-point (24-step) CFG flow sampler + VAE decode + HiFi-GAN, 1 clip of 20 s, host CPU",
-                   "clips_per_gpu": 1, "guidance": 3.0},
+        "config": {"workload": "AccompBand 25-point (24-step) CFG flow sampler + VAE decode + HiFi-GAN, 1 clip of 20 s, host CPU",
+                   "clips_per_gpu": 1, "guidance": 3.0, "t_lat": T_LAT},
         "dit_latent_frame_evals_per_s": T_LAT * N_EVALS / brk["sampler_s"],
         "cpu_baseline": {"value": value, "unit": "x real-time", "cores": cores, "kind": "port", "sample": sample,
                          "breakdown_s": brk},
@@ -249,7 +257,9 @@ def run_ours(args):
             lst.append(t)
     host = [torch.cat(l, 0).pin_memory() for l in (midi, beats, cap_c, cap_u, x0)]
     devt = [t.to(dev) for t in host]
-    gen = torch.Generator(device=dev).manual_seed(4242 + rank)
+    # per-clip seeding: clip `gid` of the job draws its router noise from its own generator,
+    # so its waveform is the same on any GPU count / batch composition
+    gen = [torch.Generator(device=dev).manual_seed(4242 + rank * B + c) for c in range(B)]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step_device(events=None):
@@ -318,12 +328,19 @@ def run_ours(args):
     barrier()
     clocks.region(False)
     clk = clocks.stop()
+    # fingerprint of job clip 0 (rank 0, first clip): per-clip seeding makes it independent of the GPU count
+    clip0_sha1 = None
+    if rank == 0:
+        import hashlib
+        gen0 = [torch.Generator(device=dev).manual_seed(4242 + c) for c in range(B)]
+        w0 = pipe.generate(devt[0], devt[1], devt[2], devt[3], x0=devt[4], generator=gen0)["wav"][0]
+        clip0_sha1 = hashlib.sha1(w0.cpu().numpy().tobytes()).hexdigest()
     t = torch.tensor([tot_ms, samp_ms, vae_ms, voc_ms, e2e_ms], device=dev, dtype=torch.float64) / args.steps
     if use_dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
     ms_step, ms_samp, ms_vae, ms_voc, ms_e2e = [float(v) for v in t]
 
-    # ---- instrumented eager pass (rank 0): per-family kernel time by CUDA events, launch count ----
+    # ---- roofline (rank 0): every time below is a CUDA-event interval of the TIMED (graph-replay) region ----
     roof, launches, fam = None, None, None
     if rank == 0:
         import json as _json
@@ -334,7 +351,29 @@ def run_ours(args):
         except Exception:
             pass
         peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
-        peak_src = "measured sustained (MEASURED_PEAKS.json)" if peaks else "fallback 1.4 PF sustained"
+        peak_bw = peaks.get("hbm_gbs") or 6650.0
+        peak_src = ("measured (MEASURED_PEAKS.json: sustained 16-bit dense tensor TFLOP/s, STREAM-copy GB/s)" if peaks
+                    else "fallback 1.4 PF sustained / 6.65 TB/s")
+        # Stage = a contiguous run of this repo's kernels bracketed by two events on the launching stream
+        # (pipeline.generate(events=...)): sampler graph | VAE-decode graph | vocoder graph. The algorithmic
+        # work per stage is SURVEY.md §8d's per-clip figure x clips. No eager-pass share is used any more.
+        stages = {
+            "dit_sampler": {"kernels": "vb_gemm_kernel / vb_gemm2_kernel (tcgen05 GEMMs) + attn_fused_kernel + norm/router/dispatch",
+                            "bound": "tensor", "ms": ms_samp, "algorithmic_flop": FLOP_SAMPLER * B,
+                            "flop_gemm": (FLOP_SAMPLER - FLOP_ATTN) * B, "flop_attention": FLOP_ATTN * B,
+                            "achieved": FLOP_SAMPLER * B / (ms_samp * 1e-3) / 1e12, "unit": "TFLOP/s", "peak": peak_tf},
+            "vae_decode": {"kernels": "vb_gemm2_kernel implicit-GEMM convs + GroupNorm", "bound": "tensor", "ms": ms_vae,
+                           "algorithmic_flop": FLOP_VAE * B, "achieved": FLOP_VAE * B / (ms_vae * 1e-3) / 1e12,
+                           "unit": "TFLOP/s", "peak": peak_tf},
+            "vocoder": {"kernels": "HiFi-GAN convs (vb_gemm*/vb_conv_halo/fused resblock) + conv_post", "bound": "hbm", "ms": ms_voc,
+                        "algorithmic_bytes": BYTES_VOC_16 * B, "achieved": BYTES_VOC_16 * B / (ms_voc * 1e-3) / 1e9,
+                        "unit": "GB/s", "peak": peak_bw,
+                        "tensor_achieved_tflops": FLOP_VOC * B / (ms_voc * 1e-3) / 1e12,
+                        "tensor_frac": FLOP_VOC * B / (ms_voc * 1e-3) / 1e12 / peak_tf},
+        }
+        for st_ in stages.values():
+            st_["frac"] = st_["achieved"] / st_["peak"]
+        # launch count of one step (an eager pass; the timed region replays the same launches from graphs)
         from versband_b200.sampler import FlowSampler
         saved = pipe.sampler
         pipe.sampler = FlowSampler(pipe.dit, use_graph=False)
@@ -348,57 +387,36 @@ def run_ours(args):
         launches = _lib.launch_count() - n0
         pipe.sampler = saved
         pipe.use_graph = True
-        gemm_ms_eager = fam["gemm"]["ms"]
-        n_gemm = fam["gemm"]["launches"]
-        share = gemm_ms_eager / sum(v["ms"] for v in fam.values())
-        # Per-launch CUDA-event pairs exist only in the instrumented EAGER pass, where the GPU idles between
-        # launches (Python-bound) and the kernels run cold. The timed region replays CUDA graphs, so the GEMM
-        # time inside it is taken as (device-timed step) x (GEMM share of kernel time from the event pairs);
-        # the raw event-timed figure is reported next to it.
-        gemm_ms = ms_step * share
-        achieved = FLOP_CLIP * B / (gemm_ms * 1e-3) / 1e12
-        traffic = None
-        try:  # dram bytes of the same kernel family over one step, from the committed ncu capture
-            with open(os.path.join(ROOT, "profiles", "r1_traffic_eager_step.json")) as f:
-                tj = _json.load(f)["vb_gemm_kernel"]
-            traffic = tj["dram_bytes"] / tj["launches"]
-        except Exception:
-            pass
-        roof = {"bound": "tensor", "kernel": "vb_gemm_kernel / vb_gemm2_kernel <BN,TF32> (tcgen05/TMA implicit-GEMM, all launches of one step)",
-                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+        traffic, traffic_src = None, None
+        for name in ("r2_traffic_step.json", "r1_traffic_eager_step.json"):
+            try:  # dram bytes of the GEMM family over one step, from the committed ncu capture
+                with open(os.path.join(ROOT, "profiles", name)) as f:
+                    tj = _json.load(f)["vb_gemm_kernel"]
+                traffic, traffic_src = tj["dram_bytes"] / tj["launches"], "profiles/" + name
+                break
+            except Exception:
+                pass
+        dom = stages["dit_sampler"]
+        n_dit = 24 * 2  # evaluations; launches of the stage = launches - prepare - vae - vocoder (see launch lists)
+        roof = {"bound": "tensor",
+                "kernel": "DiT sampler stage: tcgen05 GEMM family (vb_gemm_kernel / vb_gemm2_kernel) + attn_fused_kernel, "
+                          "48 evaluations replayed from one CUDA graph; the stage is 75-80 % of the step",
+                "achieved": dom["achieved"], "peak": peak_tf, "unit": "TFLOP/s", "frac": dom["frac"],
                 "peak_source": peak_src, "traffic": traffic,
-                "traffic_note": "mean dram read+write bytes per launch (ncu, L2 flushed before every launch), profiles/r1_traffic_eager_step.json",
-                "launches_per_step": n_gemm, "avg_launch_us": gemm_ms * 1e3 / max(n_gemm, 1),
-                "algorithmic_flop_per_step": FLOP_CLIP * B,
-                "kernel_time_share_of_step": share,
-                "method": "GEMM time in the timed (graph-replay) region = ms_per_step x share; share from per-launch CUDA-event pairs in an eager pass",
-                "eager_event_timed": {"gemm_ms": gemm_ms_eager, "achieved": FLOP_CLIP * B / (gemm_ms_eager * 1e-3) / 1e12}}
-
-    fast = None
-    if rank == 0 and world == 1 and args.precision == "tf32" and not args.no_fast_mode:
-        pipe_bf = AccompBandPipeline(*sds, dit_cfg=synth.DIT_CFG, ddconfig=synth.VAE_DDCONFIG,
-                                     embed_dim=synth.VAE_EMBED_DIM, voc_cfg=synth.HIFIGAN_CFG, device=dev,
-                                     precision="bf16")
-        for _ in range(3):
-            pipe_bf.generate(devt[0], devt[1], devt[2], devt[3], x0=devt[4], generator=gen)
-        ms = 0.0
-        for _ in range(args.steps):
-            flush.fill_(1)
-            ev = {}
-            pipe_bf.generate(devt[0], devt[1], devt[2], devt[3], x0=devt[4], generator=gen, events=ev)
-            torch.cuda.synchronize()
-            ms += ev["start"].elapsed_time(ev["end"])
-        ms /= args.steps
-        fast = {"precision": "bf16 operands everywhere (DiT forward ~1e-2 of peak vs the fp32 reference)",
-                "value": B * CLIP_SECONDS / (ms * 1e-3), "ms_per_step": ms}
-        del pipe_bf
+                "traffic_note": f"mean dram read+write bytes per GEMM launch (ncu, cold), {traffic_src}",
+                "method": "algorithmic FLOPs of the stage (SURVEY §8d: 48 x 51.0 + 22 GFLOP per clip, minimal top-1 routed count) / "
+                          "CUDA-event time of the stage inside the timed region; every kernel of the stage counts against the "
+                          "tensor roof, so this is a lower bound on the GEMM family's own fraction",
+                "stages": stages, "dit_evaluations_per_step": n_dit,
+                "eager_event_timed_family_ms": {k: round(v["ms"], 3) for k, v in fam.items()}}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = pick_cpu_threads(sds)
-        sec, brk = cpu_reference_step(sds, euler_steps=2)
+        sec, brk = cpu_reference_step(sds, euler_steps=24)
         cpu = {"value": CLIP_SECONDS / sec, "unit": "x real-time", "cores": cores, "kind": "port",
-               "sample": "1 clip: 2 of 24 Euler steps (x12 extrapolated) + full VAE decode + full HiFi-GAN, fp32 oracle port",
+               "sample": "1 complete clip: 24 Euler steps (48 dense DiT evaluations) + VAE decode + HiFi-GAN, fp32 oracle port, "
+                         "nothing extrapolated",
                "breakdown_s": brk}
 
     if rank == 0:
@@ -412,8 +430,9 @@ def run_ours(args):
             "config": {"workload": "AccompBand 25-point (24-step) CFG flow sampler + VAE decode + HiFi-GAN, 20 s clips",
                        "clips_per_gpu": B, "global_clips": clips, "guidance": 3.0, "t_lat": T_LAT,
                        "parallelism": f"dp{world}",
-                       "precision": ("bf16 operands, fp32 accumulate/residual" if args.precision == "bf16" else
-                                     "DiT linears: fp32 operands as TF32 (kind::tf32), bf16 attention core; VAE/vocoder bf16 operands"),
+                       "precision": ("IEEE fp16 GEMM operands (saturating), fp32 accumulate / residual / norms / softmax / router"
+                                     if args.precision == "fp16" else
+                                     "DiT linears: fp32 operands as TF32 (kind::tf32), fp16 attention core; VAE/vocoder fp16 operands"),
                        "l2": "256 MiB buffer written between timed steps (L2 flush)"},
             "dit_latent_frame_evals_per_s": clips * T_LAT * N_EVALS / (ms_samp * 1e-3),
             "stage_ms": {"sampler": ms_samp, "vae_decode": ms_vae, "vocoder": ms_voc},
@@ -425,8 +444,7 @@ def run_ours(args):
                              else "pinned host -> H2D -> generate -> D2H")},
             "gpu_launches": int(launches) * args.steps * 2 if launches else None,
             "gpu_launches_per_step": int(launches) if launches else None,
-            "kernel_family_ms": {k: round(v["ms"], 3) for k, v in fam.items()} if fam else None,
-            "roofline": roof, "cpu_baseline": cpu, "clocks": clk, "bf16_fast_mode": fast,
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clk, "clip0_wav_sha1": clip0_sha1,
         }
         print(json.dumps(line))
     if use_dist:
@@ -441,9 +459,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=1, help="clips per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-fast-mode", action="store_true", help="skip the extra bf16-mode measurement")
-    ap.add_argument("--precision", default="tf32", choices=["bf16", "tf32"],
-                    help="GEMM operand format of the DiT: bf16 (default) or fp32-as-TF32 (accuracy mode)")
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "tf32"],
+                    help="GEMM operand format of the DiT: fp16 (default) or fp32-as-TF32 (twice the operand bytes)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

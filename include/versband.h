@@ -54,7 +54,7 @@ int vb_check_device(void);
 /* ------------------------------------------------------------------------------------------
  * vb_gemm — the tensor-core workhorse (tcgen05.mma, TMEM accumulator, TMA-fed smem pipeline).
  *
- *   D[g][m, n] = epilogue( sum_k A[g][row(m,k), k] * B[g][n, k] )      bf16 x bf16 -> fp32
+ *   D[g][m, n] = epilogue( sum_k A[g][row(m,k), k] * B[g][n, k] )      fp16 x fp16 -> fp32
  *
  * Replaces every nn.Linear / F.linear on the path (flag_large_dit_moe.py:340,389-390,406,
  * 484-485; vocal2music_moe.py:119,132,141-142,242,290), the bmm's of attention
@@ -62,13 +62,13 @@ int vb_check_device(void);
  * addressing below — every Conv1d / ConvTranspose1d (vocal2music_moe.py:327,340-350,358;
  * autoencoder1d.py:180-231,276-313,432-478; vocoder/hifigan/modules/hifigan.py:27-58,108-141).
  *
- * A is a rank-4 strided bf16 tensor (dim0 = reduction index, contiguous). For k-block kb
+ * A is a rank-4 strided fp16 tensor (dim0 = reduction index, contiguous). For k-block kb
  * (64 elements) of tile row m0 the TMA box is fetched at coordinates
  *     c0 = (kb % kpt) * 64,  c1 = m0 + (kb / kpt) * dil - pad,
  *     c2 = g1*a_c2_g1 + g2*a_c2_g2,  c3 = g1*a_c3_g1 + g2*a_c3_g2
  * Out-of-range coordinates read as zero: this gives "same" conv padding, ragged M/K tails
  * and channel padding for free. A plain GEMM uses kpt = K/64, dil = pad = 0.
- * B is a rank-3 strided bf16 tensor (k, n, group), i.e. PyTorch's [out, in] weight layout,
+ * B is a rank-3 strided fp16 tensor (k, n, group), i.e. PyTorch's [out, in] weight layout,
  * fetched at (kb*64, n0, g1*b_c2_g1 + g2*b_c2_g2 + tile_group[m_tile]*b_c2_tile).
  * ------------------------------------------------------------------------------------------ */
 typedef struct vb_gemm_args {
@@ -112,8 +112,8 @@ typedef struct vb_gemm_args {
   int32_t accumulate;    /* v += out_f32[...] (previous contents) */
   float* out_f32;        /* optional fp32 store */
   int64_t out_ld, out_g1, out_g2; /* elements */
-  /* optional bf16 store of act_out(v * out_scale): the next GEMM's A operand */
-  void* out_bf16;
+  /* optional fp16 store of act_out(v * out_scale): the next GEMM's A operand */
+  void* out_fp16;
   int32_t outb_f32; /* 1: this slot stores fp32 (the next GEMM runs in operand_f32 mode) */
   int64_t outb_ld, outb_g1, outb_g2;
   int32_t act_out;
@@ -123,9 +123,9 @@ typedef struct vb_gemm_args {
   const float* rope_cs; /* [T][head_dim/2][2] (cos, sin), fp32; NULL = no rotation (VAE attn) */
   int32_t T, heads, head_dim, Tp;
   int32_t qkv_sec0; /* first section present: 0 = q|k|v (N = 3*H*hd), 1 = k|v only (N = 2*H*hd) */
-  void* q_out;  /* bf16 [B, heads, T, head_dim] (rotated) */
-  void* k_out;  /* bf16 [B, heads, T, head_dim] (rotated) */
-  void* vt_out; /* bf16 [B, heads, head_dim, Tp]  (V transposed: PV GEMM's K-major B) */
+  void* q_out;  /* fp16 [B, heads, T, head_dim] (rotated) */
+  void* k_out;  /* fp16 [B, heads, T, head_dim] (rotated) */
+  void* vt_out; /* fp16 [B, heads, head_dim, Tp]  (V transposed: PV GEMM's K-major B) */
   /* ---- VB_EPI_ROUTE: the caption cross-attention that feeds the Band-MoE caption gate
    * (vocal2music_moe.py:117-131: MultiheadAttention -> gating Linear) collapsed into this GEMM.
    * B holds, per batch g1 and head h, the 96 rows (scale * K_h W_q,h) (keys beyond the text length are
@@ -146,7 +146,7 @@ int vb_gemm(const vb_gemm_args* args, void* stream);
  * in one launch, and nn.MultiheadAttention's attention core (vocal2music_moe.py:119):
  *   out[b*T+t, h*hd:(h+1)*hd] = softmax(q k_self^T * scale) v_self
  *                              + tanh(gate[h]) * softmax(q k_text^T * scale) v_text
- * Either segment may be absent (k_self == NULL or k_text == NULL). All operands bf16:
+ * Either segment may be absent (k_self == NULL or k_text == NULL). All operands fp16:
  *   q        element strides (q_st token, q_sh head, q_sb batch), head_dim contiguous
  *   k_self   [B, H, T, hd]      vt_self  [B, H, hd, Tp]   (V transposed, Tp % 8 == 0)
  *   k_text   [B, H, L, hd]      vt_text  [B, H, hd, Lp]   (L <= 128, Lp % 8 == 0)
@@ -160,7 +160,7 @@ typedef struct vb_attn_args {
   const void* k_text;
   const void* vt_text;
   const float* gate;
-  void* out_bf16; /* [B*T, H*hd] */
+  void* out_fp16; /* [B*T, H*hd] */
   float* out_f32; /* optional, same layout */
   int32_t B, T, H, hd, Tp, L, Lp;
   float scale;
@@ -177,7 +177,7 @@ long long vb_launch_count(void);
  * on the launching stream; vb_prof_report() synchronises and returns total ms / launch count per
  * kernel family (0 gemm, 1 norm, 2 softmax, 3 attn_small, 4 router, 5 moe_sort, 6 elementwise,
  * 7 layout, 8 groupnorm, 9 conv_post). Not usable during CUDA-graph capture. */
-/* haloed small-C conv path inside vb_gemm (C_in <= 64, N <= 64, bf16): 0 off, 1 on */
+/* haloed small-C conv path inside vb_gemm (C_in <= 64, N <= 64, fp16): 0 off, 1 on */
 int vb_set_conv_halo(int mode);
 /* 2-CTA (tcgen05 cta_group::2, cluster of 2) GEMM path: 0 off, 1 heuristic, 2 whenever legal */
 int vb_set_gemm2(int mode);
@@ -198,27 +198,27 @@ int vb_prof_enable(int on);
 int vb_prof_report(double* ms_by_kind, long long* count_by_kind, int nkinds);
 
 /* ------------------------------------------------------------------------------------------
- * Row-wise ops of the DiT step (fp32 in, bf16 GEMM operand and/or fp32 out)
+ * Row-wise ops of the DiT step (fp32 in, fp16 GEMM operand and/or fp32 out)
  * ------------------------------------------------------------------------------------------ */
 /* kind 0: RMSNorm (flag_large_dit_moe.py:52-77); kind 1: LayerNorm (vocal2music_moe.py:274-276,
  * flag_large_dit_moe.py:156). y = norm(x)[*w][+b]; then adaLN modulate y*(1+scale[bi])+shift[bi]
  * (flag_large_dit_moe.py:80-81) with bi = row / rows_per_batch, vectors at stride mod_ld. */
 int vb_norm_mod(int kind, const float* x, const float* w, const float* b, const float* shift,
-                const float* scale, int64_t mod_ld, int rows_per_batch, float eps, void* out_bf16,
+                const float* scale, int64_t mod_ld, int rows_per_batch, float eps, void* out_fp16,
                 float* out_f32, int rows, int D, void* stream);
-/* P[r,:n] = softmax(S[r,:n]) as bf16, P[r,n:ldp] = 0 (SDPA softmax, flag_large_dit_moe.py:381;
+/* P[r,:n] = softmax(S[r,:n]) as fp16, P[r,n:ldp] = 0 (SDPA softmax, flag_large_dit_moe.py:381;
  * autoencoder1d.py:265) */
-int vb_softmax_rows(const float* S, int64_t lds, void* P_bf16, int64_t ldp, int64_t rows, int n,
+int vb_softmax_rows(const float* S, int64_t lds, void* P_fp16, int64_t ldp, int64_t rows, int n,
                     void* stream);
-/* attention against a short K/V (L <= 128 keys), fp32 K,V [B,L,*] with row pitch kv_ld; q bf16 with element
+/* attention against a short K/V (L <= 128 keys), fp32 K,V [B,L,*] with row pitch kv_ld; q fp16 with element
  * strides (batch, token, head). out[b*T+t, h*hd+d] = base + tanh(gate[h]) * ctx (gate/base
  * optional): text cross-attention flag_large_dit_moe.py:388-402, MoE MHA vocal2music_moe.py:119 */
-int vb_attn_smallkv(const void* q_bf16, int64_t q_sb, int64_t q_st, int64_t q_sh, const float* K,
+int vb_attn_smallkv(const void* q_fp16, int64_t q_sb, int64_t q_st, int64_t q_sh, const float* K,
                     const float* V, int64_t kv_ld, int B, int T, int H, int hd, int L, float scale,
-                    const float* gate, const float* base, void* out_bf16, float* out_f32,
+                    const float* gate, const float* base, void* out_fp16, float* out_f32,
                     void* stream);
 /* [cos(t f_i), sin(t f_i)] (flag_large_dit_moe.py:109-127); freqs = host table of f_i */
-int vb_timestep_embed(const int64_t* t, const float* freqs, float* out_f32, void* out_bf16, int B,
+int vb_timestep_embed(const int64_t* t, const float* freqs, float* out_f32, void* out_fp16, int B,
                       int dim, void* stream);
 
 /* out[b,:] = mean_l x[b,l,:] (caption pooling, vocal2music_moe.py:410-412) */
@@ -233,12 +233,12 @@ int vb_linear_small(const float* x, int64_t ldx, const float* W, const float* bi
 /* Gumbel-softmax router: e0 [N,2], e1/e2 [N,E] are the Exp(1) draws the reference obtains from
  * torch.empty_like(logits).exponential_() (:82). Emits hard top-1 indices and the combined
  * weights scale_g[n] = ((1-p)+p) * group_mask_g[n]. */
-int vb_router(const float* cap_feat, const void* cap_feat_bf16, const float* Wc, const float* bc, const float* ac_logits,
+int vb_router(const float* cap_feat, const void* cap_feat_fp16, const float* Wc, const float* bc, const float* ac_logits,
               int ac_ld, const float* hl_logits, int hl_ld, const float* e0, const float* e1, const float* e2, float tau,
               int N, int T, int D, int E, int32_t* idx_c, int32_t* idx_a, float* scale_c,
               float* scale_a, float* cap_logits_out, int32_t* bucket_count, float* usage,
               int32_t* slot_c, int32_t* slot_a, const float* cap_partial, int n_heads, void* stream);
-/* Features may be fp32 (cap_feat) or bf16 (cap_feat_bf16); or, with cap_partial != NULL, the caption
+/* Features may be fp32 (cap_feat) or fp16 (cap_feat_fp16); or, with cap_partial != NULL, the caption
  * gate logits are bc + the sum over heads (in head order) of cap_partial[n][h][E] written by a
  * VB_EPI_ROUTE GEMM and cap_feat / Wc are not read. With bucket_count != NULL the router also
  * claims an (unordered) slot per (token, group) in its expert bucket with atomics; vb_moe_finalize
@@ -273,8 +273,8 @@ int vb_moe_sort(const int32_t* idx_c, const int32_t* idx_a, const float* scale_c
                 const float* scale_a, int N, int E, int32_t* row_map, float* row_scale,
                 int32_t* tile_group, int32_t* m_tiles_used, int max_rows, float* lb_out,
                 void* stream);
-int vb_gather_rows(const void* x_bf16, const int32_t* row_map, const int32_t* m_tiles_used,
-                   int n_tokens, int D, void* out_bf16, int max_rows, void* stream);
+int vb_gather_rows(const void* x_fp16, const int32_t* row_map, const int32_t* m_tiles_used,
+                   int n_tokens, int D, void* out_fp16, int max_rows, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Elementwise / layout / GroupNorm / vocoder tail
@@ -282,20 +282,20 @@ int vb_gather_rows(const void* x_bf16, const int32_t* row_map, const int32_t* m_
 /* out = act(alpha*a + beta*b), rows x D fp32 in, each row written `rep` times (rep=2: nearest x2
  * upsample, autoencoder1d.py:288) */
 int vb_ew(const float* a, const float* b, float alpha, float beta, int act, float slope,
-          float* out_f32, void* out_bf16, int64_t rows, int D, int rep, void* stream);
-/* [B,C,T] fp32 -> channels-last bf16 [B,T,Cp] (zero padded), times scale */
+          float* out_f32, void* out_fp16, int64_t rows, int D, int rep, void* stream);
+/* [B,C,T] fp32 -> channels-last fp16 [B,T,Cp] (zero padded), times scale */
 int vb_nct_to_ntc(const float* in, float scale, void* out, int B, int C, int T, int Cp, int out_is_f32,
                   void* stream);
 /* e_u == NULL: x[b,c,t] = e_c[b,t,c]; else CFG + Euler (cfm1_audio.py:160):
  * x[b,c,t] += dt * (e_u + s*(e_c - e_u)).
  * x_cl != NULL (C <= 32): the new x is also written channels-last to x_cl[r][b][t][0..C) for r < x_cl_rep
- * ([rep][B][T][32], bf16 or fp32): the next DiT evaluation's stem operand for each CFG branch. */
+ * ([rep][B][T][32], fp16 or fp32): the next DiT evaluation's stem operand for each CFG branch. */
 int vb_ntc_to_nct(const float* e_c, const float* e_u, int64_t ld, float s, float dt, float* x, int B,
                   int C, int T, void* x_cl, int x_cl_is_f32, int x_cl_rep, void* stream);
 int vb_embed_rows(const int64_t* idx, const float* table, int V, int D, void* out, int64_t rows,
                   int out_is_f32, void* stream);
 /* AvgPool1d(2) of one or two branches, summed (vocal2music_moe.py:343,349,392) */
-int vb_pool2_sum(const float* a, const float* b, int B, int Tin, int Tout, int D, void* out_bf16,
+int vb_pool2_sum(const float* a, const float* b, int B, int Tin, int Tout, int D, void* out_fp16,
                  float* out_f32, void* stream);
 /* GroupNorm over channels-last [B,T,C] (autoencoder1d.py:165-166) */
 /* scratch: B*G*VB_GN_SPLIT*2 doubles (partial sums of the split-T first pass) */
@@ -303,9 +303,9 @@ int vb_pool2_sum(const float* a, const float* b, int B, int Tin, int Tout, int D
 int vb_gn_stats(const float* x, int B, int T, int C, int G, float eps, float* mean, float* rstd,
                 void* scratch, void* stream);
 int vb_gn_apply(const float* x, const float* mean, const float* rstd, const float* w,
-                const float* bias, int B, int T, int C, int G, int act, void* out_bf16, void* stream);
+                const float* bias, int B, int T, int C, int G, int act, void* out_fp16, void* stream);
 /* HiFi-GAN conv_post + tanh (vocoder/hifigan/modules/hifigan.py:139-141); w is [k][C] fp32 */
-int vb_conv_post(const void* x_bf16, const float* w, float bias, int B, int T, int C, int k,
+int vb_conv_post(const void* x_fp16, const float* w, float bias, int B, int T, int C, int k,
                  float* wav, void* stream);
 
 #ifdef __cplusplus

@@ -28,8 +28,10 @@ def _library_present():
     """The in-tree .so is git-ignored: a fresh checkout has none until `__graft_entry__.build()` ran. Building it
     here (only when it is missing altogether) is test infrastructure — the product path itself still refuses to
     run without the library (versband_b200._lib.lib)."""
+    import shutil
+
     from versband_b200 import build
 
-    if not build.LIB.exists():
-        build.build()
+    if not build.LIB.exists() and (os.path.exists(build.NVCC) or shutil.which("nvcc")):
+        build.build()  # hosts without nvcc: the tests that need the library fail on their own, loudly
     yield

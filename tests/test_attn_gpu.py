@@ -8,7 +8,7 @@ pytestmark = pytest.mark.gpu
 
 from versband_b200 import ops  # noqa: E402
 
-BF = torch.bfloat16
+H16 = torch.float16
 
 
 def ref_attn(q, k, v, scale):
@@ -18,7 +18,7 @@ def ref_attn(q, k, v, scale):
 
 def make_vt(v, pad):
     B, H, S, hd = v.shape
-    vt = torch.zeros(B, H, hd, pad, device=v.device, dtype=BF)
+    vt = torch.zeros(B, H, hd, pad, device=v.device, dtype=H16)
     vt[..., :S] = v.transpose(2, 3)
     return vt
 
@@ -31,15 +31,15 @@ def test_attn_fused(T, mode, hd):
     B, H, L = 2, 4, 80
     Tp, Lp = (T + 7) // 8 * 8, 80
     scale = 1 / math.sqrt(hd)
-    q = (torch.randn(B, H, T, hd, device="cuda") * 1.5).to(BF)
-    k = (torch.randn(B, H, T, hd, device="cuda") * 1.5).to(BF)
-    v = torch.randn(B, H, T, hd, device="cuda").to(BF)
-    kt = (torch.randn(B, H, L, hd, device="cuda") * 1.5).to(BF)
-    vtx = torch.randn(B, H, L, hd, device="cuda").to(BF)
+    q = (torch.randn(B, H, T, hd, device="cuda") * 1.5).to(H16)
+    k = (torch.randn(B, H, T, hd, device="cuda") * 1.5).to(H16)
+    v = torch.randn(B, H, T, hd, device="cuda").to(H16)
+    kt = (torch.randn(B, H, L, hd, device="cuda") * 1.5).to(H16)
+    vtx = torch.randn(B, H, L, hd, device="cuda").to(H16)
     gate = torch.randn(H, device="cuda")
-    out = torch.zeros(B * T, H * hd, device="cuda", dtype=BF)
+    out = torch.zeros(B * T, H * hd, device="cuda", dtype=H16)
     outf = torch.zeros(B * T, H * hd, device="cuda")
-    kw = dict(B=B, T=T, H=H, hd=hd, scale=scale, out_bf16=out, out_f32=outf)
+    kw = dict(B=B, T=T, H=H, hd=hd, scale=scale, out_fp16=out, out_f32=outf)
     ref = torch.zeros(B, H, T, hd, device="cuda")
     if mode in ("self", "both"):
         kw.update(k_self=k, vt_self=make_vt(v, Tp), Tp=Tp)
@@ -63,9 +63,9 @@ def test_attn_fused_token_major_q():
     torch.manual_seed(0)
     B, H, T, hd, L = 2, 8, 750, 96, 80
     D = H * hd
-    qf = (torch.randn(B * T, D, device="cuda")).to(BF)
-    kt = torch.randn(B, H, L, hd, device="cuda").to(BF)
-    vtx = torch.randn(B, H, L, hd, device="cuda").to(BF)
+    qf = (torch.randn(B * T, D, device="cuda")).to(H16)
+    kt = torch.randn(B, H, L, hd, device="cuda").to(H16)
+    vtx = torch.randn(B, H, L, hd, device="cuda").to(H16)
     out = torch.zeros(B * T, D, device="cuda")
     ops.attn_fused(qf, (D, hd, T * D), B=B, T=T, H=H, hd=hd, scale=hd ** -0.5, k_text=kt, vt_text=make_vt(vtx, 80),
                    L=L, Lp=80, out_f32=out)

@@ -25,19 +25,19 @@ def halo_on():
 def test_halo_conv_matches_conv1d(C, k, dil):
     torch.manual_seed(C + k + dil)
     B, T = 2, 20000
-    x = torch.randn(B, T, C, device="cuda").bfloat16()
-    w = (torch.randn(C, C, k, device="cuda") * 0.1).bfloat16()
-    wp = torch.zeros(C, k, 64, device="cuda", dtype=torch.bfloat16)
+    x = torch.randn(B, T, C, device="cuda").half()
+    w = (torch.randn(C, C, k, device="cuda") * 0.1).half()
+    wp = torch.zeros(C, k, 64, device="cuda", dtype=torch.float16)
     wp[:, :, :C] = w.permute(0, 2, 1)
     wp = wp.reshape(C, k * 64)
     bias = torch.randn(C, device="cuda")
     res = torch.randn(B, T, C, device="cuda")
     out = torch.zeros(B, T, C, device="cuda")
-    nxt = torch.zeros(B, T, C, device="cuda", dtype=torch.bfloat16)
+    nxt = torch.zeros(B, T, C, device="cuda", dtype=torch.float16)
     pad = (k * dil - dil) // 2
     n0 = _lib.launch_count()
     ops.gemm(x, wp, M=T, G1=B, kpt=1, dil=dil, pad=pad, a_c2=(1, 0), bias=bias, residual=res, out_f32=out, out_ld=C,
-             out_g=(T * C, 0), out_bf16=nxt, outb_ld=C, outb_g=(T * C, 0), act_out=ops.ACT_LRELU, act_out_slope=0.1)
+             out_g=(T * C, 0), out_fp16=nxt, outb_ld=C, outb_g=(T * C, 0), act_out=ops.ACT_LRELU, act_out_slope=0.1)
     ref = F.conv1d(x.float().transpose(1, 2), w.float(), bias, padding=pad, dilation=dil).transpose(1, 2) + res
     err = float((out - ref).abs().max() / ref.abs().max())
     assert err < 2e-5, err

@@ -27,7 +27,7 @@ def weights():
 
 @pytest.fixture(scope="module")
 def engine(weights):
-    return DiTEngine(weights, device=DEV, precision="bf16")
+    return DiTEngine(weights, device=DEV, precision="fp16")
 
 
 def run_engine(engine, x, t, midi, beats, cap, expo, T):
@@ -58,7 +58,7 @@ def test_forward_vs_oracle(engine, weights, B, T):
     ctx = {"c_crossattn": cap, "c_concat": {"midi": midi, "beats": beats}}
     v_ref, lb_ref, aux_ref = R.dit_forward(weights, x, t, ctx, depth=4, n_heads=8, expo=expo, return_aux=True)
     v, lb, aux, _ = run_engine(engine, x, t, midi, beats, cap, expo, T)
-    # router decisions: identical wherever the oracle's decision margin exceeds bf16 noise
+    # router decisions: identical wherever the oracle's decision margin exceeds fp16 noise
     agree = total = 0
     for k in range(4):
         for name, key in (("idx_c", "cap_idx"), ("idx_a", "ac_idx")):
@@ -68,7 +68,7 @@ def test_forward_vs_oracle(engine, weights, B, T):
     rate = agree / total
     print(f"router agreement {agree}/{total} = {rate:.4f}; v rel err {rel(v, v_ref):.3e}")
     assert rate > 0.97
-    # tokens whose routing agrees in every block must match to bf16 accuracy
+    # tokens whose routing agrees in every block must match to fp16 accuracy
     ok = torch.ones(B * T, dtype=torch.bool)
     for k in range(4):
         ok &= aux[k]["idx_c"].cpu().long() == aux_ref[k]["cap_idx"]

@@ -21,7 +21,7 @@ def force_two_cta():
 
 
 @pytest.mark.parametrize("M,N,K", [(1500, 2304, 768), (750, 768, 768), (300, 256, 128), (1500, 192, 512), (129, 1024, 64)])
-def test_plain_bf16(M, N, K):
+def test_plain_fp16(M, N, K):
     G.test_plain(M, N, K, 0)
 
 
@@ -31,7 +31,7 @@ def test_plain_tf32(M, N, K):
 
 
 def test_epilogues_and_batched():
-    G.test_epilogue_bias_act_gate_residual_bf16()
+    G.test_epilogue_bias_act_gate_residual_fp16()
     G.test_swiglu_pairs()
     G.test_qkv_rope_epilogue()
     G.test_batched_attention_shapes()
@@ -46,8 +46,8 @@ def test_many_tiles_persistent_loop():
     """More tile pairs than clusters: exercises accumulator double-buffering across the pair."""
     torch.manual_seed(0)
     M, N, K = 20000, 512, 256
-    a = torch.randn(M, K, device="cuda").bfloat16()
-    b = torch.randn(N, K, device="cuda").bfloat16()
+    a = torch.randn(M, K, device="cuda").half()
+    b = torch.randn(N, K, device="cuda").half()
     out = torch.zeros(M, N, device="cuda")
     ops.gemm(a, b, out_f32=out, out_ld=N)
     G.close(out, a.float() @ b.float().t())

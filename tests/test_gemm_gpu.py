@@ -1,6 +1,6 @@
 """vb_gemm (tcgen05/TMA) against a plain PyTorch fp32 reference of the same op.
 
-Inputs are rounded to bf16 first so products are exact in fp32; the only difference left is
+Inputs are rounded to fp16 first so products are exact in fp32; the only difference left is
 the summation order, hence the tight tolerance."""
 import pytest
 import torch
@@ -12,7 +12,7 @@ from versband_b200 import ops  # noqa: E402
 
 
 def bf(x):
-    return x.to(torch.bfloat16)
+    return x.to(torch.float16)
 
 
 def close(got, ref, tol=2e-5):
@@ -58,7 +58,7 @@ def test_ragged_k_oob_fill():
     close(out, a.float() @ b.float().t())
 
 
-def test_epilogue_bias_act_gate_residual_bf16():
+def test_epilogue_bias_act_gate_residual_fp16():
     torch.manual_seed(2)
     B, T, N, K = 2, 375, 768, 768
     M = B * T
@@ -68,9 +68,9 @@ def test_epilogue_bias_act_gate_residual_bf16():
     gate = torch.randn(B, N, device="cuda")
     res = torch.randn(M, N, device="cuda")
     out = torch.zeros(M, N, device="cuda")
-    outb = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    outb = torch.zeros(M, N, device="cuda", dtype=torch.float16)
     ops.gemm(a, w, bias=bias, act=ops.ACT_SILU, gate=gate, gate_rows=T, gate_ld=N, residual=res,
-             out_f32=out, out_ld=N, out_bf16=outb, outb_ld=N, act_out=ops.ACT_LRELU,
+             out_f32=out, out_ld=N, out_fp16=outb, outb_ld=N, act_out=ops.ACT_LRELU,
              act_out_slope=0.1, out_scale=0.5, alpha=0.25)
     v = F.silu((a.float() @ w.float().t()) * 0.25 + bias)
     v = v * gate.repeat_interleave(T, 0) + res
@@ -97,8 +97,8 @@ def test_swiglu_pairs():
     w1 = bf(torch.randn(H, K, device="cuda") * 0.05)
     w3 = bf(torch.randn(H, K, device="cuda") * 0.05)
     w13 = torch.stack([w1, w3], 1).reshape(2 * H, K).contiguous()
-    h = torch.zeros(M, H, device="cuda", dtype=torch.bfloat16)
-    ops.gemm(a, w13, swiglu=True, out_bf16=h, outb_ld=H)
+    h = torch.zeros(M, H, device="cuda", dtype=torch.float16)
+    ops.gemm(a, w13, swiglu=True, out_fp16=h, outb_ld=H)
     ref = F.silu(a.float() @ w1.float().t()) * (a.float() @ w3.float().t())
     close(h, ref, 6e-3)
 
@@ -114,7 +114,7 @@ def test_conv1d_implicit(Cin, Cout, k, dil, T):
     x = xbuf[:, :, :Cin]
     w = bf(torch.randn(Cout, Cin, k, device="cuda") * 0.1)
     kpt = (Cin + 63) // 64
-    wp = torch.zeros(Cout, k, kpt * 64, device="cuda", dtype=torch.bfloat16)
+    wp = torch.zeros(Cout, k, kpt * 64, device="cuda", dtype=torch.float16)
     wp[:, :, :Cin] = w.permute(0, 2, 1)
     wp = wp.reshape(Cout, k * kpt * 64)
     pad = (k * dil - dil) // 2
@@ -139,10 +139,10 @@ def test_batched_attention_shapes():
     ref = torch.einsum("bhtd,bhsd->bhts", q.float(), k.float()) * hd ** -0.5
     close(s[..., :T], ref)
     p = bf(torch.softmax(ref, -1))
-    pbuf = torch.zeros(B, H, T, Tp, device="cuda", dtype=torch.bfloat16)
+    pbuf = torch.zeros(B, H, T, Tp, device="cuda", dtype=torch.float16)
     pbuf[..., :T] = p
     v = bf(torch.randn(B, H, T, hd, device="cuda"))
-    vt = torch.zeros(B, H, hd, Tp, device="cuda", dtype=torch.bfloat16)
+    vt = torch.zeros(B, H, hd, Tp, device="cuda", dtype=torch.float16)
     vt[..., :T] = v.transpose(2, 3)
     o = torch.zeros(B * T, H * hd, device="cuda")
     ops.gemm(pbuf.view(B * H, T, Tp)[:, :, :T], vt.view(B * H, hd, Tp)[:, :, :T], M=T, N=hd, K=T,
@@ -161,9 +161,9 @@ def test_qkv_rope_epilogue():
     freqs = 1.0 / (10000.0 ** (torch.arange(0, hd, 2, device="cuda").float() / hd))
     ang = torch.outer(torch.arange(T, device="cuda").float(), freqs)
     cs = torch.stack([ang.cos(), ang.sin()], -1).contiguous()
-    q = torch.zeros(B, H, T, hd, device="cuda", dtype=torch.bfloat16)
+    q = torch.zeros(B, H, T, hd, device="cuda", dtype=torch.float16)
     k = torch.zeros_like(q)
-    vt = torch.zeros(B, H, hd, Tp, device="cuda", dtype=torch.bfloat16)
+    vt = torch.zeros(B, H, hd, Tp, device="cuda", dtype=torch.float16)
     ops.gemm(x, w, mode=ops.EPI_QKV_ROPE, rope_cs=cs, T=T, heads=H, head_dim=hd, Tp=Tp,
              q_out=q, k_out=k, vt_out=vt)
     y = (x.float() @ w.float().t()).view(B, T, 3, H, hd)
@@ -200,7 +200,7 @@ def test_grouped_tiles_and_row_map():
         off += int(counts[e])
     used = torch.tensor([int(padded.sum()) // 128], dtype=torch.int32, device="cuda")
     x = bf(torch.randn(ntok, K, device="cuda"))
-    xs = torch.zeros(max_rows, K, device="cuda", dtype=torch.bfloat16)
+    xs = torch.zeros(max_rows, K, device="cuda", dtype=torch.float16)
     xs[slot_of] = x
     w = bf(torch.randn(E, N, K, device="cuda") * 0.05)
     scale = torch.rand(max_rows, device="cuda")
@@ -220,7 +220,7 @@ def test_transposed_conv_polyphase_addressing():
     w = bf(torch.randn(Cin, Cout, k, device="cuda") * 0.1)
     Q = k // u
     # phase r, tap q (time s - q) uses w[:, :, r + u*q]; taps stored reversed so time = s - (Q-1) + j
-    wp = torch.zeros(u, Cout, Q, 64, device="cuda", dtype=torch.bfloat16)
+    wp = torch.zeros(u, Cout, Q, 64, device="cuda", dtype=torch.float16)
     for r in range(u):
         for j in range(Q):
             qq = Q - 1 - j
@@ -271,7 +271,7 @@ def test_tf32_conv_and_fp32_operand_output():
     wp[:, :, :Cin] = w.permute(0, 2, 1)
     wp = wp.reshape(Cout, k * kpt * 32)
     nxt = torch.zeros(B, T, Cout, device="cuda")  # fp32 "operand output" slot
-    ops.gemm(x, wp, M=T, G1=B, kpt=kpt, dil=1, pad=k // 2, a_c2=(1, 0), out_bf16=nxt, outb_ld=Cout,
+    ops.gemm(x, wp, M=T, G1=B, kpt=kpt, dil=1, pad=k // 2, a_c2=(1, 0), out_fp16=nxt, outb_ld=Cout,
              outb_g=(T * Cout, 0), act_out=ops.ACT_LRELU, act_out_slope=0.1)
     ref = F.leaky_relu(F.conv1d(x.transpose(1, 2), w, padding=k // 2), 0.1).transpose(1, 2)
     close(nxt, ref, 2e-5)

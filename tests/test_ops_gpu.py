@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 from oracle import accompband_ref as R  # noqa: E402
 from versband_b200 import ops  # noqa: E402
 
-BF = torch.bfloat16
+H16 = torch.float16
 torch.set_grad_enabled(False)
 
 
@@ -27,14 +27,14 @@ def test_norm_mod(kind):
     w = torch.randn(D, device="cuda")
     mod = torch.randn(B, 4 * D, device="cuda")
     out = torch.empty(B * T, D, device="cuda")
-    outb = torch.empty(B * T, D, device="cuda", dtype=BF)
+    outb = torch.empty(B * T, D, device="cuda", dtype=H16)
     if kind == 0:
         ops.norm_mod(x, kind=0, w=w, shift=mod[:, D:], scale=mod[:, 2 * D:], mod_ld=4 * D, rows_per_batch=T,
-                     eps=1e-5, out_f32=out, out_bf16=outb)
+                     eps=1e-5, out_f32=out, out_fp16=outb)
         ref = R.rms_norm(x.view(B, T, D), w, 1e-5)
     else:
         ops.norm_mod(x, kind=1, shift=mod[:, D:], scale=mod[:, 2 * D:], mod_ld=4 * D, rows_per_batch=T, eps=1e-6,
-                     out_f32=out, out_bf16=outb)
+                     out_f32=out, out_fp16=outb)
         ref = F.layer_norm(x.view(B, T, D), (D,), None, None, 1e-6)
     ref = R.modulate(ref, mod[:, D:2 * D], mod[:, 2 * D:3 * D]).reshape(B * T, D)
     close(out, ref, 2e-6)
@@ -44,7 +44,7 @@ def test_norm_mod(kind):
 def test_softmax_rows():
     torch.manual_seed(1)
     S = torch.randn(500, 752, device="cuda") * 4
-    P = torch.full((500, 752), 7.0, device="cuda", dtype=BF)
+    P = torch.full((500, 752), 7.0, device="cuda", dtype=H16)
     ops.softmax_rows(S, 752, P, 752, 500, 750)
     close(P[:, :750], torch.softmax(S[:, :750], -1), 5e-3)
     assert (P[:, 750:] == 0).all()
@@ -53,7 +53,7 @@ def test_softmax_rows():
 def test_attn_smallkv():
     torch.manual_seed(2)
     B, T, H, hd, L = 2, 200, 8, 96, 80
-    q = torch.randn(B, T, H * hd, device="cuda").to(BF)
+    q = torch.randn(B, T, H * hd, device="cuda").to(H16)
     kv = torch.randn(B * L, 2 * H * hd, device="cuda")
     gate = torch.randn(H, device="cuda")
     base = torch.randn(B * T, H * hd, device="cuda")
@@ -120,8 +120,8 @@ def test_moe_sort_and_gather():
     used = torch.zeros(1, dtype=torch.int32, device=d)
     lb = torch.zeros(1, device=d)
     ops.moe_sort(idx_c, idx_a, sc, sa, N, E, row_map, row_scale, tile_group, used, max_rows, lb)
-    x = torch.randn(N, D, device=d).to(BF)
-    xs = torch.full((max_rows, D), 9.0, device=d, dtype=BF)
+    x = torch.randn(N, D, device=d).to(H16)
+    xs = torch.full((max_rows, D), 9.0, device=d, dtype=H16)
     ops.gather_rows(x, row_map, used, N, xs, max_rows)
     torch.cuda.synchronize()
     rm, tg, nt = row_map.cpu(), tile_group.cpu(), int(used)
@@ -152,7 +152,7 @@ def test_layout_embed_pool_ew():
     torch.manual_seed(5)
     d = "cuda"
     x = torch.randn(2, 20, 75, device=d)
-    cl = torch.full((2, 75, 32), 5.0, device=d, dtype=BF)
+    cl = torch.full((2, 75, 32), 5.0, device=d, dtype=H16)
     ops.nct_to_ntc(x, cl, scale=0.5)
     close(cl[:, :, :20], (x * 0.5).transpose(1, 2), 5e-3)
     assert (cl[:, :, 20:] == 0).all()
@@ -167,7 +167,7 @@ def test_layout_embed_pool_ew():
     assert (xcl[:, :, 20:] == 0).all()
     idx = torch.randint(0, 130, (3, 50), device=d)
     tab = torch.randn(130, 64, device=d)
-    out = torch.empty(3, 50, 64, device=d, dtype=BF)
+    out = torch.empty(3, 50, 64, device=d, dtype=H16)
     ops.embed_rows(idx, tab, out)
     close(out, tab[idx], 5e-3)
     a, b = torch.randn(2, 20, 64, device=d), torch.randn(2, 20, 64, device=d)
@@ -187,14 +187,14 @@ def test_groupnorm_and_conv_post():
     x = torch.randn(B, T, C, device=d) * 2 + 1
     w, b = torch.randn(C, device=d), torch.randn(C, device=d)
     mean, rstd = torch.empty(B * 32, device=d), torch.empty(B * 32, device=d)
-    out = torch.empty(B, T, C, device=d, dtype=BF)
+    out = torch.empty(B, T, C, device=d, dtype=H16)
     ops.gn_stats(x, B, T, C, 32, 1e-6, mean, rstd)
     ops.gn_apply(x, mean, rstd, w, b, B, T, C, 32, ops.ACT_SILU, out)
     ref = F.silu(F.group_norm(x.transpose(1, 2), 32, w, b, 1e-6)).transpose(1, 2)
     close(out, ref, 8e-3)
-    xb = torch.randn(B, 500, 32, device=d).to(BF)
+    xb = torch.randn(B, 500, 32, device=d).to(H16)
     wp = torch.randn(7, 32, device=d) * 0.1
     wav = torch.empty(B, 500, device=d)
     ops.conv_post(xb, wp, 0.05, B, 500, 32, 7, wav)
     ref = torch.tanh(F.conv1d(xb.float().transpose(1, 2), wp.t()[None].contiguous(), torch.tensor([0.05], device=d), padding=3))[:, 0]
-    close(wav, ref, 2e-3)  # bf16 inputs, tanh output; fp32 accumulation order differs
+    close(wav, ref, 2e-3)  # fp16 inputs, tanh output; fp32 accumulation order differs

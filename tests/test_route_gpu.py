@@ -12,7 +12,7 @@ from versband_b200 import ops  # noqa: E402
 from versband_b200.dit import tf32_round  # noqa: E402
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
 @pytest.mark.parametrize("B,T,L", [(2, 750, 80), (1, 130, 96), (3, 64, 17)])
 def test_route_gemm_matches_attention_gate(B, T, L, dtype):
     torch.manual_seed(1)
@@ -25,7 +25,7 @@ def test_route_gemm_matches_attention_gate(B, T, L, dtype):
     bq = torch.randn(D, device=dev) * 0.1
     capg_w = torch.randn(E, D, device=dev) / math.sqrt(D)     # W_gate W_o
     sc = 1.0 / math.sqrt(hd)
-    rnd = (lambda t: t.to(torch.bfloat16).float()) if dtype == torch.bfloat16 else tf32_round
+    rnd = (lambda t: t.to(torch.float16).float()) if dtype == torch.float16 else tf32_round
     xo = rnd(x)
 
     # ---- reference: plain attention -> gate, fp32, on the operand-rounded inputs
@@ -44,7 +44,7 @@ def test_route_gemm_matches_attention_gate(B, T, L, dtype):
     kvo = rnd(kv).to(dtype)
     wk = torch.zeros(B, H * LK, D, device=dev, dtype=dtype)
     ops.gemm(kvo[:, :D].view(B, L, H, hd).permute(0, 2, 1, 3), wqT, M=L, N=D, G1=H, G2=B, a_c2=(1, 0), a_c3=(0, 1),
-             b_c2=(1, 0, 0), out_bf16=wk, outb_ld=D, outb_g=(LK * D, H * LK * D))
+             b_c2=(1, 0, 0), out_fp16=wk, outb_ld=D, outb_g=(LK * D, H * LK * D))
     bs = torch.empty(B, H, LK, device=dev)
     vg = torch.empty(B, H, LK, E, device=dev)
     ops.route_prepare(kv, B, L, H, hd, (bq * sc).contiguous(), capg_w, bs, vg)
@@ -54,5 +54,5 @@ def test_route_gemm_matches_attention_gate(B, T, L, dtype):
              route_vg=vg, route_vg_g1=H * LK * E, out_f32=part, out_ld=H * E)
     got = part.sum(1).view(B, T, E)
     err = float((got - ref).abs().max() / ref.abs().max())
-    tol = 3e-3 if dtype == torch.float32 else 2e-2   # WK is itself a rounded product (tf32 / bf16 operands)
+    tol = 3e-3 if dtype == torch.float32 else 2e-2   # WK is itself a rounded product (tf32 / fp16 operands)
     assert err < tol, f"max rel-to-peak err {err:.3e}"

@@ -22,11 +22,11 @@ def run(M, N, K, dt, G=1, swiglu=False):
                                      out_g=(M * N, 0), bn=bn))
         tiles = ((M + 127) // 128) * ((N + bn - 1) // bn) * G
         res.append(f"bn{bn}:{us:5.1f}({tiles})")
-    name = "tf32" if dt == torch.float32 else "bf16"
+    name = "tf32" if dt == torch.float32 else "fp16"
     print(f"{name} G={G} M={M} N={N} K={K}: " + "  ".join(res), flush=True)
 
 
-for dt in (torch.float32, torch.bfloat16):
+for dt in (torch.float32, torch.float16):
     run(1500, 2304, 768, dt)
     run(1500, 768, 768, dt)
     run(1500, 1024, 768, dt)

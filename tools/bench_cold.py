@@ -31,7 +31,7 @@ def timeit(fn, iters=10):
 
 
 M, N, K = 1500, 2304, 768
-for dt in (torch.float32, torch.bfloat16):
+for dt in (torch.float32, torch.float16):
     a = torch.randn(M, K, device="cuda").to(dt)
     ws = [torch.randn(N, K, device="cuda").to(dt) for _ in range(REP)]   # 24 x 7 MB (fp32) > L2
     out = torch.empty(M, N, device="cuda")
@@ -42,9 +42,9 @@ for dt in (torch.float32, torch.bfloat16):
     t_cold = timeit(lambda i: ops.gemm(a, ws[i], out_f32=out, out_ld=N))
 
     def mixed(i):
-        ops.norm_mod(xn, kind=0, w=wn, eps=1e-5, out_bf16=xo)
+        ops.norm_mod(xn, kind=0, w=wn, eps=1e-5, out_fp16=xo)
         ops.gemm(xo, ws[i], out_f32=out, out_ld=N)
-    t_norm = timeit(lambda i: ops.norm_mod(xn, kind=0, w=wn, eps=1e-5, out_bf16=xo))
+    t_norm = timeit(lambda i: ops.norm_mod(xn, kind=0, w=wn, eps=1e-5, out_fp16=xo))
     t_mixed = timeit(mixed)
-    print(f"{'tf32' if dt == torch.float32 else 'bf16'} wqkv: warm {t_warm:.1f} us, cold weights {t_cold:.1f} us, "
+    print(f"{'tf32' if dt == torch.float32 else 'fp16'} wqkv: warm {t_warm:.1f} us, cold weights {t_cold:.1f} us, "
           f"norm alone {t_norm:.1f} us, norm+gemm(cold) {t_mixed:.1f} us (gemm part {t_mixed - t_norm:.1f})")

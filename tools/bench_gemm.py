@@ -30,8 +30,8 @@ def timeit(fn, iters=10):
 
 
 def plain(M, N, K, bns=(32, 64, 128)):
-    a = torch.randn(M, K, device="cuda").bfloat16()
-    b = torch.randn(N, K, device="cuda").bfloat16()
+    a = torch.randn(M, K, device="cuda").half()
+    b = torch.randn(N, K, device="cuda").half()
     out = torch.empty(M, N, device="cuda")
     res = []
     for bn in bns:
@@ -41,15 +41,15 @@ def plain(M, N, K, bns=(32, 64, 128)):
 
 
 def conv(T, Cin, Cout, k, bns=(32, 64, 128), B=1):
-    x = torch.randn(B, T, Cin, device="cuda").bfloat16()
+    x = torch.randn(B, T, Cin, device="cuda").half()
     kpt = (Cin + 63) // 64
-    w = torch.randn(Cout, k * kpt * 64, device="cuda").bfloat16()
-    out = torch.empty(B, T, Cout, device="cuda", dtype=torch.bfloat16)
+    w = torch.randn(Cout, k * kpt * 64, device="cuda").half()
+    out = torch.empty(B, T, Cout, device="cuda", dtype=torch.float16)
     res = []
     for bn in bns:
         if bn > max(Cout, 32):
             continue
-        us = timeit(lambda: ops.gemm(x, w, M=T, G1=B, kpt=kpt, dil=1, pad=k // 2, a_c2=(1, 0), out_bf16=out,
+        us = timeit(lambda: ops.gemm(x, w, M=T, G1=B, kpt=kpt, dil=1, pad=k // 2, a_c2=(1, 0), out_fp16=out,
                                      outb_ld=Cout, outb_g=(T * Cout, 0), bn=bn), iters=5)
         res.append(f"bn{bn}: {us:7.1f}us {2 * T * Cout * Cin * k * B / us / 1e6:7.1f}TF")
     byt = B * T * (Cin + Cout) * 2

@@ -20,11 +20,11 @@ def run(M, N, K, dt, G=1):
         us = timeit(lambda: ops.gemm(a, b, M=M, G1=G, a_c2=(1, 0), b_c2=(1, 0, 0), out_f32=out, out_ld=N, out_g=(M * N, 0)))
         res.append(us)
     _lib.lib().vb_set_gemm2(0)
-    name = "tf32" if dt == torch.float32 else "bf16"
+    name = "tf32" if dt == torch.float32 else "fp16"
     print(f"{name} G={G} M={M} N={N} K={K}: 1-CTA {res[0]:6.1f} us   2-CTA {res[1]:6.1f} us   ({2 * G * M * N * K / res[1] / 1e6:6.0f} TF)", flush=True)
 
 
-for dt in (torch.float32, torch.bfloat16):
+for dt in (torch.float32, torch.float16):
     run(1500, 2304, 768, dt)
     run(1500, 768, 768, dt)
     run(1500, 1024, 768, dt)
@@ -32,6 +32,6 @@ for dt in (torch.float32, torch.bfloat16):
     run(1500, 192, 512, dt, G=4)
     run(3000, 2304, 768, dt)
     run(6000, 2304, 768, dt)
-run(750, 1536, 4608, torch.bfloat16)
-run(1500, 768, 2304, torch.bfloat16)
-run(8192, 8192, 8192, torch.bfloat16)
+run(750, 1536, 4608, torch.float16)
+run(1500, 768, 2304, torch.float16)
+run(8192, 8192, 8192, torch.float16)

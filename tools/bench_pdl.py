@@ -9,8 +9,8 @@ from versband_b200 import _lib, ops  # noqa: E402
 
 a = torch.randn(1500, 768, device="cuda")
 b = torch.empty_like(a)
-w = torch.randn(768, 768, device="cuda").bfloat16()
-xb = torch.randn(1500, 768, device="cuda").bfloat16()
+w = torch.randn(768, 768, device="cuda").half()
+xb = torch.randn(1500, 768, device="cuda").half()
 o = torch.empty(1500, 768, device="cuda")
 
 

@@ -10,8 +10,8 @@ from versband_b200 import _lib, ops  # noqa: E402
 
 torch.manual_seed(0)
 M, N, K = 1024, 64, 128
-a = torch.randn(M, K, device="cuda").bfloat16()
-b = torch.randn(N, K, device="cuda").bfloat16()
+a = torch.randn(M, K, device="cuda").half()
+b = torch.randn(N, K, device="cuda").half()
 ref = a.float() @ b.float().t()
 for variant in ("base_offset", "no_base_offset"):
     for s in (0, 1, 3, 5, 8, 11, 16, 40):

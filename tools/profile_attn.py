@@ -9,22 +9,22 @@ from versband_b200 import ops  # noqa: E402
 
 B, H, T, hd, L = 2, 8, 750, 96, 80
 Tp = 752
-BF = torch.bfloat16
-q = torch.randn(B, H, T, hd, device="cuda").to(BF)
-k = torch.randn(B, H, T, hd, device="cuda").to(BF)
-vt = torch.randn(B, H, hd, Tp, device="cuda").to(BF)
-kt = torch.randn(B, H, L, hd, device="cuda").to(BF)
-vtt = torch.randn(B, H, hd, 80, device="cuda").to(BF)
+H16 = torch.float16
+q = torch.randn(B, H, T, hd, device="cuda").to(H16)
+k = torch.randn(B, H, T, hd, device="cuda").to(H16)
+vt = torch.randn(B, H, hd, Tp, device="cuda").to(H16)
+kt = torch.randn(B, H, L, hd, device="cuda").to(H16)
+vtt = torch.randn(B, H, hd, 80, device="cuda").to(H16)
 gate = torch.randn(H, device="cuda")
-out = torch.zeros(B * T, H * hd, device="cuda", dtype=BF)
+out = torch.zeros(B * T, H * hd, device="cuda", dtype=H16)
 mode = sys.argv[1] if len(sys.argv) > 1 else "both"
 for _ in range(4):
     if mode == "both":
         ops.attn_fused(q, (hd, T * hd, H * T * hd), B=B, T=T, H=H, hd=hd, scale=hd ** -0.5, k_self=k, vt_self=vt, Tp=Tp,
-                       k_text=kt, vt_text=vtt, L=L, Lp=80, gate=gate, out_bf16=out)
+                       k_text=kt, vt_text=vtt, L=L, Lp=80, gate=gate, out_fp16=out)
     else:
         ops.attn_fused(q, (hd, T * hd, H * T * hd), B=B, T=T, H=H, hd=hd, scale=hd ** -0.5, k_text=kt, vt_text=vtt, L=L,
-                       Lp=80, out_bf16=out)
+                       Lp=80, out_fp16=out)
 torch.cuda.synchronize()
 
 from versband_b200 import _lib
@@ -32,7 +32,7 @@ import ctypes
 tr = torch.zeros(64, dtype=torch.int64, device="cuda")
 _lib.lib().vb_attn_set_trace(ctypes.c_void_p(tr.data_ptr()))
 ops.attn_fused(q, (hd, T * hd, H * T * hd), B=B, T=T, H=H, hd=hd, scale=hd ** -0.5, k_self=k, vt_self=vt, Tp=Tp,
-               k_text=kt, vt_text=vtt, L=L, Lp=80, gate=gate, out_bf16=out)
+               k_text=kt, vt_text=vtt, L=L, Lp=80, gate=gate, out_fp16=out)
 torch.cuda.synchronize()
 t = tr.cpu().view(8, 8)
 t0 = int(t[0, 0])

@@ -34,7 +34,7 @@ class GemmArgs(C.Structure):
         ("row_mul", c_i32), ("row_off", c_i32), ("row_off_g1", c_i32), ("rows_out", c_i32),
         ("residual", c_ptr), ("accumulate", c_i32),
         ("out_f32", c_ptr), ("out_ld", c_i64), ("out_g1", c_i64), ("out_g2", c_i64),
-        ("out_bf16", c_ptr), ("outb_f32", c_i32), ("outb_ld", c_i64), ("outb_g1", c_i64), ("outb_g2", c_i64),
+        ("out_fp16", c_ptr), ("outb_f32", c_i32), ("outb_ld", c_i64), ("outb_g1", c_i64), ("outb_g2", c_i64),
         ("act_out", c_i32), ("act_out_slope", c_f32), ("out_scale", c_f32),
         ("rope_cs", c_ptr), ("T", c_i32), ("heads", c_i32), ("head_dim", c_i32), ("Tp", c_i32), ("qkv_sec0", c_i32),
         ("q_out", c_ptr), ("k_out", c_ptr), ("vt_out", c_ptr),
@@ -48,7 +48,7 @@ class AttnArgs(C.Structure):
     _fields_ = [
         ("q", c_ptr), ("q_st", c_i64), ("q_sh", c_i64), ("q_sb", c_i64),
         ("k_self", c_ptr), ("vt_self", c_ptr), ("k_text", c_ptr), ("vt_text", c_ptr),
-        ("gate", c_ptr), ("out_bf16", c_ptr), ("out_f32", c_ptr),
+        ("gate", c_ptr), ("out_fp16", c_ptr), ("out_f32", c_ptr),
         ("B", c_i32), ("T", c_i32), ("H", c_i32), ("hd", c_i32), ("Tp", c_i32), ("L", c_i32), ("Lp", c_i32),
         ("scale", c_f32),
     ]

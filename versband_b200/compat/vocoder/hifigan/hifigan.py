@@ -1,2 +1,31 @@
-"""B200 override of the YAML target `vocoder.hifigan.hifigan.HifiGAN`."""
+"""B200 override of the YAML target `vocoder.hifigan.hifigan.HifiGAN`. Everything else the reference's
+`vocoder/hifigan/hifigan.py` defines (CodeUpsampleHifiGan: not on the hot path) is forwarded, lazily, to the
+reference file found further down the package's extended `__path__`."""
 from versband_b200.modules import HifiGAN, HifiGanGenerator  # noqa: F401
+
+
+def _reference_module():
+    import importlib.util
+    import os
+    import sys
+
+    name = __name__.rsplit(".", 1)[0] + "._reference_hifigan"
+    if name in sys.modules:
+        return sys.modules[name]
+    pkg = sys.modules[__name__.rsplit(".", 1)[0]]
+    here = os.path.dirname(os.path.abspath(__file__))
+    for d in pkg.__path__:
+        f = os.path.join(d, "hifigan.py")
+        if os.path.abspath(d) != here and os.path.exists(f):
+            spec = importlib.util.spec_from_file_location(name, f)
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[name] = mod
+            spec.loader.exec_module(mod)
+            return mod
+    raise ImportError("the reference's vocoder/hifigan/hifigan.py is not on sys.path behind versband_b200/compat")
+
+
+def __getattr__(name):
+    if name == "CodeUpsampleHifiGan":
+        return _reference_module().CodeUpsampleHifiGan
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

@@ -3,7 +3,7 @@
 // One CTA = 128 query rows of one (batch, head). Key tiles of 128 keys stream through a
 // 2-stage TMA ring; per tile:
 //   MMA1  S = Q K^T        (UMMA 128x128x16, fp32 S in TMEM, double-buffered)
-//   softmax warps: TMEM -> registers, online max/sum, P (bf16) -> swizzled smem
+//   softmax warps: TMEM -> registers, online max/sum, P (fp16) -> swizzled smem
 //   MMA2  O_j = P V        (UMMA 128xHDx16, B operand = V^T tile), TMEM -> registers,
 //                           acc = acc * alpha + O_j   (running output kept in registers)
 // P and O are double-buffered: the softmax warps start on tile j+1 right after publishing P_j and
@@ -28,14 +28,14 @@ struct AttnKParams {
   int has_text;
   float scale;
   const float* gate;
-  __nv_bfloat16* out_bf16;
+  __half* out_fp16;
   float* out_f32;
   long long* trace;  // debug: per-tile clock64 stamps of CTA (0,0,0)
 };
 
 template <int HD>
 struct AttnCfg {
-  static constexpr int kQBytes = 2 * 16384;            // Q tile: 2 k-blocks of [128 x 64] bf16
+  static constexpr int kQBytes = 2 * 16384;            // Q tile: 2 k-blocks of [128 x 64] fp16
   static constexpr int kKBytes = 2 * 16384;            // K tile per stage
   static constexpr int kVBytes = 2 * HD * 128;         // V^T tile per stage: 2 k-blocks of [HD x 64]
   static constexpr int kPBytes = 2 * 16384;            // P tile (two buffers)
@@ -121,8 +121,8 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, HD);
+      constexpr uint32_t idesc_s = make_idesc_fp16(128, 128);
+      constexpr uint32_t idesc_o = make_idesc_fp16(128, HD);
       mbar_wait(q_full, 0);
       auto mma1 = [&](int j) {
         const int st = j & 1;
@@ -133,7 +133,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           const int kb = k >> 2, off = (k & 3) * 2;
           const uint64_t da = make_kmajor_sw128_desc(smem_u32(sQ + kb * 16384)) + off;
           const uint64_t db = make_kmajor_sw128_desc(smem_u32(sK + st * Cfg::kKBytes + kb * 16384)) + off;
-          umma_bf16(tmem_base + st * 128, da, db, idesc_s, k > 0 ? 1u : 0u);
+          umma_fp16(tmem_base + st * 128, da, db, idesc_s, k > 0 ? 1u : 0u);
         }
         umma_commit(&s_full[st]);
         umma_commit(&k_empty[st]);
@@ -152,7 +152,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           const int kb = k >> 2, off = (k & 3) * 2;
           const uint64_t da = make_kmajor_sw128_desc(smem_u32(sP + st * Cfg::kPBytes + kb * 16384)) + off;
           const uint64_t db = make_kmajor_sw128_desc(smem_u32(sV + st * Cfg::kVBytes + kb * HD * 128)) + off;
-          umma_bf16(tmem_O + st * 128, da, db, idesc_o, k > 0 ? 1u : 0u);
+          umma_fp16(tmem_O + st * 128, da, db, idesc_o, k > 0 ? 1u : 0u);
         }
         umma_commit(&o_full[st]);
         umma_commit(&v_empty[st]);
@@ -270,10 +270,10 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {
         uint4 w;
-        __nv_bfloat162 t0 = __floats2bfloat162_rn(sv[8 * ch], sv[8 * ch + 1]);
-        __nv_bfloat162 t1 = __floats2bfloat162_rn(sv[8 * ch + 2], sv[8 * ch + 3]);
-        __nv_bfloat162 t2 = __floats2bfloat162_rn(sv[8 * ch + 4], sv[8 * ch + 5]);
-        __nv_bfloat162 t3 = __floats2bfloat162_rn(sv[8 * ch + 6], sv[8 * ch + 7]);
+        __half2 t0 = vb_f2h2(sv[8 * ch], sv[8 * ch + 1]);
+        __half2 t1 = vb_f2h2(sv[8 * ch + 2], sv[8 * ch + 3]);
+        __half2 t2 = vb_f2h2(sv[8 * ch + 4], sv[8 * ch + 5]);
+        __half2 t3 = vb_f2h2(sv[8 * ch + 6], sv[8 * ch + 7]);
         w.x = *reinterpret_cast<uint32_t*>(&t0); w.y = *reinterpret_cast<uint32_t*>(&t1);
         w.z = *reinterpret_cast<uint32_t*>(&t2); w.w = *reinterpret_cast<uint32_t*>(&t3);
         *reinterpret_cast<uint4*>(prow_j + ((ch ^ rsw) << 4)) = w;
@@ -309,14 +309,14 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int t = q0 + row;
     if (t < p.T) {
       const long long o = ((long long)b * p.T + t) * ((long long)p.H * HD) + (long long)h * HD + half * HH;
-      if (p.out_bf16) {
-        uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + o);
+      if (p.out_fp16) {
+        uint4* dst = reinterpret_cast<uint4*>(p.out_fp16 + o);
 #pragma unroll
         for (int i = 0; i < HH / 8; ++i) {
-          __nv_bfloat162 a0 = __floats2bfloat162_rn(acc[8 * i], acc[8 * i + 1]);
-          __nv_bfloat162 a1 = __floats2bfloat162_rn(acc[8 * i + 2], acc[8 * i + 3]);
-          __nv_bfloat162 a2 = __floats2bfloat162_rn(acc[8 * i + 4], acc[8 * i + 5]);
-          __nv_bfloat162 a3 = __floats2bfloat162_rn(acc[8 * i + 6], acc[8 * i + 7]);
+          __half2 a0 = vb_f2h2(acc[8 * i], acc[8 * i + 1]);
+          __half2 a1 = vb_f2h2(acc[8 * i + 2], acc[8 * i + 3]);
+          __half2 a2 = vb_f2h2(acc[8 * i + 4], acc[8 * i + 5]);
+          __half2 a3 = vb_f2h2(acc[8 * i + 6], acc[8 * i + 7]);
           dst[i] = make_uint4(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1),
                               *reinterpret_cast<uint32_t*>(&a2), *reinterpret_cast<uint32_t*>(&a3));
         }
@@ -350,7 +350,7 @@ static int encode4(CUtensorMap* map, const void* base, const int64_t* dims, cons
   if (reinterpret_cast<uintptr_t>(base) & 15) return set_error(VB_ERR_INVALID, "vb_attn_fused: unaligned operand");
   auto fn = get_tensor_map_encoder();
   if (!fn) return set_error(VB_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, es,
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(VB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -392,10 +392,11 @@ static int launch_attn(const vb_attn_args* a, cudaStream_t stream) {
   p.n_self = self ? (a->T + 127) / 128 : 0;
   p.has_text = text ? 1 : 0;
   p.scale = a->scale; p.gate = a->gate;
-  p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16);
+  p.out_fp16 = static_cast<__half*>(a->out_fp16);
   p.out_f32 = a->out_f32;
   p.trace = g_attn_trace;
-  static bool attr = false;
+  static PerDevice<bool> attr_flag;
+  bool& attr = attr_flag.get();
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_fused_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
     if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "attn_fused smem attr: %s", cudaGetErrorString(e));
@@ -416,7 +417,7 @@ extern "C" int vb_attn_set_trace(void* buf) {
 extern "C" int vb_attn_fused(const vb_attn_args* a, void* stream) {
   using namespace vb;
   ProfScope prof_scope(PK_ATTN_SMALL, stream);
-  if (!a || !a->q || (!a->k_self && !a->k_text) || (!a->out_bf16 && !a->out_f32))
+  if (!a || !a->q || (!a->k_self && !a->k_text) || (!a->out_fp16 && !a->out_f32))
     return set_error(VB_ERR_INVALID, "vb_attn_fused: null argument");
   if (a->k_self && (!a->vt_self || a->Tp < a->T || a->Tp % 8))
     return set_error(VB_ERR_INVALID, "vb_attn_fused: bad self K/V^T");

@@ -17,7 +17,7 @@ __device__ __forceinline__ float act_f(float v, int act, float slope) {
 // upsample of autoencoder1d.py:288 when rep == 2). Row length D % 4 == 0.
 __global__ void ew_kernel(const float* __restrict__ a, const float* __restrict__ b, float alpha,
                           float beta, int act, float slope, float* __restrict__ out_f32,
-                          __nv_bfloat16* __restrict__ out_bf16, long long rows, int D, int rep) {
+                          __half* __restrict__ out_fp16, long long rows, int D, int rep) {
   pdl_sync();
   const long long nvec = rows * (D / 4);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
@@ -35,22 +35,22 @@ __global__ void ew_kernel(const float* __restrict__ a, const float* __restrict__
     for (int k = 0; k < rep; ++k) {
       const long long o = (r * rep + k) * D + c;
       if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(y[0], y[1], y[2], y[3]);
-      if (out_bf16) {
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]);
-        __nv_bfloat162 p1 = __floats2bfloat162_rn(y[2], y[3]);
+      if (out_fp16) {
+        __half2 p0 = vb_f2h2(y[0], y[1]);
+        __half2 p1 = vb_f2h2(y[2], y[3]);
         uint2 u;
         u.x = *reinterpret_cast<uint32_t*>(&p0);
         u.y = *reinterpret_cast<uint32_t*>(&p1);
-        *reinterpret_cast<uint2*>(out_bf16 + o) = u;
+        *reinterpret_cast<uint2*>(out_fp16 + o) = u;
       }
     }
   }
 }
 
-// [B, C, T] fp32 -> [B, T, Cp] bf16 (channels-last, zero padded to Cp), value * scale.
+// [B, C, T] fp32 -> [B, T, Cp] fp16 (channels-last, zero padded to Cp), value * scale.
 // 32x32 shared-memory transpose: coalesced on both sides.
 __global__ void nct_to_ntc_kernel(const float* __restrict__ in, float scale,
-                                  __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32, int C, int T, int Cp) {
+                                  __half* __restrict__ out, float* __restrict__ out_f32, int C, int T, int Cp) {
   pdl_sync();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
@@ -64,7 +64,7 @@ __global__ void nct_to_ntc_kernel(const float* __restrict__ in, float scale,
     const int t = t0 + j, c = c0 + threadIdx.x;
     if (t < T && c < Cp) {
       if (out_f32) out_f32[((long long)b * T + t) * Cp + c] = tile[threadIdx.x][j];
-      else out[((long long)b * T + t) * Cp + c] = __float2bfloat16(tile[threadIdx.x][j]);
+      else out[((long long)b * T + t) * Cp + c] = vb_f2h(tile[threadIdx.x][j]);
     }
   }
 }
@@ -112,15 +112,15 @@ __global__ void ntc_to_nct_kernel(const float* __restrict__ e_c, const float* __
       const long long o = ((long long)b * T + t) * 32 + c;
       for (int r = 0; r < rep; ++r) {
         if (x_cl_f32) static_cast<float*>(x_cl)[r * rep_stride + o] = tile2[j][threadIdx.x];
-        else static_cast<__nv_bfloat16*>(x_cl)[r * rep_stride + o] = __float2bfloat16(tile2[j][threadIdx.x]);
+        else static_cast<__half*>(x_cl)[r * rep_stride + o] = vb_f2h(tile2[j][threadIdx.x]);
       }
     }
   }
 }
 
-// out[r, :] = table[idx[r], :] as bf16 (nn.Embedding, vocal2music_moe.py:336-337,388-389)
+// out[r, :] = table[idx[r], :] as fp16 (nn.Embedding, vocal2music_moe.py:336-337,388-389)
 __global__ void embed_rows_kernel(const long long* __restrict__ idx, const float* __restrict__ table,
-                                  int V, int D, __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32,
+                                  int V, int D, __half* __restrict__ out, float* __restrict__ out_f32,
                                   long long rows) {
   pdl_sync();
   const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -133,8 +133,8 @@ __global__ void embed_rows_kernel(const long long* __restrict__ idx, const float
     if (out_f32) {
       *reinterpret_cast<float2*>(out_f32 + r * D + d) = make_float2(src[d], src[d + 1]);
     } else {
-      __nv_bfloat162 p = __floats2bfloat162_rn(src[d], src[d + 1]);
-      *reinterpret_cast<__nv_bfloat162*>(out + r * D + d) = p;
+      __half2 p = vb_f2h2(src[d], src[d + 1]);
+      *reinterpret_cast<__half2*>(out + r * D + d) = p;
     }
   }
 }
@@ -142,7 +142,7 @@ __global__ void embed_rows_kernel(const long long* __restrict__ idx, const float
 // out[b, t, :] = 0.5*(a[b,2t]+a[b,2t+1]) + 0.5*(b[b,2t]+b[b,2t+1])  (AvgPool1d(2) of both stem
 // branches + their sum, vocal2music_moe.py:343,349,392); inputs already LeakyReLU'd.
 __global__ void pool2_sum_kernel(const float* __restrict__ a, const float* __restrict__ b2, int Tin,
-                                 int Tout, int D, __nv_bfloat16* __restrict__ out_bf16,
+                                 int Tout, int D, __half* __restrict__ out_fp16,
                                  float* __restrict__ out_f32, int B) {
   pdl_sync();
   const long long n = (long long)B * Tout * D;
@@ -155,7 +155,7 @@ __global__ void pool2_sum_kernel(const float* __restrict__ a, const float* __res
     const long long base = ((long long)b * Tin + 2 * t) * D + d;
     float v = (a[base] + a[base + D]) * 0.5f;
     if (b2) v += (b2[base] + b2[base + D]) * 0.5f;
-    if (out_bf16) out_bf16[i] = __float2bfloat16(v);
+    if (out_fp16) out_fp16[i] = vb_f2h(v);
     if (out_f32) out_f32[i] = v;
   }
 }
@@ -216,11 +216,11 @@ __global__ void gn_finish_kernel(const double* __restrict__ part, int nsplit, lo
   rstd[i] = (float)(1.0 / sqrt((var > 0 ? var : 0) + (double)eps));
 }
 
-// y = act((x - mean) * rstd * w + b) -> bf16 (A operand of the following conv GEMM)
+// y = act((x - mean) * rstd * w + b) -> fp16 (A operand of the following conv GEMM)
 __global__ void gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                                 const float* __restrict__ rstd, const float* __restrict__ w,
                                 const float* __restrict__ bias, int T, int C, int G, int act,
-                                __nv_bfloat16* __restrict__ out, long long total_vec) {
+                                __half* __restrict__ out, long long total_vec) {
   pdl_sync();
   const int cpg = C / G;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
@@ -236,8 +236,8 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, const float* __rest
       const float m = mean[b * G + g], r = rstd[b * G + g];
       y[j] = act_f((y[j] - m) * r * w[c + j] + bias[c + j], act, 0.f);
     }
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]);
-    __nv_bfloat162 p1 = __floats2bfloat162_rn(y[2], y[3]);
+    __half2 p0 = vb_f2h2(y[0], y[1]);
+    __half2 p1 = vb_f2h2(y[2], y[3]);
     uint2 u;
     u.x = *reinterpret_cast<uint32_t*>(&p0);
     u.y = *reinterpret_cast<uint32_t*>(&p1);
@@ -245,10 +245,10 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, const float* __rest
   }
 }
 
-// HiFi-GAN conv_post (modules/hifigan.py:139-141): x is the already leaky-relu'd bf16
+// HiFi-GAN conv_post (modules/hifigan.py:139-141): x is the already leaky-relu'd fp16
 // activation [B, T, C]; wav[b, t] = tanh(bias + sum_{j,c} w[j, c] * x[b, t + j - pad, c]).
 // One warp per 32 output samples: each lane owns one sample; weights in shared memory.
-__global__ void conv_post_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+__global__ void conv_post_kernel(const __half* __restrict__ x, const float* __restrict__ w,
                                  float bias, int T, int C, int k, float* __restrict__ wav) {
   pdl_sync();
   extern __shared__ float sw[];
@@ -265,10 +265,10 @@ __global__ void conv_post_kernel(const __nv_bfloat16* __restrict__ x, const floa
     const uint4* row = reinterpret_cast<const uint4*>(x + ((long long)b * T + tt) * C);
     for (int c8 = 0; c8 < C / 8; ++c8) {
       const uint4 u = row[c8];
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float2 f = __bfloat1622float2(h[q]);
+        const float2 f = __half22float2(h[q]);
         acc = fmaf(f.x, sw[j * C + c8 * 8 + 2 * q], acc);
         acc = fmaf(f.y, sw[j * C + c8 * 8 + 2 * q + 1], acc);
       }
@@ -288,24 +288,24 @@ static inline int grid_for(long long n, int threads) {
 }
 
 extern "C" int vb_ew(const float* a, const float* b, float alpha, float beta, int act, float slope,
-                     float* out_f32, void* out_bf16, int64_t rows, int D, int rep, void* stream) {
+                     float* out_f32, void* out_fp16, int64_t rows, int D, int rep, void* stream) {
   vb::ProfScope prof_scope(vb::PK_EW, stream);
-  if (!a || rows <= 0 || D <= 0 || D % 4 != 0 || rep < 1 || (!out_f32 && !out_bf16))
+  if (!a || rows <= 0 || D <= 0 || D % 4 != 0 || rep < 1 || (!out_f32 && !out_fp16))
     return set_error(VB_ERR_INVALID, "vb_ew: bad arguments (D %% 4 == 0)");
   const long long nvec = rows * (D / 4);
   launch_k(ew_kernel, dim3(grid_for(nvec, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
-      a, b, alpha, beta, act, slope, out_f32, static_cast<__nv_bfloat16*>(out_bf16), rows, D, rep);
+      a, b, alpha, beta, act, slope, out_f32, static_cast<__half*>(out_fp16), rows, D, rep);
   return check_launch("vb_ew");
 }
 
-extern "C" int vb_nct_to_ntc(const float* in, float scale, void* out_bf16, int B, int C, int T, int Cp,
+extern "C" int vb_nct_to_ntc(const float* in, float scale, void* out_fp16, int B, int C, int T, int Cp,
                              int out_is_f32, void* stream) {
   vb::ProfScope prof_scope(vb::PK_LAYOUT, stream);
-  if (!in || !out_bf16 || Cp < C) return set_error(VB_ERR_INVALID, "vb_nct_to_ntc: bad arguments");
+  if (!in || !out_fp16 || Cp < C) return set_error(VB_ERR_INVALID, "vb_nct_to_ntc: bad arguments");
   dim3 grid((T + 31) / 32, (Cp + 31) / 32, B), block(32, 8);
   launch_k(nct_to_ntc_kernel, dim3(grid), dim3(block), 0, static_cast<cudaStream_t>(stream), 
-      in, scale, out_is_f32 ? nullptr : static_cast<__nv_bfloat16*>(out_bf16),
-      out_is_f32 ? static_cast<float*>(out_bf16) : nullptr, C, T, Cp);
+      in, scale, out_is_f32 ? nullptr : static_cast<__half*>(out_fp16),
+      out_is_f32 ? static_cast<float*>(out_fp16) : nullptr, C, T, Cp);
   return check_launch("vb_nct_to_ntc");
 }
 
@@ -319,23 +319,23 @@ extern "C" int vb_ntc_to_nct(const float* e_c, const float* e_u, int64_t ld, flo
   return check_launch("vb_ntc_to_nct");
 }
 
-extern "C" int vb_embed_rows(const int64_t* idx, const float* table, int V, int D, void* out_bf16,
+extern "C" int vb_embed_rows(const int64_t* idx, const float* table, int V, int D, void* out_fp16,
                              int64_t rows, int out_is_f32, void* stream) {
   vb::ProfScope prof_scope(vb::PK_LAYOUT, stream);
-  if (!idx || !table || !out_bf16 || D % 2) return set_error(VB_ERR_INVALID, "vb_embed_rows: bad arguments");
+  if (!idx || !table || !out_fp16 || D % 2) return set_error(VB_ERR_INVALID, "vb_embed_rows: bad arguments");
   launch_k(embed_rows_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
-      reinterpret_cast<const long long*>(idx), table, V, D, out_is_f32 ? nullptr : static_cast<__nv_bfloat16*>(out_bf16),
-      out_is_f32 ? static_cast<float*>(out_bf16) : nullptr, rows);
+      reinterpret_cast<const long long*>(idx), table, V, D, out_is_f32 ? nullptr : static_cast<__half*>(out_fp16),
+      out_is_f32 ? static_cast<float*>(out_fp16) : nullptr, rows);
   return check_launch("vb_embed_rows");
 }
 
 extern "C" int vb_pool2_sum(const float* a, const float* b, int B, int Tin, int Tout, int D,
-                            void* out_bf16, float* out_f32, void* stream) {
+                            void* out_fp16, float* out_f32, void* stream) {
   vb::ProfScope prof_scope(vb::PK_EW, stream);
   if (!a || Tout * 2 > Tin) return set_error(VB_ERR_INVALID, "vb_pool2_sum: bad arguments");
   const long long n = (long long)B * Tout * D;
   launch_k(pool2_sum_kernel, dim3(grid_for(n, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
-      a, b, Tin, Tout, D, static_cast<__nv_bfloat16*>(out_bf16), out_f32, B);
+      a, b, Tin, Tout, D, static_cast<__half*>(out_fp16), out_f32, B);
   return check_launch("vb_pool2_sum");
 }
 
@@ -354,24 +354,24 @@ extern "C" int vb_gn_stats(const float* x, int B, int T, int C, int G, float eps
 }
 
 extern "C" int vb_gn_apply(const float* x, const float* mean, const float* rstd, const float* w,
-                           const float* bias, int B, int T, int C, int G, int act, void* out_bf16,
+                           const float* bias, int B, int T, int C, int G, int act, void* out_fp16,
                            void* stream) {
   vb::ProfScope prof_scope(vb::PK_GN, stream);
-  if (!x || !mean || !rstd || !w || !bias || !out_bf16 || C % 4 || C % G)
+  if (!x || !mean || !rstd || !w || !bias || !out_fp16 || C % 4 || C % G)
     return set_error(VB_ERR_INVALID, "vb_gn_apply: bad arguments");
   const long long nvec = (long long)B * T * C / 4;
   launch_k(gn_apply_kernel, dim3(grid_for(nvec, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
-      x, mean, rstd, w, bias, T, C, G, act, static_cast<__nv_bfloat16*>(out_bf16), nvec);
+      x, mean, rstd, w, bias, T, C, G, act, static_cast<__half*>(out_fp16), nvec);
   return check_launch("vb_gn_apply");
 }
 
-extern "C" int vb_conv_post(const void* x_bf16, const float* w, float bias, int B, int T, int C, int k,
+extern "C" int vb_conv_post(const void* x_fp16, const float* w, float bias, int B, int T, int C, int k,
                             float* wav, void* stream) {
   vb::ProfScope prof_scope(vb::PK_CONV_POST, stream);
-  if (!x_bf16 || !w || !wav || C % 8) return set_error(VB_ERR_INVALID, "vb_conv_post: bad arguments");
+  if (!x_fp16 || !w || !wav || C % 8) return set_error(VB_ERR_INVALID, "vb_conv_post: bad arguments");
   dim3 grid((T + 127) / 128, B);
   launch_k(conv_post_kernel, dim3(grid), dim3(128), k * C * sizeof(float), static_cast<cudaStream_t>(stream), 
-      static_cast<const __nv_bfloat16*>(x_bf16), w, bias, T, C, k, wav);
+      static_cast<const __half*>(x_fp16), w, bias, T, C, k, wav);
   return check_launch("vb_conv_post");
 }
 

@@ -32,7 +32,7 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const int64_
     return set_error(VB_ERR_INVALID, "vb_gemm: operand base pointer not 16-byte aligned");
   auto fn = get_tensor_map_encoder();
   if (!fn) return set_error(VB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  CUresult r = fn(map, tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr,
+  CUresult r = fn(map, tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr,
                   bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -209,17 +209,17 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
   p.rows_out = a->rows_out;
   p.residual = a->residual; p.accumulate = a->accumulate;
   p.out_f32 = a->out_f32; p.out_ld = a->out_ld; p.out_g1 = a->out_g1; p.out_g2 = a->out_g2;
-  p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16);
+  p.out_fp16 = static_cast<__half*>(a->out_fp16);
   p.outb_f32 = a->outb_f32;
   p.outb_ld = a->outb_ld; p.outb_g1 = a->outb_g1; p.outb_g2 = a->outb_g2;
   p.act_out = a->act_out; p.act_out_slope = a->act_out_slope; p.out_scale = a->out_scale;
   p.rope_cs = a->rope_cs; p.T = a->T; p.heads = a->heads; p.head_dim = a->head_dim; p.Tp = a->Tp; p.qkv_sec0 = a->qkv_sec0;
-  p.q_out = static_cast<__nv_bfloat16*>(a->q_out);
-  p.k_out = static_cast<__nv_bfloat16*>(a->k_out);
-  p.vt_out = static_cast<__nv_bfloat16*>(a->vt_out);
+  p.q_out = static_cast<__half*>(a->q_out);
+  p.k_out = static_cast<__half*>(a->k_out);
+  p.vt_out = static_cast<__half*>(a->vt_out);
   p.route_vg = a->route_vg; p.route_vg_g1 = a->route_vg_g1;
   if (a->mode == VB_EPI_GENERIC) {
-    if (!a->out_f32 && !a->out_bf16)
+    if (!a->out_f32 && !a->out_fp16)
       return set_error(VB_ERR_INVALID, "vb_gemm: no output pointer");
     if (a->rows_out <= 0) return set_error(VB_ERR_INVALID, "vb_gemm: rows_out must be set");
     auto al = [](const void* ptr, int bytes) {
@@ -227,12 +227,12 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
     };
     p.vec_f32 = (a->out_ld % 4 == 0) && (a->out_g1 % 4 == 0) && (a->out_g2 % 4 == 0) &&
                 (!a->out_f32 || al(a->out_f32, 16)) && (!a->residual || al(a->residual, 16));
-    p.vec_bf16 = (a->outb_ld % (a->outb_f32 ? 4 : 8) == 0) && (a->outb_g1 % 8 == 0) && (a->outb_g2 % 8 == 0) &&
-                 (!a->out_bf16 || al(a->out_bf16, 16));
+    p.vec_fp16 = (a->outb_ld % (a->outb_f32 ? 4 : 8) == 0) && (a->outb_g1 % 8 == 0) && (a->outb_g2 % 8 == 0) &&
+                 (!a->out_fp16 || al(a->out_fp16, 16));
     p.vec_aux = (!a->bias || (al(a->bias, 16) && a->bias_g1 % 4 == 0 && a->bias_tile % 4 == 0)) &&
                 (!a->gate || (al(a->gate, 16) && a->gate_ld % 4 == 0 && a->gate_g1 % 4 == 0));
     const long long lim = 1ll << 31;
-    p.fast_ok = p.vec_f32 && p.vec_bf16 && p.vec_aux && (long long)a->rows_out * a->out_ld < lim &&
+    p.fast_ok = p.vec_f32 && p.vec_fp16 && p.vec_aux && (long long)a->rows_out * a->out_ld < lim &&
                 (long long)a->rows_out * a->outb_ld < lim && a->out_ld >= 0 && a->outb_ld >= 0;
     if (a->accumulate && !a->out_f32)
       return set_error(VB_ERR_INVALID, "vb_gemm: accumulate needs out_f32");
@@ -254,13 +254,7 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
   p.m_tiles = m_tiles;
   p.n_tiles = (a->N + bn - 1) / bn;
   p.num_tiles = p.m_tiles * p.n_tiles * G;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
+  const int num_sms = device_sm_count();
   // haloed small-C conv path (see vb_conv_halo_kernel)
   if (g_conv_halo > 0 && !tf32 && !use2 && !a->tile_group && a->mode == VB_EPI_GENERIC && kpt == 1 && num_kb >= 2 &&
       num_kb <= 16 && a->N <= 64 && a->a_dims[0] <= 64 && a->dil >= 1 && !a->swiglu && a->G2 == 1 &&

@@ -49,8 +49,8 @@ __device__ __forceinline__ void apply_act_all(float (&v)[N], int act, float slop
   }
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+__device__ __forceinline__ uint32_t pack_fp16(float a, float b) {
+  __half2 t = vb_f2h2(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
@@ -219,25 +219,25 @@ __device__ __forceinline__ void epilogue_rowwise(const GemmKParams& p, float (&v
       const float a = v[2 * j], b = v[2 * j + 1];
       o[j] = (a / (1.f + __expf(-a))) * b * rs;
     }
-    if (p.out_bf16 && p.outb_f32) {
-      float* dstf = reinterpret_cast<float*>(p.out_bf16) + g1 * p.outb_g1 + g2 * p.outb_g2 + orow * p.outb_ld + n_out0;
+    if (p.out_fp16 && p.outb_f32) {
+      float* dstf = reinterpret_cast<float*>(p.out_fp16) + g1 * p.outb_g1 + g2 * p.outb_g2 + orow * p.outb_ld + n_out0;
 #pragma unroll
       for (int j = 0; j < 16; ++j)
         if (n_out0 + j < n_out_total) dstf[j] = o[j];
-    } else if (p.out_bf16) {
-      __nv_bfloat16* dst = p.out_bf16 + g1 * p.outb_g1 + g2 * p.outb_g2 + orow * p.outb_ld + n_out0;
-      if (p.vec_bf16 && n_out0 + 16 <= n_out_total) {
+    } else if (p.out_fp16) {
+      __half* dst = p.out_fp16 + g1 * p.outb_g1 + g2 * p.outb_g2 + orow * p.outb_ld + n_out0;
+      if (p.vec_fp16 && n_out0 + 16 <= n_out_total) {
         uint4 w0, w1;
-        w0.x = pack_bf16(o[0], o[1]);   w0.y = pack_bf16(o[2], o[3]);
-        w0.z = pack_bf16(o[4], o[5]);   w0.w = pack_bf16(o[6], o[7]);
-        w1.x = pack_bf16(o[8], o[9]);   w1.y = pack_bf16(o[10], o[11]);
-        w1.z = pack_bf16(o[12], o[13]); w1.w = pack_bf16(o[14], o[15]);
+        w0.x = pack_fp16(o[0], o[1]);   w0.y = pack_fp16(o[2], o[3]);
+        w0.z = pack_fp16(o[4], o[5]);   w0.w = pack_fp16(o[6], o[7]);
+        w1.x = pack_fp16(o[8], o[9]);   w1.y = pack_fp16(o[10], o[11]);
+        w1.z = pack_fp16(o[12], o[13]); w1.w = pack_fp16(o[14], o[15]);
         reinterpret_cast<uint4*>(dst)[0] = w0;
         reinterpret_cast<uint4*>(dst)[1] = w1;
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          if (n_out0 + j < n_out_total) dst[j] = __float2bfloat16(o[j]);
+          if (n_out0 + j < n_out_total) dst[j] = vb_f2h(o[j]);
       }
     }
     if (p.out_f32) {
@@ -277,12 +277,12 @@ __device__ __forceinline__ void epilogue_rowwise(const GemmKParams& p, float (&v
         if (j < n_left) dst[j] = v[j];
     }
   }
-  if (p.out_bf16) {
+  if (p.out_fp16) {
     const long long offb = g1 * p.outb_g1 + g2 * p.outb_g2 + orow * p.outb_ld + n_base;
     apply_act_all(v, p.act_out, p.act_out_slope, p.out_scale);
     if (p.outb_f32) {
-      float* dstf = reinterpret_cast<float*>(p.out_bf16) + offb;
-      if (full && p.vec_bf16) {
+      float* dstf = reinterpret_cast<float*>(p.out_fp16) + offb;
+      if (full && p.vec_fp16) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           reinterpret_cast<float4*>(dstf)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -293,21 +293,21 @@ __device__ __forceinline__ void epilogue_rowwise(const GemmKParams& p, float (&v
       }
       return;
     }
-    __nv_bfloat16* dst = p.out_bf16 + offb;
-    if (full && p.vec_bf16) {
+    __half* dst = p.out_fp16 + offb;
+    if (full && p.vec_fp16) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 w;
-        w.x = pack_bf16(v[8 * j], v[8 * j + 1]);
-        w.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-        w.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-        w.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+        w.x = pack_fp16(v[8 * j], v[8 * j + 1]);
+        w.y = pack_fp16(v[8 * j + 2], v[8 * j + 3]);
+        w.z = pack_fp16(v[8 * j + 4], v[8 * j + 5]);
+        w.w = pack_fp16(v[8 * j + 6], v[8 * j + 7]);
         reinterpret_cast<uint4*>(dst)[j] = w;
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (j < n_left) dst[j] = __float2bfloat16(v[j]);
+        if (j < n_left) dst[j] = vb_f2h(v[j]);
     }
   }
 }
@@ -385,16 +385,16 @@ __device__ __forceinline__ void epilogue_generic(const GemmKParams& p, float (&v
       o[2 * i] = silu_mul(v[4 * i], v[4 * i + 1]) * rows.rs[i];
       o[2 * i + 1] = silu_mul(v[4 * i + 2], v[4 * i + 3]) * rows.rs[i];
     }
-    if (p.out_bf16 && p.outb_f32) {
-      float* dst = reinterpret_cast<float*>(p.out_bf16) + g1 * p.outb_g1 + g2 * p.outb_g2 + no;
+    if (p.out_fp16 && p.outb_f32) {
+      float* dst = reinterpret_cast<float*>(p.out_fp16) + g1 * p.outb_g1 + g2 * p.outb_g2 + no;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         if (rows.valid >> i & 1) *reinterpret_cast<float2*>(dst + rows.offb[i]) = make_float2(o[2 * i], o[2 * i + 1]);
-    } else if (p.out_bf16) {
-      __nv_bfloat16* dst = p.out_bf16 + g1 * p.outb_g1 + g2 * p.outb_g2 + no;
+    } else if (p.out_fp16) {
+      __half* dst = p.out_fp16 + g1 * p.outb_g1 + g2 * p.outb_g2 + no;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        if (rows.valid >> i & 1) *reinterpret_cast<uint32_t*>(dst + rows.offb[i]) = pack_bf16(o[2 * i], o[2 * i + 1]);
+        if (rows.valid >> i & 1) *reinterpret_cast<uint32_t*>(dst + rows.offb[i]) = pack_fp16(o[2 * i], o[2 * i + 1]);
     }
     if (EC == EC_FULL && p.out_f32) {
       float* dst = p.out_f32 + g1 * p.out_g1 + g2 * p.out_g2 + no;
@@ -445,7 +445,7 @@ __device__ __forceinline__ void epilogue_generic(const GemmKParams& p, float (&v
       if (rows.valid >> i & 1)
         *reinterpret_cast<float4*>(dst + rows.off[i]) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
   }
-  if (p.out_bf16) {
+  if (p.out_fp16) {
     const long long gofsb = g1 * p.outb_g1 + g2 * p.outb_g2 + n;
     if (EC == EC_FULL) {
       apply_act_all(v, p.act_out, p.act_out_slope, p.out_scale);
@@ -455,18 +455,18 @@ __device__ __forceinline__ void epilogue_generic(const GemmKParams& p, float (&v
       act_loop<VB_ACT_NONE>(v, 0.f, p.out_scale);
     }
     if (p.outb_f32) {
-      float* dst = reinterpret_cast<float*>(p.out_bf16) + gofsb;
+      float* dst = reinterpret_cast<float*>(p.out_fp16) + gofsb;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         if (rows.valid >> i & 1)
           *reinterpret_cast<float4*>(dst + rows.offb[i]) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     } else {
-      __nv_bfloat16* dst = p.out_bf16 + gofsb;
+      __half* dst = p.out_fp16 + gofsb;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         if (rows.valid >> i & 1)
           *reinterpret_cast<uint2*>(dst + rows.offb[i]) =
-              make_uint2(pack_bf16(v[4 * i], v[4 * i + 1]), pack_bf16(v[4 * i + 2], v[4 * i + 3]));
+              make_uint2(pack_fp16(v[4 * i], v[4 * i + 1]), pack_fp16(v[4 * i + 2], v[4 * i + 3]));
     }
   }
 }
@@ -492,18 +492,18 @@ __device__ __forceinline__ void epilogue_qkv(const GemmKParams& p, const uint32_
     if (m >= p.M) return;
     const int b = m / T;
     const int t = m - b * T;
-    __nv_bfloat16* dst = p.vt_out + (((long long)b * H + h) * hd + d0) * p.Tp + t;
+    __half* dst = p.vt_out + (((long long)b * H + h) * hd + d0) * p.Tp + t;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       float x = __uint_as_float(raw[j]) * p.alpha;
       if (p.bias) x += __ldg(p.bias + n_base + j);
-      dst[(long long)j * p.Tp] = __float2bfloat16(x);
+      dst[(long long)j * p.Tp] = vb_f2h(x);
     }
     return;
   }
   float v[32];
   epi_transpose(raw, stg, lane, v);
-  __nv_bfloat16* out = (sec == 0 ? p.q_out : p.k_out) + (long long)h * T * hd + d0 + 4 * (lane & 7);
+  __half* out = (sec == 0 ? p.q_out : p.k_out) + (long long)h * T * hd + d0 + 4 * (lane & 7);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     float x0 = v[4 * i] * p.alpha + op.bias.x, x1 = v[4 * i + 1] * p.alpha + op.bias.y;
@@ -515,7 +515,7 @@ __device__ __forceinline__ void epilogue_qkv(const GemmKParams& p, const uint32_
       x0 = y0; x1 = y1; x2 = y2; x3 = y3;
     }
     if (rows.valid >> i & 1)
-      *reinterpret_cast<uint2*>(out + rows.off[i]) = make_uint2(pack_bf16(x0, x1), pack_bf16(x2, x3));
+      *reinterpret_cast<uint2*>(out + rows.off[i]) = make_uint2(pack_fp16(x0, x1), pack_fp16(x2, x3));
   }
 }
 
@@ -708,7 +708,7 @@ vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp_idx == 1) {
     // ===================== MMA issuer (single thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = TF32 ? make_idesc_tf32(BM, BN) : make_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = TF32 ? make_idesc_tf32(BM, BN) : make_idesc_fp16(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -729,10 +729,10 @@ vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            // advance 32 bytes (16 bf16 or 8 tf32 = one MMA K-step) inside the 128-byte swizzle
+            // advance 32 bytes (16 fp16 or 8 tf32 = one MMA K-step) inside the 128-byte swizzle
             // row: +2 in 16-byte units
             if (TF32) umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else umma_fp16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -881,7 +881,7 @@ vb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp_idx == 1) {
     // ===================== MMA issuer (leader CTA, single thread) =====================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = TF32 ? make_idesc_tf32(2 * BM, BN) : make_idesc_bf16(2 * BM, BN);
+      constexpr uint32_t idesc = TF32 ? make_idesc_tf32(2 * BM, BN) : make_idesc_fp16(2 * BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -898,7 +898,7 @@ vb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             if (TF32) umma2_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            else umma2_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else umma2_fp16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit2_mc(&empty_bar[stage], 3);  // frees the slot in both CTAs
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -998,7 +998,7 @@ vb_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp_idx == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = make_idesc_fp16(BM, BN);
       mbar_wait(w_full, 0);
       const uint64_t w_desc0 = make_kmajor_sw128_desc(smem_u32(smem_w));
       int stage = 0;
@@ -1016,15 +1016,15 @@ vb_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint64_t db = w_desc0;
         const uint64_t da_step = static_cast<uint64_t>(hp.row_shift * 8);  // row_shift rows * 128 B / 16
         constexpr uint64_t db_step = kWTap / 16;
-        umma_bf16(tmem_d, da, db, idesc, 0u);
+        umma_fp16(tmem_d, da, db, idesc, 0u);
 #pragma unroll
-        for (int k = 1; k < KSTEPS; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, 1u);
+        for (int k = 1; k < KSTEPS; ++k) umma_fp16(tmem_d, da + 2 * k, db + 2 * k, idesc, 1u);
 #pragma unroll 1
         for (int j = 1; j < hp.taps; ++j) {
           da += da_step;
           db += db_step;
 #pragma unroll
-          for (int k = 0; k < KSTEPS; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, 1u);
+          for (int k = 0; k < KSTEPS; ++k) umma_fp16(tmem_d, da + 2 * k, db + 2 * k, idesc, 1u);
         }
         umma_commit(&a_empty[stage]);
         umma_commit(&tmem_full_bar[acc]);
@@ -1063,7 +1063,8 @@ template <int BN, bool TF32, int EC>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p,
                   dim3 grid, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;
+  static PerDevice<bool> attr_flag;
+  bool& attr_set = attr_flag.get();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(vb_gemm_kernel<BN, TF32, EC>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1085,7 +1086,8 @@ template <int BN, bool TF32, int EC>
 static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, int grid,
                    cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN>;
-  static bool attr_set = false;
+  static PerDevice<bool> attr_flag;
+  bool& attr_set = attr_flag.get();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(vb_gemm2_kernel<BN, TF32, EC>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);

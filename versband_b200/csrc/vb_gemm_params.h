@@ -4,14 +4,14 @@
 // instruction-fetch bound (ncu: stall_no_inst on top, 22 % instruction-cache misses).
 #pragma once
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include "vb_internal.h"
 
 namespace vb {
 
 constexpr int BM = 128;
-constexpr int BK = 64;  // bf16 elements per k-block = one 128-byte swizzle row (32 for fp32/tf32 operands)
+constexpr int BK = 64;  // fp16 elements per k-block = one 128-byte swizzle row (32 for fp32/tf32 operands)
 constexpr int kEpiWarps = 8;                      // two per TMEM lane quadrant
 constexpr int kThreads = 64 + 32 * kEpiWarps;     // + TMA producer warp + MMA warp
 constexpr int kEpiColStep = 32 * (kEpiWarps / 4); // columns between two chunks of the same warp
@@ -54,20 +54,20 @@ struct GemmKParams {
   int accumulate;
   float* out_f32;
   long long out_ld, out_g1, out_g2;
-  __nv_bfloat16* out_bf16;
-  int outb_f32;  // the operand-output slot stores fp32 (tf32 operand mode) instead of bf16
+  __half* out_fp16;
+  int outb_f32;  // the operand-output slot stores fp32 (tf32 operand mode) instead of fp16
   long long outb_ld, outb_g1, outb_g2;
   int act_out;
   float act_out_slope, out_scale;
   int dbg_shift;  // experiment: A tile loaded `dbg_shift` rows early, UMMA descriptor shifted back
-  int vec_f32, vec_bf16, vec_aux;  // alignment allows 16-byte accesses (outputs / bias+gate)
+  int vec_f32, vec_fp16, vec_aux;  // alignment allows 16-byte accesses (outputs / bias+gate)
   int fast_ok;  // all of the above and every row offset fits 32 bits: coalesced epilogue path allowed
   // qkv-rope
   const float* rope_cs;
   int T, heads, head_dim, Tp, qkv_sec0;
-  __nv_bfloat16* q_out;
-  __nv_bfloat16* k_out;
-  __nv_bfloat16* vt_out;
+  __half* q_out;
+  __half* k_out;
+  __half* vt_out;
   // route
   const float* route_vg;
   long long route_vg_g1;

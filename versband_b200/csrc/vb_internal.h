@@ -2,7 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include "../../include/versband.h"
 
@@ -41,6 +41,17 @@ struct ProfScope {
 // grid has fully completed (memory visible), which keeps stream-order semantics intact.
 bool pdl_enabled();
 #ifdef __CUDACC__
+// fp32 -> fp16 operand conversion, round-to-nearest-even, saturating to +-65504 (never inf)
+__device__ __forceinline__ __half2 vb_f2h2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return *reinterpret_cast<__half2*>(&r);
+}
+__device__ __forceinline__ __half vb_f2h(float x) {
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  return *reinterpret_cast<__half*>(&r);
+}
 __device__ __forceinline__ void pdl_sync() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -81,6 +92,29 @@ inline cudaError_t launch_k_cluster(void (*kern)(KArgs...), int cluster_x, dim3 
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 #endif
+
+// Per-device one-time state (function attributes are per device; SM counts differ between SKUs): a process
+// that drives several GPUs initialises each of them, not just whichever was current first.
+template <typename T>
+struct PerDevice {
+  T v[64] = {};
+  T& get() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return v[d & 63];
+  }
+};
+inline int device_sm_count() {
+  static PerDevice<int> sms;
+  int& n = sms.get();
+  if (n == 0) {
+    int d = 0;
+    cudaGetDevice(&d);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
 
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();

@@ -38,7 +38,7 @@ __global__ void linear_small_kernel(const float* __restrict__ x, long long ldx,
 //               w = (1 - y[idx]) + y[idx]  (straight-through value)                       :81-93,150-151
 //  scale_c[n] = w_c * p[0], scale_a[n] = w_a * p[1]                                       :157-165
 template <int E>
-__global__ void router_kernel(const float* __restrict__ cap_feat, const __nv_bfloat16* __restrict__ cap_feat_bf,
+__global__ void router_kernel(const float* __restrict__ cap_feat, const __half* __restrict__ cap_feat_bf,
                               const float* __restrict__ Wc,
                               const float* __restrict__ bc, const float* __restrict__ ac_logits,
                               const float* __restrict__ hl_logits, int hl_ld, int ac_ld, const float* __restrict__ e0,
@@ -73,8 +73,8 @@ __global__ void router_kernel(const float* __restrict__ cap_feat, const __nv_bfl
       float4 xv;
       if (cap_feat_bf) {
         const uint2 u = *reinterpret_cast<const uint2*>(cap_feat_bf + (long long)n * D + d);
-        const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
-        const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+        const __half2 p0 = *reinterpret_cast<const __half2*>(&u.x);
+        const __half2 p1 = *reinterpret_cast<const __half2*>(&u.y);
         xv = make_float4(__low2float(p0), __high2float(p0), __low2float(p1), __high2float(p1));
       } else {
         xv = *reinterpret_cast<const float4*>(cap_feat + (long long)n * D + d);
@@ -89,10 +89,10 @@ __global__ void router_kernel(const float* __restrict__ cap_feat, const __nv_bfl
       }
     }
   } else if (cap_feat_bf) {
-    const __nv_bfloat16* xr = cap_feat_bf + (long long)n * D;
+    const __half* xr = cap_feat_bf + (long long)n * D;
 #pragma unroll 4
     for (int d = lane; d < D; d += 32) {
-      const float xv = __bfloat162float(xr[d]);
+      const float xv = __half2float(xr[d]);
 #pragma unroll
       for (int e = 0; e < E; ++e) acc[e] = fmaf(xv, __ldg(Wc + (long long)e * D + d), acc[e]);
     }
@@ -339,10 +339,10 @@ __global__ void moe_sort_kernel(const int* __restrict__ idx_c, const int* __rest
   }
 }
 
-// x_sorted[slot, :] = x[row_map[slot] % n_tokens, :] (bf16 rows, 16-byte vectors); slot invalid -> zeros
-__global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ row_map,
+// x_sorted[slot, :] = x[row_map[slot] % n_tokens, :] (fp16 rows, 16-byte vectors); slot invalid -> zeros
+__global__ void gather_rows_kernel(const __half* __restrict__ x, const int* __restrict__ row_map,
                                    const int* __restrict__ m_tiles_used, int n_tokens, int D,
-                                   __nv_bfloat16* __restrict__ out, int max_rows) {
+                                   __half* __restrict__ out, int max_rows) {
   pdl_sync();
   const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -465,19 +465,19 @@ extern "C" int vb_linear_small(const float* x, int64_t ldx, const float* W, cons
   return check_launch("vb_linear_small");
 }
 
-extern "C" int vb_router(const float* cap_feat, const void* cap_feat_bf16, const float* Wc, const float* bc,
+extern "C" int vb_router(const float* cap_feat, const void* cap_feat_fp16, const float* Wc, const float* bc,
                          const float* ac_logits, int ac_ld, const float* hl_logits, int hl_ld,
                          const float* e0, const float* e1, const float* e2, float tau, int N, int T, int D, int E,
                          int32_t* idx_c, int32_t* idx_a, float* scale_c, float* scale_a,
                          float* cap_logits_out, int32_t* bucket_count, float* usage, int32_t* slot_c,
                          int32_t* slot_a, const float* cap_partial, int n_heads, void* stream) {
   vb::ProfScope prof_scope(vb::PK_ROUTER, stream);
-  if ((!cap_feat && !cap_feat_bf16 && !cap_partial) || (!Wc && !cap_partial) || !bc || !ac_logits || !hl_logits || !e0 || !e1 || !e2 || !idx_c || !idx_a ||
+  if ((!cap_feat && !cap_feat_fp16 && !cap_partial) || (!Wc && !cap_partial) || !bc || !ac_logits || !hl_logits || !e0 || !e1 || !e2 || !idx_c || !idx_a ||
       !scale_c || !scale_a || N <= 0 || T <= 0)
     return set_error(VB_ERR_INVALID, "vb_router: null/invalid argument");
   if (E != 4) return set_error(VB_ERR_INVALID, "vb_router: num_experts %d not instantiated (4)", E);
   launch_k(router_kernel<4>, dim3((N + 15) / 16), dim3(512), 0, static_cast<cudaStream_t>(stream), 
-      cap_feat, static_cast<const __nv_bfloat16*>(cap_feat_bf16), Wc, bc, ac_logits, hl_logits, hl_ld, ac_ld, e0, e1, e2, tau, N, T, D, idx_c, idx_a, scale_c, scale_a,
+      cap_feat, static_cast<const __half*>(cap_feat_fp16), Wc, bc, ac_logits, hl_logits, hl_ld, ac_ld, e0, e1, e2, tau, N, T, D, idx_c, idx_a, scale_c, scale_a,
       cap_logits_out, bucket_count, usage, slot_c, slot_a, cap_partial, n_heads);
   return check_launch("vb_router");
 }
@@ -511,8 +511,8 @@ extern "C" int vb_gather_rows(const void* x, const int32_t* row_map, const int32
   vb::ProfScope prof_scope(vb::PK_MOE_SORT, stream);
   if (!x || !row_map || !out || D % 8 != 0) return set_error(VB_ERR_INVALID, "vb_gather_rows: bad arguments");
   launch_k(gather_rows_kernel, dim3((max_rows + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream), 
-      static_cast<const __nv_bfloat16*>(x), row_map, m_tiles_used, n_tokens, D,
-      static_cast<__nv_bfloat16*>(out), max_rows);
+      static_cast<const __half*>(x), row_map, m_tiles_used, n_tokens, D,
+      static_cast<__half*>(out), max_rows);
   return check_launch("vb_gather_rows");
 }
 

@@ -71,7 +71,8 @@ extern "C" int vb_router_noise(uint64_t seed, uint64_t offset, int N, int E, int
   ProfScope prof_scope(PK_EW, stream);
   if (!e0 || !e1 || !e2 || N <= 0 || E <= 0 || depth <= 0 || steps <= 0 || (offset & 3))
     return set_error(VB_ERR_INVALID, "vb_router_noise: bad arguments (offset must be a multiple of 4)");
-  static int max_grid = 0;
+  static PerDevice<int> max_grid_dev;
+  int& max_grid = max_grid_dev.get();
   if (max_grid == 0) {
     int dev = 0, sms = 0, tpm = 0;
     cudaGetDevice(&dev);

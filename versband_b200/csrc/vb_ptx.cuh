@@ -3,7 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace vb {
@@ -99,8 +99,8 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]; bf16 operands, fp32 accumulate. One thread issues.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+// D[tmem] (+)= A[smem] * B[smem]; fp16 operands, fp32 accumulate. One thread issues.
+__device__ __forceinline__ void umma_fp16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -216,7 +216,7 @@ __device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMa
       : "memory");
 }
 // UMMA over a CTA pair: M = 256 (128 rows from each CTA), B rows split across the pair.
-__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+__device__ __forceinline__ void umma2_fp16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                            uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -243,7 +243,7 @@ __device__ __forceinline__ void umma_commit2_mc(uint64_t* bar, uint16_t mask) {
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1").
-// Tile rows are 128 bytes (64 bf16); 8-row swizzle atoms are 1024 B apart (SBO).
+// Tile rows are 128 bytes (64 fp16); 8-row swizzle atoms are 1024 B apart (SBO).
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);  // start address, bits [0,14)
@@ -254,11 +254,13 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor for kind::f16 with bf16 A/B (both K-major), fp32 accumulate.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+// Instruction descriptor for kind::f16 with IEEE fp16 A/B (both K-major), fp32 accumulate. fp16 carries the
+// same 11-bit significand as TF32 at half the operand bytes; every producer of a 16-bit operand converts with
+// saturation (vb_f2h / vb_f2h2) so an out-of-range activation becomes +-65504 instead of inf.
+__host__ __device__ constexpr uint32_t make_idesc_fp16(int M, int N) {
   return (1u << 4)                               // c_format = F32
-         | (1u << 7)                             // a_format = BF16
-         | (1u << 10)                            // b_format = BF16
+         | (0u << 7)                             // a_format = F16 (1 would be BF16)
+         | (0u << 10)                            // b_format = F16
          | (static_cast<uint32_t>(N >> 3) << 17) // n_dim
          | (static_cast<uint32_t>(M >> 4) << 24);// m_dim
 }

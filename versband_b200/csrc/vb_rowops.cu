@@ -1,6 +1,6 @@
 // Row-wise SIMT kernels of the DiT step: RMSNorm/LayerNorm (+adaLN modulate), row softmax,
 // small-KV attention (text cross-attention / MoE cross-attention), timestep embedding.
-// All are HBM/L2-bound: one warp per row, 16-byte vector loads, fp32 math, bf16 operand output.
+// All are HBM/L2-bound: one warp per row, 16-byte vector loads, fp32 math, fp16 operand output.
 #include <math_constants.h>
 #include "vb_internal.h"
 
@@ -25,7 +25,7 @@ template <int KIND>
 __global__ void norm_mod_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                 const float* __restrict__ b, const float* __restrict__ shift,
                                 const float* __restrict__ scale, long long mod_ld,
-                                int rows_per_batch, float eps, __nv_bfloat16* __restrict__ out_bf16,
+                                int rows_per_batch, float eps, __half* __restrict__ out_fp16,
                                 float* __restrict__ out_f32, int rows, int D) {
   pdl_sync();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -69,13 +69,13 @@ __global__ void norm_mod_kernel(const float* __restrict__ x, const float* __rest
       if (sh) y[j] += sh[d + j];
     }
     if (out_f32) *reinterpret_cast<float4*>(out_f32 + (long long)row * D + d) = make_float4(y[0], y[1], y[2], y[3]);
-    if (out_bf16) {
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]);
-      __nv_bfloat162 p1 = __floats2bfloat162_rn(y[2], y[3]);
+    if (out_fp16) {
+      __half2 p0 = vb_f2h2(y[0], y[1]);
+      __half2 p1 = vb_f2h2(y[2], y[3]);
       uint2 u;
       u.x = *reinterpret_cast<uint32_t*>(&p0);
       u.y = *reinterpret_cast<uint32_t*>(&p1);
-      *reinterpret_cast<uint2*>(out_bf16 + (long long)row * D + d) = u;
+      *reinterpret_cast<uint2*>(out_fp16 + (long long)row * D + d) = u;
     }
   }
 }
@@ -89,7 +89,7 @@ template <int KIND, int NV>
 __global__ void norm_mod_reg_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                     const float* __restrict__ b, const float* __restrict__ shift,
                                     const float* __restrict__ scale, long long mod_ld,
-                                    int rows_per_batch, float eps, __nv_bfloat16* __restrict__ out_bf16,
+                                    int rows_per_batch, float eps, __half* __restrict__ out_fp16,
                                     float* __restrict__ out_f32, int rows, int D) {
   pdl_sync();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -150,22 +150,22 @@ __global__ void norm_mod_reg_kernel(const float* __restrict__ x, const float* __
       if (sh) y[j] += shj[j];
     }
     if (out_f32) *reinterpret_cast<float4*>(out_f32 + (long long)row * D + d) = make_float4(y[0], y[1], y[2], y[3]);
-    if (out_bf16) {
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]);
-      __nv_bfloat162 p1 = __floats2bfloat162_rn(y[2], y[3]);
+    if (out_fp16) {
+      __half2 p0 = vb_f2h2(y[0], y[1]);
+      __half2 p1 = vb_f2h2(y[2], y[3]);
       uint2 u;
       u.x = *reinterpret_cast<uint32_t*>(&p0);
       u.y = *reinterpret_cast<uint32_t*>(&p1);
-      *reinterpret_cast<uint2*>(out_bf16 + (long long)row * D + d) = u;
+      *reinterpret_cast<uint2*>(out_fp16 + (long long)row * D + d) = u;
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------
-// row softmax: P[r, :n] = softmax(S[r, :n]) (fp32 in, bf16 out), P[r, n:ldp] = 0
+// row softmax: P[r, :n] = softmax(S[r, :n]) (fp32 in, fp16 out), P[r, n:ldp] = 0
 // ---------------------------------------------------------------------------------------
 __global__ void softmax_rows_kernel(const float* __restrict__ S, long long lds,
-                                    __nv_bfloat16* __restrict__ P, long long ldp, long long rows,
+                                    __half* __restrict__ P, long long ldp, long long rows,
                                     int n) {
   pdl_sync();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -179,9 +179,9 @@ __global__ void softmax_rows_kernel(const float* __restrict__ S, long long lds,
   for (int c = lane; c < n; c += 32) sum += __expf(s[c] - m);
   sum = warp_sum(sum);
   const float inv = 1.f / sum;
-  __nv_bfloat16* p = P + row * ldp;
+  __half* p = P + row * ldp;
   for (int c = lane; c < ldp; c += 32)
-    p[c] = __float2bfloat16(c < n ? __expf(s[c] - m) * inv : 0.f);
+    p[c] = vb_f2h(c < n ? __expf(s[c] - m) * inv : 0.f);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -191,11 +191,11 @@ __global__ void softmax_rows_kernel(const float* __restrict__ S, long long lds,
 // flag_large_dit_moe.py:388-402 (text cross-attention, 80 keys) and vocal2music_moe.py:119.
 // ---------------------------------------------------------------------------------------
 template <int HD>
-__global__ void attn_smallkv_kernel(const __nv_bfloat16* __restrict__ q, long long q_sb,
+__global__ void attn_smallkv_kernel(const __half* __restrict__ q, long long q_sb,
                                     long long q_st, long long q_sh, const float* __restrict__ K,
                                     const float* __restrict__ V, long long kv_ld, int L, int H, int T, float scale,
                                     const float* __restrict__ gate, const float* __restrict__ base,
-                                    __nv_bfloat16* __restrict__ out_bf16,
+                                    __half* __restrict__ out_fp16,
                                     float* __restrict__ out_f32, int tokens_per_block) {
   pdl_sync();
   extern __shared__ float sm[];
@@ -219,8 +219,8 @@ __global__ void attn_smallkv_kernel(const __nv_bfloat16* __restrict__ q, long lo
   for (int tt = warp; tt < tokens_per_block; tt += nw) {
     const int t = t0 + tt;
     if (t >= T) break;
-    const __nv_bfloat16* qp = q + b * q_sb + (long long)t * q_st + h * q_sh;
-    for (int d = lane; d < HD; d += 32) myq[d] = __bfloat162float(qp[d]);
+    const __half* qp = q + b * q_sb + (long long)t * q_st + h * q_sh;
+    for (int d = lane; d < HD; d += 32) myq[d] = __half2float(qp[d]);
     __syncwarp();
     float sc[MAXL];
     float m = -CUDART_INF_F;
@@ -271,7 +271,7 @@ __global__ void attn_smallkv_kernel(const __nv_bfloat16* __restrict__ q, long lo
       if (d < HD) {
         float val = g * o[i];
         if (base) val += base[orow + d];
-        if (out_bf16) out_bf16[orow + d] = __float2bfloat16(val);
+        if (out_fp16) out_fp16[orow + d] = vb_f2h(val);
         if (out_f32) out_f32[orow + d] = val;
       }
     }
@@ -284,7 +284,7 @@ __global__ void attn_smallkv_kernel(const __nv_bfloat16* __restrict__ q, long lo
 // `freqs` is the host-computed table (identical to the reference's torch.exp result).
 __global__ void timestep_embed_kernel(const long long* __restrict__ t, const float* __restrict__ freqs,
                                       float* __restrict__ out_f32,
-                                      __nv_bfloat16* __restrict__ out_bf16, int B, int dim) {
+                                      __half* __restrict__ out_fp16, int B, int dim) {
   pdl_sync();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -293,9 +293,9 @@ __global__ void timestep_embed_kernel(const long long* __restrict__ t, const flo
   const float a = (float)t[b] * freqs[k];
   const float c = cosf(a), s = sinf(a);
   if (out_f32) { out_f32[(long long)b * dim + k] = c; out_f32[(long long)b * dim + half + k] = s; }
-  if (out_bf16) {
-    out_bf16[(long long)b * dim + k] = __float2bfloat16(c);
-    out_bf16[(long long)b * dim + half + k] = __float2bfloat16(s);
+  if (out_fp16) {
+    out_fp16[(long long)b * dim + k] = vb_f2h(c);
+    out_fp16[(long long)b * dim + half + k] = vb_f2h(s);
   }
 }
 
@@ -305,21 +305,21 @@ using namespace vb;
 
 extern "C" int vb_norm_mod(int kind, const float* x, const float* w, const float* b,
                            const float* shift, const float* scale, int64_t mod_ld,
-                           int rows_per_batch, float eps, void* out_bf16, float* out_f32, int rows,
+                           int rows_per_batch, float eps, void* out_fp16, float* out_f32, int rows,
                            int D, void* stream) {
   vb::ProfScope prof_scope(vb::PK_NORM, stream);
-  if (!x || rows <= 0 || D <= 0 || D % 4 != 0 || (!out_bf16 && !out_f32))
+  if (!x || rows <= 0 || D <= 0 || D % 4 != 0 || (!out_fp16 && !out_f32))
     return set_error(VB_ERR_INVALID, "vb_norm_mod: bad arguments (D must be a multiple of 4)");
   if (rows_per_batch <= 0) rows_per_batch = rows;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
   if (D <= 1024 && al16(x) && al16(w) && al16(b) && al16(shift) && al16(scale) && mod_ld % 4 == 0 &&
-      al16(out_f32) && al16(out_bf16)) {
+      al16(out_f32) && al16(out_fp16)) {
     const int wpb4 = 4;  // more, smaller CTAs: the rows of one DiT step spread over all SMs
     dim3 grid4((rows + wpb4 - 1) / wpb4), block4(wpb4 * 32);
     auto go = [&](auto kern) {
       launch_k(kern, dim3(grid4), dim3(block4), 0, s, x, w, b, shift, scale, mod_ld, rows_per_batch, eps,
-               static_cast<__nv_bfloat16*>(out_bf16), out_f32, rows, D);
+               static_cast<__half*>(out_fp16), out_f32, rows, D);
       return check_launch("vb_norm_mod");
     };
     if (D <= 512) return kind == 0 ? go(norm_mod_reg_kernel<0, 4>) : go(norm_mod_reg_kernel<1, 4>);
@@ -330,10 +330,10 @@ extern "C" int vb_norm_mod(int kind, const float* x, const float* w, const float
   dim3 grid((rows + wpb - 1) / wpb), block(wpb * 32);
   if (kind == 0)
     launch_k(norm_mod_kernel<0>, dim3(grid), dim3(block), 0, s, x, w, b, shift, scale, mod_ld, rows_per_batch, eps,
-                                              static_cast<__nv_bfloat16*>(out_bf16), out_f32, rows, D);
+                                              static_cast<__half*>(out_fp16), out_f32, rows, D);
   else
     launch_k(norm_mod_kernel<1>, dim3(grid), dim3(block), 0, s, x, w, b, shift, scale, mod_ld, rows_per_batch, eps,
-                                              static_cast<__nv_bfloat16*>(out_bf16), out_f32, rows, D);
+                                              static_cast<__half*>(out_fp16), out_f32, rows, D);
   return check_launch("vb_norm_mod");
 }
 
@@ -345,16 +345,16 @@ extern "C" int vb_softmax_rows(const float* S, int64_t lds, void* P, int64_t ldp
   const int wpb = 8;
   dim3 grid((unsigned)((rows + wpb - 1) / wpb)), block(wpb * 32);
   launch_k(softmax_rows_kernel, dim3(grid), dim3(block), 0, static_cast<cudaStream_t>(stream), 
-      S, lds, static_cast<__nv_bfloat16*>(P), ldp, rows, n);
+      S, lds, static_cast<__half*>(P), ldp, rows, n);
   return check_launch("vb_softmax_rows");
 }
 
 extern "C" int vb_attn_smallkv(const void* q, int64_t q_sb, int64_t q_st, int64_t q_sh,
                                const float* K, const float* V, int64_t kv_ld, int B, int T, int H,
-                               int hd, int L, float scale, const float* gate, const float* base, void* out_bf16,
+                               int hd, int L, float scale, const float* gate, const float* base, void* out_fp16,
                                float* out_f32, void* stream) {
   vb::ProfScope prof_scope(vb::PK_ATTN_SMALL, stream);
-  if (!q || !K || !V || L <= 0 || L > 128 || (!out_bf16 && !out_f32))
+  if (!q || !K || !V || L <= 0 || L > 128 || (!out_fp16 && !out_f32))
     return set_error(VB_ERR_INVALID, "vb_attn_smallkv: bad arguments (L must be <= 128)");
   if (hd != 96 && hd != 64 && hd != 128)
     return set_error(VB_ERR_INVALID, "vb_attn_smallkv: head_dim %d not instantiated (64/96/128)", hd);
@@ -363,14 +363,15 @@ extern "C" int vb_attn_smallkv(const void* q, int64_t q_sb, int64_t q_st, int64_
   dim3 grid((T + tpb - 1) / tpb, H, B);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   auto go = [&](auto kern) -> int {
-    static size_t attr_smem = 0;  // one per instantiation of this generic lambda
+    static PerDevice<size_t> attr_dev;  // one per instantiation of this generic lambda, per device
+    size_t& attr_smem = attr_dev.get();
     if (smem > attr_smem) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "attn_smallkv smem attr: %s", cudaGetErrorString(e));
       attr_smem = smem;
     }
-    launch_k(kern, dim3(grid), dim3(threads), smem, s, static_cast<const __nv_bfloat16*>(q), q_sb, q_st, q_sh, K, V, kv_ld, L,
-                                     H, T, scale, gate, base, static_cast<__nv_bfloat16*>(out_bf16),
+    launch_k(kern, dim3(grid), dim3(threads), smem, s, static_cast<const __half*>(q), q_sb, q_st, q_sh, K, V, kv_ld, L,
+                                     H, T, scale, gate, base, static_cast<__half*>(out_fp16),
                                      out_f32, tpb);
     return check_launch("vb_attn_smallkv");
   };
@@ -380,12 +381,12 @@ extern "C" int vb_attn_smallkv(const void* q, int64_t q_sb, int64_t q_st, int64_
 }
 
 extern "C" int vb_timestep_embed(const int64_t* t, const float* freqs, float* out_f32,
-                                 void* out_bf16, int B, int dim, void* stream) {
+                                 void* out_fp16, int B, int dim, void* stream) {
   vb::ProfScope prof_scope(vb::PK_EW, stream);
   if (!t || !freqs || B <= 0 || dim <= 0 || dim % 2) return set_error(VB_ERR_INVALID, "vb_timestep_embed: bad arguments");
   const int n = B * dim / 2;
   launch_k(timestep_embed_kernel, dim3((n + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), 
-      reinterpret_cast<const long long*>(t), freqs, out_f32, static_cast<__nv_bfloat16*>(out_bf16), B, dim);
+      reinterpret_cast<const long long*>(t), freqs, out_f32, static_cast<__half*>(out_fp16), B, dim);
   return check_launch("vb_timestep_embed");
 }
 

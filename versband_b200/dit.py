@@ -6,7 +6,7 @@ with the restructuring SURVEY.md §0.4/§0.8 shows to be value-equivalent:
   * routed experts evaluated sparsely (hard top-1 ⇒ non-selected weights are exactly 0, :87-89),
   * frequency experts restricted to their 192-channel band (:171-178),
   * everything that depends only on the conditioning computed once per clip (`prepare`).
-All tensors live in HBM as: residual stream fp32 [N, D]; GEMM operands bf16; N = B*T tokens.
+All tensors live in HBM as: residual stream fp32 [N, D]; GEMM operands fp16; N = B*T tokens.
 """
 from __future__ import annotations
 
@@ -18,12 +18,12 @@ import torch
 
 from . import ops
 
-BF = torch.bfloat16
+H16 = torch.float16
 F32 = torch.float32
 
 
 def _bf(t: torch.Tensor) -> torch.Tensor:
-    return t.to(BF).contiguous()
+    return t.to(H16).contiguous()
 
 
 def tf32_round(t: torch.Tensor) -> torch.Tensor:
@@ -33,15 +33,15 @@ def tf32_round(t: torch.Tensor) -> torch.Tensor:
     return ((ti + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
-def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None, dtype=BF) -> torch.Tensor:
+def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None, dtype=H16) -> torch.Tensor:
     """Conv1d weight [Cout, Cin, k] -> implicit-GEMM B operand [Cout, k * kpt*kq] (tap-major);
-    kq = 64 (bf16) or 32 (fp32/tf32) elements = one 128-byte k-block."""
+    kq = 64 (fp16) or 32 (fp32/tf32) elements = one 128-byte k-block."""
     cout, cin, k = w.shape
-    kq = 64 if dtype == BF else 32
+    kq = 64 if dtype == H16 else 32
     kp = (cin + kq - 1) // kq * kq if cin_pad is None else cin_pad
     out = torch.zeros(cout, k, kp, device=w.device, dtype=dtype)
     src = w.permute(0, 2, 1)
-    out[:, :, :cin] = src.to(BF) if dtype == BF else tf32_round(src.float())
+    out[:, :, :cin] = src.to(H16) if dtype == H16 else tf32_round(src.float())
     return out.reshape(cout, k * kp).contiguous()
 
 
@@ -55,7 +55,7 @@ class DiTCond:
     ac_logits: torch.Tensor           # fp32 [N, depth*E]
     caption: torch.Tensor             # fp32 [B, L, D]  (c_embedder output)
     cap_emb: torch.Tensor             # fp32 [B, D]
-    # per block, bf16: text cross-attention K [B,H,L,hd] and V^T [B,H,hd,Lp]; same for the MoE MHA
+    # per block, fp16: text cross-attention K [B,H,L,hd] and V^T [B,H,hd,Lp]; same for the MoE MHA
     k_y: List[torch.Tensor] = field(default_factory=list)
     vt_y: List[torch.Tensor] = field(default_factory=list)
     # per block, the MoE caption cross-attention folded into its gate (include/versband.h: VB_EPI_ROUTE):
@@ -95,14 +95,16 @@ class DiTEngine:
 
     def __init__(self, sd: Dict[str, torch.Tensor], *, in_channels=20, hidden_size=768, depth=4,
                  num_heads=8, num_experts=4, ori_dim=1024, max_len=1500, norm_eps=1e-5,
-                 temperature=2.0, device="cuda", precision: str = "tf32"):
-        """precision: "tf32" (default) — fp32 activations/weights multiplied as TF32 (UMMA
-        kind::tf32) in every linear layer, bf16 attention core: DiT output within 1e-3 (rel. L2) of
-        the fp32 reference; "bf16" — bf16 GEMM operands, ~12 % faster, ~1e-2 of peak."""
-        assert precision in ("bf16", "tf32")
+                 temperature=2.0, device="cuda", precision: str = "fp16"):
+        """precision: "fp16" (default) — IEEE fp16 GEMM operands (UMMA kind::f16, saturating
+        conversion), fp32 accumulation / residual stream / norms / softmax / router: the 11-bit significand of
+        TF32 at half the operand bytes, DiT output within 1e-3 (rel. L2) of the fp32 reference;
+        "tf32" — fp32 activations/weights multiplied as TF32 (kind::tf32) in every linear layer (same accuracy,
+        twice the operand traffic; for checkpoints whose normalised activations exceed the fp16 range)."""
+        assert precision in ("fp16", "tf32")
         self.precision = precision
-        self.adt = BF if precision == "bf16" else F32      # dtype of GEMM operands
-        self.kq = 64 if precision == "bf16" else 32        # elements per 128-byte k-block
+        self.adt = H16 if precision == "fp16" else F32      # dtype of GEMM operands
+        self.kq = 64 if precision == "fp16" else 32        # elements per 128-byte k-block
         self.C, self.D, self.depth, self.H, self.E = in_channels, hidden_size, depth, num_heads, num_experts
         self.hd = hidden_size // num_heads
         self.LK = 96  # key slots per head of the folded caption cross-attention (VB_EPI_ROUTE tile width)
@@ -118,7 +120,7 @@ class DiTEngine:
         dev, D, E = self.dev, self.D, self.E
         g = lambda k: sd[k].detach().to(dev, F32).contiguous()  # noqa: E731
         adt = self.adt
-        _bf = (lambda t: t.to(BF).contiguous()) if adt == BF else (lambda t: tf32_round(t.float()))  # noqa: E731
+        _bf = (lambda t: t.to(H16).contiguous()) if adt == H16 else (lambda t: tf32_round(t.float()))  # noqa: E731
         pack_conv = lambda w_: pack_conv_weight(w_, dtype=adt)  # noqa: E731
         w: dict = {}
         # stem
@@ -227,7 +229,7 @@ class DiTEngine:
             x_cl=z(B, T, 32, dt=AD), x=z(N, D), h=z(N, D),
             temb_sin=z(B, 256, dt=AD), temb_h=z(B, D, dt=AD), temb=z(B, D), ada_in=z(B, D, dt=AD),
             mod=z(B, self.mod_ld), hl=z(B, 2 * self.depth),
-            xa=z(N, D, dt=AD), q=z(B, H, T, hd, dt=BF), k=z(B, H, T, hd, dt=BF), vt=z(B, H, hd, Tp, dt=BF),
+            xa=z(N, D, dt=AD), q=z(B, H, T, hd, dt=H16), k=z(B, H, T, hd, dt=H16), vt=z(B, H, hd, Tp, dt=H16),
             oa=z(N, D, dt=AD),
             xm=z(N, D, dt=AD), cap_part=z(N, self.H, E),
             idx_c=z(N, dt=torch.int32), idx_a=z(N, dt=torch.int32), scale_c=z(N), scale_a=z(N),
@@ -257,7 +259,7 @@ class DiTEngine:
                      bias=w[name + "_b"], act=ops.ACT_LRELU, act_slope=0.01,
                      out_f32=conv[i], out_ld=D, out_g=(Tm * D, 0))
         pooled = torch.empty(B, Tpool, D, device=dev, dtype=self.adt)
-        ops.pool2_sum(conv[0], conv[1], B=B, Tin=Tm, Tout=Tpool, D=D, out_bf16=pooled)
+        ops.pool2_sum(conv[0], conv[1], B=B, Tin=Tm, Tout=Tpool, D=D, out_fp16=pooled)
         ac = torch.empty(B, Tpool, D, device=dev, dtype=F32)
         ops.gemm(pooled.view(B * Tpool, D), w["final_proj_w"], bias=w["final_proj_b"], out_f32=ac, out_ld=D)
         if Tpool != T:  # length fix-up, vocal2music_moe.py:397-401
@@ -283,22 +285,22 @@ class DiTEngine:
             acoustic = self.prepare_acoustic(midi, beats, T)
         ac, ac_logits = acoustic
         cap16 = torch.empty(B * L, self.ori_dim, device=dev, dtype=self.adt)
-        ops.ew(caption.to(dev, F32).contiguous().view(B * L, -1), out_bf16=cap16)
+        ops.ew(caption.to(dev, F32).contiguous().view(B * L, -1), out_fp16=cap16)
         h1 = torch.empty(B * L, D, device=dev, dtype=self.adt)
-        ops.gemm(cap16, w["c_w0"], bias=w["c_b0"], act=ops.ACT_GELU, out_bf16=h1, outb_ld=D)
+        ops.gemm(cap16, w["c_w0"], bias=w["c_b0"], act=ops.ACT_GELU, out_fp16=h1, outb_ld=D)
         h2 = torch.empty(B * L, D, device=dev, dtype=F32)
         ops.gemm(h1, w["c_w2"], bias=w["c_b2"], out_f32=h2, out_ld=D)
         cap = torch.empty(B, L, D, device=dev, dtype=F32)
-        if self.adt == BF:
-            cap_bf = torch.empty(B * L, D, device=dev, dtype=BF)
-            ops.norm_mod(h2, kind=1, w=w["c_ln_w"], b=w["c_ln_b"], eps=1e-5, out_f32=cap, out_bf16=cap_bf)
+        if self.adt == H16:
+            cap_bf = torch.empty(B * L, D, device=dev, dtype=H16)
+            ops.norm_mod(h2, kind=1, w=w["c_ln_w"], b=w["c_ln_b"], eps=1e-5, out_f32=cap, out_fp16=cap_bf)
         else:  # fp32 operands: the fp32 caption is the GEMM operand itself
             ops.norm_mod(h2, kind=1, w=w["c_ln_w"], b=w["c_ln_b"], eps=1e-5, out_f32=cap)
             cap_bf = cap.view(B * L, D)
         pool = torch.empty(B, D, device=dev, dtype=F32)
         ops.mean_tokens(cap, pool)
         pool_n = torch.empty(B, D, device=dev, dtype=self.adt)
-        ops.norm_mod(pool, kind=1, w=w["cap_ln_w"], b=w["cap_ln_b"], eps=1e-5, out_bf16=pool_n)
+        ops.norm_mod(pool, kind=1, w=w["cap_ln_w"], b=w["cap_ln_b"], eps=1e-5, out_fp16=pool_n)
         cap_emb = torch.empty(B, D, device=dev, dtype=F32)
         ops.gemm(pool_n, w["cap_w"], bias=w["cap_b"], out_f32=cap_emb, out_ld=D)
         cond = DiTCond(B=B, T=T, L=L, acoustic=ac, ac_logits=ac_logits, caption=cap, cap_emb=cap_emb)
@@ -308,9 +310,9 @@ class DiTEngine:
         for k in range(self.depth):
             b = w["blocks"][k]
             # K / V^T of the two short-KV attentions, written head-major by the k|v GEMM epilogue
-            ops.norm_mod(cap.view(B * L, D), kind=0, w=b["y_norm"], eps=self.eps, out_bf16=y16)
-            kk = torch.empty(B, H, L, hd, device=dev, dtype=BF)
-            vt = torch.zeros(B, H, hd, Lp, device=dev, dtype=BF)
+            ops.norm_mod(cap.view(B * L, D), kind=0, w=b["y_norm"], eps=self.eps, out_fp16=y16)
+            kk = torch.empty(B, H, L, hd, device=dev, dtype=H16)
+            vt = torch.zeros(B, H, hd, Lp, device=dev, dtype=H16)
             ops.gemm(y16, b["wkvy"], mode=ops.EPI_QKV_ROPE, qkv_sec0=1, T=L, heads=H, head_dim=hd, Tp=Lp,
                      k_out=kk, vt_out=vt)
             cond.k_y.append(kk)
@@ -318,12 +320,12 @@ class DiTEngine:
             # MoE caption cross-attention (vocal2music_moe.py:117-131), folded: fp32 k|v projection, then
             # WK[b,h] = K_h (scale W_q,h) as one batched GEMM, score bias and V.(W_gate W_o) by vb_route_prepare
             kvf = torch.empty(B * L, 2 * D, device=dev, dtype=F32)
-            kvo = kvf if self.adt == F32 else torch.empty(B * L, 2 * D, device=dev, dtype=BF)
+            kvo = kvf if self.adt == F32 else torch.empty(B * L, 2 * D, device=dev, dtype=H16)
             ops.gemm(cap_bf, b["mkv_w"], bias=b["mkv_b"], out_f32=kvf, out_ld=2 * D,
-                     out_bf16=None if self.adt == F32 else kvo, outb_ld=2 * D)
+                     out_fp16=None if self.adt == F32 else kvo, outb_ld=2 * D)
             wk = torch.zeros(B, H * self.LK, D, device=dev, dtype=self.adt)
             ops.gemm(kvo[:, :D].view(B, L, H, hd).permute(0, 2, 1, 3), b["mq_wT"], M=L, N=D, G1=H, G2=B,
-                     a_c2=(1, 0), a_c3=(0, 1), b_c2=(1, 0, 0), out_bf16=wk, outb_ld=D,
+                     a_c2=(1, 0), a_c3=(0, 1), b_c2=(1, 0, 0), out_fp16=wk, outb_ld=D,
                      outb_g=(self.LK * D, H * self.LK * D))
             bs = torch.empty(B, H, self.LK, device=dev, dtype=F32)
             vg = torch.empty(B, H, self.LK, self.E, device=dev, dtype=F32)
@@ -353,10 +355,10 @@ class DiTEngine:
         h = torch.empty(R, D, device=dev, dtype=self.adt)
         temb = torch.empty(R, D, device=dev, dtype=F32)
         ada = torch.empty(R, D, device=dev, dtype=self.adt)
-        ops.timestep_embed(t, w["t_freqs"], out_bf16=sin)
-        ops.gemm(sin, w["t_w0"], bias=w["t_b0"], act=ops.ACT_SILU, out_bf16=h, outb_ld=D)
+        ops.timestep_embed(t, w["t_freqs"], out_fp16=sin)
+        ops.gemm(sin, w["t_w0"], bias=w["t_b0"], act=ops.ACT_SILU, out_fp16=h, outb_ld=D)
         ops.gemm(h, w["t_w2"], bias=w["t_b2"], out_f32=temb, out_ld=D)
-        ops.ew(temb, cap_emb, act=ops.ACT_SILU, out_bf16=ada)
+        ops.ew(temb, cap_emb, act=ops.ACT_SILU, out_fp16=ada)
         ops.gemm(ada, w["ada_w"], bias=w["ada_b"], out_f32=mod_out, out_ld=self.mod_ld)
         ops.linear_small(temb, w["hl_w"], w["hl_b"], hl_out)
 
@@ -404,7 +406,7 @@ class DiTEngine:
             sh_mlp, sc_mlp, g_mlp = mod[:, m0 + 3 * D:], mod[:, m0 + 4 * D:], mod[:, m0 + 5 * D:]
             # ---- attention branch (vocal2music_moe.py:245-250; flag_large_dit_moe.py:323-406)
             ops.norm_mod(xcur, kind=0, w=b["attn_norm"], shift=sh_msa, scale=sc_msa, mod_ld=mld,
-                         rows_per_batch=T, eps=self.eps, out_bf16=ws["xa"])
+                         rows_per_batch=T, eps=self.eps, out_fp16=ws["xa"])
             ops.mark("norm_mod")
             ops.gemm(ws["xa"], b["wqkv"], mode=ops.EPI_QKV_ROPE, rope_cs=w["rope"], T=T, heads=H, head_dim=hd,
                      Tp=Tp, q_out=ws["q"], k_out=ws["k"], vt_out=ws["vt"])
@@ -412,14 +414,14 @@ class DiTEngine:
             # self-attention + gated text cross-attention in one tcgen05 flash-attention launch
             ops.attn_fused(ws["q"], (hd, T * hd, H * T * hd), B=B, T=T, H=H, hd=hd, scale=scale,
                            k_self=ws["k"], vt_self=ws["vt"], Tp=Tp, k_text=cond.k_y[k], vt_text=cond.vt_y[k],
-                           L=L, Lp=cond.vt_y[k].shape[-1], gate=b["gate"], out_bf16=ws["oa"])
+                           L=L, Lp=cond.vt_y[k].shape[-1], gate=b["gate"], out_fp16=ws["oa"])
             ops.mark("attn_fused")
             ops.gemm(ws["oa"], b["wo"], gate=g_msa, gate_rows=T, gate_ld=mld, residual=xcur,
                      out_f32=hbuf, out_ld=D)
             ops.mark("gemm:wo")
             # ---- Band-MoE branch (vocal2music_moe.py:251-257, 117-185)
             ops.norm_mod(hbuf, kind=0, w=b["ffn_norm"], shift=sh_mlp, scale=sc_mlp, mod_ld=mld,
-                         rows_per_batch=T, eps=self.eps, out_bf16=ws["xm"])
+                         rows_per_batch=T, eps=self.eps, out_fp16=ws["xm"])
             ops.mark("norm_mod")
             # caption gate: per-head softmax(xm . WK^T + bias) . VG inside one GEMM epilogue
             ops.gemm(ws["xm"].view(B, T, D), cond.wk_m[k], M=T, G1=B, a_c2=(1, 0), b_c2=(1, 0, 0), mode=ops.EPI_ROUTE,
@@ -446,18 +448,18 @@ class DiTEngine:
                                 ws["bucket_start"], N, E, ws["xm"], ws["xs"], ws["row_map"], ws["row_scale"])
             ops.mark("moe_dispatch")
             ops.gemm(ws["xs"], b["w13"], M=max_rows, b_c2=(0, 0, 1), tile_group=ws["tile_group"],
-                     m_tiles_used=ws["m_tiles"], swiglu=True, out_bf16=ws["hs"], outb_ld=Fh)
+                     m_tiles_used=ws["m_tiles"], swiglu=True, out_fp16=ws["hs"], outb_ld=Fh)
             ops.mark("gemm:w13")
             ops.gemm(ws["hs"], b["w2"], M=max_rows, b_c2=(0, 0, 1), tile_group=ws["tile_group"],
                      m_tiles_used=ws["m_tiles"], row_map=ws["row_map"], rows_out=2 * N,
-                     row_scale=ws["row_scale"], out_bf16=ws["y2"], outb_ld=D)
+                     row_scale=ws["row_scale"], out_fp16=ws["y2"], outb_ld=D)
             ops.mark("gemm:w2")
             # y = y_caption + y_acoustic (vocal2music_moe.py:166) is never materialised: the frequency experts'
             # first GEMM reads both halves of y2 through the conv addressing (2 "taps" N rows apart, the band's
             # weights repeated along K), so the sum happens in the fp32 accumulator.
             yb = ws["y2"].view(2 * N, E, self.band).permute(1, 0, 2)  # [E, 2N, band] view: per-band K slice
             ops.gemm(yb, b["f13"], M=N, G1=E, kpt=self.band // self.kq, dil=N, pad=0, a_c2=(1, 0), b_c2=(1, 0, 0),
-                     swiglu=True, out_bf16=ws["hf"], outb_ld=Fh, outb_g=(N * Fh, 0))
+                     swiglu=True, out_fp16=ws["hf"], outb_ld=Fh, outb_g=(N * Fh, 0))
             ops.mark("gemm:f13")
             ops.gemm(ws["hf"], b["f2"], M=N, G1=E, a_c2=(1, 0), b_c2=(1, 0, 0),
                      gate=g_mlp, gate_rows=T, gate_ld=mld, gate_g1=self.band, residual=hbuf,
@@ -469,7 +471,7 @@ class DiTEngine:
         # ---- final layer (vocal2music_moe.py:268-291,431)
         f0 = self.depth * 6 * D
         ops.norm_mod(xcur, kind=1, shift=mod[:, f0:], scale=mod[:, f0 + D:], mod_ld=mld, rows_per_batch=T,
-                     eps=1e-6, out_bf16=ws["xf"])
+                     eps=1e-6, out_fp16=ws["xf"])
         ops.mark("norm_mod")
         # all 32 (zero-padded) output columns are computed so the chunk takes the coalesced epilogue path
         ops.gemm(ws["xf"], w["final_w"], bias=w["final_b"], out_f32=ws["v"], out_ld=32)

@@ -113,9 +113,9 @@ class _FinalLayerParams(nn.Module):
 class TxtFlagLargeImprovedDiTV2(nn.Module):
     """AccompBand DiT with Band-MoE. forward(x, t, context) -> (v, lb_loss) exactly like the
     reference (vocal2music_moe.py:375-434); inference only.
-    `precision` ("bf16" | "tf32") selects the GEMM operand format of the engine."""
+    `precision` ("fp16" | "tf32") selects the GEMM operand format of the engine."""
 
-    precision = "tf32"
+    precision = "fp16"
 
     def __init__(self, in_channels, context_dim, hidden_size=1152, depth=28, num_heads=16, max_len=1000,
                  num_experts=4, ori_dim=1024):
@@ -180,17 +180,19 @@ class TxtFlagLargeImprovedDiTV2(nn.Module):
         return self._engine
 
     def _cond(self, eng, midi, beats, caption, T):
-        """Step-invariant conditioning, memoised on the identity of the context tensors: the
-        reference's sampler calls forward 48x with the same two context dicts (cfm1_audio.py:158-159)."""
-        key = (midi.data_ptr(), midi._version, beats.data_ptr(), beats._version, caption.data_ptr(),
-               caption._version, tuple(caption.shape), T)
-        for k, c in self._cond_cache:
-            if k == key:
-                return c
-        c = eng.prepare(midi, beats, caption, T)
-        self._cond_cache.append((key, c))
+        """Step-invariant conditioning, memoised on the IDENTITY of the caller's context tensors: the
+        reference's sampler calls forward 48x with the same two context dicts (cfm1_audio.py:158-159).
+        Each entry keeps strong references to the tensors it was computed from, so an address can never be
+        recycled for a different tensor while the entry is alive; a hit needs the same objects (`is`) at the
+        same in-place version."""
+        for (m, b, c, vers, t_len), cond in self._cond_cache:
+            if m is midi and b is beats and c is caption and t_len == T and \
+                    vers == (midi._version, beats._version, caption._version):
+                return cond
+        cond = eng.prepare(midi, beats, caption.float(), T)
+        self._cond_cache.append(((midi, beats, caption, (midi._version, beats._version, caption._version), T), cond))
         del self._cond_cache[:-4]
-        return c
+        return cond
 
     @torch.no_grad()
     def forward(self, x, t, context):
@@ -202,7 +204,7 @@ class TxtFlagLargeImprovedDiTV2(nn.Module):
         midi, beats = context["c_concat"]["midi"], context["c_concat"]["beats"]
         caption = context["c_crossattn"]
         B, _, T = x.shape
-        cond = self._cond(eng, midi, beats, caption.float(), T)
+        cond = self._cond(eng, midi, beats, caption, T)  # keyed on the caller's tensor, not a .float() temporary
         # Gumbel noise: same generator, shapes and order as MoE.forward (vocal2music_moe.py:134,150,151)
         N, E = B * T, self.num_experts
         expo = [tuple(torch.empty(N, k, device=x.device, dtype=torch.float32).exponential_() for k in (2, E, E))

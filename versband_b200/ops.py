@@ -35,12 +35,12 @@ def _rev_desc(t: torch.Tensor, rank: int):
     return dims, strides
 
 
-def _route(out_bf16, out_f32):
+def _route(out_fp16, out_f32):
     """An fp32 tensor passed in the operand-output slot is routed to the fp32 output pointer."""
-    if out_bf16 is not None and out_bf16.dtype == torch.float32:
+    if out_fp16 is not None and out_fp16.dtype == torch.float32:
         assert out_f32 is None
-        return None, out_bf16
-    return out_bf16, out_f32
+        return None, out_fp16
+    return out_fp16, out_f32
 
 
 def _check_f32(t: Optional[torch.Tensor], name: str):
@@ -61,16 +61,16 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: Optional[int] = None, N: Option
          row_off_g1: int = 0, rows_out: Optional[int] = None,
          residual: Optional[torch.Tensor] = None, accumulate: bool = False,
          out_f32: Optional[torch.Tensor] = None, out_ld: int = 0, out_g=(0, 0),
-         out_bf16: Optional[torch.Tensor] = None, outb_ld: int = 0, outb_g=(0, 0),
+         out_fp16: Optional[torch.Tensor] = None, outb_ld: int = 0, outb_g=(0, 0),
          act_out: int = ACT_NONE, act_out_slope: float = 0.0, out_scale: float = 1.0,
          rope_cs: Optional[torch.Tensor] = None, T: int = 0, heads: int = 0, head_dim: int = 0,
          Tp: int = 0, q_out=None, k_out=None, vt_out=None, qkv_sec0: int = 0,
          route_vg: Optional[torch.Tensor] = None, route_vg_g1: int = 0) -> None:
     """D = epilogue(A @ B^T) on the tcgen05 GEMM (see include/versband.h: vb_gemm).
 
-    `a` is a bf16 view of up to 4 dims [c3, c2, rows, k]; `b` a bf16 view [group, n, k].
+    `a` is a fp16 view of up to 4 dims [c3, c2, rows, k]; `b` a fp16 view [group, n, k].
     """
-    assert a.dtype == b.dtype and a.dtype in (torch.bfloat16, torch.float32) and a.is_cuda and b.is_cuda
+    assert a.dtype == b.dtype and a.dtype in (torch.float16, torch.float32) and a.is_cuda and b.is_cuda
     args = GemmArgs()
     args.operand_f32 = int(a.dtype == torch.float32)
     kq = 32 if args.operand_f32 else 64
@@ -106,10 +106,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: Optional[int] = None, N: Option
     args.residual, args.accumulate = _ptr(residual), int(accumulate)
     args.out_f32, args.out_ld = _ptr(out_f32), out_ld
     args.out_g1, args.out_g2 = out_g
-    if out_bf16 is not None:
-        assert out_bf16.dtype in (torch.bfloat16, torch.float32)
-        args.outb_f32 = int(out_bf16.dtype == torch.float32)
-    args.out_bf16, args.outb_ld = _ptr(out_bf16), outb_ld
+    if out_fp16 is not None:
+        assert out_fp16.dtype in (torch.float16, torch.float32)
+        args.outb_f32 = int(out_fp16.dtype == torch.float32)
+    args.out_fp16, args.outb_ld = _ptr(out_fp16), outb_ld
     args.outb_g1, args.outb_g2 = outb_g
     args.act_out, args.act_out_slope, args.out_scale = act_out, act_out_slope, out_scale
     _check_f32(rope_cs, "rope_cs")
@@ -129,29 +129,29 @@ def _call(name: str, *args) -> None:
 
 
 def norm_mod(x, *, kind: int, w=None, b=None, shift=None, scale=None, mod_ld: int = 0,
-             rows_per_batch: int = 0, eps: float, out_bf16=None, out_f32=None) -> None:
+             rows_per_batch: int = 0, eps: float, out_fp16=None, out_f32=None) -> None:
     """kind 0 RMSNorm / 1 LayerNorm (+ optional affine, + optional adaLN modulate)."""
     rows, D = x.numel() // x.shape[-1], x.shape[-1]
     assert x.dtype == torch.float32 and x.is_contiguous()
-    out_bf16, out_f32 = _route(out_bf16, out_f32)
+    out_fp16, out_f32 = _route(out_fp16, out_f32)
     _call("vb_norm_mod", kind, _ptr(x), _ptr(w), _ptr(b), _ptr(shift), _ptr(scale), mod_ld,
-          rows_per_batch or rows, eps, _ptr(out_bf16), _ptr(out_f32), rows, D)
+          rows_per_batch or rows, eps, _ptr(out_fp16), _ptr(out_f32), rows, D)
 
 
 def softmax_rows(S, lds: int, P, ldp: int, rows: int, n: int) -> None:
     _call("vb_softmax_rows", _ptr(S), lds, _ptr(P), ldp, rows, n)
 
 
-def attn_smallkv(q, q_strides, K, V, kv_ld, *, B, T, H, hd, L, scale, gate=None, base=None, out_bf16=None,
+def attn_smallkv(q, q_strides, K, V, kv_ld, *, B, T, H, hd, L, scale, gate=None, base=None, out_fp16=None,
                  out_f32=None) -> None:
     _call("vb_attn_smallkv", _ptr(q), q_strides[0], q_strides[1], q_strides[2], _ptr(K), _ptr(V), kv_ld, B, T, H,
-          hd, L, scale, _ptr(gate), _ptr(base), _ptr(out_bf16), _ptr(out_f32))
+          hd, L, scale, _ptr(gate), _ptr(base), _ptr(out_fp16), _ptr(out_f32))
 
 
-def timestep_embed(t, freqs, *, out_f32=None, out_bf16=None, dim: int = 256) -> None:
+def timestep_embed(t, freqs, *, out_f32=None, out_fp16=None, dim: int = 256) -> None:
     assert t.dtype == torch.int64
-    out_bf16, out_f32 = _route(out_bf16, out_f32)
-    _call("vb_timestep_embed", _ptr(t), _ptr(freqs), _ptr(out_f32), _ptr(out_bf16), t.numel(), dim)
+    out_fp16, out_f32 = _route(out_fp16, out_f32)
+    _call("vb_timestep_embed", _ptr(t), _ptr(freqs), _ptr(out_f32), _ptr(out_fp16), t.numel(), dim)
 
 
 def linear_small(x, W, bias, out) -> None:
@@ -163,10 +163,10 @@ def linear_small(x, W, bias, out) -> None:
 def router(cap_feat, Wc, bc, ac_logits, ac_ld, hl_logits, hl_ld, e0, e1, e2, tau, N, T, idx_c, idx_a,
            scale_c, scale_a, cap_logits_out=None, bucket_count=None, usage=None, slot_c=None, slot_a=None,
            cap_partial=None) -> None:
-    """cap_feat: fp32/bf16 caption-attention features [N, D] (gate = Wc . feat + bc), or None with
+    """cap_feat: fp32/fp16 caption-attention features [N, D] (gate = Wc . feat + bc), or None with
     cap_partial [N, heads, E] = per-head gate contributions from a VB_EPI_ROUTE GEMM."""
     f32 = cap_feat if cap_feat is not None and cap_feat.dtype == torch.float32 else None
-    b16 = cap_feat if cap_feat is not None and cap_feat.dtype == torch.bfloat16 else None
+    b16 = cap_feat if cap_feat is not None and cap_feat.dtype == torch.float16 else None
     D = cap_feat.shape[-1] if cap_feat is not None else 0
     _check_f32(cap_partial, "cap_partial")
     _call("vb_router", _ptr(f32), _ptr(b16), _ptr(Wc), _ptr(bc), _ptr(ac_logits), ac_ld, _ptr(hl_logits), hl_ld,
@@ -208,16 +208,16 @@ def gather_rows(x, row_map, m_tiles_used, n_tokens, out, max_rows) -> None:
           max_rows)
 
 
-def ew(a, b=None, *, alpha=1.0, beta=1.0, act=ACT_NONE, slope=0.0, out_f32=None, out_bf16=None, rep=1):
+def ew(a, b=None, *, alpha=1.0, beta=1.0, act=ACT_NONE, slope=0.0, out_f32=None, out_fp16=None, rep=1):
     rows, D = a.numel() // a.shape[-1], a.shape[-1]
-    out_bf16, out_f32 = _route(out_bf16, out_f32)
-    _call("vb_ew", _ptr(a), _ptr(b), alpha, beta, act, slope, _ptr(out_f32), _ptr(out_bf16), rows, D, rep)
+    out_fp16, out_f32 = _route(out_fp16, out_f32)
+    _call("vb_ew", _ptr(a), _ptr(b), alpha, beta, act, slope, _ptr(out_f32), _ptr(out_fp16), rows, D, rep)
 
 
-def nct_to_ntc(x, out_bf16, *, scale=1.0) -> None:
+def nct_to_ntc(x, out_fp16, *, scale=1.0) -> None:
     B, Cc, T = x.shape
-    _call("vb_nct_to_ntc", _ptr(x), scale, _ptr(out_bf16), B, Cc, T, out_bf16.shape[-1],
-          int(out_bf16.dtype == torch.float32))
+    _call("vb_nct_to_ntc", _ptr(x), scale, _ptr(out_fp16), B, Cc, T, out_fp16.shape[-1],
+          int(out_fp16.dtype == torch.float32))
 
 
 def ntc_to_nct(e_c, x, *, e_u=None, ld, s=0.0, dt=0.0, x_cl=None) -> None:
@@ -231,14 +231,14 @@ def ntc_to_nct(e_c, x, *, e_u=None, ld, s=0.0, dt=0.0, x_cl=None) -> None:
           int(x_cl is not None and x_cl.dtype == torch.float32), rep)
 
 
-def embed_rows(idx, table, out_bf16) -> None:
-    _call("vb_embed_rows", _ptr(idx), _ptr(table), table.shape[0], table.shape[1], _ptr(out_bf16), idx.numel(),
-          int(out_bf16.dtype == torch.float32))
+def embed_rows(idx, table, out_fp16) -> None:
+    _call("vb_embed_rows", _ptr(idx), _ptr(table), table.shape[0], table.shape[1], _ptr(out_fp16), idx.numel(),
+          int(out_fp16.dtype == torch.float32))
 
 
-def pool2_sum(a, b, *, B, Tin, Tout, D, out_bf16=None, out_f32=None) -> None:
-    out_bf16, out_f32 = _route(out_bf16, out_f32)
-    _call("vb_pool2_sum", _ptr(a), _ptr(b), B, Tin, Tout, D, _ptr(out_bf16), _ptr(out_f32))
+def pool2_sum(a, b, *, B, Tin, Tout, D, out_fp16=None, out_f32=None) -> None:
+    out_fp16, out_f32 = _route(out_fp16, out_f32)
+    _call("vb_pool2_sum", _ptr(a), _ptr(b), B, Tin, Tout, D, _ptr(out_fp16), _ptr(out_f32))
 
 
 GN_SPLIT = 8
@@ -250,12 +250,12 @@ def gn_stats(x, B, T, Cc, G, eps, mean, rstd, scratch=None) -> None:
     _call("vb_gn_stats", _ptr(x), B, T, Cc, G, eps, _ptr(mean), _ptr(rstd), _ptr(scratch))
 
 
-def gn_apply(x, mean, rstd, w, b, B, T, Cc, G, act, out_bf16) -> None:
-    _call("vb_gn_apply", _ptr(x), _ptr(mean), _ptr(rstd), _ptr(w), _ptr(b), B, T, Cc, G, act, _ptr(out_bf16))
+def gn_apply(x, mean, rstd, w, b, B, T, Cc, G, act, out_fp16) -> None:
+    _call("vb_gn_apply", _ptr(x), _ptr(mean), _ptr(rstd), _ptr(w), _ptr(b), B, T, Cc, G, act, _ptr(out_fp16))
 
 
-def conv_post(x_bf16, w, bias: float, B, T, Cc, k, wav) -> None:
-    _call("vb_conv_post", _ptr(x_bf16), _ptr(w), bias, B, T, Cc, k, _ptr(wav))
+def conv_post(x_fp16, w, bias: float, B, T, Cc, k, wav) -> None:
+    _call("vb_conv_post", _ptr(x_fp16), _ptr(w), bias, B, T, Cc, k, _ptr(wav))
 
 
 def mean_tokens(x, out) -> None:
@@ -264,14 +264,14 @@ def mean_tokens(x, out) -> None:
 
 
 def attn_fused(q, q_strides, *, B, T, H, hd, scale, k_self=None, vt_self=None, Tp=0, k_text=None, vt_text=None,
-               L=0, Lp=0, gate=None, out_bf16=None, out_f32=None) -> None:
+               L=0, Lp=0, gate=None, out_fp16=None, out_f32=None) -> None:
     """Fused tcgen05 attention (self segment and/or one short "text" segment), see vb_attn_fused."""
-    out_bf16, out_f32 = _route(out_bf16, out_f32)
+    out_fp16, out_f32 = _route(out_fp16, out_f32)
     a = AttnArgs()
     a.q = _ptr(q)
     a.q_st, a.q_sh, a.q_sb = q_strides
     a.k_self, a.vt_self, a.k_text, a.vt_text = _ptr(k_self), _ptr(vt_self), _ptr(k_text), _ptr(vt_text)
-    a.gate, a.out_bf16, a.out_f32 = _ptr(gate), _ptr(out_bf16), _ptr(out_f32)
+    a.gate, a.out_fp16, a.out_f32 = _ptr(gate), _ptr(out_fp16), _ptr(out_f32)
     a.B, a.T, a.H, a.hd, a.Tp, a.L, a.Lp, a.scale = B, T, H, hd, Tp, L, Lp, scale
     _lib.check(_lib.lib().vb_attn_fused(C.byref(a), _stream()), "vb_attn_fused")
 

@@ -19,7 +19,7 @@ class AccompBandPipeline:
     def __init__(self, dit_sd: Dict[str, torch.Tensor], vae_sd: Dict[str, torch.Tensor],
                  voc_sd: Dict[str, torch.Tensor], *, dit_cfg: dict, ddconfig: dict, embed_dim: int,
                  voc_cfg: dict, scale_factor: float = 1.0, device="cuda", use_graph: bool = True,
-                 n_points: int = 25, precision: str = "tf32"):
+                 n_points: int = 25, precision: str = "fp16"):
         from . import _lib
         _lib.check(_lib.lib().vb_check_device(), "vb_check_device")
         self.dev = torch.device(device)
@@ -44,6 +44,10 @@ class AccompBandPipeline:
                  noise: Optional[torch.Tensor] = None, generator=None, events: Optional[dict] = None):
         """Device tensors in, device tensors out.
         midi/beats int64 [B,1,T_mel]; caption(_uncond) fp32 [B,L,ori_dim] (FLAN-T5 states).
+        `generator`: one torch.Generator for the whole batch (the reference's semantics: one stream, draws
+        shaped by the batch) or a LIST of B generators = per-clip seeding: clip c then gets exactly the latent
+        noise and router draws of a batch-1 run with generator[c], whatever batch or GPU it lands on
+        (SURVEY.md §8e).
         Returns dict(latent [B,C,T], mel [B,80,2T], wav [B, 2T*hop])."""
         dev = self.dev
         B, _, Tm = midi.shape
@@ -52,7 +56,10 @@ class AccompBandPipeline:
         mark("start")
         cond2 = self._prepare(midi, beats, caption, caption_uncond, T)
         if x0 is None:
-            x0 = torch.randn(B, self.dit.C, T, device=dev, dtype=F32, generator=generator)
+            if isinstance(generator, (list, tuple)):
+                x0 = torch.cat([torch.randn(1, self.dit.C, T, device=dev, dtype=F32, generator=g) for g in generator], 0)
+            else:
+                x0 = torch.randn(B, self.dit.C, T, device=dev, dtype=F32, generator=generator)
         mark("sampler_start")
         z = self.sampler.sample_cfg(x0, cond2, None, guidance, noise=noise, generator=generator)
         mark("sampler_end")
@@ -62,7 +69,8 @@ class AccompBandPipeline:
             wav = self.voc.forward(mel)
             mark("end")
             return {"latent": z, "mel": mel, "wav": wav}
-        # VAE decode + vocoder replayed from one CUDA graph per (B, T)
+        # VAE decode and vocoder replayed from CUDA graphs per (B, T): two graphs, so that the stage boundary
+        # is an observable point on the stream (bench.py records an event there; one extra graph launch)
         st = self._post.get((B, T))
         if st is None:
             st = {"z": z.clone()}
@@ -72,15 +80,17 @@ class AccompBandPipeline:
                 self.voc.forward(self.vae.decode(st["z"], scale=1.0 / self.scale_factor))
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
                 st["mel"] = self.vae.decode(st["z"], scale=1.0 / self.scale_factor)
+            with torch.cuda.graph(g2, pool=g1.pool()):
                 st["wav"] = self.voc.forward(st["mel"])
-            st["graph"] = g
+            st["graph_vae"], st["graph_voc"] = g1, g2
             self._post[(B, T)] = st
         st["z"].copy_(z)
-        st["graph"].replay()
-        mark("vae_end")  # (decode and vocoder are one graph: the split is not observable)
+        st["graph_vae"].replay()
+        mark("vae_end")
+        st["graph_voc"].replay()
         mark("end")
         return {"latent": z, "mel": st["mel"].clone(), "wav": st["wav"].clone()}
 

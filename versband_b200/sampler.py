@@ -67,12 +67,41 @@ class FlowSampler:
                 self._native_noise = False
         return self._native_noise
 
-    def _draw_native(self, st: dict, generator) -> None:
-        gen = generator if generator is not None else torch.cuda.default_generators[self.dit.dev.index or 0]
+    def _draw_native(self, st: dict, generator) -> bool:
+        """All Exp(1) draws of a run in one launch, consuming `generator` (or the default generator of the
+        engine's device — the CURRENT device when the engine was built with a bare "cuda") exactly like the
+        reference's sequence of `exponential_()` calls. Returns False (nothing consumed) if the library
+        rejects the shape, in which case the caller draws with torch."""
+        if generator is not None:
+            gen = generator
+        else:
+            idx = self.dit.dev.index if self.dit.dev.index is not None else torch.cuda.current_device()
+            gen = torch.cuda.default_generators[idx]
         off = gen.get_offset()
         S, d = len(self.sched), self.dit.depth
-        ops.router_noise(gen.initial_seed(), off, st["N"], self.dit.E, d, S, st["e0"], st["e1"], st["e2"])
+        try:
+            ops.router_noise(gen.initial_seed(), off, st["N"], self.dit.E, d, S, st["e0"], st["e1"], st["e2"])
+        except Exception:
+            return False
         gen.set_offset(off + 4 * S * 2 * d * 3)
+        return True
+
+    def _draw_per_clip(self, st: dict, B: int, T: int, generators) -> None:
+        """Router draws of a batch of B clips from B generators: each clip's [steps, depth, 2T, k] block is
+        drawn as a batch-1 run (cond rows then uncond rows) and placed at the clip's rows of the batched
+        layout (cond rows of all clips first, then uncond rows)."""
+        S, d, E, dev = len(self.sched), self.dit.depth, self.dit.E, self.dit.dev
+        native = self.native_noise_ok()
+        for c, gen in enumerate(generators):
+            one = dict(N=T, e0=torch.empty(S, d, 2 * T, 2, device=dev, dtype=F32),
+                       e1=torch.empty(S, d, 2 * T, E, device=dev, dtype=F32),
+                       e2=torch.empty(S, d, 2 * T, E, device=dev, dtype=F32))
+            if not (native and self._draw_native(one, gen)):
+                for s_ in range(S):
+                    self._draw_step(one, s_, gen)
+            for name in ("e0", "e1", "e2"):
+                st[name][:, :, c * T:(c + 1) * T] = one[name][:, :, :T]
+                st[name][:, :, (B + c) * T:(B + c + 1) * T] = one[name][:, :, T:]
 
     # ---------------------------------------------------------------- noise
     def _draw_step(self, st: dict, s: int, generator) -> None:
@@ -151,12 +180,17 @@ class FlowSampler:
         elif pair is not st["cond2"]:
             st["cond2"].copy_from(pair)
         st["x"].copy_(x0)
+        if rng and isinstance(generator, (list, tuple)):
+            # per-clip seeding: clip c consumes generator[c] exactly as a batch-1 run would
+            assert len(generator) == B
+            self._draw_per_clip(st, B, T, generator)
+            rng, noise, generator = False, None, None
         if rng and self.native_noise_ok():
             # all 576 Exp(1) draws in one launch, bit-identical to torch's stream; the graph below then
             # runs without RNG nodes
-            self._draw_native(st, generator)
-            rng = False
-            noise = None
+            if self._draw_native(st, generator):
+                rng = False
+                noise = None
         elif not rng:
             st["e0"].copy_(noise[..., 0:2])
             st["e1"].copy_(noise[..., 2:2 + E])

@@ -3,7 +3,7 @@
 Mirrors reference ldm/models/autoencoder1d.py (Decoder1D.forward :480-513, Encoder1D.forward
 :384-409, ResnetBlock1D :211-231, AttnBlock1D :253-274, Upsample1D :287-291, Downsample1D
 :306-313).  Activations are channels-last fp32 [B, T, C] in HBM; every conv is one vb_gemm launch
-whose A operand is the bf16 GroupNorm+swish output (TMA out-of-bounds zero fill = conv padding).
+whose A operand is the fp16 GroupNorm+swish output (TMA out-of-bounds zero fill = conv padding).
 """
 from __future__ import annotations
 
@@ -12,7 +12,7 @@ from typing import Dict
 import torch
 
 from . import ops
-from .dit import BF, F32, _bf, pack_conv_weight
+from .dit import H16, F32, _bf, pack_conv_weight
 
 
 class VAEEngine:
@@ -48,8 +48,8 @@ class VAEEngine:
                     # k3 stride-2 conv on rows [T/2, 2C]: tap0 = (j=0 | j=1), tap1 = (j=2 | 0)
                     co, ci, k = t.shape
                     assert k == 3 and (2 * ci) % 64 == 0
-                    wp = torch.zeros(co, 2, 2 * ci, device=dev, dtype=BF)
-                    wp[:, 0, :ci], wp[:, 0, ci:], wp[:, 1, :ci] = t[:, :, 0].to(BF), t[:, :, 1].to(BF), t[:, :, 2].to(BF)
+                    wp = torch.zeros(co, 2, 2 * ci, device=dev, dtype=H16)
+                    wp[:, 0, :ci], wp[:, 0, ci:], wp[:, 1, :ci] = t[:, :, 0].to(H16), t[:, :, 1].to(H16), t[:, :, 2].to(H16)
                     self.w[base + ".w"] = wp.reshape(co, 4 * ci).contiguous()
                 else:
                     self.w[base + ".w"] = pack_conv_weight(t)
@@ -63,8 +63,8 @@ class VAEEngine:
             self.w[base + ".qkv.bias"] = torch.cat([self.w[base + f".{c}.bias"] for c in "qkv"], 0).contiguous()
 
     # ------------------------------------------------------------------ building blocks
-    def _conv(self, a_bf, name, B, T, *, out_f32=None, out_bf16=None, residual=None, Cin=None):
-        """Conv1d(k, stride 1, 'same') over channels-last bf16 a_bf [B, T, Cpitch]."""
+    def _conv(self, a_bf, name, B, T, *, out_f32=None, out_fp16=None, residual=None, Cin=None):
+        """Conv1d(k, stride 1, 'same') over channels-last fp16 a_bf [B, T, Cpitch]."""
         w = self.w[name + ".w"]
         k = self.k[name]
         Cout = w.shape[0]
@@ -72,14 +72,14 @@ class VAEEngine:
         a = a_bf if Cin is None else a_bf[:, :, :Cin]
         ops.gemm(a, w, M=T, G1=B, kpt=kpt, dil=1, pad=k // 2, a_c2=(1, 0), bias=self.w[name + ".bias"],
                  residual=residual, out_f32=out_f32, out_ld=Cout, out_g=(T * Cout, 0),
-                 out_bf16=out_bf16, outb_ld=(out_bf16.shape[-1] if out_bf16 is not None else 0),
-                 outb_g=((T * out_bf16.shape[-1], 0) if out_bf16 is not None else (0, 0)))
+                 out_fp16=out_fp16, outb_ld=(out_fp16.shape[-1] if out_fp16 is not None else 0),
+                 outb_g=((T * out_fp16.shape[-1], 0) if out_fp16 is not None else (0, 0)))
         return Cout
 
     def _gn(self, x, name, B, T, C, act):
         mean = torch.empty(B * self.G, device=self.dev, dtype=F32)
         rstd = torch.empty_like(mean)
-        out = torch.empty(B, T, C, device=self.dev, dtype=BF)
+        out = torch.empty(B, T, C, device=self.dev, dtype=H16)
         ops.gn_stats(x, B, T, C, self.G, 1e-6, mean, rstd)
         ops.gn_apply(x, mean, rstd, self.w[name + ".weight"], self.w[name + ".bias"], B, T, C, self.G, act, out)
         return out
@@ -93,8 +93,8 @@ class VAEEngine:
         a2 = self._gn(h, name + ".norm2", B, T, Cout, ops.ACT_SILU)
         res = x
         if (name + ".nin_shortcut.w") in self.w:
-            xb = torch.empty(B, T, C, device=self.dev, dtype=BF)
-            ops.ew(x, out_bf16=xb)
+            xb = torch.empty(B, T, C, device=self.dev, dtype=H16)
+            ops.ew(x, out_fp16=xb)
             res = torch.empty(B, T, Cout, device=self.dev, dtype=F32)
             self._conv(xb, name + ".nin_shortcut", B, T, out_f32=res)
         out = torch.empty(B, T, Cout, device=self.dev, dtype=F32)
@@ -105,19 +105,19 @@ class VAEEngine:
         C = x.shape[-1]
         Tp = (T + 7) // 8 * 8
         a = self._gn(x, name + ".norm", B, T, C, ops.ACT_NONE)
-        q = torch.empty(B, 1, T, C, device=self.dev, dtype=BF)
+        q = torch.empty(B, 1, T, C, device=self.dev, dtype=H16)
         k = torch.empty_like(q)
-        vt = torch.zeros(B, 1, C, Tp, device=self.dev, dtype=BF)
+        vt = torch.zeros(B, 1, C, Tp, device=self.dev, dtype=H16)
         ops.gemm(a.view(B * T, C), self.w[name + ".qkv.w"], mode=ops.EPI_QKV_ROPE, bias=self.w[name + ".qkv.bias"],
                  T=T, heads=1, head_dim=C, Tp=Tp, q_out=q, k_out=k, vt_out=vt)
         S = torch.empty(B, T, Tp, device=self.dev, dtype=F32)
         ops.gemm(q.view(B, T, C), k.view(B, T, C), M=T, N=T, K=C, G1=B, a_c2=(1, 0), b_c2=(1, 0, 0),
                  alpha=float(int(C) ** (-0.5)), out_f32=S, out_ld=Tp, out_g=(T * Tp, 0))
-        P = torch.empty(B, T, Tp, device=self.dev, dtype=BF)
+        P = torch.empty(B, T, Tp, device=self.dev, dtype=H16)
         ops.softmax_rows(S, Tp, P, Tp, B * T, T)
-        o = torch.empty(B, T, C, device=self.dev, dtype=BF)
+        o = torch.empty(B, T, C, device=self.dev, dtype=H16)
         ops.gemm(P[:, :, :T], vt.view(B, C, Tp)[:, :, :T], M=T, N=C, K=T, G1=B, a_c2=(1, 0), b_c2=(1, 0, 0),
-                 out_bf16=o, outb_ld=C, outb_g=(T * C, 0))
+                 out_fp16=o, outb_ld=C, outb_g=(T * C, 0))
         out = torch.empty(B, T, C, device=self.dev, dtype=F32)
         self._conv(o, name + ".proj_out", B, T, out_f32=out, residual=x)
         return out
@@ -129,10 +129,10 @@ class VAEEngine:
         B, zc, T = z.shape
         dev = self.dev
         zp = (zc + 7) // 8 * 8
-        z_cl = torch.zeros(B, T, zp, device=dev, dtype=BF)
+        z_cl = torch.zeros(B, T, zp, device=dev, dtype=H16)
         ops.nct_to_ntc(z.to(dev, F32).contiguous(), z_cl, scale=scale)
-        zq = torch.zeros(B, T, zp, device=dev, dtype=BF)
-        self._conv(z_cl, "post_quant_conv", B, T, out_bf16=zq, Cin=zc)
+        zq = torch.zeros(B, T, zp, device=dev, dtype=H16)
+        self._conv(z_cl, "post_quant_conv", B, T, out_fp16=zq, Cin=zc)
         d = "decoder."
         C0 = self.w[d + "conv_in.w"].shape[0]
         h = torch.empty(B, T, C0, device=dev, dtype=F32)
@@ -147,8 +147,8 @@ class VAEEngine:
                     h = self._attn(h, f"{d}up.{lvl}.attn.{blk}", B, T)
             if lvl in self.up_levels:  # nearest x2 then conv k3 (autoencoder1d.py:287-291)
                 C = h.shape[-1]
-                up = torch.empty(B, 2 * T, C, device=dev, dtype=BF)
-                ops.ew(h, out_bf16=up, rep=2)
+                up = torch.empty(B, 2 * T, C, device=dev, dtype=H16)
+                ops.ew(h, out_fp16=up, rep=2)
                 T = 2 * T
                 h = torch.empty(B, T, C, device=dev, dtype=F32)
                 self._conv(up, f"{d}up.{lvl}.upsample.conv", B, T, out_f32=h)
@@ -168,7 +168,7 @@ class VAEEngine:
         B, Cin, T = x.shape
         dev = self.dev
         e = "encoder."
-        x_cl = torch.zeros(B, T, Cin, device=dev, dtype=BF)
+        x_cl = torch.zeros(B, T, Cin, device=dev, dtype=H16)
         ops.nct_to_ntc(x.to(dev, F32).contiguous(), x_cl)
         C0 = self.w[e + "conv_in.w"].shape[0]
         h = torch.empty(B, T, C0, device=dev, dtype=F32)
@@ -181,8 +181,8 @@ class VAEEngine:
             if lvl in self.down_layers:  # pad (0,1) + conv k3 stride 2 (autoencoder1d.py:306-313)
                 C = h.shape[-1]
                 assert T % 2 == 0, "stride-2 downsample expects an even length"
-                hb = torch.empty(B, T, C, device=dev, dtype=BF)
-                ops.ew(h, out_bf16=hb)
+                hb = torch.empty(B, T, C, device=dev, dtype=H16)
+                ops.ew(h, out_fp16=hb)
                 name = f"{e}down.{lvl}.downsample.conv"
                 T = T // 2
                 h = torch.empty(B, T, C, device=dev, dtype=F32)
@@ -195,8 +195,8 @@ class VAEEngine:
         a = self._gn(h, e + "norm_out", B, T, C, ops.ACT_SILU)
         Cz = self.w[e + "conv_out.w"].shape[0]
         czp = (Cz + 7) // 8 * 8
-        hz = torch.zeros(B, T, czp, device=dev, dtype=BF)
-        self._conv(a, e + "conv_out", B, T, out_bf16=hz)
+        hz = torch.zeros(B, T, czp, device=dev, dtype=H16)
+        self._conv(a, e + "conv_out", B, T, out_fp16=hz)
         Cm = self.w["quant_conv.w"].shape[0]
         mom_cl = torch.empty(B, T, Cm, device=dev, dtype=F32)
         self._conv(hz, "quant_conv", B, T, out_f32=mom_cl, Cin=Cz)

@@ -1,5 +1,5 @@
 """HiFi-GAN generator on B200: every Conv1d / ConvTranspose1d is an implicit-GEMM vb_gemm launch
-over channels-last bf16 activations; LeakyReLU, bias, residual add, MRF sum and the 1/3 mean are
+over channels-last fp16 activations; LeakyReLU, bias, residual add, MRF sum and the 1/3 mean are
 fused into the producing GEMM's epilogue.
 
 Mirrors reference vocoder/hifigan/modules/hifigan.py (HifiGanGenerator.forward :126-143,
@@ -14,7 +14,7 @@ from typing import Dict, List
 import torch
 
 from . import ops
-from .dit import BF, F32, pack_conv_weight
+from .dit import H16, F32, pack_conv_weight
 
 LRELU = 0.1
 
@@ -50,12 +50,12 @@ class HifiGanEngine:
             cin, cout, _ = wt.shape
             Q = (k + u - 1) // u
             kp = (cin + 63) // 64 * 64
-            wp = torch.zeros(u, cout, Q, kp, device=self.dev, dtype=BF)
+            wp = torch.zeros(u, cout, Q, kp, device=self.dev, dtype=H16)
             for r in range(u):
                 for q in range(Q):
                     j = r + u * q
                     if j < k:  # tap q of phase r reads x[s - q]; stored reversed so time = s-(Q-1)+tap
-                        wp[r, :, Q - 1 - q, :cin] = wt[:, :, j].t().to(BF)
+                        wp[r, :, Q - 1 - q, :cin] = wt[:, :, j].t().to(H16)
             w[f"up{i}.w"] = wp.reshape(u, cout, Q * kp).contiguous()
             w[f"up{i}.b"] = sd[f"ups.{i}.bias"].float().contiguous()
         nk = len(self.rb_k)
@@ -86,11 +86,11 @@ class HifiGanEngine:
         dev = self.dev
         B, nm, T = mel.shape
         assert nm == self.n_mel and nm % 8 == 0
-        mel_cl = torch.empty(B, T, nm, device=dev, dtype=BF)
+        mel_cl = torch.empty(B, T, nm, device=dev, dtype=H16)
         ops.nct_to_ntc(mel.to(dev, F32).contiguous(), mel_cl)
         C = self.C0
-        xb = torch.empty(B, T, C, device=dev, dtype=BF)  # lrelu(conv_pre(mel)), hifigan.py:128-130
-        self._conv(mel_cl, "pre", B, T, 7, 1, out_bf16=xb, act_out=ops.ACT_LRELU, act_out_slope=LRELU)
+        xb = torch.empty(B, T, C, device=dev, dtype=H16)  # lrelu(conv_pre(mel)), hifigan.py:128-130
+        self._conv(mel_cl, "pre", B, T, 7, 1, out_fp16=xb, act_out=ops.ACT_LRELU, act_out_slope=LRELU)
         nk = len(self.rb_k)
         n_stages = len(self.rates)
         for i, (u, k) in enumerate(zip(self.rates, self.up_k)):
@@ -102,30 +102,30 @@ class HifiGanEngine:
             p = (k - u) // 2
             Tout = (T - 1) * u - 2 * p + k
             x = torch.empty(B, Tout, Cout, device=dev, dtype=F32)
-            xl = torch.empty(B, Tout, Cout, device=dev, dtype=BF)
+            xl = torch.empty(B, Tout, Cout, device=dev, dtype=H16)
             ops.gemm(xb, wup, M=T + Q - 1, N=Cout, K=Q * kp, G1=u, G2=B, kpt=kp // 64, dil=1, pad=Q - 1,
                      a_c2=(0, 1), b_c2=(1, 0, 0), bias=self.w[f"up{i}.b"],
                      row_mul=u, row_off=-p, row_off_g1=1, rows_out=Tout,
                      out_f32=x, out_ld=Cout, out_g=(0, Tout * Cout),
-                     out_bf16=xl, outb_ld=Cout, outb_g=(0, Tout * Cout), act_out=ops.ACT_LRELU,
+                     out_fp16=xl, outb_ld=Cout, outb_g=(0, Tout * Cout), act_out=ops.ACT_LRELU,
                      act_out_slope=LRELU)
             T, C = Tout, Cout
             # ---- MRF: mean of nk ResBlock1 chains that all start from x (hifigan.py:132-138)
             last_stage = i == n_stages - 1
             xs = torch.empty(B, T, C, device=dev, dtype=F32)
-            nxt = torch.empty(B, T, C, device=dev, dtype=BF)
-            t1 = torch.empty(B, T, C, device=dev, dtype=BF)
+            nxt = torch.empty(B, T, C, device=dev, dtype=H16)
+            t1 = torch.empty(B, T, C, device=dev, dtype=H16)
             rbuf = [torch.empty(B, T, C, device=dev, dtype=F32) for _ in range(2)]
-            rlb = [torch.empty(B, T, C, device=dev, dtype=BF) for _ in range(2)]
+            rlb = [torch.empty(B, T, C, device=dev, dtype=H16) for _ in range(2)]
             for j in range(nk):
                 kk, dils = self.rb_k[j], self.rb_d[j]
                 r, rl = x, xl
                 for c, d in enumerate(dils):
-                    self._conv(rl, f"rb{i}.{j}.convs1.{c}", B, T, kk, d, out_bf16=t1,
+                    self._conv(rl, f"rb{i}.{j}.convs1.{c}", B, T, kk, d, out_fp16=t1,
                                act_out=ops.ACT_LRELU, act_out_slope=LRELU)
                     if c < len(dils) - 1:
                         self._conv(t1, f"rb{i}.{j}.convs2.{c}", B, T, kk, 1, residual=r,
-                                   out_f32=rbuf[c % 2], out_bf16=rlb[c % 2], act_out=ops.ACT_LRELU,
+                                   out_f32=rbuf[c % 2], out_fp16=rlb[c % 2], act_out=ops.ACT_LRELU,
                                    act_out_slope=LRELU)
                         r, rl = rbuf[c % 2], rlb[c % 2]
                     else:
@@ -134,7 +134,7 @@ class HifiGanEngine:
                         final = j == nk - 1
                         self._conv(t1, f"rb{i}.{j}.convs2.{c}", B, T, kk, 1, residual=r,
                                    out_f32=xs, accumulate=(j > 0),
-                                   out_bf16=nxt if final else None, act_out=ops.ACT_LRELU,
+                                   out_fp16=nxt if final else None, act_out=ops.ACT_LRELU,
                                    act_out_slope=(0.01 if last_stage else LRELU), out_scale=1.0 / nk)
             xb = nxt
         wav = torch.empty(B, T, device=dev, dtype=F32)
