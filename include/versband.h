@@ -141,6 +141,22 @@ typedef struct vb_gemm_args {
 int vb_gemm(const vb_gemm_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * vb_gemm_chain — up to 4 DEPENDENT vb_gemm problems in ONE persistent launch (1-CTA kernel, one N tile
+ * width `bn` in {64, 128} for all of them, epilogues limited to the LINEAR / SWIGLU fusions). The flat tile
+ * list runs problem 0, 1, ... in order; dep_mode[o] says what a tile of problem o waits for:
+ *   0  nothing (mandatory for problem 0)
+ *   1  the same (group, 128-row block) of problem o-1 has stored all its N tiles (A rows of o = output
+ *      rows of o-1: expert w1|w3 -> w2, frequency-expert first -> second layer)
+ *   2  all tiles of problem o-1 (producers that scatter rows: routed experts' w2 -> frequency experts)
+ * The smem ring and the TMEM accumulators run through problem boundaries, so one problem's epilogue tail
+ * overlaps the next one's mainloop. `counters` = device int32 scratch the CALLER has zeroed before the launch
+ * (counters[0] is set to 1 if a dependency wait ever timed out); needs 2 + sum(groups*m_tiles + 1) ints.
+ * Replaces the per-layer launches of FeedForward / the MoE expert loops (vocal2music_moe.py:154-178).
+ * ------------------------------------------------------------------------------------------ */
+int vb_gemm_chain(const vb_gemm_args* ops, const int32_t* dep_mode, int n_ops, int bn, int32_t* counters,
+                  int64_t counters_len, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * vb_attn_fused — flash-style attention on tcgen05 (S and O_j in TMEM, P through shared memory).
  * Replaces Attention.forward's two SDPA calls and the gated add (flag_large_dit_moe.py:381-402)
  * in one launch, and nn.MultiheadAttention's attention core (vocal2music_moe.py:119):

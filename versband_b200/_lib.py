@@ -73,6 +73,7 @@ def lib() -> C.CDLL:
         _lib.vb_last_error.restype = C.c_char_p
         _lib.vb_launch_count.restype = C.c_longlong
         _lib.vb_gemm.argtypes = [C.POINTER(GemmArgs), c_ptr]
+        _lib.vb_gemm_chain.argtypes = [C.POINTER(GemmArgs), C.POINTER(c_i32), c_i32, c_i32, c_ptr, c_i64, c_ptr]
         _declare(_lib)
         _lib.vb_attn_fused.argtypes = [C.POINTER(AttnArgs), c_ptr]
         if _lib.vb_sizeof(1) != C.sizeof(AttnArgs):

@@ -87,10 +87,10 @@ extern "C" int vb_set_gemm2(int mode) {
   return VB_OK;
 }
 
-extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
-  vb::ProfScope prof_scope(vb::PK_GEMM, stream_);
-  using namespace vb;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+namespace vb {
+// Validation, tile selection (or `force_bn`, 1-CTA only), TMA descriptors and kernel parameter block of one
+// GEMM problem. Shared by vb_gemm (one problem per launch) and vb_gemm_chain (several per launch).
+int plan_gemm(const vb_gemm_args* a, int force_bn, GemmPlan* out) {
   if (!a || !a->a || !a->b) return set_error(VB_ERR_INVALID, "vb_gemm: null operand");
   const bool tf32 = a->operand_f32 != 0;
   const int bk = tf32 ? 32 : 64;  // elements per 128-byte k-block
@@ -105,7 +105,7 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
     return set_error(VB_ERR_INVALID, "vb_gemm: reduction dim must be contiguous");
 
   // N tile
-  int bn = a->bn;
+  int bn = force_bn > 0 ? force_bn : a->bn;
   const int m_tiles = (a->M + BM - 1) / BM;
   const int G = a->G1 * a->G2;
   // ---- tile selection -------------------------------------------------------------------
@@ -132,7 +132,7 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
       if (cost < best) { best = cost; best_bn = c; }
     }
     // 2-CTA pairs (cta_group::2): each CTA loads only half of the B tile. Non-grouped problems only.
-    if (g_gemm2_mode > 0 && !user_bn && !a->tile_group && m_tiles >= 2 && a->N >= 128) {
+    if (g_gemm2_mode > 0 && !user_bn && !force_bn && !a->tile_group && m_tiles >= 2 && a->N >= 128) {
       const int c2s[3] = {128, 192, 256};
       for (int i = 0; i < 3; ++i) {
         const int c = c2s[i];
@@ -149,7 +149,7 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
     }
     bn = best_bn;
     for (int i = 0; i < g_n_overrides; ++i)
-      if (g_overrides[i].N == a->N && g_overrides[i].K == a->K && g_overrides[i].grouped == (a->tile_group ? 1 : 0) && !user_bn) {
+      if (g_overrides[i].N == a->N && g_overrides[i].K == a->K && g_overrides[i].grouped == (a->tile_group ? 1 : 0) && !user_bn && !force_bn) {
         bn = g_overrides[i].bn;
         use2 = g_overrides[i].cta2 != 0 && !a->tile_group && m_tiles >= 2 && bn >= 128;
       }
@@ -177,7 +177,8 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
   if (a->swiglu && (a->N % 2 != 0))
     return set_error(VB_ERR_INVALID, "vb_gemm: swiglu needs an even N");
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap& tmA = out->tmA;
+  CUtensorMap& tmB = out->tmB;
   {
     uint32_t box[4] = {static_cast<uint32_t>(bk), BM, 1, 1};
     int rc = encode_map(&tmA, a->a, 4, a->a_dims, a->a_strides, box, tf32);
@@ -187,7 +188,8 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
     if (rc) return rc;
   }
 
-  GemmKParams p{};
+  GemmKParams& p = out->p;
+  p = GemmKParams{};
   p.M = a->M; p.N = a->N; p.K = a->K; p.G1 = a->G1;
   p.dbg_shift = g_dbg_shift;
   if (g_gemm_trace && g_gemm_trace_left > 0) {  // one 256-CTA x 8-slot record per traced call
@@ -254,6 +256,25 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
   p.m_tiles = m_tiles;
   p.n_tiles = (a->N + bn - 1) / bn;
   p.num_tiles = p.m_tiles * p.n_tiles * G;
+  out->bn = bn; out->tf32 = tf32; out->use2 = use2; out->ec = ec; out->kpt = kpt; out->num_kb = num_kb; out->G = G;
+  return VB_OK;
+}
+}  // namespace vb
+
+extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
+  vb::ProfScope prof_scope(vb::PK_GEMM, stream_);
+  using namespace vb;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GemmPlan pl;
+  {
+    const int rc = plan_gemm(a, 0, &pl);
+    if (rc) return rc;
+  }
+  const CUtensorMap& tmA = pl.tmA;
+  const CUtensorMap& tmB = pl.tmB;
+  const GemmKParams& p = pl.p;
+  const int bn = pl.bn, ec = pl.ec, kpt = pl.kpt, num_kb = pl.num_kb, G = pl.G, m_tiles = p.m_tiles;
+  const bool tf32 = pl.tf32, use2 = pl.use2;
   const int num_sms = device_sm_count();
   // haloed small-C conv path (see vb_conv_halo_kernel)
   if (g_conv_halo > 0 && !tf32 && !use2 && !a->tile_group && a->mode == VB_EPI_GENERIC && kpt == 1 && num_kb >= 2 &&
@@ -304,4 +325,55 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
     case EC_LINEAR: return launch_gemm_class<EC_LINEAR>(bn, tf32, use2, tmA, tmB, p, grid, stream);
     default: return launch_gemm_class<EC_FULL>(bn, tf32, use2, tmA, tmB, p, grid, stream);
   }
+}
+
+// ------------------------------------------------------------------ vb_gemm_chain
+extern "C" int vb_gemm_chain(const vb_gemm_args* ops, const int32_t* dep_mode, int n_ops, int bn, int32_t* counters,
+                             int64_t counters_len, void* stream_) {
+  vb::ProfScope prof_scope(vb::PK_GEMM, stream_);
+  using namespace vb;
+  if (!ops || !dep_mode || n_ops < 1 || n_ops > kChainMaxOps || !counters)
+    return set_error(VB_ERR_INVALID, "vb_gemm_chain: 1..%d problems, dependency modes and a counter buffer required", kChainMaxOps);
+  if (bn != 64 && bn != 128) return set_error(VB_ERR_INVALID, "vb_gemm_chain: bn must be 64 or 128");
+  if (dep_mode[0] != 0) return set_error(VB_ERR_INVALID, "vb_gemm_chain: the first problem cannot have a dependency");
+  ChainParams cp{};
+  cp.n_ops = n_ops;
+  int64_t used = 2;  // [0] = error flag, [1] spare
+  int tiles = 0;
+  bool tf32 = false;
+  for (int o = 0; o < n_ops; ++o) {
+    GemmPlan pl;
+    const int rc = plan_gemm(&ops[o], bn, &pl);
+    if (rc) return rc;
+    if (pl.ec != EC_LINEAR && pl.ec != EC_SWIGLU)
+      return set_error(VB_ERR_INVALID, "vb_gemm_chain: problem %d needs an epilogue outside LINEAR/SWIGLU", o);
+    if (o == 0) tf32 = pl.tf32;
+    else if (tf32 != pl.tf32) return set_error(VB_ERR_INVALID, "vb_gemm_chain: mixed operand types");
+    if (dep_mode[o] < 0 || dep_mode[o] > 2) return set_error(VB_ERR_INVALID, "vb_gemm_chain: bad dependency mode");
+    ChainOp& op = cp.op[o];
+    op.tmA = pl.tmA; op.tmB = pl.tmB; op.p = pl.p;
+    op.tile_start = tiles;
+    op.dep_mode = dep_mode[o];
+    op.sig_mode = o + 1 < n_ops ? dep_mode[o + 1] : 0;
+    if (o > 0 && dep_mode[o] == 1) {
+      const GemmKParams& a = cp.op[o - 1].p;
+      if (a.m_tiles != pl.p.m_tiles || a.num_tiles / (a.m_tiles * a.n_tiles) != pl.p.num_tiles / (pl.p.m_tiles * pl.p.n_tiles))
+        return set_error(VB_ERR_INVALID, "vb_gemm_chain: row dependency needs the same M tiling and group count in problems %d and %d", o - 1, o);
+      if ((a.m_tiles_used != nullptr) != (pl.p.m_tiles_used != nullptr))
+        return set_error(VB_ERR_INVALID, "vb_gemm_chain: row dependency between a grouped and a dense problem");
+    }
+    const int groups = pl.p.num_tiles / (pl.p.m_tiles * pl.p.n_tiles);
+    op.cnt_rows = counters + used;
+    used += (int64_t)groups * pl.p.m_tiles;
+    op.cnt_all = counters + used;
+    used += 1;
+    tiles += pl.p.num_tiles;
+  }
+  if (used > counters_len)
+    return set_error(VB_ERR_INVALID, "vb_gemm_chain: counter buffer too small (%lld ints needed)", (long long)used);
+  cp.total_tiles = tiles;
+  cp.err_flag = counters;
+  const int num_sms = device_sm_count();
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  return launch_chain(bn, tf32, cp, grid, static_cast<cudaStream_t>(stream_));
 }

@@ -350,7 +350,7 @@ __device__ __forceinline__ void epi_load_operands(const GemmKParams& p, const Ep
     }
     return;
   }
-  if (EC == EC_SWIGLU || (EC == EC_FULL && p.swiglu)) return;
+  if (EC == EC_SWIGLU || ((EC == EC_FULL || EC == EC_CHAIN) && p.swiglu)) return;
   if (p.bias) op.bias = __ldg(reinterpret_cast<const float4*>(p.bias + g1 * p.bias_g1 + tg * p.bias_tile + n));
   if (p.gate) {
     const float* gsrc = p.gate + g1 * p.gate_g1 + n + (long long)rows.b_lo * p.gate_ld;
@@ -376,7 +376,7 @@ __device__ __forceinline__ void epilogue_generic(const GemmKParams& p, float (&v
     for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
   }
 
-  if (EC == EC_SWIGLU || (EC == EC_FULL && p.swiglu)) {
+  if (EC == EC_SWIGLU || ((EC == EC_FULL || EC == EC_CHAIN) && p.swiglu)) {
     // columns (2i, 2i+1) = (w1 x, w3 x)  ->  silu(w1 x) * (w3 x): two outputs per quad
     const int no = n >> 1;
     float o[16];
@@ -1057,6 +1057,222 @@ vb_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_after();
     tmem_dealloc<2 * kAcc>(tmem_base);
   }
+}
+
+
+// ------------------------------------------------------------------ chained problems in one launch
+// vb_chain_kernel: the persistent 1-CTA GEMM above walking a flat tile list that spans up to kChainMaxOps
+// dependent problems (vb_gemm_params.h: ChainOp). One launch, one prologue, one TMEM allocation; the smem
+// ring and the two TMEM accumulators run straight through problem boundaries, so the epilogue tail of
+// problem o overlaps the mainloop of problem o+1 and no SM idles between them except where the data
+// dependency itself forces it. All CTAs are co-resident (grid <= SM count, 1 CTA/SM) and every CTA walks its
+// tiles in increasing flat order while dependencies only point to smaller indices, so waiting cannot deadlock.
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+struct ChainTile {
+  int o, m_tile, n_tile, g1, g2, g, tg;
+  bool skip;
+};
+__device__ __forceinline__ ChainTile chain_decode(const ChainParams& cp, int t, const int* m_used) {
+  ChainTile c;
+  int o = 0;
+#pragma unroll
+  for (int i = 1; i < kChainMaxOps; ++i)
+    if (i < cp.n_ops && t >= cp.op[i].tile_start) o = i;
+  const GemmKParams& p = cp.op[o].p;
+  const int local = t - cp.op[o].tile_start;
+  const int per_g = p.m_tiles * p.n_tiles;
+  c.o = o;
+  c.g = local / per_g;
+  const int r = local - c.g * per_g;
+  c.m_tile = r / p.n_tiles;            // n fastest: a row block's N tiles are adjacent in the list
+  c.n_tile = r - c.m_tile * p.n_tiles;
+  c.g1 = c.g % p.G1;
+  c.g2 = c.g / p.G1;
+  c.skip = c.m_tile >= m_used[o];
+  c.tg = (p.tile_group && !c.skip) ? p.tile_group[c.m_tile] : 0;
+  return c;
+}
+
+template <int BN, bool TF32>
+__global__ void __launch_bounds__(kThreads, 1)
+vb_chain_kernel(const __grid_constant__ ChainParams cp) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int EC = EC_CHAIN;
+  static_assert(BN >= 64, "chain tiles use all eight epilogue warps");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + kStages * Cfg::kBBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* epi_stage = reinterpret_cast<float*>(smem + kStages * (Cfg::kABytes + Cfg::kBBytes) + 1024);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp_idx == 0 && lane == 0) {
+    for (int o = 0; o < cp.n_ops; ++o) {
+      tma_prefetch_desc(&cp.op[o].tmA);
+      tma_prefetch_desc(&cp.op[o].tmB);
+    }
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], kEpiWarps * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
+
+  int m_used[kChainMaxOps];
+#pragma unroll
+  for (int o = 0; o < kChainMaxOps; ++o)
+    m_used[o] = o < cp.n_ops ? (cp.op[o].p.m_tiles_used ? *cp.op[o].p.m_tiles_used : cp.op[o].p.m_tiles) : 0;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < cp.total_tiles; t += gridDim.x) {
+        const ChainTile tc = chain_decode(cp, t, m_used);
+        if (tc.skip) continue;
+        const ChainOp& op = cp.op[tc.o];
+        const GemmKParams& p = op.p;
+        if (op.dep_mode != 0) {
+          // wait for the producer problem's rows, then order the generic-proxy stores we just observed
+          // before this thread's async-proxy (TMA) reads
+          const ChainOp& prev = cp.op[tc.o - 1];
+          const int* cnt = op.dep_mode == 1 ? prev.cnt_rows + (tc.g * p.m_tiles + tc.m_tile) : prev.cnt_all;
+          const int expect = op.dep_mode == 1 ? prev.p.n_tiles : m_used[tc.o - 1] * prev.p.n_tiles * (prev.p.num_tiles / (prev.p.m_tiles * prev.p.n_tiles));
+          const long long t0 = clock64();
+          while (ld_acquire_gpu(cnt) < expect) {
+            if (clock64() - t0 > 4000000000ll) { *cp.err_flag = 1; break; }  // ~2 s: a bug, not a wait
+          }
+          fence_proxy_async_all();
+        }
+        const int m0 = tc.m_tile * BM, n0 = tc.n_tile * BN;
+        const int a_c2 = tc.g1 * p.a_c2_g1 + tc.g2 * p.a_c2_g2;
+        const int a_c3 = tc.g1 * p.a_c3_g1 + tc.g2 * p.a_c3_g2;
+        const int b_c2 = tc.g1 * p.b_c2_g1 + tc.g2 * p.b_c2_g2 + tc.tg * p.b_c2_tile;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
+          const int tap = kb / p.kpt;
+          constexpr int kBkElems = TF32 ? 32 : 64;
+          const int c0 = (kb - tap * p.kpt) * kBkElems;
+          const int c1 = m0 + tap * p.dil - p.pad;
+          tma_load_4d(smem_a + stage * Cfg::kABytes, &op.tmA, &full_bar[stage], c0, c1, a_c2, a_c3);
+          tma_load_3d(smem_b + stage * Cfg::kBBytes, &op.tmB, &full_bar[stage], kb * kBkElems, n0, b_c2);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = TF32 ? make_idesc_tf32(BM, BN) : make_idesc_fp16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int t = blockIdx.x; t < cp.total_tiles; t += gridDim.x) {
+        const ChainTile tc = chain_decode(cp, t, m_used);
+        if (tc.skip) continue;
+        const int num_kb = cp.op[tc.o].p.num_kb;
+        const int acc = local & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((local >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * Cfg::kAccStride;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (TF32) umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else umma_fp16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[acc]);
+        ++local;
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp_idx & 3;
+    const int wset = (warp_idx - 2) >> 2;
+    const int c_first = wset * 32;
+    const uint32_t stg = smem_u32(epi_stage) + (warp_idx - 2) * 4096;
+    int local = 0;
+    for (int t = blockIdx.x; t < cp.total_tiles; t += gridDim.x) {
+      const ChainTile tc = chain_decode(cp, t, m_used);
+      if (tc.skip) continue;
+      const ChainOp& op = cp.op[tc.o];
+      const GemmKParams& p = op.p;
+      const int acc = local & 1;
+      const int m_base = tc.m_tile * BM + q * 32, n0 = tc.n_tile * BN;
+      const uint32_t tmem_d = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+      VB_EPILOGUE_TILE(BN, n0, tc.g1, tc.g2, tc.tg, mbar_wait(&tmem_full_bar[acc], (local >> 1) & 1))
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+      if (op.sig_mode != 0) {
+        // publish: every epilogue thread's stores of this tile are fenced, then ONE arrival per tile
+        fence_proxy_async_all();
+        __threadfence();
+        named_bar_sync(1, kEpiWarps * 32);
+        if (threadIdx.x == 64) {
+          if (op.sig_mode == 1) atomicAdd(op.cnt_rows + (tc.g * p.m_tiles + tc.m_tile), 1);
+          else atomicAdd(op.cnt_all, 1);
+        }
+      }
+      ++local;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN, bool TF32>
+static int launch_chain_t(const ChainParams& cp, int grid, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static PerDevice<bool> attr_flag;
+  bool& attr_set = attr_flag.get();
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(vb_chain_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "cudaFuncSetAttribute(chain smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  cudaError_t e = launch_k(vb_chain_kernel<BN, TF32>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, cp);
+  if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "vb_gemm_chain launch failed: %s", cudaGetErrorString(e));
+  return check_launch("vb_gemm_chain");
 }
 
 template <int BN, bool TF32, int EC>

@@ -25,6 +25,7 @@ enum EpiClass {
   EC_SWIGLU = 2,  // silu(w1 x) * (w3 x) pairs -> operand-slot output (expert FFN first layers)
   EC_QKV = 3,     // bias + rotary + head-major q/k and transposed v stores
   EC_ROUTE = 4,   // per-head softmax over 96 score columns contracted with V.(gate) -> gate-logit partials
+  EC_CHAIN = 5,   // LINEAR + SWIGLU selected per problem at run time (vb_gemm_chain)
 };
 
 struct GemmKParams {
@@ -74,6 +75,40 @@ struct GemmKParams {
   unsigned long long* trace;  // debug (vb_set_gemm_trace): 8 x u64 per CTA, see tools/trace_gemm.py
 };
 
+
+// host-side plan of one GEMM problem (vb_gemm.cu: plan_gemm)
+struct GemmPlan {
+  CUtensorMap tmA, tmB;
+  GemmKParams p;
+  int bn, ec, kpt, num_kb, G;
+  bool tf32, use2;
+};
+int plan_gemm(const vb_gemm_args* a, int force_bn, GemmPlan* out);
+
+// ---- vb_gemm_chain: several dependent GEMM problems in ONE persistent launch -------------------------------
+// Flat tile list = problem 0's tiles, then problem 1's, ... (n fastest inside a problem, so an M row block
+// completes early). A tile of problem o may only start loading A once its producer rows exist:
+//   dep_mode 0: no dependency (first problem)
+//   dep_mode 1: the same (group, m_tile) of problem o-1 has stored all of its N tiles
+//   dep_mode 2: every active tile of problem o-1 has been stored (row-scattering producers)
+// Completion is published through global counters (one arrival per tile, after a __threadfence) that the TMA
+// producer of a consuming tile polls with ld.acquire; counters are zeroed by the caller before the launch.
+constexpr int kChainMaxOps = 4;
+struct alignas(64) ChainOp {
+  CUtensorMap tmA, tmB;
+  GemmKParams p;
+  int tile_start;       // first flat tile index of this problem
+  int dep_mode;         // how this problem waits on problem o-1
+  int sig_mode;         // what this problem publishes: = dep_mode of problem o+1 (0 for the last)
+  int* cnt_rows;        // [G * m_tiles] arrivals per (group, m_tile) of THIS problem
+  int* cnt_all;         // [1] arrivals over all tiles of THIS problem
+};
+struct ChainParams {
+  ChainOp op[kChainMaxOps];
+  int n_ops, total_tiles;
+  int* err_flag;        // set to 1 if a dependency wait timed out (never in a correct run)
+};
+int launch_chain(int bn, bool tf32, const ChainParams& cp, int grid, cudaStream_t stream);
 
 struct HaloParams {
   int taps, row_shift, rows, rows8, n_ksteps, stages, base_off;

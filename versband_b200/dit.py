@@ -113,6 +113,8 @@ class DiTEngine:
         self.dev = torch.device(device)
         assert self.hd % 32 == 0 and hidden_size % (64 * 1) == 0
         self._ws: Dict[Tuple[int, int], dict] = {}
+        self.use_chain = True   # MoE expert GEMMs as one persistent chained launch (vb_gemm_chain)
+        self.chain_bn = 128
         self.pack(sd)
 
     # ------------------------------------------------------------------ packing
@@ -240,6 +242,9 @@ class DiTEngine:
             xs=z(max_rows, D, dt=AD), hs=z(max_rows, Fh, dt=AD), y2=z(2 * N, D, dt=AD),
             hf=z(E, N, Fh, dt=AD), xf=z(N, D, dt=AD), v=z(N, 32),
         )
+        # dependency counters of the chained MoE launch, one zeroed row per block (see vb_gemm_chain)
+        ws["chain_len"] = 8 + 2 * (max_rows // 128 + 1) + 2 * (E * ((N + 127) // 128) + 1)
+        ws["chain_cnt"] = torch.zeros(self.depth, ws["chain_len"], device=dev, dtype=torch.int32)
         self._ws[key] = ws
         return ws
 
@@ -366,7 +371,8 @@ class DiTEngine:
     @torch.no_grad()
     def forward(self, x: torch.Tensor, t: torch.Tensor, cond: DiTCond,
                 expo: List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]],
-                out_v: Optional[torch.Tensor] = None, want_aux: bool = False, pre=None, x_cl_ready: bool = False):
+                out_v: Optional[torch.Tensor] = None, want_aux: bool = False, pre=None, x_cl_ready: bool = False,
+                chain_cnt: Optional[torch.Tensor] = None):
         """x fp32 [B, C, T], t int64 [B]; expo[k] = Exp(1) draws ([N,2],[N,E],[N,E]) of block k.
         Returns v as the channels-last GEMM output [N, 32] (first C columns valid) unless `out_v`
         ([B, C, T]) is given, plus lb_loss per block (device tensor)."""
@@ -379,6 +385,12 @@ class DiTEngine:
         Tp, max_rows = ws["Tp"], ws["max_rows"]
         scale = 1.0 / math.sqrt(hd)
         aux = []
+        # dependency counters of the chained launches: the caller's pre-zeroed [depth, chain_len] slice (the
+        # sampler zeroes all steps with one memset) or this engine's own, zeroed here
+        cnt = chain_cnt
+        if cnt is None and self.use_chain:
+            cnt = ws["chain_cnt"]
+            cnt.zero_()
 
         # stem: proj_in conv (k5) + bias, fused "+ acoustic"  (vocal2music_moe.py:395,415)
         # (x_cl_ready: the sampler's Euler-update launch already refreshed the channels-last copies)
@@ -447,24 +459,33 @@ class DiTEngine:
                 ops.moe_scatter(ws["idx_c"], ws["idx_a"], ws["slot_c"], ws["slot_a"], ws["scale_c"], ws["scale_a"],
                                 ws["bucket_start"], N, E, ws["xm"], ws["xs"], ws["row_map"], ws["row_scale"])
             ops.mark("moe_dispatch")
-            ops.gemm(ws["xs"], b["w13"], M=max_rows, b_c2=(0, 0, 1), tile_group=ws["tile_group"],
-                     m_tiles_used=ws["m_tiles"], swiglu=True, out_fp16=ws["hs"], outb_ld=Fh)
-            ops.mark("gemm:w13")
-            ops.gemm(ws["hs"], b["w2"], M=max_rows, b_c2=(0, 0, 1), tile_group=ws["tile_group"],
-                     m_tiles_used=ws["m_tiles"], row_map=ws["row_map"], rows_out=2 * N,
-                     row_scale=ws["row_scale"], out_fp16=ws["y2"], outb_ld=D)
-            ops.mark("gemm:w2")
+            # routed experts (w1|w3 -> SwiGLU -> w2, scattered back to token rows) and frequency experts
+            # (band-sliced w1|w3 -> SwiGLU -> w2 + adaLN gate + residual): four dependent GEMM problems in ONE
+            # persistent launch (vb_gemm_chain) — or four launches with use_chain = False.
             # y = y_caption + y_acoustic (vocal2music_moe.py:166) is never materialised: the frequency experts'
             # first GEMM reads both halves of y2 through the conv addressing (2 "taps" N rows apart, the band's
             # weights repeated along K), so the sum happens in the fp32 accumulator.
             yb = ws["y2"].view(2 * N, E, self.band).permute(1, 0, 2)  # [E, 2N, band] view: per-band K slice
-            ops.gemm(yb, b["f13"], M=N, G1=E, kpt=self.band // self.kq, dil=N, pad=0, a_c2=(1, 0), b_c2=(1, 0, 0),
-                     swiglu=True, out_fp16=ws["hf"], outb_ld=Fh, outb_g=(N * Fh, 0))
-            ops.mark("gemm:f13")
-            ops.gemm(ws["hf"], b["f2"], M=N, G1=E, a_c2=(1, 0), b_c2=(1, 0, 0),
-                     gate=g_mlp, gate_rows=T, gate_ld=mld, gate_g1=self.band, residual=hbuf,
-                     out_f32=xcur, out_ld=D, out_g=(self.band, 0))
-            ops.mark("gemm:f2")
+            probs = [
+                (ws["xs"], b["w13"], dict(M=max_rows, b_c2=(0, 0, 1), tile_group=ws["tile_group"],
+                                          m_tiles_used=ws["m_tiles"], swiglu=True, out_fp16=ws["hs"], outb_ld=Fh)),
+                (ws["hs"], b["w2"], dict(M=max_rows, b_c2=(0, 0, 1), tile_group=ws["tile_group"],
+                                         m_tiles_used=ws["m_tiles"], row_map=ws["row_map"], rows_out=2 * N,
+                                         row_scale=ws["row_scale"], out_fp16=ws["y2"], outb_ld=D)),
+                (yb, b["f13"], dict(M=N, G1=E, kpt=self.band // self.kq, dil=N, pad=0, a_c2=(1, 0), b_c2=(1, 0, 0),
+                                    swiglu=True, out_fp16=ws["hf"], outb_ld=Fh, outb_g=(N * Fh, 0))),
+                (ws["hf"], b["f2"], dict(M=N, G1=E, a_c2=(1, 0), b_c2=(1, 0, 0),
+                                         gate=g_mlp, gate_rows=T, gate_ld=mld, gate_g1=self.band, residual=hbuf,
+                                         out_f32=xcur, out_ld=D, out_g=(self.band, 0))),
+            ]
+            if self.use_chain:
+                ops.gemm_chain([ops.gemm_args(a_, b_, **kw) for a_, b_, kw in probs], [0, 1, 2, 1], cnt[k],
+                               bn=self.chain_bn)
+                ops.mark("gemm:moe_chain")
+            else:
+                for (a_, b_, kw), name in zip(probs, ("w13", "w2", "f13", "f2")):
+                    ops.gemm(a_, b_, **kw)
+                    ops.mark("gemm:" + name)
             if want_aux:
                 aux.append(dict(idx_c=ws["idx_c"].clone(), idx_a=ws["idx_a"].clone(),
                                 cap_logits=ws["cap_logits"].clone(), h=hbuf.clone(), x=xcur.clone()))

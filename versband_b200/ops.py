@@ -48,7 +48,23 @@ def _check_f32(t: Optional[torch.Tensor], name: str):
         assert t.dtype == torch.float32 and t.is_cuda, name
 
 
-def gemm(a: torch.Tensor, b: torch.Tensor, *, M: Optional[int] = None, N: Optional[int] = None,
+def gemm(a: torch.Tensor, b: torch.Tensor, **kw) -> None:
+    """D = epilogue(A @ B^T) on the tcgen05 GEMM: one launch (see `gemm_args` for the arguments)."""
+    args = gemm_args(a, b, **kw)
+    _lib.check(_lib.lib().vb_gemm(C.byref(args), _stream()), "vb_gemm")
+
+
+def gemm_chain(problems, dep_mode, counters: torch.Tensor, *, bn: int = 128) -> None:
+    """Several dependent GEMM problems (`gemm_args` objects) in ONE persistent launch (include/versband.h:
+    vb_gemm_chain). `counters`: zeroed int32 device scratch."""
+    n = len(problems)
+    arr = (GemmArgs * n)(*problems)
+    deps = (C.c_int32 * n)(*dep_mode)
+    assert counters.dtype == torch.int32 and counters.is_cuda
+    _lib.check(_lib.lib().vb_gemm_chain(arr, deps, n, bn, _ptr(counters), counters.numel(), _stream()), "vb_gemm_chain")
+
+
+def gemm_args(a: torch.Tensor, b: torch.Tensor, *, M: Optional[int] = None, N: Optional[int] = None,
          K: Optional[int] = None, G1: int = 1, G2: int = 1, kpt: int = 0, dil: int = 0, pad: int = 0,
          a_c2=(0, 0), a_c3=(0, 0), b_c2=(0, 0, 0), bn: int = 0,
          tile_group: Optional[torch.Tensor] = None, m_tiles_used: Optional[torch.Tensor] = None,
@@ -65,10 +81,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: Optional[int] = None, N: Option
          act_out: int = ACT_NONE, act_out_slope: float = 0.0, out_scale: float = 1.0,
          rope_cs: Optional[torch.Tensor] = None, T: int = 0, heads: int = 0, head_dim: int = 0,
          Tp: int = 0, q_out=None, k_out=None, vt_out=None, qkv_sec0: int = 0,
-         route_vg: Optional[torch.Tensor] = None, route_vg_g1: int = 0) -> None:
-    """D = epilogue(A @ B^T) on the tcgen05 GEMM (see include/versband.h: vb_gemm).
+         route_vg: Optional[torch.Tensor] = None, route_vg_g1: int = 0) -> GemmArgs:
+    """Describe D = epilogue(A @ B^T) (see include/versband.h: vb_gemm_args).
 
-    `a` is a fp16 view of up to 4 dims [c3, c2, rows, k]; `b` a fp16 view [group, n, k].
+    `a` is a fp16 (or fp32 = TF32 mode) view of up to 4 dims [c3, c2, rows, k]; `b` a view [group, n, k].
     """
     assert a.dtype == b.dtype and a.dtype in (torch.float16, torch.float32) and a.is_cuda and b.is_cuda
     args = GemmArgs()
@@ -118,7 +134,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: Optional[int] = None, N: Option
     args.qkv_sec0 = qkv_sec0
     _check_f32(route_vg, "route_vg")
     args.route_vg, args.route_vg_g1 = _ptr(route_vg), route_vg_g1
-    _lib.check(_lib.lib().vb_gemm(C.byref(args), _stream()), "vb_gemm")
+    return args
 
 
 # ------------------------------------------------------------------------------------------

@@ -136,12 +136,13 @@ class FlowSampler:
         S, B2 = st["t_all"].shape
         self.dit.time_conditioning(st["t_all"].reshape(-1), cond2.cap_emb.repeat(S, 1), st["mod_all"].view(S * B2, -1),
                                    st["hl_all"].view(S * B2, -1))
+        st["chain_cnt"].zero_()  # dependency counters of every chained launch of the run (one memset)
         for s, (_, dt) in enumerate(self.sched):
             if rng:
                 self._draw_step(st, s, generator)
             expo = [(st["e0"][s, k], st["e1"][s, k], st["e2"][s, k]) for k in range(d)]
             v, _ = self.dit.forward(x, st["t_all"][s], cond2, expo, pre=(st["mod_all"][s], st["hl_all"][s]),
-                                    x_cl_ready=s > 0)
+                                    x_cl_ready=s > 0, chain_cnt=st["chain_cnt"][s])
             # CFG + Euler update; the same launch rewrites the DiT's channels-last copies of x for the next step
             ops.ntc_to_nct(v[:N], x, e_u=v[N:], ld=v.shape[-1], s=scale, dt=dt,
                            x_cl=self.dit._workspace(cond2.B, cond2.T)["x_cl"])
@@ -173,6 +174,7 @@ class FlowSampler:
                       t_all=torch.tensor([[t] * (2 * B) for t, _ in self.sched], device=dev, dtype=torch.int64),
                       mod_all=torch.empty(S, 2 * B, self.dit.mod_ld, device=dev, dtype=F32),
                       hl_all=torch.empty(S, 2 * B, 2 * d, device=dev, dtype=F32),
+                      chain_cnt=torch.zeros(S, d, self.dit._workspace(2 * B, T)["chain_len"], device=dev, dtype=torch.int32),
                       graphs={})
             self._state[key] = st
         elif pair is None:
@@ -185,7 +187,7 @@ class FlowSampler:
             assert len(generator) == B
             self._draw_per_clip(st, B, T, generator)
             rng, noise, generator = False, None, None
-        if rng and self.native_noise_ok():
+        elif rng and self.native_noise_ok():
             # all 576 Exp(1) draws in one launch, bit-identical to torch's stream; the graph below then
             # runs without RNG nodes
             if self._draw_native(st, generator):
@@ -195,6 +197,8 @@ class FlowSampler:
             st["e0"].copy_(noise[..., 0:2])
             st["e1"].copy_(noise[..., 2:2 + E])
             st["e2"].copy_(noise[..., 2 + E:])
+        if isinstance(generator, (list, tuple)):  # (native self-check failed and per-clip draws not taken)
+            generator = generator[0]
         if not self.use_graph:
             self._run(st, scale, rng, generator)
             return st["x"].clone()
