@@ -195,6 +195,9 @@ long long vb_launch_count(void);
  * 7 layout, 8 groupnorm, 9 conv_post). Not usable during CUDA-graph capture. */
 /* haloed small-C conv path inside vb_gemm (C_in <= 64, N <= 64, fp16): 0 off, 1 on */
 int vb_set_conv_halo(int mode);
+/* experiments on vb_gemm_chain (tools/bench_chain.py): bit 0 ignore dependencies (WRONG results), bit 1 no
+ * publish fences (WRONG), bit 2 m-fastest tile order; 0 = product behaviour */
+int vb_set_chain_debug(int mode);
 /* 2-CTA (tcgen05 cta_group::2, cluster of 2) GEMM path: 0 off, 1 heuristic, 2 whenever legal */
 int vb_set_gemm2(int mode);
 /* tuning hook: force tile width `bn` (and the 2-CTA path if cta2) for every vb_gemm with this

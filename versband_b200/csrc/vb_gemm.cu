@@ -42,6 +42,7 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const int64_
 
 static int g_dbg_shift = 0;
 static int g_conv_halo = 1;  // 0 off, 1 on
+static int g_chain_dbg = 0;
 static int g_gemm2_mode = 1;  // 0 = off, 1 = cost model, 2 = whenever legal
 // in-situ tuning hook (tools/tune_insitu.py): force the tile shape of every vb_gemm whose (N, K, grouped)
 // matches an entry. Not used by the product path.
@@ -79,6 +80,11 @@ extern "C" int vb_set_gemm_override(int N, int K, int grouped, int bn, int cta2)
 extern "C" int vb_set_gemm_trace(void* buf, int max_calls) {
   vb::g_gemm_trace = static_cast<unsigned long long*>(buf);
   vb::g_gemm_trace_left = buf ? max_calls : 0;
+  return VB_OK;
+}
+
+extern "C" int vb_set_chain_debug(int mode) {
+  vb::g_chain_dbg = mode;
   return VB_OK;
 }
 
@@ -373,6 +379,9 @@ extern "C" int vb_gemm_chain(const vb_gemm_args* ops, const int32_t* dep_mode, i
     return set_error(VB_ERR_INVALID, "vb_gemm_chain: counter buffer too small (%lld ints needed)", (long long)used);
   cp.total_tiles = tiles;
   cp.err_flag = counters;
+  cp.dbg = g_chain_dbg;
+  if (cp.dbg & 1)
+    for (int o = 0; o < n_ops; ++o) cp.op[o].dep_mode = cp.op[o].sig_mode = 0;
   const int num_sms = device_sm_count();
   const int grid = tiles < num_sms ? tiles : num_sms;
   return launch_chain(bn, tf32, cp, grid, static_cast<cudaStream_t>(stream_));

@@ -1090,8 +1090,13 @@ __device__ __forceinline__ ChainTile chain_decode(const ChainParams& cp, int t, 
   c.o = o;
   c.g = local / per_g;
   const int r = local - c.g * per_g;
-  c.m_tile = r / p.n_tiles;            // n fastest: a row block's N tiles are adjacent in the list
-  c.n_tile = r - c.m_tile * p.n_tiles;
+  if (cp.dbg & 4) {
+    c.n_tile = r / p.m_tiles;
+    c.m_tile = r - c.n_tile * p.m_tiles;
+  } else {
+    c.m_tile = r / p.n_tiles;            // n fastest: a row block's N tiles are adjacent in the list
+    c.n_tile = r - c.m_tile * p.n_tiles;
+  }
   c.g1 = c.g % p.G1;
   c.g2 = c.g / p.G1;
   c.skip = c.m_tile >= m_used[o];
@@ -1240,8 +1245,10 @@ vb_chain_kernel(const __grid_constant__ ChainParams cp) {
       mbar_arrive(&tmem_empty_bar[acc]);
       if (op.sig_mode != 0) {
         // publish: every epilogue thread's stores of this tile are fenced, then ONE arrival per tile
-        fence_proxy_async_all();
-        __threadfence();
+        if (!(cp.dbg & 2)) {
+          fence_proxy_async_all();
+          __threadfence();
+        }
         named_bar_sync(1, kEpiWarps * 32);
         if (threadIdx.x == 64) {
           if (op.sig_mode == 1) atomicAdd(op.cnt_rows + (tc.g * p.m_tiles + tc.m_tile), 1);

@@ -107,6 +107,7 @@ struct ChainParams {
   ChainOp op[kChainMaxOps];
   int n_ops, total_tiles;
   int* err_flag;        // set to 1 if a dependency wait timed out (never in a correct run)
+  int dbg;              // experiments (vb_set_chain_debug): 1 ignore dependencies, 2 no publish fences, 4 m-fastest order
 };
 int launch_chain(int bn, bool tf32, const ChainParams& cp, int grid, cudaStream_t stream);
 

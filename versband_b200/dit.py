@@ -113,7 +113,10 @@ class DiTEngine:
         self.dev = torch.device(device)
         assert self.hd % 32 == 0 and hidden_size % (64 * 1) == 0
         self._ws: Dict[Tuple[int, int], dict] = {}
-        self.use_chain = True   # MoE expert GEMMs as one persistent chained launch (vb_gemm_chain)
+        # MoE expert GEMMs as one persistent chained launch (vb_gemm_chain). Off by default: measured on B200
+        # (tools/bench_chain.py) the 4 separately tiled launches take 38 us per block, the chain 54 us — the
+        # dependency stalls of a statically scheduled tile list cost more than the 3 launch boundaries they remove
+        self.use_chain = False
         self.chain_bn = 128
         self.pack(sd)
 
