@@ -91,6 +91,8 @@ typedef struct vb_gemm_args {
   /* MoE grouped mode (optional): per-M-tile group id and device-side tile count */
   const int32_t* tile_group;
   const int32_t* m_tiles_used;
+  const int32_t* tile_row0; /* optional: first A/output row of M tile i (sparse layouts: fixed-capacity expert
+                               buckets, vb_route_dispatch); NULL = i * 128 */
 
   /* ---- epilogue --------------------------------------------------------------------- */
   int32_t mode;  /* VB_EPI_* */
@@ -139,6 +141,22 @@ typedef struct vb_gemm_args {
 } vb_gemm_args;
 
 int vb_gemm(const vb_gemm_args* args, void* stream);
+
+/* Router + expert dispatch of one Band-MoE block in ONE launch (MoE.forward, vocal2music_moe.py:132-167):
+ * per token the three Gumbel-softmaxes of vb_router (same arithmetic), then the token's operand row `x[n]`
+ * (row_bytes each) is copied into its (group, expert) bucket. Bucket k owns rows [k*cap_rows, (k+1)*cap_rows)
+ * of xs / row_map / row_scale (cap_rows = N rounded up to 128), so no prefix over bucket counts is needed. The
+ * last CTA to finish writes the compact tile table of the grouped GEMMs — tile_group[i], tile_row0[i] for every
+ * 128-row tile holding a token, *m_tiles_used —, invalidates the padding rows of partial tiles, reduces the
+ * load-balancing loss (:95-115) and re-zeroes bucket_count / usage / done_ticket (all must be zero before the
+ * first launch). row_map[r] = n (caption group) or N + n (acoustic group); row_scale[r] = hard weight x mask. */
+int vb_route_dispatch(const float* cap_partial, int n_heads, const float* bc, const float* ac_logits, int ac_ld,
+                      const float* hl_logits, int hl_ld, const float* e0, const float* e1, const float* e2, float tau,
+                      int N, int T, int E, int row_bytes, const void* x, void* xs, int cap_rows, int32_t* idx_c,
+                      int32_t* idx_a, float* cap_logits_out, int32_t* bucket_count, float* usage,
+                      int32_t* done_ticket, int32_t* next_count, float* next_usage, int32_t* row_map,
+                      float* row_scale, int32_t* tile_group, int32_t* tile_row0, int32_t* m_tiles_used,
+                      float* lb_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * vb_gemm_chain — up to 4 DEPENDENT vb_gemm problems in ONE persistent launch (1-CTA kernel, one N tile

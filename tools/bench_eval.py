@@ -22,6 +22,7 @@ xd = x.cuda()
 def measure(label, **sw):
     for k, v in sw.items():
         setattr(eng, k, v)
+    eng._ws.clear()
     for _ in range(3):
         eng.forward(xd, t, cond, expo)
     torch.cuda.synchronize()
@@ -43,6 +44,5 @@ def measure(label, **sw):
 if kv:
     measure(str(kv), **{k: int(v) for k, v in kv.items()})
 else:
-    measure("unchained", use_chain=False)
-    measure("chain bn=128", use_chain=True, chain_bn=128)
-    measure("chain bn=64", use_chain=True, chain_bn=64)
+    measure("router + dispatch (2 launches)", fused_dispatch=0)
+    measure("fused route_dispatch", fused_dispatch=1)

@@ -25,7 +25,7 @@ class GemmArgs(C.Structure):
         ("a_c2_g1", c_i32), ("a_c2_g2", c_i32), ("a_c3_g1", c_i32), ("a_c3_g2", c_i32),
         ("b_c2_g1", c_i32), ("b_c2_g2", c_i32), ("b_c2_tile", c_i32),
         ("bn", c_i32), ("operand_f32", c_i32),
-        ("tile_group", c_ptr), ("m_tiles_used", c_ptr),
+        ("tile_group", c_ptr), ("m_tiles_used", c_ptr), ("tile_row0", c_ptr),
         ("mode", c_i32), ("alpha", c_f32), ("swiglu", c_i32),
         ("bias", c_ptr), ("bias_g1", c_i64), ("bias_tile", c_i64),
         ("act", c_i32), ("act_slope", c_f32),
@@ -105,6 +105,7 @@ def _declare(l: C.CDLL) -> None:
         "vb_linear_small": [P, L, P, P, P, I, I, I, P],
         "vb_router": [P, P, P, P, P, I, P, I, P, P, P, F, I, I, I, I, P, P, P, P, P, P, P, P, P, P, I, P],
         "vb_route_prepare": [P, I, I, I, I, P, P, P, P, P],
+        "vb_route_dispatch": [P, I, P, P, I, P, I, P, P, P, F, I, I, I, I, P, P, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
         "vb_moe_finalize": [P, P, I, P, P, P, P, P, I, P, P],
         "vb_moe_dispatch": [P, P, P, P, P, P, P, P, P, P, I, I, I, P, P, P, P, P, P, I, P, P],
         "vb_moe_scatter": [P, P, P, P, P, P, P, I, I, I, P, P, P, P, P],

@@ -206,7 +206,7 @@ int plan_gemm(const vb_gemm_args* a, int force_bn, GemmPlan* out) {
   p.num_kb = num_kb; p.kpt = kpt; p.dil = a->dil; p.pad = a->pad;
   p.a_c2_g1 = a->a_c2_g1; p.a_c2_g2 = a->a_c2_g2; p.a_c3_g1 = a->a_c3_g1; p.a_c3_g2 = a->a_c3_g2;
   p.b_c2_g1 = a->b_c2_g1; p.b_c2_g2 = a->b_c2_g2; p.b_c2_tile = a->b_c2_tile;
-  p.tile_group = a->tile_group; p.m_tiles_used = a->m_tiles_used;
+  p.tile_group = a->tile_group; p.m_tiles_used = a->m_tiles_used; p.tile_row0 = a->tile_row0;
   p.mode = a->mode; p.alpha = a->alpha; p.swiglu = a->swiglu;
   p.bias = a->bias; p.bias_g1 = a->bias_g1; p.bias_tile = a->bias_tile;
   p.act = a->act; p.act_slope = a->act_slope;

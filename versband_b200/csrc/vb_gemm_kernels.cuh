@@ -616,20 +616,25 @@ struct GemmCfg {
 
 struct TileCoord {
   int m_tile, n_tile, g1, g2, tg;
+  int m0;  // first A / output row of the tile: m_tile * 128, or tile_row0[m_tile] (sparse grouped layouts)
   bool skip;
 };
 
+// `m_used` = number of M tiles actually present (device value in grouped mode, else p.m_tiles): the flat tile
+// space is COMPACT over the used tiles, so a sparse tile table (most of p.m_tiles unused) still spreads evenly
+// over the persistent CTAs.
 __device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int t, int m_used) {
   TileCoord c;
-  const int per_g = p.m_tiles * p.n_tiles;
+  const int per_g = m_used * p.n_tiles;
   const int g = t / per_g;
   const int r = t - g * per_g;
-  c.n_tile = r / p.m_tiles;
-  c.m_tile = r - c.n_tile * p.m_tiles;
+  c.n_tile = r / m_used;
+  c.m_tile = r - c.n_tile * m_used;
   c.g1 = g % p.G1;
   c.g2 = g / p.G1;
-  c.skip = c.m_tile >= m_used;
-  c.tg = (p.tile_group && !c.skip) ? p.tile_group[c.m_tile] : 0;
+  c.skip = false;
+  c.tg = p.tile_group ? p.tile_group[c.m_tile] : 0;
+  c.m0 = p.tile_row0 ? p.tile_row0[c.m_tile] : c.m_tile * BM;
   return c;
 }
 
@@ -678,17 +683,18 @@ vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) VB_TRACE(1);
 
   const int num_kb = p.num_kb;
-  const int m_used = p.m_tiles_used ? *p.m_tiles_used : p.m_tiles;
+  const int m_used = p.m_tiles_used ? min(*p.m_tiles_used, p.m_tiles) : p.m_tiles;
+  const int num_tiles = m_used * p.n_tiles * (p.num_tiles / (p.m_tiles * p.n_tiles));
 
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile(p, t, m_used);
         if (tc.skip) continue;
-        const int m0 = tc.m_tile * BM, n0 = tc.n_tile * BN;
+        const int m0 = tc.m0, n0 = tc.n_tile * BN;
         const int a_c2 = tc.g1 * p.a_c2_g1 + tc.g2 * p.a_c2_g2;
         const int a_c3 = tc.g1 * p.a_c3_g1 + tc.g2 * p.a_c3_g2;
         const int b_c2 = tc.g1 * p.b_c2_g1 + tc.g2 * p.b_c2_g2 + tc.tg * p.b_c2_tile;
@@ -712,7 +718,7 @@ vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile(p, t, m_used);
         if (tc.skip) continue;
         const int acc = local & 1;
@@ -751,12 +757,12 @@ vb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int c_first = BN == 32 ? 0 : wset * 32;
     const uint32_t stg = smem_u32(epi_stage) + (warp_idx - 2) * 4096;
     int local = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(p, t, m_used);
       if (tc.skip) continue;
       const int acc = local & 1;
       if (BN == 32 && acc != wset) { ++local; continue; }
-      const int m_base = tc.m_tile * BM + q * 32, n0 = tc.n_tile * BN;
+      const int m_base = tc.m0 + q * 32, n0 = tc.n_tile * BN;
       const uint32_t tmem_d = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
       if (EC == EC_ROUTE) {
         mbar_wait(&tmem_full_bar[acc], (local >> 1) & 1);
@@ -1075,7 +1081,7 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 struct ChainTile {
-  int o, m_tile, n_tile, g1, g2, g, tg;
+  int o, m_tile, n_tile, g1, g2, g, tg, m0;
   bool skip;
 };
 __device__ __forceinline__ ChainTile chain_decode(const ChainParams& cp, int t, const int* m_used) {
@@ -1101,6 +1107,7 @@ __device__ __forceinline__ ChainTile chain_decode(const ChainParams& cp, int t, 
   c.g2 = c.g / p.G1;
   c.skip = c.m_tile >= m_used[o];
   c.tg = (p.tile_group && !c.skip) ? p.tile_group[c.m_tile] : 0;
+  c.m0 = (p.tile_row0 && !c.skip) ? p.tile_row0[c.m_tile] : c.m_tile * BM;
   return c;
 }
 
@@ -1176,7 +1183,7 @@ vb_chain_kernel(const __grid_constant__ ChainParams cp) {
           }
           fence_proxy_async_all();
         }
-        const int m0 = tc.m_tile * BM, n0 = tc.n_tile * BN;
+        const int m0 = tc.m0, n0 = tc.n_tile * BN;
         const int a_c2 = tc.g1 * p.a_c2_g1 + tc.g2 * p.a_c2_g2;
         const int a_c3 = tc.g1 * p.a_c3_g1 + tc.g2 * p.a_c3_g2;
         const int b_c2 = tc.g1 * p.b_c2_g1 + tc.g2 * p.b_c2_g2 + tc.tg * p.b_c2_tile;
@@ -1238,7 +1245,7 @@ vb_chain_kernel(const __grid_constant__ ChainParams cp) {
       const ChainOp& op = cp.op[tc.o];
       const GemmKParams& p = op.p;
       const int acc = local & 1;
-      const int m_base = tc.m_tile * BM + q * 32, n0 = tc.n_tile * BN;
+      const int m_base = tc.m0 + q * 32, n0 = tc.n_tile * BN;
       const uint32_t tmem_d = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
       VB_EPILOGUE_TILE(BN, n0, tc.g1, tc.g2, tc.tg, mbar_wait(&tmem_full_bar[acc], (local >> 1) & 1))
       tc_fence_before();

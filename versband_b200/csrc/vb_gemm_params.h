@@ -37,6 +37,7 @@ struct GemmKParams {
   int b_c2_g1, b_c2_g2, b_c2_tile;
   const int* tile_group;
   const int* m_tiles_used;
+  const int* tile_row0;
   // epilogue
   int mode;
   float alpha;

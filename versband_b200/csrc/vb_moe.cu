@@ -421,6 +421,185 @@ __global__ void moe_dispatch_kernel(const int* __restrict__ idx_c, const int* __
 }
 
 
+// ------------------------------------------------------------------ router + dispatch in ONE launch
+// vb_route_dispatch: the Gumbel-softmax router (above) and the expert dispatch fused. Buckets have a FIXED
+// capacity of `cap_rows` rows each (cap_rows = N rounded up to 128: one group's tokens could all pick the same
+// expert), bucket k occupies rows [k*cap_rows, (k+1)*cap_rows) of xs / row_map / row_scale, so a token's row is
+// known as soon as its slot inside the bucket is claimed — no prefix over the bucket counts, hence no second
+// launch: one warp per token routes it, claims its two slots (CTA-aggregated atomics), and copies its operand
+// row into both. The LAST CTA to finish (ticket counter) builds the compact tile table of the grouped GEMMs
+// from the final counts — (group, first row) of every 128-row tile that holds at least one token — marks the
+// padding rows of partial tiles invalid, reduces the load-balancing loss and zeroes the next block's counters.
+template <int E>
+__global__ void route_dispatch_kernel(const float* __restrict__ cap_partial, int n_heads, const float* __restrict__ bc,
+                                      const float* __restrict__ ac_logits, int ac_ld,
+                                      const float* __restrict__ hl_logits, int hl_ld, const float* __restrict__ e0,
+                                      const float* __restrict__ e1, const float* __restrict__ e2, float tau, int N,
+                                      int T, int row_bytes, const uint8_t* __restrict__ x, uint8_t* __restrict__ xs,
+                                      int cap_rows, int* __restrict__ idx_c, int* __restrict__ idx_a,
+                                      float* __restrict__ cap_logits_out, int* __restrict__ bucket_count,
+                                      float* __restrict__ usage, int* __restrict__ done_ticket,
+                                      int* __restrict__ next_count, float* __restrict__ next_usage,
+                                      int* __restrict__ row_map, float* __restrict__ row_scale,
+                                      int* __restrict__ tile_group, int* __restrict__ tile_row0,
+                                      int* __restrict__ m_tiles_used, float* __restrict__ lb_out) {
+  pdl_sync();
+  static_assert(E == 4, "cap_partial layout is [N, heads, 4]");
+  __shared__ int s_cnt[2 * E], s_base[2 * E];
+  __shared__ float s_use[2 * E];
+  __shared__ int s_last;
+  if (threadIdx.x < 2 * E) { s_cnt[threadIdx.x] = 0; s_use[threadIdx.x] = 0.f; }
+  __syncthreads();
+  const int n_raw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const bool tok_ok = n_raw < N;
+  const int n = tok_ok ? n_raw : N - 1;  // surplus warps recompute the last token and store nothing
+  const int lane = threadIdx.x & 31;
+  float acc[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) acc[e] = 0.f;
+  {  // per-head contributions from the VB_EPI_ROUTE GEMM, summed in head order (deterministic)
+    const float4* pp = reinterpret_cast<const float4*>(cap_partial) + (long long)n * n_heads;
+    for (int h = 0; h < n_heads; ++h) {
+      const float4 v = __ldg(pp + h);
+      acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+    }
+  }
+  // the three Gumbel-softmaxes: identical arithmetic to router_kernel (lanes 0..E-1 caption gate,
+  // E..2E-1 acoustic gate, 2E..2E+1 group gate)
+  const int b = n / T;
+  const int gate = lane < E ? 0 : (lane < 2 * E ? 1 : 2);
+  const int base = gate == 0 ? 0 : (gate == 1 ? E : 2 * E);
+  const int width = gate == 2 ? 2 : E;
+  const int j = lane - base;
+  const bool active = lane < 2 * E + 2;
+  float logit = 0.f, ex = 1.f, tau_g = tau;
+  if (gate == 0) {
+    float lcv = acc[0];
+#pragma unroll
+    for (int e = 1; e < E; ++e) lcv = (j == e) ? acc[e] : lcv;
+    logit = lcv + bc[j < E ? j : 0];
+    if (cap_logits_out && lane < E && tok_ok) cap_logits_out[(long long)n * E + j] = logit;
+    ex = e1[(long long)n * E + (j < E ? j : 0)];
+  } else if (gate == 1) {
+    logit = ac_logits[(long long)n * ac_ld + j];
+    ex = e2[(long long)n * E + j];
+  } else if (active) {
+    logit = hl_logits[b * hl_ld + j];
+    ex = e0[(long long)n * 2 + j];
+    tau_g = 1.0f;
+  }
+  const float z = (logit + (-logf(ex))) / tau_g;
+  float zz[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) zz[e] = __shfl_sync(0xffffffffu, z, base + (e < width ? e : 0));
+  float m = zz[0];
+#pragma unroll
+  for (int e = 1; e < E; ++e) if (e < width) m = fmaxf(m, zz[e]);
+  float ssum = 0.f;
+#pragma unroll
+  for (int e = 0; e < E; ++e) if (e < width) { zz[e] = expf(zz[e] - m); ssum += zz[e]; }
+  int best = 0;
+  float pb = zz[0] / ssum;
+#pragma unroll
+  for (int e = 1; e < E; ++e) {
+    if (e < width) {
+      const float pe = zz[e] / ssum;
+      if (pe > pb) { pb = pe; best = e; }
+    }
+  }
+  const float w_hard = (1.f - pb) + pb;
+  const float mask_c = __shfl_sync(0xffffffffu, zz[0] / ssum, 2 * E);
+  const float mask_a = __shfl_sync(0xffffffffu, zz[1] / ssum, 2 * E);
+  const int ic = __shfl_sync(0xffffffffu, best, 0);
+  const float wc = __shfl_sync(0xffffffffu, w_hard, 0);
+  const int ia = __shfl_sync(0xffffffffu, best, E);
+  const float wa = __shfl_sync(0xffffffffu, w_hard, E);
+  const float sc_c = wc * mask_c, sc_a = wa * mask_a;
+  const bool writer = lane == 0 && tok_ok;
+  int rc = 0, ra = 0;
+  if (writer) {
+    idx_c[n] = ic;
+    idx_a[n] = ia;
+    rc = atomicAdd(&s_cnt[ic], 1);
+    ra = atomicAdd(&s_cnt[E + ia], 1);
+    atomicAdd(&s_use[ic], sc_c);
+    atomicAdd(&s_use[E + ia], sc_a);
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * E && s_cnt[threadIdx.x] > 0) {
+    s_base[threadIdx.x] = atomicAdd(&bucket_count[threadIdx.x], s_cnt[threadIdx.x]);
+    atomicAdd(&usage[threadIdx.x], s_use[threadIdx.x]);
+  }
+  __syncthreads();
+  if (tok_ok) {
+    // rows of this token in the two groups' buckets (all lanes need them for the copy)
+    const int row_c = ic * cap_rows + s_base[ic] + __shfl_sync(0xffffffffu, rc, 0);
+    const int row_a = (E + ia) * cap_rows + s_base[E + ia] + __shfl_sync(0xffffffffu, ra, 0);
+    if (lane == 0) {
+      row_map[row_c] = n;        row_scale[row_c] = sc_c;
+      row_map[row_a] = N + n;    row_scale[row_a] = sc_a;
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(x + (long long)n * row_bytes);
+    uint4* dc = reinterpret_cast<uint4*>(xs + (long long)row_c * row_bytes);
+    uint4* da = reinterpret_cast<uint4*>(xs + (long long)row_a * row_bytes);
+    for (int k = lane; k < row_bytes / 16; k += 32) {
+      const uint4 v = __ldg(src + k);
+      dc[k] = v;
+      da[k] = v;
+    }
+  }
+  // ---- completion ticket: the last CTA finalises
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(done_ticket, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  __shared__ int f_cnt[2 * E], f_tile0[2 * E + 1];
+  const int nb = 2 * E;
+  if (threadIdx.x == 0) {
+    int tiles = 0;
+    float tot = 0.f;
+    float us[2 * E];
+    for (int k = 0; k < nb; ++k) {
+      const int c = *reinterpret_cast<volatile int*>(&bucket_count[k]);
+      f_cnt[k] = c;
+      f_tile0[k] = tiles;
+      for (int t = 0; t * 128 < c; ++t) {
+        tile_group[tiles] = k;
+        tile_row0[tiles] = k * cap_rows + t * 128;
+        ++tiles;
+      }
+      us[k] = *reinterpret_cast<volatile float*>(&usage[k]);
+      tot += us[k];
+    }
+    f_tile0[nb] = tiles;
+    *m_tiles_used = tiles;
+    if (lb_out) {
+      float loss = 0.f;
+      const float total = tot * (float)E;
+      for (int k = 0; k < nb; ++k) {
+        const float u = us[k] / (total + 1e-10f);
+        loss += u * logf(u + 1e-10f);
+      }
+      *lb_out = loss / (float)nb;
+    }
+    *done_ticket = 0;  // ready for the next launch (graph replay)
+  }
+  __syncthreads();
+  // padding rows of each bucket's last (partial) tile: invalid, so the grouped GEMMs drop them
+  for (int k = 0; k < nb; ++k) {
+    const int c = f_cnt[k], end = (c + 127) / 128 * 128;
+    for (int r = c + threadIdx.x; r < end; r += blockDim.x) { row_map[k * cap_rows + r] = -1; row_scale[k * cap_rows + r] = 0.f; }
+  }
+  __syncthreads();
+  if (threadIdx.x < nb) {
+    // this block's counters are consumed: zero them for the next evaluation; and the next block's too
+    bucket_count[threadIdx.x] = 0; usage[threadIdx.x] = 0.f;
+    if (next_count) { next_count[threadIdx.x] = 0; next_usage[threadIdx.x] = 0.f; }
+  }
+}
+
 // Step-invariant operands of the VB_EPI_ROUTE GEMM (include/versband.h): one CTA per (batch, head),
 // thread j = key. kv = [B*L, 2*H*hd] fp32 rows (k | v) of the MoE cross-attention's in-projection.
 //   bias_s[b][h][j] = <k_h[j], bq_h>            (bq already carries 1/sqrt(hd)); -1e30 for j >= L
@@ -558,4 +737,26 @@ extern "C" int vb_moe_dispatch(const int32_t* idx_c, const int32_t* idx_a, const
            static_cast<const uint8_t*>(x), static_cast<uint8_t*>(xs), row_map, row_scale, tile_group, m_tiles_used,
            max_rows, lb_out);
   return check_launch("vb_moe_dispatch");
+}
+
+extern "C" int vb_route_dispatch(const float* cap_partial, int n_heads, const float* bc, const float* ac_logits,
+                                 int ac_ld, const float* hl_logits, int hl_ld, const float* e0, const float* e1,
+                                 const float* e2, float tau, int N, int T, int E, int row_bytes, const void* x,
+                                 void* xs, int cap_rows, int32_t* idx_c, int32_t* idx_a, float* cap_logits_out,
+                                 int32_t* bucket_count, float* usage, int32_t* done_ticket, int32_t* next_count,
+                                 float* next_usage, int32_t* row_map, float* row_scale, int32_t* tile_group,
+                                 int32_t* tile_row0, int32_t* m_tiles_used, float* lb_out, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_ROUTER, stream);
+  if (!cap_partial || !bc || !ac_logits || !hl_logits || !e0 || !e1 || !e2 || !x || !xs || !idx_c || !idx_a ||
+      !bucket_count || !usage || !done_ticket || !row_map || !row_scale || !tile_group || !tile_row0 || !m_tiles_used ||
+      N <= 0 || T <= 0 || n_heads <= 0 || row_bytes % 16)
+    return set_error(VB_ERR_INVALID, "vb_route_dispatch: null/invalid argument");
+  if (E != 4) return set_error(VB_ERR_INVALID, "vb_route_dispatch: num_experts %d not instantiated (4)", E);
+  if (cap_rows < N || cap_rows % 128)
+    return set_error(VB_ERR_INVALID, "vb_route_dispatch: cap_rows %d must be a multiple of 128 and >= N=%d", cap_rows, N);
+  launch_k(route_dispatch_kernel<4>, dim3((N + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream), cap_partial,
+           n_heads, bc, ac_logits, ac_ld, hl_logits, hl_ld, e0, e1, e2, tau, N, T, row_bytes,
+           static_cast<const uint8_t*>(x), static_cast<uint8_t*>(xs), cap_rows, idx_c, idx_a, cap_logits_out, bucket_count,
+           usage, done_ticket, next_count, next_usage, row_map, row_scale, tile_group, tile_row0, m_tiles_used, lb_out);
+  return check_launch("vb_route_dispatch");
 }

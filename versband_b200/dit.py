@@ -118,6 +118,10 @@ class DiTEngine:
         # dependency stalls of a statically scheduled tile list cost more than the 3 launch boundaries they remove
         self.use_chain = False
         self.chain_bn = 128
+        # router + dispatch in one launch over fixed-capacity buckets (vb_route_dispatch). Off by default: measured
+        # 487 vs 473 us per evaluation (tools/bench_eval.py) — the last-CTA finalisation serialises ~3 us that the
+        # two-launch version overlaps under PDL
+        self.fused_dispatch = False
         self.pack(sd)
 
     # ------------------------------------------------------------------ packing
@@ -226,11 +230,14 @@ class DiTEngine:
         dev, D, H, hd, E, Fh = self.dev, self.D, self.H, self.hd, self.E, self.Fh
         N = B * T
         Tp = (T + 7) // 8 * 8
-        max_rows = ((2 * N + 127) // 128 + 2 * E) * 128
+        # fixed-capacity expert buckets (vb_route_dispatch): bucket k owns rows [k*cap, (k+1)*cap)
+        cap = (N + 127) // 128 * 128
+        max_rows = 2 * E * cap if self.fused_dispatch else ((2 * N + 127) // 128 + 2 * E) * 128
         z = lambda *s, dt=F32: torch.zeros(*s, device=dev, dtype=dt)  # noqa: E731
         AD = self.adt
         ws = dict(
-            Tp=Tp, max_rows=max_rows,
+            Tp=Tp, max_rows=max_rows, cap=cap,
+            tile_row0=z(max_rows // 128, dt=torch.int32), done_ticket=z(self.depth, dt=torch.int32),
             x_cl=z(B, T, 32, dt=AD), x=z(N, D), h=z(N, D),
             temb_sin=z(B, 256, dt=AD), temb_h=z(B, D, dt=AD), temb=z(B, D), ada_in=z(B, D, dt=AD),
             mod=z(B, self.mod_ld), hl=z(B, 2 * self.depth),
@@ -370,6 +377,28 @@ class DiTEngine:
         ops.gemm(ada, w["ada_w"], bias=w["ada_b"], out_f32=mod_out, out_ld=self.mod_ld)
         ops.linear_small(temb, w["hl_w"], w["hl_b"], hl_out)
 
+
+    def _router_and_dispatch(self, ws, b, cond, hl_t, k, e0, e1, e2, N, T, E, max_rows, want_aux):
+        """Two-launch variant (router, then dispatch over back-to-back padded buckets)."""
+        ops.router(None, None, b["capg_b"], cond.ac_logits[:, k * E:], self.depth * E,
+                   hl_t[:, 2 * k:], 2 * self.depth, e0, e1, e2, float(self.temperature), N, T,
+                   ws["idx_c"], ws["idx_a"], ws["scale_c"], ws["scale_a"],
+                   ws["cap_logits"] if want_aux else None, ws["bucket_count"][k], ws["usage"][k],
+                   ws["slot_c"], ws["slot_a"], cap_partial=ws["cap_part"])
+        ops.mark("router")
+        if self.depth > 1:
+            kn = (k + 1) % self.depth  # the dispatch of block k zeroes the counters of block k+1
+            ops.moe_dispatch(ws["idx_c"], ws["idx_a"], ws["slot_c"], ws["slot_a"], ws["scale_c"], ws["scale_a"],
+                             ws["bucket_count"][k], ws["usage"][k], ws["bucket_count"][kn], ws["usage"][kn], N, E,
+                             ws["xm"], ws["xs"], ws["row_map"], ws["row_scale"], ws["tile_group"], ws["m_tiles"],
+                             max_rows, ws["lb"][k:])
+        else:  # single block: counters must be re-zeroed by a separate launch
+            ops.moe_finalize(ws["bucket_count"][0], ws["usage"][0], E, ws["bucket_start"], ws["row_map"],
+                             ws["row_scale"], ws["tile_group"], ws["m_tiles"], max_rows, ws["lb"][k:])
+            ops.moe_scatter(ws["idx_c"], ws["idx_a"], ws["slot_c"], ws["slot_a"], ws["scale_c"], ws["scale_a"],
+                            ws["bucket_start"], N, E, ws["xm"], ws["xs"], ws["row_map"], ws["row_scale"])
+        ops.mark("moe_dispatch")
+
     # ------------------------------------------------------------------ one DiT evaluation
     @torch.no_grad()
     def forward(self, x: torch.Tensor, t: torch.Tensor, cond: DiTCond,
@@ -444,24 +473,18 @@ class DiTEngine:
                      out_f32=ws["cap_part"], out_ld=H * E)
             ops.mark("gemm:route")
             e0, e1, e2 = expo[k]
-            ops.router(None, None, b["capg_b"], cond.ac_logits[:, k * E:], self.depth * E,
-                       hl_t[:, 2 * k:], 2 * self.depth, e0, e1, e2, float(self.temperature), N, T,
-                       ws["idx_c"], ws["idx_a"], ws["scale_c"], ws["scale_a"],
-                       ws["cap_logits"] if want_aux else None, ws["bucket_count"][k], ws["usage"][k],
-                       ws["slot_c"], ws["slot_a"], cap_partial=ws["cap_part"])
-            ops.mark("router")
-            if self.depth > 1:
-                kn = (k + 1) % self.depth  # the dispatch of block k zeroes the counters of block k+1
-                ops.moe_dispatch(ws["idx_c"], ws["idx_a"], ws["slot_c"], ws["slot_a"], ws["scale_c"], ws["scale_a"],
-                                 ws["bucket_count"][k], ws["usage"][k], ws["bucket_count"][kn], ws["usage"][kn], N, E,
-                                 ws["xm"], ws["xs"], ws["row_map"], ws["row_scale"], ws["tile_group"], ws["m_tiles"],
-                                 max_rows, ws["lb"][k:])
-            else:  # single block: counters must be re-zeroed by a separate launch
-                ops.moe_finalize(ws["bucket_count"][0], ws["usage"][0], E, ws["bucket_start"], ws["row_map"],
-                                 ws["row_scale"], ws["tile_group"], ws["m_tiles"], max_rows, ws["lb"][k:])
-                ops.moe_scatter(ws["idx_c"], ws["idx_a"], ws["slot_c"], ws["slot_a"], ws["scale_c"], ws["scale_a"],
-                                ws["bucket_start"], N, E, ws["xm"], ws["xs"], ws["row_map"], ws["row_scale"])
-            ops.mark("moe_dispatch")
+            if self.fused_dispatch:
+                ops.route_dispatch(ws["cap_part"], b["capg_b"], cond.ac_logits[:, k * E:], self.depth * E,
+                                   hl_t[:, 2 * k:], 2 * self.depth, e0, e1, e2, float(self.temperature), N, T, E,
+                                   ws["xm"], ws["xs"], ws["cap"], ws["idx_c"], ws["idx_a"], ws["bucket_count"][k],
+                                   ws["usage"][k], ws["done_ticket"][k:], ws["row_map"], ws["row_scale"],
+                                   ws["tile_group"], ws["tile_row0"], ws["m_tiles"], lb_out=ws["lb"][k:],
+                                   cap_logits_out=ws["cap_logits"] if want_aux else None)
+                ops.mark("route_dispatch")
+                tile_row0 = ws["tile_row0"]
+            else:
+                tile_row0 = None
+                self._router_and_dispatch(ws, b, cond, hl_t, k, e0, e1, e2, N, T, E, max_rows, want_aux)
             # routed experts (w1|w3 -> SwiGLU -> w2, scattered back to token rows) and frequency experts
             # (band-sliced w1|w3 -> SwiGLU -> w2 + adaLN gate + residual): four dependent GEMM problems in ONE
             # persistent launch (vb_gemm_chain) — or four launches with use_chain = False.
@@ -470,9 +493,9 @@ class DiTEngine:
             # weights repeated along K), so the sum happens in the fp32 accumulator.
             yb = ws["y2"].view(2 * N, E, self.band).permute(1, 0, 2)  # [E, 2N, band] view: per-band K slice
             probs = [
-                (ws["xs"], b["w13"], dict(M=max_rows, b_c2=(0, 0, 1), tile_group=ws["tile_group"],
+                (ws["xs"], b["w13"], dict(M=max_rows, b_c2=(0, 0, 1), tile_group=ws["tile_group"], tile_row0=tile_row0,
                                           m_tiles_used=ws["m_tiles"], swiglu=True, out_fp16=ws["hs"], outb_ld=Fh)),
-                (ws["hs"], b["w2"], dict(M=max_rows, b_c2=(0, 0, 1), tile_group=ws["tile_group"],
+                (ws["hs"], b["w2"], dict(M=max_rows, b_c2=(0, 0, 1), tile_group=ws["tile_group"], tile_row0=tile_row0,
                                          m_tiles_used=ws["m_tiles"], row_map=ws["row_map"], rows_out=2 * N,
                                          row_scale=ws["row_scale"], out_fp16=ws["y2"], outb_ld=D)),
                 (yb, b["f13"], dict(M=N, G1=E, kpt=self.band // self.kq, dil=N, pad=0, a_c2=(1, 0), b_c2=(1, 0, 0),

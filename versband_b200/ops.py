@@ -68,6 +68,7 @@ def gemm_args(a: torch.Tensor, b: torch.Tensor, *, M: Optional[int] = None, N: O
          K: Optional[int] = None, G1: int = 1, G2: int = 1, kpt: int = 0, dil: int = 0, pad: int = 0,
          a_c2=(0, 0), a_c3=(0, 0), b_c2=(0, 0, 0), bn: int = 0,
          tile_group: Optional[torch.Tensor] = None, m_tiles_used: Optional[torch.Tensor] = None,
+         tile_row0: Optional[torch.Tensor] = None,
          mode: int = EPI_GENERIC, alpha: float = 1.0, swiglu: bool = False,
          bias: Optional[torch.Tensor] = None, bias_g1: int = 0, bias_tile: int = 0,
          act: int = ACT_NONE, act_slope: float = 0.0,
@@ -108,7 +109,7 @@ def gemm_args(a: torch.Tensor, b: torch.Tensor, *, M: Optional[int] = None, N: O
     args.a_c3_g1, args.a_c3_g2 = a_c3
     args.b_c2_g1, args.b_c2_g2, args.b_c2_tile = b_c2
     args.bn = bn
-    args.tile_group, args.m_tiles_used = _ptr(tile_group), _ptr(m_tiles_used)
+    args.tile_group, args.m_tiles_used, args.tile_row0 = _ptr(tile_group), _ptr(m_tiles_used), _ptr(tile_row0)
     args.mode, args.alpha, args.swiglu = mode, alpha, int(swiglu)
     _check_f32(bias, "bias"); _check_f32(row_scale, "row_scale"); _check_f32(gate, "gate")
     _check_f32(residual, "residual"); _check_f32(out_f32, "out_f32")
@@ -189,6 +190,18 @@ def router(cap_feat, Wc, bc, ac_logits, ac_ld, hl_logits, hl_ld, e0, e1, e2, tau
           _ptr(e0), _ptr(e1), _ptr(e2), tau, N, T, D, bc.shape[0], _ptr(idx_c), _ptr(idx_a),
           _ptr(scale_c), _ptr(scale_a), _ptr(cap_logits_out), _ptr(bucket_count), _ptr(usage), _ptr(slot_c),
           _ptr(slot_a), _ptr(cap_partial), cap_partial.shape[1] if cap_partial is not None else 0)
+
+
+def route_dispatch(cap_partial, bc, ac_logits, ac_ld, hl_logits, hl_ld, e0, e1, e2, tau, N, T, E, x, xs, cap_rows,
+                   idx_c, idx_a, bucket_count, usage, done_ticket, row_map, row_scale, tile_group, tile_row0,
+                   m_tiles_used, lb_out=None, cap_logits_out=None) -> None:
+    """Router + dispatch of one MoE block in one launch (include/versband.h: vb_route_dispatch)."""
+    _check_f32(cap_partial, "cap_partial")
+    _call("vb_route_dispatch", _ptr(cap_partial), cap_partial.shape[1], _ptr(bc), _ptr(ac_logits), ac_ld,
+          _ptr(hl_logits), hl_ld, _ptr(e0), _ptr(e1), _ptr(e2), tau, N, T, E, x.shape[-1] * x.element_size(),
+          _ptr(x), _ptr(xs), cap_rows, _ptr(idx_c), _ptr(idx_a), _ptr(cap_logits_out), _ptr(bucket_count),
+          _ptr(usage), _ptr(done_ticket), None, None, _ptr(row_map), _ptr(row_scale), _ptr(tile_group),
+          _ptr(tile_row0), _ptr(m_tiles_used), _ptr(lb_out))
 
 
 def route_prepare(kv, B, L, H, hd, bq, capg_w, bias_s, vg) -> None:
