@@ -111,6 +111,9 @@ typedef struct vb_gemm_args {
   const int32_t* row_map;
   int32_t row_mul, row_off, row_off_g1, rows_out;
   const float* residual; /* v += residual[...] same addressing as out_f32 */
+  const void* res16;     /* fp16 residual stored in the ACTIVATED representation y = leaky_relu(x): v += (y >= 0 ? y :
+                            y * res16_neg), same addressing as out_fp16 (HiFi-GAN residual stream, vocoder.py) */
+  float res16_neg;       /* 1 / negative_slope (1 = plain fp16 residual) */
   int32_t accumulate;    /* v += out_f32[...] (previous contents) */
   float* out_f32;        /* optional fp32 store */
   int64_t out_ld, out_g1, out_g2; /* elements */

@@ -32,7 +32,7 @@ class GemmArgs(C.Structure):
         ("row_scale", c_ptr), ("gate", c_ptr), ("gate_rows", c_i32), ("gate_ld", c_i64), ("gate_g1", c_i64),
         ("row_map", c_ptr),
         ("row_mul", c_i32), ("row_off", c_i32), ("row_off_g1", c_i32), ("rows_out", c_i32),
-        ("residual", c_ptr), ("accumulate", c_i32),
+        ("residual", c_ptr), ("res16", c_ptr), ("res16_neg", c_f32), ("accumulate", c_i32),
         ("out_f32", c_ptr), ("out_ld", c_i64), ("out_g1", c_i64), ("out_g2", c_i64),
         ("out_fp16", c_ptr), ("outb_f32", c_i32), ("outb_ld", c_i64), ("outb_g1", c_i64), ("outb_g2", c_i64),
         ("act_out", c_i32), ("act_out_slope", c_f32), ("out_scale", c_f32),

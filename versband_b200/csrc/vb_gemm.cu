@@ -216,6 +216,7 @@ int plan_gemm(const vb_gemm_args* a, int force_bn, GemmPlan* out) {
   p.row_mul = a->row_mul; p.row_off = a->row_off; p.row_off_g1 = a->row_off_g1;
   p.rows_out = a->rows_out;
   p.residual = a->residual; p.accumulate = a->accumulate;
+  p.res16 = static_cast<const __half*>(a->res16); p.res16_neg = a->res16_neg;
   p.out_f32 = a->out_f32; p.out_ld = a->out_ld; p.out_g1 = a->out_g1; p.out_g2 = a->out_g2;
   p.out_fp16 = static_cast<__half*>(a->out_fp16);
   p.outb_f32 = a->outb_f32;
@@ -246,6 +247,8 @@ int plan_gemm(const vb_gemm_args* a, int force_bn, GemmPlan* out) {
       return set_error(VB_ERR_INVALID, "vb_gemm: accumulate needs out_f32");
     if (a->residual && a->out_ld <= 0)
       return set_error(VB_ERR_INVALID, "vb_gemm: residual needs out_ld (it shares the fp32 output addressing)");
+    if (a->res16 && (a->residual || a->outb_f32 || a->outb_ld <= 0 || (reinterpret_cast<uintptr_t>(a->res16) & 15)))
+      return set_error(VB_ERR_INVALID, "vb_gemm: res16 excludes residual, shares the fp16 output addressing (outb_ld) and must be 16-byte aligned");
   }
 
   // epilogue class: the smallest specialisation that covers the requested fusion

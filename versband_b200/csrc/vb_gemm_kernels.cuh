@@ -263,6 +263,12 @@ __device__ __forceinline__ void epilogue_rowwise(const GemmKParams& p, float (&v
                     full && p.vec_aux, n_left);
   const long long off32 = g1 * p.out_g1 + g2 * p.out_g2 + orow * p.out_ld + n_base;
   if (p.residual) combine32<false>(v, p.residual + off32, full && p.vec_f32, n_left);
+  if (p.res16) {
+    const __half* r16 = p.res16 + g1 * p.outb_g1 + g2 * p.outb_g2 + orow * p.outb_ld + n_base;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < n_left) { const float y = __half2float(r16[j]); v[j] += y < 0.f ? y * p.res16_neg : y; }
+  }
   if (p.out_f32) {
     float* dst = p.out_f32 + off32;
     if (p.accumulate) combine32<false>(v, dst, full && p.vec_f32, n_left);
@@ -357,6 +363,20 @@ __device__ __forceinline__ void epi_load_operands(const GemmKParams& p, const Ep
     op.g_lo = __ldg(reinterpret_cast<const float4*>(gsrc));
     op.g_hi = __ldg(reinterpret_cast<const float4*>(gsrc + (rows.hi ? p.gate_ld : 0)));
   }
+  if (p.res16) {
+    // fp16 residual in the activated ("y = leaky_relu(x)") representation: x = y >= 0 ? y : y * res16_neg
+    const __half* r16 = p.res16 + g1 * p.outb_g1 + g2 * p.outb_g2 + n;
+    const float ng = p.res16_neg;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(r16 + rows.offb[i]));
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+      op.res[i] = make_float4(a.x < 0.f ? a.x * ng : a.x, a.y < 0.f ? a.y * ng : a.y,
+                              b.x < 0.f ? b.x * ng : b.x, b.y < 0.f ? b.y * ng : b.y);
+    }
+    return;
+  }
   const float* rsrc = p.residual ? p.residual : ((p.accumulate && p.out_f32) ? p.out_f32 : nullptr);
   if (rsrc) {
     rsrc += g1 * p.out_g1 + g2 * p.out_g2 + n;
@@ -427,10 +447,10 @@ __device__ __forceinline__ void epilogue_generic(const GemmKParams& p, float (&v
     }
   }
   const long long gofs32 = g1 * p.out_g1 + g2 * p.out_g2 + n;
-  if (p.residual || (p.accumulate && p.out_f32)) {
+  if (p.residual || p.res16 || (p.accumulate && p.out_f32)) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { v[4 * i] += op.res[i].x; v[4 * i + 1] += op.res[i].y; v[4 * i + 2] += op.res[i].z; v[4 * i + 3] += op.res[i].w; }
-    if (p.residual && p.accumulate && p.out_f32) {  // both: the accumulate target is read here
+    if ((p.residual || p.res16) && p.accumulate && p.out_f32) {  // both: the accumulate target is read here
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 r4 = *reinterpret_cast<const float4*>(p.out_f32 + gofs32 + rows.off[i]);

@@ -53,6 +53,8 @@ struct GemmKParams {
   const int* row_map;
   int row_mul, row_off, row_off_g1, rows_out;
   const float* residual;
+  const __half* res16;  // fp16 residual in the activated representation, addressed like out_fp16
+  float res16_neg;      // multiplier that undoes the leaky-relu on negative values (1/slope; 1 = plain fp16)
   int accumulate;
   float* out_f32;
   long long out_ld, out_g1, out_g2;

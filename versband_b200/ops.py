@@ -76,7 +76,8 @@ def gemm_args(a: torch.Tensor, b: torch.Tensor, *, M: Optional[int] = None, N: O
          gate: Optional[torch.Tensor] = None, gate_rows: int = 1, gate_ld: int = 0, gate_g1: int = 0,
          row_map: Optional[torch.Tensor] = None, row_mul: int = 1, row_off: int = 0,
          row_off_g1: int = 0, rows_out: Optional[int] = None,
-         residual: Optional[torch.Tensor] = None, accumulate: bool = False,
+         residual: Optional[torch.Tensor] = None, res16: Optional[torch.Tensor] = None, res16_neg: float = 1.0,
+         accumulate: bool = False,
          out_f32: Optional[torch.Tensor] = None, out_ld: int = 0, out_g=(0, 0),
          out_fp16: Optional[torch.Tensor] = None, outb_ld: int = 0, outb_g=(0, 0),
          act_out: int = ACT_NONE, act_out_slope: float = 0.0, out_scale: float = 1.0,
@@ -121,6 +122,7 @@ def gemm_args(a: torch.Tensor, b: torch.Tensor, *, M: Optional[int] = None, N: O
     args.row_mul, args.row_off, args.row_off_g1 = row_mul, row_off, row_off_g1
     args.rows_out = args.M if rows_out is None else rows_out
     args.residual, args.accumulate = _ptr(residual), int(accumulate)
+    args.res16, args.res16_neg = _ptr(res16), res16_neg
     args.out_f32, args.out_ld = _ptr(out_f32), out_ld
     args.out_g1, args.out_g2 = out_g
     if out_fp16 is not None:

@@ -101,12 +101,14 @@ class HifiGanEngine:
             kp = wup.shape[2] // Q
             p = (k - u) // 2
             Tout = (T - 1) * u - 2 * p + k
-            x = torch.empty(B, Tout, Cout, device=dev, dtype=F32)
+            # Activations live in HBM ONLY as y = leaky_relu_0.1(x) in fp16 (2 B/element): y is directly the next
+            # conv's A operand (TMA -> tensor core, no elementwise pass), and the pre-activation x that the residual
+            # connections need is recovered exactly-to-rounding as x = y >= 0 ? y : 10 y in the consuming epilogue
+            # (vb_gemm res16 / res16_neg). No fp32 copy of the residual stream exists any more.
             xl = torch.empty(B, Tout, Cout, device=dev, dtype=H16)
             ops.gemm(xb, wup, M=T + Q - 1, N=Cout, K=Q * kp, G1=u, G2=B, kpt=kp // 64, dil=1, pad=Q - 1,
                      a_c2=(0, 1), b_c2=(1, 0, 0), bias=self.w[f"up{i}.b"],
                      row_mul=u, row_off=-p, row_off_g1=1, rows_out=Tout,
-                     out_f32=x, out_ld=Cout, out_g=(0, Tout * Cout),
                      out_fp16=xl, outb_ld=Cout, outb_g=(0, Tout * Cout), act_out=ops.ACT_LRELU,
                      act_out_slope=LRELU)
             T, C = Tout, Cout
@@ -115,24 +117,22 @@ class HifiGanEngine:
             xs = torch.empty(B, T, C, device=dev, dtype=F32)
             nxt = torch.empty(B, T, C, device=dev, dtype=H16)
             t1 = torch.empty(B, T, C, device=dev, dtype=H16)
-            rbuf = [torch.empty(B, T, C, device=dev, dtype=F32) for _ in range(2)]
             rlb = [torch.empty(B, T, C, device=dev, dtype=H16) for _ in range(2)]
             for j in range(nk):
                 kk, dils = self.rb_k[j], self.rb_d[j]
-                r, rl = x, xl
+                rl = xl
                 for c, d in enumerate(dils):
                     self._conv(rl, f"rb{i}.{j}.convs1.{c}", B, T, kk, d, out_fp16=t1,
                                act_out=ops.ACT_LRELU, act_out_slope=LRELU)
                     if c < len(dils) - 1:
-                        self._conv(t1, f"rb{i}.{j}.convs2.{c}", B, T, kk, 1, residual=r,
-                                   out_f32=rbuf[c % 2], out_fp16=rlb[c % 2], act_out=ops.ACT_LRELU,
-                                   act_out_slope=LRELU)
-                        r, rl = rbuf[c % 2], rlb[c % 2]
+                        self._conv(t1, f"rb{i}.{j}.convs2.{c}", B, T, kk, 1, res16=rl, res16_neg=1.0 / LRELU,
+                                   out_fp16=rlb[c % 2], act_out=ops.ACT_LRELU, act_out_slope=LRELU)
+                        rl = rlb[c % 2]
                     else:
                         # last pair: xs (+)= r + conv; the last resblock also emits the next stage's
                         # operand lrelu(xs / nk) (slope 0.1 before ups, 0.01 before conv_post :139)
                         final = j == nk - 1
-                        self._conv(t1, f"rb{i}.{j}.convs2.{c}", B, T, kk, 1, residual=r,
+                        self._conv(t1, f"rb{i}.{j}.convs2.{c}", B, T, kk, 1, res16=rl, res16_neg=1.0 / LRELU,
                                    out_f32=xs, accumulate=(j > 0),
                                    out_fp16=nxt if final else None, act_out=ops.ACT_LRELU,
                                    act_out_slope=(0.01 if last_stage else LRELU), out_scale=1.0 / nk)
