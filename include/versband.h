@@ -145,6 +145,23 @@ typedef struct vb_gemm_args {
 
 int vb_gemm(const vb_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * vb_resblock_pair — one HiFi-GAN ResBlock1 conv pair, x' = x + c2(lrelu(c1_{dil}(lrelu(x)) + b1)) + b2
+ * (vocoder/hifigan/modules/hifigan.py:51-58), in ONE persistent tcgen05 kernel. Activations are fp16 in the
+ * ACTIVATED representation y = leaky_relu_slope(x), channels-last [B, T, C]; y_in feeds conv1 directly, the
+ * residual is recovered from the same tile, the intermediate stays in shared memory, y_out = lrelu(x').
+ * w1 / w2: packed conv weights [C, k*64] fp16 (tap-major, C_in zero-padded to 64) as produced for vb_gemm;
+ * b1 / b2 fp32 [C]. C in {32, 64}, odd k; both convs' weights must fit shared memory next to the tiles
+ * (vb_resblock_pair_fits: e.g. C=64 up to k=11, C=32 any HiFi-GAN k). y_out must not alias y_in.
+ * vb_mrf_combine: out = lrelu_{slope_out}((x0 + x1 + x2) * scale) over up to three activated-representation
+ * tensors (the MRF mean of hifigan.py:132-138), n elements (multiple of 8).
+ * ------------------------------------------------------------------------------------------ */
+int vb_resblock_pair_fits(int C, int k, int dil);
+int vb_resblock_pair(const void* y_in, void* y_out, const void* w1, const void* w2, const float* b1, const float* b2,
+                     int B, int T, int C, int k, int dil, float slope, void* stream);
+int vb_mrf_combine(const void* r0, const void* r1, const void* r2, float neg, float scale, float slope_out, void* out,
+                   int64_t n, void* stream);
+
 /* Router + expert dispatch of one Band-MoE block in ONE launch (MoE.forward, vocal2music_moe.py:132-167):
  * per token the three Gumbel-softmaxes of vb_router (same arithmetic), then the token's operand row `x[n]`
  * (row_bytes each) is copied into its (group, expert) bucket. Bucket k owns rows [k*cap_rows, (k+1)*cap_rows)

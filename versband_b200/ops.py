@@ -289,6 +289,21 @@ def conv_post(x_fp16, w, bias: float, B, T, Cc, k, wav) -> None:
     _call("vb_conv_post", _ptr(x_fp16), _ptr(w), bias, B, T, Cc, k, _ptr(wav))
 
 
+def resblock_pair_fits(C: int, k: int, dil: int) -> bool:
+    return bool(_lib.lib().vb_resblock_pair_fits(C, k, dil))
+
+
+def resblock_pair(y_in, y_out, w1, w2, b1, b2, *, B, T, C, k, dil, slope) -> None:
+    """One HiFi-GAN ResBlock1 conv pair in one kernel (include/versband.h: vb_resblock_pair)."""
+    assert y_in.dtype == torch.float16 and y_out.dtype == torch.float16 and y_in.is_contiguous() and y_out.is_contiguous()
+    _call("vb_resblock_pair", _ptr(y_in), _ptr(y_out), _ptr(w1), _ptr(w2), _ptr(b1), _ptr(b2), B, T, C, k, dil, slope)
+
+
+def mrf_combine(rs, out, *, neg: float, scale: float, slope_out: float) -> None:
+    rs = list(rs) + [None] * (3 - len(rs))
+    _call("vb_mrf_combine", _ptr(rs[0]), _ptr(rs[1]), _ptr(rs[2]), neg, scale, slope_out, _ptr(out), out.numel())
+
+
 def mean_tokens(x, out) -> None:
     B, L, D = x.shape
     _call("vb_mean_tokens", _ptr(x), B, L, D, _ptr(out))

@@ -38,6 +38,7 @@ class HifiGanEngine:
         self.rb_d: List[List[int]] = [list(d) for d in h["resblock_dilation_sizes"]]
         self.C0 = h["upsample_initial_channel"]
         self.w: Dict[str, torch.Tensor] = {}
+        self.fuse_pairs = True  # ResBlock1 conv pairs of the C <= 64 stages in one kernel each (vb_resblock_pair)
         self._pack({k: v.detach().to(self.dev) for k, v in sd.items()})
 
     def _pack(self, sd):
@@ -114,28 +115,28 @@ class HifiGanEngine:
             T, C = Tout, Cout
             # ---- MRF: mean of nk ResBlock1 chains that all start from x (hifigan.py:132-138)
             last_stage = i == n_stages - 1
-            xs = torch.empty(B, T, C, device=dev, dtype=F32)
             nxt = torch.empty(B, T, C, device=dev, dtype=H16)
             t1 = torch.empty(B, T, C, device=dev, dtype=H16)
             rlb = [torch.empty(B, T, C, device=dev, dtype=H16) for _ in range(2)]
+            rout = [torch.empty(B, T, C, device=dev, dtype=H16) for _ in range(nk)]  # each chain's result (activated repr.)
+            assert nk <= 3, "vb_mrf_combine takes up to three resblock outputs"
             for j in range(nk):
                 kk, dils = self.rb_k[j], self.rb_d[j]
                 rl = xl
                 for c, d in enumerate(dils):
-                    self._conv(rl, f"rb{i}.{j}.convs1.{c}", B, T, kk, d, out_fp16=t1,
-                               act_out=ops.ACT_LRELU, act_out_slope=LRELU)
-                    if c < len(dils) - 1:
-                        self._conv(t1, f"rb{i}.{j}.convs2.{c}", B, T, kk, 1, res16=rl, res16_neg=1.0 / LRELU,
-                                   out_fp16=rlb[c % 2], act_out=ops.ACT_LRELU, act_out_slope=LRELU)
-                        rl = rlb[c % 2]
+                    dst = rout[j] if c == len(dils) - 1 else rlb[c % 2]
+                    n1, n2 = f"rb{i}.{j}.convs1.{c}", f"rb{i}.{j}.convs2.{c}"
+                    if self.fuse_pairs and C in (32, 64) and ops.resblock_pair_fits(C, kk, d):
+                        # both convs, the activation between them and the residual add in ONE kernel (K18)
+                        ops.resblock_pair(rl, dst, self.w[n1 + ".w"], self.w[n2 + ".w"], self.w[n1 + ".b"], self.w[n2 + ".b"],
+                                          B=B, T=T, C=C, k=kk, dil=d, slope=LRELU)
                     else:
-                        # last pair: xs (+)= r + conv; the last resblock also emits the next stage's
-                        # operand lrelu(xs / nk) (slope 0.1 before ups, 0.01 before conv_post :139)
-                        final = j == nk - 1
-                        self._conv(t1, f"rb{i}.{j}.convs2.{c}", B, T, kk, 1, res16=rl, res16_neg=1.0 / LRELU,
-                                   out_f32=xs, accumulate=(j > 0),
-                                   out_fp16=nxt if final else None, act_out=ops.ACT_LRELU,
-                                   act_out_slope=(0.01 if last_stage else LRELU), out_scale=1.0 / nk)
+                        self._conv(rl, n1, B, T, kk, d, out_fp16=t1, act_out=ops.ACT_LRELU, act_out_slope=LRELU)
+                        self._conv(t1, n2, B, T, kk, 1, res16=rl, res16_neg=1.0 / LRELU,
+                                   out_fp16=dst, act_out=ops.ACT_LRELU, act_out_slope=LRELU)
+                    rl = dst
+            # mean of the chains + the next layer's activation (slope 0.1 before ups, 0.01 before conv_post :139)
+            ops.mrf_combine(rout, nxt, neg=1.0 / LRELU, scale=1.0 / nk, slope_out=(0.01 if last_stage else LRELU))
             xb = nxt
         wav = torch.empty(B, T, device=dev, dtype=F32)
         ops.conv_post(xb, self.w["post.w"], self.post_b, B, T, C, self.post_k, wav)
