@@ -21,6 +21,7 @@
 // persistent CTA. Warp roles (320 threads): 0 TMA producer, 1 MMA issuer (single thread), 2-5 epilogue #1,
 // 6-9 epilogue #2 (one thread per accumulator row = TMEM lane; no transposes: the A-operand layout of t1 and
 // the channels-last output are both row-contiguous).
+#include <cstdlib>
 #include "vb_internal.h"
 #include "vb_ptx.cuh"
 
@@ -32,6 +33,7 @@ struct ResPairParams {
   float slope, inv_slope;
   const float* b1;
   const float* b2;
+  const __half* in;
   __half* out;
 };
 
@@ -59,8 +61,8 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
   uint64_t* t1_empty = bars + 11;    // [2]
   uint64_t* a2_full = bars + 13;     // [2]
   uint64_t* a2_empty = bars + 15;    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
-  float* s_bias = reinterpret_cast<float*>(bars + 18);  // [2][C]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  float* s_bias = reinterpret_cast<float*>(bars + 20);  // [2][C]
 
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp_idx == 0 && lane == 0) {
@@ -70,7 +72,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
     mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&y_full[i], 1);
-      mbar_init(&y_empty[i], 1 + 128);  // conv1's commit + the 128 epilogue-2 threads (residual read)
+      mbar_init(&y_empty[i], 1);        // conv1's commit (the only reader of the input stage)
       mbar_init(&a1_full[i], 1);
       mbar_init(&a1_empty[i], 128);
       mbar_init(&t1_full[i], 128);
@@ -217,14 +219,15 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
       const int b = t / p.n_t, tt = t - b * p.n_t;
       const int time = tt * p.R + r;
       const bool valid = r < p.R && time < p.T;
-      // residual row (the centre of the receptive field) out of the input tile, before its slot is recycled
-      mbar_wait(&y_full[s], (i / p.NS) & 1);
-      const int yr = r + p.h1 + p.h2;
-      const uint8_t* yrow = smem_y + s * y_slot + yr * 128;
+      // residual row = the centre of the receptive field, read straight from global memory (L2-resident: the
+      // TMA has just fetched the same lines), issued before the accumulator wait so its latency is hidden
       uint4 res[C / 8];
+      {
+        const int tc = valid ? time : 0;
+        const uint4* src = reinterpret_cast<const uint4*>(p.in + ((long long)b * p.T + tc) * C);
 #pragma unroll
-      for (int ch = 0; ch < C / 8; ++ch) res[ch] = *reinterpret_cast<const uint4*>(yrow + ((ch ^ (yr & 7)) << 4));
-      mbar_arrive(&y_empty[s]);
+        for (int ch = 0; ch < C / 8; ++ch) res[ch] = __ldg(src + ch);
+      }
       mbar_wait(&a2_full[acc], (i >> 1) & 1);
       tc_fence_after();
       __half* orow = p.out + ((long long)b * p.T + time) * C;
@@ -326,6 +329,10 @@ static void plan_smem(int C, int k, int dil, ResPairParams* p, int* smem_bytes) 
   for (int ns = 2; ns >= 1 && !p->NS; --ns)
     for (int nt = 2; nt >= 1; --nt)
       if (w + ns * p->y_rows8 * 128 + nt * p->t1_rows8 * 128 + fixed <= lim) { p->NS = ns; p->NT = nt; break; }
+  if (const char* f = getenv("VB_RESPAIR_BUFFERS")) {  // debug: "<NS><NT>", e.g. 11 = single buffering
+    if (p->NS >= 1 && f[0] == '1') p->NS = 1;
+    if (p->NT >= 1 && f[1] == '1') p->NT = 1;
+  }
   *smem_bytes = w + p->NS * p->y_rows8 * 128 + p->NT * p->t1_rows8 * 128 + fixed;
 }
 
@@ -354,7 +361,7 @@ extern "C" int vb_resblock_pair(const void* y_in, void* y_out, const void* w1, c
   plan_smem(C, k, dil, &p, &smem);
   p.T = T; p.B = B; p.C = C; p.k = k; p.dil = dil;
   p.slope = slope; p.inv_slope = 1.f / slope;
-  p.b1 = b1; p.b2 = b2; p.out = static_cast<__half*>(y_out);
+  p.b1 = b1; p.b2 = b2; p.in = static_cast<const __half*>(y_in); p.out = static_cast<__half*>(y_out);
   p.n_t = (T + p.R - 1) / p.R;
   p.num_tiles = p.n_t * B;
   CUtensorMap tmY, tmW1, tmW2;
