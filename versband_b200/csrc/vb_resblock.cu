@@ -18,9 +18,9 @@
 //   MMA #2  : conv2 as k taps over t1 (shift j rows) -> acc2 (TMEM); rows >= R of the tile are discarded
 //   epi #2  : acc2 + b2 + x -> lrelu -> fp16 -> global
 // Both convs' weights (2 x k taps x [C x 64] fp16) stay resident in shared memory for the lifetime of the
-// persistent CTA. Warp roles (320 threads): 0 TMA producer, 1 MMA issuer (single thread), 2-5 epilogue #1,
-// 6-9 epilogue #2 (one thread per accumulator row = TMEM lane; no transposes: the A-operand layout of t1 and
-// the channels-last output are both row-contiguous).
+// persistent CTA. Warp roles (576 threads): 0 TMA producer, 1 MMA issuer (single thread), 2-9 epilogue #1,
+// 10-17 epilogue #2 (two warps per TMEM lane quadrant, each thread = one accumulator row x half the channels;
+// no transposes: the A-operand layout of t1 and the channels-last output are both row-contiguous).
 #include <cstdlib>
 #include "vb_internal.h"
 #include "vb_ptx.cuh"
@@ -38,7 +38,7 @@ struct ResPairParams {
 };
 
 template <int C>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(576, 1)
 resblock_pair_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW1,
                      const __grid_constant__ CUtensorMap tmW2, const ResPairParams p) {
   constexpr int KSTEPS = C / 16;
@@ -53,16 +53,16 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
   uint8_t* smem_t = smem_y + p.NS * y_slot;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_t + p.NT * t_slot);
   uint64_t* w_full = bars;           // [1]
-  uint64_t* y_full = bars + 1;       // [2]
-  uint64_t* y_empty = bars + 3;      // [2]
-  uint64_t* a1_full = bars + 5;      // [2]
-  uint64_t* a1_empty = bars + 7;     // [2]
-  uint64_t* t1_full = bars + 9;      // [2]
-  uint64_t* t1_empty = bars + 11;    // [2]
-  uint64_t* a2_full = bars + 13;     // [2]
-  uint64_t* a2_empty = bars + 15;    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
-  float* s_bias = reinterpret_cast<float*>(bars + 20);  // [2][C]
+  uint64_t* y_full = bars + 1;       // [4]  input ring (up to 4 stages: the loop is TMA-latency bound otherwise)
+  uint64_t* y_empty = bars + 5;      // [4]
+  uint64_t* a1_full = bars + 9;      // [2]
+  uint64_t* a1_empty = bars + 11;    // [2]
+  uint64_t* t1_full = bars + 13;     // [2]
+  uint64_t* t1_empty = bars + 15;    // [2]
+  uint64_t* a2_full = bars + 17;     // [2]
+  uint64_t* a2_empty = bars + 19;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  float* s_bias = reinterpret_cast<float*>(bars + 22);  // [2][C]
 
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp_idx == 0 && lane == 0) {
@@ -70,15 +70,17 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
     mbar_init(w_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&y_full[i], 1);
       mbar_init(&y_empty[i], 1);        // conv1's commit (the only reader of the input stage)
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&a1_full[i], 1);
-      mbar_init(&a1_empty[i], 128);
-      mbar_init(&t1_full[i], 128);
+      mbar_init(&a1_empty[i], 256);
+      mbar_init(&t1_full[i], 256);
       mbar_init(&t1_empty[i], 1);
       mbar_init(&a2_full[i], 1);
-      mbar_init(&a2_empty[i], 128);
+      mbar_init(&a2_empty[i], 256);
     }
     fence_barrier_init();
   }
@@ -157,18 +159,26 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
         umma_commit(&a2_full[acc]);
         umma_commit(&t1_empty[tb]);
       };
+      // Issue order: conv1 runs TWO tiles ahead of conv2. The chain MMA1(i) -> epilogue #1 -> MMA2(i) carries
+      // ~3 k cycles of fixed latency (TMEM read, smem write, proxy fence, barrier wake-ups); with conv1 only one
+      // tile ahead the tensor pipe idled for most of it (measured: 3.75 k cycles per tile + 65 per MMA).
       if (n_local > 0) mma1(0);
+      if (n_local > 1) mma1(1);
       for (int i = 0; i < n_local; ++i) {
-        if (i + 1 < n_local) mma1(i + 1);  // conv1 of the next tile runs under this tile's epilogue #1
         mma2(i);
+        if (i + 2 < n_local) mma1(i + 2);
       }
     }
-  } else if (warp_idx < 6) {
-    // ===================== epilogue #1: acc1 -> t1 (shared memory) =====================
-    const int q = warp_idx & 3;
-    const int r = q * 32 + lane;  // accumulator row = t1 row
+  } else if (warp_idx < 10) {
+    // ===================== epilogue #1: acc1 -> t1 (shared memory), 8 warps =====================
+    // Two warps per TMEM lane quadrant, each owning half of the channels of its 32 rows: the epilogues are
+    // instruction-issue bound (long dependent chains, few warps per scheduler), so thread-level parallelism —
+    // not bytes — sets the pace. Activation math runs on packed half2.
+    constexpr int CH = C / 2;            // channels per warp
+    const int q = warp_idx & 3, half = (warp_idx - 2) >> 2;
+    const int r = q * 32 + lane;         // accumulator row = t1 row
     const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
-    const float slope = p.slope;
+    const __half2 slope2 = __float2half2_rn(p.slope);
     int i = 0;
     for (int t = first; t < p.num_tiles; t += step, ++i) {
       const int tb = i % p.NT, acc = i & 1;
@@ -178,88 +188,83 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
       mbar_wait(&a1_full[acc], (i >> 1) & 1);
       mbar_wait(&t1_empty[tb], ((i / p.NT) & 1) ^ 1);
       tc_fence_after();
-      uint8_t* row = smem_t + tb * t_slot + r * 128;
-#pragma unroll
-      for (int c0 = 0; c0 < C; c0 += 32) {
-        uint32_t raw[32];
-        tmem_ld32(tmem_base + acc * C + c0 + lane_sel, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {  // 8 channels = one 16-byte chunk
-          uint32_t w[4];
-#pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            const int c = c0 + ch * 8 + h * 2;
-            float v0 = __uint_as_float(raw[ch * 8 + h * 2]) + s_bias[c];
-            float v1 = __uint_as_float(raw[ch * 8 + h * 2 + 1]) + s_bias[c + 1];
-            v0 = v0 > 0.f ? v0 : v0 * slope;
-            v1 = v1 > 0.f ? v1 : v1 * slope;
-            if (!inside) { v0 = 0.f; v1 = 0.f; }
-            const __half2 hh = vb_f2h2(v0, v1);
-            w[h] = *reinterpret_cast<const uint32_t*>(&hh);
-          }
-          const int chunk = (c0 >> 3) + ch;
-          *reinterpret_cast<uint4*>(row + ((chunk ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-      }
+      const uint32_t row = smem_u32(smem_t + tb * t_slot) + r * 128;
+      uint32_t raw[CH];
+      if (CH == 32) tmem_ld32(tmem_base + acc * C + half * CH + lane_sel, *reinterpret_cast<uint32_t(*)[32]>(raw));
+      else tmem_ld16(tmem_base + acc * C + half * CH + lane_sel, *reinterpret_cast<uint32_t(*)[16]>(raw));
+      tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&a1_empty[acc]);
+      mbar_arrive(&a1_empty[acc]);  // accumulator is in registers
+#pragma unroll
+      for (int ch = 0; ch < CH / 8; ++ch) {  // 8 channels = one 16-byte chunk of the A-operand row
+        uint32_t w[4];
+        const float4 ba = *reinterpret_cast<const float4*>(&s_bias[half * CH + ch * 8]);
+        const float4 bb = *reinterpret_cast<const float4*>(&s_bias[half * CH + ch * 8 + 4]);
+        const float bs[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const __half2 v = vb_f2h2(__uint_as_float(raw[ch * 8 + 2 * h]) + bs[2 * h],
+                                    __uint_as_float(raw[ch * 8 + 2 * h + 1]) + bs[2 * h + 1]);
+          const __half2 a = __hmax2(v, __hmul2(v, slope2));  // leaky relu (slope < 1)
+          w[h] = inside ? *reinterpret_cast<const uint32_t*>(&a) : 0u;  // conv2 zero-pads its input
+        }
+        const int chunk = (half * CH >> 3) + ch;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((chunk ^ (r & 7)) << 4)), "r"(w[0]),
+                     "r"(w[1]), "r"(w[2]), "r"(w[3])
+                     : "memory");
+      }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core's async proxy
       mbar_arrive(&t1_full[tb]);
     }
   } else {
-    // ===================== epilogue #2: acc2 + residual -> global =====================
-    const int q = warp_idx & 3;
+    // ===================== epilogue #2: acc2 + residual -> global, 8 warps =====================
+    constexpr int CH = C / 2;
+    const int q = warp_idx & 3, half = (warp_idx - 10) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
-    const float slope = p.slope, inv_slope = p.inv_slope;
+    const __half2 slope2 = __float2half2_rn(p.slope), inv2 = __float2half2_rn(p.inv_slope);
     int i = 0;
     for (int t = first; t < p.num_tiles; t += step, ++i) {
-      const int s = i % p.NS, acc = i & 1;
+      const int acc = i & 1;
       const int b = t / p.n_t, tt = t - b * p.n_t;
       const int time = tt * p.R + r;
       const bool valid = r < p.R && time < p.T;
       // residual row = the centre of the receptive field, read straight from global memory (L2-resident: the
-      // TMA has just fetched the same lines), issued before the accumulator wait so its latency is hidden
-      uint4 res[C / 8];
+      // TMA has just fetched the same lines), issued before the accumulator wait so its latency is hidden.
+      // (Reading it from the shared-memory input stage raced with the producer's refill of that stage.)
+      uint4 res[CH / 8];
+      const long long goff = ((long long)b * p.T + (valid ? time : 0)) * C + half * CH;
       {
-        const int tc = valid ? time : 0;
-        const uint4* src = reinterpret_cast<const uint4*>(p.in + ((long long)b * p.T + tc) * C);
+        const uint4* src = reinterpret_cast<const uint4*>(p.in + goff);
 #pragma unroll
-        for (int ch = 0; ch < C / 8; ++ch) res[ch] = __ldg(src + ch);
+        for (int ch = 0; ch < CH / 8; ++ch) res[ch] = __ldg(src + ch);
       }
       mbar_wait(&a2_full[acc], (i >> 1) & 1);
       tc_fence_after();
-      __half* orow = p.out + ((long long)b * p.T + time) * C;
+      uint32_t raw[CH];
+      if (CH == 32) tmem_ld32(tmem_base + 2 * C + acc * C + half * CH + lane_sel, *reinterpret_cast<uint32_t(*)[32]>(raw));
+      else tmem_ld16(tmem_base + 2 * C + acc * C + half * CH + lane_sel, *reinterpret_cast<uint32_t(*)[16]>(raw));
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&a2_empty[acc]);
+      uint4* dst = reinterpret_cast<uint4*>(p.out + goff);
 #pragma unroll
-      for (int c0 = 0; c0 < C; c0 += 32) {
-        uint32_t raw[32];
-        tmem_ld32(tmem_base + 2 * C + acc * C + c0 + lane_sel, raw);
-        tmem_ld_wait();
-        if (c0 + 32 >= C) {  // last TMEM read of this tile: release the accumulator
-          tc_fence_before();
-          mbar_arrive(&a2_empty[acc]);
+      for (int ch = 0; ch < CH / 8; ++ch) {
+        const uint32_t rw[4] = {res[ch].x, res[ch].y, res[ch].z, res[ch].w};
+        const float4 ba = *reinterpret_cast<const float4*>(&s_bias[C + half * CH + ch * 8]);
+        const float4 bb = *reinterpret_cast<const float4*>(&s_bias[C + half * CH + ch * 8 + 4]);
+        const float bs[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+        uint32_t w[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const __half2 y = *reinterpret_cast<const __half2*>(&rw[h]);
+          const float2 x = __half22float2(__hmin2(y, __hmul2(y, inv2)));  // undo the leaky relu: x = y < 0 ? y/slope : y
+          const __half2 v = vb_f2h2(__uint_as_float(raw[ch * 8 + 2 * h]) + bs[2 * h] + x.x,
+                                    __uint_as_float(raw[ch * 8 + 2 * h + 1]) + bs[2 * h + 1] + x.y);
+          const __half2 a = __hmax2(v, __hmul2(v, slope2));
+          w[h] = *reinterpret_cast<const uint32_t*>(&a);
         }
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const uint4 rr = res[(c0 >> 3) + ch];
-          const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
-          uint32_t w[4];
-#pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            const int c = c0 + ch * 8 + h * 2;
-            const float2 y = __half22float2(*reinterpret_cast<const __half2*>(&rw[h]));
-            const float x0 = y.x < 0.f ? y.x * inv_slope : y.x;
-            const float x1 = y.y < 0.f ? y.y * inv_slope : y.y;
-            float v0 = __uint_as_float(raw[ch * 8 + h * 2]) + s_bias[C + c] + x0;
-            float v1 = __uint_as_float(raw[ch * 8 + h * 2 + 1]) + s_bias[C + c + 1] + x1;
-            v0 = v0 > 0.f ? v0 : v0 * slope;
-            v1 = v1 > 0.f ? v1 : v1 * slope;
-            const __half2 hh = vb_f2h2(v0, v1);
-            w[h] = *reinterpret_cast<const uint32_t*>(&hh);
-          }
-          if (valid) *reinterpret_cast<uint4*>(orow + c0 + ch * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
+        if (valid) dst[ch] = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
   }
@@ -326,12 +331,12 @@ static void plan_smem(int C, int k, int dil, ResPairParams* p, int* smem_bytes) 
   const int w = 2 * k * C * 128, fixed = 1024 /*align*/ + 1024 /*barriers + bias*/;
   const int lim = 227 * 1024;
   p->NS = p->NT = 0;
-  for (int ns = 2; ns >= 1 && !p->NS; --ns)
+  for (int ns = 4; ns >= 1 && !p->NS; --ns)
     for (int nt = 2; nt >= 1; --nt)
       if (w + ns * p->y_rows8 * 128 + nt * p->t1_rows8 * 128 + fixed <= lim) { p->NS = ns; p->NT = nt; break; }
-  if (const char* f = getenv("VB_RESPAIR_BUFFERS")) {  // debug: "<NS><NT>", e.g. 11 = single buffering
-    if (p->NS >= 1 && f[0] == '1') p->NS = 1;
-    if (p->NT >= 1 && f[1] == '1') p->NT = 1;
+  if (const char* f = getenv("VB_RESPAIR_BUFFERS")) {  // debug: "<NS><NT>" caps, e.g. 21 = 2 input stages, 1 t1 buffer
+    if (p->NS > f[0] - '0' && f[0] >= '1') p->NS = f[0] - '0';
+    if (p->NT > f[1] - '0' && f[1] >= '1') p->NT = f[1] - '0';
   }
   *smem_bytes = w + p->NS * p->y_rows8 * 128 + p->NT * p->t1_rows8 * 128 + fixed;
 }
@@ -384,11 +389,11 @@ extern "C" int vb_resblock_pair(const void* y_in, void* y_out, const void* w1, c
   if (C == 64) {
     e = cudaFuncSetAttribute(resblock_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
-      e = launch_k(resblock_pair_kernel<64>, dim3(grid), dim3(320), smem, static_cast<cudaStream_t>(stream), tmY, tmW1, tmW2, p);
+      e = launch_k(resblock_pair_kernel<64>, dim3(grid), dim3(576), smem, static_cast<cudaStream_t>(stream), tmY, tmW1, tmW2, p);
   } else {
     e = cudaFuncSetAttribute(resblock_pair_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
-      e = launch_k(resblock_pair_kernel<32>, dim3(grid), dim3(320), smem, static_cast<cudaStream_t>(stream), tmY, tmW1, tmW2, p);
+      e = launch_k(resblock_pair_kernel<32>, dim3(grid), dim3(576), smem, static_cast<cudaStream_t>(stream), tmY, tmW1, tmW2, p);
   }
   if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "vb_resblock_pair launch failed: %s", cudaGetErrorString(e));
   return check_launch("vb_resblock_pair");
