@@ -145,6 +145,14 @@ typedef struct vb_gemm_args {
 
 int vb_gemm(const vb_gemm_args* args, void* stream);
 
+/* Acoustic stem of the DiT (Embedding -> Conv1d k -> LeakyReLU -> AvgPool1d(2), midi + beats summed;
+ * vocal2music_moe.py:336-350,388-393) as row gathers: tab_x [k][Vx][D] = W[:, :, tap] . emb[v] precomputed at
+ * pack time (the vocabularies have 130 / 3 entries), out[b*Tpool + t] = pooled sum written as the split GEMM
+ * operand [hi | hi | lo] (3*D columns, fp16 or tf32-rounded fp32) of the following 1x1 final_proj. */
+int vb_stem_gather(const int64_t* midi, const int64_t* beats, const float* tab_m, const float* tab_b,
+                   const float* bias_m, const float* bias_b, int Vm, int Vb, int k, int B, int Tm, int Tpool, int D,
+                   float slope, void* out, int out_is_f32, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * vb_resblock_pair — one HiFi-GAN ResBlock1 conv pair, x' = x + c2(lrelu(c1_{dil}(lrelu(x)) + b1)) + b2
  * (vocoder/hifigan/modules/hifigan.py:51-58), in ONE persistent tcgen05 kernel. Activations are fp16 in the

@@ -45,7 +45,9 @@ def test_prepare_matches_oracle_conditioning(engine, weights):
     ref = R.dit_conditioning(weights, {"c_crossattn": cap, "c_concat": {"midi": midi, "beats": beats}})
     cond = engine.prepare(midi.to(DEV), beats.to(DEV), cap.to(DEV), T)
     torch.cuda.synchronize()
-    assert rel(cond.acoustic.view(B, T, -1), ref["acoustic"]) < 1e-2
+    e_ac = rel(cond.acoustic.view(B, T, -1), ref["acoustic"])
+    print(f"acoustic stem (exact tables + split-precision final_proj) vs oracle: {e_ac:.2e}")
+    assert e_ac < 2e-5
     assert rel(cond.caption, ref["caption"]) < 2e-2
     assert rel(cond.cap_emb, ref["cap_emb"]) < 2e-2
 
@@ -67,7 +69,7 @@ def test_forward_vs_oracle(engine, weights, B, T):
             total += got.numel()
     rate = agree / total
     print(f"router agreement {agree}/{total} = {rate:.4f}; v rel err {rel(v, v_ref):.3e}")
-    assert rate > 0.97
+    assert agree >= total - 1  # (exact-index assertion with margin analysis: tests/test_fullsize_gpu.py)
     # tokens whose routing agrees in every block must match to fp16 accuracy
     ok = torch.ones(B * T, dtype=torch.bool)
     for k in range(4):
@@ -75,7 +77,7 @@ def test_forward_vs_oracle(engine, weights, B, T):
         ok &= aux[k]["idx_a"].cpu().long() == aux_ref[k]["ac_idx"]
     diff = (v.cpu() - v_ref).abs().permute(0, 2, 1).reshape(B * T, -1).max(-1)[0]
     peak = float(v_ref.abs().max())
-    assert float(diff.median()) / peak < 1e-2
+    assert float(diff.median()) / peak < 1e-3 and rel(v, v_ref) < 2e-3
 
 
 def test_golden_fixture_of_live_reference(engine, weights):
@@ -91,9 +93,9 @@ def test_golden_fixture_of_live_reference(engine, weights):
         agree += int((aux[k]["idx_a"].cpu().to(torch.int16) == gd[f"ac_idx_{k}"]).sum())
         total += 2 * B * T
     print(f"golden: router agreement {agree}/{total}, v rel err {rel(v, gd['v']):.3e}")
-    assert agree / total > 0.97
+    assert agree >= total - 1
     diff = (v.cpu() - gd["v"]).abs().permute(0, 2, 1).reshape(B * T, -1).max(-1)[0]
-    assert float(diff.median()) / float(gd["v"].abs().max()) < 1e-2
+    assert float(diff.median()) / float(gd["v"].abs().max()) < 1e-3 and rel(v, gd["v"]) < 2e-3
 
 
 # ---------------------------------------------------------------------------------------------

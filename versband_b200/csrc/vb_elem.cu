@@ -160,6 +160,72 @@ __global__ void pool2_sum_kernel(const float* __restrict__ a, const float* __res
   }
 }
 
+// Acoustic stem without a GEMM: Embedding -> Conv1d(k, pad k/2) -> LeakyReLU -> AvgPool1d(2), for the midi and
+// the beats stream, summed (vocal2music_moe.py:336-350,388-393). The embedding tables have only Vm = 130 / Vb = 3
+// rows, so conv(emb[idx])[t] = bias + sum_tap M[tap][idx[t + tap - pad]] with M[tap][v] = W[:, :, tap] . emb[v]
+// precomputed at pack time in fp64: the 2 x 9.3 GMAC convolutions become 2 x k row gathers per time step, exact
+// to fp32 rounding. The pooled sum is written as the split operand [hi | hi | lo] (hi = operand-precision value,
+// lo = residue) of the 1x1 final_proj GEMM against [W_hi | W_lo | W_hi], which recovers fp32-class accuracy from
+// 11-bit tensor-core operands; the acoustic gate logits derived from it then match the reference to ~1e-6.
+__global__ void stem_gather_kernel(const long long* __restrict__ midi, const long long* __restrict__ beats,
+                                   const float* __restrict__ tab_m, const float* __restrict__ tab_b,
+                                   const float* __restrict__ bias_m, const float* __restrict__ bias_b, int Vm, int Vb,
+                                   int k, int Tm, int Tpool, int D, float slope, __half* __restrict__ out16,
+                                   float* __restrict__ out32, long long total) {
+  pdl_sync();
+  const int pad = k / 2, D4 = D / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int d4 = (int)(i % D4);
+    const long long bt = i / D4;
+    const int tp = (int)(bt % Tpool), b = (int)(bt / Tpool);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {  // stream: midi, beats
+      const long long* idx = (s ? beats : midi) + (long long)b * Tm;
+      const float* tab = s ? tab_b : tab_m;
+      const int V = s ? Vb : Vm;
+      const float4 bs = __ldg(reinterpret_cast<const float4*>(s ? bias_b : bias_m) + d4);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {  // the two time steps of the pooling window
+        const int t = 2 * tp + u;
+        float4 v = bs;
+        for (int j = 0; j < k; ++j) {
+          const int tt = t + j - pad;
+          if (tt < 0 || tt >= Tm) continue;
+          long long id = idx[tt];
+          id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+          const float4 m = __ldg(reinterpret_cast<const float4*>(tab + ((long long)j * V + id) * D) + d4);
+          v.x += m.x; v.y += m.y; v.z += m.z; v.w += m.w;
+        }
+        acc.x += 0.5f * (v.x > 0.f ? v.x : v.x * slope);
+        acc.y += 0.5f * (v.y > 0.f ? v.y : v.y * slope);
+        acc.z += 0.5f * (v.z > 0.f ? v.z : v.z * slope);
+        acc.w += 0.5f * (v.w > 0.f ? v.w : v.w * slope);
+      }
+    }
+    const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+    const long long row = bt * 3 * D + 4 * d4;
+    if (out16) {
+      __half hi[4], lo[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { hi[c] = vb_f2h(a[c]); lo[c] = vb_f2h(a[c] - __half2float(hi[c])); }
+      *reinterpret_cast<uint2*>(out16 + row) = *reinterpret_cast<const uint2*>(hi);
+      *reinterpret_cast<uint2*>(out16 + row + D) = *reinterpret_cast<const uint2*>(hi);
+      *reinterpret_cast<uint2*>(out16 + row + 2 * D) = *reinterpret_cast<const uint2*>(lo);
+    } else {
+      float hi[4], lo[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {  // TF32 grid: 10-bit mantissa, round to nearest
+        hi[c] = __uint_as_float((__float_as_uint(a[c]) + 0x1000u) & ~0x1FFFu);
+        lo[c] = a[c] - hi[c];
+      }
+      *reinterpret_cast<float4*>(out32 + row) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(out32 + row + D) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(out32 + row + 2 * D) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
 // GroupNorm statistics over channels-last x[B, T, C]: per (b, group) mean and rstd
 // (autoencoder1d.py:165-166: 32 groups, eps 1e-6). Two launches, deterministic: gn_partial splits T
 // into `nsplit` slabs (grid = G x B x nsplit, coalesced rows, fp64 accumulation), gn_finish combines.
@@ -387,4 +453,18 @@ __global__ void timestamp_kernel(unsigned long long* slot) {
 extern "C" int vb_timestamp(uint64_t* slot, void* stream) {
   vb::timestamp_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<unsigned long long*>(slot));
   return vb::check_launch("vb_timestamp");
+}
+
+extern "C" int vb_stem_gather(const int64_t* midi, const int64_t* beats, const float* tab_m, const float* tab_b,
+                              const float* bias_m, const float* bias_b, int Vm, int Vb, int k, int B, int Tm, int Tpool,
+                              int D, float slope, void* out, int out_is_f32, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_EW, stream);
+  if (!midi || !beats || !tab_m || !tab_b || !bias_m || !bias_b || !out || D % 4 || k < 1 || Tpool * 2 > Tm)
+    return set_error(VB_ERR_INVALID, "vb_stem_gather: bad arguments");
+  const long long total = (long long)B * Tpool * (D / 4);
+  launch_k(stem_gather_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+           reinterpret_cast<const long long*>(midi), reinterpret_cast<const long long*>(beats), tab_m, tab_b, bias_m, bias_b,
+           Vm, Vb, k, Tm, Tpool, D, slope, out_is_f32 ? nullptr : static_cast<__half*>(out),
+           out_is_f32 ? static_cast<float*>(out) : nullptr, total);
+  return check_launch("vb_stem_gather");
 }

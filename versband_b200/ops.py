@@ -289,6 +289,14 @@ def conv_post(x_fp16, w, bias: float, B, T, Cc, k, wav) -> None:
     _call("vb_conv_post", _ptr(x_fp16), _ptr(w), bias, B, T, Cc, k, _ptr(wav))
 
 
+def stem_gather(midi, beats, tab_m, tab_b, bias_m, bias_b, *, k, Tpool, slope, out) -> None:
+    B, _, Tm = midi.shape
+    D = tab_m.shape[-1]
+    assert out.shape[-1] == 3 * D and midi.dtype == torch.int64 and beats.dtype == torch.int64
+    _call("vb_stem_gather", _ptr(midi), _ptr(beats), _ptr(tab_m), _ptr(tab_b), _ptr(bias_m), _ptr(bias_b),
+          tab_m.shape[1], tab_b.shape[1], k, B, Tm, Tpool, D, slope, _ptr(out), int(out.dtype == torch.float32))
+
+
 def resblock_pair_fits(C: int, k: int, dil: int) -> bool:
     return bool(_lib.lib().vb_resblock_pair_fits(C, k, dil))
 
