@@ -340,6 +340,36 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
     ms_step, ms_samp, ms_vae, ms_voc, ms_e2e = [float(v) for v in t]
 
+    # ---- BASELINE configs[3] ("batch 32 over 8 GPUs" = 4 clips per GPU): same pipeline, 4 clips per rank ----
+    cfg4 = None
+    if not args.no_config4 and B != 4:
+        B4 = 4
+        lst = [[], [], [], [], []]
+        for c in range(B4):
+            for l_, t_ in zip(lst, synth.dit_inputs(1, T_LAT, seed=5000 + rank * B4 + c)):
+                l_.append(t_)
+        d4 = [torch.cat(l_, 0).to(dev) for l_ in (lst[1], lst[2], lst[3], lst[4], lst[0])]
+        gen4 = [torch.Generator(device=dev).manual_seed(9000 + rank * B4 + c) for c in range(B4)]
+        for _ in range(3):
+            pipe.generate(d4[0], d4[1], d4[2], d4[3], x0=d4[4], generator=gen4)
+        barrier()
+        ms4 = 0.0
+        n4 = max(3, args.steps // 2)
+        for _ in range(n4):
+            flush.fill_(1)
+            ev = {}
+            pipe.generate(d4[0], d4[1], d4[2], d4[3], x0=d4[4], generator=gen4, events=ev)
+            torch.cuda.synchronize()
+            ms4 += ev["start"].elapsed_time(ev["end"])
+        barrier()
+        t4 = torch.tensor([ms4 / n4], device=dev, dtype=torch.float64)
+        if use_dist:
+            dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+        cfg4 = {"workload": "BASELINE configs[3]: 4 clips per GPU (batch 32 at 8 GPUs), same pipeline, device-timed, max over ranks",
+                "clips_per_gpu": B4, "global_clips": B4 * world, "steps": n4, "ms_per_step": float(t4[0]),
+                "value": B4 * world * CLIP_SECONDS / (float(t4[0]) * 1e-3), "unit": "x real-time (24 kHz audio-s / wall-s)"}
+        del d4
+
     # ---- roofline (rank 0): every time below is a CUDA-event interval of the TIMED (graph-replay) region ----
     roof, launches, fam = None, None, None
     if rank == 0:
@@ -444,7 +474,7 @@ def run_ours(args):
                              else "pinned host -> H2D -> generate -> D2H")},
             "gpu_launches": int(launches) * args.steps * 2 if launches else None,
             "gpu_launches_per_step": int(launches) if launches else None,
-            "roofline": roof, "cpu_baseline": cpu, "clocks": clk, "clip0_wav_sha1": clip0_sha1,
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clk, "clip0_wav_sha1": clip0_sha1, "config4": cfg4,
         }
         print(json.dumps(line))
     if use_dist:
@@ -459,6 +489,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=1, help="clips per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config4", action="store_true", help="skip the extra 4-clips-per-GPU measurement (BASELINE configs[3])")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "tf32"],
                     help="GEMM operand format of the DiT: fp16 (default) or fp32-as-TF32 (twice the operand bytes)")
     args = ap.parse_args()

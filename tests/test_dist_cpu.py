@@ -29,8 +29,11 @@ def _worker(rank, world, port, n_clips, q):
         return m.float().sum((1, 2))[:, None] + c.sum((1, 2))[:, None] * torch.ones(1, 5)
 
     out = run_data_parallel(fake_pipeline, [midi, cap] if rank == 0 else None, n_clips)
+    out = out.clone() if rank == 0 else None  # (the gather buffer is reused by the next step)
+    # second step through the cached exchange: no metadata handshake, same buffers
+    out2 = run_data_parallel(fake_pipeline, [midi + 1, cap] if rank == 0 else None, n_clips)
     if rank == 0:
-        q.put(out)
+        q.put((out, out2.clone()))
     dist.destroy_process_group()
 
 
@@ -41,7 +44,7 @@ def test_scatter_compute_gather_world2():
         procs = [ctx.Process(target=_worker, args=(r, 2, 29611 + n_clips, n_clips, q)) for r in range(2)]
         for p in procs:
             p.start()
-        out = q.get()
+        out, out2 = q.get()
         for p in procs:
             p.join(60)
             assert p.exitcode == 0
@@ -50,3 +53,4 @@ def test_scatter_compute_gather_world2():
         cap = torch.randn(n_clips, 4, 8, generator=g)
         ref = midi.float().sum((1, 2))[:, None] + cap.sum((1, 2))[:, None] * torch.ones(1, 5)
         assert torch.allclose(out, ref)
+        assert torch.allclose(out2, ref + 16.0)
