@@ -36,7 +36,8 @@ enum {
   VB_ACT_SILU = 1,     /* x*sigmoid(x): adaLN SiLU, VAE swish (autoencoder1d.py:168-170) */
   VB_ACT_LRELU = 2,    /* leaky relu with slope (hifigan.py:8,53; vocal2music_moe.py:342) */
   VB_ACT_GELU_ERF = 3, /* exact GELU (flag_large_dit_moe.py:154) */
-  VB_ACT_TANH = 4      /* hifigan.py:141 */
+  VB_ACT_TANH = 4,     /* hifigan.py:141 */
+  VB_ACT_LOG10 = 5     /* log10(max(x, act_slope)): mel dynamic-range compression, preprocess/NAT_mel.py:25-26 */
 };
 
 /* vb_gemm epilogue modes */
@@ -97,7 +98,9 @@ typedef struct vb_gemm_args {
   /* ---- epilogue --------------------------------------------------------------------- */
   int32_t mode;  /* VB_EPI_* */
   float alpha;   /* v = acc * alpha */
-  int32_t swiglu; /* 1: columns come in (w1,w3) pairs; v[n/2] = silu(v[2i]) * v[2i+1] */
+  int32_t swiglu; /* gated unit over (w1,w3) column pairs: 1 = v[n/2] = silu(v[2i]) * v[2i+1] (SwiGLU FeedForward);
+                     2 = gelu_new(v[2i]) * v[2i+1] (T5 v1.1 / FLAN-T5 DenseGatedActDense);
+                     3 = sqrt(v[2i]^2 + v[2i+1]^2 + 1e-9): magnitude of interleaved (re, im) STFT columns */
   const float* bias; /* v += bias[n + g1*bias_g1 + tile_group*bias_tile] */
   int64_t bias_g1, bias_tile;
   int32_t act;
@@ -152,6 +155,18 @@ int vb_gemm(const vb_gemm_args* args, void* stream);
 int vb_stem_gather(const int64_t* midi, const int64_t* beats, const float* tab_m, const float* tab_b,
                    const float* bias_m, const float* bias_b, int Vm, int Vb, int k, int B, int Tm, int Tpool, int D,
                    float slope, void* out, int out_is_f32, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Formats either side of the path
+ * vb_wave_prepare: waveform fp32 [B, n] -> clamp to [-1, 1], reflect-pad `pad` samples each side
+ *   (preprocess/NAT_mel.py:62-66) and split into fp16 planes out[b] = [hi | lo | hi], each `plane` samples
+ *   (hi + lo = the sample to ~3e-8): the A operand of the windowed-DFT GEMM, whose three "taps" (plane apart)
+ *   against [W_hi | W_hi | W_lo] give fp32-class STFT accuracy from fp16 tensor-core operands.
+ * vb_loudness_pcm16: per clip rms -> gain to `target_db` dBFS (scripts/test_final.py:342-347) -> int16 PCM
+ *   (x * 32767, round to nearest even, saturating), scratch = B * 64 floats.
+ * ------------------------------------------------------------------------------------------ */
+int vb_wave_prepare(const float* wav, int B, int64_t n, int pad, int64_t plane, void* out_fp16, void* stream);
+int vb_loudness_pcm16(const float* wav, int B, int64_t n, float target_db, float* scratch, int16_t* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * vb_resblock_pair — one HiFi-GAN ResBlock1 conv pair, x' = x + c2(lrelu(c1_{dil}(lrelu(x)) + b1)) + b2

@@ -19,7 +19,8 @@ def install_compat() -> str:
     # shadow packages imported BEFORE the reference checkout was put on sys.path extended their __path__ over
     # what existed then: refresh them so `ldm.models.diffusion...`, `vocoder.hifigan.modules...` keep resolving
     from pkgutil import extend_path
-    for name in ("ldm", "ldm.models", "ldm.modules", "ldm.modules.diffusionmodules", "vocoder", "vocoder.hifigan"):
+    for name in ("ldm", "ldm.models", "ldm.modules", "ldm.modules.diffusionmodules", "ldm.modules.encoders", "vocoder",
+                 "vocoder.hifigan"):
         mod = sys.modules.get(name)
         if mod is not None and hasattr(mod, "__path__"):
             mod.__path__ = extend_path(list(mod.__path__), name)

@@ -226,6 +226,65 @@ __global__ void stem_gather_kernel(const long long* __restrict__ midi, const lon
   }
 }
 
+// waveform -> [hi | lo | hi] fp16 planes with reflect padding (see include/versband.h: vb_wave_prepare)
+__global__ void wave_prepare_kernel(const float* __restrict__ wav, long long n, int pad, long long plane,
+                                    __half* __restrict__ out) {
+  pdl_sync();
+  const int b = blockIdx.y;
+  const float* w = wav + (long long)b * n;
+  __half* o = out + (long long)b * 3 * plane;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < plane; i += (long long)gridDim.x * blockDim.x) {
+    long long j = i - pad;  // reflect (no edge repeat): -1 -> 1, n -> n-2
+    if (j < 0) j = -j;
+    if (j >= n) j = 2 * (n - 1) - j;
+    float v = 0.f;
+    if (i < n + 2 * pad && j >= 0 && j < n) v = fminf(fmaxf(w[j], -1.f), 1.f);
+    const __half hi = vb_f2h(v);
+    const __half lo = vb_f2h(v - __half2float(hi));
+    o[i] = hi;
+    o[plane + i] = lo;
+    o[2 * plane + i] = hi;
+  }
+}
+
+// loudness normalisation + PCM16: partial sums of squares (64 per clip), then gain and conversion
+__global__ void loudness_partial_kernel(const float* __restrict__ wav, long long n, float* __restrict__ part) {
+  pdl_sync();
+  const int b = blockIdx.y;
+  const float* w = wav + (long long)b * n;
+  double acc = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) acc += (double)w[i] * w[i];
+  __shared__ double sh[256];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[b * 64 + blockIdx.x] = (float)sh[0];
+}
+__global__ void loudness_apply_kernel(const float* __restrict__ wav, long long n, const float* __restrict__ part,
+                                      float target_db, short* __restrict__ out) {
+  pdl_sync();
+  const int b = blockIdx.y;
+  __shared__ float s_gain;
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int k = 0; k < 64; ++k) tot += part[b * 64 + k];
+    const float rms = sqrtf((float)(tot / (double)n));
+    const float loud = 20.f * log10f(rms);
+    s_gain = powf(10.f, (target_db - loud) / 20.f);
+  }
+  __syncthreads();
+  const float g = s_gain * 32767.f;
+  const float* w = wav + (long long)b * n;
+  short* o = out + (long long)b * n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = fminf(fmaxf(rintf(w[i] * g), -32768.f), 32767.f);
+    o[i] = (short)v;
+  }
+}
+
 // GroupNorm statistics over channels-last x[B, T, C]: per (b, group) mean and rstd
 // (autoencoder1d.py:165-166: 32 groups, eps 1e-6). Two launches, deterministic: gn_partial splits T
 // into `nsplit` slabs (grid = G x B x nsplit, coalesced rows, fp64 accumulation), gn_finish combines.
@@ -467,4 +526,26 @@ extern "C" int vb_stem_gather(const int64_t* midi, const int64_t* beats, const f
            Vm, Vb, k, Tm, Tpool, D, slope, out_is_f32 ? nullptr : static_cast<__half*>(out),
            out_is_f32 ? static_cast<float*>(out) : nullptr, total);
   return check_launch("vb_stem_gather");
+}
+
+extern "C" int vb_wave_prepare(const float* wav, int B, int64_t n, int pad, int64_t plane, void* out_fp16, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_EW, stream);
+  if (!wav || !out_fp16 || B <= 0 || n <= pad || pad < 0 || plane < n + 2 * pad || plane % 8)
+    return set_error(VB_ERR_INVALID, "vb_wave_prepare: bad arguments (plane >= n + 2*pad, multiple of 8; n > pad)");
+  launch_k(wave_prepare_kernel, dim3(grid_for(plane, 256) > 1024 ? 1024 : grid_for(plane, 256), B), dim3(256), 0,
+           static_cast<cudaStream_t>(stream), wav, (long long)n, pad, (long long)plane, static_cast<__half*>(out_fp16));
+  return check_launch("vb_wave_prepare");
+}
+
+extern "C" int vb_loudness_pcm16(const float* wav, int B, int64_t n, float target_db, float* scratch, int16_t* out,
+                                 void* stream) {
+  vb::ProfScope prof_scope(vb::PK_EW, stream);
+  if (!wav || !scratch || !out || B <= 0 || n <= 0) return set_error(VB_ERR_INVALID, "vb_loudness_pcm16: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  launch_k(loudness_partial_kernel, dim3(64, B), dim3(256), 0, s, wav, (long long)n, scratch);
+  int rc = check_launch("vb_loudness_pcm16");
+  if (rc) return rc;
+  launch_k(loudness_apply_kernel, dim3(256, B), dim3(256), 0, s, wav, (long long)n, static_cast<const float*>(scratch),
+           target_db, reinterpret_cast<short*>(out));
+  return check_launch("vb_loudness_pcm16");
 }

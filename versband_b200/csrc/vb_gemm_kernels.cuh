@@ -29,6 +29,7 @@ __device__ __forceinline__ float act_one(float v, float slope) {
   if (ACT == VB_ACT_LRELU) return v > 0.f ? v : v * slope;
   if (ACT == VB_ACT_GELU_ERF) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
   if (ACT == VB_ACT_TANH) return tanhf(v);
+  if (ACT == VB_ACT_LOG10) return log10f(fmaxf(v, slope));  // slope = clip value (dynamic range compression)
   return v;
 }
 template <int ACT, int N>
@@ -43,6 +44,7 @@ __device__ __forceinline__ void apply_act_all(float (&v)[N], int act, float slop
     case VB_ACT_LRELU: act_loop<VB_ACT_LRELU>(v, slope, pre); break;
     case VB_ACT_GELU_ERF: act_loop<VB_ACT_GELU_ERF>(v, slope, pre); break;
     case VB_ACT_TANH: act_loop<VB_ACT_TANH>(v, slope, pre); break;
+    case VB_ACT_LOG10: act_loop<VB_ACT_LOG10>(v, slope, pre); break;
     default:
       if (pre != 1.f) act_loop<VB_ACT_NONE>(v, slope, pre);
       break;
@@ -177,6 +179,16 @@ __device__ __forceinline__ void epi_transpose(const uint32_t (&raw)[32], uint32_
 }
 
 __device__ __forceinline__ float silu_mul(float a, float b) { return __fdividef(a, 1.f + __expf(-a)) * b; }
+// gated-GELU of T5 v1.1 / FLAN-T5 ("gelu_new": tanh approximation) x gate: DenseGatedActDense
+__device__ __forceinline__ float gelu_new_mul(float a, float b) {
+  const float u = 0.7978845608028654f * (a + 0.044715f * a * a * a);
+  return 0.5f * a * (1.f + tanhf(u)) * b;
+}
+// kind 1 = SwiGLU (silu), 2 = GEGLU (gelu_new), 3 = magnitude of a (re, im) pair: sqrt(re^2 + im^2 + 1e-9) (STFT, NAT_mel.py:75)
+__device__ __forceinline__ float glu_mul(float a, float b, int kind) {
+  if (kind == 3) return sqrtf(fmaf(a, a, fmaf(b, b, 1e-9f)));
+  return kind == 2 ? gelu_new_mul(a, b) : silu_mul(a, b);
+}
 
 // v[j] (op)= src[j] for the 32 columns of this chunk; vector path when the chunk is full & aligned
 template <bool MUL>
@@ -216,8 +228,7 @@ __device__ __forceinline__ void epilogue_rowwise(const GemmKParams& p, float (&v
     float o[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float a = v[2 * j], b = v[2 * j + 1];
-      o[j] = (a / (1.f + __expf(-a))) * b * rs;
+      o[j] = glu_mul(v[2 * j], v[2 * j + 1], p.swiglu) * rs;
     }
     if (p.out_fp16 && p.outb_f32) {
       float* dstf = reinterpret_cast<float*>(p.out_fp16) + g1 * p.outb_g1 + g2 * p.outb_g2 + orow * p.outb_ld + n_out0;
@@ -402,8 +413,8 @@ __device__ __forceinline__ void epilogue_generic(const GemmKParams& p, float (&v
     float o[16];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      o[2 * i] = silu_mul(v[4 * i], v[4 * i + 1]) * rows.rs[i];
-      o[2 * i + 1] = silu_mul(v[4 * i + 2], v[4 * i + 3]) * rows.rs[i];
+      o[2 * i] = glu_mul(v[4 * i], v[4 * i + 1], p.swiglu) * rows.rs[i];
+      o[2 * i + 1] = glu_mul(v[4 * i + 2], v[4 * i + 3], p.swiglu) * rows.rs[i];
     }
     if (p.out_fp16 && p.outb_f32) {
       float* dst = reinterpret_cast<float*>(p.out_fp16) + g1 * p.outb_g1 + g2 * p.outb_g2 + no;

@@ -514,6 +514,56 @@ class HifiGAN(nn.Module):
 
 
 # ==========================================================================================
+# Text conditioning: FLAN-T5 encoder in front of the path
+# ==========================================================================================
+class FrozenTextVocalEmbedder(nn.Module):
+    """`cond_stage_config` target of configs/vocal2music.yaml (ldm/modules/encoders/modules.py:194-233): tokenise
+    the captions to `max_length` tokens (padding="max_length", no attention mask is passed on) and return the T5
+    encoder's last hidden state together with the untouched 'acoustic' / 'name' entries. Tokeniser and checkpoint
+    loading stay `transformers` (host side); the encoder itself runs on versband_b200.t5.T5EncoderEngine."""
+
+    def __init__(self, version="google/t5-v1_1-large", device="cuda", max_length=77, freeze=True,
+                 tokenizer=None, hf_model=None):
+        super().__init__()
+        if tokenizer is None or hf_model is None:
+            from transformers import T5EncoderModel, T5Tokenizer
+            tokenizer = tokenizer or T5Tokenizer.from_pretrained(version)
+            hf_model = hf_model or T5EncoderModel.from_pretrained(version)
+        self.tokenizer = tokenizer
+        self.transformer = hf_model.eval()  # parameter owner (state_dict keys as in the reference)
+        for p_ in self.transformer.parameters():
+            p_.requires_grad = False
+        self.device = device
+        self.max_length = max_length
+        self._engine = None
+
+    def freeze(self):
+        self.transformer = self.transformer.eval()
+        for p_ in self.parameters():
+            p_.requires_grad = False
+
+    def engine(self):
+        if self._engine is None:
+            from .t5 import T5EncoderEngine
+            cfg = self.transformer.config
+            self._engine = T5EncoderEngine(self.transformer.state_dict(), num_layers=cfg.num_layers, num_heads=cfg.num_heads,
+                                           d_kv=cfg.d_kv, num_buckets=cfg.relative_attention_num_buckets,
+                                           max_distance=getattr(cfg, "relative_attention_max_distance", 128),
+                                           eps=cfg.layer_norm_epsilon, device=self.device)
+        return self._engine
+
+    @torch.no_grad()
+    def forward(self, cond, device=None, return_cuda=True):
+        enc = self.tokenizer(text=cond["caption"], truncation=True, max_length=self.max_length, return_length=True,
+                             return_overflowing_tokens=False, padding="max_length", return_tensors="pt")
+        z = self.engine().forward(enc["input_ids"])
+        return {"caption": z if return_cuda else z.cpu(), "acoustic": cond["acoustic"], "name": cond["name"]}
+
+    def encode(self, text):
+        return self(text)
+
+
+# ==========================================================================================
 # Sampler glue with the reference's call surface (cfm1_audio_sampler.py:87-116)
 # ==========================================================================================
 class CFMSampler:

@@ -10,7 +10,7 @@ import torch
 from . import _lib
 from ._lib import AttnArgs, GemmArgs
 
-ACT_NONE, ACT_SILU, ACT_LRELU, ACT_GELU, ACT_TANH = 0, 1, 2, 3, 4
+ACT_NONE, ACT_SILU, ACT_LRELU, ACT_GELU, ACT_TANH, ACT_LOG10 = 0, 1, 2, 3, 4, 5
 EPI_GENERIC, EPI_QKV_ROPE, EPI_ROUTE = 0, 1, 2
 
 
@@ -111,7 +111,7 @@ def gemm_args(a: torch.Tensor, b: torch.Tensor, *, M: Optional[int] = None, N: O
     args.b_c2_g1, args.b_c2_g2, args.b_c2_tile = b_c2
     args.bn = bn
     args.tile_group, args.m_tiles_used, args.tile_row0 = _ptr(tile_group), _ptr(m_tiles_used), _ptr(tile_row0)
-    args.mode, args.alpha, args.swiglu = mode, alpha, int(swiglu)
+    args.mode, args.alpha, args.swiglu = mode, alpha, int(swiglu)  # 1 = SwiGLU, 2 = GEGLU (gelu_new)
     _check_f32(bias, "bias"); _check_f32(row_scale, "row_scale"); _check_f32(gate, "gate")
     _check_f32(residual, "residual"); _check_f32(out_f32, "out_f32")
     args.bias, args.bias_g1, args.bias_tile = _ptr(bias), bias_g1, bias_tile
@@ -310,6 +310,17 @@ def resblock_pair(y_in, y_out, w1, w2, b1, b2, *, B, T, C, k, dil, slope) -> Non
 def mrf_combine(rs, out, *, neg: float, scale: float, slope_out: float) -> None:
     rs = list(rs) + [None] * (3 - len(rs))
     _call("vb_mrf_combine", _ptr(rs[0]), _ptr(rs[1]), _ptr(rs[2]), neg, scale, slope_out, _ptr(out), out.numel())
+
+
+def wave_prepare(wav, out_fp16, *, pad: int, plane: int) -> None:
+    B, n = wav.shape
+    _call("vb_wave_prepare", _ptr(wav), B, n, pad, plane, _ptr(out_fp16))
+
+
+def loudness_pcm16(wav, out_i16, *, target_db: float) -> None:
+    B, n = wav.shape
+    scratch = torch.empty(B * 64, device=wav.device, dtype=torch.float32)
+    _call("vb_loudness_pcm16", _ptr(wav), B, n, target_db, _ptr(scratch), _ptr(out_i16))
 
 
 def mean_tokens(x, out) -> None:
