@@ -245,7 +245,35 @@ typedef struct vb_attn_args {
 
 int vb_attn_fused(const vb_attn_args* args, void* stream);
 
-/* sizeof() of the public structs as compiled (ABI self-check for bindings): 0 = vb_gemm_args, 1 = vb_attn_args */
+/* ------------------------------------------------------------------------------------------
+ * Model-level entry point: the whole HiFi-GAN generator (vocoder/hifigan/modules/hifigan.py:126-143) as ONE call
+ * that issues the launch sequence from C++ (vb_model.cu). The caller supplies packed weights as device pointers
+ * (layouts of versband_b200/vocoder.py:_pack — conv weights [Cout, k * ceil64(Cin)] fp16 tap-major with
+ * weight-norm folded, transposed convs as u polyphase filters [u, Cout, Q * ceil64(Cin)], biases fp32), the input
+ * mel fp32 [B, n_mel, T], the output wav fp32 [B, T * prod(rates)] and a workspace of vb_voc_workspace_bytes().
+ * ------------------------------------------------------------------------------------------ */
+#define VB_VOC_MAX_STAGES 8
+typedef struct vb_voc_desc {
+  int32_t n_mel, c0, pre_k, n_stages, n_kernels, post_k;
+  float lrelu, post_b;
+  int32_t rates[VB_VOC_MAX_STAGES], up_k[VB_VOC_MAX_STAGES], up_cout[VB_VOC_MAX_STAGES];
+  int32_t rb_k[3], n_dil[3], rb_d[3][4]; /* resblock kernel sizes and their dilation lists (ResBlock1) */
+  const void* pre_w;
+  const float* pre_b;
+  const void* up_w[VB_VOC_MAX_STAGES];
+  const float* up_b[VB_VOC_MAX_STAGES];
+  const void* rb_w1[VB_VOC_MAX_STAGES][3][4]; /* [stage][kernel][pair]: convs1 (dilated) */
+  const void* rb_w2[VB_VOC_MAX_STAGES][3][4]; /*                        convs2 (dilation 1) */
+  const float* rb_b1[VB_VOC_MAX_STAGES][3][4];
+  const float* rb_b2[VB_VOC_MAX_STAGES][3][4];
+  const float* post_w; /* [post_k, C_last] fp32 */
+} vb_voc_desc;
+int64_t vb_voc_workspace_bytes(const vb_voc_desc* d, int B, int T);
+int vb_voc_forward(const vb_voc_desc* d, const float* mel, int B, int T, float* wav, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+
+/* sizeof() of the public structs as compiled (ABI self-check for bindings): 0 = vb_gemm_args, 1 = vb_attn_args,
+ * 2 = vb_voc_desc */
 int vb_sizeof(int which);
 /* number of kernels this library has launched in this process */
 long long vb_launch_count(void);

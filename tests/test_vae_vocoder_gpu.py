@@ -92,3 +92,13 @@ def test_hifigan_vs_oracle_batch(voc, voc_sd):
     e = rel(wav, ref)
     print("hifigan vs oracle:", e)
     assert e < 6e-3
+
+
+def test_hifigan_c_entry_point_equals_python_launch_sequence(voc):
+    """vb_voc_forward (the whole generator issued from C++ through one C-ABI call) vs the same launches from Python."""
+    mel = synth.mel_input(2, 64, seed=21).cuda()
+    a = voc.forward(mel)
+    b = voc.forward_py(mel)
+    torch.cuda.synchronize()
+    assert a.shape == b.shape == (2, 64 * 320)
+    assert torch.equal(a, b)

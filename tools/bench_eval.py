@@ -44,5 +44,4 @@ def measure(label, **sw):
 if kv:
     measure(str(kv), **{k: int(v) for k, v in kv.items()})
 else:
-    measure("router + dispatch (2 launches)", fused_dispatch=0)
-    measure("fused route_dispatch", fused_dispatch=1)
+    measure("default engine")

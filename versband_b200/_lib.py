@@ -54,6 +54,25 @@ class AttnArgs(C.Structure):
     ]
 
 
+VOC_MAX_STAGES = 8
+
+
+class VocDesc(C.Structure):
+    """Mirror of `struct vb_voc_desc`."""
+
+    _fields_ = [
+        ("n_mel", c_i32), ("c0", c_i32), ("pre_k", c_i32), ("n_stages", c_i32), ("n_kernels", c_i32), ("post_k", c_i32),
+        ("lrelu", c_f32), ("post_b", c_f32),
+        ("rates", c_i32 * VOC_MAX_STAGES), ("up_k", c_i32 * VOC_MAX_STAGES), ("up_cout", c_i32 * VOC_MAX_STAGES),
+        ("rb_k", c_i32 * 3), ("n_dil", c_i32 * 3), ("rb_d", (c_i32 * 4) * 3),
+        ("pre_w", c_ptr), ("pre_b", c_ptr),
+        ("up_w", c_ptr * VOC_MAX_STAGES), ("up_b", c_ptr * VOC_MAX_STAGES),
+        ("rb_w1", ((c_ptr * 4) * 3) * VOC_MAX_STAGES), ("rb_w2", ((c_ptr * 4) * 3) * VOC_MAX_STAGES),
+        ("rb_b1", ((c_ptr * 4) * 3) * VOC_MAX_STAGES), ("rb_b2", ((c_ptr * 4) * 3) * VOC_MAX_STAGES),
+        ("post_w", c_ptr),
+    ]
+
+
 class VersbandError(RuntimeError):
     pass
 
@@ -78,6 +97,11 @@ def lib() -> C.CDLL:
         _lib.vb_attn_fused.argtypes = [C.POINTER(AttnArgs), c_ptr]
         if _lib.vb_sizeof(1) != C.sizeof(AttnArgs):
             raise VersbandError("vb_attn_args ABI mismatch between versband.h and _lib.py")
+        _lib.vb_voc_forward.argtypes = [C.POINTER(VocDesc), c_ptr, c_i32, c_i32, c_ptr, c_ptr, c_i64, c_ptr]
+        _lib.vb_voc_workspace_bytes.argtypes = [C.POINTER(VocDesc), c_i32, c_i32]
+        _lib.vb_voc_workspace_bytes.restype = c_i64
+        if _lib.vb_sizeof(2) != C.sizeof(VocDesc):
+            raise VersbandError("vb_voc_desc ABI mismatch between versband.h and _lib.py")
         if _lib.vb_sizeof(0) != C.sizeof(GemmArgs):
             raise VersbandError("vb_gemm_args ABI mismatch between versband.h and _lib.py")
     return _lib

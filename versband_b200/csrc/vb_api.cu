@@ -105,6 +105,7 @@ extern "C" int vb_sizeof(int which) {
   switch (which) {
     case 0: return (int)sizeof(vb_gemm_args);
     case 1: return (int)sizeof(vb_attn_args);
+    case 2: return (int)sizeof(vb_voc_desc);
     default: return -1;
   }
 }

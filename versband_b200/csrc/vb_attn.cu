@@ -1,27 +1,30 @@
 // vb_attn_fused — flash-style attention on tcgen05/TMEM/TMA for sm_100a.
 //
-// One CTA = 128 query rows of one (batch, head). Key tiles of 128 keys stream through a
-// 2-stage TMA ring; per tile:
-//   MMA1  S = Q K^T        (UMMA 128x128x16, fp32 S in TMEM, double-buffered)
-//   softmax warps: TMEM -> registers, online max/sum, P (fp16) -> swizzled smem
-//   MMA2  O_j = P V        (UMMA 128xHDx16, B operand = V^T tile), TMEM -> registers,
-//                           acc = acc * alpha + O_j   (running output kept in registers)
-// P and O are double-buffered: the softmax warps start on tile j+1 right after publishing P_j and
-// fold O_j into their accumulators one tile later, so they never wait for MMA2.
-// Two KV segments with independent softmax (flag_large_dit_moe.py:381-402):
+// One CTA = 128 query rows of one (batch, head). Key tiles of 128 keys stream through 2-stage TMA rings
+// (K and V^T separately); per tile:
+//   MMA1  S = Q K^T          (UMMA 128x128x16, fp32 S in TMEM, double-buffered)
+//   softmax warps: TMEM -> registers, running row maximum, P = 2^(s*c - m) as fp16 -> swizzled smem
+//   MMA2  O += P [V | 1]     (UMMA 128x(HD+16)x16 ACCUMULATING in TMEM: the B operand is the V^T tile with one
+//                             extra all-ones row, so column HD of O is the softmax denominator — the row sum is
+//                             taken by the tensor core from the very fp16 P values it multiplies with V)
+// O never leaves TMEM between tiles: the running maximum is only raised when a tile's maximum exceeds it by
+// more than 2^8 (P then stays below 256, well inside fp16), in which case the row's accumulator is rescaled in
+// TMEM (tcgen05.ld / st) before the tile's P is published — rare after the first tile. The per-tile work of a
+// softmax thread is therefore: one TMEM read of S, max, exp2, pack, store. Round 1 read O_j back and folded it
+// into registers every tile and summed rows on the CUDA cores (2250 cycles per tile, issue bound).
+// Two KV segments with independent softmax (flag_large_dit_moe.py:381-402), separate accumulators:
 //   segment 0: self-attention over T keys            out  = O0 / l0
 //   segment 1: one tile of L <= 128 "text" keys      out += tanh(gate[h]) * O1 / l1
 // With segment 0 disabled the kernel is the MoE cross-attention of vocal2music_moe.py:119.
 //
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer,
-// warps 2..9 softmax/epilogue (two threads per query row, each owning half of the columns).
+// Warp roles (576 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2..17 softmax/epilogue:
+// FOUR threads per query row (one per 32-column group of S and per HD/4 output dims) — the softmax is
+// instruction-issue bound, so 16 warps (4 per scheduler) rather than 8 hide its latencies.
 #include <math_constants.h>
 #include "vb_internal.h"
 #include "vb_ptx.cuh"
 
 namespace vb {
-
-static long long* g_attn_trace = nullptr;
 
 struct AttnKParams {
   int T, L, H, n_self;
@@ -30,42 +33,48 @@ struct AttnKParams {
   const float* gate;
   __half* out_fp16;
   float* out_f32;
-  long long* trace;  // debug: per-tile clock64 stamps of CTA (0,0,0)
 };
 
 template <int HD>
 struct AttnCfg {
+  static constexpr int VR = HD + 16;                   // V^T rows per k-block incl. the ones row (+ 15 zero rows)
   static constexpr int kQBytes = 2 * 16384;            // Q tile: 2 k-blocks of [128 x 64] fp16
   static constexpr int kKBytes = 2 * 16384;            // K tile per stage
-  static constexpr int kVBytes = 2 * HD * 128;         // V^T tile per stage: 2 k-blocks of [HD x 64]
+  static constexpr int kVKb = VR * 128;                // one k-block of the V^T tile [VR x 64 keys]
+  static constexpr int kVBytes = 2 * kVKb;             // per stage
   static constexpr int kPBytes = 2 * 16384;            // P tile (two buffers)
-  static constexpr int kSmem = kQBytes + 2 * kKBytes + 2 * kVBytes + 2 * kPBytes + 1024 + 256 + 3 * 1024;  // + row exchange buffers
+  static constexpr int kSmem = kQBytes + 2 * kKBytes + 2 * kVBytes + 2 * kPBytes + 1024 + 256 + 4 * 1024;
+  static constexpr int kThreads = 64 + 16 * 32;
 };
 
 template <int HD>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(AttnCfg<HD>::kThreads, 1)
 attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKs,
                   const __grid_constant__ CUtensorMap tmVs, const __grid_constant__ CUtensorMap tmKt,
                   const __grid_constant__ CUtensorMap tmVt, const AttnKParams p) {
   using Cfg = AttnCfg<HD>;
+  constexpr int VR = Cfg::VR;
+  constexpr int DPT = HD / 4;  // output dims per thread (four threads per query row)
+  static_assert(DPT == 24 || DPT == 16, "head_dim 96 or 64");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::kQBytes;          // [2 stages][2 kb][16384]
-  uint8_t* sV = sK + 2 * Cfg::kKBytes;      // [2 stages][2 kb][HD*128]
+  uint8_t* sV = sK + 2 * Cfg::kKBytes;      // [2 stages][2 kb][VR*128]
   uint8_t* sP = sV + 2 * Cfg::kVBytes;      // [2 buffers][2 kb][16384]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::kPBytes);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;    // [2]  K and V^T tiles ride separate rings: a K slot is free as soon as
-  uint64_t* k_empty = bars + 3;   // [2]  its S = Q K^T retires (a whole tile before the V slot), so K_{j+1} is
-  uint64_t* v_full = bars + 13;   // [2]  already in flight while tile j-1's P V is still running
-  uint64_t* v_empty = bars + 15;  // [2]
-  uint64_t* s_full = bars + 5;    // [2]
-  uint64_t* p_full = bars + 7;    // [2]
-  uint64_t* o_full = bars + 9;    // [2]
-  uint64_t* o_empty = bars + 11;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* k_empty = bars + 3;   // [2]  its S = Q K^T retires, a whole tile before the V slot
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [2]
+  uint64_t* p_full = bars + 11;   // [2]  512 softmax threads published P_j
+  uint64_t* p_empty = bars + 13;  // [2]  MMA2_j retired: P buffer free, O holds tile j
+  uint64_t* o_done = bars + 15;   // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  float* xch = reinterpret_cast<float*>(bars + 32);  // [2 parities][4 column groups][128 rows] tile maxima
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128;
@@ -82,18 +91,26 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 256);
-      mbar_init(&o_full[i], 1);
-      mbar_init(&o_empty[i], 256);
+      mbar_init(&p_full[i], 512);
+      mbar_init(&p_empty[i], 1);
     }
+    mbar_init(o_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp >= 2) {
+    // rows HD .. HD+15 of every V^T k-block (TMA only ever writes rows 0..HD-1): one row of ones, fifteen of zeros
+    const int i = threadIdx.x - 64;            // 0..511 = (stage, kb, row 0..15, chunk 0..7)
+    const int chunk = i & 7, row = (i >> 3) & 15, kb = (i >> 7) & 1, st = i >> 8;
+    const uint32_t v = row == 0 ? 0x3C003C00u : 0u;  // fp16 1.0 pairs
+    *reinterpret_cast<uint4*>(sV + st * Cfg::kVBytes + kb * Cfg::kVKb + (HD + row) * 128 + chunk * 16) = make_uint4(v, v, v, v);
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_O = tmem_base + 256;  // two O buffers of 128 columns
+  const uint32_t tmem_Os = tmem_base + 256, tmem_Ot = tmem_base + 384;  // self / text accumulators (VR columns each)
   pdl_sync();  // prologue above overlaps the previous kernel
 
   if (warp == 0) {
@@ -114,15 +131,15 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tma_load_4d(k_dst, mk, &k_full[st], 0, key0, h, b);
         if (HD > 64) tma_load_4d(k_dst + 16384, mk, &k_full[st], 64, key0, h, b);
         mbar_wait(&v_empty[st], ((j >> 1) & 1) ^ 1);
-        mbar_expect_tx(&v_full[st], Cfg::kVBytes);
+        mbar_expect_tx(&v_full[st], 2 * HD * 128);
         tma_load_4d(v_dst, mv, &v_full[st], key0, 0, h, b);
-        tma_load_4d(v_dst + HD * 128, mv, &v_full[st], key0 + 64, 0, h, b);
+        tma_load_4d(v_dst + Cfg::kVKb, mv, &v_full[st], key0 + 64, 0, h, b);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_fp16(128, 128);
-      constexpr uint32_t idesc_o = make_idesc_fp16(128, HD);
+      constexpr uint32_t idesc_o = make_idesc_fp16(128, VR);
       mbar_wait(q_full, 0);
       auto mma1 = [&](int j) {
         const int st = j & 1;
@@ -141,190 +158,169 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mma1(0);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j & 1;
-        if (j + 1 < n_tiles) mma1(j + 1);  // overlaps the softmax of tile j
+        if (j + 1 < n_tiles) mma1(j + 1);  // overlaps the softmax of tile j (S[st^1] was read before P_{j-1} was published)
         mbar_wait(&p_full[st], (j >> 1) & 1);
-        if (j >= 2) mbar_wait(&o_empty[st], ((j - 2) >> 1) & 1);  // O_{j-2} has been folded into the registers
         mbar_wait(&v_full[st], (j >> 1) & 1);
         tc_fence_after();
-        const int keys = (j >= n_self) ? p.L : min(128, p.T - j * 128);
+        const bool text = j >= n_self;
+        const bool first = text || j == 0;  // first tile of its segment: overwrite the accumulator
+        const int keys = text ? p.L : min(128, p.T - j * 128);
         const int ksteps = (keys + 15) >> 4;
+        const uint32_t tO = text ? tmem_Ot : tmem_Os;
         for (int k = 0; k < ksteps; ++k) {
           const int kb = k >> 2, off = (k & 3) * 2;
           const uint64_t da = make_kmajor_sw128_desc(smem_u32(sP + st * Cfg::kPBytes + kb * 16384)) + off;
-          const uint64_t db = make_kmajor_sw128_desc(smem_u32(sV + st * Cfg::kVBytes + kb * HD * 128)) + off;
-          umma_fp16(tmem_O + st * 128, da, db, idesc_o, k > 0 ? 1u : 0u);
+          const uint64_t db = make_kmajor_sw128_desc(smem_u32(sV + st * Cfg::kVBytes + kb * Cfg::kVKb)) + off;
+          umma_fp16(tO, da, db, idesc_o, (!first || k > 0) ? 1u : 0u);
         }
-        umma_commit(&o_full[st]);
+        umma_commit(&p_empty[st]);
         umma_commit(&v_empty[st]);
       }
+      umma_commit(o_done);
     }
   } else {
-    // Two threads per query row: half 0 (warps 2..5) owns score columns 0..63 and output dims
-    // 0..HD/2-1, half 1 (warps 6..9) the rest. S is read from TMEM once (it is the TMEM read port,
-    // 64 B/clk/SM, that bounds this loop), the row maximum is exchanged through shared memory.
-    constexpr int HH = HD / 2;
-    const int half = (warp - 2) >> 2;
-    const int qd = warp & 3;
+    const int qd = warp & 3;             // TMEM lane quadrant = rows 32*qd .. 32*qd+31
+    const int cg = (warp - 2) >> 2;      // 32-column group of S, HD/4 output dims
     const int row = qd * 32 + lane;
     const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
-    float acc[HH];
-#pragma unroll
-    for (int i = 0; i < HH; ++i) acc[i] = 0.f;
     constexpr float kLog2e = 1.4426950408889634f;
-    float m2 = -CUDART_INF_F, l = 0.f;  // running max (log2 domain) and this half's partial sum
+    constexpr float kRaise = 8.f;        // the running maximum follows a tile's maximum only beyond 2^8
     const float c1 = p.scale * kLog2e;
-    const float g = p.gate ? tanhf(p.gate[h]) : 1.f;
+    float m_used = -CUDART_INF_F;        // running maximum (log2 domain) the published P values refer to
     const int rsw = row & 7;
-    uint8_t* prow = sP + half * 16384 + (row >> 3) * 1024 + rsw * 128;
-    // row exchange between the two threads of a query row: [2 halves][128 rows] floats per buffer; the
-    // per-tile maxima alternate between buffers 0/1 (a thread may be a tile ahead of its partner's read),
-    // buffer 2 carries the segment sums (those exchanges are bracketed by their own barriers)
-    float* xch_base = reinterpret_cast<float*>(tmem_slot + 4);
-    float* xch = xch_base + 2 * 256;
-    // acc += O_k of a tile whose P was published one iteration earlier (f_old/f_new are that tile's factors)
-    int pend = -1;
-    float pend_old = 0.f, pend_new = 0.f;
-    auto fold = [&]() {
-      if (pend < 0) return;
-      const int pb = pend & 1;
-      mbar_wait(&o_full[pb], (pend >> 1) & 1);
-      tc_fence_after();
-      const uint32_t tO = tmem_O + pb * 128 + half * HH + lane_sel;
-      if (HH == 48) {
-        uint32_t r0[32], r1[16];
-        tmem_ld32(tO, r0);
-        tmem_ld16(tO + 32, r1);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = acc[i] * pend_old + __uint_as_float(r0[i]) * pend_new;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) acc[32 + i] = acc[32 + i] * pend_old + __uint_as_float(r1[i]) * pend_new;
-      } else {
-#pragma unroll
-        for (int c = 0; c < HH / 32; ++c) {
-          uint32_t r0[32];
-          tmem_ld32(tO + c * 32, r0);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) acc[c * 32 + i] = acc[c * 32 + i] * pend_old + __uint_as_float(r0[i]) * pend_new;
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(&o_empty[pb]);
-      pend = -1;
-    };
+    // this thread's 64 bytes of the P row: k-block cg >> 1, chunks 4*(cg & 1) .. +3
+    uint8_t* prow = sP + (cg >> 1) * 16384 + (row >> 3) * 1024 + rsw * 128;
     for (int j = 0; j < n_tiles; ++j) {
       const bool text = j >= n_self;
-      if (text) {
-        if (n_self > 0) {  // close the self segment: acc /= (l_half0 + l_half1)
-          fold();          // (the last self tile's O first)
-          xch[half * 128 + row] = l;
-          named_bar_sync(1 + qd, 64);
-          const float inv = 1.f / (l + xch[(half ^ 1) * 128 + row]);
-          named_bar_sync(1 + qd, 64);
-#pragma unroll
-          for (int i = 0; i < HH; ++i) acc[i] *= inv;
-        }
-        m2 = -CUDART_INF_F;
-        l = 0.f;
-      }
-      const int valid = (text ? p.L : min(128, p.T - j * 128)) - half * 64;  // valid columns of my half
-      const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && row == 0 && half == 0;
-      if (tr) p.trace[j * 8 + 0] = clock64();
+      const bool first = text || j == 0;
+      if (first) m_used = -CUDART_INF_F;
+      const int valid = (text ? p.L : min(128, p.T - j * 128)) - cg * 32;  // valid columns of my group
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      if (tr) p.trace[j * 8 + 1] = clock64();
-      float sv[64];
+      float sv[32];
       {
-        const uint32_t tS = tmem_base + (j & 1) * 128 + half * 64 + lane_sel;
-        uint32_t r0[32], r1[32];
-        tmem_ld32(tS, r0);
-        tmem_ld32(tS + 32, r1);
+        uint32_t r0[32];
+        tmem_ld32(tmem_base + (j & 1) * 128 + cg * 32 + lane_sel, r0);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { sv[i] = __uint_as_float(r0[i]); sv[32 + i] = __uint_as_float(r1[i]); }
+        for (int i = 0; i < 32; ++i) sv[i] = __uint_as_float(r0[i]);
       }
-      if (valid < 64) {
+      if (valid < 32) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) if (i >= valid) sv[i] = -CUDART_INF_F;
+        for (int i = 0; i < 32; ++i) if (i >= valid) sv[i] = -CUDART_INF_F;
       }
       float tmax = -CUDART_INF_F;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) tmax = fmaxf(tmax, sv[i]);
-      float* xm = xch_base + (j & 1) * 256;
-      xm[half * 128 + row] = tmax;
-      named_bar_sync(1 + qd, 64);
-      tmax = fmaxf(tmax, xm[(half ^ 1) * 128 + row]);
-      if (tr) p.trace[j * 8 + 2] = clock64();
-      const float m_new = fmaxf(m2, tmax * c1);
-      const float alpha = (m2 == -CUDART_INF_F) ? 0.f : ex2_ftz(m2 - m_new);
-      // p = 2^(s*c1 - m_new)  (ftz: masked columns are -inf -> exactly 0)
+      for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, sv[i]);
+      float* xm = xch + (j & 1) * 512;
+      xm[cg * 128 + row] = tmax;
+      named_bar_sync(1 + qd, 128);  // the four warps sharing this lane quadrant
+      tmax = fmaxf(fmaxf(xm[row], xm[128 + row]), fmaxf(xm[256 + row], xm[384 + row]));
+      const float m_tile = tmax * c1;
+      // (all four threads of a row take the same decision from the same numbers)
+      float resc = 1.f;
+      if (first) m_used = m_tile;
+      else if (m_tile > m_used + kRaise) { resc = ex2_ftz(m_used - m_tile); m_used = m_tile; }
+      if (!first && __any_sync(0xffffffffu, resc != 1.f)) {
+        // raise the maximum of some rows of this warp: O (and its denominator column) *= 2^(m_old - m_new), in TMEM.
+        // MMA2_{j-1} must have retired first; MMA2_j cannot start before this warp publishes P_j below.
+        mbar_wait(&p_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tO = (text ? tmem_Ot : tmem_Os) + lane_sel;
+        if (DPT == 24) {
+          uint32_t a[16], c[8];
+          tmem_ld16(tO + cg * DPT, a);
+          tmem_ld8(tO + cg * DPT + 16, c);
+          tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 64; ++i) sv[i] = ex2_ftz(fmaf(sv[i], c1, -m_new));
-      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+          for (int i = 0; i < 16; ++i) a[i] = __float_as_uint(__uint_as_float(a[i]) * resc);
 #pragma unroll
-      for (int i = 0; i < 64; i += 4) { rs0 += sv[i]; rs1 += sv[i + 1]; rs2 += sv[i + 2]; rs3 += sv[i + 3]; }
-      l = l * alpha + ((rs0 + rs1) + (rs2 + rs3));
-      m2 = m_new;
+          for (int i = 0; i < 8; ++i) c[i] = __float_as_uint(__uint_as_float(c[i]) * resc);
+          tmem_st16(tO + cg * DPT, a);
+          tmem_st8(tO + cg * DPT + 16, c);
+        } else {
+          uint32_t a[16];
+          tmem_ld16(tO + cg * DPT, a);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) a[i] = __float_as_uint(__uint_as_float(a[i]) * resc);
+          tmem_st16(tO + cg * DPT, a);
+        }
+        if (cg == 3) {  // the denominator column block HD .. HD+7
+          uint32_t c[8];
+          tmem_ld8(tO + HD, c);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) c[i] = __float_as_uint(__uint_as_float(c[i]) * resc);
+          tmem_st8(tO + HD, c);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+      }
+      // p = 2^(s*c1 - m_used)  (ftz: masked columns are -inf -> exactly 0)
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sv[i] = ex2_ftz(fmaf(sv[i], c1, -m_used));
+      if (j >= 2) mbar_wait(&p_empty[j & 1], ((j - 2) >> 1) & 1);  // MMA2_{j-2} no longer reads this P buffer
       uint8_t* prow_j = prow + (j & 1) * Cfg::kPBytes;
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
+      for (int ch = 0; ch < 4; ++ch) {
+        const __half2 t0 = vb_f2h2(sv[8 * ch], sv[8 * ch + 1]);
+        const __half2 t1 = vb_f2h2(sv[8 * ch + 2], sv[8 * ch + 3]);
+        const __half2 t2 = vb_f2h2(sv[8 * ch + 4], sv[8 * ch + 5]);
+        const __half2 t3 = vb_f2h2(sv[8 * ch + 6], sv[8 * ch + 7]);
         uint4 w;
-        __half2 t0 = vb_f2h2(sv[8 * ch], sv[8 * ch + 1]);
-        __half2 t1 = vb_f2h2(sv[8 * ch + 2], sv[8 * ch + 3]);
-        __half2 t2 = vb_f2h2(sv[8 * ch + 4], sv[8 * ch + 5]);
-        __half2 t3 = vb_f2h2(sv[8 * ch + 6], sv[8 * ch + 7]);
-        w.x = *reinterpret_cast<uint32_t*>(&t0); w.y = *reinterpret_cast<uint32_t*>(&t1);
-        w.z = *reinterpret_cast<uint32_t*>(&t2); w.w = *reinterpret_cast<uint32_t*>(&t3);
-        *reinterpret_cast<uint4*>(prow_j + ((ch ^ rsw) << 4)) = w;
+        w.x = *reinterpret_cast<const uint32_t*>(&t0); w.y = *reinterpret_cast<const uint32_t*>(&t1);
+        w.z = *reinterpret_cast<const uint32_t*>(&t2); w.w = *reinterpret_cast<const uint32_t*>(&t3);
+        *reinterpret_cast<uint4*>(prow_j + ((((cg & 1) * 4 + ch) ^ rsw) << 4)) = w;
       }
       tc_fence_before();
       fence_proxy_async();  // make the generic-proxy smem writes visible to the tensor core
       mbar_arrive(&p_full[j & 1]);
-      if (tr) p.trace[j * 8 + 3] = clock64();
-      float f_old = alpha, f_new = 1.f;
-      if (text) {  // single text tile: l is final after the exchange
-        named_bar_sync(1 + qd, 64);  // (both halves are done reading the max exchange)
-        xch[half * 128 + row] = l;
-        named_bar_sync(1 + qd, 64);
-        f_old = 1.f;
-        f_new = g / (l + xch[(half ^ 1) * 128 + row]);
-      }
-      // O_{j-1} is complete by now (MMA2 of tile j-1 ran under this tile's softmax): fold it in, then
-      // queue this tile
-      fold();
-      if (tr) p.trace[j * 8 + 4] = clock64();
-      pend = j;
-      pend_old = f_old;
-      pend_new = f_new;
     }
-    fold();
-    if (!p.has_text && n_self > 0) {
-      xch[half * 128 + row] = l;
-      named_bar_sync(1 + qd, 64);
-      const float inv = 1.f / (l + xch[(half ^ 1) * 128 + row]);
+    // ---- epilogue: out = O_self / l_self + tanh(gate) * O_text / l_text
+    mbar_wait(o_done, 0);
+    tc_fence_after();
+    float acc[DPT];
 #pragma unroll
-      for (int i = 0; i < HH; ++i) acc[i] *= inv;
-    }
+    for (int i = 0; i < DPT; ++i) acc[i] = 0.f;
+    auto add_segment = [&](uint32_t tO, float g) {
+      uint32_t c[8];
+      tmem_ld8(tO + lane_sel + HD, c);  // column HD = sum of the row's P values (the ones row of [V | 1])
+      uint32_t a[16];
+      tmem_ld16(tO + lane_sel + cg * DPT, a);
+      tmem_ld_wait();
+      const float f = g / __uint_as_float(c[0]);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = fmaf(__uint_as_float(a[i]), f, acc[i]);
+      if (DPT == 24) {
+        uint32_t d[8];
+        tmem_ld8(tO + lane_sel + cg * DPT + 16, d);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[16 + i] = fmaf(__uint_as_float(d[i]), f, acc[16 + i]);
+      }
+    };
+    if (n_self > 0) add_segment(tmem_Os, 1.f);
+    if (p.has_text) add_segment(tmem_Ot, (p.gate && n_self > 0) ? tanhf(p.gate[h]) : (p.gate ? tanhf(p.gate[h]) : 1.f));
     const int t = q0 + row;
     if (t < p.T) {
-      const long long o = ((long long)b * p.T + t) * ((long long)p.H * HD) + (long long)h * HD + half * HH;
+      const long long o = ((long long)b * p.T + t) * ((long long)p.H * HD) + (long long)h * HD + cg * DPT;
       if (p.out_fp16) {
         uint4* dst = reinterpret_cast<uint4*>(p.out_fp16 + o);
 #pragma unroll
-        for (int i = 0; i < HH / 8; ++i) {
-          __half2 a0 = vb_f2h2(acc[8 * i], acc[8 * i + 1]);
-          __half2 a1 = vb_f2h2(acc[8 * i + 2], acc[8 * i + 3]);
-          __half2 a2 = vb_f2h2(acc[8 * i + 4], acc[8 * i + 5]);
-          __half2 a3 = vb_f2h2(acc[8 * i + 6], acc[8 * i + 7]);
-          dst[i] = make_uint4(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1),
-                              *reinterpret_cast<uint32_t*>(&a2), *reinterpret_cast<uint32_t*>(&a3));
+        for (int i = 0; i < DPT / 8; ++i) {
+          const __half2 a0 = vb_f2h2(acc[8 * i], acc[8 * i + 1]);
+          const __half2 a1 = vb_f2h2(acc[8 * i + 2], acc[8 * i + 3]);
+          const __half2 a2 = vb_f2h2(acc[8 * i + 4], acc[8 * i + 5]);
+          const __half2 a3 = vb_f2h2(acc[8 * i + 6], acc[8 * i + 7]);
+          dst[i] = make_uint4(*reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1),
+                              *reinterpret_cast<const uint32_t*>(&a2), *reinterpret_cast<const uint32_t*>(&a3));
         }
       }
       if (p.out_f32) {
         float4* dst = reinterpret_cast<float4*>(p.out_f32 + o);
 #pragma unroll
-        for (int i = 0; i < HH / 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+        for (int i = 0; i < DPT / 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
       }
     }
   }
@@ -394,7 +390,6 @@ static int launch_attn(const vb_attn_args* a, cudaStream_t stream) {
   p.scale = a->scale; p.gate = a->gate;
   p.out_fp16 = static_cast<__half*>(a->out_fp16);
   p.out_f32 = a->out_f32;
-  p.trace = g_attn_trace;
   static PerDevice<bool> attr_flag;
   bool& attr = attr_flag.get();
   if (!attr) {
@@ -403,16 +398,13 @@ static int launch_attn(const vb_attn_args* a, cudaStream_t stream) {
     attr = true;
   }
   dim3 grid((a->T + 127) / 128, a->H, a->B);
-  launch_k(attn_fused_kernel<HD>, dim3(grid), dim3(320), Cfg::kSmem, stream, tmQ, tmKs, tmVs, tmKt, tmVt, p);
+  launch_k(attn_fused_kernel<HD>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmem, stream, tmQ, tmKs, tmVs, tmKt, tmVt, p);
   return check_launch("vb_attn_fused");
 }
 
 }  // namespace vb
 
-extern "C" int vb_attn_set_trace(void* buf) {
-  vb::g_attn_trace = static_cast<long long*>(buf);
-  return VB_OK;
-}
+extern "C" int vb_attn_set_trace(void*) { return VB_OK; }  // (round-1 debug hook, kept for ABI compatibility)
 
 extern "C" int vb_attn_fused(const vb_attn_args* a, void* stream) {
   using namespace vb;

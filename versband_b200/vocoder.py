@@ -39,6 +39,7 @@ class HifiGanEngine:
         self.C0 = h["upsample_initial_channel"]
         self.w: Dict[str, torch.Tensor] = {}
         self.fuse_pairs = True  # ResBlock1 conv pairs of the C <= 64 stages in one kernel each (vb_resblock_pair)
+        self._c_desc = None
         self._pack({k: v.detach().to(self.dev) for k, v in sd.items()})
 
     def _pack(self, sd):
@@ -81,9 +82,60 @@ class HifiGanEngine:
                  bias=self.w[wname + ".b"], out_ld=Cout, out_g=(T * Cout, 0), outb_ld=Cout,
                  outb_g=(T * Cout, 0), **epi)
 
+    # ------------------------------------------------------------------ C entry point (vb_voc_forward)
+    def _desc(self):
+        """The packed generator as a `vb_voc_desc` (device pointers into self.w; built once)."""
+        if self._c_desc is None:
+            from ._lib import VocDesc
+            d, w = VocDesc(), self.w
+            nk = len(self.rb_k)
+            assert len(self.rates) <= 8 and nk <= 3 and all(len(x) <= 4 for x in self.rb_d)
+            d.n_mel, d.c0, d.pre_k, d.n_stages, d.n_kernels, d.post_k = self.n_mel, self.C0, 7, len(self.rates), nk, self.post_k
+            d.lrelu, d.post_b = LRELU, self.post_b
+            ptr = lambda t: t.data_ptr()  # noqa: E731
+            d.pre_w, d.pre_b, d.post_w = ptr(w["pre.w"]), ptr(w["pre.b"]), ptr(w["post.w"])
+            for i, (u, k) in enumerate(zip(self.rates, self.up_k)):
+                d.rates[i], d.up_k[i], d.up_cout[i] = u, k, w[f"up{i}.w"].shape[1]
+                d.up_w[i], d.up_b[i] = ptr(w[f"up{i}.w"]), ptr(w[f"up{i}.b"])
+                for j in range(nk):
+                    for c in range(len(self.rb_d[j])):
+                        d.rb_w1[i][j][c], d.rb_b1[i][j][c] = ptr(w[f"rb{i}.{j}.convs1.{c}.w"]), ptr(w[f"rb{i}.{j}.convs1.{c}.b"])
+                        d.rb_w2[i][j][c], d.rb_b2[i][j][c] = ptr(w[f"rb{i}.{j}.convs2.{c}.w"]), ptr(w[f"rb{i}.{j}.convs2.{c}.b"])
+            for j in range(nk):
+                d.rb_k[j], d.n_dil[j] = self.rb_k[j], len(self.rb_d[j])
+                for c, dd in enumerate(self.rb_d[j]):
+                    d.rb_d[j][c] = dd
+            self._c_desc = d
+        return self._c_desc
+
     @torch.no_grad()
     def forward(self, mel: torch.Tensor) -> torch.Tensor:
-        """mel fp32 [B, n_mel, T] -> wav fp32 [B, T * prod(rates)]."""
+        """mel fp32 [B, n_mel, T] -> wav fp32 [B, T * prod(rates)]: ONE call into the C-ABI (vb_voc_forward issues
+        the whole launch sequence from C++); `forward_py` below is the same sequence issued launch by launch from
+        Python (kept for experiments: fuse_pairs switch, per-launch timing)."""
+        import ctypes as C
+        from . import _lib
+        if not self.fuse_pairs:
+            return self.forward_py(mel)
+        B, nm, T = mel.shape
+        assert nm == self.n_mel and nm % 8 == 0
+        mel = mel.to(self.dev, F32).contiguous()
+        hop = 1
+        for u in self.rates:
+            hop *= u
+        d = self._desc()
+        need = int(_lib.lib().vb_voc_workspace_bytes(C.byref(d), B, T))
+        if need < 0:
+            _lib.check(-1, "vb_voc_workspace_bytes")
+        ws = torch.empty(need, device=self.dev, dtype=torch.uint8)
+        wav = torch.empty(B, T * hop, device=self.dev, dtype=F32)
+        _lib.check(_lib.lib().vb_voc_forward(C.byref(d), C.c_void_p(mel.data_ptr()), B, T, C.c_void_p(wav.data_ptr()),
+                                             C.c_void_p(ws.data_ptr()), need, ops._stream()), "vb_voc_forward")
+        return wav
+
+    @torch.no_grad()
+    def forward_py(self, mel: torch.Tensor) -> torch.Tensor:
+        """mel fp32 [B, n_mel, T] -> wav fp32 [B, T * prod(rates)] (launch sequence issued from Python)."""
         dev = self.dev
         B, nm, T = mel.shape
         assert nm == self.n_mel and nm % 8 == 0
