@@ -33,7 +33,10 @@ struct AttnKParams {
   const float* gate;
   __half* out_fp16;
   float* out_f32;
+  long long* trace;  // debug (vb_attn_set_trace): clock64 stamps of CTA (0,0,0), 8 per tile + MMA-thread stamps at [64 + 4*j]
 };
+
+static long long* g_attn_trace = nullptr;
 
 template <int HD>
 struct AttnCfg {
@@ -159,7 +162,10 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j & 1;
         if (j + 1 < n_tiles) mma1(j + 1);  // overlaps the softmax of tile j (S[st^1] was read before P_{j-1} was published)
+        const bool trm = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+        if (trm) p.trace[64 + 4 * j] = clock64();
         mbar_wait(&p_full[st], (j >> 1) & 1);
+        if (trm) p.trace[64 + 4 * j + 1] = clock64();
         mbar_wait(&v_full[st], (j >> 1) & 1);
         tc_fence_after();
         const bool text = j >= n_self;
@@ -175,6 +181,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         umma_commit(&p_empty[st]);
         umma_commit(&v_empty[st]);
+        if (trm) p.trace[64 + 4 * j + 2] = clock64();
       }
       umma_commit(o_done);
     }
@@ -195,8 +202,11 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const bool first = text || j == 0;
       if (first) m_used = -CUDART_INF_F;
       const int valid = (text ? p.L : min(128, p.T - j * 128)) - cg * 32;  // valid columns of my group
+      const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && row == 0 && cg == 0;
+      if (tr) p.trace[j * 8 + 0] = clock64();
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
+      if (tr) p.trace[j * 8 + 1] = clock64();
       float sv[32];
       {
         uint32_t r0[32];
@@ -215,6 +225,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       float* xm = xch + (j & 1) * 512;
       xm[cg * 128 + row] = tmax;
       named_bar_sync(1 + qd, 128);  // the four warps sharing this lane quadrant
+      if (tr) p.trace[j * 8 + 2] = clock64();
       tmax = fmaxf(fmaxf(xm[row], xm[128 + row]), fmaxf(xm[256 + row], xm[384 + row]));
       const float m_tile = tmax * c1;
       // (all four threads of a row take the same decision from the same numbers)
@@ -260,7 +271,9 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       // p = 2^(s*c1 - m_used)  (ftz: masked columns are -inf -> exactly 0)
 #pragma unroll
       for (int i = 0; i < 32; ++i) sv[i] = ex2_ftz(fmaf(sv[i], c1, -m_used));
+      if (tr) p.trace[j * 8 + 3] = clock64();
       if (j >= 2) mbar_wait(&p_empty[j & 1], ((j - 2) >> 1) & 1);  // MMA2_{j-2} no longer reads this P buffer
+      if (tr) p.trace[j * 8 + 4] = clock64();
       uint8_t* prow_j = prow + (j & 1) * Cfg::kPBytes;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
@@ -276,6 +289,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc_fence_before();
       fence_proxy_async();  // make the generic-proxy smem writes visible to the tensor core
       mbar_arrive(&p_full[j & 1]);
+      if (tr) p.trace[j * 8 + 5] = clock64();
     }
     // ---- epilogue: out = O_self / l_self + tanh(gate) * O_text / l_text
     mbar_wait(o_done, 0);
@@ -390,6 +404,7 @@ static int launch_attn(const vb_attn_args* a, cudaStream_t stream) {
   p.scale = a->scale; p.gate = a->gate;
   p.out_fp16 = static_cast<__half*>(a->out_fp16);
   p.out_f32 = a->out_f32;
+  p.trace = g_attn_trace;
   static PerDevice<bool> attr_flag;
   bool& attr = attr_flag.get();
   if (!attr) {
@@ -404,7 +419,10 @@ static int launch_attn(const vb_attn_args* a, cudaStream_t stream) {
 
 }  // namespace vb
 
-extern "C" int vb_attn_set_trace(void*) { return VB_OK; }  // (round-1 debug hook, kept for ABI compatibility)
+extern "C" int vb_attn_set_trace(void* buf) {
+  vb::g_attn_trace = static_cast<long long*>(buf);
+  return VB_OK;
+}
 
 extern "C" int vb_attn_fused(const vb_attn_args* a, void* stream) {
   using namespace vb;

@@ -258,8 +258,8 @@ int plan_gemm(const vb_gemm_args* a, int force_bn, GemmPlan* out) {
                             (a->act_out == VB_ACT_NONE || a->act_out == VB_ACT_LRELU);
     if (a->mode == VB_EPI_ROUTE) ec = EC_ROUTE;
     else if (a->mode == VB_EPI_QKV_ROPE) ec = EC_QKV;
-    else if (a->swiglu && a->alpha == 1.f && !a->out_f32) ec = EC_SWIGLU;
-    else if (!a->swiglu && a->alpha == 1.f && lrelu_only) ec = EC_LINEAR;
+    else if (a->swiglu == 1 && a->alpha == 1.f && !a->out_f32) ec = EC_SWIGLU;
+    else if (!a->swiglu && a->alpha == 1.f && lrelu_only) ec = a->res16 ? EC_RES16 : EC_LINEAR;
   }
 
   p.m_tiles = m_tiles;
@@ -316,8 +316,9 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
         const int smem_bytes = w_bytes + stages * hp.rows8 * 128 + 1024 + 1024 + kEpiStageBytes;
         const int grid_h = ph.num_tiles < num_sms ? ph.num_tiles : num_sms;
         const bool k2 = hp.n_ksteps <= 2;
-        return ec == EC_LINEAR ? launch_halo_class<EC_LINEAR>(hbn, k2, tmA2, tmB2, ph, hp, grid_h, smem_bytes, stream)
-                               : launch_halo_class<EC_FULL>(hbn, k2, tmA2, tmB2, ph, hp, grid_h, smem_bytes, stream);
+        if (ec == EC_LINEAR) return launch_halo_class<EC_LINEAR>(hbn, k2, tmA2, tmB2, ph, hp, grid_h, smem_bytes, stream);
+        if (ec == EC_RES16) return launch_halo_class<EC_RES16>(hbn, k2, tmA2, tmB2, ph, hp, grid_h, smem_bytes, stream);
+        return launch_halo_class<EC_FULL>(hbn, k2, tmA2, tmB2, ph, hp, grid_h, smem_bytes, stream);
       }
     }
   }
@@ -332,6 +333,7 @@ extern "C" int vb_gemm(const vb_gemm_args* a, void* stream_) {
     case EC_QKV: return launch_gemm_class<EC_QKV>(bn, tf32, use2, tmA, tmB, p, grid, stream);
     case EC_SWIGLU: return launch_gemm_class<EC_SWIGLU>(bn, tf32, use2, tmA, tmB, p, grid, stream);
     case EC_LINEAR: return launch_gemm_class<EC_LINEAR>(bn, tf32, use2, tmA, tmB, p, grid, stream);
+    case EC_RES16: return launch_gemm_class<EC_RES16>(bn, tf32, use2, tmA, tmB, p, grid, stream);
     default: return launch_gemm_class<EC_FULL>(bn, tf32, use2, tmA, tmB, p, grid, stream);
   }
 }
@@ -354,7 +356,7 @@ extern "C" int vb_gemm_chain(const vb_gemm_args* ops, const int32_t* dep_mode, i
     GemmPlan pl;
     const int rc = plan_gemm(&ops[o], bn, &pl);
     if (rc) return rc;
-    if (pl.ec != EC_LINEAR && pl.ec != EC_SWIGLU)
+    if (pl.ec != EC_LINEAR && pl.ec != EC_SWIGLU)  // (EC_CHAIN = these two)
       return set_error(VB_ERR_INVALID, "vb_gemm_chain: problem %d needs an epilogue outside LINEAR/SWIGLU", o);
     if (o == 0) tf32 = pl.tf32;
     else if (tf32 != pl.tf32) return set_error(VB_ERR_INVALID, "vb_gemm_chain: mixed operand types");

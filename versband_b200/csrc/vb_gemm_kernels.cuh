@@ -374,7 +374,7 @@ __device__ __forceinline__ void epi_load_operands(const GemmKParams& p, const Ep
     op.g_lo = __ldg(reinterpret_cast<const float4*>(gsrc));
     op.g_hi = __ldg(reinterpret_cast<const float4*>(gsrc + (rows.hi ? p.gate_ld : 0)));
   }
-  if (p.res16) {
+  if ((EC == EC_RES16 || EC == EC_FULL) && p.res16) {
     // fp16 residual in the activated ("y = leaky_relu(x)") representation: x = y >= 0 ? y : y * res16_neg
     const __half* r16 = p.res16 + g1 * p.outb_g1 + g2 * p.outb_g2 + n;
     const float ng = p.res16_neg;
@@ -413,8 +413,14 @@ __device__ __forceinline__ void epilogue_generic(const GemmKParams& p, float (&v
     float o[16];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      o[2 * i] = glu_mul(v[4 * i], v[4 * i + 1], p.swiglu) * rows.rs[i];
-      o[2 * i + 1] = glu_mul(v[4 * i + 2], v[4 * i + 3], p.swiglu) * rows.rs[i];
+      // the DiT's hot classes (SWIGLU, CHAIN) carry the SiLU gate only; GEGLU / magnitude live in EC_FULL
+      if (EC == EC_FULL) {
+        o[2 * i] = glu_mul(v[4 * i], v[4 * i + 1], p.swiglu) * rows.rs[i];
+        o[2 * i + 1] = glu_mul(v[4 * i + 2], v[4 * i + 3], p.swiglu) * rows.rs[i];
+      } else {
+        o[2 * i] = silu_mul(v[4 * i], v[4 * i + 1]) * rows.rs[i];
+        o[2 * i + 1] = silu_mul(v[4 * i + 2], v[4 * i + 3]) * rows.rs[i];
+      }
     }
     if (p.out_fp16 && p.outb_f32) {
       float* dst = reinterpret_cast<float*>(p.out_fp16) + g1 * p.outb_g1 + g2 * p.outb_g2 + no;
@@ -458,10 +464,10 @@ __device__ __forceinline__ void epilogue_generic(const GemmKParams& p, float (&v
     }
   }
   const long long gofs32 = g1 * p.out_g1 + g2 * p.out_g2 + n;
-  if (p.residual || p.res16 || (p.accumulate && p.out_f32)) {
+  if (p.residual || ((EC == EC_RES16 || EC == EC_FULL) && p.res16) || (p.accumulate && p.out_f32)) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { v[4 * i] += op.res[i].x; v[4 * i + 1] += op.res[i].y; v[4 * i + 2] += op.res[i].z; v[4 * i + 3] += op.res[i].w; }
-    if ((p.residual || p.res16) && p.accumulate && p.out_f32) {  // both: the accumulate target is read here
+    if ((p.residual || ((EC == EC_RES16 || EC == EC_FULL) && p.res16)) && p.accumulate && p.out_f32) {  // both: the accumulate target is read here
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 r4 = *reinterpret_cast<const float4*>(p.out_f32 + gofs32 + rows.off[i]);

@@ -26,6 +26,8 @@ enum EpiClass {
   EC_QKV = 3,     // bias + rotary + head-major q/k and transposed v stores
   EC_ROUTE = 4,   // per-head softmax over 96 score columns contracted with V.(gate) -> gate-logit partials
   EC_CHAIN = 5,   // LINEAR + SWIGLU selected per problem at run time (vb_gemm_chain)
+  EC_RES16 = 6,   // LINEAR + fp16 activated-representation residual (the vocoder's convs): kept out of LINEAR so
+                  // that the DiT's issue-bound epilogues do not carry its code (measured +1 us per DiT GEMM)
 };
 
 struct GemmKParams {
