@@ -45,8 +45,7 @@ struct AttnCfg {
   static constexpr int kKBytes = 2 * 16384;            // K tile per stage
   static constexpr int kVKb = VR * 128;                // one k-block of the V^T tile [VR x 64 keys]
   static constexpr int kVBytes = 2 * kVKb;             // per stage
-  static constexpr int kPBytes = 2 * 16384;            // P tile (two buffers)
-  static constexpr int kSmem = kQBytes + 2 * kKBytes + 2 * kVBytes + 2 * kPBytes + 1024 + 256 + 4 * 1024;
+  static constexpr int kSmem = kQBytes + 2 * kKBytes + 2 * kVBytes + 1024 + 256 + 4 * 1024;
   static constexpr int kThreads = 64 + 16 * 32;
 };
 
@@ -65,8 +64,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::kQBytes;          // [2 stages][2 kb][16384]
   uint8_t* sV = sK + 2 * Cfg::kKBytes;      // [2 stages][2 kb][VR*128]
-  uint8_t* sP = sV + 2 * Cfg::kVBytes;      // [2 buffers][2 kb][16384]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::kPBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * Cfg::kVBytes);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;    // [2]  K and V^T tiles ride separate rings: a K slot is free as soon as
   uint64_t* k_empty = bars + 3;   // [2]  its S = Q K^T retires, a whole tile before the V slot
@@ -76,7 +74,9 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* p_full = bars + 11;   // [2]  512 softmax threads published P_j
   uint64_t* p_empty = bars + 13;  // [2]  MMA2_j retired: P buffer free, O holds tile j
   uint64_t* o_done = bars + 15;   // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* s_free = bars + 17;   // [1]  the 16 softmax warps have read S_j (single S buffer)
+  uint64_t* q_ready = bars + 18;  // [1]  Q copied into tensor memory (A operand of every S = Q K^T)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);  // (bars + 16: 8 bytes)
   float* xch = reinterpret_cast<float*>(bars + 32);  // [2 parities][4 column groups][128 rows] tile maxima
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -98,6 +98,8 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mbar_init(&p_empty[i], 1);
     }
     mbar_init(o_done, 1);
+    mbar_init(s_free, 16);
+    mbar_init(q_ready, 4 * (HD / 32));  // the warps that copy Q (one 32-dim group each)
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -113,7 +115,9 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_Os = tmem_base + 256, tmem_Ot = tmem_base + 384;  // self / text accumulators (VR columns each)
+  // tensor-memory map (512 columns): S [0,128) | P [128,192) | O_self [192,192+VR) | O_text [304,304+VR) | Q [416,416+HD/2)
+  const uint32_t tmem_S = tmem_base, tmem_P = tmem_base + 128;
+  const uint32_t tmem_Os = tmem_base + 192, tmem_Ot = tmem_base + 304, tmem_Q = tmem_base + 416;
   pdl_sync();  // prologue above overlaps the previous kernel
 
   if (warp == 0) {
@@ -143,25 +147,26 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_fp16(128, 128);
       constexpr uint32_t idesc_o = make_idesc_fp16(128, VR);
-      mbar_wait(q_full, 0);
+      mbar_wait(q_ready, 0);
+      tc_fence_after();
       auto mma1 = [&](int j) {
         const int st = j & 1;
         mbar_wait(&k_full[st], (j >> 1) & 1);
+        if (j > 0) mbar_wait(s_free, (j - 1) & 1);  // the softmax warps hold S_{j-1} in registers
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) {
           const int kb = k >> 2, off = (k & 3) * 2;
-          const uint64_t da = make_kmajor_sw128_desc(smem_u32(sQ + kb * 16384)) + off;
           const uint64_t db = make_kmajor_sw128_desc(smem_u32(sK + st * Cfg::kKBytes + kb * 16384)) + off;
-          umma_fp16(tmem_base + st * 128, da, db, idesc_s, k > 0 ? 1u : 0u);
+          umma_fp16_ts(tmem_S, tmem_Q + 8 * k, db, idesc_s, k > 0 ? 1u : 0u);  // Q from tensor memory: only K streams from smem
         }
-        umma_commit(&s_full[st]);
+        umma_commit(&s_full[0]);
         umma_commit(&k_empty[st]);
       };
       mma1(0);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j & 1;
-        if (j + 1 < n_tiles) mma1(j + 1);  // overlaps the softmax of tile j (S[st^1] was read before P_{j-1} was published)
+        if (j + 1 < n_tiles) mma1(j + 1);  // overlaps the exponentials of tile j (waits until S_j has been read)
         const bool trm = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
         if (trm) p.trace[64 + 4 * j] = clock64();
         mbar_wait(&p_full[st], (j >> 1) & 1);
@@ -173,11 +178,11 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const int keys = text ? p.L : min(128, p.T - j * 128);
         const int ksteps = (keys + 15) >> 4;
         const uint32_t tO = text ? tmem_Ot : tmem_Os;
+        const uint32_t tP = tmem_P;
         for (int k = 0; k < ksteps; ++k) {
           const int kb = k >> 2, off = (k & 3) * 2;
-          const uint64_t da = make_kmajor_sw128_desc(smem_u32(sP + st * Cfg::kPBytes + kb * 16384)) + off;
           const uint64_t db = make_kmajor_sw128_desc(smem_u32(sV + st * Cfg::kVBytes + kb * Cfg::kVKb)) + off;
-          umma_fp16(tO, da, db, idesc_o, (!first || k > 0) ? 1u : 0u);
+          umma_fp16_ts(tO, tP + 8 * k, db, idesc_o, (!first || k > 0) ? 1u : 0u);
         }
         umma_commit(&p_empty[st]);
         umma_commit(&v_empty[st]);
@@ -194,9 +199,25 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     constexpr float kRaise = 8.f;        // the running maximum follows a tile's maximum only beyond 2^8
     const float c1 = p.scale * kLog2e;
     float m_used = -CUDART_INF_F;        // running maximum (log2 domain) the published P values refer to
-    const int rsw = row & 7;
-    // this thread's 64 bytes of the P row: k-block cg >> 1, chunks 4*(cg & 1) .. +3
-    uint8_t* prow = sP + (cg >> 1) * 16384 + (row >> 3) * 1024 + rsw * 128;
+    if (cg < HD / 32) {
+      // Q (the A operand of every S = Q K^T) moves from its swizzled smem tile into tensor memory once: lane = row,
+      // column c = dims (2c, 2c+1). The tensor core then fetches only the K tile from shared memory per MMA
+      // (8 KB -> 4 KB: the S MMAs were bound by that port, tools/profile_attn.py).
+      mbar_wait(q_full, 0);
+      const int d0 = cg * 32;  // 32 dims = 64 bytes = 4 chunks of k-block d0 / 64
+      const uint8_t* qrow = sQ + (d0 >> 6) * 16384 + row * 128;
+      uint32_t w[16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 v = *reinterpret_cast<const uint4*>(qrow + (((((d0 & 63) >> 3) + c) ^ (row & 7)) << 4));
+        w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+      }
+      tmem_st16(tmem_Q + cg * 16 + lane_sel, w);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_ready);
+    }
     for (int j = 0; j < n_tiles; ++j) {
       const bool text = j >= n_self;
       const bool first = text || j == 0;
@@ -204,14 +225,17 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const int valid = (text ? p.L : min(128, p.T - j * 128)) - cg * 32;  // valid columns of my group
       const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && row == 0 && cg == 0;
       if (tr) p.trace[j * 8 + 0] = clock64();
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      mbar_wait(&s_full[0], j & 1);
       tc_fence_after();
       if (tr) p.trace[j * 8 + 1] = clock64();
       float sv[32];
       {
         uint32_t r0[32];
-        tmem_ld32(tmem_base + (j & 1) * 128 + cg * 32 + lane_sel, r0);
+        tmem_ld32(tmem_S + cg * 32 + lane_sel, r0);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);  // S_j is in registers: S_{j+1} may be computed
 #pragma unroll
         for (int i = 0; i < 32; ++i) sv[i] = __uint_as_float(r0[i]);
       }
@@ -268,26 +292,30 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tmem_st_wait();
         tc_fence_before();
       }
-      // p = 2^(s*c1 - m_used)  (ftz: masked columns are -inf -> exactly 0)
+      // p = 2^(s*c1 - m_used) evaluated TWO columns per MUFU operation (ex2.approx.f16x2 on the packed
+      // exponents): the exponential unit (16 ops/clk/SM) was the bound of this loop — 1400 of a tile's 2400 cycles
+      // (tools/profile_attn.py). The exponent is rounded to fp16 first: its absolute error is <= 2^-11 |x|, i.e. a
+      // relative error in p of <= 7e-4 at x = -4 and below the fp16 rounding of p itself for the terms that carry
+      // the weight (|x| < 1.5); masked columns are -inf -> exactly 0. The result already is the packed fp16 P.
+      // P_j goes straight back into TENSOR MEMORY (64 columns next to S): lane = row,
+      // column 16*cg + i = keys 32*cg + 2i, +1 — the A operand of MMA2 is read from there (tcgen05.mma with a TMEM
+      // A operand), so P never touches shared memory: no swizzled stores, no proxy fence, and the tensor core's
+      // shared-memory port only streams V^T. (Every warp of the quadrant has read its S columns: named barrier above.)
+      uint32_t w[16];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) sv[i] = ex2_ftz(fmaf(sv[i], c1, -m_used));
-      if (tr) p.trace[j * 8 + 3] = clock64();
-      if (j >= 2) mbar_wait(&p_empty[j & 1], ((j - 2) >> 1) & 1);  // MMA2_{j-2} no longer reads this P buffer
-      if (tr) p.trace[j * 8 + 4] = clock64();
-      uint8_t* prow_j = prow + (j & 1) * Cfg::kPBytes;
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        const __half2 t0 = vb_f2h2(sv[8 * ch], sv[8 * ch + 1]);
-        const __half2 t1 = vb_f2h2(sv[8 * ch + 2], sv[8 * ch + 3]);
-        const __half2 t2 = vb_f2h2(sv[8 * ch + 4], sv[8 * ch + 5]);
-        const __half2 t3 = vb_f2h2(sv[8 * ch + 6], sv[8 * ch + 7]);
-        uint4 w;
-        w.x = *reinterpret_cast<const uint32_t*>(&t0); w.y = *reinterpret_cast<const uint32_t*>(&t1);
-        w.z = *reinterpret_cast<const uint32_t*>(&t2); w.w = *reinterpret_cast<const uint32_t*>(&t3);
-        *reinterpret_cast<uint4*>(prow_j + ((((cg & 1) * 4 + ch) ^ rsw) << 4)) = w;
+      for (int i = 0; i < 16; ++i) {
+        const float x0 = fmaf(sv[2 * i], c1, -m_used), x1 = fmaf(sv[2 * i + 1], c1, -m_used);
+        uint32_t xx;
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(xx) : "f"(x1), "f"(x0));  // (-inf stays -inf)
+        asm("ex2.approx.f16x2 %0, %1;" : "=r"(w[i]) : "r"(xx));
       }
+      if (j >= 1) {  // single P buffer: MMA2_{j-1} must have consumed P_{j-1}
+        mbar_wait(&p_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+      }
+      tmem_st16(tmem_P + cg * 16 + lane_sel, w);
+      tmem_st_wait();
       tc_fence_before();
-      fence_proxy_async();  // make the generic-proxy smem writes visible to the tensor core
       mbar_arrive(&p_full[j & 1]);
       if (tr) p.trace[j * 8 + 5] = clock64();
     }
