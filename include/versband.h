@@ -165,6 +165,10 @@ int vb_stem_gather(const int64_t* midi, const int64_t* beats, const float* tab_m
  * vb_loudness_pcm16: per clip rms -> gain to `target_db` dBFS (scripts/test_final.py:342-347) -> int16 PCM
  *   (x * 32767, round to nearest even, saturating), scratch = B * 64 floats.
  * ------------------------------------------------------------------------------------------ */
+/* AdamW update of one fp32 parameter tensor (training step): torch.optim.AdamW semantics
+ * with bias corrections c1 = 1 - b1^t, c2 = 1 - b2^t computed by the caller. */
+int vb_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, float wd,
+             float c1, float c2, void* stream);
 int vb_wave_prepare(const float* wav, int B, int64_t n, int pad, int64_t plane, void* out_fp16, void* stream);
 int vb_loudness_pcm16(const float* wav, int B, int64_t n, float target_db, float* scratch, int16_t* out, void* stream);
 

@@ -285,6 +285,22 @@ __global__ void loudness_apply_kernel(const float* __restrict__ wav, long long n
   }
 }
 
+// AdamW (decoupled weight decay), one launch per parameter tensor: the optimiser update of the training step
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
+                             float c1, float c2) {
+  pdl_sync();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float pi = p[i] * (1.f - lr * wd);
+    p[i] = pi - lr * (mi / c1) / (sqrtf(vi / c2) + eps);
+  }
+}
+
 // GroupNorm statistics over channels-last x[B, T, C]: per (b, group) mean and rstd
 // (autoencoder1d.py:165-166: 32 groups, eps 1e-6). Two launches, deterministic: gn_partial splits T
 // into `nsplit` slabs (grid = G x B x nsplit, coalesced rows, fp64 accumulation), gn_finish combines.
@@ -548,4 +564,15 @@ extern "C" int vb_loudness_pcm16(const float* wav, int B, int64_t n, float targe
   launch_k(loudness_apply_kernel, dim3(256, B), dim3(256), 0, s, wav, (long long)n, static_cast<const float*>(scratch),
            target_db, reinterpret_cast<short*>(out));
   return check_launch("vb_loudness_pcm16");
+}
+
+extern "C" int vb_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
+                        float wd, float c1, float c2, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_EW, stream);
+  if (!p || !g || !m || !v || n <= 0) return set_error(VB_ERR_INVALID, "vb_adamw: bad arguments");
+  int grid = grid_for(n, 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  launch_k(adamw_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), p, g, m, v, (long long)n, lr, b1, b2,
+           eps, wd, c1, c2);
+  return check_launch("vb_adamw");
 }

@@ -194,11 +194,34 @@ class TxtFlagLargeImprovedDiTV2(nn.Module):
         del self._cond_cache[:-4]
         return cond
 
-    @torch.no_grad()
     def forward(self, x, t, context):
+        """eval mode: the fused inference engine (no autograd). train mode: the differentiable tensor-core path of
+        versband_b200/train.py — soft routing, temperature / loss_w decay as in the reference."""
         if self.training:
-            raise NotImplementedError("versband_b200 implements the inference path (eval mode) only; "
-                                      "the soft-router training step is SURVEY.md §8f rank 2")
+            return self._forward_train(x, t, context)
+        with torch.no_grad():
+            return self._forward_eval(x, t, context)
+
+    def _forward_train(self, x, t, context, expo=None):
+        from . import train
+        _require_cuda(x, "TxtFlagLargeImprovedDiTV2.forward")
+        B, _, T = x.shape
+        ff = self.blocks[0].feed_forward
+        for blk in self.blocks:                     # vocal2music_moe.py:146-147 (every block decays its own copy)
+            if float(blk.feed_forward.temperature) > 0.3:
+                blk.feed_forward.temperature *= 0.9999
+        if expo is None:
+            expo = train.draw_router_noise(self.depth, B * T, self.num_experts, x.device)
+        P = dict(self.named_parameters())
+        ctx = {"c_crossattn": context["c_crossattn"].float(),
+               "c_concat": {"midi": context["c_concat"]["midi"], "beats": context["c_concat"]["beats"]}}
+        v, lb = train.dit_train_forward(P, x.float(), t.long(), ctx, expo, depth=self.depth, n_heads=self.num_heads,
+                                        num_experts=self.num_experts, temperature=float(ff.temperature), loss_w=self.loss_w)
+        if self.loss_w > 0.01:                      # :427-429
+            self.loss_w *= 0.9999
+        return v, lb
+
+    def _forward_eval(self, x, t, context):
         _require_cuda(x, "TxtFlagLargeImprovedDiTV2.forward")
         eng = self.engine()
         midi, beats = context["c_concat"]["midi"], context["c_concat"]["beats"]

@@ -312,6 +312,11 @@ def mrf_combine(rs, out, *, neg: float, scale: float, slope_out: float) -> None:
     _call("vb_mrf_combine", _ptr(rs[0]), _ptr(rs[1]), _ptr(rs[2]), neg, scale, slope_out, _ptr(out), out.numel())
 
 
+def adamw(p, g, m, v, *, lr, b1, b2, eps, wd, c1, c2) -> None:
+    assert p.dtype == g.dtype == m.dtype == v.dtype == torch.float32 and p.is_contiguous() and g.is_contiguous()
+    _call("vb_adamw", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), lr, b1, b2, eps, wd, c1, c2)
+
+
 def wave_prepare(wav, out_fp16, *, pad: int, plane: int) -> None:
     B, n = wav.shape
     _call("vb_wave_prepare", _ptr(wav), B, n, pad, plane, _ptr(out_fp16))
