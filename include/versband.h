@@ -184,6 +184,7 @@ int vb_loudness_pcm16(const float* wav, int B, int64_t n, float target_db, float
  * tensors (the MRF mean of hifigan.py:132-138), n elements (multiple of 8).
  * ------------------------------------------------------------------------------------------ */
 int vb_resblock_pair_fits(int C, int k, int dil);
+int vb_resblock_set_trace(void* device_buf); /* debug: 12 tiles x 16 clock64 stamps of CTA 0 (tools/trace_pair.py) */
 int vb_resblock_pair(const void* y_in, void* y_out, const void* w1, const void* w2, const float* b1, const float* b2,
                      int B, int T, int C, int k, int dil, float slope, void* stream);
 int vb_mrf_combine(const void* r0, const void* r1, const void* r2, float neg, float scale, float slope_out, void* out,

@@ -35,7 +35,9 @@ struct ResPairParams {
   const float* b2;
   const __half* in;
   __half* out;
+  long long* trace;  // debug (vb_resblock_set_trace): clock64 stamps of CTA 0, 16 per tile
 };
+static long long* g_pair_trace = nullptr;
 
 template <int C>
 __global__ void __launch_bounds__(576, 1)
@@ -124,9 +126,12 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
       constexpr uint64_t w_step = kWTap / 16;
       int n_local = 0;
       for (int t = first; t < p.num_tiles; t += step) ++n_local;
+      const bool trm = p.trace && blockIdx.x == 0;
       auto mma1 = [&](int i) {
         const int s = i % p.NS, acc = i & 1;
+        if (trm && i < 12) p.trace[i * 16 + 0] = clock64();
         mbar_wait(&y_full[s], (i / p.NS) & 1);
+        if (trm && i < 12) p.trace[i * 16 + 1] = clock64();
         mbar_wait(&a1_empty[acc], ((i >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + acc * C;
@@ -141,10 +146,13 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
         }
         umma_commit(&a1_full[acc]);
         umma_commit(&y_empty[s]);
+        if (trm && i < 12) p.trace[i * 16 + 2] = clock64();
       };
       auto mma2 = [&](int i) {
         const int tb = i % p.NT, acc = i & 1;
+        if (trm && i < 12) p.trace[i * 16 + 3] = clock64();
         mbar_wait(&t1_full[tb], (i / p.NT) & 1);
+        if (trm && i < 12) p.trace[i * 16 + 4] = clock64();
         mbar_wait(&a2_empty[acc], ((i >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + 2 * C + acc * C;
@@ -158,6 +166,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
         }
         umma_commit(&a2_full[acc]);
         umma_commit(&t1_empty[tb]);
+        if (trm && i < 12) p.trace[i * 16 + 5] = clock64();
       };
       // Issue order: conv1 runs TWO tiles ahead of conv2. The chain MMA1(i) -> epilogue #1 -> MMA2(i) carries
       // ~3 k cycles of fixed latency (TMEM read, smem write, proxy fence, barrier wake-ups); with conv1 only one
@@ -185,7 +194,10 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
       const int b = t / p.n_t, tt = t - b * p.n_t;
       const int time = tt * p.R - p.h2 + r;
       const bool inside = time >= 0 && time < p.T;
+      const bool tr1 = p.trace && blockIdx.x == 0 && threadIdx.x == 64 && i < 12;
+      if (tr1) p.trace[i * 16 + 6] = clock64();
       mbar_wait(&a1_full[acc], (i >> 1) & 1);
+      if (tr1) p.trace[i * 16 + 7] = clock64();
       mbar_wait(&t1_empty[tb], ((i / p.NT) & 1) ^ 1);
       tc_fence_after();
       const uint32_t row = smem_u32(smem_t + tb * t_slot) + r * 128;
@@ -215,6 +227,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core's async proxy
       mbar_arrive(&t1_full[tb]);
+      if (tr1) p.trace[i * 16 + 8] = clock64();
     }
   } else {
     // ===================== epilogue #2: acc2 + residual -> global, 8 warps =====================
@@ -239,7 +252,10 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
 #pragma unroll
         for (int ch = 0; ch < CH / 8; ++ch) res[ch] = __ldg(src + ch);
       }
+      const bool tr2 = p.trace && blockIdx.x == 0 && threadIdx.x == 320 && i < 12;
+      if (tr2) p.trace[i * 16 + 9] = clock64();
       mbar_wait(&a2_full[acc], (i >> 1) & 1);
+      if (tr2) p.trace[i * 16 + 10] = clock64();
       tc_fence_after();
       uint32_t raw[CH];
       if (CH == 32) tmem_ld32(tmem_base + 2 * C + acc * C + half * CH + lane_sel, *reinterpret_cast<uint32_t(*)[32]>(raw));
@@ -266,6 +282,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
         }
         if (valid) dst[ch] = make_uint4(w[0], w[1], w[2], w[3]);
       }
+      if (tr2) p.trace[i * 16 + 11] = clock64();
     }
   }
   tc_fence_before();
@@ -345,6 +362,11 @@ static void plan_smem(int C, int k, int dil, ResPairParams* p, int* smem_bytes) 
 
 using namespace vb;
 
+extern "C" int vb_resblock_set_trace(void* buf) {
+  vb::g_pair_trace = static_cast<long long*>(buf);
+  return VB_OK;
+}
+
 extern "C" int vb_resblock_pair_fits(int C, int k, int dil) {
   if ((C != 32 && C != 64) || k < 1 || !(k & 1) || dil < 1) return 0;
   ResPairParams p{};
@@ -367,6 +389,7 @@ extern "C" int vb_resblock_pair(const void* y_in, void* y_out, const void* w1, c
   p.T = T; p.B = B; p.C = C; p.k = k; p.dil = dil;
   p.slope = slope; p.inv_slope = 1.f / slope;
   p.b1 = b1; p.b2 = b2; p.in = static_cast<const __half*>(y_in); p.out = static_cast<__half*>(y_out);
+  p.trace = g_pair_trace;
   p.n_t = (T + p.R - 1) / p.R;
   p.num_tiles = p.n_t * B;
   CUtensorMap tmY, tmW1, tmW2;

@@ -85,6 +85,21 @@ class DiTCond:
                 getattr(out, name).append(torch.cat([getattr(c, name)[k] for c in conds], 0))
         return out
 
+    def split(self, parts: int) -> "List[DiTCond]":
+        """The inverse of `cat`: `parts` conditioning objects over equal slices of the batch (views, no copies)."""
+        assert self.B % parts == 0
+        b = self.B // parts
+        out = []
+        for i in range(parts):
+            rows = slice(i * b * self.T, (i + 1) * b * self.T)
+            c = DiTCond(B=b, T=self.T, L=self.L, acoustic=self.acoustic[rows], ac_logits=self.ac_logits[rows],
+                        caption=self.caption[i * b:(i + 1) * b], cap_emb=self.cap_emb[i * b:(i + 1) * b])
+            for name in DiTCond._LISTS:
+                for t in getattr(self, name):
+                    getattr(c, name).append(t[i * b:(i + 1) * b])
+            out.append(c)
+        return out
+
     def copy_from(self, other: "DiTCond") -> None:
         for dst, src in zip(self.tensors(), other.tensors()):
             dst.copy_(src)
@@ -234,8 +249,10 @@ class DiTEngine:
         self.w = w
 
     # ------------------------------------------------------------------ workspaces
-    def _workspace(self, B: int, T: int) -> dict:
-        key = (B, T)
+    def _workspace(self, B: int, T: int, slot: int = 0) -> dict:
+        """Per-(B, T) scratch tensors; `slot` distinguishes evaluations that run CONCURRENTLY (the sampler's two
+        CFG branches on two streams)."""
+        key = (B, T, slot)
         if key in self._ws:
             return self._ws[key]
         dev, D, H, hd, E, Fh = self.dev, self.D, self.H, self.hd, self.E, self.Fh
@@ -423,7 +440,7 @@ class DiTEngine:
     def forward(self, x: torch.Tensor, t: torch.Tensor, cond: DiTCond,
                 expo: List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]],
                 out_v: Optional[torch.Tensor] = None, want_aux: bool = False, pre=None, x_cl_ready: bool = False,
-                chain_cnt: Optional[torch.Tensor] = None):
+                chain_cnt: Optional[torch.Tensor] = None, ws_slot: int = 0, x_cl: Optional[torch.Tensor] = None):
         """x fp32 [B, C, T], t int64 [B]; expo[k] = Exp(1) draws ([N,2],[N,E],[N,E]) of block k.
         Returns v as the channels-last GEMM output [N, 32] (first C columns valid) unless `out_v`
         ([B, C, T]) is given, plus lb_loss per block (device tensor)."""
@@ -432,7 +449,9 @@ class DiTEngine:
         B = cond.B
         assert B % Bx == 0 and T == cond.T and T <= self.max_len
         N, L = B * T, cond.L
-        ws = self._workspace(B, T)
+        ws = self._workspace(B, T, ws_slot)
+        if x_cl is not None:  # caller-owned channels-last copy of the latent (shared between concurrent branches)
+            ws = dict(ws, x_cl=x_cl)
         Tp, max_rows = ws["Tp"], ws["max_rows"]
         scale = 1.0 / math.sqrt(hd)
         aux = []
