@@ -33,18 +33,26 @@ def _worker(rank, world, port, n_clips, q):
     # second step through the cached exchange: no metadata handshake, same buffers
     out2 = run_data_parallel(fake_pipeline, [midi + 1, cap] if rank == 0 else None, n_clips)
     if rank == 0:
-        q.put((out, out2.clone()))
+        q.put((out.tolist(), out2.tolist()))  # plain lists: tensors travel by fd and need the sender alive
     dist.destroy_process_group()
+
+
+def _free_port():
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
 
 
 def test_scatter_compute_gather_world2():
     ctx = mp.get_context("spawn")
     for n_clips in (5, 2):
         q = ctx.SimpleQueue()
-        procs = [ctx.Process(target=_worker, args=(r, 2, 29611 + n_clips, n_clips, q)) for r in range(2)]
+        port = _free_port()
+        procs = [ctx.Process(target=_worker, args=(r, 2, port, n_clips, q)) for r in range(2)]
         for p in procs:
             p.start()
-        out, out2 = q.get()
+        out, out2 = (torch.tensor(v) for v in q.get())
         for p in procs:
             p.join(60)
             assert p.exitcode == 0
