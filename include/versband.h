@@ -277,8 +277,41 @@ int64_t vb_voc_workspace_bytes(const vb_voc_desc* d, int B, int T);
 int vb_voc_forward(const vb_voc_desc* d, const float* mel, int B, int T, float* wav, void* workspace,
                    int64_t workspace_bytes, void* stream);
 
+/* AutoencoderKL 1-D decoder (reference ldm/models/autoencoder1d.py:480-513, ldm/models/autoencoder1d.py decode =
+ * post_quant_conv -> Decoder1D): z fp32 [B, zc, T] (multiplied by `scale`, i.e. 1/scale_factor of
+ * ddpm.py decode_first_stage) -> mel fp32 [B, out_ch, T * 2^n_up]. The decoder is described as conv_in, a flat
+ * list of layers in execution order (mid.block_1, mid.attn_1, mid.block_2, then per level: resblocks (+ attention)
+ * and the upsample), norm_out and conv_out. Packed weights as in versband_b200/vae.py:_pack: conv weights
+ * [Cout, k * ceil64(Cin)] fp16 tap-major, q|k|v 1x1 convs concatenated to [3C, C], biases and GroupNorm affine
+ * fp32. */
+#define VB_VAE_MAX_OPS 48
+#define VB_VAE_RES 0  /* ResnetBlock1D: n1 -> w1(k1) -> n2 -> w2(k2) + (ws ? ws(ks) x : x) */
+#define VB_VAE_ATTN 1 /* AttnBlock1D: n1 -> w1 = q|k|v [3C, C], b1 [3C] -> softmax(q k^T / sqrt(C)) v -> w2 = proj_out + x */
+#define VB_VAE_UP 2   /* Upsample1D: nearest x2 -> w1(k1) */
+typedef struct vb_vae_op {
+  int32_t kind, cin, cout, k1, k2, ks;
+  const float *n1_w, *n1_b, *n2_w, *n2_b;
+  const void *w1, *w2, *ws;
+  const float *b1, *b2, *bs;
+} vb_vae_op;
+typedef struct vb_vae_desc {
+  int32_t zc, zq_c, c0, out_ch, groups, n_ops, pq_k, in_k, out_k;
+  float eps;
+  const void* pq_w; /* post_quant_conv [zq_c, pq_k * ceil64(zc)] */
+  const float* pq_b;
+  const void* in_w; /* decoder.conv_in [c0, in_k * ceil64(zq_c)] */
+  const float* in_b;
+  const float *no_w, *no_b; /* decoder.norm_out */
+  const void* out_w;        /* decoder.conv_out [out_ch, out_k * ceil64(C_last)] */
+  const float* out_b;
+  vb_vae_op ops[VB_VAE_MAX_OPS];
+} vb_vae_desc;
+int64_t vb_vae_workspace_bytes(const vb_vae_desc* d, int B, int T);
+int vb_vae_decode(const vb_vae_desc* d, const float* z, float scale, int B, int T, float* mel, void* workspace,
+                  int64_t workspace_bytes, void* stream);
+
 /* sizeof() of the public structs as compiled (ABI self-check for bindings): 0 = vb_gemm_args, 1 = vb_attn_args,
- * 2 = vb_voc_desc */
+ * 2 = vb_voc_desc, 3 = vb_vae_desc */
 int vb_sizeof(int which);
 /* number of kernels this library has launched in this process */
 long long vb_launch_count(void);

@@ -102,3 +102,15 @@ def test_hifigan_c_entry_point_equals_python_launch_sequence(voc):
     torch.cuda.synchronize()
     assert a.shape == b.shape == (2, 64 * 320)
     assert torch.equal(a, b)
+
+
+def test_vae_c_entry_point_equals_python_launch_sequence(vae):
+    """vb_vae_decode (post_quant_conv + Decoder1D issued from C++ through one C-ABI call) vs the same launches from
+    Python, at a ragged length and at the BASELINE length."""
+    for B, T in ((2, 50), (1, 750)):
+        z = torch.randn(B, synth.VAE_EMBED_DIM, T, generator=torch.Generator().manual_seed(5)).cuda()
+        a = vae.decode(z, scale=0.7)
+        b = vae.decode_py(z, scale=0.7)
+        torch.cuda.synchronize()
+        assert a.shape == b.shape == (B, 80, 2 * T)
+        assert torch.equal(a, b)

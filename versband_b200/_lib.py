@@ -73,6 +73,27 @@ class VocDesc(C.Structure):
     ]
 
 
+VAE_MAX_OPS = 48
+VAE_RES, VAE_ATTN, VAE_UP = 0, 1, 2
+
+
+class VaeOp(C.Structure):
+    """Mirror of `struct vb_vae_op`."""
+
+    _fields_ = [("kind", c_i32), ("cin", c_i32), ("cout", c_i32), ("k1", c_i32), ("k2", c_i32), ("ks", c_i32),
+                ("n1_w", c_ptr), ("n1_b", c_ptr), ("n2_w", c_ptr), ("n2_b", c_ptr),
+                ("w1", c_ptr), ("w2", c_ptr), ("ws", c_ptr), ("b1", c_ptr), ("b2", c_ptr), ("bs", c_ptr)]
+
+
+class VaeDesc(C.Structure):
+    """Mirror of `struct vb_vae_desc`."""
+
+    _fields_ = [("zc", c_i32), ("zq_c", c_i32), ("c0", c_i32), ("out_ch", c_i32), ("groups", c_i32), ("n_ops", c_i32),
+                ("pq_k", c_i32), ("in_k", c_i32), ("out_k", c_i32), ("eps", c_f32),
+                ("pq_w", c_ptr), ("pq_b", c_ptr), ("in_w", c_ptr), ("in_b", c_ptr), ("no_w", c_ptr), ("no_b", c_ptr),
+                ("out_w", c_ptr), ("out_b", c_ptr), ("ops", VaeOp * VAE_MAX_OPS)]
+
+
 class VersbandError(RuntimeError):
     pass
 
@@ -102,6 +123,11 @@ def lib() -> C.CDLL:
         _lib.vb_voc_workspace_bytes.restype = c_i64
         if _lib.vb_sizeof(2) != C.sizeof(VocDesc):
             raise VersbandError("vb_voc_desc ABI mismatch between versband.h and _lib.py")
+        _lib.vb_vae_decode.argtypes = [C.POINTER(VaeDesc), c_ptr, c_f32, c_i32, c_i32, c_ptr, c_ptr, c_i64, c_ptr]
+        _lib.vb_vae_workspace_bytes.argtypes = [C.POINTER(VaeDesc), c_i32, c_i32]
+        _lib.vb_vae_workspace_bytes.restype = c_i64
+        if _lib.vb_sizeof(3) != C.sizeof(VaeDesc):
+            raise VersbandError("vb_vae_desc ABI mismatch between versband.h and _lib.py")
         if _lib.vb_sizeof(0) != C.sizeof(GemmArgs):
             raise VersbandError("vb_gemm_args ABI mismatch between versband.h and _lib.py")
     return _lib

@@ -106,6 +106,7 @@ extern "C" int vb_sizeof(int which) {
     case 0: return (int)sizeof(vb_gemm_args);
     case 1: return (int)sizeof(vb_attn_args);
     case 2: return (int)sizeof(vb_voc_desc);
+    case 3: return (int)sizeof(vb_vae_desc);
     default: return -1;
   }
 }

@@ -123,9 +123,82 @@ class VAEEngine:
         return out
 
     # ------------------------------------------------------------------ decoder
+    def _decoder_layers(self):
+        """(kind, name) of every decoder layer in execution order (autoencoder1d.py:480-513)."""
+        d = "decoder."
+        layers = [("res", d + "mid.block_1"), ("attn", d + "mid.attn_1"), ("res", d + "mid.block_2")]
+        for lvl in reversed(range(self.n_levels)):
+            for blk in range(self.n_res + 1):
+                layers.append(("res", f"{d}up.{lvl}.block.{blk}"))
+                if f"{d}up.{lvl}.attn.{blk}.norm.weight" in self.w:
+                    layers.append(("attn", f"{d}up.{lvl}.attn.{blk}"))
+            if lvl in self.up_levels:
+                layers.append(("up", f"{d}up.{lvl}.upsample.conv"))
+        return layers
+
+    def _desc(self):
+        """The decoder as a `vb_vae_desc` (include/versband.h) for vb_vae_decode."""
+        if getattr(self, "_vae_desc", None) is not None:
+            return self._vae_desc
+        from ._lib import VAE_ATTN, VAE_MAX_OPS, VAE_RES, VAE_UP, VaeDesc
+        w, k, P = self.w, self.k, ops._ptr
+        d = "decoder."
+        ds = VaeDesc()
+        ds.zc, ds.zq_c = self.embed_dim, w["post_quant_conv.w"].shape[0]
+        ds.c0, ds.out_ch, ds.groups, ds.eps = w[d + "conv_in.w"].shape[0], w[d + "conv_out.w"].shape[0], self.G, 1e-6
+        ds.pq_k, ds.in_k, ds.out_k = k["post_quant_conv"], k[d + "conv_in"], k[d + "conv_out"]
+        ds.pq_w, ds.pq_b = P(w["post_quant_conv.w"]), P(w["post_quant_conv.bias"])
+        ds.in_w, ds.in_b = P(w[d + "conv_in.w"]), P(w[d + "conv_in.bias"])
+        ds.no_w, ds.no_b = P(w[d + "norm_out.weight"]), P(w[d + "norm_out.bias"])
+        ds.out_w, ds.out_b = P(w[d + "conv_out.w"]), P(w[d + "conv_out.bias"])
+        layers = self._decoder_layers()
+        assert len(layers) <= VAE_MAX_OPS
+        ds.n_ops = len(layers)
+        for o, (kind, n) in zip(ds.ops, layers):
+            if kind == "res":
+                o.kind, o.cout = VAE_RES, w[n + ".conv1.w"].shape[0]
+                o.cin = w[n + ".norm1.weight"].shape[0]
+                o.k1, o.k2 = k[n + ".conv1"], k[n + ".conv2"]
+                o.n1_w, o.n1_b, o.n2_w, o.n2_b = (P(w[n + s]) for s in (".norm1.weight", ".norm1.bias", ".norm2.weight", ".norm2.bias"))
+                o.w1, o.b1, o.w2, o.b2 = P(w[n + ".conv1.w"]), P(w[n + ".conv1.bias"]), P(w[n + ".conv2.w"]), P(w[n + ".conv2.bias"])
+                if (n + ".nin_shortcut.w") in w:
+                    o.ws, o.bs, o.ks = P(w[n + ".nin_shortcut.w"]), P(w[n + ".nin_shortcut.bias"]), k[n + ".nin_shortcut"]
+            elif kind == "attn":
+                o.kind = VAE_ATTN
+                o.cin = o.cout = w[n + ".norm.weight"].shape[0]
+                assert k[n + ".q"] == 1 and k[n + ".proj_out"] == 1
+                o.k1, o.k2 = 1, 1
+                o.n1_w, o.n1_b = P(w[n + ".norm.weight"]), P(w[n + ".norm.bias"])
+                o.w1, o.b1, o.w2, o.b2 = P(w[n + ".qkv.w"]), P(w[n + ".qkv.bias"]), P(w[n + ".proj_out.w"]), P(w[n + ".proj_out.bias"])
+            else:
+                o.kind, o.cout, o.k1 = VAE_UP, w[n + ".w"].shape[0], k[n]
+                o.cin = o.cout
+                o.w1, o.b1 = P(w[n + ".w"]), P(w[n + ".bias"])
+        self._vae_desc = ds
+        return ds
+
     @torch.no_grad()
     def decode(self, z: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
-        """z fp32 [B, zc, T] (already divided by scale_factor if scale != 1) -> mel fp32 [B, out_ch, T*2^n]."""
+        """z fp32 [B, zc, T] (multiplied by `scale` = 1/scale_factor) -> mel fp32 [B, out_ch, T*2^n]: one call of
+        the model-level C entry point vb_vae_decode (csrc/vb_model.cu), which issues the launch sequence."""
+        import ctypes as C
+        from . import _lib
+        B, zc, T = z.shape
+        z = z.to(self.dev, F32).contiguous()
+        ds = self._desc()
+        need = _lib.lib().vb_vae_workspace_bytes(C.byref(ds), B, T)
+        if need < 0:
+            _lib.check(1, "vb_vae_workspace_bytes")
+        ws = torch.empty(need, device=self.dev, dtype=torch.uint8)
+        mel = torch.empty(B, ds.out_ch, T * 2 ** len(self.up_levels), device=self.dev, dtype=F32)
+        _lib.check(_lib.lib().vb_vae_decode(C.byref(ds), ops._ptr(z), float(scale), B, T, ops._ptr(mel),
+                                            ops._ptr(ws), need, ops._stream()), "vb_vae_decode")
+        return mel
+
+    @torch.no_grad()
+    def decode_py(self, z: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+        """The same launch sequence issued op by op from Python (kept as the readable statement of decode and as
+        the cross-check of the C entry point, tests/test_vae_vocoder_gpu.py)."""
         B, zc, T = z.shape
         dev = self.dev
         zp = (zc + 7) // 8 * 8
