@@ -13,7 +13,7 @@ for r in csv.DictReader(lines):
     if not r.get("Metric Name", "").startswith("dram__bytes"):
         continue
     name = r["Kernel Name"].split("(")[0].replace("void ", "")
-    gemm = any(k in name for k in ("vb_gemm_kernel", "vb_gemm2_kernel", "vb_conv_halo_kernel"))
+    gemm = any(k in name for k in ("vb_gemm_kernel", "vb_gemm2_kernel", "vb_conv_halo_kernel", "vb_chain_kernel"))
     fam = "vb_gemm_kernel" if gemm else ("attn_fused_kernel" if "attn_fused" in name else name)  # all tcgen05 GEMM kernels
     agg[fam][1] += float(r["Metric Value"].replace(",", "")) * mult.get(r.get("Metric Unit", "byte"), 1)
     ids[fam].add(r["ID"])
