@@ -310,8 +310,66 @@ int64_t vb_vae_workspace_bytes(const vb_vae_desc* d, int B, int T);
 int vb_vae_decode(const vb_vae_desc* d, const float* z, float scale, int B, int T, float* mel, void* workspace,
                   int64_t workspace_bytes, void* stream);
 
+/* One evaluation of the AccompBand DiT (reference TxtFlagLargeDiT.forward, vocal2music_moe.py:375-434) as ONE call:
+ * the launch sequence of versband_b200/dit.py:DiTEngine.forward issued from C++ (vb_model.cu). Weights are device
+ * pointers in the packed layouts of DiTEngine.pack (operand dtype = fp16, or fp32 with operand_f32 = 1); the
+ * step-invariant conditioning (DiTEngine.prepare: acoustic stem, caption K/V of every block, folded caption gate)
+ * is a vb_dit_cond; per-call inputs and outputs are a vb_dit_io. B = rows of the conditioning batch (the CFG pair
+ * of one clip is B = 2), N = B * T tokens.
+ * Workspace: vb_dit_workspace_bytes(d, B, T) bytes, ZERO-FILLED by the caller before its first use and then left to
+ * this (d, B, T) — it carries the MoE bucket counters from one call to the next. */
+#define VB_DIT_MAX_DEPTH 16
+typedef struct vb_dit_block {
+  const void *wqkv, *wo;                      /* [3D, D], [D, D] */
+  const float *gate, *attn_norm, *ffn_norm;   /* [H], [D], [D] */
+  const float* capg_b;                        /* [E]: W_gate b_out_proj + b_gate */
+  const void *w13, *w2;                       /* routed experts [2E, 2Fh, D] ((w1,w3) row pairs), [2E, D, Fh] */
+  const void *f13, *f2;                       /* frequency experts [E, 2Fh, 2*band], [E, band, Fh] */
+} vb_dit_block;
+typedef struct vb_dit_desc {
+  int32_t C, D, depth, H, E, Fh, max_len, proj_in_k, operand_f32;
+  float eps, temperature;
+  int64_t mod_ld;                             /* depth*6D + 2D */
+  const void* proj_in_w;                      /* [D, proj_in_k * kq] */
+  const float* proj_in_b;
+  const void *t_w0, *t_w2, *ada_w;            /* [D,256], [D,D], [mod_ld, D] */
+  const float *t_b0, *t_b2, *ada_b, *t_freqs; /* t_freqs [128] */
+  const float *hl_w, *hl_b;                   /* group gates of all blocks [2*depth, D], [2*depth] */
+  const void* final_w;                        /* [32, D] (rows >= C zero) */
+  const float* final_b;                       /* [32] */
+  const float* rope;                          /* [max_len, hd/2, 2] */
+  vb_dit_block blocks[VB_DIT_MAX_DEPTH];
+} vb_dit_desc;
+typedef struct vb_dit_cond {
+  int32_t B, T, L, Lp;
+  const float *acoustic, *ac_logits, *cap_emb; /* [N, D], [N, depth*E], [B, D] */
+  const void* k_y[VB_DIT_MAX_DEPTH];           /* fp16 [B, H, L, hd] */
+  const void* vt_y[VB_DIT_MAX_DEPTH];          /* fp16 [B, H, hd, Lp] */
+  const void* wk_m[VB_DIT_MAX_DEPTH];          /* operand dtype [B, H*96, D] */
+  const float* bs_m[VB_DIT_MAX_DEPTH];         /* [B, H, 96] */
+  const float* vg_m[VB_DIT_MAX_DEPTH];         /* [B, H, 96, E] */
+} vb_dit_cond;
+typedef struct vb_dit_io {
+  const float* x;     /* latent fp32 [Bx, C, T]; it feeds every group of Bx conditioning rows (CFG batching) */
+  int32_t Bx;
+  int32_t x_cl_ready; /* 1: x_cl already holds the channels-last latent of all B rows (x is not read) */
+  void* x_cl;         /* optional caller-owned [B, T, 32] operand-dtype buffer (NULL: workspace) */
+  const int64_t* t;   /* [B] integer timesteps; read only when mod / hl are NULL */
+  const float* mod;   /* optional precomputed adaLN vectors [B, mod_ld] ... */
+  const float* hl;    /* ... and group-gate logits [B, 2*depth] (the sampler precomputes all steps at once) */
+  const float* e0[VB_DIT_MAX_DEPTH]; /* Exp(1) draws of the Gumbel router per block: [N, 2], */
+  const float* e1[VB_DIT_MAX_DEPTH]; /* [N, E] (caption group), */
+  const float* e2[VB_DIT_MAX_DEPTH]; /* [N, E] (acoustic group) */
+  float* v;           /* out: velocity, channels-last fp32 [N, 32] (first C columns valid) */
+  float* out_v;       /* optional out: [B, C, T] */
+  float* lb;          /* out: load-balance loss per block [depth] */
+} vb_dit_io;
+int64_t vb_dit_workspace_bytes(const vb_dit_desc* d, int B, int T);
+int vb_dit_forward(const vb_dit_desc* d, const vb_dit_cond* cond, const vb_dit_io* io, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+
 /* sizeof() of the public structs as compiled (ABI self-check for bindings): 0 = vb_gemm_args, 1 = vb_attn_args,
- * 2 = vb_voc_desc, 3 = vb_vae_desc */
+ * 2 = vb_voc_desc, 3 = vb_vae_desc, 4 = vb_dit_desc, 5 = vb_dit_cond, 6 = vb_dit_io */
 int vb_sizeof(int which);
 /* number of kernels this library has launched in this process */
 long long vb_launch_count(void);

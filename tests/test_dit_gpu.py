@@ -125,3 +125,33 @@ def test_forward_tf32_vs_oracle(engine_tf32, weights, B, T):
     print(f"tf32: router agreement {agree}/{total}; v max {float(d.max()) / peak:.2e} median {float(d.median()) / peak:.2e} rel-L2 {l2:.2e}")
     assert agree >= total - 2
     assert float(d.median()) / peak < 1e-3 and l2 < 3e-3
+
+
+@pytest.mark.parametrize("precision,B,T", [("fp16", 2, 750), ("fp16", 3, 50), ("tf32", 2, 64)])
+def test_c_entry_point_equals_python_launch_sequence(weights, precision, B, T):
+    """vb_dit_forward (one DiT evaluation issued from C++ through one C-ABI call, include/versband.h) vs the same
+    launches issued from Python: bit-identical velocity and load-balance loss, with the time conditioning computed
+    inside the call and with it precomputed, over two consecutive calls (the workspace carries the MoE bucket
+    counters from one call to the next)."""
+    eng = DiTEngine(weights, device=DEV, precision=precision)
+    x, midi, beats, cap, _ = synth.dit_inputs(B, T, seed=3)
+    t = torch.tensor([125, 833, 41][:B]).to(DEV)
+    cond = eng.prepare(midi.to(DEV), beats.to(DEV), cap.to(DEV), T)
+    expo = [tuple(e.to(DEV) for e in blk) for blk in synth.exp_noise(4, B * T, 4, seed=5)]
+    x = x.to(DEV)
+    for call in range(2):
+        out_c, out_p = torch.zeros_like(x), torch.zeros_like(x)
+        v_c, lb_c = eng.forward(x, t, cond, expo, out_v=out_c)
+        v_c, lb_c = v_c.clone(), lb_c.clone()
+        v_p, lb_p = eng.forward_py(x, t, cond, expo, out_v=out_p)
+        torch.cuda.synchronize()
+        assert torch.equal(v_c, v_p) and torch.equal(out_c, out_p) and torch.equal(lb_c, lb_p)
+        x = x + 0.1 * out_c
+    # precomputed modulation vectors (the sampler's path)
+    mod = torch.empty(B, eng.mod_ld, device=DEV)
+    hl = torch.empty(B, 2 * eng.depth, device=DEV)
+    eng.time_conditioning(t, cond.cap_emb, mod, hl)
+    v_c = eng.forward(x, t, cond, expo, pre=(mod, hl))[0].clone()
+    v_p = eng.forward_py(x, t, cond, expo, pre=(mod, hl))[0]
+    torch.cuda.synchronize()
+    assert torch.equal(v_c, v_p)

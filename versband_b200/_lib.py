@@ -94,6 +94,40 @@ class VaeDesc(C.Structure):
                 ("out_w", c_ptr), ("out_b", c_ptr), ("ops", VaeOp * VAE_MAX_OPS)]
 
 
+DIT_MAX_DEPTH = 16
+
+
+class DitBlock(C.Structure):
+    """Mirror of `struct vb_dit_block`."""
+
+    _fields_ = [(n, c_ptr) for n in ("wqkv", "wo", "gate", "attn_norm", "ffn_norm", "capg_b", "w13", "w2", "f13", "f2")]
+
+
+class DitDesc(C.Structure):
+    """Mirror of `struct vb_dit_desc`."""
+
+    _fields_ = [("C", c_i32), ("D", c_i32), ("depth", c_i32), ("H", c_i32), ("E", c_i32), ("Fh", c_i32),
+                ("max_len", c_i32), ("proj_in_k", c_i32), ("operand_f32", c_i32), ("eps", c_f32), ("temperature", c_f32),
+                ("mod_ld", c_i64)] + [(n, c_ptr) for n in (
+                    "proj_in_w", "proj_in_b", "t_w0", "t_w2", "ada_w", "t_b0", "t_b2", "ada_b", "t_freqs", "hl_w", "hl_b",
+                    "final_w", "final_b", "rope")] + [("blocks", DitBlock * DIT_MAX_DEPTH)]
+
+
+class DitCond(C.Structure):
+    """Mirror of `struct vb_dit_cond`."""
+
+    _fields_ = [("B", c_i32), ("T", c_i32), ("L", c_i32), ("Lp", c_i32), ("acoustic", c_ptr), ("ac_logits", c_ptr),
+                ("cap_emb", c_ptr)] + [(n, c_ptr * DIT_MAX_DEPTH) for n in ("k_y", "vt_y", "wk_m", "bs_m", "vg_m")]
+
+
+class DitIO(C.Structure):
+    """Mirror of `struct vb_dit_io`."""
+
+    _fields_ = [("x", c_ptr), ("Bx", c_i32), ("x_cl_ready", c_i32), ("x_cl", c_ptr), ("t", c_ptr), ("mod", c_ptr),
+                ("hl", c_ptr), ("e0", c_ptr * DIT_MAX_DEPTH), ("e1", c_ptr * DIT_MAX_DEPTH), ("e2", c_ptr * DIT_MAX_DEPTH),
+                ("v", c_ptr), ("out_v", c_ptr), ("lb", c_ptr)]
+
+
 class VersbandError(RuntimeError):
     pass
 
@@ -128,6 +162,12 @@ def lib() -> C.CDLL:
         _lib.vb_vae_workspace_bytes.restype = c_i64
         if _lib.vb_sizeof(3) != C.sizeof(VaeDesc):
             raise VersbandError("vb_vae_desc ABI mismatch between versband.h and _lib.py")
+        _lib.vb_dit_forward.argtypes = [C.POINTER(DitDesc), C.POINTER(DitCond), C.POINTER(DitIO), c_ptr, c_i64, c_ptr]
+        _lib.vb_dit_workspace_bytes.argtypes = [C.POINTER(DitDesc), c_i32, c_i32]
+        _lib.vb_dit_workspace_bytes.restype = c_i64
+        for which, st in ((4, DitDesc), (5, DitCond), (6, DitIO)):
+            if _lib.vb_sizeof(which) != C.sizeof(st):
+                raise VersbandError(f"{st.__name__} ABI mismatch between versband.h and _lib.py")
         if _lib.vb_sizeof(0) != C.sizeof(GemmArgs):
             raise VersbandError("vb_gemm_args ABI mismatch between versband.h and _lib.py")
     return _lib

@@ -107,6 +107,9 @@ extern "C" int vb_sizeof(int which) {
     case 1: return (int)sizeof(vb_attn_args);
     case 2: return (int)sizeof(vb_voc_desc);
     case 3: return (int)sizeof(vb_vae_desc);
+    case 4: return (int)sizeof(vb_dit_desc);
+    case 5: return (int)sizeof(vb_dit_cond);
+    case 6: return (int)sizeof(vb_dit_io);
     default: return -1;
   }
 }

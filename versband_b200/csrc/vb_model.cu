@@ -379,3 +379,241 @@ extern "C" int vb_vae_decode(const vb_vae_desc* d, const float* z, float scale, 
   if (need > ws_bytes) return set_error(VB_ERR_INVALID, "vb_vae_decode: workspace too small (%lld bytes needed)", (long long)need);
   return vae_run(d, z, scale, B, T, mel, ws, ws_bytes, stream, nullptr);
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// One evaluation of the AccompBand DiT (reference TxtFlagLargeDiT.forward, vocal2music_moe.py:375-434, with the
+// step-invariant part precomputed: vb_dit_cond): the launch sequence of versband_b200/dit.py:DiTEngine.forward
+// issued from C++. 12 launches per block (norm+modulate, q|k|v+RoPE, fused attention, wo+gate+residual,
+// norm+modulate, caption-gate GEMM, router, dispatch, 4 expert GEMMs) + stem + final layer.
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+// vb_gemm operand views, innermost dimension first; size-1 / broadcast dimensions get any 16-byte-multiple stride
+// (their coordinate is always 0) — the rule of ops.py:_rev_desc
+void fill_degenerate(int64_t* dims, int64_t* strides, int rank) {
+  int64_t ext = 1;
+  for (int i = 0; i < rank; ++i) {
+    if (i > 0 && (dims[i] == 1 || strides[i] == 0)) strides[i] = pad8(ext) > 8 ? pad8(ext) : 8;
+    const int64_t e = dims[i] * (strides[i] > 1 ? strides[i] : 1);
+    if (e > ext) ext = e;
+  }
+}
+void set_a(vb_gemm_args& g, const void* p, int64_t d0, int64_t d1, int64_t s1, int64_t d2 = 1, int64_t s2 = 0, int64_t d3 = 1,
+           int64_t s3 = 0) {
+  g.a = p;
+  g.a_dims[0] = d0; g.a_dims[1] = d1; g.a_dims[2] = d2; g.a_dims[3] = d3;
+  g.a_strides[0] = 1; g.a_strides[1] = s1; g.a_strides[2] = s2; g.a_strides[3] = s3;
+  fill_degenerate(g.a_dims, g.a_strides, 4);
+}
+void set_b(vb_gemm_args& g, const void* p, int64_t d0, int64_t d1, int64_t s1, int64_t d2 = 1, int64_t s2 = 0) {
+  g.b = p;
+  g.b_dims[0] = d0; g.b_dims[1] = d1; g.b_dims[2] = d2;
+  g.b_strides[0] = 1; g.b_strides[1] = s1; g.b_strides[2] = s2;
+  fill_degenerate(g.b_dims, g.b_strides, 3);
+}
+
+struct DitCtx {
+  const vb_dit_desc* d;
+  void* stream;
+  bool dry;
+  int rc;
+  bool f32;  // TF32 mode: GEMM operands are fp32 tensors
+  int kq;    // elements per 128-byte k-block
+  template <class F> void run(F&& f) { if (!dry && !rc) rc = f(); }
+  int64_t es() const { return f32 ? 4 : 2; }
+  vb_gemm_args args(int M, int N, int K) const {
+    vb_gemm_args g = plain_args();
+    g.operand_f32 = f32;
+    g.M = M; g.N = N; g.K = (K + kq - 1) / kq * kq;
+    g.G1 = 1; g.G2 = 1;
+    g.rows_out = M;
+    return g;
+  }
+  // the operand-output slot of a GEMM / row op: fp16, or fp32 in TF32 mode
+  void out_op(vb_gemm_args& g, void* p, int64_t ld) const { g.out_fp16 = p; g.outb_ld = ld; g.outb_f32 = f32; }
+  void gemm(const vb_gemm_args& g) { run([&] { return vb_gemm(&g, stream); }); }
+  void norm_mod(int kind, const float* x, const float* w, const float* shift, const float* scale, int64_t mod_ld,
+                int rows_per_batch, float eps, void* out_op_, int rows, int D) {
+    run([&] {
+      return vb_norm_mod(kind, x, w, nullptr, shift, scale, mod_ld, rows_per_batch, eps, f32 ? nullptr : out_op_,
+                         f32 ? static_cast<float*>(out_op_) : nullptr, rows, D, stream);
+    });
+  }
+};
+
+}  // namespace
+
+static int dit_run(const vb_dit_desc* d, const vb_dit_cond* c, const vb_dit_io* io, void* ws, int64_t ws_bytes, void* stream,
+                   int B, int T, int64_t* need) {
+  const bool dry = need != nullptr;
+  if (!d || B <= 0 || T <= 0) return set_error(VB_ERR_INVALID, "vb_dit_forward: bad arguments");
+  const int D = d->D, H = d->H, E = d->E, Fh = d->Fh, depth = d->depth, C = d->C;
+  if (depth < 1 || depth > VB_DIT_MAX_DEPTH || H <= 0 || D % H || E != 4 || D % E || C > 32 || T > d->max_len)
+    return set_error(VB_ERR_INVALID, "vb_dit_forward: unsupported model (depth 1..%d, 4 experts, in_channels <= 32, T <= max_len)",
+                     VB_DIT_MAX_DEPTH);
+  const int hd = D / H, band = D / E, LK = 96;
+  const int N = B * T, Tp = (T + 7) / 8 * 8;
+  const int max_rows = ((2 * N + 127) / 128 + 2 * E) * 128;
+  const int64_t mld = d->mod_ld;
+  DitCtx x{d, stream, dry, 0, d->operand_f32 != 0, d->operand_f32 ? 32 : 64};
+  const int64_t es = x.es();
+  Bump bump{static_cast<uint8_t*>(dry ? nullptr : ws), 0, ws_bytes};
+  auto f32buf = [&](int64_t n) { return static_cast<float*>(bump.take(n * 4)); };
+  auto i32buf = [&](int64_t n) { return static_cast<int32_t*>(bump.take(n * 4)); };
+  // cross-call state first (block k's dispatch re-zeroes block k+1's counters): zero at first use
+  int32_t* bucket_count = i32buf((int64_t)depth * 2 * E);
+  float* usage = f32buf((int64_t)depth * 2 * E);
+  void* x_cl_own = bump.take((int64_t)B * T * 32 * es);
+  float* xs_ = f32buf((int64_t)N * D);
+  float* hbuf = f32buf((int64_t)N * D);
+  void* xa = bump.take((int64_t)N * D * es);
+  void* q = bump.take((int64_t)N * D * 2);
+  void* k = bump.take((int64_t)N * D * 2);
+  void* vt = bump.take((int64_t)B * H * hd * Tp * 2);
+  void* oa = bump.take((int64_t)N * D * es);
+  void* xm = bump.take((int64_t)N * D * es);
+  float* cap_part = f32buf((int64_t)N * H * E);
+  int32_t *idx_c = i32buf(N), *idx_a = i32buf(N), *slot_c = i32buf(N), *slot_a = i32buf(N);
+  float *scale_c = f32buf(N), *scale_a = f32buf(N);
+  int32_t* bucket_start = i32buf(2 * E);
+  int32_t* row_map = i32buf(max_rows);
+  float* row_scale = f32buf(max_rows);
+  int32_t* tile_group = i32buf(max_rows / 128);
+  int32_t* m_tiles = i32buf(1);
+  void* xsb = bump.take((int64_t)max_rows * D * es);
+  void* hs = bump.take((int64_t)max_rows * Fh * es);
+  void* y2 = bump.take((int64_t)2 * N * D * es);
+  void* hf = bump.take((int64_t)E * N * Fh * es);
+  void* xf = bump.take((int64_t)N * D * es);
+  void* tsin = bump.take((int64_t)B * 256 * es);
+  void* th = bump.take((int64_t)B * D * es);
+  float* temb = f32buf((int64_t)B * D);
+  void* ada = bump.take((int64_t)B * D * es);
+  float* mod_own = f32buf((int64_t)B * mld);
+  float* hl_own = f32buf((int64_t)B * 2 * depth);
+  if (dry) { *need = (bump.off + 255) & ~int64_t(255); return VB_OK; }
+  if (bump.off > ws_bytes) return set_error(VB_ERR_INVALID, "vb_dit_forward: workspace too small (%lld bytes needed)", (long long)bump.off);
+  if (!c || !io || !io->v || !io->lb || c->B != B || c->T != T || c->L > LK || (!io->x_cl_ready && (!io->x || io->Bx <= 0 || B % io->Bx)))
+    return set_error(VB_ERR_INVALID, "vb_dit_forward: bad conditioning / io block");
+  void* x_cl = io->x_cl ? io->x_cl : x_cl_own;
+  if (io->x_cl_ready && !io->x_cl) return set_error(VB_ERR_INVALID, "vb_dit_forward: x_cl_ready without x_cl");
+
+  // ---- stem: proj_in conv + bias + acoustic (vocal2music_moe.py:395,415); CFG batching: the same latent feeds
+  // every group of Bx conditioning rows
+  if (!io->x_cl_ready)
+    for (int r = 0; r < B / io->Bx; ++r)
+      x.run([&] {
+        return vb_nct_to_ntc(io->x, 1.f, static_cast<uint8_t*>(x_cl) + (int64_t)r * io->Bx * T * 32 * es, io->Bx, C, T, 32, x.f32, stream);
+      });
+  {
+    const int K = d->proj_in_k * x.kq;
+    vb_gemm_args g = x.args(T, D, K);
+    set_a(g, x_cl, C, T, 32, B, (int64_t)T * 32);
+    set_b(g, d->proj_in_w, K, D, K);
+    g.G1 = B; g.kpt = 1; g.dil = 1; g.pad = d->proj_in_k / 2; g.a_c2_g1 = 1;
+    g.bias = d->proj_in_b; g.residual = c->acoustic;
+    g.out_f32 = xs_; g.out_ld = D; g.out_g1 = (int64_t)T * D;
+    x.gemm(g);
+  }
+  // ---- timestep embedding MLP, adaLN vectors of every block + final layer, group-gate logits (:406,416,242,290)
+  const float *mod = io->mod, *hl = io->hl;
+  if (!mod || !hl) {
+    if (!io->t) return set_error(VB_ERR_INVALID, "vb_dit_forward: neither timesteps nor precomputed modulation given");
+    x.run([&] { return vb_timestep_embed(io->t, d->t_freqs, x.f32 ? static_cast<float*>(tsin) : nullptr, x.f32 ? nullptr : tsin, B, 256, stream); });
+    { vb_gemm_args g = x.args(B, D, 256); set_a(g, tsin, 256, B, 256); set_b(g, d->t_w0, 256, D, 256);
+      g.bias = d->t_b0; g.act = VB_ACT_SILU; x.out_op(g, th, D); x.gemm(g); }
+    { vb_gemm_args g = x.args(B, D, D); set_a(g, th, D, B, D); set_b(g, d->t_w2, D, D, D);
+      g.bias = d->t_b2; g.out_f32 = temb; g.out_ld = D; x.gemm(g); }
+    x.run([&] { return vb_ew(temb, c->cap_emb, 1.f, 1.f, VB_ACT_SILU, 0.f, x.f32 ? static_cast<float*>(ada) : nullptr, x.f32 ? nullptr : ada, B, D, 1, stream); });
+    { vb_gemm_args g = x.args(B, (int)mld, D); set_a(g, ada, D, B, D); set_b(g, d->ada_w, D, mld, D);
+      g.bias = d->ada_b; g.out_f32 = mod_own; g.out_ld = mld; x.gemm(g); }
+    x.run([&] { return vb_linear_small(temb, D, d->hl_w, d->hl_b, hl_own, B, D, 2 * depth, stream); });
+    mod = mod_own; hl = hl_own;
+  }
+  float* xcur = xs_;
+  const float scale = 1.f / sqrtf((float)hd);
+  for (int kb = 0; kb < depth && !x.rc; ++kb) {
+    const vb_dit_block& b = d->blocks[kb];
+    const float* m0 = mod + (int64_t)kb * 6 * D;
+    // ---- attention branch (vocal2music_moe.py:245-250; flag_large_dit_moe.py:323-406)
+    x.norm_mod(0, xcur, b.attn_norm, m0, m0 + D, mld, T, d->eps, xa, N, D);
+    { vb_gemm_args g = x.args(N, 3 * D, D); set_a(g, xa, D, N, D); set_b(g, b.wqkv, D, 3 * D, D);
+      g.mode = VB_EPI_QKV_ROPE; g.rope_cs = d->rope; g.T = T; g.heads = H; g.head_dim = hd; g.Tp = Tp;
+      g.q_out = q; g.k_out = k; g.vt_out = vt; x.gemm(g); }
+    {
+      vb_attn_args a;
+      memset(&a, 0, sizeof(a));
+      a.q = q; a.q_st = hd; a.q_sh = (int64_t)T * hd; a.q_sb = (int64_t)H * T * hd;
+      a.k_self = k; a.vt_self = vt; a.k_text = c->k_y[kb]; a.vt_text = c->vt_y[kb];
+      a.gate = b.gate;
+      a.out_fp16 = x.f32 ? nullptr : oa; a.out_f32 = x.f32 ? static_cast<float*>(oa) : nullptr;
+      a.B = B; a.T = T; a.H = H; a.hd = hd; a.Tp = Tp; a.L = c->L; a.Lp = c->Lp; a.scale = scale;
+      x.run([&] { return vb_attn_fused(&a, stream); });
+    }
+    { vb_gemm_args g = x.args(N, D, D); set_a(g, oa, D, N, D); set_b(g, b.wo, D, D, D);
+      g.gate = m0 + 2 * D; g.gate_rows = T; g.gate_ld = mld; g.residual = xcur; g.out_f32 = hbuf; g.out_ld = D; x.gemm(g); }
+    // ---- Band-MoE branch (vocal2music_moe.py:251-257, 117-185)
+    x.norm_mod(0, hbuf, b.ffn_norm, m0 + 3 * D, m0 + 4 * D, mld, T, d->eps, xm, N, D);
+    { vb_gemm_args g = x.args(T, H * LK, D);  // caption gate: per-head softmax(xm . WK^T + bias) . VG in the epilogue
+      set_a(g, xm, D, T, D, B, (int64_t)T * D); set_b(g, c->wk_m[kb], D, H * LK, D, B, (int64_t)H * LK * D);
+      g.G1 = B; g.a_c2_g1 = 1; g.b_c2_g1 = 1; g.mode = VB_EPI_ROUTE;
+      g.bias = c->bs_m[kb]; g.bias_g1 = H * LK; g.route_vg = c->vg_m[kb]; g.route_vg_g1 = (int64_t)H * LK * E;
+      g.out_f32 = cap_part; g.out_ld = H * E; x.gemm(g); }
+    int32_t* bc = bucket_count + (int64_t)kb * 2 * E;
+    float* us = usage + (int64_t)kb * 2 * E;
+    x.run([&] {
+      return vb_router(nullptr, nullptr, nullptr, b.capg_b, c->ac_logits + (int64_t)kb * E, depth * E, hl + 2 * kb, 2 * depth,
+                       io->e0[kb], io->e1[kb], io->e2[kb], d->temperature, N, T, 0, E, idx_c, idx_a, scale_c, scale_a, nullptr,
+                       bc, us, slot_c, slot_a, cap_part, H, stream);
+    });
+    if (depth > 1) {
+      const int kn = (kb + 1) % depth;  // this block's dispatch zeroes the next block's counters
+      x.run([&] {
+        return vb_moe_dispatch(idx_c, idx_a, slot_c, slot_a, scale_c, scale_a, bc, us, bucket_count + (int64_t)kn * 2 * E,
+                               usage + (int64_t)kn * 2 * E, N, E, (int)(D * es), xm, xsb, row_map, row_scale, tile_group, m_tiles,
+                               max_rows, io->lb + kb, stream);
+      });
+    } else {
+      x.run([&] { return vb_moe_finalize(bc, us, E, bucket_start, row_map, row_scale, tile_group, m_tiles, max_rows, io->lb + kb, stream); });
+      x.run([&] {
+        return vb_moe_scatter(idx_c, idx_a, slot_c, slot_a, scale_c, scale_a, bucket_start, N, E, (int)(D * es), xm, xsb, row_map,
+                              row_scale, stream);
+      });
+    }
+    // routed experts (w1|w3 -> SwiGLU -> w2, scattered back to token rows), then the frequency experts over their
+    // bands (y = y_caption + y_acoustic summed in the accumulator: 2 "taps" N rows apart) + adaLN gate + residual
+    { vb_gemm_args g = x.args(max_rows, 2 * Fh, D); set_a(g, xsb, D, max_rows, D);
+      set_b(g, b.w13, D, 2 * Fh, D, 2 * E, (int64_t)2 * Fh * D);
+      g.b_c2_tile = 1; g.tile_group = tile_group; g.m_tiles_used = m_tiles; g.swiglu = 1; x.out_op(g, hs, Fh); x.gemm(g); }
+    { vb_gemm_args g = x.args(max_rows, D, Fh); set_a(g, hs, Fh, max_rows, Fh); set_b(g, b.w2, Fh, D, Fh, 2 * E, (int64_t)D * Fh);
+      g.b_c2_tile = 1; g.tile_group = tile_group; g.m_tiles_used = m_tiles; g.row_map = row_map; g.rows_out = 2 * N;
+      g.row_scale = row_scale; x.out_op(g, y2, D); x.gemm(g); }
+    { vb_gemm_args g = x.args(N, 2 * Fh, 2 * band); set_a(g, y2, band, 2 * N, D, E, band);
+      set_b(g, b.f13, 2 * band, 2 * Fh, 2 * band, E, (int64_t)2 * Fh * 2 * band);
+      g.G1 = E; g.kpt = band / x.kq; g.dil = N; g.pad = 0; g.a_c2_g1 = 1; g.b_c2_g1 = 1; g.swiglu = 1;
+      x.out_op(g, hf, Fh); g.outb_g1 = (int64_t)N * Fh; x.gemm(g); }
+    { vb_gemm_args g = x.args(N, band, Fh); set_a(g, hf, Fh, N, Fh, E, (int64_t)N * Fh); set_b(g, b.f2, Fh, band, Fh, E, (int64_t)band * Fh);
+      g.G1 = E; g.a_c2_g1 = 1; g.b_c2_g1 = 1;
+      g.gate = m0 + 5 * D; g.gate_rows = T; g.gate_ld = mld; g.gate_g1 = band; g.residual = hbuf;
+      g.out_f32 = xcur; g.out_ld = D; g.out_g1 = band; x.gemm(g); }
+  }
+  // ---- final layer (vocal2music_moe.py:268-291,431): all 32 zero-padded output columns are computed
+  const float* f0 = mod + (int64_t)depth * 6 * D;
+  x.norm_mod(1, xcur, nullptr, f0, f0 + D, mld, T, 1e-6f, xf, N, D);
+  { vb_gemm_args g = x.args(N, 32, D); set_a(g, xf, D, N, D); set_b(g, d->final_w, D, 32, D);
+    g.bias = d->final_b; g.out_f32 = io->v; g.out_ld = 32; x.gemm(g); }
+  if (io->out_v) x.run([&] { return vb_ntc_to_nct(io->v, nullptr, 32, 0.f, 0.f, io->out_v, B, C, T, nullptr, 0, 0, stream); });
+  return x.rc;
+}
+
+extern "C" int64_t vb_dit_workspace_bytes(const vb_dit_desc* d, int B, int T) {
+  int64_t need = 0;
+  if (dit_run(d, nullptr, nullptr, nullptr, 0, nullptr, B, T, &need)) return -1;
+  return need;
+}
+
+extern "C" int vb_dit_forward(const vb_dit_desc* d, const vb_dit_cond* c, const vb_dit_io* io, void* ws, int64_t ws_bytes,
+                              void* stream) {
+  if (!d || !c || !io || !ws) return set_error(VB_ERR_INVALID, "vb_dit_forward: null pointer");
+  return dit_run(d, c, io, ws, ws_bytes, stream, c->B, c->T, nullptr);
+}

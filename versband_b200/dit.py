@@ -436,6 +436,42 @@ class DiTEngine:
         ops.mark("moe_dispatch")
 
     # ------------------------------------------------------------------ one DiT evaluation
+    def _desc(self):
+        """The packed model as a `vb_dit_desc` (include/versband.h) for vb_dit_forward."""
+        if getattr(self, "_c_desc", None) is not None:
+            return self._c_desc
+        from ._lib import DIT_MAX_DEPTH, DitDesc
+        w, P = self.w, ops._ptr
+        assert self.depth <= DIT_MAX_DEPTH
+        d = DitDesc()
+        d.C, d.D, d.depth, d.H, d.E, d.Fh = self.C, self.D, self.depth, self.H, self.E, self.Fh
+        d.max_len, d.proj_in_k, d.operand_f32 = self.max_len, self.proj_in_k, int(self.adt == F32)
+        d.eps, d.temperature, d.mod_ld = self.eps, float(self.temperature), self.mod_ld
+        for n in ("proj_in_w", "proj_in_b", "t_w0", "t_w2", "ada_w", "t_b0", "t_b2", "ada_b", "t_freqs", "hl_w", "hl_b",
+                  "final_w", "final_b", "rope"):
+            setattr(d, n, P(w[n]))
+        for blk, b in zip(d.blocks, w["blocks"]):
+            for n in ("wqkv", "wo", "gate", "attn_norm", "ffn_norm", "capg_b", "w13", "w2", "f13", "f2"):
+                setattr(blk, n, P(b[n]))
+        self._c_desc = d
+        return d
+
+    def _cond_struct(self, cond: DiTCond):
+        cs = getattr(cond, "_cstruct", None)
+        if cs is None:
+            from ._lib import DitCond
+            P = ops._ptr
+            cs = DitCond()
+            cs.B, cs.T, cs.L, cs.Lp = cond.B, cond.T, cond.L, cond.vt_y[0].shape[-1]
+            cs.acoustic, cs.ac_logits, cs.cap_emb = P(cond.acoustic), P(cond.ac_logits), P(cond.cap_emb)
+            for name in DiTCond._LISTS:
+                arr = getattr(cs, name)
+                for k, t in enumerate(getattr(cond, name)):
+                    assert t.is_contiguous()
+                    arr[k] = t.data_ptr()
+            cond._cstruct = cs
+        return cs
+
     @torch.no_grad()
     def forward(self, x: torch.Tensor, t: torch.Tensor, cond: DiTCond,
                 expo: List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]],
@@ -443,7 +479,53 @@ class DiTEngine:
                 chain_cnt: Optional[torch.Tensor] = None, ws_slot: int = 0, x_cl: Optional[torch.Tensor] = None):
         """x fp32 [B, C, T], t int64 [B]; expo[k] = Exp(1) draws ([N,2],[N,E],[N,E]) of block k.
         Returns v as the channels-last GEMM output [N, 32] (first C columns valid) unless `out_v`
-        ([B, C, T]) is given, plus lb_loss per block (device tensor)."""
+        ([B, C, T]) is given, plus lb_loss per block (device tensor).
+
+        ONE call of the model-level C entry point vb_dit_forward (csrc/vb_model.cu issues the ~52 launches);
+        `forward_py` is the same sequence issued from Python — used when per-block intermediates are wanted
+        (`want_aux`), for the experimental launch variants (use_chain / fused_dispatch) and the op timeline."""
+        if want_aux or self.use_chain or self.fused_dispatch or ops.TIMELINE is not None:
+            return self.forward_py(x, t, cond, expo, out_v=out_v, want_aux=want_aux, pre=pre, x_cl_ready=x_cl_ready,
+                                   chain_cnt=chain_cnt, ws_slot=ws_slot, x_cl=x_cl)
+        import ctypes as C
+        from . import _lib
+        from ._lib import DitIO
+        Bx, Cc, T = x.shape
+        B = cond.B
+        assert B % Bx == 0 and T == cond.T and T <= self.max_len
+        ws = self._workspace(B, T, ws_slot)
+        d = self._desc()
+        if "cws" not in ws:
+            need = int(_lib.lib().vb_dit_workspace_bytes(C.byref(d), B, T))
+            if need < 0:
+                _lib.check(-1, "vb_dit_workspace_bytes")
+            ws["cws"] = torch.zeros(need, device=self.dev, dtype=torch.uint8)  # zero-filled once (MoE bucket counters)
+        P = ops._ptr
+        io = DitIO()
+        x = x.contiguous()
+        t = t.contiguous()
+        io.x, io.Bx, io.x_cl_ready = P(x), Bx, int(x_cl_ready)
+        io.x_cl = P(ws["x_cl"] if x_cl is None else x_cl)
+        io.t = P(t)
+        if pre is not None:
+            assert pre[0].is_contiguous() and pre[1].is_contiguous()
+            io.mod, io.hl = P(pre[0]), P(pre[1])
+        for k, (e0, e1, e2) in enumerate(expo):
+            io.e0[k], io.e1[k], io.e2[k] = e0.data_ptr(), e1.data_ptr(), e2.data_ptr()
+        io.v, io.lb = P(ws["v"]), P(ws["lb"])
+        if out_v is not None:
+            assert out_v.is_contiguous()
+            io.out_v = P(out_v)
+        _lib.check(_lib.lib().vb_dit_forward(C.byref(d), C.byref(self._cond_struct(cond)), C.byref(io), P(ws["cws"]),
+                                             ws["cws"].numel(), ops._stream()), "vb_dit_forward")
+        return ws["v"], ws["lb"]
+
+    @torch.no_grad()
+    def forward_py(self, x: torch.Tensor, t: torch.Tensor, cond: DiTCond,
+                   expo: List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]],
+                   out_v: Optional[torch.Tensor] = None, want_aux: bool = False, pre=None, x_cl_ready: bool = False,
+                   chain_cnt: Optional[torch.Tensor] = None, ws_slot: int = 0, x_cl: Optional[torch.Tensor] = None):
+        """The launch sequence of `forward`, op by op from Python (same kernels, same arguments)."""
         w, D, H, hd, E, Fh = self.w, self.D, self.H, self.hd, self.E, self.Fh
         Bx, C, T = x.shape
         B = cond.B
