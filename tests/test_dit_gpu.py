@@ -145,7 +145,8 @@ def test_c_entry_point_equals_python_launch_sequence(weights, precision, B, T):
         v_c, lb_c = v_c.clone(), lb_c.clone()
         v_p, lb_p = eng.forward_py(x, t, cond, expo, out_v=out_p)
         torch.cuda.synchronize()
-        assert torch.equal(v_c, v_p) and torch.equal(out_c, out_p) and torch.equal(lb_c, lb_p)
+        assert torch.equal(v_c, v_p) and torch.equal(out_c, out_p)
+        assert torch.allclose(lb_c, lb_p, rtol=1e-5, atol=0)  # lb sums router probabilities with float atomics
         x = x + 0.1 * out_c
     # precomputed modulation vectors (the sampler's path)
     mod = torch.empty(B, eng.mod_ld, device=DEV)

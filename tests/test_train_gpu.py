@@ -13,6 +13,13 @@ from versband_b200 import modules, train  # noqa: E402
 DEV = "cuda"
 
 
+@pytest.fixture(autouse=True)
+def _grad_enabled():
+    """Other test modules switch autograd off process-wide at import; the training tests need it on."""
+    with torch.enable_grad():
+        yield
+
+
 def test_train_step_loss_and_grads_vs_oracle_autograd():
     torch.manual_seed(0)
     sd = synth.synth_state_dict(synth.load_manifest("dit"), seed=1234)

@@ -4,6 +4,7 @@
 //                    fp16 activations in the activated representation (see versband_b200/vocoder.py).
 // The caller owns every buffer: packed weights (device pointers in the descriptor), input, output and ONE
 // workspace whose size vb_voc_workspace_bytes reports. No allocation, no hidden state.
+#include <cmath>
 #include <cstring>
 #include "vb_internal.h"
 
@@ -270,7 +271,7 @@ struct VaeCtx {
       g.M = T; g.N = T; g.K = (C + 63) / 64 * 64; g.G1 = B; g.G2 = 1;
       g.a_c2_g1 = 1; g.b_c2_g1 = 1;
       g.rows_out = T;
-      g.alpha = 1.f / sqrtf((float)C);
+      g.alpha = (float)pow((double)C, -0.5);
       g.out_f32 = S; g.out_ld = Tp; g.out_g1 = (int64_t)T * Tp;
       run([&] { return vb_gemm(&g, stream); });
     }
@@ -531,7 +532,7 @@ static int dit_run(const vb_dit_desc* d, const vb_dit_cond* c, const vb_dit_io* 
     mod = mod_own; hl = hl_own;
   }
   float* xcur = xs_;
-  const float scale = 1.f / sqrtf((float)hd);
+  const float scale = (float)(1.0 / sqrt((double)hd));  // rounded once from double, like the Python host code
   for (int kb = 0; kb < depth && !x.rc; ++kb) {
     const vb_dit_block& b = d->blocks[kb];
     const float* m0 = mod + (int64_t)kb * 6 * D;
