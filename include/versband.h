@@ -249,6 +249,7 @@ typedef struct vb_attn_args {
 } vb_attn_args;
 
 int vb_attn_fused(const vb_attn_args* args, void* stream);
+int vb_attn_set_trace(void* device_buf); /* debug: clock64 stamps of CTA (0,0,0) (tools/profile_attn.py) */
 
 /* ------------------------------------------------------------------------------------------
  * Model-level entry point: the whole HiFi-GAN generator (vocoder/hifigan/modules/hifigan.py:126-143) as ONE call
