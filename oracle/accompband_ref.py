@@ -7,7 +7,7 @@ checker or the timed CPU baseline.
 
 Pinning: the reference ships no tests or golden vectors.  This restatement
 is pinned against the *live reference modules* imported from /root/reference in the build
-container (oracle/make_golden.py → tests/golden/*.pt; tests/test_oracle_vs_reference.py), so
+container (oracle/make_golden.py → tests/golden/*.pt; tests/test_oracle_golden.py), so
 it is "pinned to reference outputs generated here", not to reference-owned fixtures.
 
 Every function cites the reference file:line it follows (paths relative to /root/reference).

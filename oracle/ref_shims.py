@@ -2,7 +2,7 @@
 
 Imports the *unmodified* reference modules from /root/reference on a CUDA-less host, with the
 stubs listed in SURVEY.md §8c.  Only used in the build container (the reference tree does not
-exist on the GPU box) by oracle/make_golden.py and tests/test_oracle_vs_reference.py.
+exist on the GPU box) by oracle/make_golden.py (golden vectors checked in tests/test_oracle_golden.py) and tests/test_reference_glue_cpu.py.
 Nothing from the reference is copied; the stubs only satisfy imports the hot path never calls.
 """
 from __future__ import annotations
