@@ -369,8 +369,38 @@ int64_t vb_dit_workspace_bytes(const vb_dit_desc* d, int B, int T);
 int vb_dit_forward(const vb_dit_desc* d, const vb_dit_cond* cond, const vb_dit_io* io, void* workspace,
                    int64_t workspace_bytes, void* stream);
 
+/* Step-invariant conditioning of the DiT as ONE call (versband_b200/dit.py:DiTEngine.prepare / prepare_pair):
+ * acoustic stem of the Bm clips (midi / beats int64 [Bm, 1, Tm]) replicated to every group of Bm conditioning rows,
+ * caption embedder over the B = groups * Bm captions (fp32 [B, L, ori_dim], L <= 96), and per block the text
+ * K / V^T and the folded caption gate operands. `out` describes caller-allocated OUTPUT buffers (B, T, L,
+ * Lp = ceil8(L) set; every pointer of vb_dit_cond set and written here); caption_out: optional fp32 [B, L, D]. */
+typedef struct vb_dit_prep_block {
+  const float* y_norm;       /* [D] attention_y_norm */
+  const void* wkvy;          /* [2D, D]: wk_y | wv_y */
+  const void* mkv_w;         /* [2D, D]: k | v rows of the MoE cross-attention in_proj */
+  const float* mkv_b;        /* [2D] */
+  const void* mq_wT;         /* [H, D, ceil_kq(hd)]: (scale W_q,h)^T */
+  const float *mq_bs, *capg_w; /* [D] scale * b_q; [E, D] W_gate W_out_proj */
+} vb_dit_prep_block;
+typedef struct vb_dit_prep_desc {
+  int32_t ori_dim, stem_k, Vm, Vb;
+  const float *midi_tab, *beats_tab;       /* [stem_k, V, D]: conv tap x embedding row, folded in fp64 */
+  const float *midi_proj_b, *beats_proj_b; /* [D] */
+  const void* final_proj_w3;               /* [D, 3D] = [W_hi | W_lo | W_hi] */
+  const float* final_proj_b;
+  const float *acg_w, *acg_b;              /* acoustic gates of all blocks [depth*E, D], [depth*E] */
+  const void *c_w0, *c_w2, *cap_w;         /* [D, ori_dim], [D, D], [D, D] */
+  const float *c_b0, *c_b2, *c_ln_w, *c_ln_b, *cap_ln_w, *cap_ln_b, *cap_b;
+  vb_dit_prep_block blocks[VB_DIT_MAX_DEPTH];
+} vb_dit_prep_desc;
+int64_t vb_dit_prepare_workspace_bytes(const vb_dit_desc* d, const vb_dit_prep_desc* p, int Bm, int Tm, int B, int L, int T);
+int vb_dit_prepare(const vb_dit_desc* d, const vb_dit_prep_desc* p, const int64_t* midi, const int64_t* beats, int Bm, int Tm,
+                   const float* caption, int B, int L, const vb_dit_cond* out, float* caption_out, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+
 /* sizeof() of the public structs as compiled (ABI self-check for bindings): 0 = vb_gemm_args, 1 = vb_attn_args,
- * 2 = vb_voc_desc, 3 = vb_vae_desc, 4 = vb_dit_desc, 5 = vb_dit_cond, 6 = vb_dit_io */
+ * 2 = vb_voc_desc, 3 = vb_vae_desc, 4 = vb_dit_desc, 5 = vb_dit_cond, 6 = vb_dit_io,
+ * 7 = vb_dit_prep_desc */
 int vb_sizeof(int which);
 /* number of kernels this library has launched in this process */
 long long vb_launch_count(void);

@@ -156,3 +156,27 @@ def test_c_entry_point_equals_python_launch_sequence(weights, precision, B, T):
     v_p = eng.forward_py(x, t, cond, expo, pre=(mod, hl))[0]
     torch.cuda.synchronize()
     assert torch.equal(v_c, v_p)
+
+
+@pytest.mark.parametrize("precision", ["fp16", "tf32"])
+def test_c_prepare_equals_python_launch_sequence(weights, precision):
+    """vb_dit_prepare (step-invariant conditioning issued from C++ through one C-ABI call) vs the op-by-op Python
+    sequence: every tensor of the conditioning bit-identical — single batch, CFG pair (acoustic stem shared by the
+    two caption groups) and the length fix-up of vocal2music_moe.py:397-401 (conditioning one frame short / long)."""
+    eng = DiTEngine(weights, device=DEV, precision=precision)
+    B, T = 2, 48
+    _, midi, beats, cap, cap_u = synth.dit_inputs(B, T, seed=8)
+    midi, beats, cap, cap_u = midi.to(DEV), beats.to(DEV), cap.to(DEV), cap_u.to(DEV)
+    for T_lat in (T, T + 1, T - 1):
+        a = eng.prepare(midi, beats, cap, T_lat)
+        b = eng.prepare_py(midi, beats, cap, T_lat)
+        torch.cuda.synchronize()
+        assert len(a.tensors()) == len(b.tensors()) == 4 + 5 * eng.depth
+        for ta, tb in zip(a.tensors(), b.tensors()):
+            assert ta.shape == tb.shape and ta.dtype == tb.dtype and torch.equal(ta, tb)
+    a = eng.prepare_pair(midi, beats, cap, cap_u, T)
+    ac, acl = eng.prepare_acoustic(midi, beats, T)
+    b = eng.prepare_py(None, None, torch.cat([cap, cap_u], 0), T, acoustic=(torch.cat([ac, ac], 0), torch.cat([acl, acl], 0)))
+    torch.cuda.synchronize()
+    for ta, tb in zip(a.tensors(), b.tensors()):
+        assert ta.shape == tb.shape and torch.equal(ta, tb)

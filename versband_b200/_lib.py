@@ -120,6 +120,21 @@ class DitCond(C.Structure):
                 ("cap_emb", c_ptr)] + [(n, c_ptr * DIT_MAX_DEPTH) for n in ("k_y", "vt_y", "wk_m", "bs_m", "vg_m")]
 
 
+class DitPrepBlock(C.Structure):
+    """Mirror of `struct vb_dit_prep_block`."""
+
+    _fields_ = [(n, c_ptr) for n in ("y_norm", "wkvy", "mkv_w", "mkv_b", "mq_wT", "mq_bs", "capg_w")]
+
+
+class DitPrepDesc(C.Structure):
+    """Mirror of `struct vb_dit_prep_desc`."""
+
+    _fields_ = [("ori_dim", c_i32), ("stem_k", c_i32), ("Vm", c_i32), ("Vb", c_i32)] + [(n, c_ptr) for n in (
+        "midi_tab", "beats_tab", "midi_proj_b", "beats_proj_b", "final_proj_w3", "final_proj_b", "acg_w", "acg_b",
+        "c_w0", "c_w2", "cap_w", "c_b0", "c_b2", "c_ln_w", "c_ln_b", "cap_ln_w", "cap_ln_b", "cap_b")] + [
+            ("blocks", DitPrepBlock * DIT_MAX_DEPTH)]
+
+
 class DitIO(C.Structure):
     """Mirror of `struct vb_dit_io`."""
 
@@ -165,7 +180,11 @@ def lib() -> C.CDLL:
         _lib.vb_dit_forward.argtypes = [C.POINTER(DitDesc), C.POINTER(DitCond), C.POINTER(DitIO), c_ptr, c_i64, c_ptr]
         _lib.vb_dit_workspace_bytes.argtypes = [C.POINTER(DitDesc), c_i32, c_i32]
         _lib.vb_dit_workspace_bytes.restype = c_i64
-        for which, st in ((4, DitDesc), (5, DitCond), (6, DitIO)):
+        _lib.vb_dit_prepare.argtypes = [C.POINTER(DitDesc), C.POINTER(DitPrepDesc), c_ptr, c_ptr, c_i32, c_i32, c_ptr, c_i32,
+                                        c_i32, C.POINTER(DitCond), c_ptr, c_ptr, c_i64, c_ptr]
+        _lib.vb_dit_prepare_workspace_bytes.argtypes = [C.POINTER(DitDesc), C.POINTER(DitPrepDesc)] + [c_i32] * 5
+        _lib.vb_dit_prepare_workspace_bytes.restype = c_i64
+        for which, st in ((4, DitDesc), (5, DitCond), (6, DitIO), (7, DitPrepDesc)):
             if _lib.vb_sizeof(which) != C.sizeof(st):
                 raise VersbandError(f"{st.__name__} ABI mismatch between versband.h and _lib.py")
         if _lib.vb_sizeof(0) != C.sizeof(GemmArgs):

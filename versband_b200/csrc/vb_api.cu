@@ -110,6 +110,7 @@ extern "C" int vb_sizeof(int which) {
     case 4: return (int)sizeof(vb_dit_desc);
     case 5: return (int)sizeof(vb_dit_cond);
     case 6: return (int)sizeof(vb_dit_io);
+    case 7: return (int)sizeof(vb_dit_prep_desc);
     default: return -1;
   }
 }

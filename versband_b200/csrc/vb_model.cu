@@ -618,3 +618,126 @@ extern "C" int vb_dit_forward(const vb_dit_desc* d, const vb_dit_cond* c, const 
   if (!d || !c || !io || !ws) return set_error(VB_ERR_INVALID, "vb_dit_forward: null pointer");
   return dit_run(d, c, io, ws, ws_bytes, stream, c->B, c->T, nullptr);
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Step-invariant conditioning of the DiT (everything in TxtFlagLargeDiT.forward that does not depend on (x, t),
+// vocal2music_moe.py:388-393,397-412 + the per-block K/V projections and the folded caption gate): the launch
+// sequence of versband_b200/dit.py:DiTEngine.prepare / prepare_pair issued from C++. The acoustic stem is
+// computed for the Bm clips once and replicated to every group of Bm conditioning rows (B = groups * Bm captions:
+// the CFG pair is 2 groups).
+// ------------------------------------------------------------------------------------------------------------
+static int dit_prepare_run(const vb_dit_desc* d, const vb_dit_prep_desc* p, const int64_t* midi, const int64_t* beats, int Bm,
+                           int Tm, const float* caption, int B, int L, int T, const vb_dit_cond* out, float* caption_out,
+                           void* ws, int64_t ws_bytes, void* stream, int64_t* need) {
+  const bool dry = need != nullptr;
+  if (!d || !p || Bm <= 0 || B <= 0 || B % Bm || L <= 0 || L > 96 || T <= 0 || Tm < 2)
+    return set_error(VB_ERR_INVALID, "vb_dit_prepare: bad arguments (caption length <= 96, B a multiple of the clip count)");
+  const int D = d->D, H = d->H, E = d->E, depth = d->depth, hd = D / H, LK = 96;
+  const int Tpool = Tm / 2, Lp = (L + 7) / 8 * 8;
+  if (abs(T - Tpool) > 2) return set_error(VB_ERR_INVALID, "vb_dit_prepare: latent / conditioning length mismatch (%d vs %d)", T, Tpool);
+  DitCtx x{d, stream, dry, 0, d->operand_f32 != 0, d->operand_f32 ? 32 : 64};
+  const int64_t es = x.es();
+  const int kpad = (hd + x.kq - 1) / x.kq * x.kq;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Bump bump{static_cast<uint8_t*>(dry ? nullptr : ws), 0, ws_bytes};
+  void* pooled3 = bump.take((int64_t)Bm * Tpool * 3 * D * es);
+  float* ac_tmp = static_cast<float*>(bump.take((int64_t)Bm * Tpool * D * 4));
+  void* cap16 = bump.take((int64_t)B * L * p->ori_dim * es);
+  void* h1 = bump.take((int64_t)B * L * D * es);
+  float* h2 = static_cast<float*>(bump.take((int64_t)B * L * D * 4));
+  float* cap = static_cast<float*>(bump.take((int64_t)B * L * D * 4));
+  void* cap_h = bump.take((int64_t)B * L * D * 2);
+  float* pool = static_cast<float*>(bump.take((int64_t)B * D * 4));
+  void* pool_n = bump.take((int64_t)B * D * es);
+  void* y16 = bump.take((int64_t)B * L * D * es);
+  float* kvf = static_cast<float*>(bump.take((int64_t)B * L * 2 * D * 4));
+  void* kvh = bump.take((int64_t)B * L * 2 * D * 2);
+  if (dry) { *need = (bump.off + 255) & ~int64_t(255); return VB_OK; }
+  if (bump.off > ws_bytes) return set_error(VB_ERR_INVALID, "vb_dit_prepare: workspace too small (%lld bytes needed)", (long long)bump.off);
+  if (!midi || !beats || !caption || !out || out->B != B || out->T != T || out->L != L || out->Lp != Lp || !out->acoustic ||
+      !out->ac_logits || !out->cap_emb)
+    return set_error(VB_ERR_INVALID, "vb_dit_prepare: bad output block (B, T, L, Lp = ceil8(L) and the output pointers must be set)");
+  float* acoustic = const_cast<float*>(out->acoustic);
+  float* ac_logits = const_cast<float*>(out->ac_logits);
+  auto cuda_ok = [&](cudaError_t e) { return e == cudaSuccess ? VB_OK : set_error(VB_ERR_CUDA, "vb_dit_prepare: %s", cudaGetErrorString(e)); };
+
+  // ---- acoustic stem: conv(k) over embedding rows as exact table gathers + lrelu + AvgPool(2) + sum, then final_proj
+  // on the split-precision operand (vocal2music_moe.py:336-350,388-393)
+  x.run([&] {
+    return vb_stem_gather(midi, beats, p->midi_tab, p->beats_tab, p->midi_proj_b, p->beats_proj_b, p->Vm, p->Vb, p->stem_k, Bm, Tm,
+                          Tpool, D, 0.01f, pooled3, x.f32, stream);
+  });
+  float* ac0 = Tpool == T ? acoustic : ac_tmp;
+  { vb_gemm_args g = x.args(Bm * Tpool, D, 3 * D); set_a(g, pooled3, 3 * D, (int64_t)Bm * Tpool, 3 * D); set_b(g, p->final_proj_w3, 3 * D, D, 3 * D);
+    g.bias = p->final_proj_b; g.out_f32 = ac0; g.out_ld = D; x.gemm(g); }
+  if (Tpool != T) {  // length fix-up (vocal2music_moe.py:397-401): repeat the last frame or crop
+    const int keep = T < Tpool ? T : Tpool;
+    x.run([&] {
+      return cuda_ok(cudaMemcpy2DAsync(acoustic, (size_t)T * D * 4, ac_tmp, (size_t)Tpool * D * 4, (size_t)keep * D * 4, Bm,
+                                       cudaMemcpyDeviceToDevice, st));
+    });
+    for (int r = Tpool; r < T; ++r)
+      x.run([&] {
+        return cuda_ok(cudaMemcpy2DAsync(acoustic + (int64_t)r * D, (size_t)T * D * 4, ac_tmp + (int64_t)(Tpool - 1) * D, (size_t)Tpool * D * 4,
+                                         (size_t)D * 4, Bm, cudaMemcpyDeviceToDevice, st));
+      });
+  }
+  x.run([&] { return vb_linear_small(acoustic, D, p->acg_w, p->acg_b, ac_logits, Bm * T, D, depth * E, stream); });
+  for (int r = 1; r < B / Bm; ++r) {  // the other conditioning groups share the clips' acoustic stem
+    x.run([&] { return cuda_ok(cudaMemcpyAsync(acoustic + (int64_t)r * Bm * T * D, acoustic, (size_t)Bm * T * D * 4, cudaMemcpyDeviceToDevice, st)); });
+    x.run([&] {
+      return cuda_ok(cudaMemcpyAsync(ac_logits + (int64_t)r * Bm * T * depth * E, ac_logits, (size_t)Bm * T * depth * E * 4,
+                                     cudaMemcpyDeviceToDevice, st));
+    });
+  }
+  // ---- caption embedder (c_embedder MLP + LayerNorm), pooled caption embedding (vocal2music_moe.py:408-412)
+  const int R = B * L;
+  x.run([&] { return vb_ew(caption, nullptr, 1.f, 1.f, VB_ACT_NONE, 0.f, x.f32 ? static_cast<float*>(cap16) : nullptr, x.f32 ? nullptr : cap16, R, p->ori_dim, 1, stream); });
+  { vb_gemm_args g = x.args(R, D, p->ori_dim); set_a(g, cap16, p->ori_dim, R, p->ori_dim); set_b(g, p->c_w0, p->ori_dim, D, p->ori_dim);
+    g.bias = p->c_b0; g.act = VB_ACT_GELU_ERF; x.out_op(g, h1, D); x.gemm(g); }
+  { vb_gemm_args g = x.args(R, D, D); set_a(g, h1, D, R, D); set_b(g, p->c_w2, D, D, D); g.bias = p->c_b2; g.out_f32 = h2; g.out_ld = D; x.gemm(g); }
+  float* capf = caption_out ? caption_out : cap;
+  x.run([&] { return vb_norm_mod(1, h2, p->c_ln_w, p->c_ln_b, nullptr, nullptr, 0, R, 1e-5f, x.f32 ? nullptr : cap_h, capf, R, D, stream); });
+  const void* cap_op = x.f32 ? static_cast<const void*>(capf) : cap_h;  // fp32 operands: the fp32 caption is the operand itself
+  x.run([&] { return vb_mean_tokens(capf, B, L, D, pool, stream); });
+  x.run([&] { return vb_norm_mod(1, pool, p->cap_ln_w, p->cap_ln_b, nullptr, nullptr, 0, B, 1e-5f, x.f32 ? nullptr : pool_n, x.f32 ? static_cast<float*>(pool_n) : nullptr, B, D, stream); });
+  { vb_gemm_args g = x.args(B, D, D); set_a(g, pool_n, D, B, D); set_b(g, p->cap_w, D, D, D); g.bias = p->cap_b;
+    g.out_f32 = const_cast<float*>(out->cap_emb); g.out_ld = D; x.gemm(g); }
+  // ---- per block: K / V^T of the text cross-attention, and the MoE caption cross-attention folded into its gate
+  for (int kb = 0; kb < depth && !x.rc; ++kb) {
+    const vb_dit_prep_block& b = p->blocks[kb];
+    void* k_y = const_cast<void*>(out->k_y[kb]);
+    void* vt_y = const_cast<void*>(out->vt_y[kb]);
+    void* wk = const_cast<void*>(out->wk_m[kb]);
+    if (!k_y || !vt_y || !wk || !out->bs_m[kb] || !out->vg_m[kb]) return set_error(VB_ERR_INVALID, "vb_dit_prepare: output pointer of block %d missing", kb);
+    x.norm_mod(0, capf, b.y_norm, nullptr, nullptr, 0, R, d->eps, y16, R, D);
+    x.run([&] { return cuda_ok(cudaMemsetAsync(vt_y, 0, (size_t)B * H * hd * Lp * 2, st)); });  // key padding columns L..Lp
+    { vb_gemm_args g = x.args(R, 2 * D, D); set_a(g, y16, D, R, D); set_b(g, b.wkvy, D, 2 * D, D);
+      g.mode = VB_EPI_QKV_ROPE; g.qkv_sec0 = 1; g.T = L; g.heads = H; g.head_dim = hd; g.Tp = Lp; g.k_out = k_y; g.vt_out = vt_y; x.gemm(g); }
+    { vb_gemm_args g = x.args(R, 2 * D, D); set_a(g, cap_op, D, R, D); set_b(g, b.mkv_w, D, 2 * D, D); g.bias = b.mkv_b;
+      g.out_f32 = kvf; g.out_ld = 2 * D; if (!x.f32) { g.out_fp16 = kvh; g.outb_ld = 2 * D; } x.gemm(g); }
+    x.run([&] { return cuda_ok(cudaMemsetAsync(wk, 0, (size_t)B * H * LK * D * es, st)); });  // key slots L..96 of every head
+    { vb_gemm_args g = x.args(L, D, kpad);  // WK[b,h] = K_h (scale W_q,h): batched over (head, batch)
+      set_a(g, x.f32 ? static_cast<const void*>(kvf) : kvh, hd, L, 2 * D, H, hd, B, (int64_t)L * 2 * D);
+      set_b(g, b.mq_wT, kpad, D, kpad, H, (int64_t)D * kpad);
+      g.G1 = H; g.G2 = B; g.a_c2_g1 = 1; g.a_c3_g2 = 1; g.b_c2_g1 = 1;
+      x.out_op(g, wk, D); g.outb_g1 = (int64_t)LK * D; g.outb_g2 = (int64_t)H * LK * D; x.gemm(g); }
+    x.run([&] {
+      return vb_route_prepare(kvf, B, L, H, hd, b.mq_bs, b.capg_w, const_cast<float*>(out->bs_m[kb]), const_cast<float*>(out->vg_m[kb]), stream);
+    });
+  }
+  return x.rc;
+}
+
+extern "C" int64_t vb_dit_prepare_workspace_bytes(const vb_dit_desc* d, const vb_dit_prep_desc* p, int Bm, int Tm, int B, int L, int T) {
+  int64_t need = 0;
+  if (dit_prepare_run(d, p, nullptr, nullptr, Bm, Tm, nullptr, B, L, T, nullptr, nullptr, nullptr, 0, nullptr, &need)) return -1;
+  return need;
+}
+
+extern "C" int vb_dit_prepare(const vb_dit_desc* d, const vb_dit_prep_desc* p, const int64_t* midi, const int64_t* beats, int Bm, int Tm,
+                              const float* caption, int B, int L, const vb_dit_cond* out, float* caption_out, void* ws,
+                              int64_t ws_bytes, void* stream) {
+  if (!d || !p || !out || !ws) return set_error(VB_ERR_INVALID, "vb_dit_prepare: null pointer");
+  return dit_prepare_run(d, p, midi, beats, Bm, Tm, caption, B, L, out->T, out, caption_out, ws, ws_bytes, stream, nullptr);
+}

@@ -287,6 +287,59 @@ class DiTEngine:
         return ws
 
     # ------------------------------------------------------------------ step-invariant part
+    def _prep_desc(self):
+        """The conditioning-side weights as a `vb_dit_prep_desc` (include/versband.h) for vb_dit_prepare."""
+        if getattr(self, "_c_prep", None) is not None:
+            return self._c_prep
+        from ._lib import DitPrepDesc
+        w, P = self.w, ops._ptr
+        p = DitPrepDesc()
+        p.ori_dim, p.stem_k = self.ori_dim, self.stem_k
+        p.Vm, p.Vb = w["midi_tab"].shape[1], w["beats_tab"].shape[1]
+        for n in ("midi_tab", "beats_tab", "midi_proj_b", "beats_proj_b", "final_proj_w3", "final_proj_b", "acg_w", "acg_b",
+                  "c_w0", "c_w2", "cap_w", "c_b0", "c_b2", "c_ln_w", "c_ln_b", "cap_ln_w", "cap_ln_b", "cap_b"):
+            setattr(p, n, P(w[n]))
+        for blk, b in zip(p.blocks, w["blocks"]):
+            for n in ("y_norm", "wkvy", "mkv_w", "mkv_b", "mq_wT", "mq_bs", "capg_w"):
+                setattr(blk, n, P(b[n]))
+        self._c_prep = p
+        return p
+
+    @torch.no_grad()
+    def _prepare_c(self, midi: torch.Tensor, beats: torch.Tensor, caption: torch.Tensor, T: int) -> DiTCond:
+        """ONE call of the model-level C entry point vb_dit_prepare: the acoustic stem of the Bm clips is computed
+        once and shared by the B = groups x Bm caption rows (CFG pair: B = 2 Bm, cond rows first)."""
+        import ctypes as C
+        from . import _lib
+        dev, D, H, hd, E = self.dev, self.D, self.H, self.hd, self.E
+        Bm, _, Tm = midi.shape
+        B, L, _ = caption.shape
+        if L > self.LK:
+            raise ValueError(f"caption length {L} > {self.LK}: the folded caption gate (VB_EPI_ROUTE) holds {self.LK} key "
+                             "slots per head (the reference pads captions to 80 tokens, encoders/modules.py:88-89)")
+        assert B % Bm == 0 and abs(T - Tm // 2) <= 2, "latent / conditioning length mismatch"
+        midi, beats = midi.to(dev).contiguous(), beats.to(dev).contiguous()
+        caption = caption.to(dev, F32).contiguous()
+        Lp = (L + 7) // 8 * 8
+        e = lambda *s, dt=F32: torch.empty(*s, device=dev, dtype=dt)  # noqa: E731
+        cond = DiTCond(B=B, T=T, L=L, acoustic=e(B * T, D), ac_logits=e(B * T, self.depth * E), caption=e(B, L, D),
+                       cap_emb=e(B, D))
+        for _ in range(self.depth):
+            cond.k_y.append(e(B, H, L, hd, dt=H16))
+            cond.vt_y.append(e(B, H, hd, Lp, dt=H16))
+            cond.wk_m.append(e(B, H * self.LK, D, dt=self.adt))
+            cond.bs_m.append(e(B, H, self.LK))
+            cond.vg_m.append(e(B, H, self.LK, E))
+        d, p, cs = self._desc(), self._prep_desc(), self._cond_struct(cond)
+        need = int(_lib.lib().vb_dit_prepare_workspace_bytes(C.byref(d), C.byref(p), Bm, Tm, B, L, T))
+        if need < 0:
+            _lib.check(-1, "vb_dit_prepare_workspace_bytes")
+        ws = torch.empty(need, device=dev, dtype=torch.uint8)
+        P = ops._ptr
+        _lib.check(_lib.lib().vb_dit_prepare(C.byref(d), C.byref(p), P(midi), P(beats), Bm, Tm, P(caption), B, L, C.byref(cs),
+                                             P(cond.caption), P(ws), need, ops._stream()), "vb_dit_prepare")
+        return cond
+
     @torch.no_grad()
     def prepare_acoustic(self, midi: torch.Tensor, beats: torch.Tensor, T: int):
         """midi/beats int64 [B,1,Tm] -> acoustic fp32 [B*T, D] and the acoustic gate logits
@@ -326,7 +379,15 @@ class DiTEngine:
 
     @torch.no_grad()
     def prepare(self, midi, beats, caption: torch.Tensor, T: int, acoustic=None) -> DiTCond:
-        """Everything in TxtFlagLargeDiT.forward that does not depend on (x, t)."""
+        """Everything in TxtFlagLargeDiT.forward that does not depend on (x, t): one vb_dit_prepare call
+        (`prepare_py` = the same launches from Python; also used when a precomputed `acoustic` is passed)."""
+        if acoustic is None and self.exact_stem and ops.TIMELINE is None:
+            return self._prepare_c(midi, beats, caption, T)
+        return self.prepare_py(midi, beats, caption, T, acoustic=acoustic)
+
+    @torch.no_grad()
+    def prepare_py(self, midi, beats, caption: torch.Tensor, T: int, acoustic=None) -> DiTCond:
+        """The launch sequence of `prepare`, op by op from Python."""
         w, D, dev = self.w, self.D, self.dev
         B, L, _ = caption.shape
         if L > self.LK:
@@ -390,9 +451,11 @@ class DiTEngine:
     def prepare_pair(self, midi, beats, caption: torch.Tensor, caption_uncond: torch.Tensor, T: int) -> DiTCond:
         """Conditioning of the (cond, uncond) CFG pair as ONE batch of 2B clips (cond rows first): the
         acoustic stem is computed once and shared, the caption path runs once on the stacked captions."""
+        caps = torch.cat([caption.to(self.dev, F32), caption_uncond.to(self.dev, F32)], 0)
+        if self.exact_stem and ops.TIMELINE is None:
+            return self._prepare_c(midi, beats, caps, T)
         ac, ac_logits = self.prepare_acoustic(midi, beats, T)
-        return self.prepare(None, None, torch.cat([caption, caption_uncond], 0), T,
-                            acoustic=(torch.cat([ac, ac], 0), torch.cat([ac_logits, ac_logits], 0)))
+        return self.prepare_py(None, None, caps, T, acoustic=(torch.cat([ac, ac], 0), torch.cat([ac_logits, ac_logits], 0)))
 
     # ------------------------------------------------------------------ time conditioning
     @torch.no_grad()
