@@ -398,9 +398,28 @@ int vb_dit_prepare(const vb_dit_desc* d, const vb_dit_prep_desc* p, const int64_
                    const float* caption, int B, int L, const vb_dit_cond* out, float* caption_out, void* workspace,
                    int64_t workspace_bytes, void* stream);
 
+/* The classifier-free-guidance flow sampler as ONE call (reference cfm1_audio_sampler.py:87-116 + cfm1_audio.py:145-162
+ * + torchdyn's fixed-step Euler; versband_b200/sampler.py:FlowSampler._run): n_steps x { DiT evaluation of the
+ * stacked (cond, uncond) batch; x += dt * (v_u + guidance * (v_c - v_u)) }. cond2 holds 2 * Bc rows, cond rows
+ * first. The router's Exp(1) draws come from the caller (vb_router_noise reproduces torch's Philox stream).
+ * Workspace: vb_sample_workspace_bytes() bytes, ZERO-FILLED once before first use (see vb_dit_forward). */
+typedef struct vb_sample_args {
+  int32_t n_steps; /* Euler steps (24 for the reference's 25-point t_span) */
+  int32_t Bc;      /* clips */
+  float guidance;
+  const int64_t* t_all; /* device [n_steps, 2*Bc]: integer timestep trunc(1000 t) of every step and row (cfm1_audio.py:156) */
+  const float* dt;      /* HOST [n_steps]: Euler step sizes, derived from t_span in fp32 like torchdyn */
+  const float *e0, *e1, *e2; /* device [n_steps, depth, 2*Bc*T, 2 | E | E] */
+  float* x;             /* device fp32 [Bc, C, T]: x0 in, x1 out */
+  float* lb;            /* optional device [depth]: load-balance loss of the last evaluation */
+} vb_sample_args;
+int64_t vb_sample_workspace_bytes(const vb_dit_desc* d, int Bc, int T, int n_steps);
+int vb_sample_cfg(const vb_dit_desc* d, const vb_dit_cond* cond2, const vb_sample_args* args, void* workspace,
+                  int64_t workspace_bytes, void* stream);
+
 /* sizeof() of the public structs as compiled (ABI self-check for bindings): 0 = vb_gemm_args, 1 = vb_attn_args,
  * 2 = vb_voc_desc, 3 = vb_vae_desc, 4 = vb_dit_desc, 5 = vb_dit_cond, 6 = vb_dit_io,
- * 7 = vb_dit_prep_desc */
+ * 7 = vb_dit_prep_desc, 8 = vb_sample_args */
 int vb_sizeof(int which);
 /* number of kernels this library has launched in this process */
 long long vb_launch_count(void);

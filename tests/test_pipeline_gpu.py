@@ -130,3 +130,20 @@ def test_sampler_tf32_meets_1e3(sds):
     # router amplifies sub-1e-4 logit differences into occasional expert flips (SURVEY.md §7 "router
     # bit-exactness"), which dominate this bound on a 32-frame clip.
     assert l2 < 5e-3 and med < 1e-3
+
+
+def test_c_sampler_equals_python_loop(pipe):
+    """vb_sample_cfg (the 24-step CFG Euler loop issued from C++ through one C-ABI call) vs the loop issued from
+    Python with the same pre-drawn router noise: bit-identical latents, for one clip and for a batch of two."""
+    dit = pipe.dit
+    for B, T in ((1, 750), (2, 40)):
+        x0, midi, beats, cap_c, cap_u = synth.dit_inputs(B, T, seed=13)
+        cond2 = dit.prepare_pair(midi.cuda(), beats.cuda(), cap_c.cuda(), cap_u.cuda(), T)
+        c_loop, py_loop = FlowSampler(dit, use_graph=False), FlowSampler(dit, use_graph=False)
+        py_loop._run = py_loop._run_py
+        noise = c_loop.draw_noise(B, T, torch.Generator(device="cuda").manual_seed(9))
+        xa = c_loop.sample_cfg(x0.cuda(), cond2, None, 3.0, noise=noise)
+        xb = py_loop.sample_cfg(x0.cuda(), cond2, None, 3.0, noise=noise)
+        torch.cuda.synchronize()
+        assert "sws" in c_loop._state[(B, T, cond2.L)] and "sws" not in py_loop._state[(B, T, cond2.L)]
+        assert torch.isfinite(xa).all() and torch.equal(xa, xb)

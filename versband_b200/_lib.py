@@ -143,6 +143,13 @@ class DitIO(C.Structure):
                 ("v", c_ptr), ("out_v", c_ptr), ("lb", c_ptr)]
 
 
+class SampleArgs(C.Structure):
+    """Mirror of `struct vb_sample_args`."""
+
+    _fields_ = [("n_steps", c_i32), ("Bc", c_i32), ("guidance", c_f32), ("t_all", c_ptr), ("dt", C.POINTER(c_f32)),
+                ("e0", c_ptr), ("e1", c_ptr), ("e2", c_ptr), ("x", c_ptr), ("lb", c_ptr)]
+
+
 class VersbandError(RuntimeError):
     pass
 
@@ -184,7 +191,10 @@ def lib() -> C.CDLL:
                                         c_i32, C.POINTER(DitCond), c_ptr, c_ptr, c_i64, c_ptr]
         _lib.vb_dit_prepare_workspace_bytes.argtypes = [C.POINTER(DitDesc), C.POINTER(DitPrepDesc)] + [c_i32] * 5
         _lib.vb_dit_prepare_workspace_bytes.restype = c_i64
-        for which, st in ((4, DitDesc), (5, DitCond), (6, DitIO), (7, DitPrepDesc)):
+        _lib.vb_sample_cfg.argtypes = [C.POINTER(DitDesc), C.POINTER(DitCond), C.POINTER(SampleArgs), c_ptr, c_i64, c_ptr]
+        _lib.vb_sample_workspace_bytes.argtypes = [C.POINTER(DitDesc), c_i32, c_i32, c_i32]
+        _lib.vb_sample_workspace_bytes.restype = c_i64
+        for which, st in ((4, DitDesc), (5, DitCond), (6, DitIO), (7, DitPrepDesc), (8, SampleArgs)):
             if _lib.vb_sizeof(which) != C.sizeof(st):
                 raise VersbandError(f"{st.__name__} ABI mismatch between versband.h and _lib.py")
         if _lib.vb_sizeof(0) != C.sizeof(GemmArgs):

@@ -111,6 +111,7 @@ extern "C" int vb_sizeof(int which) {
     case 5: return (int)sizeof(vb_dit_cond);
     case 6: return (int)sizeof(vb_dit_io);
     case 7: return (int)sizeof(vb_dit_prep_desc);
+    case 8: return (int)sizeof(vb_sample_args);
     default: return -1;
   }
 }

@@ -444,6 +444,25 @@ struct DitCtx {
 
 }  // namespace
 
+// timestep embedding MLP, adaLN vectors of every block + final layer, group-gate logits for R independent rows
+// (vocal2music_moe.py:406,416,242,290; DiTEngine.time_conditioning)
+static void dit_time_cond(DitCtx& x, int R, const int64_t* t, const float* cap_emb, void* tsin, void* th, float* temb, void* ada,
+                          float* mod_out, float* hl_out) {
+  const vb_dit_desc* d = x.d;
+  const int D = d->D;
+  const int64_t mld = d->mod_ld;
+  void* stream = x.stream;
+  x.run([&] { return vb_timestep_embed(t, d->t_freqs, x.f32 ? static_cast<float*>(tsin) : nullptr, x.f32 ? nullptr : tsin, R, 256, stream); });
+  { vb_gemm_args g = x.args(R, D, 256); set_a(g, tsin, 256, R, 256); set_b(g, d->t_w0, 256, D, 256);
+    g.bias = d->t_b0; g.act = VB_ACT_SILU; x.out_op(g, th, D); x.gemm(g); }
+  { vb_gemm_args g = x.args(R, D, D); set_a(g, th, D, R, D); set_b(g, d->t_w2, D, D, D);
+    g.bias = d->t_b2; g.out_f32 = temb; g.out_ld = D; x.gemm(g); }
+  x.run([&] { return vb_ew(temb, cap_emb, 1.f, 1.f, VB_ACT_SILU, 0.f, x.f32 ? static_cast<float*>(ada) : nullptr, x.f32 ? nullptr : ada, R, D, 1, stream); });
+  { vb_gemm_args g = x.args(R, (int)mld, D); set_a(g, ada, D, R, D); set_b(g, d->ada_w, D, mld, D);
+    g.bias = d->ada_b; g.out_f32 = mod_out; g.out_ld = mld; x.gemm(g); }
+  x.run([&] { return vb_linear_small(temb, D, d->hl_w, d->hl_b, hl_out, R, D, 2 * d->depth, stream); });
+}
+
 static int dit_run(const vb_dit_desc* d, const vb_dit_cond* c, const vb_dit_io* io, void* ws, int64_t ws_bytes, void* stream,
                    int B, int T, int64_t* need) {
   const bool dry = need != nullptr;
@@ -520,15 +539,7 @@ static int dit_run(const vb_dit_desc* d, const vb_dit_cond* c, const vb_dit_io* 
   const float *mod = io->mod, *hl = io->hl;
   if (!mod || !hl) {
     if (!io->t) return set_error(VB_ERR_INVALID, "vb_dit_forward: neither timesteps nor precomputed modulation given");
-    x.run([&] { return vb_timestep_embed(io->t, d->t_freqs, x.f32 ? static_cast<float*>(tsin) : nullptr, x.f32 ? nullptr : tsin, B, 256, stream); });
-    { vb_gemm_args g = x.args(B, D, 256); set_a(g, tsin, 256, B, 256); set_b(g, d->t_w0, 256, D, 256);
-      g.bias = d->t_b0; g.act = VB_ACT_SILU; x.out_op(g, th, D); x.gemm(g); }
-    { vb_gemm_args g = x.args(B, D, D); set_a(g, th, D, B, D); set_b(g, d->t_w2, D, D, D);
-      g.bias = d->t_b2; g.out_f32 = temb; g.out_ld = D; x.gemm(g); }
-    x.run([&] { return vb_ew(temb, c->cap_emb, 1.f, 1.f, VB_ACT_SILU, 0.f, x.f32 ? static_cast<float*>(ada) : nullptr, x.f32 ? nullptr : ada, B, D, 1, stream); });
-    { vb_gemm_args g = x.args(B, (int)mld, D); set_a(g, ada, D, B, D); set_b(g, d->ada_w, D, mld, D);
-      g.bias = d->ada_b; g.out_f32 = mod_own; g.out_ld = mld; x.gemm(g); }
-    x.run([&] { return vb_linear_small(temb, D, d->hl_w, d->hl_b, hl_own, B, D, 2 * depth, stream); });
+    dit_time_cond(x, B, io->t, c->cap_emb, tsin, th, temb, ada, mod_own, hl_own);
     mod = mod_own; hl = hl_own;
   }
   float* xcur = xs_;
@@ -740,4 +751,76 @@ extern "C" int vb_dit_prepare(const vb_dit_desc* d, const vb_dit_prep_desc* p, c
                               int64_t ws_bytes, void* stream) {
   if (!d || !p || !out || !ws) return set_error(VB_ERR_INVALID, "vb_dit_prepare: null pointer");
   return dit_prepare_run(d, p, midi, beats, Bm, Tm, caption, B, L, out->T, out, caption_out, ws, ws_bytes, stream, nullptr);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// The classifier-free-guidance flow sampler (reference ldm/models/diffusion/cfm1_audio_sampler.py:87-116,
+// cfm1_audio.py:145-162 `Wrapper_cfg`, torchdyn fixed-step Euler): n_steps x { one DiT evaluation of the stacked
+// (cond, uncond) batch ; x += dt * (v_u + w (v_c - v_u)) } — the launch sequence of versband_b200/sampler.py:
+// FlowSampler._run issued from C++. The adaLN / gate vectors of all steps are computed first in one batch of
+// n_steps * B rows (they depend only on t and the caption).
+// ------------------------------------------------------------------------------------------------------------
+static int sample_run(const vb_dit_desc* d, const vb_dit_cond* c, const vb_sample_args* a, int Bc, int T, int S, void* ws, int64_t ws_bytes,
+                      void* stream, int64_t* need) {
+  const bool dry = need != nullptr;
+  if (!d || Bc <= 0 || T <= 0 || S <= 0) return set_error(VB_ERR_INVALID, "vb_sample_cfg: bad arguments");
+  const int B = 2 * Bc, D = d->D, depth = d->depth, E = d->E, C = d->C;
+  const int64_t N = (int64_t)B * T, mld = d->mod_ld;
+  int64_t dit_bytes = 0;
+  int rc = dit_run(d, nullptr, nullptr, nullptr, 0, nullptr, B, T, &dit_bytes);
+  if (rc) return rc;
+  DitCtx x{d, stream, dry, 0, d->operand_f32 != 0, d->operand_f32 ? 32 : 64};
+  const int64_t es = x.es();
+  Bump bump{static_cast<uint8_t*>(dry ? nullptr : ws), 0, ws_bytes};
+  void* dit_ws = bump.take(dit_bytes);  // first: the caller's one-time zero fill covers the MoE counters
+  void* x_cl = bump.take(N * 32 * es);
+  float* v = static_cast<float*>(bump.take(N * 32 * 4));
+  float* lb_own = static_cast<float*>(bump.take((int64_t)depth * 4));
+  const int R = S * B;
+  void* tsin = bump.take((int64_t)R * 256 * es);
+  void* th = bump.take((int64_t)R * D * es);
+  float* temb = static_cast<float*>(bump.take((int64_t)R * D * 4));
+  float* cap_rep = static_cast<float*>(bump.take((int64_t)R * D * 4));
+  void* ada = bump.take((int64_t)R * D * es);
+  float* mod_all = static_cast<float*>(bump.take((int64_t)R * mld * 4));
+  float* hl_all = static_cast<float*>(bump.take((int64_t)R * 2 * depth * 4));
+  if (dry) { *need = (bump.off + 255) & ~int64_t(255); return VB_OK; }
+  if (bump.off > ws_bytes) return set_error(VB_ERR_INVALID, "vb_sample_cfg: workspace too small (%lld bytes needed)", (long long)bump.off);
+  if (!c || !a || c->B != B || c->T != T || !a->t_all || !a->dt || !a->e0 || !a->e1 || !a->e2 || !a->x)
+    return set_error(VB_ERR_INVALID, "vb_sample_cfg: bad conditioning / argument block (the conditioning batch must hold 2 * Bc rows)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int s = 0; s < S && !x.rc; ++s)
+    x.run([&] {
+      cudaError_t e = cudaMemcpyAsync(cap_rep + (int64_t)s * B * D, c->cap_emb, (size_t)B * D * 4, cudaMemcpyDeviceToDevice, st);
+      return e == cudaSuccess ? VB_OK : set_error(VB_ERR_CUDA, "vb_sample_cfg: %s", cudaGetErrorString(e));
+    });
+  dit_time_cond(x, R, a->t_all, cap_rep, tsin, th, temb, ada, mod_all, hl_all);
+  for (int s = 0; s < S && !x.rc; ++s) {
+    vb_dit_io io;
+    memset(&io, 0, sizeof(io));
+    io.x = a->x; io.Bx = Bc; io.x_cl = x_cl; io.x_cl_ready = s > 0;
+    io.mod = mod_all + (int64_t)s * B * mld; io.hl = hl_all + (int64_t)s * B * 2 * depth;
+    for (int k = 0; k < depth; ++k) {
+      const int64_t blk = (int64_t)s * depth + k;
+      io.e0[k] = a->e0 + blk * N * 2; io.e1[k] = a->e1 + blk * N * E; io.e2[k] = a->e2 + blk * N * E;
+    }
+    io.v = v; io.lb = a->lb ? a->lb : lb_own;
+    x.run([&] { return dit_run(d, c, &io, dit_ws, dit_bytes, stream, B, T, nullptr); });
+    // CFG mix + Euler update; the same launch rewrites the channels-last operand copies of x for the next step
+    x.run([&] { return vb_ntc_to_nct(v, v + (N / 2) * 32, 32, a->guidance, a->dt[s], a->x, Bc, C, T, x_cl, x.f32, 2, stream); });
+  }
+  return x.rc;
+}
+
+extern "C" int64_t vb_sample_workspace_bytes(const vb_dit_desc* d, int Bc, int T, int n_steps) {
+  int64_t need = 0;
+  if (sample_run(d, nullptr, nullptr, Bc, T, n_steps, nullptr, 0, nullptr, &need)) return -1;
+  return need;
+}
+
+extern "C" int vb_sample_cfg(const vb_dit_desc* d, const vb_dit_cond* cond2, const vb_sample_args* a, void* ws, int64_t ws_bytes,
+                             void* stream) {
+  if (!d || !cond2 || !a || !ws) return set_error(VB_ERR_INVALID, "vb_sample_cfg: null pointer");
+  return sample_run(d, cond2, a, a->Bc, cond2->T, a->n_steps, ws, ws_bytes, stream, nullptr);
 }

@@ -132,7 +132,37 @@ class FlowSampler:
         return torch.cat([st["e0"], st["e1"], st["e2"]], -1)
 
     # ---------------------------------------------------------------- loop body
+    def _run_c(self, st: dict, scale: float) -> None:
+        """The whole loop as ONE call of the model-level C entry point vb_sample_cfg (csrc/vb_model.cu)."""
+        import ctypes as C
+        from . import _lib
+        from ._lib import SampleArgs
+        dit, cond2 = self.dit, st["cond2"]
+        B, S = cond2.B // 2, len(self.sched)
+        d = dit._desc()
+        if "sws" not in st:
+            need = int(_lib.lib().vb_sample_workspace_bytes(C.byref(d), B, cond2.T, S))
+            if need < 0:
+                _lib.check(-1, "vb_sample_workspace_bytes")
+            st["sws"] = torch.zeros(need, device=dit.dev, dtype=torch.uint8)  # zero-filled once (MoE bucket counters)
+            st["dt_host"] = (C.c_float * S)(*[dt for _, dt in self.sched])
+            st["lb"] = torch.zeros(dit.depth, device=dit.dev, dtype=F32)
+        P = ops._ptr
+        a = SampleArgs()
+        a.n_steps, a.Bc, a.guidance = S, B, float(scale)
+        a.t_all, a.dt = P(st["t_all"]), st["dt_host"]
+        a.e0, a.e1, a.e2, a.x, a.lb = P(st["e0"]), P(st["e1"]), P(st["e2"]), P(st["x"]), P(st["lb"])
+        _lib.check(_lib.lib().vb_sample_cfg(C.byref(d), C.byref(dit._cond_struct(cond2)), C.byref(a), P(st["sws"]),
+                                            st["sws"].numel(), ops._stream()), "vb_sample_cfg")
+
     def _run(self, st: dict, scale: float, rng: bool, generator) -> None:
+        dit = self.dit
+        if not (rng or self.concurrent_cfg or dit.use_chain or dit.fused_dispatch or ops.TIMELINE is not None):
+            return self._run_c(st, scale)
+        return self._run_py(st, scale, rng, generator)
+
+    def _run_py(self, st: dict, scale: float, rng: bool, generator) -> None:
+        """The loop issued from Python (torch RNG inside the loop, or one of the experimental launch variants)."""
         d = self.dit.depth
         x, cond2, N = st["x"], st["cond2"], st["N"]
         # adaLN / gate vectors of all steps in one batch of S*2B rows (they only depend on t and caption)
