@@ -558,6 +558,12 @@ int vb_gn_stats(const float* x, int B, int T, int C, int G, float eps, float* me
                 void* scratch, void* stream);
 int vb_gn_apply(const float* x, const float* mean, const float* rstd, const float* w,
                 const float* bias, int B, int T, int C, int G, int act, void* out_fp16, void* stream);
+/* GroupNorm + activation -> fp16 in ONE launch (a cluster of 8 CTAs per (batch, group) exchanges fp64 partial sums
+ * through distributed shared memory; x is read once). vb_gn_fused_fits: 1 if the shape is supported (C/G a multiple
+ * of 4, T >= 8, the slab of T/8 rows x C/G channels fits in shared memory); otherwise use vb_gn_stats + vb_gn_apply. */
+int vb_gn_fused_fits(int T, int C, int G);
+int vb_gn_fused(const float* x, const float* w, const float* bias, int B, int T, int C, int G, float eps, int act,
+                void* out_fp16, void* stream);
 /* HiFi-GAN conv_post + tanh (vocoder/hifigan/modules/hifigan.py:139-141); w is [k][C] fp32 */
 int vb_conv_post(const void* x_fp16, const float* w, float bias, int B, int T, int C, int k,
                  float* wav, void* stream);

@@ -42,8 +42,61 @@ def _fan_in(shape) -> int:
     return n
 
 
-def synth_state_dict(manifest: Dict[str, list], seed: int, gain: float = 1.0) -> Dict[str, torch.Tensor]:
-    """Seeded fp32 tensors for every key of `manifest` (sorted key order → reproducible)."""
+def survey_state_dict(manifest: Dict[str, list], seed: int) -> Dict[str, torch.Tensor]:
+    """The weight recipe of SURVEY.md §8(d), restated from the manifest alone (names + shapes): PyTorch's default
+    module inits — Linear / Conv: weight and bias ~ U(+-1/sqrt(fan_in)) (kaiming_uniform, a = sqrt 5); Embedding
+    N(0, 1); MultiheadAttention in_proj xavier-uniform with zero biases — then every parameter the reference
+    zero-initialises (`final_layer.linear.*`, `adaLN_modulation.1.*`) ~ N(0, 0.02), `attention.gate` ~ N(0, 0.5),
+    norm weights 1 + N(0, 0.02) (norm biases stay 0); HiFi-GAN: weight_v ~ N(0, 0.01) (init_weights,
+    vocoder/hifigan/modules/hifigan.py:11-14), weight_g = ||v|| (weight_norm's initial value)."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    keys = sorted(manifest)
+    for key in keys:
+        shape = list(manifest[key])
+        leaf = key.rsplit(".", 1)[-1]
+        stem = key[: -len(leaf)]
+        rn = lambda: torch.randn(shape, generator=g, dtype=torch.float32)  # noqa: E731
+        ru = lambda b: (torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1) * b  # noqa: E731
+        if "final_layer.linear." in key or "adaLN_modulation.1." in key:
+            t = 0.02 * rn()
+        elif "embedding" in key:
+            t = rn()
+        elif leaf == "gate":
+            t = 0.5 * rn()
+        elif leaf == "weight_v":
+            t = 0.01 * rn()
+        elif leaf == "weight_g":
+            t = None
+        elif leaf == "in_proj_weight":
+            t = ru(math.sqrt(6.0 / (shape[0] + shape[1])))
+        elif leaf == "in_proj_bias" or key.endswith("out_proj.bias"):
+            t = torch.zeros(shape)
+        elif leaf == "bias":
+            wshape = manifest.get(stem + "weight") or manifest.get(stem + "weight_v")
+            if wshape is None or len(wshape) == 1:  # norm bias
+                t = torch.zeros(shape)
+            else:
+                fan = _fan_in(list(wshape)) if not key.startswith("ups.") else wshape[1] * wshape[2]
+                t = ru(1.0 / math.sqrt(fan))
+        elif len(shape) == 1:  # norm scales
+            t = 1.0 + 0.02 * rn()
+        else:
+            t = ru(1.0 / math.sqrt(_fan_in(shape)))
+        sd[key] = t
+    for key in keys:
+        if key.endswith("weight_g"):
+            v = sd[key[:-1] + "v"]
+            sd[key] = v.flatten(1).norm(dim=1).view(manifest[key])
+    return sd
+
+
+def synth_state_dict(manifest: Dict[str, list], seed: int, gain: float = 1.0, recipe: str = "fan_in") -> Dict[str, torch.Tensor]:
+    """Seeded fp32 tensors for every key of `manifest` (sorted key order → reproducible).
+    recipe "fan_in" (default): every matrix ~ N(0, gain^2 / fan_in), so that activations stay O(1) through all
+    layers and every branch (gates, adaLN, final layer) contributes; "survey": SURVEY.md §8(d)'s recipe."""
+    if recipe == "survey":
+        return survey_state_dict(manifest, seed)
     g = torch.Generator().manual_seed(seed)
     sd = {}
     for key in sorted(manifest):

@@ -192,6 +192,20 @@ def test_groupnorm_and_conv_post():
     ops.gn_apply(x, mean, rstd, w, b, B, T, C, 32, ops.ACT_SILU, out)
     ref = F.silu(F.group_norm(x.transpose(1, 2), 32, w, b, 1e-6)).transpose(1, 2)
     close(out, ref, 8e-3)
+    # the single-launch cluster kernel: same statistics (fp64 partial sums), same fp16 output up to rounding
+    for Bf, Tf, Cf in ((2, 300, 384), (1, 750, 1536), (3, 1501, 768), (1, 9, 128)):
+        xf = torch.randn(Bf, Tf, Cf, device=d) * 2 + 1
+        wf, bf = torch.randn(Cf, device=d), torch.randn(Cf, device=d)
+        assert ops.gn_fused_fits(Tf, Cf, 32)
+        of = torch.zeros(Bf, Tf, Cf, device=d, dtype=H16)
+        ops.gn_fused(xf, wf, bf, Bf, Tf, Cf, 32, 1e-6, ops.ACT_SILU, of)
+        rf = F.silu(F.group_norm(xf.double().transpose(1, 2), 32, wf.double(), bf.double(), 1e-6)).transpose(1, 2)
+        close(of, rf.float(), 2e-3)
+        m2, r2, o2 = torch.empty(Bf * 32, device=d), torch.empty(Bf * 32, device=d), torch.empty_like(of)
+        ops.gn_stats(xf, Bf, Tf, Cf, 32, 1e-6, m2, r2)
+        ops.gn_apply(xf, m2, r2, wf, bf, Bf, Tf, Cf, 32, ops.ACT_SILU, o2)
+        assert float((of.float() - o2.float()).abs().max()) <= 4e-3 * float(o2.float().abs().max())
+    assert not ops.gn_fused_fits(750, 384 + 2, 32) and not ops.gn_fused_fits(4, 384, 32)
     xb = torch.randn(B, 500, 32, device=d).to(H16)
     wp = torch.randn(7, 32, device=d) * 0.1
     wav = torch.empty(B, 500, device=d)

@@ -239,6 +239,7 @@ def _declare(l: C.CDLL) -> None:
         "vb_pool2_sum": [P, P, I, I, I, I, P, P, P],
         "vb_gn_stats": [P, I, I, I, I, F, P, P, P, P],
         "vb_gn_apply": [P, P, P, P, P, I, I, I, I, I, P, P],
+        "vb_gn_fused": [P, P, P, I, I, I, I, F, I, P, P],
         "vb_conv_post": [P, P, F, I, I, I, I, P, P],
         "vb_resblock_pair": [P, P, P, P, P, P, I, I, I, I, I, F, P],
         "vb_adamw": [P, P, P, P, L, F, F, F, F, F, F, F, P],

@@ -1,5 +1,6 @@
 // Elementwise / layout / GroupNorm kernels (HBM-bound; coalesced, vectorised where aligned).
 #include "vb_internal.h"
+#include "vb_ptx.cuh"
 
 namespace vb {
 
@@ -386,6 +387,80 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, const float* __rest
   }
 }
 
+// GroupNorm (+ activation) -> fp16 in ONE launch: a thread-block cluster of GN_CL CTAs owns one (batch, group); each
+// CTA stages its slab of rows in shared memory while accumulating fp64 partial sums, the partials are exchanged
+// through distributed shared memory (every CTA sums them in the same order: deterministic), and the slab is
+// normalised from shared memory — x is read from HBM/L2 once, no statistics round trip, one launch instead of three.
+constexpr int GN_CL = 8;
+__global__ void __launch_bounds__(256) gn_fused_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, int T, int C, int G, float eps,
+                                                       int act, __half* __restrict__ out) {
+  pdl_sync();
+  extern __shared__ float gn_tile[];  // [rows][cpg]
+  __shared__ double part[2];
+  __shared__ double sh[2][8];
+  __shared__ float stat[2];
+  const int sp = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
+  const int cpg = C / G, cq = cpg >> 2;
+  const int t0 = (int)((long long)T * sp / GN_CL), t1 = (int)((long long)T * (sp + 1) / GN_CL);
+  const long long base = ((long long)b * T + t0) * C + g * cpg;
+  const int nvec = (t1 - t0) * cq;
+  double s = 0.0, ss = 0.0;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const int r = i / cq, c4 = i - r * cq;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + base + (long long)r * C + c4 * 4));
+    reinterpret_cast<float4*>(gn_tile)[i] = v;
+    s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
+    ss += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh[0][warp] = s; sh[1][warp] = ss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s = 0.0; ss = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { s += sh[0][k]; ss += sh[1][k]; }
+    part[0] = s; part[1] = ss;
+  }
+  cluster_sync_all();  // partials of all GN_CL CTAs visible cluster-wide
+  if (threadIdx.x == 0) {
+    s = 0.0; ss = 0.0;
+    const uint32_t local = smem_u32(part);
+    for (int k = 0; k < GN_CL; ++k) {
+      const uint32_t remote = mapa_shared(local, (uint32_t)k);
+      double a, q;
+      asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(a) : "r"(remote));
+      asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(q) : "r"(remote + 8));
+      s += a; ss += q;
+    }
+    const double n = (double)T * cpg;
+    const double m = s / n;
+    const double var = ss / n - m * m;
+    stat[0] = (float)m;
+    stat[1] = (float)(1.0 / sqrt((var > 0 ? var : 0) + (double)eps));
+  }
+  cluster_sync_all();  // (also: no CTA exits while a peer may still read its partials)
+  const float m = stat[0], r_ = stat[1];
+  const float* wg = w + g * cpg;
+  const float* bg = bias + g * cpg;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const int r = i / cq, c4 = i - r * cq;
+    const float4 v = reinterpret_cast<const float4*>(gn_tile)[i];
+    const float4 ww = __ldg(reinterpret_cast<const float4*>(wg + c4 * 4));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(bg + c4 * 4));
+    const __half2 p0 = vb_f2h2(act_f((v.x - m) * r_ * ww.x + bb.x, act, 0.f), act_f((v.y - m) * r_ * ww.y + bb.y, act, 0.f));
+    const __half2 p1 = vb_f2h2(act_f((v.z - m) * r_ * ww.z + bb.z, act, 0.f), act_f((v.w - m) * r_ * ww.w + bb.w, act, 0.f));
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&p0);
+    u.y = *reinterpret_cast<const uint32_t*>(&p1);
+    *reinterpret_cast<uint2*>(out + base + (long long)r * C + c4 * 4) = u;
+  }
+}
+
 // HiFi-GAN conv_post (modules/hifigan.py:139-141): x is the already leaky-relu'd fp16
 // activation [B, T, C]; wav[b, t] = tanh(bias + sum_{j,c} w[j, c] * x[b, t + j - pad, c]).
 // One warp per 32 output samples: each lane owns one sample; weights in shared memory.
@@ -504,6 +579,31 @@ extern "C" int vb_gn_apply(const float* x, const float* mean, const float* rstd,
   launch_k(gn_apply_kernel, dim3(grid_for(nvec, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       x, mean, rstd, w, bias, T, C, G, act, static_cast<__half*>(out_fp16), nvec);
   return check_launch("vb_gn_apply");
+}
+
+// GroupNorm + activation -> fp16 in one cluster launch (falls back to stats + apply for shapes whose slab does not
+// fit in shared memory: scratch / mean / rstd as for vb_gn_stats, may be NULL when the fused kernel applies)
+extern "C" int vb_gn_fused_fits(int T, int C, int G) {
+  if (C % G || (C / G) % 4 || T < vb::GN_CL) return 0;
+  const long long rows = ((long long)T + vb::GN_CL - 1) / vb::GN_CL + 1;
+  return rows * (C / G) * 4 <= 200 * 1024;
+}
+
+extern "C" int vb_gn_fused(const float* x, const float* w, const float* bias, int B, int T, int C, int G, float eps, int act,
+                           void* out_fp16, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_GN, stream);
+  if (!x || !w || !bias || !out_fp16 || !vb_gn_fused_fits(T, C, G)) return set_error(VB_ERR_INVALID, "vb_gn_fused: bad arguments / shape does not fit");
+  const long long rows = ((long long)T + vb::GN_CL - 1) / vb::GN_CL + 1;
+  const size_t smem = (size_t)rows * (C / G) * 4;
+  static vb::PerDevice<size_t> attr_smem;
+  if (smem > 48 * 1024 && attr_smem.get() < smem) {
+    cudaError_t e = cudaFuncSetAttribute(vb::gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return set_error(VB_ERR_CUDA, "vb_gn_fused: %s", cudaGetErrorString(e));
+    attr_smem.get() = 200 * 1024;
+  }
+  launch_k_cluster(vb::gn_fused_kernel, vb::GN_CL, dim3(vb::GN_CL, G, B), dim3(256), smem, static_cast<cudaStream_t>(stream), x, w, bias,
+                   T, C, G, eps, act, static_cast<__half*>(out_fp16));
+  return check_launch("vb_gn_fused");
 }
 
 extern "C" int vb_conv_post(const void* x_fp16, const float* w, float bias, int B, int T, int C, int k,

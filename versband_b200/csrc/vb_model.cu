@@ -213,6 +213,10 @@ struct VaeCtx {
   // GroupNorm (+ optional swish) of fp32 x [B, T, C] -> fp16 scratch buffer
   void* gn(const float* x, int T, int C, const float* w, const float* b, int act) {
     void* out = sc.take((int64_t)B * T * C * 2);
+    if (vb_gn_fused_fits(T, C, d->groups)) {  // one cluster launch: statistics through DSMEM, x read once
+      run([&] { return vb_gn_fused(x, w, b, B, T, C, d->groups, d->eps, act, out, stream); });
+      return out;
+    }
     run([&] { return vb_gn_stats(x, B, T, C, d->groups, d->eps, mean, rstd, gn_scratch, stream); });
     run([&] { return vb_gn_apply(x, mean, rstd, w, b, B, T, C, d->groups, act, out, stream); });
     return out;

@@ -285,6 +285,15 @@ def gn_apply(x, mean, rstd, w, b, B, T, Cc, G, act, out_fp16) -> None:
     _call("vb_gn_apply", _ptr(x), _ptr(mean), _ptr(rstd), _ptr(w), _ptr(b), B, T, Cc, G, act, _ptr(out_fp16))
 
 
+def gn_fused_fits(T: int, Cc: int, G: int) -> bool:
+    return bool(_lib.lib().vb_gn_fused_fits(T, Cc, G))
+
+
+def gn_fused(x, w, b, B, T, Cc, G, eps, act, out_fp16) -> None:
+    """GroupNorm + activation -> fp16 in one cluster launch (include/versband.h: vb_gn_fused)."""
+    _call("vb_gn_fused", _ptr(x), _ptr(w), _ptr(b), B, T, Cc, G, eps, act, _ptr(out_fp16))
+
+
 def conv_post(x_fp16, w, bias: float, B, T, Cc, k, wav) -> None:
     _call("vb_conv_post", _ptr(x_fp16), _ptr(w), bias, B, T, Cc, k, _ptr(wav))
 

@@ -77,6 +77,10 @@ class VAEEngine:
         return Cout
 
     def _gn(self, x, name, B, T, C, act):
+        if ops.gn_fused_fits(T, C, self.G):  # one cluster launch: stats through DSMEM, x read once
+            out = torch.empty(B, T, C, device=self.dev, dtype=H16)
+            ops.gn_fused(x, self.w[name + ".weight"], self.w[name + ".bias"], B, T, C, self.G, 1e-6, act, out)
+            return out
         mean = torch.empty(B * self.G, device=self.dev, dtype=F32)
         rstd = torch.empty_like(mean)
         out = torch.empty(B, T, C, device=self.dev, dtype=H16)
