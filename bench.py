@@ -276,9 +276,27 @@ def run_ours(args):
         host_all = [torch.cat(allc[i], 0).pin_memory() for i in (1, 2, 3, 4, 0)]
         wav_all = torch.empty(B * world, T_MEL * 320, dtype=torch.float32, pin_memory=True)
 
+    # N > 1, one node: the controller's host buffers are shared page-locked memory and every GPU moves its own shard
+    # over its own PCIe link (versband_b200/dist.py:HostExchange); set up collectively, NCCL scatter/gather otherwise
+    hx = None
+    if use_dist and args.e2e_exchange == "host":
+        try:
+            from versband_b200.dist import HostExchange
+            specs = [(tuple(t.shape[1:]), t.dtype) for t in host_all] if rank == 0 else None
+            hx = HostExchange(B * world, specs, ((T_MEL * 320,), torch.float32) if rank == 0 else None, device=dev)
+            if rank == 0:
+                for dst_, src_ in zip(hx.inputs, host_all):
+                    dst_.copy_(src_)
+        except RuntimeError as e:
+            hx = None
+            if rank == 0:
+                print(f"[bench] HostExchange unavailable ({e}); e2e leg uses NCCL scatter/gather", file=sys.stderr)
+
     def step_host():
         if not use_dist:
             return pipe.generate_host(host[0], host[1], host[2], host[3], x0=host[4], generator=gen, out_wav=wav_host)
+        if hx is not None:
+            return hx.step(lambda loc: pipe.generate(loc[0], loc[1], loc[2], loc[3], x0=loc[4], generator=gen)["wav"])
         # N > 1: H2D on rank 0 -> NCCL scatter of the clips -> generate -> NCCL gather -> D2H on rank 0
         from versband_b200.dist import run_data_parallel
         ins = [t.to(dev, non_blocking=True) for t in host_all] if rank == 0 else None
@@ -470,7 +488,9 @@ def run_ours(args):
                     "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in (host_all if use_dist else host))),
                     "d2h_bytes_per_step": int((wav_all if use_dist else wav_host).numel() * 4),
-                    "path": ("pinned host -> H2D -> NCCL scatter -> generate -> NCCL gather -> D2H (rank 0)" if use_dist
+                    "path": ("shared pinned host -> per-rank H2D of its shard -> generate -> per-rank D2H -> sequence counters (no collective)"
+                             if use_dist and hx is not None else
+                             "pinned host -> H2D -> NCCL scatter -> generate -> NCCL gather -> D2H (rank 0)" if use_dist
                              else "pinned host -> H2D -> generate -> D2H")},
             "gpu_launches": int(launches) * args.steps * 2 if launches else None,
             "gpu_launches_per_step": int(launches) if launches else None,
@@ -489,6 +509,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=1, help="clips per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-exchange", default="host", choices=["host", "nccl"],
+                    help="N > 1 e2e leg: shared pinned host memory (each GPU moves its own shard) or NCCL scatter/gather via rank 0")
     ap.add_argument("--no-config4", action="store_true", help="skip the extra 4-clips-per-GPU measurement (BASELINE configs[3])")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "tf32"],
                     help="GEMM operand format of the DiT: fp16 (default) or fp32-as-TF32 (twice the operand bytes)")

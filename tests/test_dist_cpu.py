@@ -62,3 +62,45 @@ def test_scatter_compute_gather_world2():
         ref = midi.float().sum((1, 2))[:, None] + cap.sum((1, 2))[:, None] * torch.ones(1, 5)
         assert torch.allclose(out, ref)
         assert torch.allclose(out2, ref + 16.0)
+
+
+def _host_worker(rank, world, port, n_clips, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from versband_b200.dist import HostExchange
+    specs = [((1, 16), torch.int64), ((4, 8), torch.float32)] if rank == 0 else None
+    ex = HostExchange(n_clips, specs, ((5,), torch.float32) if rank == 0 else None, device="cpu", spin_timeout_s=30)
+    outs = []
+    for step in range(3):
+        if rank == 0:
+            g = torch.Generator().manual_seed(step)
+            ex.inputs[0].copy_(torch.randint(0, 130, (n_clips, 1, 16), generator=g))
+            ex.inputs[1].copy_(torch.randn(n_clips, 4, 8, generator=g))
+        out = ex.step(lambda loc: loc[0].float().sum((1, 2))[:, None] + loc[1].sum((1, 2))[:, None] * torch.ones(1, 5))
+        if rank == 0:
+            outs.append(out.clone().tolist())
+    if rank == 0:
+        q.put(outs)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_host_exchange_shared_memory_world2():
+    """Shared-host-memory exchange (each rank moves its own shard; sequence counters instead of collectives)."""
+    ctx = mp.get_context("spawn")
+    for n_clips in (4, 3):
+        q = ctx.SimpleQueue()
+        port = _free_port()
+        procs = [ctx.Process(target=_host_worker, args=(r, 2, port, n_clips, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        outs = q.get()
+        for p in procs:
+            p.join(60)
+            assert p.exitcode == 0
+        for step, out in enumerate(outs):
+            g = torch.Generator().manual_seed(step)
+            midi = torch.randint(0, 130, (n_clips, 1, 16), generator=g)
+            cap = torch.randn(n_clips, 4, 8, generator=g)
+            ref = midi.float().sum((1, 2))[:, None] + cap.sum((1, 2))[:, None] * torch.ones(1, 5)
+            assert torch.allclose(torch.tensor(out), ref)

@@ -28,7 +28,9 @@ if world > 1:
 net = modules.TxtFlagLargeImprovedDiTV2(**synth.DIT_CFG)
 net.load_state_dict(synth.synth_state_dict(synth.load_manifest("dit"), seed=1234))
 net = net.to(dev).train()
-model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local]) if world > 1 else net
+# find_unused_parameters: `code_proj.*` exists in the reference's state_dict but is not on the forward path (SURVEY.md
+# section 8b); pytorch_lightning 1.9's DDP strategy (main.py:657) passes find_unused_parameters=True by default
+model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], find_unused_parameters=True) if world > 1 else net
 opt = train.FusedAdamW(net.parameters(), lr=1e-5)
 B, T = args.batch, args.T
 g = torch.Generator(device=dev).manual_seed(100 + rank)

@@ -8,8 +8,13 @@ what the reference's `mp.spawn` + `DistributedSampler` arrangement amounts to
 """
 from __future__ import annotations
 
+import atexit
+import os
+import time
+import uuid
 from typing import Callable, List, Optional, Sequence
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -128,3 +133,118 @@ def run_data_parallel(fn: Callable[[List[torch.Tensor]], torch.Tensor], inputs: 
     local = ex.scatter(inputs)
     res = fn(local)
     return ex.gather(res)
+
+
+class HostExchange:
+    """Single-node alternative to ClipExchange for a controller whose inputs and results live in HOST memory: the
+    controller's buffers are a page-locked shared-memory segment (/dev/shm, mapped and cudaHostRegister-ed by every
+    rank), so each GPU DMAs its own shard of the inputs and writes its own waveforms over ITS OWN PCIe link — instead
+    of funnelling every byte through rank 0's link and an NCCL scatter / gather (8 GPUs: 5.9 MB in + 15.4 MB out per
+    step through one link and five collectives vs 0.74 + 1.9 MB per link and no collective). Step hand-off is two
+    sequence counters in the same segment (controller -> workers "inputs ready", workers -> controller "shard done").
+
+    Rank `src` fills `inputs[i]` ([n_clips, ...] host tensors) and reads `output` after `step`; `step(fn)` maps this
+    rank's device shard through `fn` (list of [b, ...] tensors -> [b, ...] tensor). Setup is collective; if any rank
+    cannot map or page-lock the segment every rank raises, and the caller falls back to ClipExchange."""
+
+    def __init__(self, n_clips: int, in_specs: Optional[Sequence[tuple]], out_spec: Optional[tuple], *, device,
+                 src: int = 0, group=None, spin_timeout_s: float = 120.0):
+        self.n, self.src, self.group, self.device = n_clips, src, group, torch.device(device)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.lo, self.hi = shard_bounds(n_clips, self.rank, self.world)
+        self.timeout = spin_timeout_s
+        self.k = 0
+        meta = [None]
+        if self.rank == src:
+            path = f"/dev/shm/versband_{os.getpid()}_{uuid.uuid4().hex[:12]}"
+            meta = [dict(path=path, ins=[(tuple(sh), str(dt)) for sh, dt in in_specs], out=(tuple(out_spec[0]), str(out_spec[1])))]
+        dist.broadcast_object_list(meta, src=src, group=group)
+        m = meta[0]
+        dt_of = lambda name: getattr(torch, name.split(".")[-1])  # noqa: E731
+        specs = [(sh, dt_of(dt)) for sh, dt in m["ins"]] + [(m["out"][0], dt_of(m["out"][1]))]
+        offs, off = [], 4096  # first page: control block (int64 seq, int64 done[world])
+        for sh, dt in specs:
+            nbytes = n_clips * int(np.prod(sh, dtype=np.int64)) * torch.empty(0, dtype=dt).element_size()
+            offs.append((off, nbytes))
+            off += (nbytes + 4095) // 4096 * 4096
+        self.nbytes, self.path = off, m["path"]
+        ok, err = 1, None
+        try:
+            if self.rank == src:
+                with open(self.path, "wb") as f:
+                    f.truncate(self.nbytes)
+            self._sync_cpu_or_gpu()
+            self.map = np.memmap(self.path, dtype=np.uint8, mode="r+", shape=(self.nbytes,))
+            self.registered = False
+            if self.device.type == "cuda":
+                rc = torch.cuda.cudart().cudaHostRegister(self.map.ctypes.data, self.nbytes, 1)  # cudaHostRegisterPortable
+                if int(rc) != 0:
+                    raise RuntimeError(f"cudaHostRegister failed with status {int(rc)}")
+                self.registered = True
+        except Exception as e:  # noqa: BLE001  (decided collectively below)
+            ok, err = 0, e
+        flag = torch.tensor([ok], device=self.device if self.device.type == "cuda" else "cpu", dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            self.close()
+            raise RuntimeError(f"HostExchange: shared pinned host memory unavailable on at least one rank ({err})")
+        self.ctrl = self.map[:4096].view(np.int64)
+        if self.rank == src:
+            self.ctrl[: 1 + self.world] = 0
+        views = []
+        for (o, nb), (sh, dt) in zip(offs, specs):
+            views.append(torch.from_numpy(self.map[o:o + nb]).view(dt).view(n_clips, *sh))
+        self.inputs, self.output = views[:-1], views[-1]
+        b = self.hi - self.lo
+        self.recv = [torch.empty((b, *sh), dtype=dt, device=self.device) for sh, dt in specs[:-1]]
+        self._sync_cpu_or_gpu()
+        if self.rank == src:
+            try:
+                os.unlink(self.path)  # every rank has mapped it: the name can go now, the pages live on
+            except OSError:
+                pass
+        atexit.register(self.close)
+
+    def _sync_cpu_or_gpu(self) -> None:
+        if self.device.type == "cuda":
+            torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+
+    def _spin(self, cond) -> None:
+        t0 = time.monotonic()
+        while not cond():
+            if time.monotonic() - t0 > self.timeout:
+                raise RuntimeError("HostExchange: peer did not arrive (timeout)")
+
+    def step(self, fn: Callable[[List[torch.Tensor]], torch.Tensor]) -> Optional[torch.Tensor]:
+        self.k += 1
+        k, ctrl = self.k, self.ctrl
+        if self.rank == self.src:
+            ctrl[0] = k                                   # inputs of step k are in place
+        else:
+            self._spin(lambda: ctrl[0] >= k)
+        for buf, host in zip(self.recv, self.inputs):
+            buf.copy_(host[self.lo:self.hi], non_blocking=True)
+        res = fn(self.recv)
+        self.output[self.lo:self.hi].copy_(res, non_blocking=True)
+        if self.device.type == "cuda":
+            torch.cuda.current_stream().synchronize()
+        ctrl[1 + self.rank] = k                           # this rank's waveforms are in host memory
+        if self.rank != self.src:
+            return None
+        self._spin(lambda: int(ctrl[1:1 + self.world].min()) >= k)
+        return self.output
+
+    def close(self) -> None:
+        m = getattr(self, "map", None)
+        if m is not None and getattr(self, "registered", False):
+            try:
+                torch.cuda.cudart().cudaHostUnregister(m.ctypes.data)
+            except Exception:  # noqa: BLE001
+                pass
+            self.registered = False
+        if getattr(self, "path", None) and self.rank == self.src and os.path.exists(self.path):
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
