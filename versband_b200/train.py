@@ -157,12 +157,14 @@ def _attend(q, k, v):
 def _attention(P, pre, x, y, ang, H):              # flag_large_dit_moe.py:323-406
     B, T, D = x.shape
     hd = D // H
-    q = _rope(linear(x, P[pre + "wq.weight"]).view(B, T, H, hd), ang).permute(0, 2, 1, 3)
-    k = _rope(linear(x, P[pre + "wk.weight"]).view(B, T, H, hd), ang).permute(0, 2, 1, 3)
-    v = linear(x, P[pre + "wv.weight"]).view(B, T, H, hd).permute(0, 2, 1, 3)
+    # q|k|v (and the text k|v) as one stacked projection each: one forward GEMM, one dX, one dW
+    qkv = linear(x, torch.cat([P[pre + "wq.weight"], P[pre + "wk.weight"], P[pre + "wv.weight"]], 0)).view(B, T, 3, H, hd)
+    q = _rope(qkv[:, :, 0], ang).permute(0, 2, 1, 3)
+    k = _rope(qkv[:, :, 1], ang).permute(0, 2, 1, 3)
+    v = qkv[:, :, 2].permute(0, 2, 1, 3)
     out = _attend(q, k, v)
-    yk = linear(y, P[pre + "wk_y.weight"]).view(B, -1, H, hd).permute(0, 2, 1, 3)
-    yv = linear(y, P[pre + "wv_y.weight"]).view(B, -1, H, hd).permute(0, 2, 1, 3)
+    ykv = linear(y, torch.cat([P[pre + "wk_y.weight"], P[pre + "wv_y.weight"]], 0)).view(B, -1, 2, H, hd)
+    yk, yv = ykv[:, :, 0].permute(0, 2, 1, 3), ykv[:, :, 1].permute(0, 2, 1, 3)
     out = out + _attend(q, yk, yv) * P[pre + "gate"].tanh().view(1, -1, 1, 1)
     return linear(out.permute(0, 2, 1, 3).reshape(B, T, D), P[pre + "wo.weight"])
 
@@ -181,8 +183,8 @@ def _moe(P, pre, x, time, caption, acoustic, E, tau, expo, H=8):   # vocal2music
     w, b = P[pre + "cross_attention.in_proj_weight"], P[pre + "cross_attention.in_proj_bias"]
     L = caption.shape[1]
     q = linear(x, w[:D], b[:D]).view(B, T, H, hd).permute(0, 2, 1, 3)
-    k = linear(caption, w[D:2 * D], b[D:2 * D]).view(B, L, H, hd).permute(0, 2, 1, 3)
-    v = linear(caption, w[2 * D:], b[2 * D:]).view(B, L, H, hd).permute(0, 2, 1, 3)
+    kv = linear(caption, w[D:], b[D:]).view(B, L, 2, H, hd)
+    k, v = kv[:, :, 0].permute(0, 2, 1, 3), kv[:, :, 1].permute(0, 2, 1, 3)
     cap_feat = linear(_attend(q, k, v).permute(0, 2, 1, 3).reshape(B, T, D),
                       P[pre + "cross_attention.out_proj.weight"], P[pre + "cross_attention.out_proj.bias"])
     xf, cap_flat, ac_flat = x.reshape(-1, D), cap_feat.reshape(-1, D), acoustic.reshape(-1, D)
@@ -192,16 +194,30 @@ def _moe(P, pre, x, time, caption, acoustic, E, tau, expo, H=8):   # vocal2music
     cap_mask, ac_mask = hl_p[:, 0:1], hl_p[:, 1:2]
     cap_p = _gumbel_soft(linear(cap_flat, P[pre + "caption_gating_network.weight"], P[pre + "caption_gating_network.bias"]), tau, e1)
     ac_p = _gumbel_soft(linear(ac_flat, P[pre + "acoustic_gating_network.weight"], P[pre + "acoustic_gating_network.bias"]), tau, e2)
-    z_c = sum(_ffn(P, f"{pre}caption_experts.{i}.", xf) * cap_p[:, i:i + 1] for i in range(E)) * cap_mask
-    z_a = sum(_ffn(P, f"{pre}acoustic_experts.{i}.", xf) * ac_p[:, i:i + 1] for i in range(E)) * ac_mask
-    yb = (z_c + z_a).view(B, T, D)
+    # The 2E routed experts run densely on every token in train mode (:157-165). Stacked: ONE GEMM for all w1|w3
+    # (N = 2 * 2E * Fh), and — since sum_e p_e (h_e W2_e^T) = [p_e h_e]_e [W2_e]_e^T — ONE GEMM with K = 2E * Fh for all
+    # w2 with the soft gates applied to the hidden activations: 2 large launches (and 2 x 2 in the backward pass,
+    # sharing one transposed copy of x) instead of 24 small ones whose dW products (K = all tokens) each filled
+    # a sixth of the machine.
+    names = [f"{pre}caption_experts.{i}." for i in range(E)] + [f"{pre}acoustic_experts.{i}." for i in range(E)]
+    Fh = P[names[0] + "w1.weight"].shape[0]
+    w13 = torch.cat([P[n + "w1.weight"] for n in names] + [P[n + "w3.weight"] for n in names], 0)   # [2 * 2E * Fh, D]
+    h13 = linear(xf, w13)
+    gate_w = torch.cat([cap_p * cap_mask, ac_p * ac_mask], dim=1)                                   # [N, 2E]
+    hid = (F.silu(h13[:, : 2 * E * Fh]) * h13[:, 2 * E * Fh:]).view(-1, 2 * E, Fh) * gate_w.unsqueeze(-1)
+    w2 = torch.cat([P[n + "w2.weight"] for n in names], 1)                                          # [D, 2E * Fh]
+    yb = linear(hid.reshape(-1, 2 * E * Fh), w2).view(B, T, D)
     band = D // E
-    zs = []
-    for i in range(E):                             # each frequency expert sees only its band (:171-178)
-        region = torch.zeros_like(yb)
-        region[:, :, band * i: band * (i + 1)] = 1.0
-        zs.append(_ffn(P, f"{pre}freq_experts.{i}.", yb * region)[:, :, band * i: band * (i + 1)])
-    z = torch.cat(zs, dim=-1)
+    # frequency experts: expert i sees only its band of y and keeps only its band of the output (:171-178) =
+    # batched GEMMs over the band slices of the weights (the masked-out columns / rows get exactly zero gradient)
+    fn = [f"{pre}freq_experts.{i}." for i in range(E)]
+    f13 = torch.stack([torch.cat([P[n + "w1.weight"][:, band * i: band * (i + 1)], P[n + "w3.weight"][:, band * i: band * (i + 1)]], 0)
+                       for i, n in enumerate(fn)], 0)                                               # [E, 2 Fh, band]
+    yband = yb.reshape(-1, E, band).permute(1, 0, 2)                                                # [E, N, band]
+    hf13 = bmm_nt(yband, f13)                                                                       # [E, N, 2 Fh]
+    hf = F.silu(hf13[..., :Fh]) * hf13[..., Fh:]
+    f2 = torch.stack([P[n + "w2.weight"][band * i: band * (i + 1)] for i, n in enumerate(fn)], 0)   # [E, band, Fh]
+    z = bmm_nt(hf, f2).permute(1, 0, 2).reshape(B, T, D)                                            # [E, N, band] -> [B, T, D]
     all_p = torch.cat([cap_p, ac_p], dim=1)        # load-balancing loss, :95-115
     all_m = torch.cat([cap_mask.repeat(1, E), ac_mask.repeat(1, E)], dim=1)
     usage = (all_p * all_m).sum(dim=0) / (all_m.sum() + 1e-10)
