@@ -167,6 +167,10 @@ int vb_stem_gather(const int64_t* midi, const int64_t* beats, const float* tab_m
  * ------------------------------------------------------------------------------------------ */
 /* AdamW update of one fp32 parameter tensor (training step): torch.optim.AdamW semantics
  * with bias corrections c1 = 1 - b1^t, c2 = 1 - b2^t computed by the caller. */
+/* out[g][c][r] = in[g][r][c], fp32, `batch` matrices of rows x cols; ld_out >= rows, the padding columns are zeroed
+ * (operand transposes of the training backward pass: dW = dY^T X reduces over the tokens, vb_gemm operands are K-major) */
+int vb_transpose_f32(const float* in, int64_t rows, int64_t cols, int64_t ld_in, int64_t in_batch_stride, float* out,
+                     int64_t ld_out, int64_t out_batch_stride, int batch, void* stream);
 int vb_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, float wd,
              float c1, float c2, void* stream);
 int vb_wave_prepare(const float* wav, int B, int64_t n, int pad, int64_t plane, void* out_fp16, void* stream);

@@ -212,3 +212,17 @@ def test_groupnorm_and_conv_post():
     ops.conv_post(xb, wp, 0.05, B, 500, 32, 7, wav)
     ref = torch.tanh(F.conv1d(xb.float().transpose(1, 2), wp.t()[None].contiguous(), torch.tensor([0.05], device=d), padding=3))[:, 0]
     close(wav, ref, 2e-3)  # fp16 inputs, tanh output; fp32 accumulation order differs
+
+
+def test_transpose_f32():
+    d = "cuda"
+    for shape in ((6000, 768), (37, 5), (3, 750, 96), (2, 33, 130)):
+        x = torch.randn(*shape, device=d)
+        y = ops.transpose_f32(x)
+        R, Cc = shape[-2], shape[-1]
+        Rp = (R + 3) // 4 * 4
+        assert y.shape == (*shape[:-2], Cc, Rp)
+        assert torch.equal(y[..., :R], x.transpose(-1, -2)) and float(y[..., R:].abs().sum()) == 0.0
+    big = torch.randn(4, 100, 64, device=d)
+    v = big[:, 10:50, 8:40]  # strided view: ld 64, batch stride 6400
+    assert torch.equal(ops.transpose_f32(v), v.transpose(1, 2).contiguous())

@@ -243,6 +243,7 @@ def _declare(l: C.CDLL) -> None:
         "vb_conv_post": [P, P, F, I, I, I, I, P, P],
         "vb_resblock_pair": [P, P, P, P, P, P, I, I, I, I, I, F, P],
         "vb_adamw": [P, P, P, P, L, F, F, F, F, F, F, F, P],
+        "vb_transpose_f32": [P, L, L, L, L, P, L, L, I, P],
         "vb_wave_prepare": [P, I, L, I, L, P, P],
         "vb_loudness_pcm16": [P, I, L, F, P, P, P],
         "vb_stem_gather": [P, P, P, P, P, P, I, I, I, I, I, I, I, F, P, I, P],

@@ -676,3 +676,43 @@ extern "C" int vb_adamw(float* p, const float* g, float* m, float* v, int64_t n,
            eps, wd, c1, c2);
   return check_launch("vb_adamw");
 }
+
+// out[g][c][r] = in[g][r][c] for fp32 matrices (rows x cols, leading dimensions ld_in / ld_out >= rows; the
+// ld_out - rows padding columns are zero-filled): the operand transposes of the training backward pass
+// (dW = dY^T X needs both factors K-major over the tokens). 32 x 32 tiles through padded shared memory, both sides coalesced.
+namespace vb {
+__global__ void __launch_bounds__(256) transpose_f32_kernel(const float* __restrict__ in, long long rows, long long cols,
+                                                            long long ld_in, long long in_g, float* __restrict__ out,
+                                                            long long ld_out, long long out_g) {
+  pdl_sync();
+  __shared__ float tile[32][33];
+  const long long r0 = (long long)blockIdx.y * 32, c0 = (long long)blockIdx.x * 32;
+  const float* src = in + (long long)blockIdx.z * in_g;
+  float* dst = out + (long long)blockIdx.z * out_g;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const long long r = r0 + ty + j, c = c0 + tx;
+    tile[ty + j][tx] = (r < rows && c < cols) ? __ldg(src + r * ld_in + c) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const long long c = c0 + ty + j, r = r0 + tx;   // out row = input column
+    if (c < cols && r < ld_out) dst[c * ld_out + r] = tile[tx][ty + j];
+  }
+}
+}  // namespace vb
+
+extern "C" int vb_transpose_f32(const float* in, int64_t rows, int64_t cols, int64_t ld_in, int64_t in_batch_stride, float* out,
+                                int64_t ld_out, int64_t out_batch_stride, int batch, void* stream) {
+  vb::ProfScope prof_scope(vb::PK_LAYOUT, stream);
+  if (!in || !out || rows <= 0 || cols <= 0 || ld_in < cols || ld_out < rows || batch <= 0 || batch > 65535)
+    return set_error(VB_ERR_INVALID, "vb_transpose_f32: bad arguments");
+  const long long gy = (ld_out + 31) / 32, gx = (cols + 31) / 32;
+  if (gy > 65535) return set_error(VB_ERR_INVALID, "vb_transpose_f32: too many rows");
+  launch_k(vb::transpose_f32_kernel, dim3((unsigned)gx, (unsigned)gy, (unsigned)batch), dim3(256), 0, static_cast<cudaStream_t>(stream), in,
+           (long long)rows, (long long)cols, (long long)ld_in, (long long)in_batch_stride, out, (long long)ld_out,
+           (long long)out_batch_stride);
+  return check_launch("vb_transpose_f32");
+}

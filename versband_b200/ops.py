@@ -326,6 +326,18 @@ def adamw(p, g, m, v, *, lr, b1, b2, eps, wd, c1, c2) -> None:
     _call("vb_adamw", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), lr, b1, b2, eps, wd, c1, c2)
 
 
+def transpose_f32(x: torch.Tensor) -> torch.Tensor:
+    """[..., R, C] fp32 (last two dims dense: stride(-1) == 1) -> contiguous [..., C, ceil4(R)] with zero padding: the
+    K-major operand of a GEMM that reduces over R (include/versband.h: vb_transpose_f32)."""
+    assert x.dtype == torch.float32 and x.is_cuda and x.stride(-1) == 1 and x.dim() in (2, 3)
+    R, Cc = x.shape[-2], x.shape[-1]
+    G = x.shape[0] if x.dim() == 3 else 1
+    Rp = (R + 3) // 4 * 4
+    out = torch.empty((*x.shape[:-2], Cc, Rp), device=x.device, dtype=torch.float32)
+    _call("vb_transpose_f32", _ptr(x), R, Cc, x.stride(-2), x.stride(0) if x.dim() == 3 else 0, _ptr(out), Rp, Cc * Rp, G)
+    return out
+
+
 def wave_prepare(wav, out_fp16, *, pad: int, plane: int) -> None:
     B, n = wav.shape
     _call("vb_wave_prepare", _ptr(wav), B, n, pad, plane, _ptr(out_fp16))

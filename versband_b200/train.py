@@ -49,6 +49,17 @@ def _c(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def _kmajor(t: torch.Tensor) -> torch.Tensor:
+    """A GEMM operand [.., rows, K] as vb_gemm wants it: K contiguous, K % 4 == 0 (zero padded), 16-byte aligned. A
+    transposed view (the dW / dX factors of the backward pass) goes through the tiled transpose kernel
+    (vb_transpose_f32, both sides coalesced) instead of a generic strided copy."""
+    if t.dim() in (2, 3) and t.stride(-1) != 1 and t.stride(-2) == 1 and t.shape[-1] > 1:
+        base = t.transpose(-1, -2)
+        if base.data_ptr() % 16 == 0 and (t.dim() == 2 or base.stride(0) >= base.shape[1] * base.stride(1)):
+            return ops.transpose_f32(base)
+    return _c(_pad_k(t))
+
+
 class _LinearFn(torch.autograd.Function):
     """y = x W^T + b with forward and both backward products on the tcgen05 GEMM."""
 
@@ -67,9 +78,9 @@ class _LinearFn(torch.autograd.Function):
         dy2 = _c(dy.reshape(-1, dy.shape[-1]).float())
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = _gemm_nt(_c(_pad_k(dy2)), _c(_pad_k(w.t()))).view(ctx.shape)    # dX = dY W   (B operand = W^T, K-major in N)
+            dx = _gemm_nt(_kmajor(dy2), _kmajor(w.t())).view(ctx.shape)         # dX = dY W   (B operand = W^T, K-major in N)
         if ctx.needs_input_grad[1]:
-            dw = _gemm_nt(_c(_pad_k(dy2.t())), _c(_pad_k(x2.t())))              # dW = dY^T X (reduction over the tokens)
+            dw = _gemm_nt(_kmajor(dy2.t()), _kmajor(x2.t()))                    # dW = dY^T X (reduction over the tokens)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy2.sum(0)
         return dx, dw, db
@@ -101,7 +112,7 @@ class _BmmNT(torch.autograd.Function):
 
     @staticmethod
     def _run(a, b):
-        a, b = _c(_pad_k(a)), _c(_pad_k(b))
+        a, b = _kmajor(a), _kmajor(b)
         G, M, K = a.shape
         N = b.shape[1]
         out = torch.empty(G, M, N, device=a.device, dtype=F32)
