@@ -168,26 +168,30 @@ class HostExchange:
             offs.append((off, nbytes))
             off += (nbytes + 4095) // 4096 * 4096
         self.nbytes, self.path = off, m["path"]
+        # every step below is decided COLLECTIVELY (all_reduce MIN of a success flag, which is also the barrier the
+        # next step needs): a rank that fails never leaves its peers waiting in a different collective
+        self.registered = False
         ok, err = 1, None
+        if self.rank == src:
+            try:
+                fd = os.open(self.path, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+                try:
+                    os.posix_fallocate(fd, 0, self.nbytes)  # reserve the pages now: ENOSPC here, not SIGBUS on first touch
+                finally:
+                    os.close(fd)
+            except Exception as e:  # noqa: BLE001
+                ok, err = 0, e
+        self._agree(ok, err, "cannot create the shared segment")
         try:
-            if self.rank == src:
-                with open(self.path, "wb") as f:
-                    f.truncate(self.nbytes)
-            self._sync_cpu_or_gpu()
             self.map = np.memmap(self.path, dtype=np.uint8, mode="r+", shape=(self.nbytes,))
-            self.registered = False
             if self.device.type == "cuda":
                 rc = torch.cuda.cudart().cudaHostRegister(self.map.ctypes.data, self.nbytes, 1)  # cudaHostRegisterPortable
                 if int(rc) != 0:
                     raise RuntimeError(f"cudaHostRegister failed with status {int(rc)}")
                 self.registered = True
-        except Exception as e:  # noqa: BLE001  (decided collectively below)
+        except Exception as e:  # noqa: BLE001
             ok, err = 0, e
-        flag = torch.tensor([ok], device=self.device if self.device.type == "cuda" else "cpu", dtype=torch.int32)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-        if int(flag.item()) == 0:
-            self.close()
-            raise RuntimeError(f"HostExchange: shared pinned host memory unavailable on at least one rank ({err})")
+        self._agree(ok, err, "cannot map / page-lock the shared segment")
         self.ctrl = self.map[:4096].view(np.int64)
         if self.rank == src:
             self.ctrl[: 1 + self.world] = 0
@@ -204,6 +208,13 @@ class HostExchange:
             except OSError:
                 pass
         atexit.register(self.close)
+
+    def _agree(self, ok: int, err, what: str) -> None:
+        flag = torch.tensor([ok], device=self.device if self.device.type == "cuda" else "cpu", dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            self.close()
+            raise RuntimeError(f"HostExchange: {what} on at least one rank ({err})")
 
     def _sync_cpu_or_gpu(self) -> None:
         if self.device.type == "cuda":

@@ -132,6 +132,23 @@ class FlowSampler:
         return torch.cat([st["e0"], st["e1"], st["e2"]], -1)
 
     # ---------------------------------------------------------------- loop body
+    def _c_state(self, st: dict) -> None:
+        """Workspace of vb_sample_cfg, allocated and zero-filled ONCE (outside any graph capture: it carries the MoE
+        bucket counters from one evaluation to the next)."""
+        if "sws" in st:
+            return
+        import ctypes as C
+        from . import _lib
+        dit, cond2 = self.dit, st["cond2"]
+        S = len(self.sched)
+        d = dit._desc()
+        need = int(_lib.lib().vb_sample_workspace_bytes(C.byref(d), cond2.B // 2, cond2.T, S))
+        if need < 0:
+            _lib.check(-1, "vb_sample_workspace_bytes")
+        st["sws"] = torch.zeros(need, device=dit.dev, dtype=torch.uint8)
+        st["dt_host"] = (C.c_float * S)(*[dt for _, dt in self.sched])
+        st["lb"] = torch.zeros(dit.depth, device=dit.dev, dtype=F32)
+
     def _run_c(self, st: dict, scale: float) -> None:
         """The whole loop as ONE call of the model-level C entry point vb_sample_cfg (csrc/vb_model.cu)."""
         import ctypes as C
@@ -140,13 +157,7 @@ class FlowSampler:
         dit, cond2 = self.dit, st["cond2"]
         B, S = cond2.B // 2, len(self.sched)
         d = dit._desc()
-        if "sws" not in st:
-            need = int(_lib.lib().vb_sample_workspace_bytes(C.byref(d), B, cond2.T, S))
-            if need < 0:
-                _lib.check(-1, "vb_sample_workspace_bytes")
-            st["sws"] = torch.zeros(need, device=dit.dev, dtype=torch.uint8)  # zero-filled once (MoE bucket counters)
-            st["dt_host"] = (C.c_float * S)(*[dt for _, dt in self.sched])
-            st["lb"] = torch.zeros(dit.depth, device=dit.dev, dtype=F32)
+        self._c_state(st)
         P = ops._ptr
         a = SampleArgs()
         a.n_steps, a.Bc, a.guidance = S, B, float(scale)
@@ -251,6 +262,8 @@ class FlowSampler:
         elif pair is not st["cond2"]:
             st["cond2"].copy_from(pair)
         st["x"].copy_(x0)
+        if not torch.cuda.is_current_stream_capturing():
+            self._c_state(st)
         if rng and isinstance(generator, (list, tuple)):
             # per-clip seeding: clip c consumes generator[c] exactly as a batch-1 run would
             assert len(generator) == B
