@@ -38,7 +38,7 @@ __global__ void linear_small_kernel(const float* __restrict__ x, long long ldx,
 //               w = (1 - y[idx]) + y[idx]  (straight-through value)                       :81-93,150-151
 //  scale_c[n] = w_c * p[0], scale_a[n] = w_a * p[1]                                       :157-165
 template <int E>
-__global__ void router_kernel(const float* __restrict__ cap_feat, const __half* __restrict__ cap_feat_bf,
+__global__ void router_kernel(const float* __restrict__ cap_feat, const __half* __restrict__ cap_feat_h,
                               const float* __restrict__ Wc,
                               const float* __restrict__ bc, const float* __restrict__ ac_logits,
                               const float* __restrict__ hl_logits, int hl_ld, int ac_ld, const float* __restrict__ e0,
@@ -71,8 +71,8 @@ __global__ void router_kernel(const float* __restrict__ cap_feat, const __half* 
   } else if ((D & 127) == 0) {  // 16-byte loads: lane owns 4 consecutive features per 128-feature slab
     for (int d = lane * 4; d < D; d += 128) {
       float4 xv;
-      if (cap_feat_bf) {
-        const uint2 u = *reinterpret_cast<const uint2*>(cap_feat_bf + (long long)n * D + d);
+      if (cap_feat_h) {
+        const uint2 u = *reinterpret_cast<const uint2*>(cap_feat_h + (long long)n * D + d);
         const __half2 p0 = *reinterpret_cast<const __half2*>(&u.x);
         const __half2 p1 = *reinterpret_cast<const __half2*>(&u.y);
         xv = make_float4(__low2float(p0), __high2float(p0), __low2float(p1), __high2float(p1));
@@ -88,8 +88,8 @@ __global__ void router_kernel(const float* __restrict__ cap_feat, const __half* 
         acc[e] = fmaf(xv.w, wv.w, acc[e]);
       }
     }
-  } else if (cap_feat_bf) {
-    const __half* xr = cap_feat_bf + (long long)n * D;
+  } else if (cap_feat_h) {
+    const __half* xr = cap_feat_h + (long long)n * D;
 #pragma unroll 4
     for (int d = lane; d < D; d += 32) {
       const float xv = __half2float(xr[d]);

@@ -22,7 +22,7 @@ H16 = torch.float16
 F32 = torch.float32
 
 
-def _bf(t: torch.Tensor) -> torch.Tensor:
+def _h16(t: torch.Tensor) -> torch.Tensor:
     return t.to(H16).contiguous()
 
 
@@ -145,7 +145,7 @@ class DiTEngine:
         dev, D, E = self.dev, self.D, self.E
         g = lambda k: sd[k].detach().to(dev, F32).contiguous()  # noqa: E731
         adt = self.adt
-        _bf = (lambda t: t.to(H16).contiguous()) if adt == H16 else (lambda t: tf32_round(t.float()))  # noqa: E731
+        _op = (lambda t: t.to(H16).contiguous()) if adt == H16 else (lambda t: tf32_round(t.float()))  # noqa: E731
         pack_conv = lambda w_: pack_conv_weight(w_, dtype=adt)  # noqa: E731
         w: dict = {}
         # stem
@@ -153,7 +153,7 @@ class DiTEngine:
         for name in ("midi_proj", "beats_proj"):
             w[name + "_w"] = pack_conv(g(name + ".0.weight"))
             w[name + "_b"] = g(name + ".0.bias")
-        w["final_proj_w"] = _bf(g("final_proj.weight")[:, :, 0])
+        w["final_proj_w"] = _op(g("final_proj.weight")[:, :, 0])
         w["final_proj_b"] = g("final_proj.bias")
         # exact-table stem (vb_stem_gather): tab[tap][v] = W[:, :, tap] . emb[v] in fp64, and final_proj as the
         # split operand [W_hi | W_lo | W_hi] matching the activations' [hi | hi | lo]
@@ -162,8 +162,8 @@ class DiTEngine:
             em = sd[name + "_embedding.weight"].detach().to(dev, torch.float64)       # [V, D]
             w[name + "_tab"] = torch.einsum("oik,vi->kvo", cw, em).float().contiguous()  # [k, V, D]
         fp = g("final_proj.weight")[:, :, 0]
-        fp_hi = _bf(fp)
-        fp_lo = _bf(fp - fp_hi.float())
+        fp_hi = _op(fp)
+        fp_lo = _op(fp - fp_hi.float())
         w["final_proj_w3"] = torch.cat([fp_hi, fp_lo, fp_hi], 1).contiguous()
         w["proj_in_w"] = pack_conv(g("proj_in.weight"))
         w["proj_in_b"] = g("proj_in.bias")
@@ -171,11 +171,11 @@ class DiTEngine:
         self.stem_k = sd["midi_proj.0.weight"].shape[-1]
         # embedders
         for i in (0, 2):
-            w[f"t_w{i}"], w[f"t_b{i}"] = _bf(g(f"t_embedder.mlp.{i}.weight")), g(f"t_embedder.mlp.{i}.bias")
-            w[f"c_w{i}"], w[f"c_b{i}"] = _bf(g(f"c_embedder.mlp.{i}.weight")), g(f"c_embedder.mlp.{i}.bias")
+            w[f"t_w{i}"], w[f"t_b{i}"] = _op(g(f"t_embedder.mlp.{i}.weight")), g(f"t_embedder.mlp.{i}.bias")
+            w[f"c_w{i}"], w[f"c_b{i}"] = _op(g(f"c_embedder.mlp.{i}.weight")), g(f"c_embedder.mlp.{i}.bias")
         w["c_ln_w"], w["c_ln_b"] = g("c_embedder.mlp.3.weight"), g("c_embedder.mlp.3.bias")
         w["cap_ln_w"], w["cap_ln_b"] = g("cap_embedder.0.weight"), g("cap_embedder.0.bias")
-        w["cap_w"], w["cap_b"] = _bf(g("cap_embedder.1.weight")), g("cap_embedder.1.bias")
+        w["cap_w"], w["cap_b"] = _op(g("cap_embedder.1.weight")), g("cap_embedder.1.bias")
         half = 128
         w["t_freqs"] = torch.exp(-math.log(10000.0) * torch.arange(0, half, dtype=F32) / half).to(dev)
         # adaLN of all blocks + final layer as one [depth*6D + 2D, D] operand
@@ -183,7 +183,7 @@ class DiTEngine:
         ada_b = [g(f"blocks.{k}.adaLN_modulation.1.bias") for k in range(self.depth)]
         ada_w.append(g("final_layer.adaLN_modulation.1.weight"))
         ada_b.append(g("final_layer.adaLN_modulation.1.bias"))
-        w["ada_w"], w["ada_b"] = _bf(torch.cat(ada_w, 0)), torch.cat(ada_b, 0).contiguous()
+        w["ada_w"], w["ada_b"] = _op(torch.cat(ada_w, 0)), torch.cat(ada_b, 0).contiguous()
         self.mod_ld = w["ada_w"].shape[0]
         # gating networks stacked over blocks
         w["hl_w"] = torch.cat([g(f"blocks.{k}.feed_forward.high_level_gating_network.weight") for k in range(self.depth)], 0).contiguous()
@@ -196,13 +196,13 @@ class DiTEngine:
             p = f"blocks.{k}."
             a, f = p + "attention.", p + "feed_forward."
             b: dict = {}
-            b["wqkv"] = _bf(torch.cat([g(a + "wq.weight"), g(a + "wk.weight"), g(a + "wv.weight")], 0))
-            b["wo"] = _bf(g(a + "wo.weight"))
-            b["wkvy"] = _bf(torch.cat([g(a + "wk_y.weight"), g(a + "wv_y.weight")], 0))
+            b["wqkv"] = _op(torch.cat([g(a + "wq.weight"), g(a + "wk.weight"), g(a + "wv.weight")], 0))
+            b["wo"] = _op(g(a + "wo.weight"))
+            b["wkvy"] = _op(torch.cat([g(a + "wk_y.weight"), g(a + "wv_y.weight")], 0))
             b["gate"] = g(a + "gate")
             b["attn_norm"], b["ffn_norm"], b["y_norm"] = g(p + "attention_norm.weight"), g(p + "ffn_norm.weight"), g(p + "attention_y_norm.weight")
             ipw, ipb = g(f + "cross_attention.in_proj_weight"), g(f + "cross_attention.in_proj_bias")
-            b["mkv_w"], b["mkv_b"] = _bf(ipw[D:]), ipb[D:].contiguous()
+            b["mkv_w"], b["mkv_b"] = _op(ipw[D:]), ipb[D:].contiguous()
             # caption gate folded through the MHA out-projection (its only consumer, vocal2music_moe.py:122,141):
             # logits = Wg (Wo ctx + bo) + bg = (Wg Wo) ctx + (Wg bo + bg), all in fp32
             wo_m, bo_m = g(f + "cross_attention.out_proj.weight"), g(f + "cross_attention.out_proj.bias")
@@ -215,7 +215,7 @@ class DiTEngine:
             kpad = (self.hd + self.kq - 1) // self.kq * self.kq
             wqT = torch.zeros(self.H, D, kpad, device=dev)
             wqT[:, :, : self.hd] = (ipw[:D] * sc).view(self.H, self.hd, D).permute(0, 2, 1)
-            b["mq_wT"] = _bf(wqT)
+            b["mq_wT"] = _op(wqT)
             b["mq_bs"] = (ipb[:D] * sc).contiguous()
             w13, w2 = [], []
             for grp in ("caption_experts", "acoustic_experts"):
@@ -223,7 +223,7 @@ class DiTEngine:
                     w1, w3 = g(f"{f}{grp}.{e}.w1.weight"), g(f"{f}{grp}.{e}.w3.weight")
                     w13.append(torch.stack([w1, w3], 1).reshape(2 * w1.shape[0], D))
                     w2.append(g(f"{f}{grp}.{e}.w2.weight"))
-            b["w13"], b["w2"] = _bf(torch.stack(w13, 0)), _bf(torch.stack(w2, 0))  # [2E,2Fh,D], [2E,D,Fh]
+            b["w13"], b["w2"] = _op(torch.stack(w13, 0)), _op(torch.stack(w2, 0))  # [2E,2Fh,D], [2E,D,Fh]
             f13, f2 = [], []
             for e in range(E):
                 w1, w3 = g(f"{f}freq_experts.{e}.w1.weight"), g(f"{f}freq_experts.{e}.w3.weight")
@@ -231,7 +231,7 @@ class DiTEngine:
                 f13.append(torch.stack([w1[:, sl], w3[:, sl]], 1).reshape(2 * w1.shape[0], band))
                 f2.append(g(f"{f}freq_experts.{e}.w2.weight")[sl, :])
             f13w = torch.stack(f13, 0)
-            b["f13"], b["f2"] = _bf(torch.cat([f13w, f13w], -1)), _bf(torch.stack(f2, 0))  # [E,2Fh,2*band], [E,band,Fh]
+            b["f13"], b["f2"] = _op(torch.cat([f13w, f13w], -1)), _op(torch.stack(f2, 0))  # [E,2Fh,2*band], [E,band,Fh]
             blocks.append(b)
         self.Fh = blocks[0]["w2"].shape[-1]
         self.band = band
@@ -240,7 +240,7 @@ class DiTEngine:
         fl_w[: self.C] = g("final_layer.linear.weight")
         fl_b = torch.zeros(32, device=dev)
         fl_b[: self.C] = g("final_layer.linear.bias")
-        w["final_w"], w["final_b"] = _bf(fl_w), fl_b
+        w["final_w"], w["final_b"] = _op(fl_w), fl_b
         # RoPE table [max_len, hd/2, (cos, sin)] computed exactly like the reference (vocal2music_moe.py:464-475)
         freqs = 1.0 / (10000.0 ** (torch.arange(0, self.hd, 2)[: self.hd // 2].float() / self.hd))
         ang = torch.outer(torch.arange(self.max_len, dtype=F32), freqs).float()

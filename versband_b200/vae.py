@@ -12,7 +12,7 @@ from typing import Dict
 import torch
 
 from . import ops
-from .dit import H16, F32, _bf, pack_conv_weight
+from .dit import H16, F32, _h16, pack_conv_weight
 
 
 class VAEEngine:
