@@ -985,7 +985,7 @@ vb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // per tap (k = 3..11); here each tile's rows are fetched ONCE as a tall tile of 128 + (taps-1)*dil
 // rows, tap j is the same shared-memory tile seen through a UMMA descriptor shifted by j*dil rows
 // (start address + rows*128 B; base_offset stays 0 because the 128B swizzle is a pure function of the
-// shared-memory address — verified by tools/exp_rowshift.py), and all tap weights stay resident in shared
+// shared-memory address; tests/test_conv_halo_gpu.py), and all tap weights stay resident in shared
 // memory for the lifetime of the persistent CTA. Operand traffic per output row drops ~taps-fold.
 
 template <int BN, int KSTEPS, int EC>
