@@ -293,6 +293,7 @@ int vb_voc_forward(const vb_voc_desc* d, const float* mel, int B, int T, float* 
 #define VB_VAE_RES 0  /* ResnetBlock1D: n1 -> w1(k1) -> n2 -> w2(k2) + (ws ? ws(ks) x : x) */
 #define VB_VAE_ATTN 1 /* AttnBlock1D: n1 -> w1 = q|k|v [3C, C], b1 [3C] -> softmax(q k^T / sqrt(C)) v -> w2 = proj_out + x */
 #define VB_VAE_UP 2   /* Upsample1D: nearest x2 -> w1(k1) */
+#define VB_VAE_DOWN 3 /* Downsample1D (encoder): pad (0,1) + conv k3 stride 2 as a 2-tap conv over row pairs, w1 [C, 2 * 2C] */
 typedef struct vb_vae_op {
   int32_t kind, cin, cout, k1, k2, ks;
   const float *n1_w, *n1_b, *n2_w, *n2_b;
@@ -313,6 +314,14 @@ typedef struct vb_vae_desc {
 } vb_vae_desc;
 int64_t vb_vae_workspace_bytes(const vb_vae_desc* d, int B, int T);
 int vb_vae_decode(const vb_vae_desc* d, const float* z, float scale, int B, int T, float* mel, void* workspace,
+                  int64_t workspace_bytes, void* stream);
+/* The encoder through the same descriptor type (reference autoencoder1d.py:49-53,384-409): zc = in_ch,
+ * in_w = encoder.conv_in, ops = resblocks / attention / VB_VAE_DOWN, no_* = encoder.norm_out, out_w = encoder.conv_out
+ * (out_ch = 2 * z_channels), pq_w = quant_conv applied LAST (zq_c = 2 * embed_dim).
+ * x fp32 [B, in_ch, T] -> moments fp32 [B, zq_c, T / 2^n_down] (mean | logvar; DiagonalGaussianDistribution.mode() is
+ * the first half). */
+int64_t vb_vae_encode_workspace_bytes(const vb_vae_desc* d, int B, int T);
+int vb_vae_encode(const vb_vae_desc* d, const float* x, int B, int T, float* moments, void* workspace,
                   int64_t workspace_bytes, void* stream);
 
 /* One evaluation of the AccompBand DiT (reference TxtFlagLargeDiT.forward, vocal2music_moe.py:375-434) as ONE call:

@@ -114,3 +114,14 @@ def test_vae_c_entry_point_equals_python_launch_sequence(vae):
         torch.cuda.synchronize()
         assert a.shape == b.shape == (B, 80, 2 * T)
         assert torch.equal(a, b)
+
+
+def test_vae_encode_c_entry_point_equals_python_launch_sequence(vae):
+    """vb_vae_encode (Encoder1D + quant_conv issued from C++ through one C-ABI call) vs the same launches from Python."""
+    for B, T in ((2, 96), (1, 750)):
+        x = synth.mel_input(B, T, seed=31).cuda()
+        a = vae.encode_moments(x)
+        b = vae.encode_moments_py(x)
+        torch.cuda.synchronize()
+        assert a.shape == b.shape == (B, 2 * synth.VAE_EMBED_DIM, T // 2)
+        assert torch.equal(a, b)

@@ -74,7 +74,7 @@ class VocDesc(C.Structure):
 
 
 VAE_MAX_OPS = 48
-VAE_RES, VAE_ATTN, VAE_UP = 0, 1, 2
+VAE_RES, VAE_ATTN, VAE_UP, VAE_DOWN = 0, 1, 2, 3
 
 
 class VaeOp(C.Structure):
@@ -182,6 +182,9 @@ def lib() -> C.CDLL:
         _lib.vb_vae_decode.argtypes = [C.POINTER(VaeDesc), c_ptr, c_f32, c_i32, c_i32, c_ptr, c_ptr, c_i64, c_ptr]
         _lib.vb_vae_workspace_bytes.argtypes = [C.POINTER(VaeDesc), c_i32, c_i32]
         _lib.vb_vae_workspace_bytes.restype = c_i64
+        _lib.vb_vae_encode.argtypes = [C.POINTER(VaeDesc), c_ptr, c_i32, c_i32, c_ptr, c_ptr, c_i64, c_ptr]
+        _lib.vb_vae_encode_workspace_bytes.argtypes = [C.POINTER(VaeDesc), c_i32, c_i32]
+        _lib.vb_vae_encode_workspace_bytes.restype = c_i64
         if _lib.vb_sizeof(3) != C.sizeof(VaeDesc):
             raise VersbandError("vb_vae_desc ABI mismatch between versband.h and _lib.py")
         _lib.vb_dit_forward.argtypes = [C.POINTER(DitDesc), C.POINTER(DitCond), C.POINTER(DitIO), c_ptr, c_i64, c_ptr]

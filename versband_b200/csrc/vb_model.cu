@@ -385,6 +385,87 @@ extern "C" int vb_vae_decode(const vb_vae_desc* d, const float* z, float scale, 
   return vae_run(d, z, scale, B, T, mel, ws, ws_bytes, stream, nullptr);
 }
 
+// AutoencoderKL 1-D encoder (reference ldm/models/autoencoder1d.py:49-53,384-409: Encoder1D.forward then quant_conv):
+// mel fp32 [B, in_ch, T] -> moments fp32 [B, 2 * embed_dim, T / 2^n_down] (mean | logvar); the launch sequence of
+// versband_b200/vae.py:VAEEngine.encode_moments issued from C++. The SAME descriptor type describes the encoder:
+// zc = in_ch, in_w = encoder.conv_in, ops = resblocks / attention / VB_VAE_DOWN, no_* = encoder.norm_out,
+// out_w = encoder.conv_out (out_ch = 2 * z_channels), pq_w = quant_conv applied LAST (zq_c = 2 * embed_dim).
+static int vae_enc_run(const vb_vae_desc* d, const float* x, int B, int T, float* moments, void* ws, int64_t ws_bytes, void* stream,
+                       int64_t* need) {
+  if (!d || B <= 0 || T <= 0) return set_error(VB_ERR_INVALID, "vb_vae_encode: bad arguments");
+  if (d->n_ops < 0 || d->n_ops > VB_VAE_MAX_OPS || d->groups <= 0 || d->c0 % d->groups)
+    return set_error(VB_ERR_INVALID, "vb_vae_encode: bad descriptor");
+  const bool dry = need != nullptr;
+  uint8_t* base = static_cast<uint8_t*>(dry ? nullptr : ws);
+  int64_t slot = (int64_t)B * T * d->c0 * 4;
+  for (int i = 0; i < d->n_ops; ++i) {  // lengths only shrink: the largest activation is at full length
+    const int64_t b = (int64_t)B * T * d->ops[i].cout * 4;
+    if (b > slot) slot = b;
+  }
+  slot = (slot + 255) & ~int64_t(255);
+  const int xp = (d->zc + 7) / 8 * 8, ocp = (d->out_ch + 7) / 8 * 8;
+  Bump fix{base, 0, ws_bytes};
+  void* x_cl = fix.take((int64_t)B * T * xp * 2);
+  void* hz = fix.take((int64_t)B * T * ocp * 2);
+  float* mean = static_cast<float*>(fix.take((int64_t)B * d->groups * 4));
+  float* rstd = static_cast<float*>(fix.take((int64_t)B * d->groups * 4));
+  void* gn_scratch = fix.take((int64_t)B * d->groups * VB_GN_SPLIT * 2 * 8);
+  float* slots[2] = {static_cast<float*>(fix.take(slot)), static_cast<float*>(fix.take(slot))};
+  const int64_t fixed = (fix.off + 255) & ~int64_t(255);
+  VaeCtx c{d, B, dry, stream, Scratch{base ? base + fixed : nullptr, 0, 0}, mean, rstd, gn_scratch, 0};
+
+  c.run([&] { return vb_nct_to_ntc(x, 1.f, x_cl, B, d->zc, T, xp, 0, stream); });
+  int cur = 0, C = d->c0;
+  c.conv(x_cl, T, d->zc, xp, d->in_w, d->in_b, C, d->in_k, slots[cur], nullptr, nullptr, 0);  // encoder.conv_in
+  for (int i = 0; i < d->n_ops && !c.rc; ++i) {
+    const vb_vae_op& o = d->ops[i];
+    if (o.cin != C || o.cout % d->groups || o.cout % 8)
+      return set_error(VB_ERR_INVALID, "vb_vae_encode: layer %d expects %d input channels, got %d", i, o.cin, C);
+    c.sc.reset();
+    float* in = slots[cur];
+    float* out = slots[cur ^ 1];
+    if (o.kind == VB_VAE_RES) {
+      c.resblock(o, in, out, T);
+    } else if (o.kind == VB_VAE_ATTN) {
+      c.attn(o, in, out, T);
+    } else if (o.kind == VB_VAE_DOWN) {  // pad (0, 1) + conv k3 stride 2 (autoencoder1d.py:306-313) on row pairs [T/2, 2C]
+      if (T % 2 || (2 * C) % 64) return set_error(VB_ERR_INVALID, "vb_vae_encode: stride-2 downsample expects an even length and 2C %% 64 == 0");
+      void* hb = c.sc.take((int64_t)B * T * C * 2);
+      c.run([&] { return vb_ew(in, nullptr, 1.f, 1.f, VB_ACT_NONE, 0.f, nullptr, hb, (int64_t)B * T, C, 1, stream); });
+      T /= 2;
+      c.conv(hb, T, 2 * C, 2 * C, o.w1, o.b1, o.cout, 2, out, nullptr, nullptr, 0);
+    } else {
+      return set_error(VB_ERR_INVALID, "vb_vae_encode: unknown layer kind %d", o.kind);
+    }
+    C = o.cout;
+    cur ^= 1;
+  }
+  c.sc.reset();
+  void* a = c.gn(slots[cur], T, C, d->no_w, d->no_b, VB_ACT_SILU);
+  c.conv(a, T, C, C, d->out_w, d->out_b, d->out_ch, d->out_k, nullptr, nullptr, hz, ocp);       // encoder.conv_out
+  float* mom_cl = slots[cur ^ 1];
+  c.conv(hz, T, d->out_ch, ocp, d->pq_w, d->pq_b, d->zq_c, d->pq_k, mom_cl, nullptr, nullptr, 0);  // quant_conv
+  c.run([&] { return vb_ntc_to_nct(mom_cl, nullptr, d->zq_c, 0.f, 0.f, moments, B, d->zq_c, T, nullptr, 0, 0, stream); });
+  if (c.rc) return c.rc;
+  if (dry) *need = fixed + ((c.sc.peak + 255) & ~int64_t(255));
+  return VB_OK;
+}
+
+extern "C" int64_t vb_vae_encode_workspace_bytes(const vb_vae_desc* d, int B, int T) {
+  int64_t need = 0;
+  if (vae_enc_run(d, nullptr, B, T, nullptr, nullptr, 0, nullptr, &need)) return -1;
+  return need;
+}
+
+extern "C" int vb_vae_encode(const vb_vae_desc* d, const float* x, int B, int T, float* moments, void* ws, int64_t ws_bytes,
+                             void* stream) {
+  if (!x || !moments || !ws) return set_error(VB_ERR_INVALID, "vb_vae_encode: null pointer");
+  const int64_t need = vb_vae_encode_workspace_bytes(d, B, T);
+  if (need < 0) return VB_ERR_INVALID;
+  if (need > ws_bytes) return set_error(VB_ERR_INVALID, "vb_vae_encode: workspace too small (%lld bytes needed)", (long long)need);
+  return vae_enc_run(d, x, B, T, moments, ws, ws_bytes, stream, nullptr);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // One evaluation of the AccompBand DiT (reference TxtFlagLargeDiT.forward, vocal2music_moe.py:375-434, with the
 // step-invariant part precomputed: vb_dit_cond): the launch sequence of versband_b200/dit.py:DiTEngine.forward

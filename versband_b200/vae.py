@@ -144,7 +144,7 @@ class VAEEngine:
         """The decoder as a `vb_vae_desc` (include/versband.h) for vb_vae_decode."""
         if getattr(self, "_vae_desc", None) is not None:
             return self._vae_desc
-        from ._lib import VAE_ATTN, VAE_MAX_OPS, VAE_RES, VAE_UP, VaeDesc
+        from ._lib import VAE_MAX_OPS, VaeDesc
         w, k, P = self.w, self.k, ops._ptr
         d = "decoder."
         ds = VaeDesc()
@@ -159,25 +159,7 @@ class VAEEngine:
         assert len(layers) <= VAE_MAX_OPS
         ds.n_ops = len(layers)
         for o, (kind, n) in zip(ds.ops, layers):
-            if kind == "res":
-                o.kind, o.cout = VAE_RES, w[n + ".conv1.w"].shape[0]
-                o.cin = w[n + ".norm1.weight"].shape[0]
-                o.k1, o.k2 = k[n + ".conv1"], k[n + ".conv2"]
-                o.n1_w, o.n1_b, o.n2_w, o.n2_b = (P(w[n + s]) for s in (".norm1.weight", ".norm1.bias", ".norm2.weight", ".norm2.bias"))
-                o.w1, o.b1, o.w2, o.b2 = P(w[n + ".conv1.w"]), P(w[n + ".conv1.bias"]), P(w[n + ".conv2.w"]), P(w[n + ".conv2.bias"])
-                if (n + ".nin_shortcut.w") in w:
-                    o.ws, o.bs, o.ks = P(w[n + ".nin_shortcut.w"]), P(w[n + ".nin_shortcut.bias"]), k[n + ".nin_shortcut"]
-            elif kind == "attn":
-                o.kind = VAE_ATTN
-                o.cin = o.cout = w[n + ".norm.weight"].shape[0]
-                assert k[n + ".q"] == 1 and k[n + ".proj_out"] == 1
-                o.k1, o.k2 = 1, 1
-                o.n1_w, o.n1_b = P(w[n + ".norm.weight"]), P(w[n + ".norm.bias"])
-                o.w1, o.b1, o.w2, o.b2 = P(w[n + ".qkv.w"]), P(w[n + ".qkv.bias"]), P(w[n + ".proj_out.w"]), P(w[n + ".proj_out.bias"])
-            else:
-                o.kind, o.cout, o.k1 = VAE_UP, w[n + ".w"].shape[0], k[n]
-                o.cin = o.cout
-                o.w1, o.b1 = P(w[n + ".w"]), P(w[n + ".bias"])
+            self._fill_op(o, kind, n)
         self._vae_desc = ds
         return ds
 
@@ -239,9 +221,83 @@ class VAEEngine:
         return mel
 
     # ------------------------------------------------------------------ encoder (config 1)
+    def _fill_op(self, o, kind: str, n: str) -> None:
+        """One layer of a vb_vae_desc from the packed weights under prefix `n`."""
+        from ._lib import VAE_ATTN, VAE_DOWN, VAE_RES, VAE_UP
+        w, k, P = self.w, self.k, ops._ptr
+        if kind == "res":
+            o.kind, o.cout = VAE_RES, w[n + ".conv1.w"].shape[0]
+            o.cin = w[n + ".norm1.weight"].shape[0]
+            o.k1, o.k2 = k[n + ".conv1"], k[n + ".conv2"]
+            o.n1_w, o.n1_b, o.n2_w, o.n2_b = (P(w[n + s]) for s in (".norm1.weight", ".norm1.bias", ".norm2.weight", ".norm2.bias"))
+            o.w1, o.b1, o.w2, o.b2 = P(w[n + ".conv1.w"]), P(w[n + ".conv1.bias"]), P(w[n + ".conv2.w"]), P(w[n + ".conv2.bias"])
+            if (n + ".nin_shortcut.w") in w:
+                o.ws, o.bs, o.ks = P(w[n + ".nin_shortcut.w"]), P(w[n + ".nin_shortcut.bias"]), k[n + ".nin_shortcut"]
+        elif kind == "attn":
+            o.kind = VAE_ATTN
+            o.cin = o.cout = w[n + ".norm.weight"].shape[0]
+            assert k[n + ".q"] == 1 and k[n + ".proj_out"] == 1
+            o.k1, o.k2 = 1, 1
+            o.n1_w, o.n1_b = P(w[n + ".norm.weight"]), P(w[n + ".norm.bias"])
+            o.w1, o.b1, o.w2, o.b2 = P(w[n + ".qkv.w"]), P(w[n + ".qkv.bias"]), P(w[n + ".proj_out.w"]), P(w[n + ".proj_out.bias"])
+        else:
+            o.kind, o.cout, o.k1 = (VAE_UP if kind == "up" else VAE_DOWN), w[n + ".w"].shape[0], k[n]
+            o.cin = o.cout
+            o.w1, o.b1 = P(w[n + ".w"]), P(w[n + ".bias"])
+
+    def _desc_enc(self):
+        """The encoder (+ quant_conv) as a `vb_vae_desc` for vb_vae_encode (include/versband.h)."""
+        if getattr(self, "_vae_desc_enc", None) is not None:
+            return self._vae_desc_enc
+        from ._lib import VAE_MAX_OPS, VaeDesc
+        w, k, P = self.w, self.k, ops._ptr
+        e = "encoder."
+        ds = VaeDesc()
+        ds.zc, ds.c0 = self.dd["in_channels"], w[e + "conv_in.w"].shape[0]
+        ds.out_ch, ds.zq_c, ds.groups, ds.eps = w[e + "conv_out.w"].shape[0], w["quant_conv.w"].shape[0], self.G, 1e-6
+        ds.in_k, ds.out_k, ds.pq_k = k[e + "conv_in"], k[e + "conv_out"], k["quant_conv"]
+        ds.in_w, ds.in_b = P(w[e + "conv_in.w"]), P(w[e + "conv_in.bias"])
+        ds.no_w, ds.no_b = P(w[e + "norm_out.weight"]), P(w[e + "norm_out.bias"])
+        ds.out_w, ds.out_b = P(w[e + "conv_out.w"]), P(w[e + "conv_out.bias"])
+        ds.pq_w, ds.pq_b = P(w["quant_conv.w"]), P(w["quant_conv.bias"])
+        layers = []
+        for lvl in range(self.n_levels):
+            for blk in range(self.n_res):
+                layers.append(("res", f"{e}down.{lvl}.block.{blk}"))
+                if f"{e}down.{lvl}.attn.{blk}.norm.weight" in w:
+                    layers.append(("attn", f"{e}down.{lvl}.attn.{blk}"))
+            if lvl in self.down_layers:
+                layers.append(("down", f"{e}down.{lvl}.downsample.conv"))
+        layers += [("res", e + "mid.block_1"), ("attn", e + "mid.attn_1"), ("res", e + "mid.block_2")]
+        assert len(layers) <= VAE_MAX_OPS
+        ds.n_ops = len(layers)
+        for o, (kind, n) in zip(ds.ops, layers):
+            self._fill_op(o, kind, n)
+        self._vae_desc_enc = ds
+        return ds
+
     @torch.no_grad()
     def encode_moments(self, x: torch.Tensor) -> torch.Tensor:
-        """mel fp32 [B, in_ch, T] -> moments fp32 [B, 2*embed, T/2^n] (mean | logvar)."""
+        """mel fp32 [B, in_ch, T] -> moments fp32 [B, 2*embed, T/2^n] (mean | logvar): one call of the model-level C
+        entry point vb_vae_encode (`encode_moments_py` = the same launches from Python)."""
+        import ctypes as C
+        from . import _lib
+        B, Cin, T = x.shape
+        assert T % (2 ** len(self.down_layers)) == 0, "stride-2 downsample expects an even length"
+        x = x.to(self.dev, F32).contiguous()
+        ds = self._desc_enc()
+        need = int(_lib.lib().vb_vae_encode_workspace_bytes(C.byref(ds), B, T))
+        if need < 0:
+            _lib.check(-1, "vb_vae_encode_workspace_bytes")
+        ws = torch.empty(need, device=self.dev, dtype=torch.uint8)
+        mom = torch.empty(B, ds.zq_c, T // 2 ** len(self.down_layers), device=self.dev, dtype=F32)
+        _lib.check(_lib.lib().vb_vae_encode(C.byref(ds), ops._ptr(x), B, T, ops._ptr(mom), ops._ptr(ws), need, ops._stream()),
+                   "vb_vae_encode")
+        return mom
+
+    @torch.no_grad()
+    def encode_moments_py(self, x: torch.Tensor) -> torch.Tensor:
+        """The launch sequence of `encode_moments`, op by op from Python."""
         B, Cin, T = x.shape
         dev = self.dev
         e = "encoder."
