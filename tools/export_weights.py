@@ -43,7 +43,7 @@ def _tensors(obj) -> List[torch.Tensor]:
 def export(path: str, structs: List[Tuple[str, C.Structure]], weight_holders) -> Dict[str, int]:
     """structs: [(name, ctypes descriptor)], weight_holders: objects (dicts / lists) holding every tensor the
     descriptors point to."""
-    by_ptr = {t.data_ptr(): t for t in _tensors(weight_holders) if t.is_cuda}
+    by_ptr = {t.data_ptr(): t for t in _tensors(weight_holders)}
     data = bytearray()
     placed: Dict[int, int] = {}
     blobs = []
